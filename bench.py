@@ -1,0 +1,494 @@
+#!/usr/bin/env python
+"""bench.py -- stencil GLUP/s (f64 3D 7-point Jacobi sweep + fused ghost fill + update norm) on
+N B200s, through librnmf_b200.so (C ABI).  Prints ONE JSON line (rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--sub-iters S]
+  python bench.py --impl reference ...     # the reference's CPU algorithm (oracle port) on host cores
+
+step      = one solve_poisson-shaped call (poisson.rs:67-92): S = --sub-iters Jacobi sweeps, each
+            followed by the ghost fill (fused), plus the L1 norm of the last update (main.rs:68-69);
+            S defaults to 550 = n_sub_iter of examples/magnetostatics/magnetostatics.lua:12.
+value     = lattice updates (valid cells x sweeps, all ranks) / time, inputs resident in HBM.
+e2e       = the same call through rnmf_solve_poisson_host: pinned HOST frames in the reference's
+            dense layout in, result frame out; H2D + S sweeps + D2H inside the timed region.
+workloads = 3d7_768 (default; SURVEY 8d C5: 768^3 per GPU, weak scaling, mixed Dirichlet/Neumann),
+            3d7_512 (C3), 3d7_1024 (C4, strong), 2d5_8192 (C2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_LUP = 24          # read psi (8) + read rhs (8) + write psi' (8)   
+SEED_PSI, SEED_RHS = 0x5EED0001, 0x5EED0002
+
+MIXED_3D = ([("dirichlet", 0.0), ("neumann", 0.0), ("dirichlet", 0.25)],
+            [("dirichlet", 1.0), ("neumann", -0.5), ("neumann", 0.5)])
+DIRICHLET_2D = ([("dirichlet", 0.0), ("dirichlet", 0.0)], [("dirichlet", 1.0), ("dirichlet", 1.0)])
+
+WORKLOADS = {
+    # name: (per-GPU or global n, scaling, bc spec, description)
+    "3d7_768": dict(n=(768, 768, 768), scaling="weak", bc=MIXED_3D,
+                    desc="3D 7-point f64 Poisson Jacobi sweep, 768^3 cells per GPU (z-slabs), mixed Dirichlet/Neumann ghost fill"),
+    "3d7_512": dict(n=(512, 512, 512), scaling="weak", bc=MIXED_3D,
+                    desc="3D 7-point f64 Poisson Jacobi sweep, 512^3 per GPU, mixed Dirichlet/Neumann ghost fill"),
+    "3d7_1024": dict(n=(1024, 1024, 1024), scaling="strong", bc=MIXED_3D,
+                     desc="3D 7-point f64 Poisson Jacobi sweep, 1024^3 global, z-slab decomposed"),
+    "2d5_8192": dict(n=(8192, 8192), scaling="weak", bc=DIRICHLET_2D,
+                     desc="2D 5-point f64 Poisson Jacobi sweep, 8192^2 per GPU (y-slabs), Dirichlet"),
+}
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="rnmf_b200", choices=["rnmf_b200", "reference"])
+    p.add_argument("--workload", default="3d7_768", choices=sorted(WORKLOADS))
+    p.add_argument("--sub-iters", type=int, default=550)
+    p.add_argument("--e2e-steps", type=int, default=2, help="timed end-to-end calls (after 1 warm-up)")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-others", action="store_true", help="skip the short extra runs of the other configs")
+    p.add_argument("--variant", default=None, help="sweep kernel variant (measurement knob)")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[3 + i].lower().startswith("active")})
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples), "power_w_max": max(pw) if pw else None}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(workload: str):
+    """dram bytes per sweep launch from the committed ncu capture, if any (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle's reference-faithful Gauss-Seidel sweep (poisson.rs:80-89 loop order)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_geom(workload: str):
+    """Bounded sample of the workload for the CPU: same x/y extents (so the reference's
+    stride-G0 column walk sees the same strides), a thin slab in the slowest direction."""
+    w = WORKLOADS[workload]
+    n = list(w["n"])
+    n[-1] = 32 if len(n) == 3 else 512
+    return n
+
+
+def cpu_reference_run(workload: str, sweeps: int, reps: int, jacobi_omp: bool = False):
+    """returns (seconds per rep list, LUPs per rep)"""
+    import numpy as np
+    from oracle import oracle as ora
+    w = WORKLOADS[workload]
+    n = cpu_sample_geom(workload)
+    g = ora.geom(n, hi=[float(v) for v in n])
+    bc = ora.bcs(g.dim, [w["bc"]])
+    nv = int(np.prod(n))
+    psi, rhs = ora.zeros(g), ora.zeros(g)
+    ora.valid_view(g, psi)[0] = ora.splitmix_field(nv, SEED_PSI).reshape(tuple(reversed(n)))
+    ora.valid_view(g, rhs)[0] = ora.splitmix_field(nv, SEED_RHS).reshape(tuple(reversed(n)))
+    ora.fill_bc(g, psi, bc)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        if jacobi_omp:
+            ora.jacobi(g, psi, rhs, bc, sweeps, omp=True)
+        else:
+            ora.gs(g, psi, rhs, bc, sweeps)
+        times.append(time.perf_counter() - t0)
+    return times, nv * sweeps
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU algorithm for the path.  The Rust crate cannot be
+    built in this image (no cargo/rustc), so this is the oracle port (oracle/rnmf_oracle.c):
+    lexicographic Gauss-Seidel in the reference's loop order, 1 thread (the reference is
+    single-threaded; rayon is declared but unused)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    sweeps = 1
+    times, lups = cpu_reference_run(args.workload, sweeps, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = lups * len(timed) / total / 1e9
+    n = cpu_sample_geom(args.workload)
+    sample = (f"each step = {sweeps} reference-order Gauss-Seidel sweep (poisson.rs:80-89 loop order) over a "
+              f"{'x'.join(map(str, n))} slab of the workload (same x/y extents, {n[-1]} slices), 1 thread")
+    line = {
+        "impl": "reference", "metric": "stencil GLUP/s (f64 3D 7-pt)" if len(n) == 3 else "stencil GLUP/s (f64 2D 5-pt)",
+        "value": value, "unit": "GLUP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": w["scaling"],
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (splitmix64 field, same seeds as the GPU arm)",
+        "config": {"workload": args.workload, "desc": w["desc"], "update_order": "lexicographic Gauss-Seidel (reference)",
+                   "sub_iters": sweeps},
+        "cpu_baseline": {"value": value, "unit": "GLUP/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host": {"nproc": os.cpu_count(), "cpu": _cpu_model()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def make_bcs(R, spec):
+    mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
+    return R.BCs([R.ComponentBCs([mk[k](v) for k, v in spec[0]], [mk[k](v) for k, v in spec[1]])])
+
+
+def global_shape(workload: str, nranks: int):
+    w = WORKLOADS[workload]
+    n = list(w["n"])
+    if w["scaling"] == "weak":
+        n[-1] *= nranks
+    return n
+
+
+def timed_steps(ctx, psi, rhs, coef, sub_iters, steps, barrier):
+    """K steps, device-timed on the context's stream; returns (ms, last norm)."""
+    from rnmf_b200 import poisson
+    barrier()
+    ctx.sync()
+    ctx.timer_begin()
+    l1 = 0.0
+    for _ in range(steps):
+        l1 = poisson.jacobi_sweeps(psi, rhs, sub_iters, want_norm=True, coef=coef)
+    ms = ctx.timer_end()
+    ctx.sync()
+    barrier()
+    return ms, l1
+
+
+def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, reduce_max):
+    from rnmf_b200 import poisson
+    w = WORKLOADS[workload]
+    n = global_shape(workload, nranks)
+    dim = len(n)
+    mesh = R.CartesianMesh.new([0.0] * dim, [float(v) for v in n], n)       # dx = 1
+    bc = make_bcs(R, w["bc"])
+    psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=nranks > 1)
+    rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=nranks > 1)
+    psi.fill_synthetic(SEED_PSI)
+    rhs.fill_synthetic(SEED_RHS)
+    psi.fill_bc()
+    coef = poisson.poisson_coefs(dim, mesh.dx)
+    for _ in range(warmup):
+        poisson.jacobi_sweeps(psi, rhs, sub_iters, want_norm=True, coef=coef)
+    launches0 = ctx.kernel_launches
+    ms, l1 = timed_steps(ctx, psi, rhs, coef, sub_iters, steps, barrier)
+    launches = ctx.kernel_launches - launches0
+    ms = reduce_max(ms)
+    cells = 1
+    for v in n:
+        cells *= v
+    lups = cells * sub_iters * steps
+    checksum = psi.ctx.allreduce_sum(psi.abs_sum())
+    res = dict(n_global=n, ms=ms, ms_per_step=ms / steps, glups=lups / (ms * 1e-3) / 1e9, launches=launches,
+               l1_last=l1, abs_sum=checksum, local_cells=int(psi.n_local[0] * psi.n_local[1] * (psi.n_local[2] if dim == 3 else 1)))
+    psi.close()
+    rhs.close()
+    return res
+
+
+def run_e2e(R, ctx, workload, sub_iters, steps):
+    """The reference-facing call with HOST frames (pinned), single rank."""
+    import ctypes as C
+    import numpy as np
+    from rnmf_b200 import _capi
+    from rnmf_b200.dataframe import _faces_array
+    w = WORKLOADS[workload]
+    n = list(w["n"])
+    dim = len(n)
+    L = _capi.lib()
+    G = [v + 2 for v in n]
+    count = 1
+    for v in G:
+        count *= v
+    nbytes = count * 8
+    bufs = []
+    for _ in range(3):
+        p = C.c_void_p()
+        _capi.check(L.rnmf_host_alloc(nbytes, C.byref(p)))
+        bufs.append(p)
+    try:
+        arrs = [np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(count,)) for p in bufs]
+        psi_h, rhs_h, out_h = arrs
+        # host frames in the reference's dense layout: deterministic, cheap to generate
+        shape = tuple(reversed(G))
+        rng = np.random.default_rng(7)
+        blk = rng.standard_normal(shape[-1] * shape[-2])
+        psi_h.reshape(-1, shape[-1] * shape[-2])[:] = blk
+        rhs_h.reshape(-1, shape[-1] * shape[-2])[:] = blk[::-1]
+        faces = _faces_array(make_bcs(R, w["bc"]), dim, 1)
+        nn = (C.c_int64 * 3)(*n, *([1] * (3 - dim)))
+        lo = (C.c_double * 3)(0.0, 0.0, 0.0)
+        dx = (C.c_double * 3)(1.0, 1.0, 1.0)
+        l1 = C.c_double()
+
+        def call():
+            _capi.check(L.rnmf_solve_poisson_host(ctx._h, dim, nn, lo, dx, 1, faces, bufs[0], bufs[1], sub_iters, 0,
+                                                  bufs[2], C.byref(l1)))
+        call()                                   # warm-up (allocates the cached device frames)
+        ctx.sync()
+        t0 = time.perf_counter()
+        ctx.timer_begin()
+        for _ in range(steps):
+            call()
+        ms_dev = ctx.timer_end()
+        ctx.sync()
+        wall = time.perf_counter() - t0
+        cells = 1
+        for v in n:
+            cells *= v
+        secs = max(wall, ms_dev * 1e-3)
+        return {"value": cells * sub_iters * steps / secs / 1e9, "unit": "GLUP/s",
+                "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes + 8,
+                "ms_per_step": 1e3 * secs / steps, "steps": steps,
+                "call": "rnmf_solve_poisson_host: pinned host psi+rhs (dense reference layout) -> H2D -> "
+                        f"{sub_iters} sweeps(+fill_bc) + L1 norm -> D2H psi"}
+    finally:
+        for p in bufs:
+            L.rnmf_host_free(p)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; rnmf_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    import rnmf_b200 as R
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx = R.Context.from_torch_distributed()
+
+        def barrier():
+            dist.barrier()
+            torch.cuda.synchronize()
+
+        def reduce_max(x):
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def reduce_sum(x):
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+    else:
+        ctx = R.Context(local)
+
+        def barrier():
+            torch.cuda.synchronize()
+
+        def reduce_max(x):
+            return x
+
+        def reduce_sum(x):
+            return x
+
+    if args.variant is not None:
+        ctx.set_option("sweep_variant", args.variant)
+
+    w = WORKLOADS[args.workload]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    main_res = run_config(R, ctx, args.workload, world, args.sub_iters, args.steps, args.warmup, barrier, reduce_max)
+    if rank == 0:
+        sampler.stop()
+    launches_total = int(reduce_sum(float(main_res["launches"])))
+
+    peak, peak_src = measured_peak()
+    sweep_ms = main_res["ms"] / (args.steps * args.sub_iters)            # average sweep-kernel launch duration (upper bound)
+    achieved = BYTES_PER_LUP * main_res["local_cells"] / (sweep_ms * 1e-3) / 1e9     # GB/s per GPU (the slowest rank's clock)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(args.workload), "kernel": "jacobi sweep (fused ghost fill)",
+                "algorithmic_bytes_per_launch": BYTES_PER_LUP * main_res["local_cells"],
+                "avg_launch_ms": sweep_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
+
+    others = {}
+    if rank == 0 and world == 1 and not args.no_others:
+        for name, sub, st in (("3d7_512", 100, 3), ("2d5_8192", 100, 3)):
+            if name == args.workload:
+                continue
+            try:
+                r = run_config(R, ctx, name, 1, sub, st, 1, barrier, reduce_max)
+                others[name] = {"glups": r["glups"], "ms_per_sweep": r["ms"] / (sub * st),
+                                "hbm_frac": BYTES_PER_LUP * r["local_cells"] / (r["ms"] / (sub * st) * 1e-3) / 1e9 / peak}
+            except Exception as e:       # reported, never hidden
+                others[name] = {"error": str(e)}
+
+    e2e = None
+    if rank == 0 and not args.no_e2e:
+        if world == 1:
+            e2e = run_e2e(R, ctx, args.workload, args.sub_iters, max(1, args.e2e_steps))
+    if world > 1:
+        # multi-GPU end-to-end: every rank moves its own slab; measured on rank-local calls and reduced
+        if not args.no_e2e and w["scaling"] == "weak":
+            wl = args.workload
+            barrier()
+            local_e2e = run_e2e(R, ctx_single(R, local), wl, args.sub_iters, max(1, args.e2e_steps))
+            barrier()
+            if local_e2e is not None:
+                slow_ms = reduce_max(local_e2e["ms_per_step"])
+                cells = 1
+                for v in WORKLOADS[wl]["n"]:
+                    cells *= v
+                e2e = dict(local_e2e)
+                e2e["ms_per_step"] = slow_ms
+                e2e["value"] = world * cells * args.sub_iters / (slow_ms * 1e-3) / 1e9
+                e2e["h2d_bytes_per_step"] *= world
+                e2e["d2h_bytes_per_step"] *= world
+                e2e["call"] += " (each rank solves its own 768^3 host frame concurrently: replicas of the host-buffer call; the halo-coupled device path is `value`)"
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, lups = cpu_reference_run(args.workload, 1, 12)
+        best = lups * len(times[2:]) / sum(times[2:]) / 1e9
+        n = cpu_sample_geom(args.workload)
+        cpu_baseline = {"value": best, "unit": "GLUP/s", "cores": 1, "kind": "port",
+                        "sample": f"10 timed (2 warm-up) reference-order Gauss-Seidel sweeps (poisson.rs:80-89 loop order, oracle port) "
+                                  f"over a {'x'.join(map(str, n))} slab of the workload, 1 thread; the Rust reference is single-threaded",
+                        "host": {"nproc": os.cpu_count(), "cpu": _cpu_model()}}
+        try:
+            from oracle import oracle as ora
+            t2, l2 = cpu_reference_run(args.workload, 1, 6, jacobi_omp=True)
+            cpu_baseline["jacobi_all_cores_not_the_reference"] = {"value": l2 * len(t2[2:]) / sum(t2[2:]) / 1e9, "unit": "GLUP/s",
+                                                                  "cores": ora.lib().ora_num_threads()}
+        except Exception as e:
+            cpu_baseline["jacobi_all_cores_not_the_reference"] = {"error": str(e)}
+
+    if rank == 0:
+        dim = len(w["n"])
+        line = {
+            "metric": f"stencil GLUP/s (f64 {'3D 7-pt' if dim == 3 else '2D 5-pt'})",
+            "value": main_res["glups"], "unit": "GLUP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (splitmix64 field generated on device; random-free, deterministic)",
+            "config": {"workload": args.workload, "desc": w["desc"], "n_global": main_res["n_global"],
+                       "sub_iters": args.sub_iters, "step": "solve_poisson-shaped call: sub_iters Jacobi sweeps + fused fill_bc each + L1 update norm",
+                       "n_ghost": 1, "bytes_per_lup": BYTES_PER_LUP,
+                       "l2": "three 3.65 GB frames per GPU >> 126 MB L2: no flush needed" if args.workload == "3d7_768" else "frames >> L2",
+                       "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+                       "sweep_variant": args.variant or os.environ.get("RNMF_SWEEP_VARIANT", "auto")},
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": launches_total,
+            "clocks": sampler.summary(),
+            "checks": {"l1_update_last": main_res["l1_last"], "abs_sum_psi": main_res["abs_sum"]},
+            "other_configs": others,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+_single = {}
+
+
+def ctx_single(R, local):
+    if local not in _single:
+        _single[local] = R.Context(local)
+    return _single[local]
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,992 @@
+// capi.cu -- the C ABI of librnmf_b200 (include/rnmf_b200.h): contexts, device-resident data
+// frames, and the host-side sequencing of the sweep / ghost-fill / norm kernels, including the
+// slab halo exchange (NCCL, loaded with dlopen so single-GPU users never need it).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void rnmf_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* rnmf_last_error(void) { return g_err; }
+extern "C" int32_t rnmf_abi_version(void) { return RNMF_ABI_VERSION; }
+extern "C" const char* rnmf_build_info(void)
+{
+    return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
+           "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi2d_ymarch{128,256},"
+           "fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+}
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen (types from the system header; the library is whichever libnccl.so.2 the
+// process already has -- torch's bundled one under Python -- or the system one)
+// ------------------------------------------------------------------------------------------
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.handle) return RNMF_OK;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for (const char* nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        rnmf_set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+        return RNMF_ERR_NCCL;
+    }
+#define LOAD(field, sym)                                                          \
+    *(void**)(&g_nccl.field) = dlsym(h, sym);                                     \
+    if (!g_nccl.field) { rnmf_set_error("libnccl lacks %s", sym); return RNMF_ERR_NCCL; }
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(Send, "ncclSend");
+    LOAD(Recv, "ncclRecv");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(GroupStart, "ncclGroupStart");
+    LOAD(GroupEnd, "ncclGroupEnd");
+    LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    g_nccl.handle = h;
+    return RNMF_OK;
+}
+}  // namespace
+
+#define RNMF_NCCL_TRY(expr)                                                                  \
+    do {                                                                                     \
+        ncclResult_t _r = (expr);                                                            \
+        if (_r != ncclSuccess) {                                                             \
+            rnmf_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(_r)); \
+            return RNMF_ERR_NCCL;                                                            \
+        }                                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------
+struct rnmf_frame;
+
+struct rnmf_ctx {
+    int device = 0;
+    int rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;        // compute
+    cudaStream_t stream_halo = nullptr;   // halo exchange (high priority)
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_boundary = nullptr, ev_halo = nullptr;
+    long long launches = 0;
+    double* d_scalar = nullptr;           // device scalars (norms)
+    double* h_scalar = nullptr;           // pinned
+    double* d_partials = nullptr;
+    long long partial_cap = 0;
+    int sweep_variant = 0;
+    int overlap_halo = 1;
+    ncclComm_t comm = nullptr;
+    rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
+    rnmf_frame* hp_rhs = nullptr;
+};
+
+struct rnmf_frame {
+    rnmf_ctx* ctx = nullptr;
+    FrameGeom g;
+    double* d = nullptr;                  // current buffer
+    double* d2 = nullptr;                 // ping-pong partner (lazily allocated)
+    int distributed = 0;
+    int bc_set = 0;
+    int has_reflect = 0;
+    std::vector<rnmf_bc_face> raw;        // as given (global BCs), prescribed pointers cleared
+    std::vector<FaceSet> faces;           // per component, HALO applied
+    std::vector<double*> prescribed_dev;  // per raw face (nullptr if not Prescribed)
+    std::vector<long long> prescribed_n;
+};
+
+namespace {
+
+constexpr long long kTailPad = 64;   // doubles; lets edge threads read a little past the last row
+
+int ensure_partials(rnmf_ctx* c, long long n)
+{
+    if (n <= c->partial_cap) return RNMF_OK;
+    if (c->d_partials) RNMF_CUDA_TRY(cudaFree(c->d_partials));
+    c->d_partials = nullptr;
+    c->partial_cap = 0;
+    long long cap = n < 4096 ? 4096 : n;
+    RNMF_CUDA_TRY(cudaMalloc(&c->d_partials, (size_t)cap * sizeof(double)));
+    c->partial_cap = cap;
+    return RNMF_OK;
+}
+
+int bind(rnmf_ctx* c)
+{
+    RNMF_CUDA_TRY(cudaSetDevice(c->device));
+    return RNMF_OK;
+}
+
+int alloc_buffer(const FrameGeom& g, double** out, cudaStream_t s)
+{
+    const size_t bytes = (size_t)(g.total + kTailPad) * sizeof(double);
+    RNMF_CUDA_TRY(cudaMalloc(out, bytes));
+    RNMF_CUDA_TRY(cudaMemsetAsync(*out, 0, bytes, s));   // new_from zero-initialises (dataframe.rs:155)
+    return RNMF_OK;
+}
+
+void make_geom(FrameGeom& g, int dim, const int64_t* n, const double* lo, const double* dx, int ng, int ncomp)
+{
+    memset(&g, 0, sizeof(g));
+    g.dim = dim; g.ng = ng; g.ncomp = ncomp;
+    g.kg = dim == 3 ? ng : 0;
+    for (int d = 0; d < 3; ++d) {
+        g.n[d] = d < dim ? n[d] : 1;
+        g.G[d] = d < dim ? n[d] + 2 * ng : 1;
+        g.dx[d] = d < dim ? dx[d] : 1.0;
+        g.lo[d] = d < dim ? lo[d] : 0.0;
+        g.nglob[d] = g.n[d];
+        g.off[d] = 0;
+    }
+    g.xoff = RNMF_ROW_ALIGN - ng;
+    g.pitch = ((RNMF_ROW_ALIGN + g.n[0] + ng + RNMF_ROW_ALIGN - 1) / RNMF_ROW_ALIGN) * RNMF_ROW_ALIGN;
+    g.plane = g.pitch * g.G[1];
+    g.comp = g.plane * g.G[2];
+    g.total = g.comp * ncomp;
+}
+
+bool same_shape(const FrameGeom& a, const FrameGeom& b)
+{
+    return a.dim == b.dim && a.ng == b.ng && a.ncomp == b.ncomp && a.n[0] == b.n[0] && a.n[1] == b.n[1] &&
+           a.n[2] == b.n[2];
+}
+
+// FaceBC for one raw face (HALO / Prescribed / Reflect -> mode 0 here)
+FaceBC make_face(const rnmf_bc_face& f, int side, double dxd)
+{
+    FaceBC b;
+    b.mode = 0; b.value = f.value; b.s1 = 0.0;
+    if (f.kind == RNMF_BC_DIRICHLET) {
+        b.mode = 1;
+        b.s1 = 2.0 * f.value;                               // dataframe.rs:328,344
+    } else if (f.kind == RNMF_BC_NEUMANN) {
+        b.mode = side == 0 ? 2 : 3;
+        b.s1 = f.value * (2.0 * 1.0 - 1.0) * dxd;           // :293-294 (g=1), :311-312 (g=0)
+    }
+    return b;
+}
+
+int slow_dim(const FrameGeom& g) { return g.dim - 1; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static int ctx_common_init(rnmf_ctx* c)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        rnmf_set_error("no CUDA device available (%s): librnmf_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return RNMF_ERR_CUDA;
+    }
+    RNMF_REQUIRE(c->device >= 0 && c->device < count, "device %d out of range (count %d)", c->device, count);
+    RNMF_CUDA_TRY(cudaSetDevice(c->device));
+    int lo_p = 0, hi_p = 0;
+    RNMF_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    RNMF_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, lo_p));
+    RNMF_CUDA_TRY(cudaStreamCreateWithPriority(&c->stream_halo, cudaStreamNonBlocking, hi_p));
+    RNMF_CUDA_TRY(cudaEventCreate(&c->ev_t0));
+    RNMF_CUDA_TRY(cudaEventCreate(&c->ev_t1));
+    RNMF_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_boundary, cudaEventDisableTiming));
+    RNMF_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    RNMF_CUDA_TRY(cudaMalloc(&c->d_scalar, 8 * sizeof(double)));
+    RNMF_CUDA_TRY(cudaMallocHost(&c->h_scalar, 8 * sizeof(double)));
+    const char* v = getenv("RNMF_SWEEP_VARIANT");
+    if (v) c->sweep_variant = atoi(v);
+    const char* o = getenv("RNMF_HALO_OVERLAP");
+    if (o) c->overlap_halo = atoi(o);
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_ctx_create(int32_t device, rnmf_ctx** out)
+{
+    RNMF_REQUIRE(out, "out is null");
+    rnmf_ctx* c = new rnmf_ctx();
+    c->device = device;
+    int rc = ctx_common_init(c);
+    if (rc) { delete c; return rc; }
+    *out = c;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_nccl_unique_id(void* id128)
+{
+    RNMF_REQUIRE(id128, "id128 is null");
+    int rc = nccl_load();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    RNMF_NCCL_TRY(g_nccl.GetUniqueId((ncclUniqueId*)id128));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_ctx_create_dist(int32_t device, int32_t rank, int32_t nranks, const void* nccl_id, rnmf_ctx** out)
+{
+    RNMF_REQUIRE(out && nccl_id, "null argument");
+    RNMF_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / nranks %d", rank, nranks);
+    rnmf_ctx* c = new rnmf_ctx();
+    c->device = device; c->rank = rank; c->nranks = nranks;
+    int rc = ctx_common_init(c);
+    if (rc) { delete c; return rc; }
+    if (nranks > 1) {
+        rc = nccl_load();
+        if (rc) { delete c; return rc; }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            rnmf_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+            delete c;
+            return RNMF_ERR_NCCL;
+        }
+    }
+    *out = c;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_ctx_destroy(rnmf_ctx* c)
+{
+    if (!c) return RNMF_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    if (c->hp_psi) rnmf_frame_destroy(c->hp_psi);
+    if (c->hp_rhs) rnmf_frame_destroy(c->hp_rhs);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_scalar) cudaFree(c->d_scalar);
+    if (c->h_scalar) cudaFreeHost(c->h_scalar);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream_halo) cudaStreamDestroy(c->stream_halo);
+    delete c;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_sync(rnmf_ctx* c)
+{
+    RNMF_REQUIRE(c, "ctx is null");
+    if (bind(c)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream_halo));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_ctx_stream(rnmf_ctx* c, void** s)
+{
+    RNMF_REQUIRE(c && s, "null argument");
+    *s = (void*)c->stream;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_ctx_rank(rnmf_ctx* c, int32_t* rank, int32_t* nranks)
+{
+    RNMF_REQUIRE(c, "ctx is null");
+    if (rank) *rank = c->rank;
+    if (nranks) *nranks = c->nranks;
+    return RNMF_OK;
+}
+
+extern "C" int64_t rnmf_kernel_launches(rnmf_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int32_t rnmf_timer_begin(rnmf_ctx* c)
+{
+    RNMF_REQUIRE(c, "ctx is null");
+    if (bind(c)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaEventRecord(c->ev_t0, c->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_timer_end(rnmf_ctx* c, double* ms)
+{
+    RNMF_REQUIRE(c && ms, "null argument");
+    if (bind(c)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaEventRecord(c->ev_t1, c->stream));
+    RNMF_CUDA_TRY(cudaEventSynchronize(c->ev_t1));
+    float f = 0.f;
+    RNMF_CUDA_TRY(cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+    *ms = (double)f;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* value)
+{
+    RNMF_REQUIRE(c && key && value, "null argument");
+    if (!strcmp(key, "sweep_variant")) { c->sweep_variant = !strcmp(value, "auto") ? 0 : atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "halo_overlap")) { c->overlap_halo = atoi(value); return RNMF_OK; }
+    rnmf_set_error("unknown option '%s'", key);
+    return RNMF_ERR_INVALID;
+}
+
+// Domain::new_rectangular (cartesian2d/mod.rs:64-73,109-116): floor(n/P) cells per block, the
+// last block takes the remainder.
+extern "C" int32_t rnmf_slab_partition(int64_t n, int32_t nranks, int32_t rank, int64_t* start, int64_t* count)
+{
+    RNMF_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && n >= 0, "bad partition arguments");
+    const int64_t per = n / nranks;
+    const int64_t rem = n % nranks;
+    if (start) *start = per * rank;
+    if (count) *count = per + (rank == nranks - 1 ? rem : 0);
+    return RNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// frames
+// ------------------------------------------------------------------------------------------
+static int frame_create_impl(rnmf_ctx* c, int dim, const int64_t* n_local, const int64_t* n_global,
+                             const int64_t* offset, const double* lo, const double* dx, int ng, int ncomp,
+                             int distributed, rnmf_frame** out)
+{
+    RNMF_REQUIRE(c && n_local && lo && dx && out, "null argument");
+    RNMF_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3 (got %d)", dim);
+    RNMF_REQUIRE(ng >= 1 && ng <= RNMF_ROW_ALIGN, "n_ghost must be in [1,16] (got %d)", ng);
+    RNMF_REQUIRE(ncomp >= 1, "n_comp must be >= 1");
+    for (int d = 0; d < dim; ++d) RNMF_REQUIRE(n_local[d] >= 1, "n[%d] must be >= 1", d);
+    if (bind(c)) return RNMF_ERR_CUDA;
+    rnmf_frame* f = new rnmf_frame();
+    f->ctx = c;
+    make_geom(f->g, dim, n_local, lo, dx, ng, ncomp);
+    for (int d = 0; d < dim; ++d) {
+        f->g.nglob[d] = n_global[d];
+        f->g.off[d] = offset[d];
+    }
+    f->distributed = distributed;
+    int rc = alloc_buffer(f->g, &f->d, c->stream);
+    if (rc) { delete f; return rc; }
+    f->faces.assign(ncomp, FaceSet());
+    for (auto& fs : f->faces)
+        for (int i = 0; i < 6; ++i) { fs.f[i].mode = 0; fs.f[i].value = 0.0; fs.f[i].s1 = 0.0; }
+    *out = f;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_create(rnmf_ctx* c, int32_t dim, const int64_t* n, const double* lo, const double* dx,
+                                     int32_t ng, int32_t ncomp, rnmf_frame** out)
+{
+    RNMF_REQUIRE(n, "n is null");
+    const int64_t zero[3] = { 0, 0, 0 };
+    return frame_create_impl(c, dim, n, n, zero, lo, dx, ng, ncomp, 0, out);
+}
+
+extern "C" int32_t rnmf_frame_create_slab(rnmf_ctx* c, int32_t dim, const int64_t* ng_n, const double* lo,
+                                          const double* dx, int32_t ng, int32_t ncomp, rnmf_frame** out)
+{
+    RNMF_REQUIRE(c && ng_n && lo && dx, "null argument");
+    RNMF_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+    const int D = dim - 1;
+    RNMF_REQUIRE(ng_n[D] >= c->nranks, "global n[%d]=%lld smaller than nranks=%d", D, (long long)ng_n[D], c->nranks);
+    int64_t start = 0, count = 0;
+    rnmf_slab_partition(ng_n[D], c->nranks, c->rank, &start, &count);
+    int64_t nl[3] = { 1, 1, 1 }, off[3] = { 0, 0, 0 };
+    double lo_l[3] = { 0, 0, 0 };
+    for (int d = 0; d < dim; ++d) { nl[d] = ng_n[d]; lo_l[d] = lo[d]; }
+    nl[D] = count;
+    off[D] = start;
+    lo_l[D] = lo[D] + (double)start * dx[D];
+    RNMF_REQUIRE(count >= ng, "slab of %lld cells thinner than n_ghost=%d", (long long)count, ng);
+    return frame_create_impl(c, dim, nl, ng_n, off, lo_l, dx, ng, ncomp, c->nranks > 1 ? 1 : 0, out);
+}
+
+extern "C" int32_t rnmf_frame_destroy(rnmf_frame* f)
+{
+    if (!f) return RNMF_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaStreamSynchronize(f->ctx->stream_halo);
+    if (f->d) cudaFree(f->d);
+    if (f->d2) cudaFree(f->d2);
+    for (double* p : f->prescribed_dev) if (p) cudaFree(p);
+    delete f;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_info_get(const rnmf_frame* f, rnmf_frame_info* o)
+{
+    RNMF_REQUIRE(f && o, "null argument");
+    memset(o, 0, sizeof(*o));
+    o->dim = f->g.dim; o->n_ghost = f->g.ng; o->n_comp = f->g.ncomp; o->distributed = f->distributed;
+    for (int d = 0; d < 3; ++d) {
+        o->n[d] = f->g.n[d]; o->n_global[d] = f->g.nglob[d]; o->offset[d] = f->g.off[d];
+        o->dx[d] = f->g.dx[d]; o->lo[d] = f->g.lo[d];
+    }
+    o->pitch = f->g.pitch; o->x_offset = f->g.xoff;
+    o->n_rows = f->g.G[1] * f->g.G[2] * f->g.ncomp;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_set_bc(rnmf_frame* f, const rnmf_bc_face* faces, int32_t n_faces)
+{
+    RNMF_REQUIRE(f && faces, "null argument");
+    const FrameGeom& g = f->g;
+    RNMF_REQUIRE(n_faces == g.ncomp * g.dim * 2, "expected %d faces (n_comp*dim*2), got %d", g.ncomp * g.dim * 2, n_faces);
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    for (int i = 0; i < n_faces; ++i)
+        RNMF_REQUIRE(faces[i].kind >= RNMF_BC_DIRICHLET && faces[i].kind <= RNMF_BC_HALO, "face %d: unknown kind %d", i, faces[i].kind);
+    for (double* p : f->prescribed_dev) if (p) RNMF_CUDA_TRY(cudaFree(p));
+    f->prescribed_dev.assign(n_faces, nullptr);
+    f->prescribed_n.assign(n_faces, 0);
+    f->raw.assign(faces, faces + n_faces);
+    f->has_reflect = 0;
+    const int D = slow_dim(g);
+    for (int c = 0; c < g.ncomp; ++c)
+        for (int d = 0; d < g.dim; ++d)
+            for (int side = 0; side < 2; ++side) {
+                const int idx = (c * g.dim + d) * 2 + side;
+                rnmf_bc_face& r = f->raw[idx];
+                // internal faces of a slab are halos whatever the global BC says
+                if (f->distributed && d == D) {
+                    const bool internal = side == 0 ? f->ctx->rank > 0 : f->ctx->rank < f->ctx->nranks - 1;
+                    if (internal) r.kind = RNMF_BC_HALO;
+                }
+                if (r.kind == RNMF_BC_REFLECT) f->has_reflect = 1;
+                if (r.kind == RNMF_BC_PRESCRIBED && r.n_prescribed > 0) {
+                    RNMF_REQUIRE(r.prescribed, "face %d: Prescribed with null values", idx);
+                    RNMF_CUDA_TRY(cudaMalloc(&f->prescribed_dev[idx], (size_t)r.n_prescribed * sizeof(double)));
+                    RNMF_CUDA_TRY(cudaMemcpyAsync(f->prescribed_dev[idx], r.prescribed, (size_t)r.n_prescribed * sizeof(double),
+                                                  cudaMemcpyHostToDevice, f->ctx->stream));
+                    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));   // caller may free its Vec right away
+                    f->prescribed_n[idx] = r.n_prescribed;
+                }
+                r.prescribed = nullptr;
+                f->faces[c].f[d * 2 + side] = make_face(r, side, g.dx[d]);
+            }
+    f->bc_set = 1;
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_upload(rnmf_frame* f, const double* host)
+{
+    RNMF_REQUIRE(f && host, "null argument");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    const FrameGeom& g = f->g;
+    const size_t rows = (size_t)(g.G[1] * g.G[2] * g.ncomp);
+    RNMF_CUDA_TRY(cudaMemcpy2DAsync(f->d + g.xoff, (size_t)g.pitch * 8, host, (size_t)g.G[0] * 8, (size_t)g.G[0] * 8, rows,
+                                    cudaMemcpyHostToDevice, f->ctx->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_download(rnmf_frame* f, double* host)
+{
+    RNMF_REQUIRE(f && host, "null argument");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    const FrameGeom& g = f->g;
+    const size_t rows = (size_t)(g.G[1] * g.G[2] * g.ncomp);
+    RNMF_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)g.G[0] * 8, f->d + g.xoff, (size_t)g.pitch * 8, (size_t)g.G[0] * 8, rows,
+                                    cudaMemcpyDeviceToHost, f->ctx->stream));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
+    return RNMF_OK;
+}
+
+static int copy_valid(rnmf_frame* f, double* host, bool to_host)
+{
+    const FrameGeom& g = f->g;
+    const size_t per_comp = (size_t)(g.n[0] * g.n[1] * g.n[2]);
+    for (int c = 0; c < g.ncomp; ++c) {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        cudaPitchedPtr dev = make_cudaPitchedPtr(f->d + g.comp * c, (size_t)g.pitch * 8, (size_t)g.pitch * 8, (size_t)g.G[1]);
+        cudaPitchedPtr hst = make_cudaPitchedPtr(host + per_comp * c, (size_t)g.n[0] * 8, (size_t)g.n[0] * 8, (size_t)g.n[1]);
+        cudaPos dpos = make_cudaPos((size_t)(g.xoff + g.ng) * 8, (size_t)g.ng, (size_t)g.kg);
+        cudaPos hpos = make_cudaPos(0, 0, 0);
+        p.extent = make_cudaExtent((size_t)g.n[0] * 8, (size_t)g.n[1], (size_t)g.n[2]);
+        if (to_host) { p.srcPtr = dev; p.srcPos = dpos; p.dstPtr = hst; p.dstPos = hpos; p.kind = cudaMemcpyDeviceToHost; }
+        else { p.srcPtr = hst; p.srcPos = hpos; p.dstPtr = dev; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+        RNMF_CUDA_TRY(cudaMemcpy3DAsync(&p, f->ctx->stream));
+    }
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_download_valid(rnmf_frame* f, double* host)
+{
+    RNMF_REQUIRE(f && host, "null argument");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    int rc = copy_valid(f, host, true);
+    if (rc) return rc;
+    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_upload_valid(rnmf_frame* f, const double* host)
+{
+    RNMF_REQUIRE(f && host, "null argument");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    return copy_valid(f, const_cast<double*>(host), false);
+}
+
+extern "C" int32_t rnmf_frame_fill_zero(rnmf_frame* f)
+{
+    RNMF_REQUIRE(f, "frame is null");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaMemsetAsync(f->d, 0, (size_t)f->g.total * 8, f->ctx->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_copy(rnmf_frame* dst, const rnmf_frame* src)
+{
+    RNMF_REQUIRE(dst && src, "null argument");
+    RNMF_REQUIRE(dst->ctx == src->ctx && same_shape(dst->g, src->g), "frame shapes differ");
+    if (bind(dst->ctx)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaMemcpyAsync(dst->d, src->d, (size_t)src->g.total * 8, cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_fill_synthetic(rnmf_frame* f, uint64_t seed)
+{
+    RNMF_REQUIRE(f, "frame is null");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaMemsetAsync(f->d, 0, (size_t)f->g.total * 8, f->ctx->stream));
+    f->ctx->launches += launch_fill_synthetic(f->g, f->d, seed, f->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_device_ptr(rnmf_frame* f, void** p)
+{
+    RNMF_REQUIRE(f && p, "null argument");
+    *p = f->d;
+    return RNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fill_bc
+// ------------------------------------------------------------------------------------------
+static int fill_bc_on(rnmf_frame* f, double* buf, cudaStream_t s)
+{
+    RNMF_REQUIRE(f->bc_set, "fill_bc: frame has no boundary conditions (BCs::empty() would panic in the reference)");
+    if (f->has_reflect) {
+        rnmf_set_error("Reflect boundary condition not supported yet (dataframe.rs:375-377)");
+        return RNMF_ERR_UNIMPLEMENTED;
+    }
+    const FrameGeom& g = f->g;
+    int k = launch_fill_bc_faces(g, buf, f->faces.data(), s);
+    f->ctx->launches += k;
+    // Prescribed sides overlap each other at the corners: keep the reference's order
+    // comp -> dim -> lo, hi (dataframe.rs:362-430)
+    for (int c = 0; c < g.ncomp; ++c)
+        for (int d = 0; d < g.dim; ++d)
+            for (int side = 0; side < 2; ++side) {
+                const int idx = (c * g.dim + d) * 2 + side;
+                if (f->raw[idx].kind == RNMF_BC_PRESCRIBED && f->prescribed_n[idx] > 0)
+                    f->ctx->launches += launch_fill_prescribed(g, buf, c, d, side, f->prescribed_dev[idx], f->prescribed_n[idx], s);
+            }
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_fill_bc(rnmf_frame* f)
+{
+    RNMF_REQUIRE(f, "frame is null");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    return fill_bc_on(f, f->d, f->ctx->stream);
+}
+
+// poisson.rs:72-76; 3D by the extrapolation rule.  Host arithmetic, compiled with
+// -ffp-contract=off: the same IEEE operations as the reference.
+extern "C" int32_t rnmf_poisson_coefs(int32_t dim, const double* dx, double* coef)
+{
+    RNMF_REQUIRE(dx && coef && (dim == 2 || dim == 3), "bad arguments");
+    if (dim == 2) {
+        const double dx2 = dx[0] * dx[0], dy2 = dx[1] * dx[1];
+        coef[0] = dx2 * dy2 / (2.0 * (dx2 + dy2));
+        coef[1] = dy2 / (2.0 * (dx2 + dy2));
+        coef[2] = dx2 / (2.0 * (dx2 + dy2));
+        coef[3] = 0.0;
+    } else {
+        const double dx2 = dx[0] * dx[0], dy2 = dx[1] * dx[1], dz2 = dx[2] * dx[2];
+        const double a = 1.0 / (2.0 * (1.0 / dx2 + 1.0 / dy2 + 1.0 / dz2));
+        coef[0] = a; coef[1] = a / dx2; coef[2] = a / dy2; coef[3] = a / dz2;
+    }
+    return RNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// halo exchange: the slab's first/last valid slices go to the neighbours' ghost slices.
+// Slices of the slowest direction are contiguous in memory (pitch*G1 [*1] doubles per z-plane,
+// pitch doubles per y-row in 2D), so no pack kernel is needed: pack order == collect_typed_cells
+// order (dataframe.rs:273-278, pinned by :1148-1201), unpack == fill_prescribed_bc (:280-284).
+// ------------------------------------------------------------------------------------------
+static int halo_exchange_on(rnmf_frame* f, double* buf, cudaStream_t s)
+{
+    rnmf_ctx* c = f->ctx;
+    if (!f->distributed || c->nranks == 1) return RNMF_OK;
+    const FrameGeom& g = f->g;
+    const int D = slow_dim(g);
+    const long long slice = D == 2 ? g.plane : g.pitch;          // doubles per slowest-direction slice
+    const long long ng = g.ng;
+    const long long cnt = slice * ng;
+    for (int comp = 0; comp < g.ncomp; ++comp) {
+        double* base = buf + g.comp * comp;                       // grown slice 0 of this component
+        double* lo_ghost = base;                                  // slices [0, ng)
+        double* lo_valid = base + slice * ng;                     // slices [ng, 2ng)
+        double* hi_valid = base + slice * g.n[D];                 // slices [n, n+ng)   (grown index)
+        double* hi_ghost = base + slice * (g.n[D] + ng);          // slices [n+ng, n+2ng)
+        RNMF_NCCL_TRY(g_nccl.GroupStart());
+        if (c->rank > 0) {
+            RNMF_NCCL_TRY(g_nccl.Send(lo_valid, (size_t)cnt, ncclDouble, c->rank - 1, c->comm, s));
+            RNMF_NCCL_TRY(g_nccl.Recv(lo_ghost, (size_t)cnt, ncclDouble, c->rank - 1, c->comm, s));
+        }
+        if (c->rank < c->nranks - 1) {
+            RNMF_NCCL_TRY(g_nccl.Send(hi_valid, (size_t)cnt, ncclDouble, c->rank + 1, c->comm, s));
+            RNMF_NCCL_TRY(g_nccl.Recv(hi_ghost, (size_t)cnt, ncclDouble, c->rank + 1, c->comm, s));
+        }
+        RNMF_NCCL_TRY(g_nccl.GroupEnd());
+    }
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_halo_exchange(rnmf_frame* f)
+{
+    RNMF_REQUIRE(f, "frame is null");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    return halo_exchange_on(f, f->d, f->ctx->stream);
+}
+
+extern "C" int32_t rnmf_allreduce_sum(rnmf_ctx* c, double* inout)
+{
+    RNMF_REQUIRE(c && inout, "null argument");
+    if (c->nranks == 1) return RNMF_OK;
+    if (bind(c)) return RNMF_ERR_CUDA;
+    c->h_scalar[0] = *inout;
+    RNMF_CUDA_TRY(cudaMemcpyAsync(c->d_scalar, c->h_scalar, 8, cudaMemcpyHostToDevice, c->stream));
+    RNMF_NCCL_TRY(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *inout = c->h_scalar[0];
+    return RNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sweeps
+// ------------------------------------------------------------------------------------------
+static int check_sweep_args(rnmf_frame* psi, const rnmf_frame* rhs, const double* coef, int64_t n_sweeps)
+{
+    RNMF_REQUIRE(psi && rhs && coef, "null argument");
+    RNMF_REQUIRE(psi->ctx == rhs->ctx, "frames belong to different contexts");
+    RNMF_REQUIRE(same_shape(psi->g, rhs->g), "psi and rhs shapes differ");
+    RNMF_REQUIRE(psi->g.ncomp == 1, "sweeps need n_comp == 1 (poisson.rs uses component 0 of a 1-component frame)");
+    RNMF_REQUIRE(n_sweeps >= 0, "n_sweeps < 0");
+    RNMF_REQUIRE(psi->bc_set, "psi has no boundary conditions");
+    if (psi->has_reflect) {
+        rnmf_set_error("Reflect boundary condition not supported yet (dataframe.rs:375-377)");
+        return RNMF_ERR_UNIMPLEMENTED;
+    }
+    return RNMF_OK;
+}
+
+static bool has_prescribed(const rnmf_frame* f)
+{
+    for (auto& r : f->raw) if (r.kind == RNMF_BC_PRESCRIBED) return true;
+    return false;
+}
+
+extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, const double* coef, int64_t n_sweeps,
+                                      double* l1_update)
+{
+    int rc = check_sweep_args(psi, rhs, coef, n_sweeps);
+    if (rc) return rc;
+    rnmf_ctx* c = psi->ctx;
+    if (bind(c)) return RNMF_ERR_CUDA;
+    const FrameGeom& g = psi->g;
+    cudaStream_t s = c->stream;
+    if (l1_update) *l1_update = 0.0;
+    if (n_sweeps == 0) return RNMF_OK;
+
+    if (!psi->d2) {
+        rc = alloc_buffer(g, &psi->d2, s);
+        if (rc) return rc;
+    }
+    // cells no sweep/fill ever writes (edges, corners; all ghosts for ng>1 until the fill) must
+    // agree in both buffers: the reference's in-place frame keeps them untouched.
+    c->launches += launch_copy_ghost_shell(g, psi->d, psi->d2, s);
+
+    const bool dist = psi->distributed && c->nranks > 1;
+    if (dist) {
+        rc = halo_exchange_on(psi, psi->d, s);
+        if (rc) return rc;
+    }
+    const int D = slow_dim(g);
+    const long long m = g.n[D];
+    const bool fused = g.ng == 1 && !has_prescribed(psi);
+
+    SweepArgs a;
+    a.g = g;
+    a.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
+    a.faces = psi->faces[0];
+    a.fuse_fill = fused ? 1 : 0;
+    a.variant = c->sweep_variant;
+    a.rhs = rhs->d;
+
+    for (int64_t it = 0; it < n_sweeps; ++it) {
+        const bool want_norm = l1_update && it == n_sweeps - 1;
+        a.in = psi->d;
+        a.out = psi->d2;
+        a.partials = nullptr;
+        long long n_part = 0;
+        if (!dist || m < 3 || !c->overlap_halo || !fused) {
+            a.k_begin = 0; a.k_end = m;
+            if (want_norm) {
+                n_part = sweep_num_partials(a);
+                rc = ensure_partials(c, n_part);
+                if (rc) return rc;
+                a.partials = c->d_partials;
+            }
+            c->launches += launch_jacobi_sweep(a, s);
+            if (!fused) { rc = fill_bc_on(psi, psi->d2, s); if (rc) return rc; }
+            if (dist) { rc = halo_exchange_on(psi, psi->d2, s); if (rc) return rc; }
+        } else {
+            // boundary slices first, then exchange them on the halo stream while the interior runs
+            SweepArgs lo = a, hi = a, mid = a;
+            lo.k_begin = 0; lo.k_end = 1;
+            hi.k_begin = m - 1; hi.k_end = m;
+            mid.k_begin = 1; mid.k_end = m - 1;
+            long long p_lo = 0, p_hi = 0, p_mid = 0;
+            if (want_norm) {
+                p_lo = sweep_num_partials(lo); p_hi = sweep_num_partials(hi); p_mid = sweep_num_partials(mid);
+                n_part = p_lo + p_hi + p_mid;
+                rc = ensure_partials(c, n_part);
+                if (rc) return rc;
+                lo.partials = c->d_partials;
+                hi.partials = c->d_partials + p_lo;
+                mid.partials = c->d_partials + p_lo + p_hi;
+            }
+            c->launches += launch_jacobi_sweep(lo, s);
+            c->launches += launch_jacobi_sweep(hi, s);
+            RNMF_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
+            RNMF_CUDA_TRY(cudaStreamWaitEvent(c->stream_halo, c->ev_boundary, 0));
+            rc = halo_exchange_on(psi, psi->d2, c->stream_halo);
+            if (rc) return rc;
+            RNMF_CUDA_TRY(cudaEventRecord(c->ev_halo, c->stream_halo));
+            c->launches += launch_jacobi_sweep(mid, s);
+            RNMF_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_halo, 0));
+        }
+        if (want_norm) {
+            c->launches += launch_reduce_partials(c->d_partials, (int)n_part, c->d_scalar, s);
+            if (dist) RNMF_NCCL_TRY(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclSum, c->comm, s));
+            RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, s));
+        }
+        double* t = psi->d; psi->d = psi->d2; psi->d2 = t;
+    }
+    RNMF_CUDA_TRY(cudaGetLastError());
+    if (l1_update) {
+        RNMF_CUDA_TRY(cudaStreamSynchronize(s));
+        *l1_update = c->h_scalar[0];
+    }
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_gs_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, const double* coef, int64_t n_sweeps)
+{
+    int rc = check_sweep_args(psi, rhs, coef, n_sweeps);
+    if (rc) return rc;
+    rnmf_ctx* c = psi->ctx;
+    const FrameGeom& g = psi->g;
+    RNMF_REQUIRE(g.dim == 2 && g.ng == 1, "reference-order GS: 2D frames with n_ghost=1 only");
+    RNMF_REQUIRE(!(psi->distributed && c->nranks > 1), "reference-order GS is single-GPU (replicas only)");
+    for (int i = 0; i < 4; ++i)
+        RNMF_REQUIRE(psi->faces[0].f[i].mode != 0, "reference-order GS needs Dirichlet/Neumann on all four faces");
+    if (bind(c)) return RNMF_ERR_CUDA;
+    if (n_sweeps == 0) return RNMF_OK;
+    int k = launch_gs_wavefront_2d(g, psi->d, rhs->d, SweepCoef{ coef[0], coef[1], coef[2], coef[3] }, psi->faces[0],
+                                   n_sweeps, c->stream);
+    if (k < 0) return RNMF_ERR_CUDA;
+    c->launches += k;
+    return fill_bc_on(psi, psi->d, c->stream);     // the fill after the last sweep (poisson.rs:88)
+}
+
+// ------------------------------------------------------------------------------------------
+// operators, norm, variable-mu operator
+// ------------------------------------------------------------------------------------------
+static int check_same(const rnmf_frame* a, const rnmf_frame* b)
+{
+    RNMF_REQUIRE(a && b, "null argument");
+    RNMF_REQUIRE(a->ctx == b->ctx && same_shape(a->g, b->g), "frame shapes differ");
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_scale(rnmf_frame* out, double a, const rnmf_frame* x)
+{
+    int rc = check_same(out, x);
+    if (rc) return rc;
+    if (bind(out->ctx)) return RNMF_ERR_CUDA;
+    out->ctx->launches += launch_scale(x->g.total, a, x->d, out->d, out->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_add(rnmf_frame* out, const rnmf_frame* x, const rnmf_frame* y)
+{
+    int rc = check_same(out, x);
+    if (!rc) rc = check_same(out, y);
+    if (rc) return rc;
+    if (bind(out->ctx)) return RNMF_ERR_CUDA;
+    out->ctx->launches += launch_add(x->g.total, x->d, y->d, out->d, out->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_mul(rnmf_frame* out, const rnmf_frame* x, const rnmf_frame* y)
+{
+    int rc = check_same(out, x);
+    if (!rc) rc = check_same(out, y);
+    if (rc) return rc;
+    if (bind(out->ctx)) return RNMF_ERR_CUDA;
+    out->ctx->launches += launch_mul(x->g.total, x->d, y->d, out->d, out->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_axpby(rnmf_frame* out, double a, const rnmf_frame* x, double b, const rnmf_frame* y)
+{
+    int rc = check_same(out, x);
+    if (!rc) rc = check_same(out, y);
+    if (rc) return rc;
+    if (bind(out->ctx)) return RNMF_ERR_CUDA;
+    out->ctx->launches += launch_axpby(x->g.total, a, x->d, b, y->d, out->d, out->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_abs_sum_valid(rnmf_frame* f, double* out)
+{
+    RNMF_REQUIRE(f && out, "null argument");
+    rnmf_ctx* c = f->ctx;
+    if (bind(c)) return RNMF_ERR_CUDA;
+    const int nb = abs_sum_num_partials(f->g);
+    int rc = ensure_partials(c, nb);
+    if (rc) return rc;
+    int k = launch_abs_sum_valid(f->g, f->d, c->d_partials, (int)c->partial_cap, c->d_scalar + 1, c->stream);
+    if (k < 0) { rnmf_set_error("abs_sum_valid: partial buffer too small"); return RNMF_ERR_INVALID; }
+    c->launches += k;
+    RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar + 1, c->d_scalar + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c->h_scalar[1];
+    return RNMF_OK;
+}
+
+static int varcoef_impl(const rnmf_frame* phi, const rnmf_mu_params* mu, int with_source, double relax, rnmf_frame* out)
+{
+    int rc = check_same(out, phi);
+    if (rc) return rc;
+    RNMF_REQUIRE(mu, "mu params null");
+    RNMF_REQUIRE(phi->g.dim == 2 && phi->g.ncomp == 1, "variable-mu operator: 2D, n_comp=1 (poisson.rs:13-44)");
+    RNMF_REQUIRE(out != phi, "out must not alias phi");
+    if (bind(out->ctx)) return RNMF_ERR_CUDA;
+    out->ctx->launches += launch_varcoef_2d(phi->g, phi->d, *mu, with_source, relax, out->d, out->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_varcoef_laplace_2d(const rnmf_frame* phi, const rnmf_mu_params* mu, rnmf_frame* out)
+{
+    return varcoef_impl(phi, mu, 0, 1.0, out);
+}
+
+extern "C" int32_t rnmf_poisson_source_2d(const rnmf_frame* phi, const rnmf_mu_params* mu, double relax, rnmf_frame* out)
+{
+    return varcoef_impl(phi, mu, 1, relax, out);
+}
+
+extern "C" int32_t rnmf_gradient_h_2d(const rnmf_frame* psi, rnmf_frame* h)
+{
+    RNMF_REQUIRE(psi && h, "null argument");
+    RNMF_REQUIRE(psi->ctx == h->ctx, "different contexts");
+    RNMF_REQUIRE(psi->g.dim == 2 && psi->g.ncomp == 1 && h->g.dim == 2 && h->g.ncomp == 2, "get_h: 2D psi (1 comp) -> h (2 comps)");
+    RNMF_REQUIRE(psi->g.n[0] == h->g.n[0] && psi->g.n[1] == h->g.n[1] && psi->g.ng == h->g.ng, "shapes differ");
+    if (bind(h->ctx)) return RNMF_ERR_CUDA;
+    h->ctx->launches += launch_gradient_h_2d(psi->g, psi->d, h->g, h->d, h->ctx->stream);
+    RNMF_CUDA_TRY(cudaGetLastError());
+    return RNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry point (the reference-facing call: solve_poisson with host frames)
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64_t* n, const double* lo, const double* dx,
+                                           int32_t ng, const rnmf_bc_face* faces, const double* psi_in, const double* rhs_in,
+                                           int64_t n_sub_iter, int32_t mode, double* psi_out, double* l1_update)
+{
+    RNMF_REQUIRE(c && n && lo && dx && faces && psi_in && rhs_in && psi_out, "null argument");
+    RNMF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (Jacobi) or 1 (reference-order GS)");
+    FrameGeom want;
+    RNMF_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+    make_geom(want, dim, n, lo, dx, ng, 1);
+    if (c->hp_psi && !same_shape(c->hp_psi->g, want)) {
+        rnmf_frame_destroy(c->hp_psi); c->hp_psi = nullptr;
+        rnmf_frame_destroy(c->hp_rhs); c->hp_rhs = nullptr;
+    }
+    int rc;
+    if (!c->hp_psi) {
+        rc = rnmf_frame_create(c, dim, n, lo, dx, ng, 1, &c->hp_psi);
+        if (rc) return rc;
+        rc = rnmf_frame_create(c, dim, n, lo, dx, ng, 1, &c->hp_rhs);
+        if (rc) return rc;
+    }
+    for (int d = 0; d < dim; ++d) { c->hp_psi->g.dx[d] = dx[d]; c->hp_psi->g.lo[d] = lo[d]; c->hp_rhs->g.dx[d] = dx[d]; c->hp_rhs->g.lo[d] = lo[d]; }
+    rc = rnmf_frame_set_bc(c->hp_psi, faces, dim * 2);
+    if (rc) return rc;
+    rc = rnmf_frame_upload(c->hp_psi, psi_in);
+    if (rc) return rc;
+    rc = rnmf_frame_upload(c->hp_rhs, rhs_in);
+    if (rc) return rc;
+    double coef[4];
+    rnmf_poisson_coefs(dim, dx, coef);
+    if (mode == 0) rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter, l1_update);
+    else { rc = rnmf_gs_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter); if (l1_update) *l1_update = 0.0; }
+    if (rc) return rc;
+    return rnmf_frame_download(c->hp_psi, psi_out);
+}
+
+extern "C" int32_t rnmf_host_alloc(int64_t bytes, void** out)
+{
+    RNMF_REQUIRE(out && bytes >= 0, "bad arguments");
+    RNMF_CUDA_TRY(cudaMallocHost(out, (size_t)bytes));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_host_free(void* p)
+{
+    if (p) RNMF_CUDA_TRY(cudaFreeHost(p));
+    return RNMF_OK;
+}

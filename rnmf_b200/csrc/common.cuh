@@ -1,0 +1,128 @@
+// common.cuh -- internal types shared by the kernels and the C ABI of librnmf_b200.
+// Device layout of a data frame (replaces `data: Vec<S>` of dataframe.rs:35-60):
+//   element (ii,jj,kk,c) in GROWN indices lives at
+//       base + xoff + ii + pitch*(jj + G1*(kk + G2*c)),      xoff = 16 - ng
+//   so valid cell i=0 (ii=ng) is at row_base + 16 doubles = 128 B aligned; pitch % 16 == 0.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/rnmf_b200.h"
+
+#define RNMF_ROW_ALIGN 16  // doubles (128 bytes)
+
+struct FrameGeom {
+    int dim, ng, ncomp;
+    long long n[3];      // valid cells
+    long long G[3];      // grown cells (G[2]=1 in 2D)
+    long long pitch;     // doubles per grown row
+    long long xoff;      // 16 - ng
+    long long plane;     // pitch*G[1]
+    long long comp;      // plane*G[2]
+    long long total;     // comp*ncomp (doubles allocated)
+    double dx[3], lo[3];
+    long long nglob[3], off[3];
+    int kg;              // ghost depth in z (ng in 3D, 0 in 2D)
+
+    // pointer offset of valid-indexed cell (i,j,k,c)  (low ghosts negative, dataframe.rs:209-211)
+    __host__ __device__ inline long long at(long long i, long long j, long long k, long long c) const
+    {
+        return xoff + (i + ng) + pitch * ((j + ng) + G[1] * ((k + kg) + G[2] * c));
+    }
+};
+
+// One face of the fused / stand-alone Dirichlet-Neumann fill, precomputed on the host with the
+// reference's own operations so the kernel only does one add/sub per ghost cell:
+//   mode 1 (Dirichlet):  ghost = s - mirror,        s = 2.0*value                    (dataframe.rs:328,344)
+//   mode 2 (Neumann lo): ghost = mirror - s_g,      s_g = (grad*(2.0*g-1.0))*dx      (:293-294)
+//   mode 3 (Neumann hi): ghost = mirror + s_g,      s_g = (grad*(2.0*(g+1)-1.0))*dx  (:311-312)
+//   mode 0: skip (HALO / Prescribed handled elsewhere)
+// For ng>1 the Neumann scalar depends on the ghost layer; the kernels recompute it from
+// grad and dx with the same association.
+struct FaceBC {
+    int mode;
+    double value;   // Dirichlet value or Neumann gradient
+    double s1;      // precomputed scalar for ghost layer 1 (the ng=1 fast path)
+};
+
+struct FaceSet {      // faces of ONE component: [d*2+side]
+    FaceBC f[6];
+};
+
+__host__ __device__ inline double rnmf_ghost_value(const FaceBC& b, int side, double mirror, int layer /*0-based*/, double dxd)
+{
+    // layer = ghost_indx of the reference loops for Dirichlet/Neumann-high, ghost_indx-1 for Neumann-low
+    if (b.mode == 1) {
+#ifdef __CUDA_ARCH__
+        return __dsub_rn(__dmul_rn(2.0, b.value), mirror);
+#else
+        return 2.0 * b.value - mirror;
+#endif
+    }
+    double fac = 2.0 * (double)(layer + 1) - 1.0;
+#ifdef __CUDA_ARCH__
+    double s = __dmul_rn(__dmul_rn(b.value, fac), dxd);
+    return side == 0 ? __dsub_rn(mirror, s) : __dadd_rn(mirror, s);
+#else
+    double s = b.value * fac * dxd;
+    return side == 0 ? mirror - s : mirror + s;
+#endif
+}
+
+// error plumbing (capi.cu)
+void rnmf_set_error(const char* fmt, ...);
+#define RNMF_CUDA_TRY(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            rnmf_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return RNMF_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+#define RNMF_REQUIRE(cond, ...)                                                          \
+    do {                                                                                 \
+        if (!(cond)) { rnmf_set_error(__VA_ARGS__); return RNMF_ERR_INVALID; }          \
+    } while (0)
+
+struct SweepCoef { double c0, c1, c2, c3; };
+
+// ---- kernel launchers (each returns the number of kernels it launched, or <0 on error) -----
+int launch_fill_bc_faces(const FrameGeom& g, double* d, const FaceSet* faces_host, cudaStream_t s);
+int launch_fill_prescribed(const FrameGeom& g, double* d, int comp, int dir, int side,
+                           const double* vals_dev, long long nvals, cudaStream_t s);
+int launch_copy_ghost_shell(const FrameGeom& g, const double* src, double* dst, cudaStream_t s);
+
+struct SweepArgs {
+    FrameGeom g;
+    const double* in;
+    const double* rhs;       // same geometry as in/out (pitch equal)
+    double* out;
+    SweepCoef c;
+    FaceSet faces;           // comp 0 (sweeps are for n_comp = 1 frames)
+    int fuse_fill;           // 1: write face ghosts of `out` (ng == 1)
+    double* partials;        // nullable: per-block partial sums of |out-in|
+    long long k_begin, k_end;// 3D: range of valid planes to update (slab interior/boundary split)
+                             // 2D: range of valid rows
+    int variant;
+};
+int sweep_num_partials(const SweepArgs& a);
+int launch_jacobi_sweep(const SweepArgs& a, cudaStream_t s);
+int launch_reduce_partials(const double* partials, int n, double* out_dev, cudaStream_t s);
+
+int launch_abs_sum_valid(const FrameGeom& g, const double* d, double* partials, int max_partials,
+                         double* out_dev, cudaStream_t s);
+int abs_sum_num_partials(const FrameGeom& g);
+
+int launch_scale(long long n, double a, const double* x, double* out, cudaStream_t s);
+int launch_add(long long n, const double* x, const double* y, double* out, cudaStream_t s);
+int launch_mul(long long n, const double* x, const double* y, double* out, cudaStream_t s);
+int launch_axpby(long long n, double a, const double* x, double b, const double* y, double* out, cudaStream_t s);
+int launch_fill_synthetic(const FrameGeom& g, double* d, unsigned long long seed, cudaStream_t s);
+int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s);
+int launch_unpack_valid(const FrameGeom& g, const double* packed, double* d, cudaStream_t s);
+
+int launch_varcoef_2d(const FrameGeom& g, const double* phi, const rnmf_mu_params& mu,
+                      int with_source, double relax, double* out, cudaStream_t s);
+int launch_gradient_h_2d(const FrameGeom& g, const double* psi, const FrameGeom& gh, double* h, cudaStream_t s);
+
+int launch_gs_wavefront_2d(const FrameGeom& g, double* psi, const double* rhs, SweepCoef c,
+                           const FaceSet& faces, long long n_sweeps, cudaStream_t s);
