@@ -31,7 +31,7 @@ extern "C" int32_t rnmf_abi_version(void) { return RNMF_ABI_VERSION; }
 extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
-           "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi2d_ymarch{128,256},"
+           "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_ymarch{128,256},"
            "fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 

@@ -156,11 +156,12 @@ SWEEP_CASES_3D = [
     ([2, 2, 2], [2.0, 2.0, 2.0], MIXED_3D, 5),
     ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 3),
     ([31, 40, 3], [1.0, 2.0, 3.0], MIXED_3D, 3),
+    ([300, 70, 80], [3.0, 2.0, 1.0], MIXED_3D, 3),       # several x tiles of the TMA variant, ragged edges
 ]
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_3D)
-@pytest.mark.parametrize("variant", [0, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 7, 8, 10, 11])
 def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
@@ -321,10 +322,13 @@ def test_magnetostatics_small_case_reference_order(R, ctx):
 
 def test_magnetostatics_lua_case_full(R, ctx):
     """examples/magnetostatics/magnetostatics.lua verbatim (301x301, 10 x 550 sweeps) in the
-    reference's update order: the sum_diff trajectory of the oracle (tests/test_oracle_known_answers.py)
+    reference's update order: the sum_diff trajectory of the oracle (tests/golden/magnetostatics_trace.json)
     to 1e-12, and psi(150,150) bit-exact."""
     from rnmf_b200 import poisson
-    from tests.test_oracle_known_answers import MAGNETOSTATICS_PSI_150_150, MAGNETOSTATICS_TRACE
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "magnetostatics_trace.json")) as fh:
+        gold = json.load(fh)
+    MAGNETOSTATICS_TRACE, MAGNETOSTATICS_PSI_150_150 = gold["sum_diff"], gold["psi_150_150"]
     cfg = poisson.Config(poisson.GeomConfig(2, (301.0, 301.0), (301, 301)),
                          poisson.UserModel((0.0, 1.0), 0.2, 10, 550, (301.0 / 2, 301.0 / 2), 301.0 / 20, (3.2, 1.0), 0.1))
     psi, trace, iters = poisson.magnetostatics(cfg, order="reference", ctx=ctx)

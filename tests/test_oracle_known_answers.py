@@ -38,6 +38,10 @@ def test_magnetostatics_trajectory_full_case():
     assert it.value == 10                      # never drops below tol=0.1
     assert tr.tolist() == MAGNETOSTATICS_TRACE
     assert ora.as_grid(g, psi)[0, 151, 151] == MAGNETOSTATICS_PSI_150_150
+    import json, os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "magnetostatics_trace.json")) as fh:
+        gold = json.load(fh)
+    assert gold["sum_diff"] == MAGNETOSTATICS_TRACE and gold["psi_150_150"] == MAGNETOSTATICS_PSI_150_150
 
 
 def test_linear_field_is_fixed_point():
