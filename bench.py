@@ -61,6 +61,7 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-others", action="store_true", help="skip the short extra runs of the other configs")
     p.add_argument("--variant", default=None, help="sweep kernel variant (measurement knob)")
+    p.add_argument("--chunk", default=None, help="marching chunk per CTA (measurement knob)")
     return p.parse_args()
 
 
@@ -383,6 +384,8 @@ def main():
 
     if args.variant is not None:
         ctx.set_option("sweep_variant", args.variant)
+    if args.chunk is not None:
+        ctx.set_option("sweep_chunk", args.chunk)
 
     w = WORKLOADS[args.workload]
     sampler = ClockSampler(local)

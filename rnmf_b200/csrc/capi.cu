@@ -113,6 +113,7 @@ struct rnmf_ctx {
     double* d_partials = nullptr;
     long long partial_cap = 0;
     int sweep_variant = 0;
+    int sweep_chunk = 0;
     int overlap_halo = 1;
     ncclComm_t comm = nullptr;
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
@@ -355,6 +356,7 @@ extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* val
 {
     RNMF_REQUIRE(c && key && value, "null argument");
     if (!strcmp(key, "sweep_variant")) { c->sweep_variant = !strcmp(value, "auto") ? 0 : atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "sweep_chunk")) { c->sweep_chunk = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "halo_overlap")) { c->overlap_halo = atoi(value); return RNMF_OK; }
     rnmf_set_error("unknown option '%s'", key);
     return RNMF_ERR_INVALID;
@@ -756,6 +758,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     a.faces = psi->faces[0];
     a.fuse_fill = fused ? 1 : 0;
     a.variant = c->sweep_variant;
+    a.chunk_override = c->sweep_chunk;
     a.rhs = rhs->d;
 
     for (int64_t it = 0; it < n_sweeps; ++it) {

@@ -103,6 +103,7 @@ struct SweepArgs {
     long long k_begin, k_end;// 3D: range of valid planes to update (slab interior/boundary split)
                              // 2D: range of valid rows
     int variant;
+    int chunk_override;      // 0 = planner decides (measurement knob "sweep_chunk")
 };
 int sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep(const SweepArgs& a, cudaStream_t s);

@@ -244,6 +244,7 @@ Plan make_plan(const SweepArgs& a)
         if (want < 1) want = 1;
         long long chunk = (span + want - 1) / want;
         if (chunk < 16) chunk = 16;
+        if (a.chunk_override > 0) chunk = a.chunk_override;
         if (chunk > span) chunk = span > 0 ? span : 1;
         long long bz = (span + chunk - 1) / chunk;
         if (bz > 65535) { bz = 65535; chunk = (span + bz - 1) / bz; bz = (span + chunk - 1) / chunk; }
@@ -288,7 +289,7 @@ void launch2d(const Plan& pl, const SweepParams& p, cudaStream_t s)
 int tma_sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s);
 // default (variant 0 = auto): the TMA kernel for 3D frames (measured 240 vs 203 GLUP/s at 768^3)
-static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9)); }
+static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9) || a.variant == 13); }
 
 int sweep_num_partials(const SweepArgs& a)
 {

@@ -17,6 +17,8 @@
 // Arithmetic: same explicitly rounded sequence as kernels_sweep.cu => bit-identical results.
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -96,8 +98,9 @@ struct TmaCfg {
 
 // TX must be 128: a consumer warp covers a 128-cell row as two 64-cell halves, each lane owning
 // the pairs (2*lane, 2*lane+1) and (64+2*lane, 65+2*lane).
-template <int TY, int NS, bool NORM>
-__global__ void __launch_bounds__(32 * TY + 32) jacobi3d_tma_kernel(const __grid_constant__ CUtensorMap tm_psi,
+// MINB: CTAs/SM the register allocation must allow (shared memory permitting)
+template <int TY, int NS, bool NORM, int MINB>
+__global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const __grid_constant__ CUtensorMap tm_psi,
                                                                     const __grid_constant__ CUtensorMap tm_rhs,
                                                                     const TmaSweepParams p)
 {
@@ -289,8 +292,13 @@ int encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, 
     cuuint64_t strides[2] = { (cuuint64_t)g.pitch * 8, (cuuint64_t)g.plane * 8 };
     cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1 };
     cuuint32_t estr[3] = { 1, 1, 1 };
+    static int promo = -1;
+    if (promo < 0) { const char* e = getenv("RNMF_TMA_L2PROMO"); promo = e ? atoi(e) : 3; }
+    const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                    : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         rnmf_set_error("cuTensorMapEncodeTiled failed (%d): pitch=%lld G1=%lld G2=%lld box=%dx%d", (int)r, g.pitch, g.G[1], g.G[2], bx, by);
@@ -299,7 +307,7 @@ int encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, 
     return 0;
 }
 
-template <int TY, int NS>
+template <int TY, int NS, int MINB = 1>
 struct Launcher {
     using Cfg = TmaCfg<128, TY, NS>;
     static int plan(const SweepArgs& a, dim3& grid, int& chunk)
@@ -307,11 +315,15 @@ struct Launcher {
         const FrameGeom& g = a.g;
         const long long span = a.k_end - a.k_begin;
         const long long bx = (g.n[0] + 127) / 128, by = (g.n[1] + TY - 1) / TY;
-        // enough z-chunks for ~6 waves of 2 CTAs/SM, chunk >= 32 planes so the 2 re-read planes stay <~6%
-        long long want = (148LL * 2 * 6 + bx * by - 1) / (bx * by);
+        // Short chunks keep the last partial wave short (measured at 768^3: 258 GLUP/s for 32..64
+        // planes, 244 for 192); each chunk re-reads 2 planes, so stay >= 16 unless the xy plane has
+        // too few tiles to fill the SMs otherwise.
+        long long want = (148LL * 3 * 8 + bx * by - 1) / (bx * by);
         if (want < 1) want = 1;
         long long c = (span + want - 1) / want;
-        if (c < 32) c = 32;
+        if (c > 48) c = 48;
+        if (c < 16) c = 16;
+        if (a.chunk_override > 0) c = a.chunk_override;
         if (c > span) c = span > 0 ? span : 1;
         long long bz = (span + c - 1) / c;
         if (bz > 65535) { bz = 65535; c = (span + bz - 1) / bz; bz = (span + c - 1) / c; }
@@ -333,16 +345,18 @@ struct Launcher {
         static bool attr_set[2] = { false, false };
         if (a.partials) {
             if (!attr_set[1]) {
-                if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+                if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+                cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, true, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 attr_set[1] = true;
             }
-            jacobi3d_tma_kernel<TY, NS, true><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
+            jacobi3d_tma_kernel<TY, NS, true, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
         } else {
             if (!attr_set[0]) {
-                if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+                if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+                cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, false, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 attr_set[0] = true;
             }
-            jacobi3d_tma_kernel<TY, NS, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
+            jacobi3d_tma_kernel<TY, NS, false, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
         }
         return 1;
     }
@@ -356,10 +370,12 @@ int tma_sweep_num_partials(const SweepArgs& a)
     dim3 grid;
     int chunk;
     switch (a.variant) {
-    case 5: return Launcher<8, 5>::plan(a, grid, chunk);
+    case 5: return Launcher<8, 5, 2>::plan(a, grid, chunk);
     case 7: return Launcher<16, 4>::plan(a, grid, chunk);
-    case 8: return Launcher<4, 6>::plan(a, grid, chunk);
-    default: return Launcher<8, 4>::plan(a, grid, chunk);
+    case 8: return Launcher<4, 6, 3>::plan(a, grid, chunk);
+    case 9: return Launcher<8, 3, 2>::plan(a, grid, chunk);
+    case 13: return Launcher<16, 3, 1>::plan(a, grid, chunk);
+    default: return Launcher<8, 4, 2>::plan(a, grid, chunk);
     }
 }
 
@@ -367,9 +383,11 @@ int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
     switch (a.variant) {
-    case 5: return Launcher<8, 5>::launch(a, s);
+    case 5: return Launcher<8, 5, 2>::launch(a, s);
     case 7: return Launcher<16, 4>::launch(a, s);
-    case 8: return Launcher<4, 6>::launch(a, s);
-    default: return Launcher<8, 4>::launch(a, s);
+    case 8: return Launcher<4, 6, 3>::launch(a, s);
+    case 9: return Launcher<8, 3, 2>::launch(a, s);
+    case 13: return Launcher<16, 3, 1>::launch(a, s);
+    default: return Launcher<8, 4, 2>::launch(a, s);
     }
 }

@@ -161,7 +161,7 @@ SWEEP_CASES_3D = [
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_3D)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 7, 8, 10, 11])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 13])
 def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
