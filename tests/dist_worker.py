@@ -1,0 +1,175 @@
+"""Multi-rank worker (one process per rank) used by the distributed tests.
+
+  backend "nccl": run under torchrun on >= 2 GPUs; every rank owns a slab of a global frame in
+      librnmf_b200 (rnmf_frame_create_slab), runs halo-exchanging Jacobi sweeps and the result is
+      compared, slab by slab, against the single-domain CPU oracle -- bit-exact.
+  backend "gloo": CPU only (no GPU, no librnmf compute): the same decomposition rule
+      (rnmf_slab_partition == Domain::new_rectangular's split) driven with the ORACLE as the
+      per-slab sweep and torch.distributed(gloo) send/recv as the halo exchange; checks that slab
+      frames + HALO faces + plane exchange reproduce the single-domain result exactly.
+Exit code 0 = pass.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+MIXED_3D = ([("dirichlet", 0.0), ("neumann", 0.0), ("dirichlet", 0.25)],
+            [("dirichlet", 1.0), ("neumann", -0.5), ("neumann", 0.5)])
+MIXED_2D = ([("neumann", 0.3), ("dirichlet", -1.0)], [("dirichlet", 2.0), ("neumann", -0.7)])
+
+CASES = [
+    # n_global, hi, spec, sweeps
+    ([40, 36, 50], [40.0, 72.0, 150.0], MIXED_3D, 5),
+    ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 4),      # uneven split: remainder goes to the last rank
+    ([64, 37], [64.0, 37.0], MIXED_2D, 6),
+]
+
+
+def reference(n, hi, spec, sweeps):
+    from oracle import oracle as ora
+    g = ora.geom(n, hi=hi)
+    bc = ora.bcs(g.dim, [spec])
+    nv = int(np.prod(n))
+    psi, rhs = ora.zeros(g), ora.zeros(g)
+    ora.valid_view(g, psi)[0] = ora.splitmix_field(nv, 101).reshape(tuple(reversed(n)))
+    ora.valid_view(g, rhs)[0] = ora.splitmix_field(nv, 202).reshape(tuple(reversed(n)))
+    ora.fill_bc(g, psi, bc)
+    l1 = ora.jacobi(g, psi, rhs, bc, sweeps)
+    return ora.valid_view(g, psi)[0].copy(), l1
+
+
+def run_nccl():
+    import torch
+    import torch.distributed as dist
+    import rnmf_b200 as R
+    from rnmf_b200 import poisson
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ctx = R.Context.from_torch_distributed()
+    mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
+    ok = True
+    for overlap in (1, 0):
+        ctx.set_option("halo_overlap", overlap)
+        for n, hi, spec, sweeps in CASES:
+            dim = len(n)
+            want, l1_ref = reference(n, hi, spec, sweeps)
+            bc = R.BCs([R.ComponentBCs([mk[k](v) for k, v in spec[0]], [mk[k](v) for k, v in spec[1]])])
+            mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
+            psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+            rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+            psi.fill_synthetic(101)
+            rhs.fill_synthetic(202)
+            psi.fill_bc()
+            l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
+            start, count = R.slab_partition(n[-1], world, rank)
+            got = psi.get_valid_cells().reshape((count,) + tuple(reversed(n[:-1])))
+            same = np.array_equal(got, want[start:start + count])
+            norm_ok = abs(l1 - l1_ref) <= 1e-12 * abs(l1_ref)
+            total = poisson.sum(psi)
+            sum_ok = abs(total - np.abs(want).sum()) <= 1e-12 * np.abs(want).sum()
+            if not (same and norm_ok and sum_ok):
+                ok = False
+                print(f"[rank {rank}] FAIL n={n} overlap={overlap}: field={same} norm={norm_ok} ({l1} vs {l1_ref}) sum={sum_ok}",
+                      flush=True)
+            psi.close()
+            rhs.close()
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    ctx.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("dist nccl parity:", "PASS" if flag.item() == 0 else "FAIL", f"(world={world})", flush=True)
+    return int(flag.item() != 0)
+
+
+def run_gloo(rank: int, world: int, port: int, results):
+    """CPU: oracle per slab + gloo halo exchange == oracle on the whole domain."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as ora
+    from rnmf_b200 import slab_partition
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ok = True
+    for n, hi, spec, sweeps in CASES:
+        dim = len(n)
+        D = dim - 1
+        want, _ = reference(n, hi, spec, sweeps)
+        start, count = slab_partition(n[D], world, rank)
+        dx = [hi[d] / n[d] for d in range(dim)]
+        nl = list(n)
+        nl[D] = count
+        lo = [0.0] * dim
+        lo[D] = start * dx[D]
+        hil = list(hi)
+        hil[D] = lo[D] + count * dx[D]
+        g = ora.geom(nl, lo=lo, hi=hil)
+        for d in range(dim):
+            g.dx[d] = dx[d]                       # exactly the global dx (what the C ABI passes)
+        lo_spec, hi_spec = list(spec[0]), list(spec[1])
+        if rank > 0:
+            lo_spec[D] = ("halo", None)
+        if rank < world - 1:
+            hi_spec[D] = ("halo", None)
+        bc = ora.bcs(dim, [(lo_spec, hi_spec)])
+        nv_glob = int(np.prod(n))
+        per_slice = int(np.prod(n[:D]))
+        psi, rhs = ora.zeros(g), ora.zeros(g)
+        full_psi = ora.splitmix_field(nv_glob, 101).reshape(tuple(reversed(n)))
+        full_rhs = ora.splitmix_field(nv_glob, 202).reshape(tuple(reversed(n)))
+        ora.valid_view(g, psi)[0] = full_psi[start:start + count]
+        ora.valid_view(g, rhs)[0] = full_rhs[start:start + count]
+        ora.fill_bc(g, psi, bc)
+        grid = ora.as_grid(g, psi)[0]
+
+        def exchange():
+            # first/last valid slices -> neighbours' ghost slices (whole grown slices, as the library does)
+            reqs = []
+            recv_lo = torch.empty(grid[0].shape, dtype=torch.float64)
+            recv_hi = torch.empty(grid[0].shape, dtype=torch.float64)
+            if rank > 0:
+                reqs.append(dist.isend(torch.from_numpy(grid[1].copy()), rank - 1))
+                reqs.append(dist.irecv(recv_lo, rank - 1))
+            if rank < world - 1:
+                reqs.append(dist.isend(torch.from_numpy(grid[-2].copy()), rank + 1))
+                reqs.append(dist.irecv(recv_hi, rank + 1))
+            for r in reqs:
+                r.wait()
+            if rank > 0:
+                grid[0] = recv_lo.numpy()
+            if rank < world - 1:
+                grid[-1] = recv_hi.numpy()
+
+        exchange()
+        for _ in range(sweeps):
+            ora.jacobi(g, psi, rhs, bc, 1)
+            exchange()
+        got = ora.valid_view(g, psi)[0]
+        if not np.array_equal(got, want[start:start + count]):
+            ok = False
+            print(f"[gloo rank {rank}] FAIL n={n}", flush=True)
+        del per_slice
+    t = torch.tensor([0 if ok else 1])
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    if results is not None:
+        results[rank] = int(t.item())
+    return int(t.item() != 0)
+
+
+if __name__ == "__main__":
+    backend = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    if backend == "nccl":
+        sys.exit(run_nccl())
+    else:
+        sys.exit(run_gloo(int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("MASTER_PORT", "29533")), None))
