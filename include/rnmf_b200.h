@@ -191,6 +191,14 @@ int32_t rnmf_allreduce_sum(rnmf_ctx* ctx, double* inout);
 /* fill the RNMF_BC_HALO ghost planes from the neighbouring slabs (halo unpack =
  * fill_prescribed_bc analogue, dataframe.rs:280-284; pack = collect_typed_cells :273-278). */
 int32_t rnmf_halo_exchange(rnmf_frame* f);
+/* Fused compute + halo exchange over NVLink peer memory (one process per GPU, one NVSwitch box):
+ * export writes 3 CUDA IPC handles (3 x 64 bytes: the frame's two ping-pong buffers and the
+ * context's epoch flags); the caller ships them to the neighbouring ranks (rank-1 / rank+1) and
+ * attaches theirs.  Afterwards rnmf_jacobi_sweeps stores each slab's boundary planes straight
+ * into the neighbours' ghost planes from inside the sweep kernel (no NCCL call per sweep).
+ * lo handles: from rank-1 (NULL on rank 0); hi handles: from rank+1 (NULL on the last rank). */
+int32_t rnmf_frame_peer_export(rnmf_frame* f, void* handles192);
+int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo_handles192, const void* hi_handles192);
 
 /* get_h (model.rs:72-88): h = -grad(psi) by central differences into a 2-component frame. 2D. */
 int32_t rnmf_gradient_h_2d(const rnmf_frame* psi, rnmf_frame* h2);

@@ -85,6 +85,8 @@ SIGNATURES = {
     "rnmf_abs_sum_valid": (C.c_int32, [_vp, _dp]),
     "rnmf_allreduce_sum": (C.c_int32, [_vp, _dp]),
     "rnmf_halo_exchange": (C.c_int32, [_vp]),
+    "rnmf_frame_peer_export": (C.c_int32, [_vp, _vp]),
+    "rnmf_frame_peer_attach": (C.c_int32, [_vp, _vp, _vp]),
     "rnmf_gradient_h_2d": (C.c_int32, [_vp, _vp]),
     "rnmf_solve_poisson_host": (C.c_int32, [_vp, C.c_int32, _i64p, _dp, _dp, C.c_int32, _P(BcFace), _vp, _vp,
                                             C.c_int64, C.c_int32, _vp, _dp]),

@@ -116,6 +116,14 @@ struct rnmf_ctx {
     int sweep_chunk = 0;
     int overlap_halo = 1;
     ncclComm_t comm = nullptr;
+    // fused peer-memory halo: [0] written by the lo neighbour, [1] by the hi neighbour, [2] status
+    unsigned long long* d_flags = nullptr;
+    unsigned long long* peer_flag_lo = nullptr;   // lo neighbour's flags[1] (peer-mapped)
+    unsigned long long* peer_flag_hi = nullptr;   // hi neighbour's flags[0] (peer-mapped)
+    void* peer_flag_base_lo = nullptr;
+    void* peer_flag_base_hi = nullptr;
+    unsigned long long epoch = 0;                 // sweeps completed in peer mode (same on all ranks)
+    int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
     rnmf_frame* hp_rhs = nullptr;
 };
@@ -125,6 +133,10 @@ struct rnmf_frame {
     FrameGeom g;
     double* d = nullptr;                  // current buffer
     double* d2 = nullptr;                 // ping-pong partner (lazily allocated)
+    int parity = 0;                       // physical id of `d` (0 = the buffer the frame was created with)
+    int peer_attached = 0;
+    double* peer_lo[2] = { nullptr, nullptr };   // lo neighbour's physical buffers 0/1 (peer-mapped bases)
+    double* peer_hi[2] = { nullptr, nullptr };
     int distributed = 0;
     int bc_set = 0;
     int has_reflect = 0;
@@ -233,6 +245,8 @@ static int ctx_common_init(rnmf_ctx* c)
     RNMF_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
     RNMF_CUDA_TRY(cudaMalloc(&c->d_scalar, 8 * sizeof(double)));
     RNMF_CUDA_TRY(cudaMallocHost(&c->h_scalar, 8 * sizeof(double)));
+    RNMF_CUDA_TRY(cudaMalloc(&c->d_flags, 64));
+    RNMF_CUDA_TRY(cudaMemset(c->d_flags, 0, 64));
     const char* v = getenv("RNMF_SWEEP_VARIANT");
     if (v) c->sweep_variant = atoi(v);
     const char* o = getenv("RNMF_HALO_OVERLAP");
@@ -293,6 +307,9 @@ extern "C" int32_t rnmf_ctx_destroy(rnmf_ctx* c)
     if (c->hp_psi) rnmf_frame_destroy(c->hp_psi);
     if (c->hp_rhs) rnmf_frame_destroy(c->hp_rhs);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->peer_flag_base_lo) cudaIpcCloseMemHandle(c->peer_flag_base_lo);
+    if (c->peer_flag_base_hi) cudaIpcCloseMemHandle(c->peer_flag_base_hi);
+    if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_scalar) cudaFree(c->d_scalar);
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
@@ -357,6 +374,7 @@ extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* val
     RNMF_REQUIRE(c && key && value, "null argument");
     if (!strcmp(key, "sweep_variant")) { c->sweep_variant = !strcmp(value, "auto") ? 0 : atoi(value); return RNMF_OK; }
     if (!strcmp(key, "sweep_chunk")) { c->sweep_chunk = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "peer_halo")) { c->peer_halo = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "halo_overlap")) { c->overlap_halo = atoi(value); return RNMF_OK; }
     rnmf_set_error("unknown option '%s'", key);
     return RNMF_ERR_INVALID;
@@ -437,6 +455,10 @@ extern "C" int32_t rnmf_frame_destroy(rnmf_frame* f)
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->stream_halo);
+    for (int i = 0; i < 2; ++i) {
+        if (f->peer_lo[i]) cudaIpcCloseMemHandle(f->peer_lo[i]);
+        if (f->peer_hi[i]) cudaIpcCloseMemHandle(f->peer_hi[i]);
+    }
     if (f->d) cudaFree(f->d);
     if (f->d2) cudaFree(f->d2);
     for (double* p : f->prescribed_dev) if (p) cudaFree(p);
@@ -761,13 +783,39 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     a.chunk_override = c->sweep_chunk;
     a.rhs = rhs->d;
 
+    a.peer_lo_plane = nullptr;
+    a.peer_hi_plane = nullptr;
+    // fused compute + halo exchange over NVLink peer memory (3D TMA kernel): one launch per sweep,
+    // the boundary planes are stored into the neighbours' ghost planes by the sweep kernel itself
+    const bool peer = dist && psi->peer_attached && c->peer_halo && fused && sweep_supports_peer_halo(a);
+    unsigned long long* my_flag_lo = c->rank > 0 ? c->d_flags + 0 : nullptr;
+    unsigned long long* my_flag_hi = c->rank < c->nranks - 1 ? c->d_flags + 1 : nullptr;
+    int64_t n_lo_slab = 0;
+    if (peer && c->rank > 0) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank - 1, nullptr, &n_lo_slab);
+
     for (int64_t it = 0; it < n_sweeps; ++it) {
         const bool want_norm = l1_update && it == n_sweeps - 1;
         a.in = psi->d;
         a.out = psi->d2;
         a.partials = nullptr;
         long long n_part = 0;
-        if (!dist || m < 3 || !c->overlap_halo || !fused) {
+        if (peer) {
+            const int out_phys = psi->parity ^ 1;
+            c->launches += launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s);
+            a.k_begin = 0; a.k_end = m;
+            a.peer_lo_plane = c->rank > 0 ? psi->peer_lo[out_phys] + g.plane * (n_lo_slab + g.kg) : nullptr;
+            a.peer_hi_plane = c->rank < c->nranks - 1 ? psi->peer_hi[out_phys] + g.plane * (g.kg - 1) : nullptr;
+            if (want_norm) {
+                n_part = sweep_num_partials(a);
+                rc = ensure_partials(c, n_part);
+                if (rc) return rc;
+                a.partials = c->d_partials;
+            }
+            c->launches += launch_jacobi_sweep(a, s);
+            c->launches += launch_peer_signal(c->rank > 0 ? c->peer_flag_lo : nullptr,
+                                              c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr, c->epoch + 1, s);
+            c->epoch += 1;
+        } else if (!dist || m < 3 || !c->overlap_halo || !fused) {
             a.k_begin = 0; a.k_end = m;
             if (want_norm) {
                 n_part = sweep_num_partials(a);
@@ -810,12 +858,113 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, s));
         }
         double* t = psi->d; psi->d = psi->d2; psi->d2 = t;
+        psi->parity ^= 1;
     }
+    // neighbours' last sweep must have landed in this frame's ghost planes before anything else
+    // in this stream touches the frame
+    if (peer) c->launches += launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s);
     RNMF_CUDA_TRY(cudaGetLastError());
     if (l1_update) {
         RNMF_CUDA_TRY(cudaStreamSynchronize(s));
         *l1_update = c->h_scalar[0];
+        if (peer) {
+            unsigned long long st = 0;
+            RNMF_CUDA_TRY(cudaMemcpy(&st, c->d_flags + 2, 8, cudaMemcpyDeviceToHost));
+            if (st) { rnmf_set_error("peer halo handshake timed out waiting for epoch %llu", st); return RNMF_ERR_NCCL; }
+        }
     }
+    return RNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-memory halo: CUDA IPC export / attach (one process per GPU on one NVSwitch box)
+// ------------------------------------------------------------------------------------------
+static unsigned long long peer_tag(int rank, int which)
+{
+    return 0x524E4D4600000000ULL ^ ((unsigned long long)(rank + 1) << 8) ^ (unsigned long long)which;
+}
+
+static int verify_peer_tag(const void* mapped, int rank, int which)
+{
+    unsigned long long v = 0;
+    RNMF_CUDA_TRY(cudaMemcpy(&v, mapped, 8, cudaMemcpyDeviceToHost));
+    if (v != peer_tag(rank, which)) {
+        rnmf_set_error("peer attach: mapped pointer is not the base of rank %d's buffer %d (tag %llx)", rank, which, v);
+        return RNMF_ERR_CUDA;
+    }
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_peer_export(rnmf_frame* f, void* handles192)
+{
+    RNMF_REQUIRE(f && handles192, "null argument");
+    rnmf_ctx* c = f->ctx;
+    if (bind(c)) return RNMF_ERR_CUDA;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!f->d2) {
+        int rc = alloc_buffer(f->g, &f->d2, c->stream);
+        if (rc) return rc;
+        RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles192;
+    double* phys0 = f->parity == 0 ? f->d : f->d2;
+    double* phys1 = f->parity == 0 ? f->d2 : f->d;
+    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[0], phys0));
+    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[1], phys1));
+    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[2], c->d_flags));
+    // tags in the tail padding / spare flag word: attach verifies that the pointer it maps really
+    // is the base of the neighbour's buffer (guards against allocator sub-allocation offsets)
+    const unsigned long long t0 = peer_tag(c->rank, 0), t1 = peer_tag(c->rank, 1), t2 = peer_tag(c->rank, 2);
+    RNMF_CUDA_TRY(cudaMemcpy(phys0 + f->g.total + 8, &t0, 8, cudaMemcpyHostToDevice));
+    RNMF_CUDA_TRY(cudaMemcpy(phys1 + f->g.total + 8, &t1, 8, cudaMemcpyHostToDevice));
+    RNMF_CUDA_TRY(cudaMemcpy(c->d_flags + 7, &t2, 8, cudaMemcpyHostToDevice));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo192, const void* hi192)
+{
+    RNMF_REQUIRE(f, "frame is null");
+    rnmf_ctx* c = f->ctx;
+    RNMF_REQUIRE(f->distributed && c->nranks > 1, "peer halo needs a slab frame on a distributed context");
+    RNMF_REQUIRE((c->rank == 0) == (lo192 == nullptr), "lo handles must be given exactly on ranks > 0");
+    RNMF_REQUIRE((c->rank == c->nranks - 1) == (hi192 == nullptr), "hi handles must be given exactly on ranks < nranks-1");
+    RNMF_REQUIRE(f->g.dim == 3, "peer halo: 3D slab frames (the 2D path exchanges rows with NCCL)");
+    if (bind(c)) return RNMF_ERR_CUDA;
+    auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> int {
+        RNMF_CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+        return RNMF_OK;
+    };
+    if (lo192) {
+        const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)lo192;
+        for (int i = 0; i < 2; ++i) {
+            int rc = open(h[i], (void**)&f->peer_lo[i]);
+            if (!rc) rc = verify_peer_tag(f->peer_lo[i] + f->g.plane * (f->g.nglob[f->g.dim - 1] / c->nranks + 2 * f->g.kg) * f->g.ncomp + 8, c->rank - 1, i);
+            if (rc) return rc;
+        }
+        if (!c->peer_flag_base_lo) {
+            int rc = open(h[2], &c->peer_flag_base_lo);
+            if (!rc) rc = verify_peer_tag((unsigned long long*)c->peer_flag_base_lo + 7, c->rank - 1, 2);
+            if (rc) return rc;
+            c->peer_flag_lo = (unsigned long long*)c->peer_flag_base_lo + 1;    // its hi-side flag
+        }
+    }
+    if (hi192) {
+        const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)hi192;
+        int64_t n_hi = 0;
+        rnmf_slab_partition(f->g.nglob[f->g.dim - 1], c->nranks, c->rank + 1, nullptr, &n_hi);
+        for (int i = 0; i < 2; ++i) {
+            int rc = open(h[i], (void**)&f->peer_hi[i]);
+            if (!rc) rc = verify_peer_tag(f->peer_hi[i] + f->g.plane * (n_hi + 2 * f->g.kg) * f->g.ncomp + 8, c->rank + 1, i);
+            if (rc) return rc;
+        }
+        if (!c->peer_flag_base_hi) {
+            int rc = open(h[2], &c->peer_flag_base_hi);
+            if (!rc) rc = verify_peer_tag((unsigned long long*)c->peer_flag_base_hi + 7, c->rank + 1, 2);
+            if (rc) return rc;
+            c->peer_flag_hi = (unsigned long long*)c->peer_flag_base_hi + 0;    // its lo-side flag
+        }
+    }
+    f->peer_attached = 1;
     return RNMF_OK;
 }
 

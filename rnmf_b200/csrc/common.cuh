@@ -104,7 +104,16 @@ struct SweepArgs {
                              // 2D: range of valid rows
     int variant;
     int chunk_override;      // 0 = planner decides (measurement knob "sweep_chunk")
+    double* peer_lo_plane;   // fused peer-memory halo (3D TMA kernel): neighbour ghost-plane bases
+    double* peer_hi_plane;   //   for this sweep's `out` buffer, or null
 };
+bool sweep_supports_peer_halo(const SweepArgs& a);
+
+// peer-memory halo handshake (kernels_peer.cu): epoch flags live in each rank's own memory and
+// are written by the neighbours over NVLink
+int launch_peer_signal(unsigned long long* peer_flag_a, unsigned long long* peer_flag_b, unsigned long long value, cudaStream_t s);
+int launch_peer_wait(const unsigned long long* flag_a, const unsigned long long* flag_b, unsigned long long target,
+                     unsigned long long* status, cudaStream_t s);
 int sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep(const SweepArgs& a, cudaStream_t s);
 int launch_reduce_partials(const double* partials, int n, double* out_dev, cudaStream_t s);

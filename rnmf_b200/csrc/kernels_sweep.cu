@@ -291,6 +291,8 @@ int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s);
 // default (variant 0 = auto): the TMA kernel for 3D frames (measured 240 vs 203 GLUP/s at 768^3)
 static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9) || a.variant == 13); }
 
+bool sweep_supports_peer_halo(const SweepArgs& a) { return use_tma(a); }
+
 int sweep_num_partials(const SweepArgs& a)
 {
     if (use_tma(a)) return tma_sweep_num_partials(a);

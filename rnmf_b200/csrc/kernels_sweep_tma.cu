@@ -82,6 +82,11 @@ struct TmaSweepParams {
     double* partials;
     long long m_begin, m_end;
     int chunk;
+    // fused halo exchange over NVLink peer memory: base (grown cell ii=0,jj=0) of the neighbour's
+    // ghost plane that mirrors this slab's first / last valid plane, in the neighbour's `out`
+    // buffer; null on physical faces / single GPU
+    double* peer_lo_plane;
+    double* peer_hi_plane;
 };
 
 template <int TX, int TY, int NS>
@@ -217,6 +222,21 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
             double* ob = oa + 64;
             if (va1) *reinterpret_cast<double2*>(oa) = na; else if (va0) oa[0] = na.x;
             if (vb1) *reinterpret_cast<double2*>(ob) = nb; else if (vb0) ob[0] = nb.x;
+            // compute + halo "send" in one kernel: the slab's boundary planes are also stored
+            // straight into the neighbour GPU's ghost plane (peer-mapped pointer, NVLink)
+            if ((k == 0 && p.peer_lo_plane) || (k == g.n[2] - 1 && p.peer_hi_plane)) {
+                const long long inpl = g.xoff + (ia + g.ng) + pitch * (j + g.ng);
+                if (k == 0 && p.peer_lo_plane) {
+                    double* qa = p.peer_lo_plane + inpl;
+                    if (va1) *reinterpret_cast<double2*>(qa) = na; else if (va0) qa[0] = na.x;
+                    if (vb1) *reinterpret_cast<double2*>(qa + 64) = nb; else if (vb0) qa[64] = nb.x;
+                }
+                if (k == g.n[2] - 1 && p.peer_hi_plane) {
+                    double* qa = p.peer_hi_plane + inpl;
+                    if (va1) *reinterpret_cast<double2*>(qa) = na; else if (va0) qa[0] = na.x;
+                    if (vb1) *reinterpret_cast<double2*>(qa + 64) = nb; else if (vb0) qa[64] = nb.x;
+                }
+            }
             if (NORM) {
                 if (va0) acc += fabs(__dsub_rn(na.x, cur_a.x));
                 if (va1) acc += fabs(__dsub_rn(na.y, cur_a.y));
@@ -342,6 +362,7 @@ struct Launcher {
         TmaSweepParams p;
         p.g = a.g; p.out = a.out; p.in = a.in; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
         p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
+        p.peer_lo_plane = a.peer_lo_plane; p.peer_hi_plane = a.peer_hi_plane;
         static bool attr_set[2] = { false, false };
         if (a.partials) {
             if (!attr_set[1]) {

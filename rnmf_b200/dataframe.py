@@ -117,6 +117,23 @@ class CartesianDataFrame:
     def halo_exchange(self) -> None:
         _capi.check(_capi.lib().rnmf_halo_exchange(self._h))
 
+    def enable_peer_halo(self) -> None:
+        """Fused compute + halo exchange over NVLink peer memory: swap CUDA IPC handles of the
+        frame's buffers with the neighbouring ranks (through torch.distributed) and attach them.
+        Collective over all ranks; 3D slab frames."""
+        import torch.distributed as dist
+        L = _capi.lib()
+        mine = C.create_string_buffer(192)
+        _capi.check(L.rnmf_frame_peer_export(self._h, C.cast(mine, C.c_void_p)))
+        world, rank = dist.get_world_size(), dist.get_rank()
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine.raw)
+        lo = C.create_string_buffer(everyone[rank - 1], 192) if rank > 0 else None
+        hi = C.create_string_buffer(everyone[rank + 1], 192) if rank < world - 1 else None
+        _capi.check(L.rnmf_frame_peer_attach(self._h, C.cast(lo, C.c_void_p) if lo else None,
+                                             C.cast(hi, C.c_void_p) if hi else None))
+        dist.barrier()
+
     def fill_synthetic(self, seed: int) -> None:
         _capi.check(_capi.lib().rnmf_frame_fill_synthetic(self._h, seed))
 

@@ -56,8 +56,10 @@ def run_nccl():
     ctx = R.Context.from_torch_distributed()
     mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
     ok = True
-    for overlap in (1, 0):
-        ctx.set_option("halo_overlap", overlap)
+    for mode in ("peer", "nccl_overlap", "nccl_serial"):
+        ctx.set_option("halo_overlap", 0 if mode == "nccl_serial" else 1)
+        ctx.set_option("peer_halo", 1 if mode == "peer" else 0)
+        overlap = mode
         for n, hi, spec, sweeps in CASES:
             dim = len(n)
             want, l1_ref = reference(n, hi, spec, sweeps)
@@ -68,7 +70,13 @@ def run_nccl():
             psi.fill_synthetic(101)
             rhs.fill_synthetic(202)
             psi.fill_bc()
-            l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
+            if mode == "peer" and dim == 3:
+                psi.enable_peer_halo()
+                # two calls: the epoch handshake and buffer parity must carry over between calls
+                poisson.jacobi_sweeps(psi, rhs, 2)
+                l1 = poisson.jacobi_sweeps(psi, rhs, sweeps - 2, want_norm=True)
+            else:
+                l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
             start, count = R.slab_partition(n[-1], world, rank)
             got = psi.get_valid_cells().reshape((count,) + tuple(reversed(n[:-1])))
             same = np.array_equal(got, want[start:start + count])
