@@ -71,7 +71,7 @@ def parse_args():
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,clocks.mem,clocks.max.mem")
 
     def __init__(self, device_index: int):
         self.idx = device_index
@@ -108,8 +108,42 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples for i in range(4) if s[3 + i].lower().startswith("active")})
         pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        mem = sorted(float(s[7]) for s in self.samples if len(s) > 8 and s[7].replace(".", "").isdigit())
+        mem_max = [float(s[8]) for s in self.samples if len(s) > 8 and s[8].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples), "power_w_max": max(pw) if pw else None}
+                "reasons": reasons, "samples": len(self.samples), "power_w_max": max(pw) if pw else None,
+                "mem_mhz": mem[len(mem) // 2] if mem else None, "mem_max_mhz": max(mem_max) if mem_max else None}
+
+
+def copy_bandwidth_this_box():
+    """The driver's own peak recipe (MEASURED_PEAKS.json `how`) repeated on THIS box, for context:
+    torch b.copy_(a) over 1 Gi bf16 elements, read+write bytes, best of 10, CUDA events."""
+    import torch
+    n = 1 << 30
+    a = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    b = torch.empty_like(a)
+    a.zero_()
+    best = None
+    for _ in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    # the same copy back to back for ~2 s: what the box sustains once the 1 kW power cap bites
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(10, int(2000.0 / best))
+    e0.record()
+    for _ in range(reps):
+        b.copy_(a)
+    e1.record()
+    e1.synchronize()
+    sustained = 2.0 * n * 2 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n * 2 / (best * 1e-3) / 1e9, sustained
 
 
 def measured_peak():
@@ -405,6 +439,16 @@ def main():
                 "traffic": ncu_traffic(args.workload), "kernel": "jacobi sweep (fused ghost fill)",
                 "algorithmic_bytes_per_launch": BYTES_PER_LUP * main_res["local_cells"],
                 "avg_launch_ms": sweep_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
+    if rank == 0:
+        try:
+            burst, sustained = copy_bandwidth_this_box()
+            roofline["copy_gbs_this_box"] = burst
+            roofline["copy_gbs_this_box_sustained_2s"] = sustained
+            roofline["frac_of_this_box_copy"] = achieved / burst
+            roofline["frac_of_this_box_copy_sustained"] = achieved / sustained
+        except Exception as e:
+            roofline["copy_gbs_this_box"] = None
+            roofline["copy_error"] = str(e)
 
     others = {}
     if rank == 0 and world == 1 and not args.no_others:

@@ -2,17 +2,22 @@
 // (poisson.rs:80-89 as out-of-place Jacobi; fused ghost fill + update norm as in kernels_sweep.cu).
 //
 // Data movement is done entirely by TMA (cp.async.bulk.tensor, SASS UTMALDG):
-//   * a CTA owns an (TX x TY) xy-tile and marches a chunk of z-planes;
+//   * a CTA owns a (128 x TY) xy-tile and marches a chunk of z-planes;
 //   * one producer warp streams, plane by plane, the psi tile WITH its xy halo
-//     ((TX+4) x (TY+2) box: the x halo is two cells wide so the interior starts 16-byte aligned in
-//     shared memory) and the rhs tile (TX x TY box) into an NS-stage shared-memory ring, completion
-//     signalled on mbarriers (full[]); consumers hand stages back through empty[] mbarriers;
+//     ((128+4) x (TY+2) box: the x halo is two cells wide so the interior starts 16-byte aligned
+//     in shared memory) and the rhs tile (128 x TY box) into an NS-stage shared-memory ring,
+//     completion signalled on mbarriers (full[]); consumers hand stages back through empty[];
 //   * TY consumer warps (one tile row each) keep planes k-1, k, k+1 of their own cells in registers
-//     (register z-marching), read N/S neighbours and rhs from shared memory with conflict-free
-//     128-bit loads and get E/W neighbours by warp shuffles, then store psi' with 128-bit
-//     coalesced global stores.
+//     (register z-marching) and read the N/S/E/W neighbours and rhs of plane k from shared memory
+//     (conflict-free 128-bit loads for N/S/rhs/centre), then store psi' with 128-bit coalesced
+//     global stores.
 // No consumer thread ever waits on a global load, so a handful of warps per SM keeps
 // (NS-2) planes x ~18 KB x CTAs/SM of HBM traffic in flight.
+//
+// The consumer loop is unrolled NS times so that every shared-memory address is a compile-time
+// offset from two per-thread base registers, and all boundary handling (fused ghost fill, peer
+// halo stores) is reduced to a few precomputed per-thread predicates: at 1 kW the B200 power cap
+// makes instruction count a first-order cost (profiles/r1_power.md).
 //
 // Arithmetic: same explicitly rounded sequence as kernels_sweep.cu => bit-identical results.
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
@@ -25,57 +30,79 @@ namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    const uint32_t a = smem_u32(bar);
-    uint32_t ok = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!ok);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar)
 {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ double2 lds2(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds1(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
 
-__device__ __forceinline__ double upd3(const SweepCoef& c, double r, double e, double w, double n, double s,
-                                       double u, double d)
+__device__ __forceinline__ double upd3(double c0, double c1, double c2, double c3, double r, double e, double w,
+                                       double n, double s, double u, double d)
 {
-    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c.c0, r), __dmul_rn(c.c1, __dadd_rn(e, w))),
-                               __dmul_rn(c.c2, __dadd_rn(n, s))),
-                     __dmul_rn(c.c3, __dadd_rn(u, d)));
+    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(c0, r), __dmul_rn(c1, __dadd_rn(e, w))),
+                               __dmul_rn(c2, __dadd_rn(n, s))),
+                     __dmul_rn(c3, __dadd_rn(u, d)));
 }
-__device__ __forceinline__ double ghost1(const FaceBC& b, double m)
+
+// One face of the ng=1 ghost fill in branch-free form:  ghost = (neg ? -m : m) + add
+//   Dirichlet : 2v - m  == (-m) + 2v        Neumann lo: m - s == m + (-s)        Neumann hi: m + s
+// (IEEE: a - b == a + (-b) bit for bit, addition commutes), dataframe.rs:289-355.
+struct Face1 {
+    double add;
+    bool neg;
+    bool on;
+};
+__device__ __forceinline__ Face1 make_face1(const FaceBC& b, bool fuse)
 {
-    return b.mode == 1 ? __dsub_rn(b.s1, m) : (b.mode == 2 ? __dsub_rn(m, b.s1) : __dadd_rn(m, b.s1));
+    Face1 f;
+    f.on = fuse && b.mode != 0;
+    f.neg = b.mode == 1;
+    f.add = b.mode == 2 ? -b.s1 : b.s1;
+    return f;
 }
-__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double ghost1(const Face1& f, double m) { return __dadd_rn(f.neg ? -m : m, f.add); }
 
 struct TmaSweepParams {
     FrameGeom g;
     double* out;
-    const double* in;        // only for nothing but debugging; loads go through the tensor maps
     SweepCoef c;
     FaceSet faces;
     int fuse_fill;
@@ -97,39 +124,48 @@ struct TmaCfg {
     static constexpr int PSI_STAGE = (PSI_BYTES + 127) / 128 * 128;
     static constexpr int RHS_BYTES = TX * TY * 8;
     static constexpr int RHS_STAGE = (RHS_BYTES + 127) / 128 * 128;
-    static constexpr int SMEM = NS * (PSI_STAGE + RHS_STAGE) + 2 * NS * 8 + 128;
+    static constexpr int BAR_OFF = NS * (PSI_STAGE + RHS_STAGE);
+    static constexpr int SMEM = BAR_OFF + 2 * NS * 8 + 128;
     static constexpr int THREADS = 32 * TY + 32;          // TY consumer warps + 1 producer warp
 };
 
-// TX must be 128: a consumer warp covers a 128-cell row as two 64-cell halves, each lane owning
-// the pairs (2*lane, 2*lane+1) and (64+2*lane, 65+2*lane).
-// MINB: CTAs/SM the register allocation must allow (shared memory permitting)
+// store the four cells of a lane (two pairs, 64 cells apart) with the tile-edge validity masks
+__device__ __forceinline__ void store4(double* a, const double2& va, const double2& vb, bool full, bool a0, bool a1, bool b0, bool b1)
+{
+    if (full) {
+        *reinterpret_cast<double2*>(a) = va;
+        *reinterpret_cast<double2*>(a + 64) = vb;
+    } else {
+        if (a1) *reinterpret_cast<double2*>(a) = va; else if (a0) a[0] = va.x;
+        if (b1) *reinterpret_cast<double2*>(a + 64) = vb; else if (b0) a[64] = vb.x;
+    }
+}
+
+// A consumer warp covers a 128-cell row as two 64-cell halves; lane l owns the pairs
+// (2l, 2l+1) and (64+2l, 65+2l).  MINB: CTAs/SM the register allocation must allow.
 template <int TY, int NS, bool NORM, int MINB>
 __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const __grid_constant__ CUtensorMap tm_psi,
-                                                                    const __grid_constant__ CUtensorMap tm_rhs,
-                                                                    const TmaSweepParams p)
+                                                                          const __grid_constant__ CUtensorMap tm_rhs,
+                                                                          const __grid_constant__ TmaSweepParams p)
 {
     constexpr int TX = 128;
     using Cfg = TmaCfg<TX, TY, NS>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    double* psi_st = reinterpret_cast<double*>(sm);
-    double* rhs_st = reinterpret_cast<double*>(sm + NS * Cfg::PSI_STAGE);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sm + NS * (Cfg::PSI_STAGE + Cfg::RHS_STAGE));
-    uint64_t* empty = full + NS;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t psi0 = sb, rhs0 = sb + NS * Cfg::PSI_STAGE, full0 = sb + Cfg::BAR_OFF, empty0 = full0 + NS * 8;
 
-    const FrameGeom& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long i0 = (long long)blockIdx.x * TX;
     const long long j0 = (long long)blockIdx.y * TY;
     const long long k0 = p.m_begin + (long long)blockIdx.z * p.chunk;
     const long long k1 = k0 + p.chunk < p.m_end ? k0 + p.chunk : p.m_end;
-    const int n_planes = (int)(k1 - k0) + 2;              // psi planes k0-1 .. k1
+    const int n_planes = (int)(k1 - k0) + 2;              // psi planes k0-1 .. k1  (plane idx <-> stage idx % NS)
 
     if (threadIdx.x == 0) {
+#pragma unroll
         for (int s = 0; s < NS; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], TY);
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, TY);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -139,137 +175,133 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
     if (warp == TY) {
         // ------------------------------ producer warp ------------------------------
         if (lane == 0) {
-            const int cx_psi = (int)(g.xoff + g.ng + i0 - 2);
-            const int cy_psi = (int)(g.ng + j0 - 1);
-            const int cx_rhs = (int)(g.xoff + g.ng + i0);
-            const int cy_rhs = (int)(g.ng + j0);
-            for (int idx = 0; idx < n_planes; ++idx) {
-                const int s = idx % NS, use = idx / NS;
-                if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
-                const long long plane = k0 - 1 + idx;
-                const bool with_rhs = idx >= 1 && idx <= n_planes - 2;
-                mbar_arrive_expect_tx(&full[s], (uint32_t)(Cfg::PSI_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
-                const int cz = (int)(g.kg + plane);
-                tma_load_3d(reinterpret_cast<unsigned char*>(psi_st) + s * Cfg::PSI_STAGE, &tm_psi, cx_psi, cy_psi, cz, &full[s]);
-                if (with_rhs)
-                    tma_load_3d(reinterpret_cast<unsigned char*>(rhs_st) + s * Cfg::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, &full[s]);
+            const int cx_psi = (int)(p.g.xoff + p.g.ng + i0 - 2);
+            const int cy_psi = (int)(p.g.ng + j0 - 1);
+            const int cx_rhs = cx_psi + 2, cy_rhs = cy_psi + 1;
+            int cz = (int)(p.g.kg + k0 - 1);
+            uint32_t wrap = 0;
+            for (int base = 0; base < n_planes; base += NS, ++wrap) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int idx = base + s;
+                    if (idx < n_planes) {
+                        if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1);
+                        const bool with_rhs = idx >= 1 && idx <= n_planes - 2;
+                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::PSI_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
+                        tma_load_3d(psi0 + s * Cfg::PSI_STAGE, &tm_psi, cx_psi, cy_psi, cz, full0 + 8 * s);
+                        if (with_rhs) tma_load_3d(rhs0 + s * Cfg::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s);
+                        ++cz;
+                    }
+                }
             }
         }
     } else {
         // ------------------------------ consumer warps ------------------------------
-        const int ty = warp;
-        const long long j = j0 + ty;
-        const bool row_ok = j < g.n[1];
-        const long long ia = i0 + 2 * lane, ib = i0 + 64 + 2 * lane;       // first cell of the lane's two pairs
-        const bool va0 = row_ok && ia < g.n[0], va1 = row_ok && ia + 1 < g.n[0];
-        const bool vb0 = row_ok && ib < g.n[0], vb1 = row_ok && ib + 1 < g.n[0];
-        // shared-memory element offsets inside a psi stage: cell (i0+c, j0+r) <-> (r+1)*BX + c + 2
-        const int ea = (ty + 1) * Cfg::BX + 2 + 2 * lane;
-        const int eb = ea + 64;
-        const int ra = ty * TX + 2 * lane;                                 // rhs stage offsets
-        const int rb = ra + 64;
-        const long long pitch = g.pitch, plane_sz = g.plane;
-        double* __restrict__ out = p.out;
-        long long off_a = g.at(ia, j, k0, 0);
+        const long long j = j0 + warp;
+        const long long n0 = p.g.n[0], n1 = p.g.n[1], n2 = p.g.n[2];
+        const bool row_ok = j < n1;
+        const long long ia = i0 + 2 * lane, ib = ia + 64;
+        const bool va0 = row_ok && ia < n0, va1 = row_ok && ia + 1 < n0;
+        const bool vb0 = row_ok && ib < n0, vb1 = row_ok && ib + 1 < n0;
+        const bool full = vb1;                                            // all four cells valid
+        // per-thread shared-memory byte offsets: cell (i0+c, j0+r) of a psi stage is at ((r+1)*BX + c + 2)*8
+        const uint32_t pa = psi0 + (uint32_t)(((warp + 1) * Cfg::BX + 2 + 2 * lane) * 8);
+        const uint32_t ra = rhs0 + (uint32_t)((warp * TX + 2 * lane) * 8);
+        const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
+        const long long pitch = p.g.pitch, plane_sz = p.g.plane;
+        double* oa = p.out + p.g.at(ia, j, k0, 0);
 
-        auto stage_psi = [&](int idx) { return reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(psi_st) + (idx % NS) * Cfg::PSI_STAGE); };
-        auto stage_rhs = [&](int idx) { return reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(rhs_st) + (idx % NS) * Cfg::RHS_STAGE); };
+        // boundary work reduced to per-thread predicates
+        const bool fuse = p.fuse_fill != 0;
+        const Face1 fx0 = make_face1(p.faces.f[0], fuse), fx1 = make_face1(p.faces.f[1], fuse);
+        const Face1 fy0 = make_face1(p.faces.f[2], fuse), fy1 = make_face1(p.faces.f[3], fuse);
+        const bool do_xlo = fx0.on && va0 && ia == 0;
+        const long long last = n0 - 1;
+        const int xhi_sel = !fx1.on ? -1 : (va0 && ia == last) ? 0 : (va1 && ia + 1 == last) ? 1 : (vb0 && ib == last) ? 2 : (vb1 && ib + 1 == last) ? 3 : -1;
+        const bool do_ylo = fy0.on && j == 0, do_yhi = fy1.on && j == n1 - 1;
+        const bool any_xy = do_xlo || xhi_sel >= 0 || do_ylo || do_yhi;
+        // z faces / peer halo planes only concern the first and last plane of the slab
+        const bool z_lo_here = k0 == 0 && ((fuse && p.faces.f[4].mode) || p.peer_lo_plane);
+        const bool z_hi_here = k1 == n2 && ((fuse && p.faces.f[5].mode) || p.peer_hi_plane);
+        const int idx_zlo = z_lo_here ? 1 : -1, idx_zhi = z_hi_here ? n_planes - 2 : -1;
 
-        // plane k0-1: centre only
-        mbar_wait(&full[0], 0);
-        double2 below_a = lds2(stage_psi(0) + ea), below_b = lds2(stage_psi(0) + eb);
+        // plane k0-1: centre only; plane k0: centre
+        mbar_wait(full0, 0);
+        double2 below_a = lds2(pa), below_b = lds2(pa + 512);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[0]);
-        // plane k0: centre
-        mbar_wait(&full[1 % NS], (uint32_t)((1 / NS) & 1));
-        double2 cur_a = lds2(stage_psi(1) + ea), cur_b = lds2(stage_psi(1) + eb);
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8 * (1 % NS), (uint32_t)(1 / NS));
+        double2 cur_a = lds2(pa + (1 % NS) * Cfg::PSI_STAGE), cur_b = lds2(pa + (1 % NS) * Cfg::PSI_STAGE + 512);
 
-        const bool f = p.fuse_fill != 0;
-        const bool y_lo = f && j == 0 && p.faces.f[2].mode, y_hi = f && j == g.n[1] - 1 && p.faces.f[3].mode;
+        uint32_t wrap = 0;
+        for (int base = 0; base < n_planes - 1; base += NS, ++wrap) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int idx = base + s;                       // plane being updated (stage s)
+                if (idx >= 1 && idx <= n_planes - 2) {
+                    const int sn = (s + 1) % NS;                // stage of plane idx+1 (constant after unrolling)
+                    mbar_wait(full0 + 8 * sn, (wrap + (s + 1 == NS ? 1u : 0u)) & 1u);
+                    const uint32_t pn = pa + sn * Cfg::PSI_STAGE, pc = pa + s * Cfg::PSI_STAGE, pr = ra + s * Cfg::RHS_STAGE;
+                    const double2 above_a = lds2(pn), above_b = lds2(pn + 512);
+                    const double2 n_a = lds2(pc + Cfg::BX * 8), n_b = lds2(pc + Cfg::BX * 8 + 512);
+                    const double2 s_a = lds2(pc - Cfg::BX * 8), s_b = lds2(pc - Cfg::BX * 8 + 512);
+                    const double2 r_a = lds2(pr), r_b = lds2(pr + 512);
+                    // the row is contiguous in shared memory (halo | 64 cells | 64 cells | halo), so the
+                    // E/W neighbours of the pair ends are plain 8-byte loads for every lane
+                    const double w_a0 = lds1(pc - 8), e_a1 = lds1(pc + 16);
+                    const double w_b0 = lds1(pc + 512 - 8), e_b1 = lds1(pc + 512 + 16);
 
-        for (int idx = 1; idx <= n_planes - 2; ++idx, off_a += plane_sz) {
-            const long long k = k0 + idx - 1;
-            // above plane (idx+1)
-            mbar_wait(&full[(idx + 1) % NS], (uint32_t)(((idx + 1) / NS) & 1));
-            const double* pa = stage_psi(idx + 1);
-            const double2 above_a = lds2(pa + ea), above_b = lds2(pa + eb);
-            const double* pc = stage_psi(idx);
-            const double2 n_a = lds2(pc + ea + Cfg::BX), n_b = lds2(pc + eb + Cfg::BX);
-            const double2 s_a = lds2(pc + ea - Cfg::BX), s_b = lds2(pc + eb - Cfg::BX);
-            const double* pr = stage_rhs(idx);
-            const double2 r_a = lds2(pr + ra), r_b = lds2(pr + rb);
-            // E/W by shuffles; the tile-edge lanes read the halo from shared memory
-            double w_a0 = __shfl_up_sync(0xffffffffu, cur_a.y, 1);
-            double e_a1 = __shfl_down_sync(0xffffffffu, cur_a.x, 1);
-            double w_b0 = __shfl_up_sync(0xffffffffu, cur_b.y, 1);
-            double e_b1 = __shfl_down_sync(0xffffffffu, cur_b.x, 1);
-            const double b0_first = __shfl_sync(0xffffffffu, cur_b.x, 0);
-            const double a1_last = __shfl_sync(0xffffffffu, cur_a.y, 31);
-            if (lane == 0) { w_a0 = pc[ea - 1]; w_b0 = a1_last; }
-            if (lane == 31) { e_a1 = b0_first; e_b1 = pc[eb + 2]; }
+                    double2 na, nb;
+                    na.x = upd3(c0, c1, c2, c3, r_a.x, cur_a.y, w_a0, n_a.x, s_a.x, above_a.x, below_a.x);
+                    na.y = upd3(c0, c1, c2, c3, r_a.y, e_a1, cur_a.x, n_a.y, s_a.y, above_a.y, below_a.y);
+                    nb.x = upd3(c0, c1, c2, c3, r_b.x, cur_b.y, w_b0, n_b.x, s_b.x, above_b.x, below_b.x);
+                    nb.y = upd3(c0, c1, c2, c3, r_b.y, e_b1, cur_b.x, n_b.y, s_b.y, above_b.y, below_b.y);
 
-            double2 na, nb;
-            na.x = upd3(p.c, r_a.x, cur_a.y, w_a0, n_a.x, s_a.x, above_a.x, below_a.x);
-            na.y = upd3(p.c, r_a.y, e_a1, cur_a.x, n_a.y, s_a.y, above_a.y, below_a.y);
-            nb.x = upd3(p.c, r_b.x, cur_b.y, w_b0, n_b.x, s_b.x, above_b.x, below_b.x);
-            nb.y = upd3(p.c, r_b.y, e_b1, cur_b.x, n_b.y, s_b.y, above_b.y, below_b.y);
+                    // stage s is no longer needed by this warp (its centre lives on in registers)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * s);
 
-            // stage idx is no longer needed by this warp (its centre lives on in registers)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[idx % NS]);
-
-            double* oa = out + off_a;
-            double* ob = oa + 64;
-            if (va1) *reinterpret_cast<double2*>(oa) = na; else if (va0) oa[0] = na.x;
-            if (vb1) *reinterpret_cast<double2*>(ob) = nb; else if (vb0) ob[0] = nb.x;
-            // compute + halo "send" in one kernel: the slab's boundary planes are also stored
-            // straight into the neighbour GPU's ghost plane (peer-mapped pointer, NVLink)
-            if ((k == 0 && p.peer_lo_plane) || (k == g.n[2] - 1 && p.peer_hi_plane)) {
-                const long long inpl = g.xoff + (ia + g.ng) + pitch * (j + g.ng);
-                if (k == 0 && p.peer_lo_plane) {
-                    double* qa = p.peer_lo_plane + inpl;
-                    if (va1) *reinterpret_cast<double2*>(qa) = na; else if (va0) qa[0] = na.x;
-                    if (vb1) *reinterpret_cast<double2*>(qa + 64) = nb; else if (vb0) qa[64] = nb.x;
-                }
-                if (k == g.n[2] - 1 && p.peer_hi_plane) {
-                    double* qa = p.peer_hi_plane + inpl;
-                    if (va1) *reinterpret_cast<double2*>(qa) = na; else if (va0) qa[0] = na.x;
-                    if (vb1) *reinterpret_cast<double2*>(qa + 64) = nb; else if (vb0) qa[64] = nb.x;
-                }
-            }
-            if (NORM) {
-                if (va0) acc += fabs(__dsub_rn(na.x, cur_a.x));
-                if (va1) acc += fabs(__dsub_rn(na.y, cur_a.y));
-                if (vb0) acc += fabs(__dsub_rn(nb.x, cur_b.x));
-                if (vb1) acc += fabs(__dsub_rn(nb.y, cur_b.y));
-            }
-            if (f) {
-                // x faces
-                if (p.faces.f[0].mode && va0 && ia == 0) oa[-1] = ghost1(p.faces.f[0], na.x);
-                if (p.faces.f[1].mode) {
-                    const long long last = g.n[0] - 1;
-                    if (va0 && ia == last) oa[1] = ghost1(p.faces.f[1], na.x);
-                    if (va1 && ia + 1 == last) oa[2] = ghost1(p.faces.f[1], na.y);
-                    if (vb0 && ib == last) ob[1] = ghost1(p.faces.f[1], nb.x);
-                    if (vb1 && ib + 1 == last) ob[2] = ghost1(p.faces.f[1], nb.y);
-                }
-                // y and z faces: the ghost row/plane of every valid cell of this row
-                const bool z_lo = k == 0 && p.faces.f[4].mode, z_hi = k == g.n[2] - 1 && p.faces.f[5].mode;
-                if (y_lo | y_hi | z_lo | z_hi) {
-                    auto put = [&](double* base, const FaceBC& b) {
-                        if (va1) *reinterpret_cast<double2*>(base) = make_double2(ghost1(b, na.x), ghost1(b, na.y));
-                        else if (va0) base[0] = ghost1(b, na.x);
-                        if (vb1) *reinterpret_cast<double2*>(base + 64) = make_double2(ghost1(b, nb.x), ghost1(b, nb.y));
-                        else if (vb0) base[64] = ghost1(b, nb.x);
-                    };
-                    if (y_lo) put(oa - pitch, p.faces.f[2]);
-                    if (y_hi) put(oa + pitch, p.faces.f[3]);
-                    if (z_lo) put(oa - plane_sz, p.faces.f[4]);
-                    if (z_hi) put(oa + plane_sz, p.faces.f[5]);
+                    store4(oa, na, nb, full, va0, va1, vb0, vb1);
+                    if (NORM) {
+                        double t = 0.0;
+                        if (va0) t += fabs(__dsub_rn(na.x, cur_a.x));
+                        if (va1) t += fabs(__dsub_rn(na.y, cur_a.y));
+                        if (vb0) t += fabs(__dsub_rn(nb.x, cur_b.x));
+                        if (vb1) t += fabs(__dsub_rn(nb.y, cur_b.y));
+                        acc += t;
+                    }
+                    if (any_xy) {
+                        if (do_xlo) oa[-1] = ghost1(fx0, na.x);
+                        if (xhi_sel >= 0) {
+                            const double m = xhi_sel == 0 ? na.x : xhi_sel == 1 ? na.y : xhi_sel == 2 ? nb.x : nb.y;
+                            oa[(xhi_sel >= 2 ? 64 : 0) + (xhi_sel & 1) + 1] = ghost1(fx1, m);
+                        }
+                        if (do_ylo)
+                            store4(oa - pitch, make_double2(ghost1(fy0, na.x), ghost1(fy0, na.y)),
+                                   make_double2(ghost1(fy0, nb.x), ghost1(fy0, nb.y)), full, va0, va1, vb0, vb1);
+                        if (do_yhi)
+                            store4(oa + pitch, make_double2(ghost1(fy1, na.x), ghost1(fy1, na.y)),
+                                   make_double2(ghost1(fy1, nb.x), ghost1(fy1, nb.y)), full, va0, va1, vb0, vb1);
+                    }
+                    if (idx == idx_zlo || idx == idx_zhi) {
+                        for (int pass = 0; pass < 2; ++pass) {          // a 1-plane slab does both
+                            const bool is_lo = pass == 0;
+                            if (is_lo ? idx != idx_zlo : idx != idx_zhi) continue;
+                            const Face1 fz = is_lo ? make_face1(p.faces.f[4], fuse) : make_face1(p.faces.f[5], fuse);
+                            if (fz.on)
+                                store4(is_lo ? oa - plane_sz : oa + plane_sz, make_double2(ghost1(fz, na.x), ghost1(fz, na.y)),
+                                       make_double2(ghost1(fz, nb.x), ghost1(fz, nb.y)), full, va0, va1, vb0, vb1);
+                            // compute + halo "send" in one kernel: the slab's boundary plane is also stored
+                            // straight into the neighbour GPU's ghost plane (peer-mapped pointer, NVLink)
+                            double* peer = is_lo ? p.peer_lo_plane : p.peer_hi_plane;
+                            if (peer) store4(peer + p.g.xoff + (ia + p.g.ng) + pitch * (j + p.g.ng), na, nb, full, va0, va1, vb0, vb1);
+                        }
+                    }
+                    below_a = cur_a; below_b = cur_b;
+                    cur_a = above_a; cur_b = above_b;
+                    oa += plane_sz;
                 }
             }
-            below_a = cur_a; below_b = cur_b;
-            cur_a = above_a; cur_b = above_b;
         }
     }
     if (NORM) {
@@ -351,6 +383,18 @@ struct Launcher {
         grid = dim3((unsigned)bx, (unsigned)by, (unsigned)(bz > 0 ? bz : 1));
         return (int)(bx * by * bz);
     }
+    template <bool NORM>
+    static int launch_one(const dim3& grid, const CUtensorMap& tm_psi, const CUtensorMap& tm_rhs, const TmaSweepParams& p, cudaStream_t s)
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, NORM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, NORM, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr_set = true;
+        }
+        jacobi3d_tma_kernel<TY, NS, NORM, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
+        return 1;
+    }
     static int launch(const SweepArgs& a, cudaStream_t s)
     {
         dim3 grid;
@@ -360,32 +404,17 @@ struct Launcher {
         if (encode_map(&tm_psi, a.g, a.in, Cfg::BX, Cfg::BY)) return -1;
         if (encode_map(&tm_rhs, a.g, a.rhs, 128, TY)) return -1;
         TmaSweepParams p;
-        p.g = a.g; p.out = a.out; p.in = a.in; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
+        p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
         p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
         p.peer_lo_plane = a.peer_lo_plane; p.peer_hi_plane = a.peer_hi_plane;
-        static bool attr_set[2] = { false, false };
-        if (a.partials) {
-            if (!attr_set[1]) {
-                if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
-                cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, true, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                attr_set[1] = true;
-            }
-            jacobi3d_tma_kernel<TY, NS, true, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
-        } else {
-            if (!attr_set[0]) {
-                if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
-                cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, false, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                attr_set[0] = true;
-            }
-            jacobi3d_tma_kernel<TY, NS, false, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
-        }
-        return 1;
+        return a.partials ? launch_one<true>(grid, tm_psi, tm_rhs, p, s) : launch_one<false>(grid, tm_psi, tm_rhs, p, s);
     }
 };
 
 }  // namespace
 
-// variants: 0/6 = 128x8 tile, 4 stages (default); 5 = 128x8, 5 stages; 7 = 128x16, 4 stages; 8 = 128x4, 6 stages
+// variants: 0/6 = 128x8 tile, 4 stages (default); 5 = 128x8, 5 stages; 7 = 128x16, 4 stages;
+//           8 = 128x4, 6 stages; 9 = 128x8, 3 stages; 13 = 128x16, 3 stages
 int tma_sweep_num_partials(const SweepArgs& a)
 {
     dim3 grid;
