@@ -128,6 +128,8 @@ int32_t rnmf_frame_create_slab(rnmf_ctx* ctx, int32_t dim, const int64_t* n_glob
                                const double* dx, int32_t n_ghost, int32_t n_comp, rnmf_frame** out);
 int32_t rnmf_frame_destroy(rnmf_frame* f);
 int32_t rnmf_frame_info_get(const rnmf_frame* f, rnmf_frame_info* out);
+/* debug aid: every device buffer ends in a canary band; *ok = 0 if a kernel stored past the end */
+int32_t rnmf_frame_check_guards(rnmf_frame* f, int32_t* ok);
 /* the `bc: BCs<S>` field (dataframe.rs:59): n_faces must be n_comp*dim*2 */
 int32_t rnmf_frame_set_bc(rnmf_frame* f, const rnmf_bc_face* faces, int32_t n_faces);
 /* host mirror <-> device (replaces direct access to `data: Vec<S>`, dataframe.rs:37) */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "rnmf_frame_create_slab": (C.c_int32, [_vp, C.c_int32, _i64p, _dp, _dp, C.c_int32, C.c_int32, _P(_vp)]),
     "rnmf_frame_destroy": (C.c_int32, [_vp]),
     "rnmf_frame_info_get": (C.c_int32, [_vp, _P(FrameInfo)]),
+    "rnmf_frame_check_guards": (C.c_int32, [_vp, _P(C.c_int32)]),
     "rnmf_frame_set_bc": (C.c_int32, [_vp, _P(BcFace), C.c_int32]),
     "rnmf_frame_upload": (C.c_int32, [_vp, _vp]),
     "rnmf_frame_download": (C.c_int32, [_vp, _vp]),

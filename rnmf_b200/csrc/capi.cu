@@ -31,7 +31,7 @@ extern "C" int32_t rnmf_abi_version(void) { return RNMF_ABI_VERSION; }
 extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
-           "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_ymarch{128,256},"
+           "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
            "fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
@@ -149,6 +149,17 @@ struct rnmf_frame {
 namespace {
 
 constexpr long long kTailPad = 64;   // doubles; lets edge threads read a little past the last row
+constexpr long long kGuard = 256;    // doubles after the tail pad holding a canary pattern (rnmf_frame_check_guards)
+constexpr unsigned long long kCanary = 0x7FF8C0DEC0DE0000ULL;   // a quiet-NaN payload
+
+int write_guard(double* buf, const FrameGeom& g, cudaStream_t s)
+{
+    static unsigned long long pattern[kGuard];
+    static bool init = false;
+    if (!init) { for (long long i = 0; i < kGuard; ++i) pattern[i] = kCanary + (unsigned long long)i; init = true; }
+    RNMF_CUDA_TRY(cudaMemcpyAsync(buf + g.total + kTailPad, pattern, sizeof(pattern), cudaMemcpyHostToDevice, s));
+    return RNMF_OK;
+}
 
 int ensure_partials(rnmf_ctx* c, long long n)
 {
@@ -170,10 +181,10 @@ int bind(rnmf_ctx* c)
 
 int alloc_buffer(const FrameGeom& g, double** out, cudaStream_t s)
 {
-    const size_t bytes = (size_t)(g.total + kTailPad) * sizeof(double);
+    const size_t bytes = (size_t)(g.total + kTailPad + kGuard) * sizeof(double);
     RNMF_CUDA_TRY(cudaMalloc(out, bytes));
     RNMF_CUDA_TRY(cudaMemsetAsync(*out, 0, bytes, s));   // new_from zero-initialises (dataframe.rs:155)
-    return RNMF_OK;
+    return write_guard(*out, g, s);
 }
 
 void make_geom(FrameGeom& g, int dim, const int64_t* n, const double* lo, const double* dx, int ng, int ncomp)
@@ -463,6 +474,24 @@ extern "C" int32_t rnmf_frame_destroy(rnmf_frame* f)
     if (f->d2) cudaFree(f->d2);
     for (double* p : f->prescribed_dev) if (p) cudaFree(p);
     delete f;
+    return RNMF_OK;
+}
+
+// Debug aid (compute-sanitizer is not available on every pool): every buffer ends in a canary band;
+// a kernel that stores past the end of a frame destroys it.  ok = 1 when both buffers are intact.
+extern "C" int32_t rnmf_frame_check_guards(rnmf_frame* f, int32_t* ok)
+{
+    RNMF_REQUIRE(f && ok, "null argument");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
+    *ok = 1;
+    unsigned long long host[kGuard];
+    for (double* buf : { f->d, f->d2 }) {
+        if (!buf) continue;
+        RNMF_CUDA_TRY(cudaMemcpy(host, buf + f->g.total + kTailPad, sizeof(host), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < kGuard; ++i)
+            if (host[i] != kCanary + (unsigned long long)i) { *ok = 0; break; }
+    }
     return RNMF_OK;
 }
 

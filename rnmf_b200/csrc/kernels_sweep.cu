@@ -291,11 +291,17 @@ int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s);
 // default (variant 0 = auto): the TMA kernel for 3D frames (measured 240 vs 203 GLUP/s at 768^3)
 static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9) || a.variant == 13); }
 
+int tma2d_sweep_num_partials(const SweepArgs& a);
+int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s);
+// 2D default (variant 0 = auto, or 20): the TMA row-streaming kernel; variants 1/2 = jacobi2d_ymarch
+static inline bool use_tma2d(const SweepArgs& a) { return a.g.dim == 2 && (a.variant == 0 || a.variant == 20); }
+
 bool sweep_supports_peer_halo(const SweepArgs& a) { return use_tma(a); }
 
 int sweep_num_partials(const SweepArgs& a)
 {
     if (use_tma(a)) return tma_sweep_num_partials(a);
+    if (use_tma2d(a)) return tma2d_sweep_num_partials(a);
     const Plan pl = make_plan(a);
     return (int)(pl.grid.x * pl.grid.y * pl.grid.z);
 }
@@ -304,6 +310,7 @@ int launch_jacobi_sweep(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
     if (use_tma(a)) return launch_jacobi_sweep_tma(a, s);
+    if (use_tma2d(a)) return launch_jacobi_sweep_tma2d(a, s);
     const Plan pl = make_plan(a);
     SweepParams p;
     p.g = a.g; p.in = a.in; p.rhs = a.rhs; p.out = a.out; p.c = a.c; p.faces = a.faces;

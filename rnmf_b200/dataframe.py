@@ -134,6 +134,12 @@ class CartesianDataFrame:
                                              C.cast(hi, C.c_void_p) if hi else None))
         dist.barrier()
 
+    def guards_intact(self) -> bool:
+        """debug aid: False if some kernel stored past the end of one of the frame's buffers."""
+        ok = C.c_int32()
+        _capi.check(_capi.lib().rnmf_frame_check_guards(self._h, C.byref(ok)))
+        return bool(ok.value)
+
     def fill_synthetic(self, seed: int) -> None:
         _capi.check(_capi.lib().rnmf_frame_fill_synthetic(self._h, seed))
 

@@ -133,20 +133,27 @@ SWEEP_CASES_2D = [
     ([2, 3], [2.0, 3.0], MIXED_2D, 5),
     ([1, 1], [1.0, 1.0], MIXED_2D, 3),
     ([1031, 67], [1.0, 1.0], DIRICHLET_2D, 2),
+    ([1500, 300], [15.0, 3.0], MIXED_2D, 3),     # several 512-column tiles and row chunks of the TMA kernel
 ]
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_2D)
-def test_jacobi_2d_bit_exact(R, ctx, n, hi, spec, sweeps):
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_jacobi_2d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
-    g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=21)
-    ora.fill_bc(g, psi0, obc)
-    psi.fill_bc()
-    l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
-    want = psi0.copy()
-    l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
-    np.testing.assert_array_equal(psi.data, want)
-    assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+    ctx.set_option("sweep_variant", variant)
+    try:
+        g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=21)
+        ora.fill_bc(g, psi0, obc)
+        psi.fill_bc()
+        l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
+        want = psi0.copy()
+        l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
+        np.testing.assert_array_equal(psi.data, want)
+        assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+        assert psi.guards_intact() and rhs.guards_intact()
+    finally:
+        ctx.set_option("sweep_variant", "auto")
 
 
 SWEEP_CASES_3D = [
@@ -174,6 +181,7 @@ def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
         l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
         np.testing.assert_array_equal(psi.data, want)
         assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+        assert psi.guards_intact() and rhs.guards_intact()       # no store past the end of a buffer
     finally:
         ctx.set_option("sweep_variant", "auto")
 
