@@ -284,7 +284,30 @@ EncodeTiledFn get_encoder2d()
     return fn;
 }
 
+struct MapKey2 { const double* base; long long pitch, g1n; int bx; };
+struct MapSlot2 { MapKey2 k; CUtensorMap tm; bool used; };
+static MapSlot2 g_map_cache2[16];
+static int g_map_next2 = 0;
+
+int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);
+
+// cached: see kernels_sweep_tma.cu
 int encode_map2d(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx)
+{
+    const MapKey2 k = { base, g.pitch, g.G[1] * g.ncomp, bx };
+    for (auto& sl : g_map_cache2)
+        if (sl.used && sl.k.base == k.base && sl.k.pitch == k.pitch && sl.k.g1n == k.g1n && sl.k.bx == k.bx) {
+            *tm = sl.tm;
+            return 0;
+        }
+    if (encode_map2d_uncached(tm, g, base, bx)) return -1;
+    MapSlot2& sl = g_map_cache2[g_map_next2];
+    g_map_next2 = (g_map_next2 + 1) % 16;
+    sl.k = k; sl.tm = *tm; sl.used = true;
+    return 0;
+}
+
+int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx)
 {
     EncodeTiledFn enc = get_encoder2d();
     if (!enc) return -1;

@@ -336,7 +336,31 @@ EncodeTiledFn get_encoder()
     return fn;
 }
 
+// tensor maps depend only on (buffer, geometry, box): a frame ping-pongs between two buffers, so a
+// small cache removes the encoder from the per-sweep path (it matters for small, launch-bound grids)
+struct MapKey { const double* base; long long pitch, g1, g2n; int bx, by; };
+struct MapSlot { MapKey k; CUtensorMap tm; bool used; };
+static MapSlot g_map_cache[16];
+static int g_map_next = 0;
+
+int encode_map_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by);
+
 int encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by)
+{
+    const MapKey k = { base, g.pitch, g.G[1], g.G[2] * g.ncomp, bx, by };
+    for (auto& sl : g_map_cache)
+        if (sl.used && sl.k.base == k.base && sl.k.pitch == k.pitch && sl.k.g1 == k.g1 && sl.k.g2n == k.g2n && sl.k.bx == k.bx && sl.k.by == k.by) {
+            *tm = sl.tm;
+            return 0;
+        }
+    if (encode_map_uncached(tm, g, base, bx, by)) return -1;
+    MapSlot& sl = g_map_cache[g_map_next];
+    g_map_next = (g_map_next + 1) % 16;
+    sl.k = k; sl.tm = *tm; sl.used = true;
+    return 0;
+}
+
+int encode_map_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by)
 {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return -1;
