@@ -32,7 +32,7 @@ extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
            "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -124,6 +124,8 @@ struct rnmf_ctx {
     void* peer_flag_base_hi = nullptr;
     unsigned long long epoch = 0;                 // sweeps completed in peer mode (same on all ranks)
     int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
+    int resident = 1;                             // option "resident": multi-sweep cooperative kernel for L2-resident frames
+    long long resident_max_bytes = 48LL << 20;    // psi + psi' + rhs must fit comfortably in the 126 MB L2
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
     rnmf_frame* hp_rhs = nullptr;
 };
@@ -386,6 +388,7 @@ extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* val
     if (!strcmp(key, "sweep_variant")) { c->sweep_variant = !strcmp(value, "auto") ? 0 : atoi(value); return RNMF_OK; }
     if (!strcmp(key, "sweep_chunk")) { c->sweep_chunk = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "peer_halo")) { c->peer_halo = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "resident")) { c->resident = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "halo_overlap")) { c->overlap_halo = atoi(value); return RNMF_OK; }
     rnmf_set_error("unknown option '%s'", key);
     return RNMF_ERR_INVALID;
@@ -822,7 +825,20 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     int64_t n_lo_slab = 0;
     if (peer && c->rank > 0) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank - 1, nullptr, &n_lo_slab);
 
-    for (int64_t it = 0; it < n_sweeps; ++it) {
+    // small (L2-resident) frames: all sweeps but a norm-carrying last one in ONE cooperative launch
+    int64_t it0 = 0;
+    if (!dist && fused && c->resident && g.total * 8 * 3 <= c->resident_max_bytes) {
+        const int64_t nres = n_sweeps - (l1_update ? 1 : 0);
+        if (nres >= 4) {
+            int k = launch_jacobi_resident(g, psi->d, psi->d2, rhs->d, a.c, a.faces, nres, s);
+            if (k < 0) return RNMF_ERR_CUDA;
+            c->launches += k;
+            if (nres & 1) { double* t = psi->d; psi->d = psi->d2; psi->d2 = t; psi->parity ^= 1; }
+            it0 = nres;
+        }
+    }
+
+    for (int64_t it = it0; it < n_sweeps; ++it) {
         const bool want_norm = l1_update && it == n_sweeps - 1;
         a.in = psi->d;
         a.out = psi->d2;

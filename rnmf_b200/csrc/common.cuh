@@ -134,5 +134,7 @@ int launch_varcoef_2d(const FrameGeom& g, const double* phi, const rnmf_mu_param
                       int with_source, double relax, double* out, cudaStream_t s);
 int launch_gradient_h_2d(const FrameGeom& g, const double* psi, const FrameGeom& gh, double* h, cudaStream_t s);
 
+int launch_jacobi_resident(const FrameGeom& g, double* buf0, double* buf1, const double* rhs, SweepCoef c,
+                           const FaceSet& faces, long long n_sweeps, cudaStream_t s);
 int launch_gs_wavefront_2d(const FrameGeom& g, double* psi, const double* rhs, SweepCoef c,
                            const FaceSet& faces, long long n_sweeps, cudaStream_t s);

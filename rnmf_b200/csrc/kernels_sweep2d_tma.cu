@@ -8,7 +8,7 @@
 //   * four consumer warps own 128 cells each (lane l: pairs 2l,2l+1 and 64+2l,65+2l) and keep rows
 //     j-1, j, j+1 of their cells in registers: the N/S neighbours of the stencil ARE the marching
 //     direction, so shared memory only serves the next row's centre, rhs and the E/W neighbours.
-// Chunks of <= 128 rows per CTA (measured best; see plan2d).
+// Chunks of <= 64 rows per CTA (measured best; see plan2d).
 #include <cuda.h>
 
 #include <stdlib.h>
@@ -332,13 +332,14 @@ int plan2d(const SweepArgs& a, dim3& grid, int& chunk)
     const FrameGeom& g = a.g;
     const long long span = a.k_end - a.k_begin;
     const long long bx = (g.n[0] + TXC - 1) / TXC;
-    // 128-row chunks: measured best at 8192^2 (260 GLUP/s; 249 for one balanced wave of 304-row
-    // chunks, 223 for 1024 rows): several waves of short CTAs keep HBM busier than one wave of
-    // long ones, and the 2 re-read rows cost 1.6 %.  Narrow frames get shorter chunks to fill the SMs.
+    // 64-row chunks: measured best at 8192^2 (267 GLUP/s sustained; 264 / 260 / 249 / 223 for
+    // 96 / 128 / 304 / 1024 rows): many waves of short CTAs keep HBM busier than one wave of long
+    // ones although each chunk re-reads 2 rows.  Small frames get shorter chunks (>= 4 rows) so
+    // that they still spread over the SMs.
     long long rows_chunks = (148LL * 3 * 2 + bx - 1) / bx;
     long long c = (span + rows_chunks - 1) / rows_chunks;
-    if (c > 128) c = 128;
-    if (c < 32) c = 32;
+    if (c > 64) c = 64;
+    if (c < 4) c = 4;
     if (a.chunk_override > 0) c = a.chunk_override;
     if (c > span) c = span > 0 ? span : 1;
     long long by = (span + c - 1) / c;

@@ -392,13 +392,13 @@ struct Launcher {
         const long long span = a.k_end - a.k_begin;
         const long long bx = (g.n[0] + 127) / 128, by = (g.n[1] + TY - 1) / TY;
         // Short chunks keep the last partial wave short (measured at 768^3: 258 GLUP/s for 32..64
-        // planes, 244 for 192); each chunk re-reads 2 planes, so stay >= 16 unless the xy plane has
-        // too few tiles to fill the SMs otherwise.
+        // planes, 244 for 192); each chunk re-reads 2 planes.  Small frames get shorter chunks (>= 4
+        // planes) so that they still spread over the SMs.
         long long want = (148LL * 3 * 8 + bx * by - 1) / (bx * by);
         if (want < 1) want = 1;
         long long c = (span + want - 1) / want;
         if (c > 48) c = 48;
-        if (c < 16) c = 16;
+        if (c < 4) c = 4;
         if (a.chunk_override > 0) c = a.chunk_override;
         if (c > span) c = span > 0 ? span : 1;
         long long bz = (span + c - 1) / c;

@@ -142,6 +142,7 @@ SWEEP_CASES_2D = [
 def test_jacobi_2d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
+    ctx.set_option("resident", 0)          # exercise the streaming kernels themselves
     try:
         g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=21)
         ora.fill_bc(g, psi0, obc)
@@ -154,6 +155,7 @@ def test_jacobi_2d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
         assert psi.guards_intact() and rhs.guards_intact()
     finally:
         ctx.set_option("sweep_variant", "auto")
+        ctx.set_option("resident", 1)
 
 
 SWEEP_CASES_3D = [
@@ -172,6 +174,7 @@ SWEEP_CASES_3D = [
 def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
+    ctx.set_option("resident", 0)          # exercise the streaming kernels themselves
     try:
         g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=22)
         ora.fill_bc(g, psi0, obc)
@@ -184,6 +187,33 @@ def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
         assert psi.guards_intact() and rhs.guards_intact()       # no store past the end of a buffer
     finally:
         ctx.set_option("sweep_variant", "auto")
+        ctx.set_option("resident", 1)
+
+
+@pytest.mark.parametrize("n,hi,spec,sweeps", [
+    ([301, 301], [301.0, 301.0], MIXED_2D, 57), ([301, 301], [301.0, 301.0], MIXED_2D, 24),
+    ([7, 5], [7.0, 5.0], MIXED_2D, 9), ([1, 1], [1.0, 1.0], MIXED_2D, 6),
+    ([65, 33, 17], [1.0, 2.0, 3.0], MIXED_3D, 21), ([64, 64, 64], [64.0, 64.0, 64.0], MIXED_3D, 12),
+])
+def test_jacobi_resident_multi_sweep_kernel(R, ctx, n, hi, spec, sweeps):
+    """Small (L2-resident) frames run all sweeps in one cooperative launch (kernels_resident.cu);
+    with and without the norm-carrying last sweep, odd and even sweep counts."""
+    from rnmf_b200 import poisson
+    g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=24)
+    ora.fill_bc(g, psi0, obc)
+    psi.fill_bc()
+    before = ctx.kernel_launches
+    l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
+    ctx.sync()
+    assert ctx.kernel_launches - before <= 6                 # shell copy + resident + last sweep + reduce
+    want = psi0.copy()
+    l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
+    np.testing.assert_array_equal(psi.data, want)
+    assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+    poisson.jacobi_sweeps(psi, rhs, sweeps + 1)               # no norm: every sweep in the resident kernel
+    ora.jacobi(g, want, rhs0, obc, sweeps + 1)
+    np.testing.assert_array_equal(psi.data, want)
+    assert psi.guards_intact()
 
 
 def test_jacobi_two_ghost_layers_and_unfilled_ghosts(R, ctx):
@@ -390,7 +420,9 @@ def test_solve_poisson_host_entry_point(R, ctx):
 def test_kernel_launch_counter_moves(R, ctx):
     from rnmf_b200 import poisson
     g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, [32, 32, 32], [32.0] * 3, MIXED_3D, seed=91)
+    ctx.set_option("resident", 0)
     before = ctx.kernel_launches
     poisson.jacobi_sweeps(psi, rhs, 10)
     ctx.sync()
+    ctx.set_option("resident", 1)
     assert ctx.kernel_launches - before >= 10
