@@ -285,7 +285,7 @@ def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, redu
     psi.fill_synthetic(SEED_PSI)
     rhs.fill_synthetic(SEED_RHS)
     psi.fill_bc()
-    if nranks > 1 and dim == 3 and os.environ.get("RNMF_PEER_HALO", "1") != "0":
+    if nranks > 1 and os.environ.get("RNMF_PEER_HALO", "1") != "0":
         psi.enable_peer_halo()       # fused compute + halo exchange over NVLink peer memory
     coef = poisson.poisson_coefs(dim, mesh.dx)
     for _ in range(warmup):
@@ -515,7 +515,7 @@ def main():
                        "l2": "three 3.65 GB frames per GPU >> 126 MB L2: no flush needed" if args.workload == "3d7_768" else "frames >> L2",
                        "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
                        "halo": ("fused peer-memory stores from the sweep kernel (NVLink) + epoch flags" if os.environ.get("RNMF_PEER_HALO", "1") != "0"
-                                else "NCCL send/recv overlapped with the interior") if world > 1 and dim == 3 else ("NCCL send/recv" if world > 1 else "none"),
+                                else "NCCL send/recv overlapped with the interior") if world > 1 else "none",
                        "sweep_variant": args.variant or os.environ.get("RNMF_SWEEP_VARIANT", "auto")},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -197,7 +197,7 @@ int32_t rnmf_halo_exchange(rnmf_frame* f);
  * export writes 3 CUDA IPC handles (3 x 64 bytes: the frame's two ping-pong buffers and the
  * context's epoch flags); the caller ships them to the neighbouring ranks (rank-1 / rank+1) and
  * attaches theirs.  Afterwards rnmf_jacobi_sweeps stores each slab's boundary planes straight
- * into the neighbours' ghost planes from inside the sweep kernel (no NCCL call per sweep).
+ * into the neighbours' ghost planes (rows in 2D) from inside the sweep kernel (no NCCL call per sweep).
  * lo handles: from rank-1 (NULL on rank 0); hi handles: from rank+1 (NULL on the last rank). */
 int32_t rnmf_frame_peer_export(rnmf_frame* f, void* handles192);
 int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo_handles192, const void* hi_handles192);

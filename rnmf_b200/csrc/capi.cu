@@ -848,8 +848,9 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             const int out_phys = psi->parity ^ 1;
             c->launches += launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s);
             a.k_begin = 0; a.k_end = m;
-            a.peer_lo_plane = c->rank > 0 ? psi->peer_lo[out_phys] + g.plane * (n_lo_slab + g.kg) : nullptr;
-            a.peer_hi_plane = c->rank < c->nranks - 1 ? psi->peer_hi[out_phys] + g.plane * (g.kg - 1) : nullptr;
+            const long long slice = D == 2 ? g.plane : g.pitch;       // one slowest-direction slice (z-plane / y-row)
+            a.peer_lo_plane = c->rank > 0 ? psi->peer_lo[out_phys] + slice * (n_lo_slab + g.ng) : nullptr;
+            a.peer_hi_plane = c->rank < c->nranks - 1 ? psi->peer_hi[out_phys] + slice * (g.ng - 1) : nullptr;
             if (want_norm) {
                 n_part = sweep_num_partials(a);
                 rc = ensure_partials(c, n_part);
@@ -973,7 +974,12 @@ extern "C" int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo192, cons
     RNMF_REQUIRE(f->distributed && c->nranks > 1, "peer halo needs a slab frame on a distributed context");
     RNMF_REQUIRE((c->rank == 0) == (lo192 == nullptr), "lo handles must be given exactly on ranks > 0");
     RNMF_REQUIRE((c->rank == c->nranks - 1) == (hi192 == nullptr), "hi handles must be given exactly on ranks < nranks-1");
-    RNMF_REQUIRE(f->g.dim == 3, "peer halo: 3D slab frames (the 2D path exchanges rows with NCCL)");
+    // doubles in a neighbour's buffer holding n_peer slices of the slowest direction
+    auto peer_total = [&](int64_t n_peer) -> long long {
+        const FrameGeom& g = f->g;
+        const long long slice = g.dim == 3 ? g.plane : g.pitch;
+        return slice * (n_peer + 2 * g.ng) * g.ncomp;
+    };
     if (bind(c)) return RNMF_ERR_CUDA;
     auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> int {
         RNMF_CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
@@ -983,7 +989,7 @@ extern "C" int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo192, cons
         const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)lo192;
         for (int i = 0; i < 2; ++i) {
             int rc = open(h[i], (void**)&f->peer_lo[i]);
-            if (!rc) rc = verify_peer_tag(f->peer_lo[i] + f->g.plane * (f->g.nglob[f->g.dim - 1] / c->nranks + 2 * f->g.kg) * f->g.ncomp + 8, c->rank - 1, i);
+            if (!rc) rc = verify_peer_tag(f->peer_lo[i] + peer_total(f->g.nglob[f->g.dim - 1] / c->nranks) + 8, c->rank - 1, i);
             if (rc) return rc;
         }
         if (!c->peer_flag_base_lo) {
@@ -999,7 +1005,7 @@ extern "C" int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo192, cons
         rnmf_slab_partition(f->g.nglob[f->g.dim - 1], c->nranks, c->rank + 1, nullptr, &n_hi);
         for (int i = 0; i < 2; ++i) {
             int rc = open(h[i], (void**)&f->peer_hi[i]);
-            if (!rc) rc = verify_peer_tag(f->peer_hi[i] + f->g.plane * (n_hi + 2 * f->g.kg) * f->g.ncomp + 8, c->rank + 1, i);
+            if (!rc) rc = verify_peer_tag(f->peer_hi[i] + peer_total(n_hi) + 8, c->rank + 1, i);
             if (rc) return rc;
         }
         if (!c->peer_flag_base_hi) {

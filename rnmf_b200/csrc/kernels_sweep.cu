@@ -296,7 +296,7 @@ int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s);
 // 2D default (variant 0 = auto, or 20): the TMA row-streaming kernel; variants 1/2 = jacobi2d_ymarch
 static inline bool use_tma2d(const SweepArgs& a) { return a.g.dim == 2 && (a.variant == 0 || a.variant == 20); }
 
-bool sweep_supports_peer_halo(const SweepArgs& a) { return use_tma(a); }
+bool sweep_supports_peer_halo(const SweepArgs& a) { return use_tma(a) || use_tma2d(a); }
 
 int sweep_num_partials(const SweepArgs& a)
 {

@@ -100,6 +100,10 @@ struct Tma2dParams {
     double* partials;
     long long m_begin, m_end;   // valid rows to update
     int chunk;
+    // fused halo exchange over NVLink peer memory (y-slabs): base (grown cell ii=0) of the
+    // neighbour's ghost row mirroring this slab's first / last valid row, in its `out` buffer
+    double* peer_lo_row;
+    double* peer_hi_row;
 };
 
 constexpr int NW = 4;                                  // consumer warps: 128 columns each
@@ -188,8 +192,9 @@ __global__ void __launch_bounds__(32 * NW + 32, 3) jacobi2d_tma_kernel(const __g
         const long long last = n0 - 1;
         const int xhi_sel = !fx1.on ? -1 : (va0 && ia == last) ? 0 : (va1 && ia + 1 == last) ? 1 : (vb0 && ib == last) ? 2 : (vb1 && ib + 1 == last) ? 3 : -1;
         const bool any_x = do_xlo || xhi_sel >= 0;
-        const int idx_ylo = (j0 == 0 && fuse && p.faces.f[2].mode) ? 1 : -1;
-        const int idx_yhi = (j1 == n1 && fuse && p.faces.f[3].mode) ? n_rows - 2 : -1;
+        const int idx_ylo = (j0 == 0 && ((fuse && p.faces.f[2].mode) || p.peer_lo_row)) ? 1 : -1;
+        const int idx_yhi = (j1 == n1 && ((fuse && p.faces.f[3].mode) || p.peer_hi_row)) ? n_rows - 2 : -1;
+        const long long in_row = p.g.xoff + (ia + p.g.ng);
 
         mbar_wait(full0, 0);
         double2 below_a = lds2(pa), below_b = lds2(pa + 512);
@@ -237,13 +242,18 @@ __global__ void __launch_bounds__(32 * NW + 32, 3) jacobi2d_tma_kernel(const __g
                     }
                     if (idx == idx_ylo) {
                         const Face1 fy = make_face1(p.faces.f[2], fuse);
-                        store4(oa - pitch, make_double2(ghost1(fy, na.x), ghost1(fy, na.y)),
-                               make_double2(ghost1(fy, nb.x), ghost1(fy, nb.y)), full, va0, va1, vb0, vb1);
+                        if (fy.on)
+                            store4(oa - pitch, make_double2(ghost1(fy, na.x), ghost1(fy, na.y)),
+                                   make_double2(ghost1(fy, nb.x), ghost1(fy, nb.y)), full, va0, va1, vb0, vb1);
+                        // compute + halo "send" in one kernel: boundary row stored into the neighbour GPU's ghost row
+                        if (p.peer_lo_row) store4(p.peer_lo_row + in_row, na, nb, full, va0, va1, vb0, vb1);
                     }
                     if (idx == idx_yhi) {
                         const Face1 fy = make_face1(p.faces.f[3], fuse);
-                        store4(oa + pitch, make_double2(ghost1(fy, na.x), ghost1(fy, na.y)),
-                               make_double2(ghost1(fy, nb.x), ghost1(fy, nb.y)), full, va0, va1, vb0, vb1);
+                        if (fy.on)
+                            store4(oa + pitch, make_double2(ghost1(fy, na.x), ghost1(fy, na.y)),
+                                   make_double2(ghost1(fy, nb.x), ghost1(fy, nb.y)), full, va0, va1, vb0, vb1);
+                        if (p.peer_hi_row) store4(p.peer_hi_row + in_row, na, nb, full, va0, va1, vb0, vb1);
                     }
                     below_a = cur_a; below_b = cur_b;
                     cur_a = above_a; cur_b = above_b;
@@ -385,6 +395,7 @@ int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s)
     Tma2dParams p;
     p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
     p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
+    p.peer_lo_row = a.peer_lo_plane; p.peer_hi_row = a.peer_hi_plane;
     return a.partials ? launch2d_one<true>(grid, tm_psi256, tm_psi4, tm_rhs256, p, s)
                       : launch2d_one<false>(grid, tm_psi256, tm_psi4, tm_rhs256, p, s);
 }

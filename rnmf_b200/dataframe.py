@@ -120,7 +120,7 @@ class CartesianDataFrame:
     def enable_peer_halo(self) -> None:
         """Fused compute + halo exchange over NVLink peer memory: swap CUDA IPC handles of the
         frame's buffers with the neighbouring ranks (through torch.distributed) and attach them.
-        Collective over all ranks; 3D slab frames."""
+        Collective over all ranks; slab frames (z-slabs in 3D, y-slabs in 2D)."""
         import torch.distributed as dist
         L = _capi.lib()
         mine = C.create_string_buffer(192)

@@ -70,7 +70,7 @@ def run_nccl():
             psi.fill_synthetic(101)
             rhs.fill_synthetic(202)
             psi.fill_bc()
-            if mode == "peer" and dim == 3:
+            if mode == "peer":
                 psi.enable_peer_halo()
                 # two calls: the epoch handshake and buffer parity must carry over between calls
                 poisson.jacobi_sweeps(psi, rhs, 2)
