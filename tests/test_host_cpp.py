@@ -28,7 +28,7 @@ def _dump(host_bins, path):
 
 
 def test_lua_reader_shipped_case(host_bins):
-    rc, cfg = _dump(host_bins, os.path.join(ROOT, "cases", "magnetostatics.lua"))
+    rc, cfg = _dump(host_bins, os.path.join(ROOT, "cases", "ferro_droplet.lua"))
     assert rc == 0
     # values of examples/magnetostatics/magnetostatics.lua:1-16, arithmetic evaluated as Lua does (IEEE double)
     assert cfg == {"dim": 2, "length": [301.0, 301.0], "n_cells": [301, 301], "residual_iters": 1,
@@ -110,11 +110,11 @@ def test_example_small_case_matches_oracle(host_bins, tmp_path):
 def test_example_shipped_lua_case(host_bins):
     with open(os.path.join(ROOT, "tests", "golden", "magnetostatics_trace.json")) as fh:
         gold = json.load(fh)
-    res, out = _run_example(host_bins, os.path.join(ROOT, "cases", "magnetostatics.lua"), "--no-vtk")
+    res, out = _run_example(host_bins, os.path.join(ROOT, "cases", "ferro_droplet.lua"), "--no-vtk")
     assert res["iters"] == gold["iters"]
     for a, b in zip(res["sum_diff"], gold["sum_diff"]):
         assert abs(a - b) <= 1e-12 * b
     assert res["psi_centre"] == gold["psi_150_150"]
     # the throughput (Jacobi) order runs the same case; different update order => different numbers, same scale
-    res_j, _ = _run_example(host_bins, os.path.join(ROOT, "cases", "magnetostatics.lua"), "--no-vtk", "--order", "jacobi")
+    res_j, _ = _run_example(host_bins, os.path.join(ROOT, "cases", "ferro_droplet.lua"), "--no-vtk", "--order", "jacobi")
     assert res_j["iters"] == 10 and 0.2 < res_j["sum_diff"][-1] / gold["sum_diff"][-1] < 5.0
