@@ -124,6 +124,8 @@ struct rnmf_ctx {
     void* peer_flag_base_hi = nullptr;
     unsigned long long epoch = 0;                 // sweeps completed in peer mode (same on all ranks)
     int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
+    double* d_staging = nullptr;                  // dense staging for large uploads (1-D PCIe copy + device repack)
+    long long staging_cap = 0;                    // doubles
     int resident = 1;                             // option "resident": multi-sweep cooperative kernel for L2-resident frames
     long long resident_max_bytes = 48LL << 20;    // psi + psi' + rhs must fit comfortably in the 126 MB L2
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
@@ -324,6 +326,7 @@ extern "C" int32_t rnmf_ctx_destroy(rnmf_ctx* c)
     if (c->peer_flag_base_hi) cudaIpcCloseMemHandle(c->peer_flag_base_hi);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_staging) cudaFree(c->d_staging);
     if (c->d_scalar) cudaFree(c->d_scalar);
     if (c->h_scalar) cudaFreeHost(c->h_scalar);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -558,8 +561,24 @@ extern "C" int32_t rnmf_frame_upload(rnmf_frame* f, const double* host)
     if (bind(f->ctx)) return RNMF_ERR_CUDA;
     const FrameGeom& g = f->g;
     const size_t rows = (size_t)(g.G[1] * g.G[2] * g.ncomp);
+    rnmf_ctx* c = f->ctx;
+    const long long dense = g.G[0] * (long long)rows;
+    if (dense * 8 >= (64LL << 20)) {
+        // Large frames: a pitched 2-D PCIe copy runs at ~37 GB/s on this platform, a 1-D one at ~55
+        // (scripts/h2d_probe.py), so stage the dense host frame 1-D and repack on the device
+        // (HBM speed, ~1 ms for 768^3).
+        if (c->staging_cap < dense) {
+            if (c->d_staging) { RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream)); RNMF_CUDA_TRY(cudaFree(c->d_staging)); c->d_staging = nullptr; c->staging_cap = 0; }
+            RNMF_CUDA_TRY(cudaMalloc(&c->d_staging, (size_t)dense * 8));
+            c->staging_cap = dense;
+        }
+        RNMF_CUDA_TRY(cudaMemcpyAsync(c->d_staging, host, (size_t)dense * 8, cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_unpack_dense(g, c->d_staging, f->d, c->stream);
+        RNMF_CUDA_TRY(cudaGetLastError());
+        return RNMF_OK;
+    }
     RNMF_CUDA_TRY(cudaMemcpy2DAsync(f->d + g.xoff, (size_t)g.pitch * 8, host, (size_t)g.G[0] * 8, (size_t)g.G[0] * 8, rows,
-                                    cudaMemcpyHostToDevice, f->ctx->stream));
+                                    cudaMemcpyHostToDevice, c->stream));
     return RNMF_OK;
 }
 

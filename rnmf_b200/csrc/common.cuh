@@ -127,6 +127,7 @@ int launch_add(long long n, const double* x, const double* y, double* out, cudaS
 int launch_mul(long long n, const double* x, const double* y, double* out, cudaStream_t s);
 int launch_axpby(long long n, double a, const double* x, double b, const double* y, double* out, cudaStream_t s);
 int launch_fill_synthetic(const FrameGeom& g, double* d, unsigned long long seed, cudaStream_t s);
+int launch_unpack_dense(const FrameGeom& g, const double* dense, double* frame, cudaStream_t s);
 int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s);
 int launch_unpack_valid(const FrameGeom& g, const double* packed, double* d, cudaStream_t s);
 

@@ -81,6 +81,17 @@ __global__ void __launch_bounds__(256) pack_valid_kernel(FrameGeom g, double* __
     }
 }
 
+// ---- dense (reference layout, G0 doubles per row) -> pitched frame, all grown rows -----------
+__global__ void __launch_bounds__(256) unpack_dense_kernel(FrameGeom g, const double* __restrict__ dense, double* __restrict__ frame)
+{
+    const long long rows = g.G[1] * g.G[2] * g.ncomp;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* src = dense + r * g.G[0];
+        double* dst = frame + g.xoff + g.pitch * r;
+        for (long long i = threadIdx.x; i < g.G[0]; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
 // ---- K5: sum |v| over valid cells (poisson.rs:94-100), deterministic two-stage tree ---------
 constexpr int kSumThreads = 256;
 __global__ void __launch_bounds__(kSumThreads) abs_sum_valid_kernel(FrameGeom g, const double* __restrict__ d,
@@ -224,6 +235,11 @@ static unsigned row_blocks(long long rows)
 int launch_fill_synthetic(const FrameGeom& g, double* d, unsigned long long seed, cudaStream_t s)
 {
     fill_synthetic_kernel<<<row_blocks(g.n[1] * g.n[2] * g.ncomp), 256, 0, s>>>(g, d, seed);
+    return 1;
+}
+int launch_unpack_dense(const FrameGeom& g, const double* dense, double* frame, cudaStream_t s)
+{
+    unpack_dense_kernel<<<row_blocks(g.G[1] * g.G[2] * g.ncomp), 256, 0, s>>>(g, dense, frame);
     return 1;
 }
 int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s)

@@ -498,3 +498,62 @@ def test_full_size_properties(R, ctx, n, spec):
         assert all(f.guards_intact() for f in (a, b, s))
     finally:
         ctx.set_option("sweep_variant", "auto")
+
+
+# ---- error behaviour of the C ABI (the Rust shim turns these into panics) ------------------------
+def test_error_paths(R, ctx):
+    from rnmf_b200 import _capi, poisson
+    L = _capi.lib()
+    mesh2 = R.CartesianMesh.new([0.0, 0.0], [8.0, 8.0], [8, 8])
+    mesh2b = R.CartesianMesh.new([0.0, 0.0], [8.0, 8.0], [8, 9])
+    _, bc = _bc_pair(R, 2, MIXED_2D)
+    a = R.CartesianDataFrame.new_from(mesh2, bc, 1, 1, ctx)
+    b = R.CartesianDataFrame.new_from(mesh2b, bc, 1, 1, ctx)
+    nobc = R.CartesianDataFrame.new_from(mesh2, R.BCs.empty(), 1, 1, ctx)
+    two = R.CartesianDataFrame.new_from(mesh2, R.BCs([bc.bcs[0], bc.bcs[0]]), 2, 1, ctx)
+    coef = (C.c_double * 4)(0.25, 0.25, 0.25, 0.0)
+
+    def code(fn, *args):
+        rc = fn(*args)
+        assert rc != 0 and len(L.rnmf_last_error()) > 0
+        return rc
+
+    assert code(L.rnmf_jacobi_sweeps, a._h, b._h, coef, 1, None) == _capi.ERR_INVALID        # shape mismatch
+    assert code(L.rnmf_jacobi_sweeps, nobc._h, a._h, coef, 1, None) == _capi.ERR_INVALID     # BCs::empty(): the reference would panic
+    assert code(L.rnmf_jacobi_sweeps, two._h, two._h, coef, 1, None) == _capi.ERR_INVALID    # sweeps are for n_comp = 1
+    assert code(L.rnmf_jacobi_sweeps, a._h, a._h, coef, -1, None) == _capi.ERR_INVALID
+    assert code(L.rnmf_add, a._h, a._h, b._h) == _capi.ERR_INVALID
+    assert code(L.rnmf_fill_bc, nobc._h) == _capi.ERR_INVALID
+    assert code(L.rnmf_frame_set_bc, a._h, None, 4) == _capi.ERR_INVALID
+    h = C.c_void_p()
+    n = (C.c_int64 * 3)(4, 4, 1)
+    lo = (C.c_double * 3)(0, 0, 0)
+    dx = (C.c_double * 3)(1, 1, 1)
+    assert code(L.rnmf_frame_create, ctx._h, 4, n, lo, dx, 1, 1, C.byref(h)) == _capi.ERR_INVALID     # dim
+    assert code(L.rnmf_frame_create, ctx._h, 2, n, lo, dx, 0, 1, C.byref(h)) == _capi.ERR_INVALID     # n_ghost
+    assert code(L.rnmf_frame_create, ctx._h, 2, n, lo, dx, 1, 0, C.byref(h)) == _capi.ERR_INVALID     # n_comp
+    # reference-order GS: 2D, one ghost layer, Dirichlet/Neumann everywhere
+    mesh3 = R.CartesianMesh.new([0.0] * 3, [4.0] * 3, [4, 4, 4])
+    _, bc3 = _bc_pair(R, 3, MIXED_3D)
+    f3 = R.CartesianDataFrame.new_from(mesh3, bc3, 1, 1, ctx)
+    assert code(L.rnmf_gs_sweeps, f3._h, f3._h, coef, 1) == _capi.ERR_INVALID
+    _, bcp = _bc_pair(R, 2, ([("prescribed", [1.0, 2.0]), ("dirichlet", 0.0)], [("dirichlet", 0.0)] * 2))
+    fp = R.CartesianDataFrame.new_from(mesh2, bcp, 1, 1, ctx)
+    assert code(L.rnmf_gs_sweeps, fp._h, a._h, coef, 1) == _capi.ERR_INVALID
+    # after the errors the context still works
+    assert poisson.jacobi_sweeps(a, a.clone(), 2, want_norm=True) >= 0.0
+
+
+def test_large_upload_uses_staged_path_and_roundtrips(R, ctx):
+    """Frames >= 64 MB are uploaded as one 1-D copy into a staging buffer and repacked on the device;
+    the round trip through the pitched layout must be exact (odd sizes, 2 ghost layers, 2 components)."""
+    n, ng, ncomp = [2051, 1001], 2, 2
+    g = ora.geom(n, ng=ng, ncomp=ncomp)
+    assert g.n_nodes * 8 >= 64 << 20
+    mesh = R.CartesianMesh.new([0.0, 0.0], [1.0, 1.0], n)
+    f = R.CartesianDataFrame.new_from(mesh, R.BCs.empty(), ncomp, ng, ctx)
+    host = np.random.default_rng(3).standard_normal(g.n_nodes)
+    f.data = host
+    np.testing.assert_array_equal(f.data, host)
+    np.testing.assert_array_equal(f.get_valid_cells(), ora.valid_view(g, host).reshape(-1))
+    assert f.guards_intact()

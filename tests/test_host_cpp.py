@@ -118,3 +118,30 @@ def test_example_shipped_lua_case(host_bins):
     # the throughput (Jacobi) order runs the same case; different update order => different numbers, same scale
     res_j, _ = _run_example(host_bins, os.path.join(ROOT, "cases", "ferro_droplet.lua"), "--no-vtk", "--order", "jacobi")
     assert res_j["iters"] == 10 and 0.2 < res_j["sum_diff"][-1] / gold["sum_diff"][-1] < 5.0
+
+
+@pytest.mark.gpu
+def test_solver_stage_drives_gpu_sweeps(host_bins):
+    """solver.rs's Stage/Step/GlobalStop shape around the device sweep: stop when the L1 update norm
+    (fused in the sweep kernel, read back only every check_every iterations) drops below tol.  The
+    oracle iterated the same way must stop at the same iteration with the same field."""
+    from oracle import oracle as ora
+    n, max_iters, every, tol = 48, 4000, 25, 1.0
+    r = subprocess.run([os.path.join(host_bins, "stage_gpu"), str(n), str(max_iters), str(every), str(tol)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    g = ora.geom([n, n], hi=[1.0, 1.0])
+    bc = ora.bcs(2, [([("dirichlet", 0.0), ("dirichlet", 0.0)], [("dirichlet", 1.0), ("dirichlet", 1.0)])])
+    psi, rhs = ora.zeros(g), ora.zeros(g)
+    ora.fill_ic(g, rhs, lambda x, y, c: 8.0 * x * (1.0 - y))
+    ora.fill_bc(g, psi, bc)
+    it, norm = 0, np.inf
+    while it < max_iters:
+        norm = ora.jacobi(g, psi, rhs, bc, every)      # norm of the last of `every` sweeps
+        it += every
+        if norm < tol:
+            break
+    assert res["iterations"] == it and it < max_iters
+    assert abs(res["norm"] - norm) <= 1e-12 * norm
+    assert res["psi_mid"] == ora.as_grid(g, psi)[0, n // 2 + 1, n // 2 + 1]
