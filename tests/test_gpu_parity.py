@@ -547,7 +547,7 @@ def test_error_paths(R, ctx):
 def test_large_upload_uses_staged_path_and_roundtrips(R, ctx):
     """Frames >= 64 MB are uploaded as one 1-D copy into a staging buffer and repacked on the device;
     the round trip through the pitched layout must be exact (odd sizes, 2 ghost layers, 2 components)."""
-    n, ng, ncomp = [2051, 1001], 2, 2
+    n, ng, ncomp = [2051, 2101], 2, 2
     g = ora.geom(n, ng=ng, ncomp=ncomp)
     assert g.n_nodes * 8 >= 64 << 20
     mesh = R.CartesianMesh.new([0.0, 0.0], [1.0, 1.0], n)
