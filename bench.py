@@ -367,6 +367,64 @@ def run_e2e(R, ctx, workload, sub_iters, steps):
             L.rnmf_host_free(p)
 
 
+def run_e2e_dist(R, ctx, workload, nranks, sub_iters, steps, barrier, reduce_max, reduce_sum):
+    import ctypes as C
+    import numpy as np
+    from rnmf_b200 import _capi, poisson
+    w = WORKLOADS[workload]
+    n = global_shape(workload, nranks)
+    dim = len(n)
+    L = _capi.lib()
+    mesh = R.CartesianMesh.new([0.0] * dim, [float(v) for v in n], n)
+    bc = make_bcs(R, w["bc"])
+    psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+    rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+    if os.environ.get("RNMF_PEER_HALO", "1") != "0":
+        psi.enable_peer_halo()
+    count = psi.n_nodes                               # this rank's dense grown slab
+    nbytes = count * 8
+    bufs = []
+    for _ in range(3):
+        p = C.c_void_p()
+        _capi.check(L.rnmf_host_alloc(nbytes, C.byref(p)))
+        bufs.append(p)
+    try:
+        arrs = [np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(count,)) for p in bufs]
+        row = int(psi.n_grown[0] * psi.n_grown[1])
+        blk = np.random.default_rng(7 + ctx.rank).standard_normal(row)
+        arrs[0].reshape(-1, row)[:] = blk
+        arrs[1].reshape(-1, row)[:] = blk[::-1]
+        coef = poisson.poisson_coefs(dim, mesh.dx)
+
+        def call():
+            _capi.check(L.rnmf_frame_upload(psi._h, bufs[0]))
+            _capi.check(L.rnmf_frame_upload(rhs._h, bufs[1]))
+            l1 = poisson.jacobi_sweeps(psi, rhs, sub_iters, want_norm=True, coef=coef)
+            _capi.check(L.rnmf_frame_download(psi._h, bufs[2]))
+            return l1
+        call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        ctx.sync()
+        barrier()
+        secs = reduce_max(time.perf_counter() - t0)
+        cells = 1
+        for v in n:
+            cells *= v
+        return {"value": cells * sub_iters * steps / secs / 1e9, "unit": "GLUP/s",
+                "h2d_bytes_per_step": int(reduce_sum(2.0 * nbytes)), "d2h_bytes_per_step": int(reduce_sum(nbytes + 8.0)),
+                "ms_per_step": 1e3 * secs / steps, "steps": steps,
+                "call": "per rank: rnmf_frame_upload(psi slab), rnmf_frame_upload(rhs slab) from pinned host frames (dense reference "
+                        f"layout) -> {sub_iters} halo-coupled sweeps(+fill_bc) + all-reduced L1 norm -> rnmf_frame_download(psi slab)"}
+    finally:
+        for p in bufs:
+            L.rnmf_host_free(p)
+        psi.close()
+        rhs.close()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -466,24 +524,11 @@ def main():
     if rank == 0 and not args.no_e2e:
         if world == 1:
             e2e = run_e2e(R, ctx, args.workload, args.sub_iters, max(1, args.e2e_steps))
-    if world > 1:
-        # multi-GPU end-to-end: every rank moves its own slab; measured on rank-local calls and reduced
-        if not args.no_e2e and w["scaling"] == "weak":
-            wl = args.workload
-            barrier()
-            local_e2e = run_e2e(R, ctx_single(R, local), wl, args.sub_iters, max(1, args.e2e_steps))
-            barrier()
-            if local_e2e is not None:
-                slow_ms = reduce_max(local_e2e["ms_per_step"])
-                cells = 1
-                for v in WORKLOADS[wl]["n"]:
-                    cells *= v
-                e2e = dict(local_e2e)
-                e2e["ms_per_step"] = slow_ms
-                e2e["value"] = world * cells * args.sub_iters / (slow_ms * 1e-3) / 1e9
-                e2e["h2d_bytes_per_step"] *= world
-                e2e["d2h_bytes_per_step"] *= world
-                e2e["call"] += " (each rank solves its own 768^3 host frame concurrently: replicas of the host-buffer call; the halo-coupled device path is `value`)"
+    if world > 1 and not args.no_e2e:
+        # multi-GPU end-to-end through the data-frame API: every rank uploads ITS SLAB of the global
+        # host frames (pinned, dense reference layout), the ranks run the halo-coupled sweeps together,
+        # every rank downloads its slab of the result.  Timed region = barrier .. barrier, max over ranks.
+        e2e = run_e2e_dist(R, ctx, args.workload, world, args.sub_iters, max(1, args.e2e_steps), barrier, reduce_max, reduce_sum)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -530,15 +575,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-
-
-_single = {}
-
-
-def ctx_single(R, local):
-    if local not in _single:
-        _single[local] = R.Context(local)
-    return _single[local]
 
 
 if __name__ == "__main__":
