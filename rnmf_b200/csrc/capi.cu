@@ -17,6 +17,7 @@
 // errors
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+static thread_local unsigned g_err_seq = 0;     // bumped by every rnmf_set_error (lets callers add context only when needed)
 
 void rnmf_set_error(const char* fmt, ...)
 {
@@ -24,6 +25,7 @@ void rnmf_set_error(const char* fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+    ++g_err_seq;
 }
 
 extern "C" const char* rnmf_last_error(void) { return g_err; }
@@ -86,6 +88,18 @@ int nccl_load()
     return RNMF_OK;
 }
 }  // namespace
+
+// a kernel launcher returns the number of kernels it launched, or < 0 (message already set)
+#define RNMF_LAUNCH(ctx, expr)                                                               \
+    do {                                                                                     \
+        const unsigned _seq = g_err_seq;                                                     \
+        int _k = (expr);                                                                     \
+        if (_k < 0) {                                                                        \
+            if (_seq == g_err_seq) rnmf_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(cudaGetLastError())); \
+            return RNMF_ERR_CUDA;                                                            \
+        }                                                                                    \
+        (ctx)->launches += _k;                                                               \
+    } while (0)
 
 #define RNMF_NCCL_TRY(expr)                                                                  \
     do {                                                                                     \
@@ -573,7 +587,7 @@ extern "C" int32_t rnmf_frame_upload(rnmf_frame* f, const double* host)
             c->staging_cap = dense;
         }
         RNMF_CUDA_TRY(cudaMemcpyAsync(c->d_staging, host, (size_t)dense * 8, cudaMemcpyHostToDevice, c->stream));
-        c->launches += launch_unpack_dense(g, c->d_staging, f->d, c->stream);
+        RNMF_LAUNCH(c, launch_unpack_dense(g, c->d_staging, f->d, c->stream));
         RNMF_CUDA_TRY(cudaGetLastError());
         return RNMF_OK;
     }
@@ -652,7 +666,7 @@ extern "C" int32_t rnmf_frame_fill_synthetic(rnmf_frame* f, uint64_t seed)
     RNMF_REQUIRE(f, "frame is null");
     if (bind(f->ctx)) return RNMF_ERR_CUDA;
     RNMF_CUDA_TRY(cudaMemsetAsync(f->d, 0, (size_t)f->g.total * 8, f->ctx->stream));
-    f->ctx->launches += launch_fill_synthetic(f->g, f->d, seed, f->ctx->stream);
+    RNMF_LAUNCH(f->ctx, launch_fill_synthetic(f->g, f->d, seed, f->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
@@ -684,7 +698,7 @@ static int fill_bc_on(rnmf_frame* f, double* buf, cudaStream_t s)
             for (int side = 0; side < 2; ++side) {
                 const int idx = (c * g.dim + d) * 2 + side;
                 if (f->raw[idx].kind == RNMF_BC_PRESCRIBED && f->prescribed_n[idx] > 0)
-                    f->ctx->launches += launch_fill_prescribed(g, buf, c, d, side, f->prescribed_dev[idx], f->prescribed_n[idx], s);
+                    RNMF_LAUNCH(f->ctx, launch_fill_prescribed(g, buf, c, d, side, f->prescribed_dev[idx], f->prescribed_n[idx], s));
             }
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
@@ -814,7 +828,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     }
     // cells no sweep/fill ever writes (edges, corners; all ghosts for ng>1 until the fill) must
     // agree in both buffers: the reference's in-place frame keeps them untouched.
-    c->launches += launch_copy_ghost_shell(g, psi->d, psi->d2, s);
+    RNMF_LAUNCH(c, launch_copy_ghost_shell(g, psi->d, psi->d2, s));
 
     const bool dist = psi->distributed && c->nranks > 1;
     if (dist) {
@@ -865,7 +879,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
         long long n_part = 0;
         if (peer) {
             const int out_phys = psi->parity ^ 1;
-            c->launches += launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s);
+            RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
             a.k_begin = 0; a.k_end = m;
             const long long slice = D == 2 ? g.plane : g.pitch;       // one slowest-direction slice (z-plane / y-row)
             a.peer_lo_plane = c->rank > 0 ? psi->peer_lo[out_phys] + slice * (n_lo_slab + g.ng) : nullptr;
@@ -876,9 +890,9 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
                 if (rc) return rc;
                 a.partials = c->d_partials;
             }
-            c->launches += launch_jacobi_sweep(a, s);
-            c->launches += launch_peer_signal(c->rank > 0 ? c->peer_flag_lo : nullptr,
-                                              c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr, c->epoch + 1, s);
+            RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
+            RNMF_LAUNCH(c, launch_peer_signal(c->rank > 0 ? c->peer_flag_lo : nullptr,
+                                              c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr, c->epoch + 1, s));
             c->epoch += 1;
         } else if (!dist || m < 3 || !c->overlap_halo || !fused) {
             a.k_begin = 0; a.k_end = m;
@@ -888,7 +902,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
                 if (rc) return rc;
                 a.partials = c->d_partials;
             }
-            c->launches += launch_jacobi_sweep(a, s);
+            RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
             if (!fused) { rc = fill_bc_on(psi, psi->d2, s); if (rc) return rc; }
             if (dist) { rc = halo_exchange_on(psi, psi->d2, s); if (rc) return rc; }
         } else {
@@ -907,18 +921,18 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
                 hi.partials = c->d_partials + p_lo;
                 mid.partials = c->d_partials + p_lo + p_hi;
             }
-            c->launches += launch_jacobi_sweep(lo, s);
-            c->launches += launch_jacobi_sweep(hi, s);
+            RNMF_LAUNCH(c, launch_jacobi_sweep(lo, s));
+            RNMF_LAUNCH(c, launch_jacobi_sweep(hi, s));
             RNMF_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
             RNMF_CUDA_TRY(cudaStreamWaitEvent(c->stream_halo, c->ev_boundary, 0));
             rc = halo_exchange_on(psi, psi->d2, c->stream_halo);
             if (rc) return rc;
             RNMF_CUDA_TRY(cudaEventRecord(c->ev_halo, c->stream_halo));
-            c->launches += launch_jacobi_sweep(mid, s);
+            RNMF_LAUNCH(c, launch_jacobi_sweep(mid, s));
             RNMF_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_halo, 0));
         }
         if (want_norm) {
-            c->launches += launch_reduce_partials(c->d_partials, (int)n_part, c->d_scalar, s);
+            RNMF_LAUNCH(c, launch_reduce_partials(c->d_partials, (int)n_part, c->d_scalar, s));
             if (dist) RNMF_NCCL_TRY(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclSum, c->comm, s));
             RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, s));
         }
@@ -927,7 +941,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     }
     // neighbours' last sweep must have landed in this frame's ghost planes before anything else
     // in this stream touches the frame
-    if (peer) c->launches += launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s);
+    if (peer) RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
     RNMF_CUDA_TRY(cudaGetLastError());
     if (l1_update) {
         RNMF_CUDA_TRY(cudaStreamSynchronize(s));
@@ -1072,7 +1086,7 @@ extern "C" int32_t rnmf_scale(rnmf_frame* out, double a, const rnmf_frame* x)
     int rc = check_same(out, x);
     if (rc) return rc;
     if (bind(out->ctx)) return RNMF_ERR_CUDA;
-    out->ctx->launches += launch_scale(x->g.total, a, x->d, out->d, out->ctx->stream);
+    RNMF_LAUNCH(out->ctx, launch_scale(x->g.total, a, x->d, out->d, out->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
@@ -1083,7 +1097,7 @@ extern "C" int32_t rnmf_add(rnmf_frame* out, const rnmf_frame* x, const rnmf_fra
     if (!rc) rc = check_same(out, y);
     if (rc) return rc;
     if (bind(out->ctx)) return RNMF_ERR_CUDA;
-    out->ctx->launches += launch_add(x->g.total, x->d, y->d, out->d, out->ctx->stream);
+    RNMF_LAUNCH(out->ctx, launch_add(x->g.total, x->d, y->d, out->d, out->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
@@ -1094,7 +1108,7 @@ extern "C" int32_t rnmf_mul(rnmf_frame* out, const rnmf_frame* x, const rnmf_fra
     if (!rc) rc = check_same(out, y);
     if (rc) return rc;
     if (bind(out->ctx)) return RNMF_ERR_CUDA;
-    out->ctx->launches += launch_mul(x->g.total, x->d, y->d, out->d, out->ctx->stream);
+    RNMF_LAUNCH(out->ctx, launch_mul(x->g.total, x->d, y->d, out->d, out->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
@@ -1105,7 +1119,7 @@ extern "C" int32_t rnmf_axpby(rnmf_frame* out, double a, const rnmf_frame* x, do
     if (!rc) rc = check_same(out, y);
     if (rc) return rc;
     if (bind(out->ctx)) return RNMF_ERR_CUDA;
-    out->ctx->launches += launch_axpby(x->g.total, a, x->d, b, y->d, out->d, out->ctx->stream);
+    RNMF_LAUNCH(out->ctx, launch_axpby(x->g.total, a, x->d, b, y->d, out->d, out->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
@@ -1135,7 +1149,7 @@ static int varcoef_impl(const rnmf_frame* phi, const rnmf_mu_params* mu, int wit
     RNMF_REQUIRE(phi->g.dim == 2 && phi->g.ncomp == 1, "variable-mu operator: 2D, n_comp=1 (poisson.rs:13-44)");
     RNMF_REQUIRE(out != phi, "out must not alias phi");
     if (bind(out->ctx)) return RNMF_ERR_CUDA;
-    out->ctx->launches += launch_varcoef_2d(phi->g, phi->d, *mu, with_source, relax, out->d, out->ctx->stream);
+    RNMF_LAUNCH(out->ctx, launch_varcoef_2d(phi->g, phi->d, *mu, with_source, relax, out->d, out->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
@@ -1157,7 +1171,7 @@ extern "C" int32_t rnmf_gradient_h_2d(const rnmf_frame* psi, rnmf_frame* h)
     RNMF_REQUIRE(psi->g.dim == 2 && psi->g.ncomp == 1 && h->g.dim == 2 && h->g.ncomp == 2, "get_h: 2D psi (1 comp) -> h (2 comps)");
     RNMF_REQUIRE(psi->g.n[0] == h->g.n[0] && psi->g.n[1] == h->g.n[1] && psi->g.ng == h->g.ng, "shapes differ");
     if (bind(h->ctx)) return RNMF_ERR_CUDA;
-    h->ctx->launches += launch_gradient_h_2d(psi->g, psi->d, h->g, h->d, h->ctx->stream);
+    RNMF_LAUNCH(h->ctx, launch_gradient_h_2d(psi->g, psi->d, h->g, h->d, h->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());
     return RNMF_OK;
 }
