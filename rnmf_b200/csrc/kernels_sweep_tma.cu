@@ -369,7 +369,7 @@ int encode_map_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base,
     cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1 };
     cuuint32_t estr[3] = { 1, 1, 1 };
     static int promo = -1;
-    if (promo < 0) { const char* e = getenv("RNMF_TMA_L2PROMO"); promo = e ? atoi(e) : 3; }
+    if (promo < 0) { const char* e = getenv("RNMF_TMA_L2PROMO"); promo = e ? atoi(e) : 2; }   // 128 B: same throughput as 256 B with 20 % fewer L2 read sectors (profiles/r1_power.md)
     const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                     : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
