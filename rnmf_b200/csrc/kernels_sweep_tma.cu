@@ -61,6 +61,27 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+// L2 eviction-priority hints: rhs and psi' are touched once per sweep, psi tiles are re-read by the
+// neighbouring CTAs (xy halo) a few microseconds later; at 6.6 TB/s the 126 MB L2 turns over in
+// ~19 us, so streaming the one-touch traffic with evict_first keeps the psi lines alive longer.
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void st2_hint(double* p, const double2& v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ double2 lds2(uint32_t a)
 {
     double2 v;
@@ -114,6 +135,7 @@ struct TmaSweepParams {
     // buffer; null on physical faces / single GPU
     double* peer_lo_plane;
     double* peer_hi_plane;
+    int l2_hints;            // 1: evict_first on rhs loads and psi' stores
 };
 
 template <int TX, int TY, int NS>
@@ -179,6 +201,8 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
             const int cy_psi = (int)(p.g.ng + j0 - 1);
             const int cx_rhs = cx_psi + 2, cy_rhs = cy_psi + 1;
             int cz = (int)(p.g.kg + k0 - 1);
+            const bool hints = p.l2_hints != 0;
+            const uint64_t pol = policy_evict_first();
             uint32_t wrap = 0;
             for (int base = 0; base < n_planes; base += NS, ++wrap) {
 #pragma unroll
@@ -189,7 +213,10 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
                         const bool with_rhs = idx >= 1 && idx <= n_planes - 2;
                         mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::PSI_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
                         tma_load_3d(psi0 + s * Cfg::PSI_STAGE, &tm_psi, cx_psi, cy_psi, cz, full0 + 8 * s);
-                        if (with_rhs) tma_load_3d(rhs0 + s * Cfg::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s);
+                        if (with_rhs) {
+                            if (hints) tma_load_3d_hint(rhs0 + s * Cfg::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s, pol);
+                            else tma_load_3d(rhs0 + s * Cfg::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s);
+                        }
                         ++cz;
                     }
                 }
@@ -211,6 +238,8 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
         const long long pitch = p.g.pitch, plane_sz = p.g.plane;
         double* oa = p.out + p.g.at(ia, j, k0, 0);
 
+        const bool hints = p.l2_hints != 0;
+        const uint64_t pol = policy_evict_first();
         // boundary work reduced to per-thread predicates
         const bool fuse = p.fuse_fill != 0;
         const Face1 fx0 = make_face1(p.faces.f[0], fuse), fx1 = make_face1(p.faces.f[1], fuse);
@@ -261,7 +290,8 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty0 + 8 * s);
 
-                    store4(oa, na, nb, full, va0, va1, vb0, vb1);
+                    if (full && hints) { st2_hint(oa, na, pol); st2_hint(oa + 64, nb, pol); }
+                    else store4(oa, na, nb, full, va0, va1, vb0, vb1);
                     if (NORM) {
                         double t = 0.0;
                         if (va0) t += fabs(__dsub_rn(na.x, cur_a.x));
@@ -431,6 +461,9 @@ struct Launcher {
         p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
         p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
         p.peer_lo_plane = a.peer_lo_plane; p.peer_hi_plane = a.peer_hi_plane;
+        static int hints = -1;
+        if (hints < 0) { const char* e = getenv("RNMF_L2_HINTS"); hints = e ? atoi(e) : 0; }
+        p.l2_hints = hints;
         return a.partials ? launch_one<true>(grid, tm_psi, tm_rhs, p, s) : launch_one<false>(grid, tm_psi, tm_rhs, p, s);
     }
 };
