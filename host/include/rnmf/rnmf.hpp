@@ -232,6 +232,23 @@ public:
         return data().at(p);
     }
 
+    // IndexMut<(isize,isize,usize)>, dataframe.rs:208-218 (one cell; not for loops)
+    void set(std::ptrdiff_t i, std::ptrdiff_t j, std::size_t n, Real value)
+    {
+        check(rnmf_frame_set_cell(h_.get(), i, j, 0, (int32_t)n, value), "rnmf_frame_set_cell");
+        mirror_valid_ = false;
+    }
+    // collect_typed_cells / the side iterators (dataframe.rs:273-278, 709-817): valid strip next to a
+    // face (ghost=false) or the ghost cells of that side (ghost=true), flat order, corners included
+    std::vector<Real> collect_side(int dir, int side, bool ghost = false, int comp = -1) const
+    {
+        int64_t n = 0;
+        check(rnmf_frame_collect_side(h_.get(), dir, side, ghost ? 1 : 0, comp, nullptr, &n), "rnmf_frame_collect_side");
+        std::vector<Real> v((std::size_t)n);
+        if (n) check(rnmf_frame_collect_side(h_.get(), dir, side, ghost ? 1 : 0, comp, v.data(), &n), "rnmf_frame_collect_side");
+        return v;
+    }
+
     rnmf_frame* handle() const { return h_.get(); }
     void invalidate_mirror() { mirror_valid_ = false; }
 

@@ -139,6 +139,18 @@ int32_t rnmf_frame_download(rnmf_frame* f, double* host_dense);
 int32_t rnmf_frame_download_valid(rnmf_frame* f, double* host_valid);
 /* fill_ic result (dataframe.rs:166-173): valid cells in flat order; ghosts untouched */
 int32_t rnmf_frame_upload_valid(rnmf_frame* f, const double* host_valid);
+/* Index / IndexMut<(isize,isize,usize)> (dataframe.rs:208-233): one cell by its valid-cell index
+ * (low ghosts negative; k ignored in 2D).  For occasional host access, not for loops. */
+int32_t rnmf_frame_get_cell(rnmf_frame* f, int64_t i, int64_t j, int64_t k, int32_t comp, double* value);
+int32_t rnmf_frame_set_cell(rnmf_frame* f, int64_t i, int64_t j, int64_t k, int32_t comp, double value);
+/* The side iterators (dataframe.rs:709-817) / collect_typed_cells (:273-278): the cells of one side
+ * of direction `dir` in the frame's flat order, corners included, as the reference's side lists do.
+ *   which = 0: the n_ghost-wide strip of VALID cells adjacent to the face (Valid(North|NE|NW) etc.:
+ *              the halo PACK order pinned by dataframe.rs:1148-1201);
+ *   which = 1: the GHOST cells of that side (Ghost(West|NW|SW) etc., the order fill_prescribed_bc uses).
+ * comp < 0 = IterComp::All.  n_out receives the number of values written (host_out may be NULL to query). */
+int32_t rnmf_frame_collect_side(rnmf_frame* f, int32_t dir, int32_t side, int32_t which, int32_t comp,
+                                double* host_out, int64_t* n_out);
 int32_t rnmf_frame_fill_zero(rnmf_frame* f);
 int32_t rnmf_frame_copy(rnmf_frame* dst, const rnmf_frame* src);            /* Clone, poisson.rs:71 */
 /* synthetic data for benchmarks, generated on the device: valid cell with GLOBAL flat valid

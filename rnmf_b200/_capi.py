@@ -69,6 +69,9 @@ SIGNATURES = {
     "rnmf_frame_download": (C.c_int32, [_vp, _vp]),
     "rnmf_frame_download_valid": (C.c_int32, [_vp, _vp]),
     "rnmf_frame_upload_valid": (C.c_int32, [_vp, _vp]),
+    "rnmf_frame_get_cell": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _dp]),
+    "rnmf_frame_set_cell": (C.c_int32, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_double]),
+    "rnmf_frame_collect_side": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _i64p]),
     "rnmf_frame_fill_zero": (C.c_int32, [_vp]),
     "rnmf_frame_copy": (C.c_int32, [_vp, _vp]),
     "rnmf_frame_fill_synthetic": (C.c_int32, [_vp, C.c_uint64]),

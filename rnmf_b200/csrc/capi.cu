@@ -644,6 +644,63 @@ extern "C" int32_t rnmf_frame_upload_valid(rnmf_frame* f, const double* host)
     return copy_valid(f, const_cast<double*>(host), false);
 }
 
+static int cell_offset(const rnmf_frame* f, int64_t i, int64_t j, int64_t k, int32_t comp, long long* off)
+{
+    const FrameGeom& g = f->g;
+    const long long ng = g.ng;
+    if (g.dim == 2) k = 0;
+    RNMF_REQUIRE(comp >= 0 && comp < g.ncomp, "component %d out of range", comp);
+    RNMF_REQUIRE(i >= -ng && i < g.n[0] + ng && j >= -ng && j < g.n[1] + ng && k >= -(long long)g.kg && k < g.n[2] + g.kg,
+                 "index (%lld, %lld, %lld) outside the grown frame", (long long)i, (long long)j, (long long)k);
+    *off = g.at(i, j, k, comp);
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_get_cell(rnmf_frame* f, int64_t i, int64_t j, int64_t k, int32_t comp, double* value)
+{
+    RNMF_REQUIRE(f && value, "null argument");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    long long off = 0;
+    int rc = cell_offset(f, i, j, k, comp, &off);
+    if (rc) return rc;
+    RNMF_CUDA_TRY(cudaMemcpyAsync(value, f->d + off, 8, cudaMemcpyDeviceToHost, f->ctx->stream));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_set_cell(rnmf_frame* f, int64_t i, int64_t j, int64_t k, int32_t comp, double value)
+{
+    RNMF_REQUIRE(f, "frame is null");
+    if (bind(f->ctx)) return RNMF_ERR_CUDA;
+    long long off = 0;
+    int rc = cell_offset(f, i, j, k, comp, &off);
+    if (rc) return rc;
+    RNMF_CUDA_TRY(cudaMemcpyAsync(f->d + off, &value, 8, cudaMemcpyHostToDevice, f->ctx->stream));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
+    return RNMF_OK;
+}
+
+extern "C" int32_t rnmf_frame_collect_side(rnmf_frame* f, int32_t dir, int32_t side, int32_t which, int32_t comp,
+                                           double* host_out, int64_t* n_out)
+{
+    RNMF_REQUIRE(f && n_out, "null argument");
+    const FrameGeom& g = f->g;
+    RNMF_REQUIRE(dir >= 0 && dir < g.dim && (side == 0 || side == 1) && (which == 0 || which == 1), "bad dir/side/which");
+    RNMF_REQUIRE(comp < g.ncomp, "component %d out of range", comp);
+    rnmf_ctx* c = f->ctx;
+    if (bind(c)) return RNMF_ERR_CUDA;
+    const int comp0 = comp < 0 ? 0 : comp, ncomp = comp < 0 ? g.ncomp : 1;
+    const long long total = collect_side_count(g, dir, which, ncomp);
+    *n_out = total;
+    if (!host_out || total == 0) return RNMF_OK;
+    int rc = ensure_partials(c, total);              // reuse the scratch buffer
+    if (rc) return rc;
+    RNMF_LAUNCH(c, launch_collect_side(g, f->d, dir, side, which, comp0, ncomp, c->d_partials, c->stream));
+    RNMF_CUDA_TRY(cudaMemcpyAsync(host_out, c->d_partials, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RNMF_OK;
+}
+
 extern "C" int32_t rnmf_frame_fill_zero(rnmf_frame* f)
 {
     RNMF_REQUIRE(f, "frame is null");

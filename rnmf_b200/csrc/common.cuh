@@ -89,6 +89,9 @@ struct SweepCoef { double c0, c1, c2, c3; };
 int launch_fill_bc_faces(const FrameGeom& g, double* d, const FaceSet* faces_host, cudaStream_t s);
 int launch_fill_prescribed(const FrameGeom& g, double* d, int comp, int dir, int side,
                            const double* vals_dev, long long nvals, cudaStream_t s);
+long long collect_side_count(const FrameGeom& g, int dir, int which, int ncomp);
+int launch_collect_side(const FrameGeom& g, const double* d, int dir, int side, int which, int comp0, int ncomp,
+                        double* out_dev, cudaStream_t s);
 int launch_copy_ghost_shell(const FrameGeom& g, const double* src, double* dst, cudaStream_t s);
 
 struct SweepArgs {

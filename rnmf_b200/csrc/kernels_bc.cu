@@ -154,3 +154,52 @@ int launch_copy_ghost_shell(const FrameGeom& g, const double* src, double* dst, 
     copy_ghost_shell_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, src, dst);
     return 1;
 }
+
+// Side gather (collect_typed_cells, dataframe.rs:273-278; side iterators :709-817): cells of one side
+// of direction `dir`, flat order inside each component, corners included.
+//   which = 0: valid strip adjacent to the face: 0 <= idx[dir] < ng (lo) / n-ng <= idx[dir] < n (hi),
+//              the other directions over their VALID range (the lists Valid(North|NE|NW) ...);
+//   which = 1: ghost side: idx[dir] < 0 (lo) / >= n (hi), other directions over the GROWN range.
+__global__ void __launch_bounds__(256) collect_side_kernel(FrameGeom g, const double* __restrict__ data, int dir, int side,
+                                                           int which, int comp0, int ncomp, double* __restrict__ out)
+{
+    long long e[3], lo[3];
+    for (int d = 0; d < 3; ++d) {
+        const long long gh = d < g.dim ? g.ng : 0;
+        if (which == 0) { e[d] = g.n[d]; lo[d] = gh; }            // valid range, in grown coordinates
+        else { e[d] = g.G[d]; lo[d] = 0; }
+    }
+    e[dir] = g.ng;
+    if (which == 0) lo[dir] = side == 0 ? g.ng : g.n[dir];        // grown index of the strip's first layer
+    else lo[dir] = side == 0 ? 0 : g.n[dir] + g.ng;
+    const long long per = e[0] * e[1] * e[2];
+    const long long total = per * ncomp;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+        const long long c = m / per;
+        long long r = m % per;
+        const long long ii = r % e[0] + lo[0];
+        r /= e[0];
+        const long long jj = r % e[1] + lo[1];
+        const long long kk = r / e[1] + lo[2];
+        out[m] = data[g.xoff + ii + g.pitch * (jj + g.G[1] * (kk + g.G[2] * (comp0 + c)))];
+    }
+}
+
+long long collect_side_count(const FrameGeom& g, int dir, int which, int ncomp)
+{
+    long long e[3];
+    for (int d = 0; d < 3; ++d) e[d] = which == 0 ? g.n[d] : g.G[d];
+    e[dir] = g.ng;
+    return e[0] * e[1] * e[2] * ncomp;
+}
+
+int launch_collect_side(const FrameGeom& g, const double* d, int dir, int side, int which, int comp0, int ncomp,
+                        double* out_dev, cudaStream_t s)
+{
+    const long long total = collect_side_count(g, dir, which, ncomp);
+    if (total <= 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    collect_side_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, d, dir, side, which, comp0, ncomp, out_dev);
+    return 1;
+}

@@ -166,12 +166,31 @@ class CartesianDataFrame:
         return out
 
     def __getitem__(self, idx):
-        """Index<(isize,isize,usize)> (dataframe.rs:221-233); low ghosts are negative.  Debug aid."""
-        d = self.data.reshape((self.n_comp,) + tuple(reversed(self.n_grown)))
+        """Index<(isize,isize,usize)> (dataframe.rs:221-233); low ghosts are negative."""
         *ijk, n = idx
-        g = self.n_ghost
-        pos = tuple(reversed([v + g for v in ijk]))
-        return float(d[(n,) + pos])
+        ijk = list(ijk) + [0] * (3 - len(ijk))
+        v = C.c_double()
+        _capi.check(_capi.lib().rnmf_frame_get_cell(self._h, ijk[0], ijk[1], ijk[2], n, C.byref(v)))
+        return v.value
+
+    def __setitem__(self, idx, value) -> None:
+        """IndexMut<(isize,isize,usize)> (dataframe.rs:208-218)."""
+        *ijk, n = idx
+        ijk = list(ijk) + [0] * (3 - len(ijk))
+        _capi.check(_capi.lib().rnmf_frame_set_cell(self._h, ijk[0], ijk[1], ijk[2], n, float(value)))
+
+    def collect_side(self, direction: int, side: int, ghost: bool = False, comp: int = -1) -> np.ndarray:
+        """collect_typed_cells / the side iterators (dataframe.rs:273-278, 709-817): the valid strip
+        next to a face (ghost=False: Valid(North|NE|NW) ...) or the ghost cells of that side
+        (ghost=True: Ghost(West|NW|SW) ...), flat order, corners included."""
+        L = _capi.lib()
+        n = C.c_int64()
+        _capi.check(L.rnmf_frame_collect_side(self._h, direction, side, 1 if ghost else 0, comp, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float64)
+        if n.value:
+            _capi.check(L.rnmf_frame_collect_side(self._h, direction, side, 1 if ghost else 0, comp,
+                                                  out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
 
     # ---- whole-frame operators (dataframe.rs:628-691), ghosts included ---------------------
     def __rmul__(self, a: float) -> "CartesianDataFrame":            # Real * &df

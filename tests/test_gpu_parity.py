@@ -557,3 +557,72 @@ def test_large_upload_uses_staged_path_and_roundtrips(R, ctx):
     np.testing.assert_array_equal(f.data, host)
     np.testing.assert_array_equal(f.get_valid_cells(), ora.valid_view(g, host).reshape(-1))
     assert f.guards_intact()
+
+
+# ---- side iterators / collect_typed_cells / IndexMut --------------------
+def test_collect_side_golden_vectors_on_gpu(R, ctx, golden):
+    """The halo PACK order pinned by dataframe.rs:1148-1201 and the ghost-side iteration pinned by
+    :1065-1145, through the GPU gather."""
+    case = golden["ghost_collect_two_edge"]
+    _, bc = _bc_pair(R, 2, ([tuple(f) for f in case["lo"]], [tuple(f) for f in case["hi_bc"]]))
+    f = R.CartesianDataFrame.new_from(R.CartesianMesh.new([0.0, 0.0], case["hi"], case["n"]), bc, 1, case["ng"], ctx)
+    f.fill_ic(lambda x, y, c: x + 1.0)
+    f.fill_bc()
+    want = {tuple(c["sides"])[0]: c["values"] for c in case["collect"]}
+    assert f.collect_side(1, 1).tolist() == want["Valid(North)"]
+    assert f.collect_side(1, 0).tolist() == want["Valid(South)"]
+    assert f.collect_side(0, 1).tolist() == want["Valid(East)"]
+    assert f.collect_side(0, 0).tolist() == want["Valid(West)"]
+    case = golden["ghost_iter_two_ghost"]
+    _, bc = _bc_pair(R, 2, ([tuple(x) for x in case["lo"]], [tuple(x) for x in case["hi_bc"]]))
+    f = R.CartesianDataFrame.new_from(R.CartesianMesh.new([0.0, 0.0], case["hi"], case["n"]), bc, 1, case["ng"], ctx)
+    f.fill_ic(lambda x, y, c: x + 1.0)
+    f.fill_bc()
+    ng, n = case["ng"], case["n"][0]
+    east = f.collect_side(0, 1, ghost=True)             # Ghost(East|NE|SE): rows 0..G1-1, ng cells each
+    want = {it["sides"][0]: it["values"] for it in case["iters"]}
+    assert east[ng * ng:-ng * ng].tolist() == want["Ghost(East)"]
+    assert east[-ng * ng:].tolist() == want["Ghost(NorthEast)"]
+    south = f.collect_side(1, 0, ghost=True).reshape(ng, n + 2 * ng)
+    assert south[:, ng:-ng].reshape(-1).tolist() == want["Ghost(South)"]
+
+
+@pytest.mark.parametrize("n,ng,ncomp", [([7, 5], 2, 2), ([6, 5, 4], 1, 1), ([5, 6, 7], 2, 2)])
+def test_collect_side_matches_dense_slices(R, ctx, n, ng, ncomp):
+    dim = len(n)
+    g = ora.geom(n, ng=ng, ncomp=ncomp)
+    mesh = R.CartesianMesh.new([0.0] * dim, [float(v) for v in n], n)
+    f = R.CartesianDataFrame.new_from(mesh, R.BCs.empty(), ncomp, ng, ctx)
+    host = np.random.default_rng(17).standard_normal(g.n_nodes)
+    f.data = host
+    grid = ora.as_grid(g, host)                       # (c, [z,] y, x)
+    for d in range(dim):
+        ax = grid.ndim - 1 - d                        # numpy axis of direction d
+        for side in (0, 1):
+            # ghost side: full grown extent in the other directions
+            sl = [slice(None)] * grid.ndim
+            sl[ax] = slice(0, ng) if side == 0 else slice(n[d] + ng, n[d] + 2 * ng)
+            np.testing.assert_array_equal(f.collect_side(d, side, ghost=True), grid[tuple(sl)].reshape(-1))
+            np.testing.assert_array_equal(f.collect_side(d, side, ghost=True, comp=ncomp - 1), grid[tuple(sl)][ncomp - 1].reshape(-1))
+            # valid strip: valid extent in the other directions
+            sl = [slice(None)] + [slice(ng, ng + n[dim - 1 - a]) for a in range(dim)]
+            sl[ax] = slice(ng, 2 * ng) if side == 0 else slice(n[d], n[d] + ng)
+            np.testing.assert_array_equal(f.collect_side(d, side), grid[tuple(sl)].reshape(-1))
+
+
+def test_index_and_index_mut(R, ctx):
+    n, ng = [6, 5, 4], 2
+    g = ora.geom(n, ng=ng, ncomp=2)
+    f = R.CartesianDataFrame.new_from(R.CartesianMesh.new([0.0] * 3, [6.0, 5.0, 4.0], n), R.BCs.empty(), 2, ng, ctx)
+    host = np.random.default_rng(19).standard_normal(g.n_nodes)
+    f.data = host
+    grid = ora.as_grid(g, host)
+    for (i, j, k, c) in ((0, 0, 0, 0), (-2, -1, 3, 1), (5, 4, 3, 1), (7, 6, 5, 0), (-2, -2, -2, 1)):
+        assert f[(i, j, k, c)] == grid[c, k + ng, j + ng, i + ng]
+    f[(3, -2, 5, 1)] = 42.5
+    host2 = f.data
+    assert ora.as_grid(g, host2)[1, 5 + ng, -2 + ng, 3 + ng] == 42.5
+    host2.reshape(grid.shape)[1, 5 + ng, -2 + ng, 3 + ng] = grid[1, 5 + ng, -2 + ng, 3 + ng]
+    np.testing.assert_array_equal(host2, host)
+    with pytest.raises(R.RnmfError):
+        f[(8, 0, 0, 0)]
