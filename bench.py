@@ -176,7 +176,7 @@ def cpu_sample_geom(workload: str):
     return n
 
 
-def cpu_reference_run(workload: str, sweeps: int, reps: int, jacobi_omp: bool = False):
+def cpu_reference_run(workload: str, sweeps: int, reps: int, jacobi_omp: bool = False, jacobi_1core: bool = False):
     """returns (seconds per rep list, LUPs per rep)"""
     import numpy as np
     from oracle import oracle as ora
@@ -192,8 +192,8 @@ def cpu_reference_run(workload: str, sweeps: int, reps: int, jacobi_omp: bool = 
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        if jacobi_omp:
-            ora.jacobi(g, psi, rhs, bc, sweeps, omp=True)
+        if jacobi_omp or jacobi_1core:
+            ora.jacobi(g, psi, rhs, bc, sweeps, omp=jacobi_omp)
         else:
             ora.gs(g, psi, rhs, bc, sweeps)
         times.append(time.perf_counter() - t0)
@@ -539,6 +539,11 @@ def main():
                         "sample": f"10 timed (2 warm-up) reference-order Gauss-Seidel sweeps (poisson.rs:80-89 loop order, oracle port) "
                                   f"over a {'x'.join(map(str, n))} slab of the workload, 1 thread; the Rust reference is single-threaded",
                         "host": {"nproc": os.cpu_count(), "cpu": _cpu_model()}}
+        try:
+            t1, l1c = cpu_reference_run(args.workload, 4, 3, jacobi_1core=True)
+            cpu_baseline["jacobi_same_expression_1_core"] = {"value": l1c * len(t1[1:]) / sum(t1[1:]) / 1e9, "unit": "GLUP/s", "cores": 1}
+        except Exception as e:
+            cpu_baseline["jacobi_same_expression_1_core"] = {"error": str(e)}
         try:
             from oracle import oracle as ora
             t2, l2 = cpu_reference_run(args.workload, 8, 4, jacobi_omp=True)      # 8 sweeps per call: amortises the ping-pong copies
