@@ -193,7 +193,7 @@ def cpu_reference_run(workload: str, sweeps: int, reps: int, jacobi_omp: bool = 
     for _ in range(reps):
         t0 = time.perf_counter()
         if jacobi_omp or jacobi_1core:
-            ora.jacobi(g, psi, rhs, bc, sweeps, omp=jacobi_omp)
+            ora.jacobi(g, psi, rhs, bc, sweeps, omp=jacobi_omp, want_norm=False)
         else:
             ora.gs(g, psi, rhs, bc, sweeps)
         times.append(time.perf_counter() - t0)

@@ -186,15 +186,15 @@ def coefs(g: Geom) -> np.ndarray:
     return np.array(list(out))
 
 
-def jacobi(g, psi, rhs, faces, n_sweeps, omp=False):
-    """returns l1 norm of the last update; psi updated in place."""
+def jacobi(g, psi, rhs, faces, n_sweeps, omp=False, want_norm=True):
+    """returns l1 norm of the last update (long-double accumulation; None if not wanted); psi updated in place."""
     scratch = np.empty_like(psi)
     l1 = C.c_double(0.0)
     fn = lib().ora_jacobi_sweeps_omp if omp else lib().ora_jacobi_sweeps
-    rc = fn(C.byref(g), psi, scratch, rhs, faces, n_sweeps, C.byref(l1))
+    rc = fn(C.byref(g), psi, scratch, rhs, faces, n_sweeps, C.byref(l1) if want_norm else None)
     if rc:
         raise RuntimeError(f"oracle jacobi rc={rc}")
-    return l1.value
+    return l1.value if want_norm else None
 
 
 def gs(g, psi, rhs, faces, n_sub_iter, wavefront=False):
