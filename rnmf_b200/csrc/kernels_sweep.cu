@@ -6,7 +6,13 @@
 // SURVEY 8a), every operation rounded separately (__dmul_rn/__dadd_rn: no FMA contraction):
 //      new = ((c0*rhs + c1*(E+W)) + c2*(N+S)) [+ c3*(U+D)]
 //
-// Bandwidth plan (24 B per lattice update: read psi, read rhs, write psi'):
+// This file holds the sweep dispatcher and the NON-TMA comparison kernels (variants 1-4, 10, 11 in
+// 3D; 1, 2 in 2D).  The defaults are the TMA/mbarrier kernels in kernels_sweep_tma.cu (3D) and
+// kernels_sweep2d_tma.cu (2D); small L2-resident frames take kernels_resident.cu.  Measured at
+// 768^3 (sustained): zmarch 195-231 GLUP/s, TMA 259; at 8192^2: ymarch 244, TMA 270
+// (profiles/r1_power.md).
+//
+// Bandwidth plan of the kernels below (24 B per lattice update: read psi, read rhs, write psi'):
 //   3D "zmarch": a CTA owns a (2*TX x TY) xy-tile and marches ZC planes in z.  Each thread
 //   owns two adjacent x cells (one 128-bit access per array per plane) and keeps the planes
 //   k-1, k, k+1 of its own cells in registers, so psi is fetched from L2/HBM once per cell;
@@ -288,7 +294,7 @@ void launch2d(const Plan& pl, const SweepParams& p, cudaStream_t s)
 
 int tma_sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s);
-// default (variant 0 = auto): the TMA kernel for 3D frames (measured 240 vs 203 GLUP/s at 768^3)
+// default (variant 0 = auto): the TMA kernel for 3D frames (measured 259 vs 195-231 GLUP/s at 768^3, sustained)
 static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9) || a.variant == 13); }
 
 int tma2d_sweep_num_partials(const SweepArgs& a);
