@@ -22,6 +22,8 @@
  *    return; calls that return a scalar (norms) or copy to pageable host memory synchronise.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *    RNMF_ERR_CUDA.
+ *  - thread safety: none beyond "one host thread per context at a time"; the library keeps small
+ *    process-wide caches (NCCL entry points, TMA descriptors) that are not locked.
  */
 #ifndef RNMF_B200_H
 #define RNMF_B200_H
@@ -99,6 +101,7 @@ int32_t rnmf_ctx_create(int32_t device, rnmf_ctx** out);
 int32_t rnmf_ctx_create_dist(int32_t device, int32_t rank, int32_t nranks, const void* nccl_id,
                              rnmf_ctx** out);
 int32_t rnmf_nccl_unique_id(void* id128);
+/* Destroy every frame of the context first (frames point into it); synchronises the device. */
 int32_t rnmf_ctx_destroy(rnmf_ctx* ctx);
 int32_t rnmf_sync(rnmf_ctx* ctx);
 int32_t rnmf_ctx_stream(rnmf_ctx* ctx, void** cuda_stream);  /* cudaStream_t the kernels run on   */
