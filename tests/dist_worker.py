@@ -24,16 +24,18 @@ MIXED_3D = ([("dirichlet", 0.0), ("neumann", 0.0), ("dirichlet", 0.25)],
 MIXED_2D = ([("neumann", 0.3), ("dirichlet", -1.0)], [("dirichlet", 2.0), ("neumann", -0.7)])
 
 CASES = [
-    # n_global, hi, spec, sweeps
-    ([40, 36, 50], [40.0, 72.0, 150.0], MIXED_3D, 5),
-    ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 4),      # uneven split: remainder goes to the last rank
-    ([64, 37], [64.0, 37.0], MIXED_2D, 6),
+    # n_global, hi, spec, sweeps, n_ghost
+    ([40, 36, 50], [40.0, 72.0, 150.0], MIXED_3D, 5, 1),
+    ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 4, 1),      # uneven split: remainder goes to the last rank
+    ([64, 37], [64.0, 37.0], MIXED_2D, 6, 1),
+    ([20, 18, 29], [2.0, 2.0, 3.0], MIXED_3D, 3, 2),       # two ghost layers: stand-alone fill + 2-slice halos
+    ([33, 41], [1.0, 2.0], MIXED_2D, 4, 2),
 ]
 
 
-def reference(n, hi, spec, sweeps):
+def reference(n, hi, spec, sweeps, ng=1):
     from oracle import oracle as ora
-    g = ora.geom(n, hi=hi)
+    g = ora.geom(n, hi=hi, ng=ng)
     bc = ora.bcs(g.dim, [spec])
     nv = int(np.prod(n))
     psi, rhs = ora.zeros(g), ora.zeros(g)
@@ -60,17 +62,17 @@ def run_nccl():
         ctx.set_option("halo_overlap", 0 if mode == "nccl_serial" else 1)
         ctx.set_option("peer_halo", 1 if mode == "peer" else 0)
         overlap = mode
-        for n, hi, spec, sweeps in CASES:
+        for n, hi, spec, sweeps, ng in CASES:
             dim = len(n)
-            want, l1_ref = reference(n, hi, spec, sweeps)
+            want, l1_ref = reference(n, hi, spec, sweeps, ng)
             bc = R.BCs([R.ComponentBCs([mk[k](v) for k, v in spec[0]], [mk[k](v) for k, v in spec[1]])])
             mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
-            psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
-            rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+            psi = R.CartesianDataFrame.new_from(mesh, bc, 1, ng, ctx, slab=True)
+            rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, ng, ctx, slab=True)
             psi.fill_synthetic(101)
             rhs.fill_synthetic(202)
             psi.fill_bc()
-            if mode == "peer":
+            if mode == "peer" and ng == 1:
                 psi.enable_peer_halo()
                 # two calls: the epoch handshake and buffer parity must carry over between calls
                 poisson.jacobi_sweeps(psi, rhs, 2)
@@ -109,10 +111,10 @@ def run_gloo(rank: int, world: int, port: int, results):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ok = True
-    for n, hi, spec, sweeps in CASES:
+    for n, hi, spec, sweeps, ng in CASES:
         dim = len(n)
         D = dim - 1
-        want, _ = reference(n, hi, spec, sweeps)
+        want, _ = reference(n, hi, spec, sweeps, ng)
         start, count = slab_partition(n[D], world, rank)
         dx = [hi[d] / n[d] for d in range(dim)]
         nl = list(n)
@@ -121,7 +123,7 @@ def run_gloo(rank: int, world: int, port: int, results):
         lo[D] = start * dx[D]
         hil = list(hi)
         hil[D] = lo[D] + count * dx[D]
-        g = ora.geom(nl, lo=lo, hi=hil)
+        g = ora.geom(nl, lo=lo, hi=hil, ng=ng)
         for d in range(dim):
             g.dx[d] = dx[d]                       # exactly the global dx (what the C ABI passes)
         lo_spec, hi_spec = list(spec[0]), list(spec[1])
@@ -143,20 +145,20 @@ def run_gloo(rank: int, world: int, port: int, results):
         def exchange():
             # first/last valid slices -> neighbours' ghost slices (whole grown slices, as the library does)
             reqs = []
-            recv_lo = torch.empty(grid[0].shape, dtype=torch.float64)
-            recv_hi = torch.empty(grid[0].shape, dtype=torch.float64)
+            recv_lo = torch.empty(grid[:ng].shape, dtype=torch.float64)
+            recv_hi = torch.empty(grid[:ng].shape, dtype=torch.float64)
             if rank > 0:
-                reqs.append(dist.isend(torch.from_numpy(grid[1].copy()), rank - 1))
+                reqs.append(dist.isend(torch.from_numpy(grid[ng:2 * ng].copy()), rank - 1))
                 reqs.append(dist.irecv(recv_lo, rank - 1))
             if rank < world - 1:
-                reqs.append(dist.isend(torch.from_numpy(grid[-2].copy()), rank + 1))
+                reqs.append(dist.isend(torch.from_numpy(grid[-2 * ng:-ng].copy()), rank + 1))
                 reqs.append(dist.irecv(recv_hi, rank + 1))
             for r in reqs:
                 r.wait()
             if rank > 0:
-                grid[0] = recv_lo.numpy()
+                grid[:ng] = recv_lo.numpy()
             if rank < world - 1:
-                grid[-1] = recv_hi.numpy()
+                grid[-ng:] = recv_hi.numpy()
 
         exchange()
         for _ in range(sweeps):
