@@ -137,6 +137,8 @@ struct rnmf_ctx {
     void* peer_flag_base_lo = nullptr;
     void* peer_flag_base_hi = nullptr;
     unsigned long long epoch = 0;                 // sweeps completed in peer mode (same on all ranks)
+    unsigned long long done_target[2] = { 0, 0 }; // cumulative boundary-CTA counts (in-kernel handshake), lo / hi
+    int peer_inkernel = 1;                        // option "peer_inkernel": handshake inside the sweep kernel
     int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
     double* d_staging = nullptr;                  // dense staging for large uploads (1-D PCIe copy + device repack)
     long long staging_cap = 0;                    // doubles
@@ -405,6 +407,7 @@ extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* val
     if (!strcmp(key, "sweep_variant")) { c->sweep_variant = !strcmp(value, "auto") ? 0 : atoi(value); return RNMF_OK; }
     if (!strcmp(key, "sweep_chunk")) { c->sweep_chunk = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "peer_halo")) { c->peer_halo = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "peer_inkernel")) { c->peer_inkernel = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "resident")) { c->resident = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "halo_overlap")) { c->overlap_halo = atoi(value); return RNMF_OK; }
     rnmf_set_error("unknown option '%s'", key);
@@ -907,6 +910,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
 
     a.peer_lo_plane = nullptr;
     a.peer_hi_plane = nullptr;
+    memset(&a.ps, 0, sizeof(a.ps));
     // fused compute + halo exchange over NVLink peer memory (3D TMA kernel): one launch per sweep,
     // the boundary planes are stored into the neighbours' ghost planes by the sweep kernel itself
     const bool peer = dist && psi->peer_attached && c->peer_halo && fused && sweep_supports_peer_halo(a);
@@ -936,7 +940,8 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
         long long n_part = 0;
         if (peer) {
             const int out_phys = psi->parity ^ 1;
-            RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
+            const bool inkernel = c->peer_inkernel != 0;
+            if (!inkernel) RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
             a.k_begin = 0; a.k_end = m;
             const long long slice = D == 2 ? g.plane : g.pitch;       // one slowest-direction slice (z-plane / y-row)
             a.peer_lo_plane = c->rank > 0 ? psi->peer_lo[out_phys] + slice * (n_lo_slab + g.ng) : nullptr;
@@ -947,9 +952,25 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
                 if (rc) return rc;
                 a.partials = c->d_partials;
             }
+            if (inkernel) {
+                // handshake inside the sweep kernel: boundary CTAs (scheduled last) wait / publish
+                const unsigned long long tiles = (unsigned long long)sweep_boundary_ctas(a);
+                a.ps.enabled = 1;
+                a.ps.wait_lo = my_flag_lo; a.ps.wait_hi = my_flag_hi;
+                a.ps.sig_lo = c->rank > 0 ? c->peer_flag_lo : nullptr;
+                a.ps.sig_hi = c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr;
+                a.ps.done = c->d_flags + 3;
+                if (a.peer_lo_plane) c->done_target[0] += tiles;
+                if (a.peer_hi_plane) c->done_target[1] += tiles;
+                a.ps.target_lo = c->done_target[0]; a.ps.target_hi = c->done_target[1];
+                a.ps.epoch = c->epoch;
+                a.ps.status = c->d_flags + 2;
+            }
             RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
-            RNMF_LAUNCH(c, launch_peer_signal(c->rank > 0 ? c->peer_flag_lo : nullptr,
-                                              c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr, c->epoch + 1, s));
+            a.ps.enabled = 0;
+            if (!inkernel)
+                RNMF_LAUNCH(c, launch_peer_signal(c->rank > 0 ? c->peer_flag_lo : nullptr,
+                                                  c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr, c->epoch + 1, s));
             c->epoch += 1;
         } else if (!dist || m < 3 || !c->overlap_halo || !fused) {
             a.k_begin = 0; a.k_end = m;

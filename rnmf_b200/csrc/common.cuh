@@ -94,6 +94,56 @@ int launch_collect_side(const FrameGeom& g, const double* d, int dir, int side, 
                         double* out_dev, cudaStream_t s);
 int launch_copy_ghost_shell(const FrameGeom& g, const double* src, double* dst, cudaStream_t s);
 
+// In-kernel epoch handshake of the fused peer-memory halo (kernels_sweep_tma.cu, kernels_sweep2d_tma.cu):
+// only the CTAs whose chunk holds the slab's first / last slice take part.  They are scheduled LAST,
+// wait (thread 0, bounded spin) until the neighbour has finished the boundary CTAs of its previous
+// sweep (flag >= epoch: its halo stores into my input ghosts have landed and it no longer reads the
+// ghost slice I am about to overwrite), and the last of them to finish publishes epoch+1 to the
+// neighbour.  Dependency chain: my sweep e+1 <- neighbour's sweep e <- my sweep e-1 (complete):
+// no cycle, and the waiter only depends on another GPU's progress.
+struct PeerSync {
+    const unsigned long long* wait_lo;   // my flag written by the lo neighbour (null: no lo neighbour / not used)
+    const unsigned long long* wait_hi;
+    unsigned long long* sig_lo;          // lo neighbour's flag for its hi side (peer-mapped)
+    unsigned long long* sig_hi;
+    unsigned long long* done;            // [2] local completion counters of the boundary CTAs (lo, hi)
+    unsigned long long target_lo;        // counter value that marks the last boundary CTA of this launch
+    unsigned long long target_hi;
+    unsigned long long epoch;            // sweeps completed before this launch
+    unsigned long long* status;          // set on spin timeout
+    int enabled;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void peer_spin_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* status)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= target) break;
+        if (clock64() - t0 > 20LL * 1000 * 1000 * 1000) { *status = target; break; }   // ~10 s: a dead neighbour
+        __nanosleep(100);
+    }
+}
+// called by ONE thread after a CTA-wide barrier that follows the CTA's last peer store
+__device__ __forceinline__ void peer_publish(unsigned long long* done, unsigned long long target, unsigned long long* peer_flag,
+                                             unsigned long long value)
+{
+    __threadfence_system();
+    const unsigned long long old = atomicAdd(done, 1ULL);
+    if (old + 1 == target) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(value) : "memory");
+    }
+}
+// boundary chunks last: chunk index -> 1, 2, .., n-2, 0, n-1
+__device__ __forceinline__ unsigned peer_chunk_order(unsigned b, unsigned n)
+{
+    return n < 3 ? b : (b < n - 2 ? b + 1 : (b == n - 2 ? 0u : n - 1));
+}
+#endif
+
 struct SweepArgs {
     FrameGeom g;
     const double* in;
@@ -109,8 +159,10 @@ struct SweepArgs {
     int chunk_override;      // 0 = planner decides (measurement knob "sweep_chunk")
     double* peer_lo_plane;   // fused peer-memory halo (3D TMA kernel): neighbour ghost-plane bases
     double* peer_hi_plane;   //   for this sweep's `out` buffer, or null
+    PeerSync ps;             // in-kernel handshake (enabled = 0: none)
 };
 bool sweep_supports_peer_halo(const SweepArgs& a);
+int sweep_boundary_ctas(const SweepArgs& a);     // CTAs per boundary side (tiles across the slice) of the kernel that will run
 
 // peer-memory halo handshake (kernels_peer.cu): epoch flags live in each rank's own memory and
 // are written by the neighbours over NVLink

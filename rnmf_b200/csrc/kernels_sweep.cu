@@ -303,6 +303,9 @@ int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s);
 static inline bool use_tma2d(const SweepArgs& a) { return a.g.dim == 2 && (a.variant == 0 || a.variant == 20); }
 
 bool sweep_supports_peer_halo(const SweepArgs& a) { return use_tma(a) || use_tma2d(a); }
+int tma_sweep_boundary_ctas(const SweepArgs& a);
+int tma2d_sweep_boundary_ctas(const SweepArgs& a);
+int sweep_boundary_ctas(const SweepArgs& a) { return use_tma(a) ? tma_sweep_boundary_ctas(a) : (use_tma2d(a) ? tma2d_sweep_boundary_ctas(a) : 0); }
 
 int sweep_num_partials(const SweepArgs& a)
 {

@@ -104,6 +104,7 @@ struct Tma2dParams {
     // neighbour's ghost row mirroring this slab's first / last valid row, in its `out` buffer
     double* peer_lo_row;
     double* peer_hi_row;
+    PeerSync ps;
 };
 
 constexpr int NW = 4;                                  // consumer warps: 128 columns each
@@ -133,9 +134,12 @@ __global__ void __launch_bounds__(32 * NW + 32, 3) jacobi2d_tma_kernel(const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long i0 = (long long)blockIdx.x * TXC;
-    const long long j0 = p.m_begin + (long long)blockIdx.y * p.chunk;
+    const unsigned yc = p.ps.enabled ? peer_chunk_order(blockIdx.y, gridDim.y) : blockIdx.y;
+    const long long j0 = p.m_begin + (long long)yc * p.chunk;
     const long long j1 = j0 + p.chunk < p.m_end ? j0 + p.chunk : p.m_end;
     const int n_rows = (int)(j1 - j0) + 2;               // psi rows j0-1 .. j1   (row idx <-> stage idx % NS)
+    const bool sync_lo = p.ps.enabled && p.peer_lo_row && j0 == 0;
+    const bool sync_hi = p.ps.enabled && p.peer_hi_row && j1 == p.g.n[1];
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -144,6 +148,8 @@ __global__ void __launch_bounds__(32 * NW + 32, 3) jacobi2d_tma_kernel(const __g
             mbar_init(empty0 + 8 * s, NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
+        if (sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
     }
     __syncthreads();
 
@@ -260,6 +266,13 @@ __global__ void __launch_bounds__(32 * NW + 32, 3) jacobi2d_tma_kernel(const __g
                     oa += pitch;
                 }
             }
+        }
+    }
+    if (sync_lo || sync_hi) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (sync_lo) peer_publish(p.ps.done + 0, p.ps.target_lo, p.ps.sig_lo, p.ps.epoch + 1);
+            if (sync_hi) peer_publish(p.ps.done + 1, p.ps.target_hi, p.ps.sig_hi, p.ps.epoch + 1);
         }
     }
     if (NORM) {
@@ -382,6 +395,14 @@ int tma2d_sweep_num_partials(const SweepArgs& a)
     return plan2d(a, grid, chunk);
 }
 
+int tma2d_sweep_boundary_ctas(const SweepArgs& a)
+{
+    dim3 grid;
+    int chunk;
+    plan2d(a, grid, chunk);
+    return (int)grid.x;
+}
+
 int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
@@ -396,6 +417,7 @@ int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s)
     p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
     p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
     p.peer_lo_row = a.peer_lo_plane; p.peer_hi_row = a.peer_hi_plane;
+    p.ps = a.ps;
     return a.partials ? launch2d_one<true>(grid, tm_psi256, tm_psi4, tm_rhs256, p, s)
                       : launch2d_one<false>(grid, tm_psi256, tm_psi4, tm_rhs256, p, s);
 }

@@ -136,6 +136,7 @@ struct TmaSweepParams {
     double* peer_lo_plane;
     double* peer_hi_plane;
     int l2_hints;            // 1: evict_first on rhs loads and psi' stores
+    PeerSync ps;
 };
 
 template <int TX, int TY, int NS>
@@ -179,9 +180,13 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long i0 = (long long)blockIdx.x * TX;
     const long long j0 = (long long)blockIdx.y * TY;
-    const long long k0 = p.m_begin + (long long)blockIdx.z * p.chunk;
+    const unsigned zc = p.ps.enabled ? peer_chunk_order(blockIdx.z, gridDim.z) : blockIdx.z;
+    const long long k0 = p.m_begin + (long long)zc * p.chunk;
     const long long k1 = k0 + p.chunk < p.m_end ? k0 + p.chunk : p.m_end;
     const int n_planes = (int)(k1 - k0) + 2;              // psi planes k0-1 .. k1  (plane idx <-> stage idx % NS)
+    // fused-halo handshake: CTAs holding the slab's first / last plane
+    const bool sync_lo = p.ps.enabled && p.peer_lo_plane && k0 == 0;
+    const bool sync_hi = p.ps.enabled && p.peer_hi_plane && k1 == p.g.n[2];
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -190,6 +195,8 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
             mbar_init(empty0 + 8 * s, TY);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
+        if (sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
     }
     __syncthreads();
 
@@ -334,6 +341,13 @@ __global__ void __launch_bounds__(32 * TY + 32, MINB) jacobi3d_tma_kernel(const 
             }
         }
     }
+    if (sync_lo || sync_hi) {
+        __syncthreads();                                   // every peer store of this CTA has been issued
+        if (threadIdx.x == 0) {
+            if (sync_lo) peer_publish(p.ps.done + 0, p.ps.target_lo, p.ps.sig_lo, p.ps.epoch + 1);
+            if (sync_hi) peer_publish(p.ps.done + 1, p.ps.target_hi, p.ps.sig_hi, p.ps.epoch + 1);
+        }
+    }
     if (NORM) {
         __shared__ double warp_sums[TY + 1];
 #pragma unroll
@@ -464,6 +478,7 @@ struct Launcher {
         static int hints = -1;
         if (hints < 0) { const char* e = getenv("RNMF_L2_HINTS"); hints = e ? atoi(e) : 0; }
         p.l2_hints = hints;
+        p.ps = a.ps;
         return a.partials ? launch_one<true>(grid, tm_psi, tm_rhs, p, s) : launch_one<false>(grid, tm_psi, tm_rhs, p, s);
     }
 };
@@ -484,6 +499,21 @@ int tma_sweep_num_partials(const SweepArgs& a)
     case 13: return Launcher<16, 3, 1>::plan(a, grid, chunk);
     default: return Launcher<8, 4, 2>::plan(a, grid, chunk);
     }
+}
+
+int tma_sweep_boundary_ctas(const SweepArgs& a)
+{
+    dim3 grid;
+    int chunk;
+    switch (a.variant) {
+    case 5: Launcher<8, 5, 2>::plan(a, grid, chunk); break;
+    case 7: Launcher<16, 4>::plan(a, grid, chunk); break;
+    case 8: Launcher<4, 6, 3>::plan(a, grid, chunk); break;
+    case 9: Launcher<8, 3, 2>::plan(a, grid, chunk); break;
+    case 13: Launcher<16, 3, 1>::plan(a, grid, chunk); break;
+    default: Launcher<8, 4, 2>::plan(a, grid, chunk); break;
+    }
+    return (int)(grid.x * grid.y);
 }
 
 int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s)

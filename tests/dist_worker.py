@@ -58,9 +58,10 @@ def run_nccl():
     ctx = R.Context.from_torch_distributed()
     mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
     ok = True
-    for mode in ("peer", "nccl_overlap", "nccl_serial"):
+    for mode in ("peer", "peer_flag_kernels", "nccl_overlap", "nccl_serial"):
         ctx.set_option("halo_overlap", 0 if mode == "nccl_serial" else 1)
-        ctx.set_option("peer_halo", 1 if mode == "peer" else 0)
+        ctx.set_option("peer_halo", 1 if mode.startswith("peer") else 0)
+        ctx.set_option("peer_inkernel", 1 if mode == "peer" else 0)       # handshake inside the sweep kernel vs 1-thread flag kernels
         overlap = mode
         for n, hi, spec, sweeps, ng in CASES:
             dim = len(n)
@@ -72,7 +73,7 @@ def run_nccl():
             psi.fill_synthetic(101)
             rhs.fill_synthetic(202)
             psi.fill_bc()
-            if mode == "peer" and ng == 1:
+            if mode.startswith("peer") and ng == 1:
                 psi.enable_peer_halo()
                 # two calls: the epoch handshake and buffer parity must carry over between calls
                 poisson.jacobi_sweeps(psi, rhs, 2)
