@@ -1,12 +1,10 @@
+# bench.py at 1/2/4/8 GPUs on one box (weak scaling, 768^3 per GPU), as the driver launches it
 nvidia-smi -L | wc -l
-B="--steps 3 --warmup 3 --no-cpu-baseline --no-others"
+B="--steps 3 --warmup 3 --no-cpu-baseline --no-others --e2e-steps 1"
 for n in 1 2 4 8; do
   if [ $n = 1 ]; then timeout 600 python bench.py $B > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
   else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n bench.py --gpus $n $B > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; fi
-  tail -1 gpurun_out/scale_n$n.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2), d['e2e'] and round(d['e2e']['value'],1), d['clocks']['sm_mhz'], d['clocks']['power_w_max'], round(d['roofline']['frac'],3))"
+  tail -1 gpurun_out/scale_n$n.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2), d['e2e'] and round(d['e2e']['value'],1), d['clocks']['sm_mhz'], d['clocks']['power_w_max'], round(d['roofline']['frac'],3), d['gpu_launches'])"
 done
-S="--steps 3 --warmup 3 --sub-iters 200 --no-cpu-baseline --no-others --no-e2e"
-echo "== N=8 nccl path"; RNMF_PEER_HALO=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 $S 2>/dev/null | tail -1 | tee gpurun_out/scale_n8_nccl.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2))"
-echo "== N=8 strong 1024"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29562 bench.py --gpus 8 --workload 3d7_1024 $S 2>/dev/null | tail -1 | tee gpurun_out/scale_n8_strong1024.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2))"
-echo "== N=8 2D weak"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29563 bench.py --gpus 8 --workload 2d5_8192 --steps 3 --warmup 3 --sub-iters 1000 --no-cpu-baseline --no-others --no-e2e 2>/dev/null | tail -1 | tee gpurun_out/scale_n8_2d.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2))"
-timeout 600 python -m pytest tests/test_dist.py -x -q -m gpu 2>&1 | tail -2
+S="--workload 2d5_8192 --steps 3 --warmup 3 --sub-iters 1500 --no-cpu-baseline --no-others --no-e2e"
+echo "== N=8 2D weak"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29563 bench.py --gpus 8 $S 2>/dev/null | tail -1 | tee gpurun_out/scale_n8_2d.json | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],2))"
