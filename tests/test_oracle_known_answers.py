@@ -200,3 +200,26 @@ def test_3d_fill_bc_extrapolation_rule():
             sel |= ia.reshape(shp_a) & ib.reshape(shp_b)
             mask |= sel
     np.testing.assert_array_equal(A[mask], B[mask])
+
+
+def test_gs_3d_extrapolation_matches_plain_python_loop():
+    # the 3D lexicographic sweep used by bench.py's reference arm: i outer, j, k inner, in place
+    # (the continuation of poisson.rs:80-89's loop nest), then fill_bc
+    n = [5, 4, 3]
+    g = ora.geom(n, hi=[5.0, 8.0, 9.0])
+    bc = ora.bcs(3, MIXED_3D)
+    psi, rhs = _rand_frame(g, 11), _rand_frame(g, 12)
+    ora.fill_bc(g, psi, bc)
+    want = psi.copy()
+    c = ora.coefs(g)
+    u = ora.as_grid(g, want)[0]
+    r = ora.as_grid(g, rhs)[0]
+    for _ in range(2):
+        for i in range(1, n[0] + 1):
+            for j in range(1, n[1] + 1):
+                for k in range(1, n[2] + 1):
+                    u[k, j, i] = (c[0] * r[k, j, i] + c[1] * (u[k, j, i + 1] + u[k, j, i - 1])
+                                  + c[2] * (u[k, j + 1, i] + u[k, j - 1, i]) + c[3] * (u[k + 1, j, i] + u[k - 1, j, i]))
+        ora.fill_bc(g, want, bc)
+    ora.gs(g, psi, rhs, bc, 2)
+    np.testing.assert_array_equal(psi, want)
