@@ -892,6 +892,10 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
 
     const bool dist = psi->distributed && c->nranks > 1;
     if (dist) {
+        // Entry exchange of the current buffer's halos.  It is also what orders the shell copy
+        // above (which rewrites d2's ghost slices) before the neighbours' first peer stores into
+        // d2 of this call: a neighbour cannot leave its own entry exchange before this rank's
+        // send/recv, which is stream-ordered after the copy.
         rc = halo_exchange_on(psi, psi->d, s);
         if (rc) return rc;
     }
