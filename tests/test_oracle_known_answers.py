@@ -223,3 +223,85 @@ def test_gs_3d_extrapolation_matches_plain_python_loop():
         ora.fill_bc(g, want, bc)
     ora.gs(g, psi, rhs, bc, 2)
     np.testing.assert_array_equal(psi, want)
+
+
+def test_outer_loop_against_an_independent_pure_python_restatement():
+    """Second, independent restatement (plain Python floats, written from poisson.rs / main.rs /
+    dataframe.rs line by line, sharing no code with the C oracle) of the whole magnetostatics loop on
+    a small droplet case with a bubble that covers several cells: mu, get_laplace, get_source,
+    lexicographic GS sweeps + Neumann fill, the operator chain, sum, the under-relaxed update."""
+    n, L = 9, 9.0
+    h_far, relax, n_iter, n_sub, centre, radius, mus, tol = (0.25, 1.0), 0.2, 3, 4, (4.3, 4.6), 2.2, (3.2, 1.0), 0.1
+    dx = (L / n, L / n)                                      # mesh.rs:40
+    G = n + 2
+
+    def at(i, j):                                            # mod.rs:31-37, ng = 1
+        return (i + 1) + G * (j + 1)
+
+    def mu(i, j):                                            # poisson.rs:47-64
+        x, y = (i + 0.5) * dx[0], (j + 0.5) * dx[1]
+        inside = (x - centre[0]) * (x - centre[0]) + (y - centre[1]) * (y - centre[1]) <= radius * radius
+        return mus[0] if inside else mus[1]
+
+    def fill_neumann(u, grad):                               # dataframe.rs:289-322, ng = 1
+        for d in range(2):
+            for t in range(n):
+                lo_g, lo_m = (at(-1, t), at(0, t)) if d == 0 else (at(t, -1), at(t, 0))
+                hi_g, hi_m = (at(n, t), at(n - 1, t)) if d == 0 else (at(t, n), at(t, n - 1))
+                u[lo_g] = u[lo_m] - grad[d] * (2.0 * 1 - 1.0) * dx[d]
+                u[hi_g] = u[hi_m] + grad[d] * (2.0 * (0 + 1) - 1.0) * dx[d]
+
+    grad = (-h_far[0] / dx[0], -h_far[1] / dx[1])            # main.rs:40-44
+    psi = [0.0] * (G * G)
+    for j in range(n):
+        for i in range(n):
+            x, y = 0.0 + (i + 0.5) * dx[0], 0.0 + (j + 0.5) * dx[1]           # mesh.rs:69-70
+            psi[at(i, j)] = -h_far[0] / dx[0] * x - h_far[1] / dx[1] * y      # main.rs:50-53
+    fill_neumann(psi, grad)
+    dx2, dy2 = dx[0] * dx[0], dx[1] * dx[1]
+    alpha, beta, gamma = dx2 * dy2 / (2.0 * (dx2 + dy2)), dy2 / (2.0 * (dx2 + dy2)), dx2 / (2.0 * (dx2 + dy2))
+    trace, sum_diff, it = [], 1.0, 0
+    while it < n_iter and sum_diff > tol:                    # main.rs:65
+        lap = [0.0] * (G * G)                                # poisson.rs:13-36
+        for j in range(n):
+            for i in range(n):
+                lap[at(i, j)] = (psi[at(i + 1, j)] * (mu(i + 1, j) + mu(i, j)) / 2.0
+                                 + psi[at(i - 1, j)] * (mu(i - 1, j) + mu(i, j)) / 2.0
+                                 + psi[at(i, j + 1)] * (mu(i, j + 1) + mu(i, j)) / 2.0
+                                 + psi[at(i, j - 1)] * (mu(i, j - 1) + mu(i, j)) / 2.0
+                                 - (psi[at(i, j)] * (mu(i + 1, j) + mu(i - 1, j) + mu(i, j + 1) + mu(i, j - 1) + 4.0 * mu(i, j))) / 2.0)
+        for t in range(n):                                   # Dirichlet(0) fill of lap, dataframe.rs:324-355
+            lap[at(-1, t)] = 2.0 * 0.0 - lap[at(0, t)]
+            lap[at(n, t)] = 2.0 * 0.0 - lap[at(n - 1, t)]
+        for t in range(n):
+            lap[at(t, -1)] = 2.0 * 0.0 - lap[at(t, 0)]
+            lap[at(t, n)] = 2.0 * 0.0 - lap[at(t, n - 1)]
+        src = [0.0] * (G * G)                                # poisson.rs:38-44
+        for j in range(n):
+            for i in range(n):
+                src[at(i, j)] = -(1.0 - 1.0 / relax) / mu(i, j)
+        rhs = [a * b for a, b in zip(src, lap)]
+        star = list(psi)                                     # poisson.rs:71
+        for _ in range(n_sub):                               # poisson.rs:80-89
+            for i in range(n):
+                for j in range(n):
+                    star[at(i, j)] = (alpha * rhs[at(i, j)] + beta * (star[at(i + 1, j)] + star[at(i - 1, j)])
+                                      + gamma * (star[at(i, j + 1)] + star[at(i, j - 1)]))
+            fill_neumann(star, grad)
+        diff = [a + (-1.0 * b) for a, b in zip(star, psi)]   # main.rs:68
+        sum_diff = 0.0
+        for j in range(n):                                   # poisson.rs:94-100, flat order
+            for i in range(n):
+                sum_diff += abs(diff[at(i, j)])
+        psi = [a + relax * b for a, b in zip(psi, diff)]     # main.rs:70
+        fill_neumann(psi, grad)                              # main.rs:71
+        trace.append(sum_diff)
+        it += 1
+
+    g = ora.geom([n, n], hi=[L, L])
+    m = ora.model(h_far=h_far, relax=relax, n_iter=n_iter, n_sub_iter=n_sub, bubble_centre=centre, bubble_radius=radius, mu=mus, tol=tol)
+    got, tr, its = ora.zeros(g), np.zeros(n_iter), C.c_int64()
+    assert ora.lib().ora_magnetostatics_run(C.byref(g), got, C.byref(m), 0, tr, C.byref(its)) == 0
+    assert its.value == it and tr[:it].tolist() == trace
+    np.testing.assert_array_equal(got, np.array(psi))
+    assert len({mu(i, j) for i in range(n) for j in range(n)}) == 2      # the droplet really is inside the mesh
