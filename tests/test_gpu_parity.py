@@ -626,3 +626,31 @@ def test_index_and_index_mut(R, ctx):
     np.testing.assert_array_equal(host2, host)
     with pytest.raises(R.RnmfError):
         f[(8, 0, 0, 0)]
+
+
+def test_context_and_frame_lifecycle_frees_device_memory(R):
+    """Contexts and frames are created and destroyed repeatedly (the Rust wrapper frees in Drop);
+    device memory must come back and a context destroyed with live Python frames must not crash."""
+    import gc
+    import torch
+    from rnmf_b200 import poisson
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for rep in range(3):
+        c = R.Context(0)
+        mesh = R.CartesianMesh.new([0.0] * 3, [96.0] * 3, [96, 96, 96])
+        _, bc = _bc_pair(R, 3, MIXED_3D)
+        frames = [R.CartesianDataFrame.new_from(mesh, bc, 1, 1, c) for _ in range(4)]
+        frames[0].fill_synthetic(1)
+        frames[1].fill_synthetic(2)
+        frames[0].fill_bc()
+        assert poisson.jacobi_sweeps(frames[0], frames[1], 6, want_norm=True) > 0.0
+        if rep == 0:
+            for f in frames:
+                f.close()
+        c.close()                       # rep > 0: closes the still-open frames first
+        assert all(f._h is None for f in frames)
+    gc.collect()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20     # nothing but allocator slack left behind
