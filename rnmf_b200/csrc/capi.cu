@@ -34,7 +34,7 @@ extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
            "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi3d_tb2{128x12,128x8},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -936,7 +936,27 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
         }
     }
 
+    // two sweeps per pass over HBM (kernels_sweep_tb2.cu): every pair of sweeps that does not carry
+    // the norm; a face without a Dirichlet/Neumann rule must be a slab neighbour
+    bool all_faces = true;
+    for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
+    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 20 || c->sweep_variant == 21);
+    const bool tb2_single = tb2_variant && !dist && fused && all_faces;
+    const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
+
     for (int64_t it = it0; it < n_sweeps; ++it) {
+        if (tb2_single && it + 2 <= n_pairable) {
+            Tb2Args t;
+            memset(&t, 0, sizeof(t));
+            t.a = a;
+            t.a.in = psi->d; t.a.out = psi->d2; t.a.partials = nullptr;
+            t.a.k_begin = 0; t.a.k_end = m;
+            RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
+            double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
+            psi->parity ^= 1;
+            ++it;
+            continue;
+        }
         const bool want_norm = l1_update && it == n_sweeps - 1;
         a.in = psi->d;
         a.out = psi->d2;

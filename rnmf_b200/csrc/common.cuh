@@ -162,6 +162,26 @@ struct SweepArgs {
     PeerSync ps;             // in-kernel handshake (enabled = 0: none)
 };
 bool sweep_supports_peer_halo(const SweepArgs& a);
+
+// Two sweeps per pass over HBM (kernels_sweep_tb2.cu).  `a` carries the frame, the range of output
+// planes of the "A" chunks and, for slabs, the full-step handshake and the neighbours' ghost planes
+// of the `out` buffer; the rest is the half-step exchange of u1 boundary planes between slabs.
+struct Tb2Args {
+    SweepArgs a;
+    int b_lo, b_hi;                            // one-plane "B" chunk for the slab's first / last plane
+    double* peer_u1_lo;                        // neighbours' scratch planes receiving my u1(0) / u1(m-1)
+    double* peer_u1_hi;
+    const double* u1_in_lo;                    // my scratch planes (written by the neighbours)
+    const double* u1_in_hi;
+    const unsigned long long* half_wait_lo;    // my half-step flags / the neighbours' (peer-mapped)
+    const unsigned long long* half_wait_hi;
+    unsigned long long* half_sig_lo;
+    unsigned long long* half_sig_hi;
+    unsigned long long* done_b;                // [2] completion counters of the B chunks
+    unsigned long long target_b_lo, target_b_hi;
+};
+int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s);
+int double_sweep_boundary_ctas(const Tb2Args& t);
 int sweep_boundary_ctas(const SweepArgs& a);     // CTAs per boundary side (tiles across the slice) of the kernel that will run
 
 // peer-memory halo handshake (kernels_peer.cu): epoch flags live in each rank's own memory and

@@ -1,0 +1,485 @@
+// kernels_sweep_tb2.cu -- K1, temporally blocked: TWO Jacobi sweeps (each followed by the ng=1
+// ghost fill, poisson.rs:80-89 + dataframe.rs:289-355) per pass over HBM.
+//
+// The single-sweep TMA kernel moves 24 B per update and sits at the DRAM limit of the part; the
+// only way past that limit is fewer bytes per update.  Here a CTA streams psi (u0) and rhs once,
+// forms u1 = sweep(u0) in shared memory and writes only u2 = sweep(u1): 24 B per TWO updates.
+//
+//   * CTA tile: 128 x TY cells of u2, a chunk of z-planes.  u1 is needed on the tile grown by one
+//     cell in x and y (no corners) and by one plane in z, u0 on the tile grown by two.
+//   * producer warp: per plane one TMA box of u0 ((128+4) x (TY+4), the two-cell x halo keeps the
+//     interior 16-byte aligned in shared memory) and one of rhs ((128+4) x (TY+2)) into a 4-stage
+//     ring (full/empty mbarriers), exactly as in kernels_sweep_tma.cu.
+//   * TY "row" warps own one tile row each (lane l: cell pairs 2l,2l+1 and 64+2l,65+2l), two more
+//     row warps own the halo rows j0-1 and j0+TY (level 1 only), one warp owns the two halo columns
+//     i0-1 and i0+128 (level 1 only).  Level 1 is register z-marched over u0 exactly like the
+//     single-sweep kernel; its result goes to a 4-slot shared-memory ring of u1 planes, together
+//     with the ghost values fill_bc would give u1 on the physical x/y faces.  Level 2 is register
+//     z-marched over the lane's own u1 values (the z ghosts of u1 are formed in registers) and
+//     reads the N/S/E/W neighbours of u1 from the ring.
+//   * u1 ring protocol: one mbarrier per slot, every level-1 warp arrives after writing plane it
+//     into slot it%4.  A warp waits for plane it-1 before its level-2 reads and for plane it-2
+//     before it overwrites slot it%4 (all warps have then finished iteration it-3, whose level-2
+//     reads were the last of the plane that lived in that slot): warps may drift a whole plane
+//     apart, no CTA-wide barrier in the loop.
+//   * u2 is stored with the fused ghost fill of the output frame, as in the single-sweep kernel.
+//
+// Slabs (one GPU per z-slab): u2 of the slab's first/last plane needs the neighbour's u1 boundary
+// plane.  "A" chunks cover the planes that do not (1..m-2); the A chunks next to a neighbour store
+// u1 of plane 0 / m-1 into that neighbour's scratch plane (peer memory, NVLink) and publish the
+// half step; one-plane "B" chunks, scheduled last, wait for the neighbour's half step, recompute
+// u1 of their two planes, take the missing u1 plane from the scratch and store u2 both locally and
+// into the neighbour's ghost plane, then publish the full step (see PeerSync in common.cuh).
+//
+// Arithmetic: the same explicitly rounded sequence as every other sweep kernel: u2 is bit-identical
+// to two single sweeps.
+#include <stdlib.h>
+
+#include "tma_util.cuh"
+
+namespace {
+using namespace tmau;
+
+struct Tb2Params {
+    FrameGeom g;
+    double* out;
+    SweepCoef c;
+    FaceSet faces;
+    long long m_begin, m_end;    // output planes of the A chunks
+    int chunk;
+    int n_a;                     // A chunks: blockIdx.z < n_a; then the B chunks (lo first)
+    int b_lo, b_hi;              // one-plane B chunk for the slab's first / last plane
+    // slab neighbours (all null on a single GPU)
+    double* peer_u1_lo;          // lo neighbour's scratch plane that receives my u1(0)
+    double* peer_u1_hi;          // hi neighbour's scratch plane that receives my u1(m-1)
+    const double* u1_in_lo;      // my scratch plane holding the lo neighbour's last u1 plane
+    const double* u1_in_hi;      // my scratch plane holding the hi neighbour's first u1 plane
+    double* peer_lo_plane;       // neighbour ghost planes of its `out` buffer (my u2(0) / u2(m-1))
+    double* peer_hi_plane;
+    PeerSync ps;                 // full-step flags / A-boundary counters
+    const unsigned long long* half_wait_lo;   // my half-step flags, written by the neighbours' A chunks
+    const unsigned long long* half_wait_hi;
+    unsigned long long* half_sig_lo;          // neighbours' half-step flags (peer-mapped)
+    unsigned long long* half_sig_hi;
+    unsigned long long* done_b;               // [2] completion counters of the B chunks
+    unsigned long long target_b_lo, target_b_hi;
+};
+
+template <int TY>
+struct Tb2Cfg {
+    static constexpr int TX = 128;
+    static constexpr int NS = 4;                          // u0/rhs stages == u1 slots (loop unrolled by 4)
+    static constexpr int BX = TX + 4;
+    static constexpr int U0_ROWS = TY + 4;
+    static constexpr int R_ROWS = TY + 2;
+    static constexpr int U0_BYTES = BX * U0_ROWS * 8;
+    static constexpr int U0_STAGE = (U0_BYTES + 127) / 128 * 128;
+    static constexpr int RHS_BYTES = BX * R_ROWS * 8;
+    static constexpr int RHS_STAGE = (RHS_BYTES + 127) / 128 * 128;
+    static constexpr int U1_SLOT = RHS_STAGE;
+    static constexpr int RHS_OFF = NS * U0_STAGE;
+    static constexpr int U1_OFF = RHS_OFF + NS * RHS_STAGE;
+    static constexpr int BAR_OFF = U1_OFF + NS * U1_SLOT;
+    static constexpr int SMEM = BAR_OFF + 3 * NS * 8 + 128;
+    static constexpr int NCONS = TY + 3;                  // TY row warps + 2 halo-row warps + 1 halo-column warp
+    static constexpr int THREADS = 32 * (TY + 4);         // + producer warp
+};
+
+template <int TY>
+__global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __grid_constant__ CUtensorMap tm_u0,
+                                                                         const __grid_constant__ CUtensorMap tm_rhs,
+                                                                         const __grid_constant__ Tb2Params p)
+{
+    using Cfg = Tb2Cfg<TY>;
+    constexpr int TX = Cfg::TX, NS = Cfg::NS, BX = Cfg::BX;
+    static_assert(TY <= 16, "the halo-column warp maps 16 rows per side");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, u1_0 = sb + Cfg::U1_OFF;
+    const uint32_t full0 = sb + Cfg::BAR_OFF, empty0 = full0 + NS * 8, u1full0 = empty0 + NS * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n0 = p.g.n[0], n1 = p.g.n[1], n2 = p.g.n[2];
+    const long long i0 = (long long)blockIdx.x * TX;
+    const long long j0 = (long long)blockIdx.y * TY;
+
+    // ---- which planes: A chunk (blockIdx.z < n_a) or one-plane B chunk -------------------------
+    const int bz = (int)blockIdx.z;
+    const bool is_b = bz >= p.n_a;
+    long long k0, k1;
+    if (!is_b) {
+        const unsigned zc = p.ps.enabled ? peer_chunk_order((unsigned)bz, (unsigned)p.n_a) : (unsigned)bz;
+        k0 = p.m_begin + (long long)zc * p.chunk;
+        k1 = k0 + p.chunk < p.m_end ? k0 + p.chunk : p.m_end;
+    } else {
+        k0 = (p.b_lo && bz == p.n_a) ? 0 : n2 - 1;
+        k1 = k0 + 1;
+    }
+    const long long a = k0 > 0 ? k0 - 1 : 0;              // level-1 planes a..b
+    const long long b = k1 < n2 ? k1 : n2 - 1;
+    const int nL1 = (int)(b - a) + 1;
+    const int n_planes = nL1 + 2;                         // u0 planes a-1..b+1  (plane a-1+idx <-> stage idx % 4)
+    const int n_iters = nL1 + (b < k1 ? 1 : 0);           // iteration it: level 1 of plane a+it, level 2 of plane a+it-1
+    const int it_l2_first = (int)(k0 - a) + 1;
+
+    // slab handshake roles of this CTA
+    const bool a_sync_lo = !is_b && p.peer_u1_lo && k0 == p.m_begin;     // computes u1(0), reads ghost plane -1 of u0
+    const bool a_sync_hi = !is_b && p.peer_u1_hi && k1 == p.m_end;
+    const bool b_is_lo = is_b && k0 == 0 && p.b_lo;
+    const bool b_is_hi = is_b && !b_is_lo;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, Cfg::NCONS);
+            mbar_init(u1full0 + 8 * s, Cfg::NCONS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (a_sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
+        if (a_sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
+        if (b_is_lo) peer_spin_wait(p.half_wait_lo, p.ps.epoch + 1, p.ps.status);
+        if (b_is_hi) peer_spin_wait(p.half_wait_hi, p.ps.epoch + 1, p.ps.status);
+    }
+    __syncthreads();
+
+    const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
+
+    if (warp == TY + 3) {
+        // ------------------------------ producer warp ------------------------------
+        if (lane == 0) {
+            const int cx = (int)(p.g.xoff + p.g.ng + i0 - 2);
+            const int cy_u0 = (int)(p.g.ng + j0 - 2);
+            const int cy_rhs = cy_u0 + 1;
+            int cz = (int)(p.g.kg + a - 1);
+            uint32_t wrap = 0;
+            for (int base = 0; base < n_planes; base += NS, ++wrap) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int idx = base + s;
+                    if (idx < n_planes) {
+                        if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1);
+                        const bool with_rhs = idx >= 1 && idx <= nL1;
+                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::U0_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
+                        tma_load_3d(u0_0 + s * Cfg::U0_STAGE, &tm_u0, cx, cy_u0, cz, full0 + 8 * s);
+                        if (with_rhs) tma_load_3d(rhs_0 + s * Cfg::RHS_STAGE, &tm_rhs, cx, cy_rhs, cz, full0 + 8 * s);
+                        ++cz;
+                    }
+                }
+            }
+        }
+    } else if (warp == TY + 2) {
+        // ------------------------------ halo-column warp (level 1 only) ------------------------------
+        // lanes 0..15: column i0-1, rows j0+lane; lanes 16..31: column i0+128, rows j0+lane-16
+        const int side = lane >> 4, r = lane & 15;
+        const bool act = r < TY;
+        const int rc = act ? r : 0;
+        const int col = side ? TX : -1;
+        const long long i = i0 + col, j = j0 + rc;
+        const bool ok = act && i >= 0 && i < n0 && j < n1;
+        const uint32_t hp = u0_0 + (uint32_t)(((rc + 2) * BX + col + 2) * 8);
+        const uint32_t hr = rhs_0 + (uint32_t)(((rc + 1) * BX + col + 2) * 8);
+        const uint32_t hu = u1_0 + (uint32_t)(((rc + 1) * BX + col + 2) * 8);
+
+        mbar_wait(full0, 0);
+        double below = lds1(hp);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        double cur = lds1(hp + Cfg::U0_STAGE);
+
+        uint32_t wrap = 0;
+        for (int base = 0; base < nL1; base += NS, ++wrap) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int it = base + s;
+                if (it < nL1) {
+                    const int sc = (s + 1) % NS, sn = (s + 2) % NS;
+                    mbar_wait(full0 + 8 * sn, (wrap + (uint32_t)((s + 2) / NS)) & 1u);
+                    const uint32_t pc = hp + sc * Cfg::U0_STAGE;
+                    const double above = lds1(hp + sn * Cfg::U0_STAGE);
+                    const double nn = lds1(pc + BX * 8), ss = lds1(pc - BX * 8);
+                    const double ee = lds1(pc + 8), ww = lds1(pc - 8);
+                    const double rr = lds1(hr + sc * Cfg::RHS_STAGE);
+                    const double v = upd3(c0, c1, c2, c3, rr, ee, ww, nn, ss, above, below);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * sc);
+                    if (it >= NS) mbar_wait(u1full0 + 8 * ((s + 2) % NS), (wrap - (s < 2 ? 1u : 0u)) & 1u);
+                    if (ok) sts1(hu + s * Cfg::U1_SLOT, v);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(u1full0 + 8 * s);
+                    below = cur;
+                    cur = above;
+                }
+            }
+        }
+    } else {
+        // ------------------------------ row warps ------------------------------
+        // warps 0..TY-1: tile rows (levels 1 and 2); warp TY: halo row j0-1; warp TY+1: halo row j0+TY (level 1 only)
+        const bool do_l2 = warp < TY;
+        const int rr = do_l2 ? warp : (warp == TY ? -1 : TY);
+        const long long j = j0 + rr;
+        const bool row_ok = j >= 0 && j < n1;
+        const long long ia = i0 + 2 * lane, ib = ia + 64;
+        const bool va0 = row_ok && ia < n0, va1 = row_ok && ia + 1 < n0;
+        const bool vb0 = row_ok && ib < n0, vb1 = row_ok && ib + 1 < n0;
+        const bool full = vb1;
+        // byte offsets: cell (i0+c, j0+r) sits at ((r+2)*BX + c+2)*8 in a u0 stage and at ((r+1)*BX + c+2)*8
+        // in an rhs stage / u1 slot
+        const uint32_t pa = u0_0 + (uint32_t)(((rr + 2) * BX + 2 + 2 * lane) * 8);
+        const uint32_t ra = rhs_0 + (uint32_t)(((rr + 1) * BX + 2 + 2 * lane) * 8);
+        const uint32_t ua = u1_0 + (uint32_t)(((rr + 1) * BX + 2 + 2 * lane) * 8);
+        const long long pitch = p.g.pitch, plane_sz = p.g.plane;
+        // plane offset of the lane's first cell inside a grown xy plane (scratch / peer ghost planes)
+        const long long xy_off = p.g.xoff + (ia + p.g.ng) + pitch * (j + p.g.ng);
+        double* oa = p.out + p.g.at(ia, j, k0, 0);
+
+        // ghost rules of the six faces (a face with mode 0 is a slab neighbour: handled below)
+        const Face1 fx0 = make_face1(p.faces.f[0], true), fx1 = make_face1(p.faces.f[1], true);
+        const Face1 fy0 = make_face1(p.faces.f[2], true), fy1 = make_face1(p.faces.f[3], true);
+        const Face1 fz0 = make_face1(p.faces.f[4], true), fz1 = make_face1(p.faces.f[5], true);
+        const bool do_xlo = do_l2 && fx0.on && va0 && ia == 0;
+        const long long last = n0 - 1;
+        const int xhi_sel = !(do_l2 && fx1.on) ? -1 : (va0 && ia == last) ? 0 : (va1 && ia + 1 == last) ? 1 : (vb0 && ib == last) ? 2 : (vb1 && ib + 1 == last) ? 3 : -1;
+        const bool do_ylo = do_l2 && fy0.on && j == 0, do_yhi = do_l2 && fy1.on && j == n1 - 1;
+        const bool any_xy = do_xlo || xhi_sel >= 0 || do_ylo || do_yhi;
+        const uint32_t xhi_off = (uint32_t)((xhi_sel >= 2 ? 512 : 0) + ((xhi_sel & 1) + 1) * 8);
+        // the slab's first / last plane: iteration whose level 2 produces it (-1: not in this chunk)
+        const int it_zlo = k0 == 0 ? 1 : -1;
+        const int it_zhi = k1 == n2 ? n_iters - 1 : -1;
+        // u1 boundary planes for the slab neighbours: level-1 iterations that produce plane 0 / m-1
+        const int it_u1lo = (a_sync_lo && do_l2) ? 0 : -1;
+        const int it_u1hi = (a_sync_hi && do_l2) ? nL1 - 1 : -1;
+
+        mbar_wait(full0, 0);
+        double2 below_a = lds2(pa), below_b = lds2(pa + 512);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        double2 cur_a = lds2(pa + Cfg::U0_STAGE), cur_b = lds2(pa + Cfg::U0_STAGE + 512);
+
+        const double2 zero2 = make_double2(0.0, 0.0);
+        double2 u1lo_a = zero2, u1lo_b = zero2;       // u1 of plane q-1 (q = plane level 2 is producing)
+        double2 u1c_a = zero2, u1c_b = zero2;         // u1 of plane q
+        double2 rp_a = zero2, rp_b = zero2;           // rhs of plane q
+
+        uint32_t wrap = 0;
+        for (int base = 0; base < n_iters; base += NS, ++wrap) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int it = base + s;
+                if (it < n_iters) {
+                    double2 u1n_a = zero2, u1n_b = zero2, rc_a = zero2, rc_b = zero2;
+                    const bool l1_on = it < nL1;
+                    if (l1_on) {
+                        // ---------------- level 1: u1 of plane a+it ----------------
+                        const int sc = (s + 1) % NS, sn = (s + 2) % NS;
+                        mbar_wait(full0 + 8 * sn, (wrap + (uint32_t)((s + 2) / NS)) & 1u);
+                        const uint32_t pn = pa + sn * Cfg::U0_STAGE, pc = pa + sc * Cfg::U0_STAGE, pr = ra + sc * Cfg::RHS_STAGE;
+                        const double2 above_a = lds2(pn), above_b = lds2(pn + 512);
+                        const double2 n_a = lds2(pc + BX * 8), n_b = lds2(pc + BX * 8 + 512);
+                        const double2 s_a = lds2(pc - BX * 8), s_b = lds2(pc - BX * 8 + 512);
+                        rc_a = lds2(pr); rc_b = lds2(pr + 512);
+                        const double w_a0 = lds1(pc - 8), e_a1 = lds1(pc + 16);
+                        const double w_b0 = lds1(pc + 512 - 8), e_b1 = lds1(pc + 512 + 16);
+
+                        u1n_a.x = upd3(c0, c1, c2, c3, rc_a.x, cur_a.y, w_a0, n_a.x, s_a.x, above_a.x, below_a.x);
+                        u1n_a.y = upd3(c0, c1, c2, c3, rc_a.y, e_a1, cur_a.x, n_a.y, s_a.y, above_a.y, below_a.y);
+                        u1n_b.x = upd3(c0, c1, c2, c3, rc_b.x, cur_b.y, w_b0, n_b.x, s_b.x, above_b.x, below_b.x);
+                        u1n_b.y = upd3(c0, c1, c2, c3, rc_b.y, e_b1, cur_b.x, n_b.y, s_b.y, above_b.y, below_b.y);
+
+                        // odd n0: the last valid cell is the first of a pair, whose E neighbour at level 2 is the
+                        // pair's second register: it must hold the x-hi ghost of u1, not a stencil value
+                        if (xhi_sel == 0) u1n_a.y = ghost1(fx1, u1n_a.x);
+                        if (xhi_sel == 2) u1n_b.y = ghost1(fx1, u1n_b.x);
+
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty0 + 8 * sc);      // stage of plane a+it is free for this warp
+                        below_a = cur_a; below_b = cur_b;
+                        cur_a = above_a; cur_b = above_b;
+
+                        // slot s held plane a+it-4, last read by level 2 in iteration it-3: every warp has
+                        // finished that iteration once it has arrived for plane a+it-2
+                        if (it >= NS) mbar_wait(u1full0 + 8 * ((s + 2) % NS), (wrap - (s < 2 ? 1u : 0u)) & 1u);
+                        const uint32_t us = ua + s * Cfg::U1_SLOT;
+                        sstore4(us, u1n_a, u1n_b, full, va0, va1, vb0, vb1);
+                        if (any_xy) {
+                            // what fill_bc gives u1 on the physical x / y faces (read by level 2 of the edge cells)
+                            if (do_xlo) sts1(us - 8, ghost1(fx0, u1n_a.x));
+                            if (xhi_sel >= 0) {
+                                const double m = xhi_sel == 0 ? u1n_a.x : xhi_sel == 1 ? u1n_a.y : xhi_sel == 2 ? u1n_b.x : u1n_b.y;
+                                sts1(us + xhi_off, ghost1(fx1, m));
+                            }
+                            if (do_ylo) sstore4(us - BX * 8, ghost1(fy0, u1n_a), ghost1(fy0, u1n_b), full, va0, va1, vb0, vb1);
+                            if (do_yhi) sstore4(us + BX * 8, ghost1(fy1, u1n_a), ghost1(fy1, u1n_b), full, va0, va1, vb0, vb1);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(u1full0 + 8 * s);
+                        // slab neighbours get u1 of my boundary plane (half step) over NVLink
+                        if (it == it_u1lo) store4(p.peer_u1_lo + xy_off, u1n_a, u1n_b, full, va0, va1, vb0, vb1);
+                        if (it == it_u1hi) store4(p.peer_u1_hi + xy_off, u1n_a, u1n_b, full, va0, va1, vb0, vb1);
+                    }
+                    if (do_l2 && it >= it_l2_first) {
+                        // ---------------- level 2: u2 of plane q = a+it-1 ----------------
+                        const int sp = (s + 3) % NS;                      // slot of u1 plane q
+                        mbar_wait(u1full0 + 8 * sp, (wrap - (s < 1 ? 1u : 0u)) & 1u);
+                        const uint32_t up = ua + sp * Cfg::U1_SLOT;
+                        const double2 n_a = lds2(up + BX * 8), n_b = lds2(up + BX * 8 + 512);
+                        const double2 s_a = lds2(up - BX * 8), s_b = lds2(up - BX * 8 + 512);
+                        const double w_a0 = lds1(up - 8), e_a1 = lds1(up + 16);
+                        const double w_b0 = lds1(up + 512 - 8), e_b1 = lds1(up + 512 + 16);
+                        // z neighbours of u1: registers, the face's ghost rule, or the neighbour slab's plane
+                        double2 dn_a = u1lo_a, dn_b = u1lo_b, upl_a = u1n_a, upl_b = u1n_b;
+                        if (it == it_zlo) {
+                            if (fz0.on) { dn_a = ghost1(fz0, u1c_a); dn_b = ghost1(fz0, u1c_b); }
+                            else if (p.u1_in_lo) {
+                                const double* q = p.u1_in_lo + xy_off;
+                                if (full) { dn_a = *reinterpret_cast<const double2*>(q); dn_b = *reinterpret_cast<const double2*>(q + 64); }
+                                else {
+                                    if (va0) dn_a.x = q[0];
+                                    if (va1) dn_a.y = q[1];
+                                    if (vb0) dn_b.x = q[64];
+                                    if (vb1) dn_b.y = q[65];
+                                }
+                            }
+                        }
+                        if (it == it_zhi) {
+                            if (fz1.on) { upl_a = ghost1(fz1, u1c_a); upl_b = ghost1(fz1, u1c_b); }
+                            else if (p.u1_in_hi) {
+                                const double* q = p.u1_in_hi + xy_off;
+                                if (full) { upl_a = *reinterpret_cast<const double2*>(q); upl_b = *reinterpret_cast<const double2*>(q + 64); }
+                                else {
+                                    if (va0) upl_a.x = q[0];
+                                    if (va1) upl_a.y = q[1];
+                                    if (vb0) upl_b.x = q[64];
+                                    if (vb1) upl_b.y = q[65];
+                                }
+                            }
+                        }
+                        double2 na, nb;
+                        na.x = upd3(c0, c1, c2, c3, rp_a.x, u1c_a.y, w_a0, n_a.x, s_a.x, upl_a.x, dn_a.x);
+                        na.y = upd3(c0, c1, c2, c3, rp_a.y, e_a1, u1c_a.x, n_a.y, s_a.y, upl_a.y, dn_a.y);
+                        nb.x = upd3(c0, c1, c2, c3, rp_b.x, u1c_b.y, w_b0, n_b.x, s_b.x, upl_b.x, dn_b.x);
+                        nb.y = upd3(c0, c1, c2, c3, rp_b.y, e_b1, u1c_b.x, n_b.y, s_b.y, upl_b.y, dn_b.y);
+
+                        store4(oa, na, nb, full, va0, va1, vb0, vb1);
+                        if (any_xy) {
+                            if (do_xlo) oa[-1] = ghost1(fx0, na.x);
+                            if (xhi_sel >= 0) {
+                                const double m = xhi_sel == 0 ? na.x : xhi_sel == 1 ? na.y : xhi_sel == 2 ? nb.x : nb.y;
+                                oa[(xhi_sel >= 2 ? 64 : 0) + (xhi_sel & 1) + 1] = ghost1(fx1, m);
+                            }
+                            if (do_ylo) store4(oa - pitch, ghost1(fy0, na), ghost1(fy0, nb), full, va0, va1, vb0, vb1);
+                            if (do_yhi) store4(oa + pitch, ghost1(fy1, na), ghost1(fy1, nb), full, va0, va1, vb0, vb1);
+                        }
+                        if (it == it_zlo) {
+                            if (fz0.on) store4(oa - plane_sz, ghost1(fz0, na), ghost1(fz0, nb), full, va0, va1, vb0, vb1);
+                            if (p.peer_lo_plane) store4(p.peer_lo_plane + xy_off, na, nb, full, va0, va1, vb0, vb1);
+                        }
+                        if (it == it_zhi) {
+                            if (fz1.on) store4(oa + plane_sz, ghost1(fz1, na), ghost1(fz1, nb), full, va0, va1, vb0, vb1);
+                            if (p.peer_hi_plane) store4(p.peer_hi_plane + xy_off, na, nb, full, va0, va1, vb0, vb1);
+                        }
+                        oa += plane_sz;
+                    }
+                    u1lo_a = u1c_a; u1lo_b = u1c_b;
+                    u1c_a = u1n_a; u1c_b = u1n_b;
+                    rp_a = rc_a; rp_b = rc_b;
+                }
+            }
+        }
+    }
+    if (a_sync_lo || a_sync_hi || is_b) {
+        if (p.ps.enabled) {
+            __syncthreads();                                   // every peer store of this CTA has been issued
+            if (threadIdx.x == 0) {
+                if (a_sync_lo) peer_publish(p.ps.done + 0, p.ps.target_lo, p.half_sig_lo, p.ps.epoch + 1);
+                if (a_sync_hi) peer_publish(p.ps.done + 1, p.ps.target_hi, p.half_sig_hi, p.ps.epoch + 1);
+                if (b_is_lo) peer_publish(p.done_b + 0, p.target_b_lo, p.ps.sig_lo, p.ps.epoch + 2);
+                if (b_is_hi) peer_publish(p.done_b + 1, p.target_b_hi, p.ps.sig_hi, p.ps.epoch + 2);
+            }
+        }
+    }
+}
+
+template <int TY>
+struct Tb2Launcher {
+    using Cfg = Tb2Cfg<TY>;
+    // chunk length: whole waves of one CTA per SM, each CTA paying chunk+3 plane iterations
+    static void plan(const Tb2Args& t, dim3& grid, int& chunk, int& n_a)
+    {
+        const FrameGeom& g = t.a.g;
+        const long long span = t.a.k_end - t.a.k_begin;
+        const long long tiles = ((g.n[0] + 127) / 128) * ((g.n[1] + TY - 1) / TY);
+        long long best_c = 1, best_cost = -1;
+        static const int cand[] = { 2, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128, 192, 256 };
+        for (int c : cand) {
+            const long long cc = c > span ? span : c;
+            if (cc < 1) break;
+            const long long chunks = (span + cc - 1) / cc;
+            if (chunks <= 60000) {
+                const long long waves = (tiles * chunks + 147) / 148;
+                const long long cost = waves * (cc + 3);
+                if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_c = cc; }
+            }
+            if (c >= span) break;
+        }
+        if (t.a.chunk_override > 0) best_c = t.a.chunk_override > span ? span : t.a.chunk_override;
+        if (best_c < 1) best_c = 1;
+        chunk = (int)best_c;
+        n_a = (int)((span + best_c - 1) / best_c);
+        grid = dim3((unsigned)((g.n[0] + 127) / 128), (unsigned)((g.n[1] + TY - 1) / TY), (unsigned)(n_a + (t.b_lo ? 1 : 0) + (t.b_hi ? 1 : 0)));
+    }
+    static int launch(const Tb2Args& t, cudaStream_t s)
+    {
+        const SweepArgs& a = t.a;
+        dim3 grid;
+        int chunk, n_a;
+        plan(t, grid, chunk, n_a);
+        CUtensorMap tm_u0, tm_rhs;
+        if (tma3d_encode_map(&tm_u0, a.g, a.in, Cfg::BX, Cfg::U0_ROWS)) return -1;
+        if (tma3d_encode_map(&tm_rhs, a.g, a.rhs, Cfg::BX, Cfg::R_ROWS)) return -1;
+        Tb2Params p;
+        p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
+        p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk; p.n_a = n_a;
+        p.b_lo = t.b_lo; p.b_hi = t.b_hi;
+        p.peer_u1_lo = t.peer_u1_lo; p.peer_u1_hi = t.peer_u1_hi;
+        p.u1_in_lo = t.u1_in_lo; p.u1_in_hi = t.u1_in_hi;
+        p.peer_lo_plane = a.peer_lo_plane; p.peer_hi_plane = a.peer_hi_plane;
+        p.ps = a.ps;
+        p.half_wait_lo = t.half_wait_lo; p.half_wait_hi = t.half_wait_hi;
+        p.half_sig_lo = t.half_sig_lo; p.half_sig_hi = t.half_sig_hi;
+        p.done_b = t.done_b; p.target_b_lo = t.target_b_lo; p.target_b_hi = t.target_b_hi;
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            attr_set = true;
+        }
+        jacobi3d_tb2_kernel<TY><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_u0, tm_rhs, p);
+        return 1;
+    }
+};
+
+}  // namespace
+
+// variants: 20 = 128x12 tile; 21 = 128x8  (16 / 12 warps: registers are allocated per 4 warps, so
+// 128x14 or 128x16 tiles would leave only 96 registers per thread and spill)
+int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
+{
+    if (t.a.k_end <= t.a.k_begin && !t.b_lo && !t.b_hi) return 0;
+    switch (t.a.variant) {
+    case 21: return Tb2Launcher<8>::launch(t, s);
+    default: return Tb2Launcher<12>::launch(t, s);
+    }
+}
+
+int double_sweep_boundary_ctas(const Tb2Args& t)
+{
+    dim3 grid;
+    int chunk, n_a;
+    switch (t.a.variant) {
+    case 21: Tb2Launcher<8>::plan(t, grid, chunk, n_a); break;
+    default: Tb2Launcher<12>::plan(t, grid, chunk, n_a); break;
+    }
+    return (int)(grid.x * grid.y);
+}

@@ -170,7 +170,7 @@ SWEEP_CASES_3D = [
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_3D)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 13])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 13, 20, 21])
 def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
@@ -185,6 +185,47 @@ def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
         np.testing.assert_array_equal(psi.data, want)
         assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
         assert psi.guards_intact() and rhs.guards_intact()       # no store past the end of a buffer
+    finally:
+        ctx.set_option("sweep_variant", "auto")
+        ctx.set_option("resident", 1)
+
+
+ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
+
+
+@pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
+    ([64, 64, 64], [64.0, 128.0, 192.0], MIXED_3D, 6, False),     # three double sweeps
+    ([65, 33, 17], [1.0, 1.0, 1.0], MIXED_3D, 7, False),          # three double sweeps + one single
+    ([65, 33, 17], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 8, True),     # three double + two single (the last carries the norm)
+    ([300, 70, 80], [3.0, 2.0, 1.0], MIXED_3D, 5, True),          # x/y/z tiling with ragged edges
+    ([129, 13, 5], [1.0, 2.0, 3.0], ALL_NEUMANN_3D, 4, False),    # one cell / one row past a tile edge
+    ([128, 12, 4], [1.0, 2.0, 3.0], MIXED_3D, 2, False),          # exactly one tile
+    ([127, 25, 1], [1.0, 2.0, 3.0], MIXED_3D, 4, False),          # a single plane: both z ghosts in registers
+    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 6, False),
+    ([260, 30, 2], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 9, True),
+])
+@pytest.mark.parametrize("variant", [20, 21])
+def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, variant):
+    """kernels_sweep_tb2.cu: two sweeps (+ the ghost fill after each) per pass over HBM must equal two
+    single sweeps bit for bit, for every tiling edge case and both parities of the sweep count."""
+    from rnmf_b200 import poisson
+    ctx.set_option("sweep_variant", variant)
+    ctx.set_option("resident", 0)
+    try:
+        g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=29)
+        ora.fill_bc(g, psi0, obc)
+        psi.fill_bc()
+        before = ctx.kernel_launches
+        l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=norm)
+        ctx.sync()
+        pairs = (sweeps - (1 if norm else 0)) // 2
+        assert ctx.kernel_launches - before <= 1 + pairs + (sweeps - 2 * pairs) + 1      # shell copy, doubles, singles, reduce
+        want = psi0.copy()
+        l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
+        np.testing.assert_array_equal(psi.data, want)
+        if norm:
+            assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+        assert psi.guards_intact() and rhs.guards_intact()
     finally:
         ctx.set_option("sweep_variant", "auto")
         ctx.set_option("resident", 1)
