@@ -138,6 +138,7 @@ struct rnmf_ctx {
     void* peer_flag_base_hi = nullptr;
     unsigned long long epoch = 0;                 // sweeps completed in peer mode (same on all ranks)
     unsigned long long done_target[2] = { 0, 0 }; // cumulative boundary-CTA counts (in-kernel handshake), lo / hi
+    unsigned long long done_target_b[2] = { 0, 0 }; // same for the B chunks of the double-sweep kernel
     int peer_inkernel = 1;                        // option "peer_inkernel": handshake inside the sweep kernel
     int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
     double* d_staging = nullptr;                  // dense staging for large uploads (1-D PCIe copy + device repack)
@@ -199,9 +200,14 @@ int bind(rnmf_ctx* c)
     return RNMF_OK;
 }
 
+// 3D one-component ng=1 frames carry two scratch planes behind the guard band: the u1 boundary planes
+// the slab neighbours store during a double sweep (kernels_sweep_tb2.cu); [0] from lo, [1] from hi
+long long scratch_planes(const FrameGeom& g) { return g.dim == 3 && g.ng == 1 && g.ncomp == 1 ? 2 : 0; }
+long long scratch_off(long long total) { return total + kTailPad + kGuard; }
+
 int alloc_buffer(const FrameGeom& g, double** out, cudaStream_t s)
 {
-    const size_t bytes = (size_t)(g.total + kTailPad + kGuard) * sizeof(double);
+    const size_t bytes = (size_t)(g.total + kTailPad + kGuard + scratch_planes(g) * g.plane) * sizeof(double);
     RNMF_CUDA_TRY(cudaMalloc(out, bytes));
     RNMF_CUDA_TRY(cudaMemsetAsync(*out, 0, bytes, s));   // new_from zero-initialises (dataframe.rs:155)
     return write_guard(*out, g, s);
@@ -276,8 +282,10 @@ static int ctx_common_init(rnmf_ctx* c)
     RNMF_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
     RNMF_CUDA_TRY(cudaMalloc(&c->d_scalar, 8 * sizeof(double)));
     RNMF_CUDA_TRY(cudaMallocHost(&c->h_scalar, 8 * sizeof(double)));
-    RNMF_CUDA_TRY(cudaMalloc(&c->d_flags, 64));
-    RNMF_CUDA_TRY(cudaMemset(c->d_flags, 0, 64));
+    // words: [0],[1] full-step flags (written by the lo / hi neighbour), [2] handshake status, [3],[4] boundary-CTA
+    // counters, [7] attach tag, [8],[9] half-step flags of the double-sweep kernel, [10],[11] its B-chunk counters
+    RNMF_CUDA_TRY(cudaMalloc(&c->d_flags, 128));
+    RNMF_CUDA_TRY(cudaMemset(c->d_flags, 0, 128));
     const char* v = getenv("RNMF_SWEEP_VARIANT");
     if (v) c->sweep_variant = atoi(v);
     const char* o = getenv("RNMF_HALO_OVERLAP");
@@ -942,15 +950,56 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
     const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 20 || c->sweep_variant == 21);
     const bool tb2_single = tb2_variant && !dist && fused && all_faces;
+    // slabs: the fused peer path with the in-kernel handshake; z faces are physical or a neighbour
+    const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
+    bool xy_faces = true;
+    for (int fi = 0; fi < 4; ++fi) xy_faces = xy_faces && a.faces.f[fi].mode != 0;
+    const bool tb2_peer = tb2_variant && peer && c->peer_inkernel && D == 2 && m >= 4 && xy_faces && scratch_planes(g) == 2 &&
+                          (has_lo || a.faces.f[4].mode != 0) && (has_hi || a.faces.f[5].mode != 0);
+    int64_t n_hi_slab = 0;
+    if (tb2_peer && has_hi) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank + 1, nullptr, &n_hi_slab);
     const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
 
     for (int64_t it = it0; it < n_sweeps; ++it) {
-        if (tb2_single && it + 2 <= n_pairable) {
+        if ((tb2_single || tb2_peer) && it + 2 <= n_pairable) {
             Tb2Args t;
             memset(&t, 0, sizeof(t));
             t.a = a;
             t.a.in = psi->d; t.a.out = psi->d2; t.a.partials = nullptr;
             t.a.k_begin = 0; t.a.k_end = m;
+            if (tb2_peer) {
+                const int out_phys = psi->parity ^ 1;
+                double* my_phys0 = psi->parity == 0 ? psi->d : psi->d2;
+                t.a.k_begin = has_lo ? 1 : 0;
+                t.a.k_end = has_hi ? m - 1 : m;
+                t.b_lo = has_lo; t.b_hi = has_hi;
+                // u2 boundary planes go to the neighbours' ghost planes of their `out` buffer (as in the single sweep)
+                t.a.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + g.plane * (n_lo_slab + g.ng) : nullptr;
+                t.a.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + g.plane * (g.ng - 1) : nullptr;
+                // u1 boundary planes go to the scratch planes behind the neighbours' physical buffer 0
+                t.peer_u1_lo = has_lo ? psi->peer_lo[0] + scratch_off(g.plane * (n_lo_slab + 2)) + g.plane : nullptr;
+                t.peer_u1_hi = has_hi ? psi->peer_hi[0] + scratch_off(g.plane * (n_hi_slab + 2)) : nullptr;
+                t.u1_in_lo = has_lo ? my_phys0 + scratch_off(g.total) : nullptr;
+                t.u1_in_hi = has_hi ? my_phys0 + scratch_off(g.total) + g.plane : nullptr;
+                const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(t);
+                t.a.ps.enabled = 1;
+                t.a.ps.wait_lo = my_flag_lo; t.a.ps.wait_hi = my_flag_hi;
+                t.a.ps.sig_lo = has_lo ? c->peer_flag_lo : nullptr;
+                t.a.ps.sig_hi = has_hi ? c->peer_flag_hi : nullptr;
+                t.a.ps.done = c->d_flags + 3;
+                if (has_lo) { c->done_target[0] += tiles; c->done_target_b[0] += tiles; }
+                if (has_hi) { c->done_target[1] += tiles; c->done_target_b[1] += tiles; }
+                t.a.ps.target_lo = c->done_target[0]; t.a.ps.target_hi = c->done_target[1];
+                t.a.ps.epoch = c->epoch;
+                t.a.ps.status = c->d_flags + 2;
+                t.half_wait_lo = has_lo ? c->d_flags + 8 : nullptr;
+                t.half_wait_hi = has_hi ? c->d_flags + 9 : nullptr;
+                t.half_sig_lo = has_lo ? (unsigned long long*)c->peer_flag_base_lo + 9 : nullptr;   // its hi-side half flag
+                t.half_sig_hi = has_hi ? (unsigned long long*)c->peer_flag_base_hi + 8 : nullptr;   // its lo-side half flag
+                t.done_b = c->d_flags + 10;
+                t.target_b_lo = c->done_target_b[0]; t.target_b_hi = c->done_target_b[1];
+                c->epoch += 2;
+            }
             RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
             double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
             psi->parity ^= 1;

@@ -31,6 +31,12 @@ CASES = [
     ([20, 18, 29], [2.0, 2.0, 3.0], MIXED_3D, 3, 2),       # two ghost layers: stand-alone fill + 2-slice halos
     ([33, 41], [1.0, 2.0], MIXED_2D, 4, 2),
 ]
+# extra cases for the double-sweep kernel across slabs (two sweeps per launch, half-step exchange of u1 planes)
+TB2_CASES = [
+    ([40, 36, 50], [40.0, 72.0, 150.0], MIXED_3D, 9, 1),   # 1 double | 3 doubles + the norm-carrying single
+    ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 8, 1),      # uneven split; 1 double | 2 doubles + 2 singles
+    ([257, 30, 16], [3.0, 2.0, 1.0], MIXED_3D, 6, 1),      # 4-plane slabs at world 4 (the minimum), ragged x tiles
+]
 
 
 def reference(n, hi, spec, sweeps, ng=1):
@@ -58,16 +64,18 @@ def run_nccl():
     ctx = R.Context.from_torch_distributed()
     mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
     ok = True
-    for mode in ("peer", "peer_flag_kernels", "nccl_overlap", "nccl_serial"):
+    for mode in ("peer", "peer_tb2", "peer_flag_kernels", "nccl_overlap", "nccl_serial"):
+        ctx.set_option("sweep_variant", 20 if mode == "peer_tb2" else "auto")
         ctx.set_option("halo_overlap", 0 if mode == "nccl_serial" else 1)
         ctx.set_option("peer_halo", 1 if mode.startswith("peer") else 0)
-        ctx.set_option("peer_inkernel", 1 if mode == "peer" else 0)       # handshake inside the sweep kernel vs 1-thread flag kernels
+        ctx.set_option("peer_inkernel", 1 if mode in ("peer", "peer_tb2") else 0)   # handshake inside the sweep kernel vs 1-thread flag kernels
         overlap = mode
-        for n, hi, spec, sweeps, ng in CASES:
+        for n, hi, spec, sweeps, ng in CASES + (TB2_CASES if mode == "peer_tb2" else []):
             dim = len(n)
             want, l1_ref = reference(n, hi, spec, sweeps, ng)
             bc = R.BCs([R.ComponentBCs([mk[k](v) for k, v in spec[0]], [mk[k](v) for k, v in spec[1]])])
             mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
+            start, count = R.slab_partition(n[-1], world, rank)
             psi = R.CartesianDataFrame.new_from(mesh, bc, 1, ng, ctx, slab=True)
             rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, ng, ctx, slab=True)
             psi.fill_synthetic(101)
@@ -76,11 +84,16 @@ def run_nccl():
             if mode.startswith("peer") and ng == 1:
                 psi.enable_peer_halo()
                 # two calls: the epoch handshake and buffer parity must carry over between calls
+                before = ctx.kernel_launches
                 poisson.jacobi_sweeps(psi, rhs, 2)
+                if mode == "peer_tb2" and dim == 3 and count >= 4:
+                    # shell copy + ONE double-sweep launch + the closing wait kernel
+                    if ctx.kernel_launches - before != 3:
+                        ok = False
+                        print(f"[rank {rank}] FAIL n={n}: double-sweep kernel not used ({ctx.kernel_launches - before} launches)", flush=True)
                 l1 = poisson.jacobi_sweeps(psi, rhs, sweeps - 2, want_norm=True)
             else:
                 l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
-            start, count = R.slab_partition(n[-1], world, rank)
             got = psi.get_valid_cells().reshape((count,) + tuple(reversed(n[:-1])))
             same = np.array_equal(got, want[start:start + count])
             norm_ok = abs(l1 - l1_ref) <= 1e-12 * abs(l1_ref)
