@@ -290,16 +290,17 @@ def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, redu
     coef = poisson.poisson_coefs(dim, mesh.dx)
     for _ in range(warmup):
         poisson.jacobi_sweeps(psi, rhs, sub_iters, want_norm=True, coef=coef)
-    launches0 = ctx.kernel_launches
+    launches0, doubles0 = ctx.kernel_launches, ctx.double_sweep_launches
     ms, l1 = timed_steps(ctx, psi, rhs, coef, sub_iters, steps, barrier)
     launches = ctx.kernel_launches - launches0
+    doubles = ctx.double_sweep_launches - doubles0
     ms = reduce_max(ms)
     cells = 1
     for v in n:
         cells *= v
     lups = cells * sub_iters * steps
     checksum = psi.ctx.allreduce_sum(psi.abs_sum())
-    res = dict(n_global=n, ms=ms, ms_per_step=ms / steps, glups=lups / (ms * 1e-3) / 1e9, launches=launches,
+    res = dict(n_global=n, ms=ms, ms_per_step=ms / steps, glups=lups / (ms * 1e-3) / 1e9, launches=launches, doubles=doubles,
                l1_last=l1, abs_sum=checksum, local_cells=int(psi.n_local[0] * psi.n_local[1] * (psi.n_local[2] if dim == 3 else 1)))
     psi.close()
     rhs.close()
@@ -491,12 +492,28 @@ def main():
     launches_total = int(reduce_sum(float(main_res["launches"])))
 
     peak, peak_src = measured_peak()
-    sweep_ms = main_res["ms"] / (args.steps * args.sub_iters)            # average sweep-kernel launch duration (upper bound)
-    achieved = BYTES_PER_LUP * main_res["local_cells"] / (sweep_ms * 1e-3) / 1e9     # GB/s per GPU (the slowest rank's clock)
+    sweep_ms = main_res["ms"] / (args.steps * args.sub_iters)            # average time per sweep over the timed region
+    # dominant kernel: 3D default = the double-sweep kernel (two sweeps + ghost fills per launch, one pass over HBM);
+    # its launch duration is taken as two sweeps' share of the timed region (an upper bound: the region also holds
+    # the norm-carrying single sweep, the shell copy and the reduction)
+    double = main_res["doubles"] * 2 > args.steps * args.sub_iters // 2
+    sweeps_per_launch = 2 if double else 1
+    launch_ms = sweep_ms * sweeps_per_launch
+    alg_bytes = BYTES_PER_LUP * main_res["local_cells"] * sweeps_per_launch   # 24 B per update x updates per launch
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9                           # GB/s per GPU (the slowest rank's clock)
+    traffic = ncu_traffic(args.workload + ("_tb2" if double else ""))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload), "kernel": "jacobi sweep (fused ghost fill)",
-                "algorithmic_bytes_per_launch": BYTES_PER_LUP * main_res["local_cells"],
-                "avg_launch_ms": sweep_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
+                "traffic": traffic,
+                "kernel": "jacobi3d_tb2 double sweep (2 sweeps + fused ghost fills per launch)" if double else "jacobi sweep (fused ghost fill)",
+                "sweeps_per_launch": sweeps_per_launch, "double_sweep_launches": main_res["doubles"],
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": launch_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
+    if double:
+        roofline["note"] = ("achieved counts the ALGORITHMIC 24 B per update; the kernel performs two updates per byte pass "
+                            "(temporal blocking), so frac can exceed 1. dram_frac = measured DRAM traffic per launch / launch time / peak.")
+        if traffic:
+            roofline["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
+            roofline["dram_frac"] = roofline["dram_gbs"] / peak
     if rank == 0:
         try:
             burst, sustained = copy_bandwidth_this_box()

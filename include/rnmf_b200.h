@@ -109,6 +109,9 @@ int32_t rnmf_ctx_rank(rnmf_ctx* ctx, int32_t* rank, int32_t* nranks);
 /* number of this library's kernels launched on the context since creation (graph replays count
  * their kernel nodes) -- bench.py's gpu_launches */
 int64_t rnmf_kernel_launches(rnmf_ctx* ctx);
+/* how many of those were the 3D double-sweep kernel (two Jacobi sweeps + ghost fills per pass over HBM;
+ * rnmf_jacobi_sweeps pairs up every two sweeps that do not carry the norm) -- bench.py's roofline accounting */
+int64_t rnmf_double_sweep_launches(rnmf_ctx* ctx);
 /* CUDA-event timer on the context's stream: begin records, end records+synchronises. */
 int32_t rnmf_timer_begin(rnmf_ctx* ctx);
 int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);

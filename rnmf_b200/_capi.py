@@ -55,6 +55,7 @@ SIGNATURES = {
     "rnmf_ctx_stream": (C.c_int32, [_vp, _P(_vp)]),
     "rnmf_ctx_rank": (C.c_int32, [_vp, _P(C.c_int32), _P(C.c_int32)]),
     "rnmf_kernel_launches": (C.c_int64, [_vp]),
+    "rnmf_double_sweep_launches": (C.c_int64, [_vp]),
     "rnmf_timer_begin": (C.c_int32, [_vp]),
     "rnmf_timer_end": (C.c_int32, [_vp, _dp]),
     "rnmf_set_option": (C.c_int32, [_vp, C.c_char_p, C.c_char_p]),

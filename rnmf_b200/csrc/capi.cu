@@ -127,6 +127,7 @@ struct rnmf_ctx {
     double* d_partials = nullptr;
     long long partial_cap = 0;
     int sweep_variant = 0;
+    long long double_sweeps = 0;                  // launches of the two-sweeps-per-pass kernel (rnmf_double_sweep_launches)
     int sweep_chunk = 0;
     int overlap_halo = 1;
     ncclComm_t comm = nullptr;
@@ -388,6 +389,7 @@ extern "C" int32_t rnmf_ctx_rank(rnmf_ctx* c, int32_t* rank, int32_t* nranks)
 }
 
 extern "C" int64_t rnmf_kernel_launches(rnmf_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t rnmf_double_sweep_launches(rnmf_ctx* c) { return c ? c->double_sweeps : 0; }
 
 extern "C" int32_t rnmf_timer_begin(rnmf_ctx* c)
 {
@@ -948,7 +950,8 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     // the norm; a face without a Dirichlet/Neumann rule must be a slab neighbour
     bool all_faces = true;
     for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
-    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 20 || c->sweep_variant == 21);
+    // default (variant 0 = auto) for 3D; variant 6 = the single-sweep TMA kernel only
+    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21);
     const bool tb2_single = tb2_variant && !dist && fused && all_faces;
     // slabs: the fused peer path with the in-kernel handshake; z faces are physical or a neighbour
     const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
@@ -1001,6 +1004,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
                 c->epoch += 2;
             }
             RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
+            c->double_sweeps += 1;
             double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
             psi->parity ^= 1;
             ++it;

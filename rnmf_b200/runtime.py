@@ -54,6 +54,11 @@ class Context:
         return int(_capi.lib().rnmf_kernel_launches(self._h))
 
     @property
+    def double_sweep_launches(self) -> int:
+        """launches of the 3D two-sweeps-per-pass kernel (kernels_sweep_tb2.cu)"""
+        return int(_capi.lib().rnmf_double_sweep_launches(self._h))
+
+    @property
     def stream(self) -> int:
         s = C.c_void_p()
         _capi.check(_capi.lib().rnmf_ctx_stream(self._h, C.byref(s)))

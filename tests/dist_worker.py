@@ -65,13 +65,14 @@ def run_nccl():
     mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
     ok = True
     for mode in ("peer", "peer_tb2", "peer_flag_kernels", "nccl_overlap", "nccl_serial"):
-        ctx.set_option("sweep_variant", 20 if mode == "peer_tb2" else "auto")
         ctx.set_option("halo_overlap", 0 if mode == "nccl_serial" else 1)
         ctx.set_option("peer_halo", 1 if mode.startswith("peer") else 0)
         ctx.set_option("peer_inkernel", 1 if mode in ("peer", "peer_tb2") else 0)   # handshake inside the sweep kernel vs 1-thread flag kernels
         overlap = mode
         for n, hi, spec, sweeps, ng in CASES + (TB2_CASES if mode == "peer_tb2" else []):
             dim = len(n)
+            # 3D default = the double-sweep kernel ("peer_tb2"); variant 6 = single-sweep TMA kernel only
+            ctx.set_option("sweep_variant", "auto" if (mode == "peer_tb2" or dim == 2) else 6)
             want, l1_ref = reference(n, hi, spec, sweeps, ng)
             bc = R.BCs([R.ComponentBCs([mk[k](v) for k, v in spec[0]], [mk[k](v) for k, v in spec[1]])])
             mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
@@ -105,6 +106,7 @@ def run_nccl():
                       flush=True)
             psi.close()
             rhs.close()
+    ctx.set_option("sweep_variant", "auto")
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     ctx.close()
