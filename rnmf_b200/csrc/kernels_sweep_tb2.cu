@@ -65,10 +65,11 @@ struct Tb2Params {
     unsigned long long target_b_lo, target_b_hi;
 };
 
-template <int TY>
+template <int TY, int NS_>
 struct Tb2Cfg {
     static constexpr int TX = 128;
-    static constexpr int NS = 4;                          // u0/rhs stages == u1 slots (loop unrolled by 4)
+    static constexpr int NS = NS_;                        // u0/rhs stages
+    static constexpr int NU1 = 2;                         // u1 slots
     static constexpr int BX = TX + 4;
     static constexpr int U0_ROWS = TY + 4;
     static constexpr int R_ROWS = TY + 2;
@@ -79,19 +80,189 @@ struct Tb2Cfg {
     static constexpr int U1_SLOT = RHS_STAGE;
     static constexpr int RHS_OFF = NS * U0_STAGE;
     static constexpr int U1_OFF = RHS_OFF + NS * RHS_STAGE;
-    static constexpr int BAR_OFF = U1_OFF + NS * U1_SLOT;
-    static constexpr int SMEM = BAR_OFF + 3 * NS * 8 + 128;
+    static constexpr int BAR_OFF = U1_OFF + NU1 * U1_SLOT;
+    static constexpr int SMEM = BAR_OFF + (2 * NS + NU1) * 8 + 128;
     static constexpr int NCONS = TY + 3;                  // TY row warps + 2 halo-row warps + 1 halo-column warp
     static constexpr int THREADS = 32 * (TY + 4);         // + producer warp
+    static_assert(NS >= 3 && SMEM <= 227 * 1024, "shared-memory budget");
 };
 
-template <int TY>
+// per-thread constants of a row warp
+struct RowK {
+    uint32_t pa, ra, ua;                 // byte address of the lane's first cell in u0 stage 0 / rhs stage 0 / u1 slot 0
+    uint32_t full0, empty0, u1full0;
+    double c0, c1, c2, c3;
+    bool full, va0, va1, vb0, vb1;       // validity of the lane's four cells
+    bool do_xlo, any_x, any_y, do_ylo, do_yhi;
+    int xhi_sel;                         // which of the four cells is i == n0-1 (-1: none)
+    uint32_t xhi_off;                    // byte offset of the x-hi ghost from the lane's first cell
+    Face1 fx0, fx1, fy0, fy1, fz0, fz1;
+    long long pitch, plane_sz, xy_off;
+    int lane;
+    int it_zlo;                          // iteration whose level 2 produces the slab's first plane (-1: not in this chunk)
+    int it_u1lo, it_u1hi;                // level-1 iterations whose plane goes to a slab neighbour (-1: none)
+};
+
+// rotating per-thread state of a row warp
+struct RowSt {
+    double2 below_a, below_b, cur_a, cur_b;      // u0 of planes a+it-1, a+it        (own cells)
+    double2 u1lo_a, u1lo_b, u1c_a, u1c_b;        // u1 of planes q-1, q, q = a+it-1  (own cells)
+    double2 rp_a, rp_b;                          // rhs of plane q
+    double* oa;                                  // where u2 of plane q goes
+    uint32_t sc, sn, phn;                        // ring: stage of plane a+it, of plane a+it+1, parity its full barrier completes with
+};
+
+// first two terms of poisson.rs:83-88 (the z term is added last: same association as upd3)
+__device__ __forceinline__ double part2(double c0, double c1, double c2, double r, double e, double w, double n, double s)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(c0, r), __dmul_rn(c1, __dadd_rn(e, w))), __dmul_rn(c2, __dadd_rn(n, s)));
+}
+__device__ __forceinline__ double fin2(double part, double c3, double u, double d) { return __dadd_rn(part, __dmul_rn(c3, __dadd_rn(u, d))); }
+
+__device__ __forceinline__ void load4(const double* q, double2& a, double2& b, const RowK& k)
+{
+    if (k.full) { a = *reinterpret_cast<const double2*>(q); b = *reinterpret_cast<const double2*>(q + 64); }
+    else {
+        if (k.va0) a.x = q[0];
+        if (k.va1) a.y = q[1];
+        if (k.vb0) b.x = q[64];
+        if (k.vb1) b.y = q[65];
+    }
+}
+
+// One plane iteration of a row warp: level 1 of plane a+it (DO_L1) and level 2 of plane q = a+it-1 (DO_L2).
+// All shared-memory loads of both levels are issued behind ONE wait phase; level 2's x/y part is formed
+// before level 1's result exists (part2), its z term is added once u1 of plane a+it is known (fin2).
+template <int TY, int NS, bool DO_L1, bool DO_L2>
+__device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowSt& st, const int it)
+{
+    using Cfg = Tb2Cfg<TY, NS>;
+    constexpr int BX = Cfg::BX;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 above_a = zero2, above_b = zero2, u1n_a = zero2, u1n_b = zero2, rc_a = zero2, rc_b = zero2, P_a = zero2, P_b = zero2;
+    double2 n_a, n_b, s_a, s_b;
+    double w_a0, e_a1, w_b0, e_b1;
+
+    // ---- wait phase --------------------------------------------------------------------------
+    if (DO_L1) mbar_wait(k.full0 + 8 * st.sn, st.phn);                    // u0 plane a+it+1 (plane a+it was waited for one iteration ago)
+    // u1 plane a+it-1 complete: level 2 reads it; and every warp has finished reading plane a+it-2,
+    // whose slot level 1 overwrites below (reads precede the arrival in program order)
+    if (DO_L2 || it >= 2) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+
+    // ---- loads ---------------------------------------------------------------------------------
+    if (DO_L2) {
+        const uint32_t up = k.ua + (uint32_t)((it - 1) & 1) * Cfg::U1_SLOT;
+        const double2 un_a = lds2(up + BX * 8), un_b = lds2(up + BX * 8 + 512);
+        const double2 us_a = lds2(up - BX * 8), us_b = lds2(up - BX * 8 + 512);
+        const double uw_a0 = lds1(up - 8), ue_a1 = lds1(up + 16);
+        const double uw_b0 = lds1(up + 512 - 8), ue_b1 = lds1(up + 512 + 16);
+        P_a.x = part2(k.c0, k.c1, k.c2, st.rp_a.x, st.u1c_a.y, uw_a0, un_a.x, us_a.x);
+        P_a.y = part2(k.c0, k.c1, k.c2, st.rp_a.y, ue_a1, st.u1c_a.x, un_a.y, us_a.y);
+        P_b.x = part2(k.c0, k.c1, k.c2, st.rp_b.x, st.u1c_b.y, uw_b0, un_b.x, us_b.x);
+        P_b.y = part2(k.c0, k.c1, k.c2, st.rp_b.y, ue_b1, st.u1c_b.x, un_b.y, us_b.y);
+    }
+    if (DO_L1) {
+        const uint32_t pn = k.pa + st.sn * Cfg::U0_STAGE, pc = k.pa + st.sc * Cfg::U0_STAGE, pr = k.ra + st.sc * Cfg::RHS_STAGE;
+        above_a = lds2(pn); above_b = lds2(pn + 512);
+        n_a = lds2(pc + BX * 8); n_b = lds2(pc + BX * 8 + 512);
+        s_a = lds2(pc - BX * 8); s_b = lds2(pc - BX * 8 + 512);
+        rc_a = lds2(pr); rc_b = lds2(pr + 512);
+        w_a0 = lds1(pc - 8); e_a1 = lds1(pc + 16);
+        w_b0 = lds1(pc + 512 - 8); e_b1 = lds1(pc + 512 + 16);
+
+        // ---------------- level 1: u1 of plane a+it ----------------
+        u1n_a.x = upd3(k.c0, k.c1, k.c2, k.c3, rc_a.x, st.cur_a.y, w_a0, n_a.x, s_a.x, above_a.x, st.below_a.x);
+        u1n_a.y = upd3(k.c0, k.c1, k.c2, k.c3, rc_a.y, e_a1, st.cur_a.x, n_a.y, s_a.y, above_a.y, st.below_a.y);
+        u1n_b.x = upd3(k.c0, k.c1, k.c2, k.c3, rc_b.x, st.cur_b.y, w_b0, n_b.x, s_b.x, above_b.x, st.below_b.x);
+        u1n_b.y = upd3(k.c0, k.c1, k.c2, k.c3, rc_b.y, e_b1, st.cur_b.x, n_b.y, s_b.y, above_b.y, st.below_b.y);
+        // odd n0: the last valid cell is the first of a pair, whose E neighbour at level 2 is the pair's
+        // second register: it must hold the x-hi ghost of u1, not a stencil value
+        if (k.xhi_sel == 0) u1n_a.y = ghost1(k.fx1, u1n_a.x);
+        if (k.xhi_sel == 2) u1n_b.y = ghost1(k.fx1, u1n_b.x);
+
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);              // this warp is done with the stage of plane a+it
+        const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
+        sstore4(us, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        // what fill_bc gives u1 on the physical x / y faces (read by level 2 of the edge cells)
+        if (k.any_x) {
+            if (k.do_xlo) sts1(us - 8, ghost1(k.fx0, u1n_a.x));
+            if (k.xhi_sel >= 0) {
+                const double m = k.xhi_sel == 0 ? u1n_a.x : k.xhi_sel == 1 ? u1n_a.y : k.xhi_sel == 2 ? u1n_b.x : u1n_b.y;
+                sts1(us + k.xhi_off, ghost1(k.fx1, m));
+            }
+        }
+        if (k.any_y) {
+            if (k.do_ylo) sstore4(us - BX * 8, ghost1(k.fy0, u1n_a), ghost1(k.fy0, u1n_b), k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.do_yhi) sstore4(us + BX * 8, ghost1(k.fy1, u1n_a), ghost1(k.fy1, u1n_b), k.full, k.va0, k.va1, k.vb0, k.vb1);
+        }
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+        // slab neighbours get u1 of my boundary plane (half step) over NVLink
+        if (it == k.it_u1lo) store4(p.peer_u1_lo + k.xy_off, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (it == k.it_u1hi) store4(p.peer_u1_hi + k.xy_off, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+    }
+    if (DO_L2) {
+        // ---------------- level 2: u2 of plane q = a+it-1 ----------------
+        // z neighbours of u1: registers, the face's ghost rule, or the neighbour slab's plane
+        double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
+        const bool zlo = it == k.it_zlo;
+        if (zlo) {
+            if (k.fz0.on) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
+            else if (p.u1_in_lo) load4(p.u1_in_lo + k.xy_off, dn_a, dn_b, k);
+        }
+        if (!DO_L1) {                                                     // the slab's last plane (no plane above)
+            if (k.fz1.on) { up_a = ghost1(k.fz1, st.u1c_a); up_b = ghost1(k.fz1, st.u1c_b); }
+            else if (p.u1_in_hi) load4(p.u1_in_hi + k.xy_off, up_a, up_b, k);
+        }
+        double2 na, nb;
+        na.x = fin2(P_a.x, k.c3, up_a.x, dn_a.x);
+        na.y = fin2(P_a.y, k.c3, up_a.y, dn_a.y);
+        nb.x = fin2(P_b.x, k.c3, up_b.x, dn_b.x);
+        nb.y = fin2(P_b.y, k.c3, up_b.y, dn_b.y);
+
+        double* oa = st.oa;
+        store4(oa, na, nb, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (k.any_x) {
+            if (k.do_xlo) oa[-1] = ghost1(k.fx0, na.x);
+            if (k.xhi_sel >= 0) {
+                const double m = k.xhi_sel == 0 ? na.x : k.xhi_sel == 1 ? na.y : k.xhi_sel == 2 ? nb.x : nb.y;
+                oa[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, m);
+            }
+        }
+        if (k.any_y) {
+            if (k.do_ylo) store4(oa - k.pitch, ghost1(k.fy0, na), ghost1(k.fy0, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.do_yhi) store4(oa + k.pitch, ghost1(k.fy1, na), ghost1(k.fy1, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
+        }
+        if (zlo) {
+            if (k.fz0.on) store4(oa - k.plane_sz, ghost1(k.fz0, na), ghost1(k.fz0, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_lo_plane) store4(p.peer_lo_plane + k.xy_off, na, nb, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        }
+        if (!DO_L1) {
+            if (k.fz1.on) store4(oa + k.plane_sz, ghost1(k.fz1, na), ghost1(k.fz1, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_hi_plane) store4(p.peer_hi_plane + k.xy_off, na, nb, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        }
+        st.oa = oa + k.plane_sz;
+    }
+    // ---- rotate --------------------------------------------------------------------------------
+    if (DO_L1) {
+        st.below_a = st.cur_a; st.below_b = st.cur_b;
+        st.cur_a = above_a; st.cur_b = above_b;
+        st.sc = st.sn;
+        if (++st.sn == NS) { st.sn = 0; st.phn ^= 1u; }
+    }
+    st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
+    st.u1c_a = u1n_a; st.u1c_b = u1n_b;
+    st.rp_a = rc_a; st.rp_b = rc_b;
+}
+
+template <int TY, int NS>
 __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __grid_constant__ CUtensorMap tm_u0,
                                                                          const __grid_constant__ CUtensorMap tm_rhs,
                                                                          const __grid_constant__ Tb2Params p)
 {
-    using Cfg = Tb2Cfg<TY>;
-    constexpr int TX = Cfg::TX, NS = Cfg::NS, BX = Cfg::BX;
+    using Cfg = Tb2Cfg<TY, NS>;
+    constexpr int TX = Cfg::TX, BX = Cfg::BX;
     static_assert(TY <= 16, "the halo-column warp maps 16 rows per side");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -118,9 +289,9 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
     const long long a = k0 > 0 ? k0 - 1 : 0;              // level-1 planes a..b
     const long long b = k1 < n2 ? k1 : n2 - 1;
     const int nL1 = (int)(b - a) + 1;
-    const int n_planes = nL1 + 2;                         // u0 planes a-1..b+1  (plane a-1+idx <-> stage idx % 4)
-    const int n_iters = nL1 + (b < k1 ? 1 : 0);           // iteration it: level 1 of plane a+it, level 2 of plane a+it-1
-    const int it_l2_first = (int)(k0 - a) + 1;
+    const int n_planes = nL1 + 2;                         // u0 planes a-1..b+1  (plane a-1+idx <-> stage idx % NS)
+    const bool top = b < k1;                              // the chunk ends with the slab's last plane: one level-2-only iteration
+    const int it_l2_first = (int)(k0 - a) + 1;            // iteration it: level 1 of plane a+it, level 2 of plane a+it-1
 
     // slab handshake roles of this CTA
     const bool a_sync_lo = !is_b && p.peer_u1_lo && k0 == p.m_begin;     // computes u1(0), reads ghost plane -1 of u0
@@ -133,8 +304,9 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
         for (int s = 0; s < NS; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, Cfg::NCONS);
-            mbar_init(u1full0 + 8 * s, Cfg::NCONS);
         }
+        mbar_init(u1full0, Cfg::NCONS);
+        mbar_init(u1full0 + 8, Cfg::NCONS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (a_sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
         if (a_sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
@@ -143,8 +315,6 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
     }
     __syncthreads();
 
-    const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
-
     if (warp == TY + 3) {
         // ------------------------------ producer warp ------------------------------
         if (lane == 0) {
@@ -152,25 +322,21 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
             const int cy_u0 = (int)(p.g.ng + j0 - 2);
             const int cy_rhs = cy_u0 + 1;
             int cz = (int)(p.g.kg + a - 1);
-            uint32_t wrap = 0;
-            for (int base = 0; base < n_planes; base += NS, ++wrap) {
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const int idx = base + s;
-                    if (idx < n_planes) {
-                        if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1);
-                        const bool with_rhs = idx >= 1 && idx <= nL1;
-                        mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::U0_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
-                        tma_load_3d(u0_0 + s * Cfg::U0_STAGE, &tm_u0, cx, cy_u0, cz, full0 + 8 * s);
-                        if (with_rhs) tma_load_3d(rhs_0 + s * Cfg::RHS_STAGE, &tm_rhs, cx, cy_rhs, cz, full0 + 8 * s);
-                        ++cz;
-                    }
-                }
+            uint32_t s = 0, wrap = 0;
+            for (int idx = 0; idx < n_planes; ++idx) {
+                if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
+                const bool with_rhs = idx >= 1 && idx <= nL1;
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::U0_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
+                tma_load_3d(u0_0 + s * Cfg::U0_STAGE, &tm_u0, cx, cy_u0, cz, full0 + 8 * s);
+                if (with_rhs) tma_load_3d(rhs_0 + s * Cfg::RHS_STAGE, &tm_rhs, cx, cy_rhs, cz, full0 + 8 * s);
+                ++cz;
+                if (++s == NS) { s = 0; ++wrap; }
             }
         }
     } else if (warp == TY + 2) {
         // ------------------------------ halo-column warp (level 1 only) ------------------------------
         // lanes 0..15: column i0-1, rows j0+lane; lanes 16..31: column i0+128, rows j0+lane-16
+        const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
         const int side = lane >> 4, r = lane & 15;
         const bool act = r < TY;
         const int rc = act ? r : 0;
@@ -187,31 +353,25 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
         if (lane == 0) mbar_arrive(empty0);
         mbar_wait(full0 + 8, 0);
         double cur = lds1(hp + Cfg::U0_STAGE);
-
-        uint32_t wrap = 0;
-        for (int base = 0; base < nL1; base += NS, ++wrap) {
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int it = base + s;
-                if (it < nL1) {
-                    const int sc = (s + 1) % NS, sn = (s + 2) % NS;
-                    mbar_wait(full0 + 8 * sn, (wrap + (uint32_t)((s + 2) / NS)) & 1u);
-                    const uint32_t pc = hp + sc * Cfg::U0_STAGE;
-                    const double above = lds1(hp + sn * Cfg::U0_STAGE);
-                    const double nn = lds1(pc + BX * 8), ss = lds1(pc - BX * 8);
-                    const double ee = lds1(pc + 8), ww = lds1(pc - 8);
-                    const double rr = lds1(hr + sc * Cfg::RHS_STAGE);
-                    const double v = upd3(c0, c1, c2, c3, rr, ee, ww, nn, ss, above, below);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8 * sc);
-                    if (it >= NS) mbar_wait(u1full0 + 8 * ((s + 2) % NS), (wrap - (s < 2 ? 1u : 0u)) & 1u);
-                    if (ok) sts1(hu + s * Cfg::U1_SLOT, v);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(u1full0 + 8 * s);
-                    below = cur;
-                    cur = above;
-                }
-            }
+        uint32_t sc = 1, sn = 2, phn = 0;
+        for (int it = 0; it < nL1; ++it) {
+            mbar_wait(full0 + 8 * sn, phn);
+            if (it >= 2) mbar_wait(u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+            const uint32_t pc = hp + sc * Cfg::U0_STAGE;
+            const double above = lds1(hp + sn * Cfg::U0_STAGE);
+            const double nn = lds1(pc + BX * 8), ss = lds1(pc - BX * 8);
+            const double ee = lds1(pc + 8), ww = lds1(pc - 8);
+            const double rr = lds1(hr + sc * Cfg::RHS_STAGE);
+            const double v = upd3(c0, c1, c2, c3, rr, ee, ww, nn, ss, above, below);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * sc);
+            if (ok) sts1(hu + (uint32_t)(it & 1) * Cfg::U1_SLOT, v);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(u1full0 + 8 * (it & 1));
+            below = cur;
+            cur = above;
+            sc = sn;
+            if (++sn == NS) { sn = 0; phn ^= 1u; }
         }
     } else {
         // ------------------------------ row warps ------------------------------
@@ -221,172 +381,62 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
         const long long j = j0 + rr;
         const bool row_ok = j >= 0 && j < n1;
         const long long ia = i0 + 2 * lane, ib = ia + 64;
-        const bool va0 = row_ok && ia < n0, va1 = row_ok && ia + 1 < n0;
-        const bool vb0 = row_ok && ib < n0, vb1 = row_ok && ib + 1 < n0;
-        const bool full = vb1;
+        RowK k;
+        k.va0 = row_ok && ia < n0; k.va1 = row_ok && ia + 1 < n0;
+        k.vb0 = row_ok && ib < n0; k.vb1 = row_ok && ib + 1 < n0;
+        k.full = k.vb1;
         // byte offsets: cell (i0+c, j0+r) sits at ((r+2)*BX + c+2)*8 in a u0 stage and at ((r+1)*BX + c+2)*8
         // in an rhs stage / u1 slot
-        const uint32_t pa = u0_0 + (uint32_t)(((rr + 2) * BX + 2 + 2 * lane) * 8);
-        const uint32_t ra = rhs_0 + (uint32_t)(((rr + 1) * BX + 2 + 2 * lane) * 8);
-        const uint32_t ua = u1_0 + (uint32_t)(((rr + 1) * BX + 2 + 2 * lane) * 8);
-        const long long pitch = p.g.pitch, plane_sz = p.g.plane;
-        // plane offset of the lane's first cell inside a grown xy plane (scratch / peer ghost planes)
-        const long long xy_off = p.g.xoff + (ia + p.g.ng) + pitch * (j + p.g.ng);
-        double* oa = p.out + p.g.at(ia, j, k0, 0);
-
-        // ghost rules of the six faces (a face with mode 0 is a slab neighbour: handled below)
-        const Face1 fx0 = make_face1(p.faces.f[0], true), fx1 = make_face1(p.faces.f[1], true);
-        const Face1 fy0 = make_face1(p.faces.f[2], true), fy1 = make_face1(p.faces.f[3], true);
-        const Face1 fz0 = make_face1(p.faces.f[4], true), fz1 = make_face1(p.faces.f[5], true);
-        const bool do_xlo = do_l2 && fx0.on && va0 && ia == 0;
+        k.pa = u0_0 + (uint32_t)(((rr + 2) * BX + 2 + 2 * lane) * 8);
+        k.ra = rhs_0 + (uint32_t)(((rr + 1) * BX + 2 + 2 * lane) * 8);
+        k.ua = u1_0 + (uint32_t)(((rr + 1) * BX + 2 + 2 * lane) * 8);
+        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0;
+        k.c0 = p.c.c0; k.c1 = p.c.c1; k.c2 = p.c.c2; k.c3 = p.c.c3;
+        k.pitch = p.g.pitch; k.plane_sz = p.g.plane;
+        // offset of the lane's first cell inside a grown xy plane (scratch / peer ghost planes)
+        k.xy_off = p.g.xoff + (ia + p.g.ng) + k.pitch * (j + p.g.ng);
+        k.lane = lane;
+        // ghost rules of the six faces (a face with mode 0 is a slab neighbour)
+        k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
+        k.fy0 = make_face1(p.faces.f[2], true); k.fy1 = make_face1(p.faces.f[3], true);
+        k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
+        k.do_xlo = do_l2 && k.fx0.on && k.va0 && ia == 0;
         const long long last = n0 - 1;
-        const int xhi_sel = !(do_l2 && fx1.on) ? -1 : (va0 && ia == last) ? 0 : (va1 && ia + 1 == last) ? 1 : (vb0 && ib == last) ? 2 : (vb1 && ib + 1 == last) ? 3 : -1;
-        const bool do_ylo = do_l2 && fy0.on && j == 0, do_yhi = do_l2 && fy1.on && j == n1 - 1;
-        const bool any_xy = do_xlo || xhi_sel >= 0 || do_ylo || do_yhi;
-        const uint32_t xhi_off = (uint32_t)((xhi_sel >= 2 ? 512 : 0) + ((xhi_sel & 1) + 1) * 8);
-        // the slab's first / last plane: iteration whose level 2 produces it (-1: not in this chunk)
-        const int it_zlo = k0 == 0 ? 1 : -1;
-        const int it_zhi = k1 == n2 ? n_iters - 1 : -1;
-        // u1 boundary planes for the slab neighbours: level-1 iterations that produce plane 0 / m-1
-        const int it_u1lo = (a_sync_lo && do_l2) ? 0 : -1;
-        const int it_u1hi = (a_sync_hi && do_l2) ? nL1 - 1 : -1;
+        k.xhi_sel = !(do_l2 && k.fx1.on) ? -1 : (k.va0 && ia == last) ? 0 : (k.va1 && ia + 1 == last) ? 1 : (k.vb0 && ib == last) ? 2 : (k.vb1 && ib + 1 == last) ? 3 : -1;
+        k.xhi_off = (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        k.do_ylo = do_l2 && k.fy0.on && j == 0; k.do_yhi = do_l2 && k.fy1.on && j == n1 - 1;
+        k.any_x = k.do_xlo || k.xhi_sel >= 0;
+        k.any_y = k.do_ylo || k.do_yhi;
+        k.it_zlo = k0 == 0 ? 1 : -1;
+        k.it_u1lo = (a_sync_lo && do_l2) ? 0 : -1;
+        k.it_u1hi = (a_sync_hi && do_l2) ? nL1 - 1 : -1;
 
+        RowSt st;
+        const double2 zero2 = make_double2(0.0, 0.0);
         mbar_wait(full0, 0);
-        double2 below_a = lds2(pa), below_b = lds2(pa + 512);
+        st.below_a = lds2(k.pa); st.below_b = lds2(k.pa + 512);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0);
         mbar_wait(full0 + 8, 0);
-        double2 cur_a = lds2(pa + Cfg::U0_STAGE), cur_b = lds2(pa + Cfg::U0_STAGE + 512);
+        st.cur_a = lds2(k.pa + Cfg::U0_STAGE); st.cur_b = lds2(k.pa + Cfg::U0_STAGE + 512);
+        st.u1lo_a = zero2; st.u1lo_b = zero2; st.u1c_a = zero2; st.u1c_b = zero2; st.rp_a = zero2; st.rp_b = zero2;
+        st.oa = p.out + p.g.at(ia, j, k0, 0);
+        st.sc = 1; st.sn = 2; st.phn = 0;
 
-        const double2 zero2 = make_double2(0.0, 0.0);
-        double2 u1lo_a = zero2, u1lo_b = zero2;       // u1 of plane q-1 (q = plane level 2 is producing)
-        double2 u1c_a = zero2, u1c_b = zero2;         // u1 of plane q
-        double2 rp_a = zero2, rp_b = zero2;           // rhs of plane q
-
-        uint32_t wrap = 0;
-        for (int base = 0; base < n_iters; base += NS, ++wrap) {
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int it = base + s;
-                if (it < n_iters) {
-                    double2 u1n_a = zero2, u1n_b = zero2, rc_a = zero2, rc_b = zero2;
-                    const bool l1_on = it < nL1;
-                    if (l1_on) {
-                        // ---------------- level 1: u1 of plane a+it ----------------
-                        const int sc = (s + 1) % NS, sn = (s + 2) % NS;
-                        mbar_wait(full0 + 8 * sn, (wrap + (uint32_t)((s + 2) / NS)) & 1u);
-                        const uint32_t pn = pa + sn * Cfg::U0_STAGE, pc = pa + sc * Cfg::U0_STAGE, pr = ra + sc * Cfg::RHS_STAGE;
-                        const double2 above_a = lds2(pn), above_b = lds2(pn + 512);
-                        const double2 n_a = lds2(pc + BX * 8), n_b = lds2(pc + BX * 8 + 512);
-                        const double2 s_a = lds2(pc - BX * 8), s_b = lds2(pc - BX * 8 + 512);
-                        rc_a = lds2(pr); rc_b = lds2(pr + 512);
-                        const double w_a0 = lds1(pc - 8), e_a1 = lds1(pc + 16);
-                        const double w_b0 = lds1(pc + 512 - 8), e_b1 = lds1(pc + 512 + 16);
-
-                        u1n_a.x = upd3(c0, c1, c2, c3, rc_a.x, cur_a.y, w_a0, n_a.x, s_a.x, above_a.x, below_a.x);
-                        u1n_a.y = upd3(c0, c1, c2, c3, rc_a.y, e_a1, cur_a.x, n_a.y, s_a.y, above_a.y, below_a.y);
-                        u1n_b.x = upd3(c0, c1, c2, c3, rc_b.x, cur_b.y, w_b0, n_b.x, s_b.x, above_b.x, below_b.x);
-                        u1n_b.y = upd3(c0, c1, c2, c3, rc_b.y, e_b1, cur_b.x, n_b.y, s_b.y, above_b.y, below_b.y);
-
-                        // odd n0: the last valid cell is the first of a pair, whose E neighbour at level 2 is the
-                        // pair's second register: it must hold the x-hi ghost of u1, not a stencil value
-                        if (xhi_sel == 0) u1n_a.y = ghost1(fx1, u1n_a.x);
-                        if (xhi_sel == 2) u1n_b.y = ghost1(fx1, u1n_b.x);
-
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(empty0 + 8 * sc);      // stage of plane a+it is free for this warp
-                        below_a = cur_a; below_b = cur_b;
-                        cur_a = above_a; cur_b = above_b;
-
-                        // slot s held plane a+it-4, last read by level 2 in iteration it-3: every warp has
-                        // finished that iteration once it has arrived for plane a+it-2
-                        if (it >= NS) mbar_wait(u1full0 + 8 * ((s + 2) % NS), (wrap - (s < 2 ? 1u : 0u)) & 1u);
-                        const uint32_t us = ua + s * Cfg::U1_SLOT;
-                        sstore4(us, u1n_a, u1n_b, full, va0, va1, vb0, vb1);
-                        if (any_xy) {
-                            // what fill_bc gives u1 on the physical x / y faces (read by level 2 of the edge cells)
-                            if (do_xlo) sts1(us - 8, ghost1(fx0, u1n_a.x));
-                            if (xhi_sel >= 0) {
-                                const double m = xhi_sel == 0 ? u1n_a.x : xhi_sel == 1 ? u1n_a.y : xhi_sel == 2 ? u1n_b.x : u1n_b.y;
-                                sts1(us + xhi_off, ghost1(fx1, m));
-                            }
-                            if (do_ylo) sstore4(us - BX * 8, ghost1(fy0, u1n_a), ghost1(fy0, u1n_b), full, va0, va1, vb0, vb1);
-                            if (do_yhi) sstore4(us + BX * 8, ghost1(fy1, u1n_a), ghost1(fy1, u1n_b), full, va0, va1, vb0, vb1);
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(u1full0 + 8 * s);
-                        // slab neighbours get u1 of my boundary plane (half step) over NVLink
-                        if (it == it_u1lo) store4(p.peer_u1_lo + xy_off, u1n_a, u1n_b, full, va0, va1, vb0, vb1);
-                        if (it == it_u1hi) store4(p.peer_u1_hi + xy_off, u1n_a, u1n_b, full, va0, va1, vb0, vb1);
-                    }
-                    if (do_l2 && it >= it_l2_first) {
-                        // ---------------- level 2: u2 of plane q = a+it-1 ----------------
-                        const int sp = (s + 3) % NS;                      // slot of u1 plane q
-                        mbar_wait(u1full0 + 8 * sp, (wrap - (s < 1 ? 1u : 0u)) & 1u);
-                        const uint32_t up = ua + sp * Cfg::U1_SLOT;
-                        const double2 n_a = lds2(up + BX * 8), n_b = lds2(up + BX * 8 + 512);
-                        const double2 s_a = lds2(up - BX * 8), s_b = lds2(up - BX * 8 + 512);
-                        const double w_a0 = lds1(up - 8), e_a1 = lds1(up + 16);
-                        const double w_b0 = lds1(up + 512 - 8), e_b1 = lds1(up + 512 + 16);
-                        // z neighbours of u1: registers, the face's ghost rule, or the neighbour slab's plane
-                        double2 dn_a = u1lo_a, dn_b = u1lo_b, upl_a = u1n_a, upl_b = u1n_b;
-                        if (it == it_zlo) {
-                            if (fz0.on) { dn_a = ghost1(fz0, u1c_a); dn_b = ghost1(fz0, u1c_b); }
-                            else if (p.u1_in_lo) {
-                                const double* q = p.u1_in_lo + xy_off;
-                                if (full) { dn_a = *reinterpret_cast<const double2*>(q); dn_b = *reinterpret_cast<const double2*>(q + 64); }
-                                else {
-                                    if (va0) dn_a.x = q[0];
-                                    if (va1) dn_a.y = q[1];
-                                    if (vb0) dn_b.x = q[64];
-                                    if (vb1) dn_b.y = q[65];
-                                }
-                            }
-                        }
-                        if (it == it_zhi) {
-                            if (fz1.on) { upl_a = ghost1(fz1, u1c_a); upl_b = ghost1(fz1, u1c_b); }
-                            else if (p.u1_in_hi) {
-                                const double* q = p.u1_in_hi + xy_off;
-                                if (full) { upl_a = *reinterpret_cast<const double2*>(q); upl_b = *reinterpret_cast<const double2*>(q + 64); }
-                                else {
-                                    if (va0) upl_a.x = q[0];
-                                    if (va1) upl_a.y = q[1];
-                                    if (vb0) upl_b.x = q[64];
-                                    if (vb1) upl_b.y = q[65];
-                                }
-                            }
-                        }
-                        double2 na, nb;
-                        na.x = upd3(c0, c1, c2, c3, rp_a.x, u1c_a.y, w_a0, n_a.x, s_a.x, upl_a.x, dn_a.x);
-                        na.y = upd3(c0, c1, c2, c3, rp_a.y, e_a1, u1c_a.x, n_a.y, s_a.y, upl_a.y, dn_a.y);
-                        nb.x = upd3(c0, c1, c2, c3, rp_b.x, u1c_b.y, w_b0, n_b.x, s_b.x, upl_b.x, dn_b.x);
-                        nb.y = upd3(c0, c1, c2, c3, rp_b.y, e_b1, u1c_b.x, n_b.y, s_b.y, upl_b.y, dn_b.y);
-
-                        store4(oa, na, nb, full, va0, va1, vb0, vb1);
-                        if (any_xy) {
-                            if (do_xlo) oa[-1] = ghost1(fx0, na.x);
-                            if (xhi_sel >= 0) {
-                                const double m = xhi_sel == 0 ? na.x : xhi_sel == 1 ? na.y : xhi_sel == 2 ? nb.x : nb.y;
-                                oa[(xhi_sel >= 2 ? 64 : 0) + (xhi_sel & 1) + 1] = ghost1(fx1, m);
-                            }
-                            if (do_ylo) store4(oa - pitch, ghost1(fy0, na), ghost1(fy0, nb), full, va0, va1, vb0, vb1);
-                            if (do_yhi) store4(oa + pitch, ghost1(fy1, na), ghost1(fy1, nb), full, va0, va1, vb0, vb1);
-                        }
-                        if (it == it_zlo) {
-                            if (fz0.on) store4(oa - plane_sz, ghost1(fz0, na), ghost1(fz0, nb), full, va0, va1, vb0, vb1);
-                            if (p.peer_lo_plane) store4(p.peer_lo_plane + xy_off, na, nb, full, va0, va1, vb0, vb1);
-                        }
-                        if (it == it_zhi) {
-                            if (fz1.on) store4(oa + plane_sz, ghost1(fz1, na), ghost1(fz1, nb), full, va0, va1, vb0, vb1);
-                            if (p.peer_hi_plane) store4(p.peer_hi_plane + xy_off, na, nb, full, va0, va1, vb0, vb1);
-                        }
-                        oa += plane_sz;
-                    }
-                    u1lo_a = u1c_a; u1lo_b = u1c_b;
-                    u1c_a = u1n_a; u1c_b = u1n_b;
-                    rp_a = rc_a; rp_b = rc_b;
-                }
+        // level 1 only: the planes before the chunk's first output plane; every plane for the halo rows
+        const int n_l1_only = do_l2 ? it_l2_first : nL1;
+        int it = 0;
+        for (; it < n_l1_only; ++it) row_iter<TY, NS, true, false>(p, k, st, it);
+        if (do_l2) {
+            // both levels; three plane iterations per trip so that the three-plane register windows rotate by renaming
+            for (; it < nL1; it += 3) {
+                row_iter<TY, NS, true, true>(p, k, st, it);
+                if (it + 1 >= nL1) { ++it; break; }
+                row_iter<TY, NS, true, true>(p, k, st, it + 1);
+                if (it + 2 >= nL1) { it += 2; break; }
+                row_iter<TY, NS, true, true>(p, k, st, it + 2);
             }
+            if (top) row_iter<TY, NS, false, true>(p, k, st, nL1);
         }
     }
     if (a_sync_lo || a_sync_hi || is_b) {
@@ -402,9 +452,9 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
     }
 }
 
-template <int TY>
+template <int TY, int NS>
 struct Tb2Launcher {
-    using Cfg = Tb2Cfg<TY>;
+    using Cfg = Tb2Cfg<TY, NS>;
     // chunk length: whole waves of one CTA per SM, each CTA paying chunk+3 plane iterations
     static void plan(const Tb2Args& t, dim3& grid, int& chunk, int& n_a)
     {
@@ -452,10 +502,10 @@ struct Tb2Launcher {
         p.done_b = t.done_b; p.target_b_lo = t.target_b_lo; p.target_b_hi = t.target_b_hi;
         static bool attr_set = false;
         if (!attr_set) {
-            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             attr_set = true;
         }
-        jacobi3d_tb2_kernel<TY><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_u0, tm_rhs, p);
+        jacobi3d_tb2_kernel<TY, NS><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_u0, tm_rhs, p);
         return 1;
     }
 };
@@ -468,8 +518,8 @@ int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
 {
     if (t.a.k_end <= t.a.k_begin && !t.b_lo && !t.b_hi) return 0;
     switch (t.a.variant) {
-    case 21: return Tb2Launcher<8>::launch(t, s);
-    default: return Tb2Launcher<12>::launch(t, s);
+    case 21: return Tb2Launcher<8, 6>::launch(t, s);
+    default: return Tb2Launcher<12, 6>::launch(t, s);
     }
 }
 
@@ -478,8 +528,8 @@ int double_sweep_boundary_ctas(const Tb2Args& t)
     dim3 grid;
     int chunk, n_a;
     switch (t.a.variant) {
-    case 21: Tb2Launcher<8>::plan(t, grid, chunk, n_a); break;
-    default: Tb2Launcher<12>::plan(t, grid, chunk, n_a); break;
+    case 21: Tb2Launcher<8, 6>::plan(t, grid, chunk, n_a); break;
+    default: Tb2Launcher<12, 6>::plan(t, grid, chunk, n_a); break;
     }
     return (int)(grid.x * grid.y);
 }
