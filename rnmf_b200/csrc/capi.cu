@@ -34,7 +34,7 @@ extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
            "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "jacobi3d_tb2{128x12,128x8},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi3d_tb2{128x12,128x8},jacobi2d_tb2{512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -963,7 +963,21 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     if (tb2_peer && has_hi) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank + 1, nullptr, &n_hi_slab);
     const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
 
+    // 2D analogue (kernels_sweep2d_tb2.cu): single GPU; variant 0 = auto, 30 = explicit, 20 = single-sweep TMA kernel only
+    const bool tb2_2d = g.dim == 2 && (c->sweep_variant == 0 || c->sweep_variant == 30) && !dist && fused && xy_faces;
+
     for (int64_t it = it0; it < n_sweeps; ++it) {
+        if (tb2_2d && it + 2 <= n_pairable) {
+            SweepArgs t = a;
+            t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
+            t.k_begin = 0; t.k_end = m;
+            RNMF_LAUNCH(c, launch_jacobi_double_sweep_2d(t, s));
+            c->double_sweeps += 1;
+            double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
+            psi->parity ^= 1;
+            ++it;
+            continue;
+        }
         if ((tb2_single || tb2_peer) && it + 2 <= n_pairable) {
             Tb2Args t;
             memset(&t, 0, sizeof(t));

@@ -309,7 +309,7 @@ EncodeTiledFn get_encoder2d()
 
 struct MapKey2 { const double* base; long long pitch, g1n; int bx; };
 struct MapSlot2 { MapKey2 k; CUtensorMap tm; bool used; };
-static MapSlot2 g_map_cache2[16];
+static MapSlot2 g_map_cache2[32];
 static int g_map_next2 = 0;
 
 int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);
@@ -325,7 +325,7 @@ int encode_map2d(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx
         }
     if (encode_map2d_uncached(tm, g, base, bx)) return -1;
     MapSlot2& sl = g_map_cache2[g_map_next2];
-    g_map_next2 = (g_map_next2 + 1) % 16;
+    g_map_next2 = (g_map_next2 + 1) % 32;
     sl.k = k; sl.tm = *tm; sl.used = true;
     return 0;
 }
@@ -387,6 +387,8 @@ int launch2d_one(const dim3& grid, const CUtensorMap& a, const CUtensorMap& b, c
 }
 
 }  // namespace
+
+int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx) { return encode_map2d(tm, g, base, bx); }
 
 int tma2d_sweep_num_partials(const SweepArgs& a)
 {

@@ -41,6 +41,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
 // L2 eviction-priority hints: rhs and psi' are touched once per sweep, psi tiles are re-read by the
 // neighbouring CTAs (xy halo) a few microseconds later; at 6.6 TB/s the 126 MB L2 turns over in
 // ~19 us, so streaming the one-touch traffic with evict_first keeps the psi lines alive longer.
@@ -138,3 +145,5 @@ __device__ __forceinline__ void sstore4(uint32_t a, const double2& va, const dou
 
 // tensor map of a frame buffer with a (bx, by, 1) box (kernels_sweep_tma.cu; cached per buffer/geometry/box)
 int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by);
+// tensor map of a 2D frame buffer with a (bx, 1) box (kernels_sweep2d_tma.cu)
+int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);

@@ -138,7 +138,7 @@ SWEEP_CASES_2D = [
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_2D)
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 20, 30])
 def test_jacobi_2d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
@@ -185,6 +185,41 @@ def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
         np.testing.assert_array_equal(psi.data, want)
         assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
         assert psi.guards_intact() and rhs.guards_intact()       # no store past the end of a buffer
+    finally:
+        ctx.set_option("sweep_variant", "auto")
+        ctx.set_option("resident", 1)
+
+
+@pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
+    ([301, 301], [301.0, 301.0], MIXED_2D, 6, False),        # three double sweeps
+    ([1500, 300], [15.0, 3.0], MIXED_2D, 7, False),          # three 512-column strips, several row chunks; + one single
+    ([1031, 67], [1.0, 1.0], DIRICHLET_2D, 8, True),         # 3 double + 2 single; last valid cell is the first of a pair
+    ([512, 40], [512.0, 40.0], MIXED_2D, 4, False),          # exactly one strip
+    ([513, 9], [1.0, 2.0], MIXED_2D, 5, True),               # one cell past a strip edge
+    ([255, 1], [3.0, 5.0], MIXED_2D, 4, False),              # a single row: both y ghosts in registers
+    ([2, 3], [2.0, 3.0], MIXED_2D, 9, True),
+    ([1, 1], [1.0, 1.0], MIXED_2D, 6, False),
+    ([2048, 700], [1.0, 1.0], DIRICHLET_2D, 6, False),
+])
+def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
+    """kernels_sweep2d_tb2.cu: two 2D sweeps (+ ghost fills) per pass over HBM == two single sweeps, bit for bit."""
+    from rnmf_b200 import poisson
+    ctx.set_option("sweep_variant", 30)
+    ctx.set_option("resident", 0)
+    try:
+        g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=31)
+        ora.fill_bc(g, psi0, obc)
+        psi.fill_bc()
+        d0 = ctx.double_sweep_launches
+        l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=norm)
+        ctx.sync()
+        assert ctx.double_sweep_launches - d0 == (sweeps - (1 if norm else 0)) // 2
+        want = psi0.copy()
+        l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
+        np.testing.assert_array_equal(psi.data, want)
+        if norm:
+            assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+        assert psi.guards_intact() and rhs.guards_intact()
     finally:
         ctx.set_option("sweep_variant", "auto")
         ctx.set_option("resident", 1)
