@@ -109,7 +109,7 @@ int32_t rnmf_ctx_rank(rnmf_ctx* ctx, int32_t* rank, int32_t* nranks);
 /* number of this library's kernels launched on the context since creation (graph replays count
  * their kernel nodes) -- bench.py's gpu_launches */
 int64_t rnmf_kernel_launches(rnmf_ctx* ctx);
-/* how many of those were the 3D double-sweep kernel (two Jacobi sweeps + ghost fills per pass over HBM;
+/* how many of those were double-sweep kernels (two Jacobi sweeps + ghost fills per pass over HBM, 2D and 3D;
  * rnmf_jacobi_sweeps pairs up every two sweeps that do not carry the norm) -- bench.py's roofline accounting */
 int64_t rnmf_double_sweep_launches(rnmf_ctx* ctx);
 /* CUDA-event timer on the context's stream: begin records, end records+synchronises. */
@@ -176,7 +176,8 @@ int32_t rnmf_poisson_coefs(int32_t dim, const double* dx, double* coef4);
 /* The sweep of solve_poisson (poisson.rs:80-89) as out-of-place Jacobi:
  *   n_sweeps x { psi' = coef0*rhs + coef1*(E+W) + coef2*(N+S) [+ coef3*(U+D)] on valid cells;
  *                psi'.fill_bc() }        (association exactly as poisson.rs:83-85)
- * psi is updated in place from the caller's view (internally ping-pong).  On a distributed
+ * psi is updated in place from the caller's view (internally ping-pong; every two sweeps that do not carry
+ * the norm run as ONE double-sweep launch with bit-identical results).  On a distributed
  * context the slab halos are exchanged every sweep, overlapped with the interior update.
  * l1_update (nullable): sum |psi'_last - psi_prev| over valid cells (all ranks), i.e. the
  * quantity main.rs:68-69 forms with two frame operators and `sum`; requesting it synchronises. */

@@ -64,7 +64,8 @@ def run_nccl():
     ctx = R.Context.from_torch_distributed()
     mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
     ok = True
-    for mode in ("peer", "peer_tb2", "peer_flag_kernels", "nccl_overlap", "nccl_serial"):
+    modes = os.environ.get("RNMF_DIST_MODES", "peer,peer_tb2,peer_flag_kernels,nccl_overlap,nccl_serial").split(",")
+    for mode in modes:
         ctx.set_option("halo_overlap", 0 if mode == "nccl_serial" else 1)
         ctx.set_option("peer_halo", 1 if mode.startswith("peer") else 0)
         ctx.set_option("peer_inkernel", 1 if mode in ("peer", "peer_tb2") else 0)   # handshake inside the sweep kernel vs 1-thread flag kernels
