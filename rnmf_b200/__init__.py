@@ -8,7 +8,8 @@ from .boundary_conditions import BCs, BcType, ComponentBCs
 from .dataframe import CartesianDataFrame, CartesianDataFrame2D, CartesianDataFrame3D
 from .mesh import CartesianMesh, CartesianMesh2D, CartesianMesh3D
 from .runtime import Context, default_context, slab_partition
+from .config import ConfigPanic, read_lua
 
 __all__ = ["BCs", "BcType", "ComponentBCs", "CartesianDataFrame", "CartesianDataFrame2D", "CartesianDataFrame3D",
            "CartesianMesh", "CartesianMesh2D", "CartesianMesh3D", "Context", "default_context", "slab_partition",
-           "RnmfError"]
+           "RnmfError", "ConfigPanic", "read_lua"]

@@ -443,8 +443,11 @@ def test_magnetostatics_lua_case_full(R, ctx):
     with open(os.path.join(os.path.dirname(__file__), "golden", "magnetostatics_trace.json")) as fh:
         gold = json.load(fh)
     MAGNETOSTATICS_TRACE, MAGNETOSTATICS_PSI_150_150 = gold["sum_diff"], gold["psi_150_150"]
-    cfg = poisson.Config(poisson.GeomConfig(2, (301.0, 301.0), (301, 301)),
-                         poisson.UserModel((0.0, 1.0), 0.2, 10, 550, (301.0 / 2, 301.0 / 2), 301.0 / 20, (3.2, 1.0), 0.1))
+    from rnmf_b200 import config
+    # the .lua case itself, unedited, through the Lua-subset reader (config.rs:90-158 mirror)
+    cfg = config.read_lua(os.path.join(os.path.dirname(os.path.dirname(__file__)), "cases", "ferro_droplet.lua"))
+    assert cfg == poisson.Config(poisson.GeomConfig(2, (301.0, 301.0), (301, 301)),
+                                 poisson.UserModel((0.0, 1.0), 0.2, 10, 550, (301.0 / 2, 301.0 / 2), 301.0 / 20, (3.2, 1.0), 0.1))
     psi, trace, iters = poisson.magnetostatics(cfg, order="reference", ctx=ctx)
     assert iters == 10
     for a, b in zip(trace, MAGNETOSTATICS_TRACE):
