@@ -164,6 +164,34 @@ def ncu_traffic(workload: str):
         return None
 
 
+def build_roofline(main_res: dict, steps: int, sub_iters: int, workload: str, peak: float, peak_src: str) -> dict:
+    """The `roofline` object of the JSON line from one timed region (pure; tested on the CPU).
+    main_res: ms (timed region, max over ranks), doubles (double-sweep launches in it), local_cells."""
+    sweep_ms = main_res["ms"] / (steps * sub_iters)                       # average time per sweep over the timed region
+    # dominant kernel: by default the double-sweep kernel (two sweeps + ghost fills per launch, one pass over HBM);
+    # its launch duration is taken as two sweeps' share of the timed region (an upper bound: the region also holds
+    # the norm-carrying single sweep, the shell copy and the reduction)
+    double = main_res["doubles"] * 2 > steps * sub_iters // 2
+    sweeps_per_launch = 2 if double else 1
+    launch_ms = sweep_ms * sweeps_per_launch
+    alg_bytes = BYTES_PER_LUP * main_res["local_cells"] * sweeps_per_launch   # SURVEY 8d: 24 B per update x updates per launch
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9                           # GB/s per GPU (the slowest rank's clock)
+    traffic = ncu_traffic(workload + ("_tb2" if double else ""))
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "kernel": "double sweep (2 sweeps + fused ghost fills per launch)" if double else "jacobi sweep (fused ghost fill)",
+                "sweeps_per_launch": sweeps_per_launch, "double_sweep_launches": main_res["doubles"],
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": launch_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
+    if double:
+        roofline["note"] = ("achieved counts the ALGORITHMIC 24 B per update; the kernel performs two updates per byte pass "
+                            "(temporal blocking), so frac can exceed 1. dram_frac = measured DRAM traffic per launch / launch time / peak.")
+        if traffic:
+            roofline["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
+            roofline["dram_frac"] = roofline["dram_gbs"] / peak
+    return roofline
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU side: the oracle's reference-faithful Gauss-Seidel sweep (poisson.rs:80-89 loop order)
 # ------------------------------------------------------------------------------------------------
@@ -492,28 +520,8 @@ def main():
     launches_total = int(reduce_sum(float(main_res["launches"])))
 
     peak, peak_src = measured_peak()
-    sweep_ms = main_res["ms"] / (args.steps * args.sub_iters)            # average time per sweep over the timed region
-    # dominant kernel: 3D default = the double-sweep kernel (two sweeps + ghost fills per launch, one pass over HBM);
-    # its launch duration is taken as two sweeps' share of the timed region (an upper bound: the region also holds
-    # the norm-carrying single sweep, the shell copy and the reduction)
-    double = main_res["doubles"] * 2 > args.steps * args.sub_iters // 2
-    sweeps_per_launch = 2 if double else 1
-    launch_ms = sweep_ms * sweeps_per_launch
-    alg_bytes = BYTES_PER_LUP * main_res["local_cells"] * sweeps_per_launch   # 24 B per update x updates per launch
-    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9                           # GB/s per GPU (the slowest rank's clock)
-    traffic = ncu_traffic(args.workload + ("_tb2" if double else ""))
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
-                "kernel": "jacobi3d_tb2 double sweep (2 sweeps + fused ghost fills per launch)" if double else "jacobi sweep (fused ghost fill)",
-                "sweeps_per_launch": sweeps_per_launch, "double_sweep_launches": main_res["doubles"],
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_ms": launch_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
-    if double:
-        roofline["note"] = ("achieved counts the ALGORITHMIC 24 B per update; the kernel performs two updates per byte pass "
-                            "(temporal blocking), so frac can exceed 1. dram_frac = measured DRAM traffic per launch / launch time / peak.")
-        if traffic:
-            roofline["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
-            roofline["dram_frac"] = roofline["dram_gbs"] / peak
+    roofline = build_roofline(main_res, args.steps, args.sub_iters, args.workload, peak, peak_src)
+    achieved = roofline["achieved"]
     if rank == 0:
         try:
             burst, sustained = copy_bandwidth_this_box()

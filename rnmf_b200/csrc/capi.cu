@@ -957,7 +957,8 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
     bool xy_faces = true;
     for (int fi = 0; fi < 4; ++fi) xy_faces = xy_faces && a.faces.f[fi].mode != 0;
-    const bool tb2_peer = tb2_variant && peer && c->peer_inkernel && D == 2 && m >= 4 && xy_faces && scratch_planes(g) == 2 &&
+    // every rank must take the same decision: the thinnest slab (floor(n/P), cartesian2d/mod.rs:64-73) needs 4 planes
+    const bool tb2_peer = tb2_variant && peer && c->peer_inkernel && D == 2 && g.nglob[D] / c->nranks >= 4 && xy_faces && scratch_planes(g) == 2 &&
                           (has_lo || a.faces.f[4].mode != 0) && (has_hi || a.faces.f[5].mode != 0);
     int64_t n_hi_slab = 0;
     if (tb2_peer && has_hi) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank + 1, nullptr, &n_hi_slab);

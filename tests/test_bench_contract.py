@@ -37,3 +37,32 @@ def test_gpu_arm_refuses_without_device():
         pytest.skip("a device is present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def _bench_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_roofline_accounting_single_and_double_sweep():
+    """`roofline.achieved` = SURVEY 8d's 24 B per update x the updates one launch of the dominant kernel performs /
+    that launch's share of the timed region: the double-sweep kernel counts two sweeps per launch, so frac may
+    exceed 1; dram_frac puts the measured DRAM bytes of the committed ncu capture beside it."""
+    b = _bench_module()
+    cells = 768 ** 3
+    # the committed default line (profiles/r1_bench_default_n1_tb2.json): 5 steps x 550 sweeps, 1370 double launches
+    r = b.build_roofline({"ms": 663.694677734375 * 5, "doubles": 1370, "local_cells": cells}, 5, 550, "3d7_768", 6549.8, "MEASURED_PEAKS.json hbm_gbs")
+    assert r["sweeps_per_launch"] == 2 and r["algorithmic_bytes_per_launch"] == 2 * 24 * cells
+    assert abs(r["avg_launch_ms"] - 2 * 663.694677734375 / 550) < 1e-9
+    assert abs(r["frac"] - 1.3755) < 1e-3 and r["frac"] == r["achieved"] / r["peak"]
+    assert r["traffic"] and abs(r["dram_frac"] - r["traffic"] / (r["avg_launch_ms"] * 1e-3) / 1e9 / 6549.8) < 1e-12
+    assert r["dram_frac"] < 1.0 < r["frac"]
+    # single-sweep kernel only (variant 6): one sweep per launch, no note
+    r1 = b.build_roofline({"ms": 965.5 * 5, "doubles": 0, "local_cells": cells}, 5, 550, "3d7_768", 6549.8, "MEASURED_PEAKS.json hbm_gbs")
+    assert r1["sweeps_per_launch"] == 1 and r1["algorithmic_bytes_per_launch"] == 24 * cells and "note" not in r1
+    assert abs(r1["frac"] - 0.9455) < 1e-3
+    # both describe the same GLUP/s <-> GB/s relation: achieved / 24 B = updates per second
+    assert abs(r["achieved"] / 24 - cells * 550 / (663.694677734375e-3) / 1e9) < 1e-6 * r["achieved"]
