@@ -101,6 +101,13 @@ int launch_copy_ghost_shell(const FrameGeom& g, const double* src, double* dst, 
 // ghost slice I am about to overwrite), and the last of them to finish publishes epoch+1 to the
 // neighbour.  Dependency chain: my sweep e+1 <- neighbour's sweep e <- my sweep e-1 (complete):
 // no cycle, and the waiter only depends on another GPU's progress.
+// The double-sweep kernel (kernels_sweep_tb2.cu) advances the epoch by two per launch and adds a second
+// flag word per side for the half step: its A chunks next to a neighbour wait flag >= epoch (the neighbour's
+// previous launch has delivered my input ghosts and no longer reads my scratch plane), store u1 of their
+// boundary plane into the neighbour's scratch plane and publish half = epoch+1; its one-plane B chunks wait
+// half >= epoch+1, store u2 of the boundary plane into the neighbour's ghost plane and publish
+// flag = epoch+2.  Each word is written by one kind of chunk per launch, so both stay monotonic, and the
+// single-sweep kernels' "wait flag >= epoch, publish epoch+1" interleaves with it unchanged.
 struct PeerSync {
     const unsigned long long* wait_lo;   // my flag written by the lo neighbour (null: no lo neighbour / not used)
     const unsigned long long* wait_hi;

@@ -8,20 +8,27 @@
 //   * CTA tile: 128 x TY cells of u2, a chunk of z-planes.  u1 is needed on the tile grown by one
 //     cell in x and y (no corners) and by one plane in z, u0 on the tile grown by two.
 //   * producer warp: per plane one TMA box of u0 ((128+4) x (TY+4), the two-cell x halo keeps the
-//     interior 16-byte aligned in shared memory) and one of rhs ((128+4) x (TY+2)) into a 4-stage
-//     ring (full/empty mbarriers), exactly as in kernels_sweep_tma.cu.
+//     interior 16-byte aligned in shared memory) and one of rhs ((128+4) x (TY+2)) into an NS-stage
+//     ring (full/empty mbarriers), as in kernels_sweep_tma.cu; ring indices are run-time values.
 //   * TY "row" warps own one tile row each (lane l: cell pairs 2l,2l+1 and 64+2l,65+2l), two more
 //     row warps own the halo rows j0-1 and j0+TY (level 1 only), one warp owns the two halo columns
 //     i0-1 and i0+128 (level 1 only).  Level 1 is register z-marched over u0 exactly like the
-//     single-sweep kernel; its result goes to a 4-slot shared-memory ring of u1 planes, together
+//     single-sweep kernel; its result goes to a 2-slot shared-memory ring of u1 planes, together
 //     with the ghost values fill_bc would give u1 on the physical x/y faces.  Level 2 is register
 //     z-marched over the lane's own u1 values (the z ghosts of u1 are formed in registers) and
 //     reads the N/S/E/W neighbours of u1 from the ring.
-//   * u1 ring protocol: one mbarrier per slot, every level-1 warp arrives after writing plane it
-//     into slot it%4.  A warp waits for plane it-1 before its level-2 reads and for plane it-2
-//     before it overwrites slot it%4 (all warps have then finished iteration it-3, whose level-2
-//     reads were the last of the plane that lived in that slot): warps may drift a whole plane
-//     apart, no CTA-wide barrier in the loop.
+//   * one wait phase per plane iteration: full[stage of the next u0 plane] and u1full[slot of u1
+//     plane it-1] (one mbarrier per slot; every level-1 warp arrives after writing plane it into slot
+//     it%2).  The second wait is the read-after-write guard of level 2 AND the write-after-read guard
+//     of the slot level 1 is about to overwrite: a warp reads plane it-2 at the top of iteration it-1,
+//     before it arrives for plane it-1 (release), so once all have arrived nobody reads it any more.
+//   * behind the waits all shared-memory loads of both levels are issued together; level 2's x/y part
+//     (c0*rhs + c1*(E+W)) + c2*(N+S) is formed BEFORE level 1 (it does not depend on the new u1
+//     plane), its z term + c3*(U+D) is added once level 1 has produced that plane -- the
+//     reference's association (poisson.rs:83-88), so u2 does not change.
+//   * the main loop makes three plane iterations per trip: the three-plane register windows of both
+//     levels rotate by renaming; level-1-only iterations (planes before the chunk's first output,
+//     and the halo-row warps) and the level-2-only last plane of the slab are peeled.
 //   * u2 is stored with the fused ghost fill of the output frame, as in the single-sweep kernel.
 //
 // Slabs (one GPU per z-slab): u2 of the slab's first/last plane needs the neighbour's u1 boundary
