@@ -207,5 +207,40 @@ std::shared_ptr<Stage<T>> make_jacobi_stage(const std::string& psi, const std::s
     return stage;
 }
 
+// The same loop with the sweeps between two checks handed to the device in ONE call: a step is
+// `check_every` sweeps (the update norm comes from the last of them), the stage stops after
+// ceil(max_sweeps / check_every) steps or when the norm drops below `tol`.  The stop test therefore
+// happens at exactly the sweep counts of make_jacobi_stage and the field is bit-identical, but
+// rnmf_jacobi_sweeps can pair the sweeps up (two per pass over HBM) or keep a small frame resident in
+// L2, and the host launches once per check instead of once per sweep.  sweeps_run() = steps x check_every.
+template <class T>
+std::shared_ptr<Stage<T>> make_jacobi_stage_batched(const std::string& psi, const std::string& rhs, std::size_t max_sweeps,
+                                                    std::size_t check_every, Real tol)
+{
+    const std::size_t every = check_every ? check_every : 1;
+    struct State { Real last_norm = HUGE_VAL; };
+    auto st = std::make_shared<State>();
+    auto stage = std::make_shared<Stage<T>>();
+    stage->stop.max_iters = (max_sweeps + every - 1) / every;
+    typename Step<T>::Callback cb = [st, psi, rhs, every](const config::Config<T>&, CartesianBlock& b) {
+        CartesianDataFrame2D& f = b[psi];
+        const auto& m = *f.underlying_mesh;
+        const double dx[3] = { m.dx[0], m.dx[1], 1.0 };
+        double coef[4];
+        check(rnmf_poisson_coefs(2, dx, coef), "rnmf_poisson_coefs");
+        double l1 = 0.0;
+        check(rnmf_jacobi_sweeps(f.handle(), b[rhs].handle(), coef, (int64_t)every, &l1), "rnmf_jacobi_sweeps");
+        f.invalidate_mirror();
+        st->last_norm = l1;
+    };
+    stage->iteration.emplace_back(cb);
+    GlobalStop gs;
+    gs.global.get_value = [st](const CartesianBlock&) { return st->last_norm; };
+    gs.condition = { global::GlobalCompare::Less, tol };
+    gs.check_every = 1;
+    stage->stop.global_stop.push_back(gs);
+    return stage;
+}
+
 }  // namespace solver
 }  // namespace rnmf

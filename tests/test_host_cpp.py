@@ -131,6 +131,14 @@ def test_solver_stage_drives_gpu_sweeps(host_bins):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     res = json.loads(r.stdout.strip().splitlines()[-1])
+    # the batched stage (one device call per check: sweeps paired up / kept L2-resident) stops at the same sweep
+    # with the same field and norm
+    rb = subprocess.run([os.path.join(host_bins, "stage_gpu"), str(n), str(max_iters), str(every), str(tol), "batched"],
+                        capture_output=True, text=True, timeout=300)
+    assert rb.returncode == 0, rb.stdout + rb.stderr
+    resb = json.loads(rb.stdout.strip().splitlines()[-1])
+    assert resb["iterations"] == res["iterations"] and resb["psi_mid"] == res["psi_mid"]
+    assert abs(resb["norm"] - res["norm"]) <= 1e-12 * res["norm"]
     g = ora.geom([n, n], hi=[1.0, 1.0])
     bc = ora.bcs(2, [([("dirichlet", 0.0), ("dirichlet", 0.0)], [("dirichlet", 1.0), ("dirichlet", 1.0)])])
     psi, rhs = ora.zeros(g), ora.zeros(g)
