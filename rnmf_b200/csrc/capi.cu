@@ -214,45 +214,10 @@ int alloc_buffer(const FrameGeom& g, double** out, cudaStream_t s)
     return write_guard(*out, g, s);
 }
 
-void make_geom(FrameGeom& g, int dim, const int64_t* n, const double* lo, const double* dx, int ng, int ncomp)
-{
-    memset(&g, 0, sizeof(g));
-    g.dim = dim; g.ng = ng; g.ncomp = ncomp;
-    g.kg = dim == 3 ? ng : 0;
-    for (int d = 0; d < 3; ++d) {
-        g.n[d] = d < dim ? n[d] : 1;
-        g.G[d] = d < dim ? n[d] + 2 * ng : 1;
-        g.dx[d] = d < dim ? dx[d] : 1.0;
-        g.lo[d] = d < dim ? lo[d] : 0.0;
-        g.nglob[d] = g.n[d];
-        g.off[d] = 0;
-    }
-    g.xoff = RNMF_ROW_ALIGN - ng;
-    g.pitch = ((RNMF_ROW_ALIGN + g.n[0] + ng + RNMF_ROW_ALIGN - 1) / RNMF_ROW_ALIGN) * RNMF_ROW_ALIGN;
-    g.plane = g.pitch * g.G[1];
-    g.comp = g.plane * g.G[2];
-    g.total = g.comp * ncomp;
-}
-
 bool same_shape(const FrameGeom& a, const FrameGeom& b)
 {
     return a.dim == b.dim && a.ng == b.ng && a.ncomp == b.ncomp && a.n[0] == b.n[0] && a.n[1] == b.n[1] &&
            a.n[2] == b.n[2];
-}
-
-// FaceBC for one raw face (HALO / Prescribed / Reflect -> mode 0 here)
-FaceBC make_face(const rnmf_bc_face& f, int side, double dxd)
-{
-    FaceBC b;
-    b.mode = 0; b.value = f.value; b.s1 = 0.0;
-    if (f.kind == RNMF_BC_DIRICHLET) {
-        b.mode = 1;
-        b.s1 = 2.0 * f.value;                               // dataframe.rs:328,344
-    } else if (f.kind == RNMF_BC_NEUMANN) {
-        b.mode = side == 0 ? 2 : 3;
-        b.s1 = f.value * (2.0 * 1.0 - 1.0) * dxd;           // :293-294 (g=1), :311-312 (g=0)
-    }
-    return b;
 }
 
 int slow_dim(const FrameGeom& g) { return g.dim - 1; }

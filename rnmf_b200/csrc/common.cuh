@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/rnmf_b200.h"
 
 #define RNMF_ROW_ALIGN 16  // doubles (128 bytes)
@@ -66,6 +67,42 @@ __host__ __device__ inline double rnmf_ghost_value(const FaceBC& b, int side, do
     double s = b.value * fac * dxd;
     return side == 0 ? mirror - s : mirror + s;
 #endif
+}
+
+// geometry of a frame with n valid cells per direction (capi.cu: rnmf_frame_create*)
+inline void make_geom(FrameGeom& g, int dim, const int64_t* n, const double* lo, const double* dx, int ng, int ncomp)
+{
+    memset(&g, 0, sizeof(g));
+    g.dim = dim; g.ng = ng; g.ncomp = ncomp;
+    g.kg = dim == 3 ? ng : 0;
+    for (int d = 0; d < 3; ++d) {
+        g.n[d] = d < dim ? n[d] : 1;
+        g.G[d] = d < dim ? n[d] + 2 * ng : 1;
+        g.dx[d] = d < dim ? dx[d] : 1.0;
+        g.lo[d] = d < dim ? lo[d] : 0.0;
+        g.nglob[d] = g.n[d];
+        g.off[d] = 0;
+    }
+    g.xoff = RNMF_ROW_ALIGN - ng;
+    g.pitch = ((RNMF_ROW_ALIGN + g.n[0] + ng + RNMF_ROW_ALIGN - 1) / RNMF_ROW_ALIGN) * RNMF_ROW_ALIGN;
+    g.plane = g.pitch * g.G[1];
+    g.comp = g.plane * g.G[2];
+    g.total = g.comp * ncomp;
+}
+
+// FaceBC for one raw face (HALO / Prescribed / Reflect -> mode 0 here)
+inline FaceBC make_face(const rnmf_bc_face& f, int side, double dxd)
+{
+    FaceBC b;
+    b.mode = 0; b.value = f.value; b.s1 = 0.0;
+    if (f.kind == RNMF_BC_DIRICHLET) {
+        b.mode = 1;
+        b.s1 = 2.0 * f.value;                               // dataframe.rs:328,344
+    } else if (f.kind == RNMF_BC_NEUMANN) {
+        b.mode = side == 0 ? 2 : 3;
+        b.s1 = f.value * (2.0 * 1.0 - 1.0) * dxd;           // :293-294 (g=1), :311-312 (g=0)
+    }
+    return b;
 }
 
 // error plumbing (capi.cu)
@@ -146,6 +183,26 @@ __device__ __forceinline__ void peer_publish(unsigned long long* done, unsigned 
 }
 // boundary chunks last: chunk index -> 1, 2, .., n-2, 0, n-1
 __device__ __forceinline__ unsigned peer_chunk_order(unsigned b, unsigned n)
+{
+    return n < 3 ? b : (b < n - 2 ? b + 1 : (b == n - 2 ? 0u : n - 1));
+}
+#elif defined(RNMF_EMULATE)
+// host emulation (tests/emu/emu_cuda.hpp; test builds only): "devices" share the process's memory, flags are std atomics
+inline void peer_spin_wait(const unsigned long long* flag, unsigned long long target, unsigned long long* status)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) >= target) break;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(emu::g_wait_timeout_s.load())) { __atomic_store_n(status, target, __ATOMIC_RELEASE); break; }
+        std::this_thread::yield();
+    }
+}
+inline void peer_publish(unsigned long long* done, unsigned long long target, unsigned long long* peer_flag, unsigned long long value)
+{
+    const unsigned long long old = __atomic_fetch_add(done, 1ULL, __ATOMIC_ACQ_REL);
+    if (old + 1 == target) __atomic_store_n(peer_flag, value, __ATOMIC_RELEASE);
+}
+inline unsigned peer_chunk_order(unsigned b, unsigned n)
 {
     return n < 3 ? b : (b < n - 2 ? b + 1 : (b == n - 2 ? 0u : n - 1));
 }

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32 * (NW2 + 2), 2) jacobi2d_tb2_kernel(const _
                                                                          const __grid_constant__ Tb2dParams p)
 {
     using Cfg = Cfg2<NS>;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    RNMF_DYNAMIC_SMEM(smem_raw);
     const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, u1_0 = sb + Cfg::U1_OFF;
     const uint32_t full0 = sb + Cfg::BAR_OFF, empty0 = full0 + NS * 8, u1full0 = empty0 + NS * 8;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(32 * (NW2 + 2), 2) jacobi2d_tb2_kernel(const _
         }
         mbar_init(u1full0, Cfg::NCONS);
         mbar_init(u1full0 + 8, Cfg::NCONS);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
 
@@ -347,12 +347,14 @@ int launch_jacobi_double_sweep_2d(const SweepArgs& a, cudaStream_t s)
     Tb2dParams p;
     p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
     p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
+#ifndef RNMF_EMULATE
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(jacobi2d_tb2_kernel<kNS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
         cudaFuncSetAttribute(jacobi2d_tb2_kernel<kNS2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr_set = true;
     }
-    jacobi2d_tb2_kernel<kNS2><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_u256, tm_u4, tm_r256, tm_r4, p);
+#endif
+    RNMF_KERNEL_LAUNCH(jacobi2d_tb2_kernel<kNS2>, grid, Cfg::THREADS, Cfg::SMEM, s, tm_u256, tm_u4, tm_r256, tm_r4, p);
     return 1;
 }

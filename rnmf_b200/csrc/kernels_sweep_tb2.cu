@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
     using Cfg = Tb2Cfg<TY, NS>;
     constexpr int TX = Cfg::TX, BX = Cfg::BX;
     static_assert(TY <= 16, "the halo-column warp maps 16 rows per side");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    RNMF_DYNAMIC_SMEM(smem_raw);
     const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, u1_0 = sb + Cfg::U1_OFF;
     const uint32_t full0 = sb + Cfg::BAR_OFF, empty0 = full0 + NS * 8, u1full0 = empty0 + NS * 8;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
         }
         mbar_init(u1full0, Cfg::NCONS);
         mbar_init(u1full0 + 8, Cfg::NCONS);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
         if (a_sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
         if (a_sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
         if (b_is_lo) peer_spin_wait(p.half_wait_lo, p.ps.epoch + 1, p.ps.status);
@@ -507,12 +507,14 @@ struct Tb2Launcher {
         p.half_wait_lo = t.half_wait_lo; p.half_wait_hi = t.half_wait_hi;
         p.half_sig_lo = t.half_sig_lo; p.half_sig_hi = t.half_sig_hi;
         p.done_b = t.done_b; p.target_b_lo = t.target_b_lo; p.target_b_hi = t.target_b_hi;
+#ifndef RNMF_EMULATE
         static bool attr_set = false;
         if (!attr_set) {
             if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             attr_set = true;
         }
-        jacobi3d_tb2_kernel<TY, NS><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_u0, tm_rhs, p);
+#endif
+        RNMF_KERNEL_LAUNCH((jacobi3d_tb2_kernel<TY, NS>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
         return 1;
     }
 };

@@ -2,17 +2,42 @@
 // kernels_sweep_tb2.cu): mbarrier / cp.async.bulk.tensor wrappers, shared-memory accessors, the
 // explicitly rounded 7-point update and the branch-free ng=1 ghost rule.
 #pragma once
+#ifdef RNMF_EMULATE
+#include "emu_cuda.hpp"   // tests/emu (test builds only: g++ -DRNMF_EMULATE -Itests/emu); never part of librnmf_b200.so
+#endif
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 
 #include "common.cuh"
 
 namespace tmau {
 
+#ifdef RNMF_EMULATE
+// ---- host emulation of the PTX wrappers (tests/emu/emu_cuda.hpp; test builds only) --------------------------
+inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - emu::g_cta->smem); }
+inline void mbar_init(uint32_t bar, uint32_t count) { emu::mbar_init(bar, count); }
+inline void mbar_fence_init() {}
+inline void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) { emu::mbar_arrive(bar, bytes); }
+inline void mbar_arrive(uint32_t bar) { emu::mbar_arrive(bar); }
+inline void mbar_wait(uint32_t bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
+inline void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) { emu::tma_load(dst, tm, c0, c1, c2, bar); }
+inline void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) { emu::tma_load(dst, tm, c0, c1, 0, bar); }
+inline uint64_t policy_evict_first() { return 0; }
+inline void tma_load_3d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar, uint64_t) { emu::tma_load(dst, tm, c0, c1, c2, bar); }
+inline void st2_hint(double* p, const double2& v, uint64_t) { p[0] = v.x; p[1] = v.y; }
+inline double2 lds2(uint32_t a) { double2 v; std::memcpy(&v, emu::g_cta->smem + a, 16); return v; }
+inline double lds1(uint32_t a) { double v; std::memcpy(&v, emu::g_cta->smem + a, 8); return v; }
+inline void sts2(uint32_t a, const double2& v) { std::memcpy(emu::g_cta->smem + a, &v, 16); }
+inline void sts1(uint32_t a, double v) { std::memcpy(emu::g_cta->smem + a, &v, 8); }
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -90,6 +115,8 @@ __device__ __forceinline__ void sts1(uint32_t a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
+#endif  // RNMF_EMULATE
+
 // poisson.rs:83-88 with the reference's association, every operation explicitly rounded
 __device__ __forceinline__ double upd3(double c0, double c1, double c2, double c3, double r, double e, double w,
                                        double n, double s, double u, double d)
@@ -142,6 +169,20 @@ __device__ __forceinline__ void sstore4(uint32_t a, const double2& va, const dou
 }
 
 }  // namespace tmau
+
+// dynamic shared memory of the CTA (the emulator hands each CTA a host buffer)
+#ifdef RNMF_EMULATE
+#define RNMF_DYNAMIC_SMEM(name) unsigned char* const name = emu::g_cta->smem
+#else
+#define RNMF_DYNAMIC_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+#endif
+
+// kernel launch: <<<>>> on the device, the thread-per-lane emulator in -DRNMF_EMULATE test builds
+#ifdef RNMF_EMULATE
+#define RNMF_KERNEL_LAUNCH(kernel, grid, threads, smem, stream, ...) emu_launch_checked(kernel, grid, threads, smem, __VA_ARGS__)
+#else
+#define RNMF_KERNEL_LAUNCH(kernel, grid, threads, smem, stream, ...) kernel<<<grid, threads, smem, stream>>>(__VA_ARGS__)
+#endif
 
 // tensor map of a frame buffer with a (bx, by, 1) box (kernels_sweep_tma.cu; cached per buffer/geometry/box)
 int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by);

@@ -1,0 +1,301 @@
+// emu_driver.cpp -- TEST INFRASTRUCTURE: the double-sweep kernel SOURCES (kernels_sweep_tb2.cu,
+// kernels_sweep2d_tb2.cu) compiled with g++ -DRNMF_EMULATE and run on host threads by the SIMT emulator
+// (tests/emu/emu_cuda.hpp).  Exposes a small C interface for tests/test_emulated_kernels.py:
+// dense reference-layout frames in, dense frames out, through the very launchers (planner, tensor maps,
+// A/B chunk roles, handshake flags) the library uses.  Slabs: every "rank" is a host thread with its own
+// buffers; peer pointers are plain pointers into the neighbours' buffers.
+#define RNMF_EMULATE 1
+#include "emu_cuda.hpp"
+#include "../../rnmf_b200/csrc/tma_util.cuh"
+
+#include <cstdarg>
+#include <cstdlib>
+
+namespace {
+std::atomic<int> g_deadlocks{0};
+
+template <class Kernel, class... Args>
+void emu_launch_checked(Kernel kernel, dim3 grid, int threads, size_t smem_bytes, Args... args)
+{
+    std::vector<unsigned char> raw(smem_bytes + 2048);                 // one CTA at a time per launch
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw.data()) + 1023) & ~uintptr_t(1023));
+    if (!emu::launch(kernel, grid, threads, smem, smem_bytes, args...)) ++g_deadlocks;
+}
+}  // namespace
+
+void rnmf_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fputc('\n', stderr);
+}
+
+// what cuTensorMapEncodeTiled describes, for the emulated TMA (dims / strides as kernels_sweep_tma.cu encodes them)
+int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by)
+{
+    emu::Map m;
+    m.base = base; m.rank = 3;
+    m.dims[0] = (unsigned long long)g.pitch; m.dims[1] = (unsigned long long)g.G[1]; m.dims[2] = (unsigned long long)(g.G[2] * g.ncomp);
+    m.stride[0] = 1; m.stride[1] = (unsigned long long)g.pitch; m.stride[2] = (unsigned long long)g.plane;
+    m.box[0] = (unsigned)bx; m.box[1] = (unsigned)by; m.box[2] = 1;
+    emu::encode(tm, m);
+    return 0;
+}
+int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx)
+{
+    emu::Map m;
+    m.base = base; m.rank = 2;
+    m.dims[0] = (unsigned long long)g.pitch; m.dims[1] = (unsigned long long)(g.G[1] * g.ncomp); m.dims[2] = 1;
+    m.stride[0] = 1; m.stride[1] = (unsigned long long)g.pitch; m.stride[2] = 0;
+    m.box[0] = (unsigned)bx; m.box[1] = 1; m.box[2] = 1;
+    emu::encode(tm, m);
+    return 0;
+}
+
+#include "../../rnmf_b200/csrc/kernels_sweep_tb2.cu"
+#include "../../rnmf_b200/csrc/kernels_sweep2d_tb2.cu"
+
+namespace {
+
+constexpr long long kTail = 64 + 256;       // tail pad + guard band of the library's buffers (capi.cu)
+
+struct Frame {
+    FrameGeom g;
+    std::vector<double> buf[2];              // ping-pong; each: total + tail + 2 scratch planes
+    std::vector<double> rhs;
+    int cur = 0;
+    long long scratch_off() const { return g.total + kTail; }
+};
+
+void unpack(const FrameGeom& g, const double* dense, double* pitched)
+{
+    const long long rows = g.G[1] * g.G[2];
+    for (long long r = 0; r < rows; ++r)
+        for (long long i = 0; i < g.G[0]; ++i) pitched[g.xoff + i + g.pitch * r] = dense[i + g.G[0] * r];
+}
+void pack(const FrameGeom& g, const double* pitched, double* dense)
+{
+    const long long rows = g.G[1] * g.G[2];
+    for (long long r = 0; r < rows; ++r)
+        for (long long i = 0; i < g.G[0]; ++i) dense[i + g.G[0] * r] = pitched[g.xoff + i + g.pitch * r];
+}
+
+void init_frame(Frame& f, int dim, const long long* n, const double* dx, const double* psi_dense, const double* rhs_dense)
+{
+    const int64_t n64[3] = { n[0], n[1], dim == 3 ? n[2] : 1 };
+    const double lo[3] = { 0, 0, 0 };
+    make_geom(f.g, dim, n64, lo, dx, 1, 1);
+    const size_t len = (size_t)(f.g.total + kTail + 2 * f.g.plane);
+    // poison what is not data: padding columns, the tail, the scratch planes
+    f.buf[0].assign(len, -7.0e300); f.buf[1].assign(len, 9.0e300); f.rhs.assign(len, 5.0e300);
+    unpack(f.g, psi_dense, f.buf[0].data());
+    unpack(f.g, psi_dense, f.buf[1].data());       // the library copies the ghost shell into the second buffer
+    unpack(f.g, rhs_dense, f.rhs.data());
+}
+
+FaceSet make_faces(int dim, const int* kind, const double* value, const double* dx)
+{
+    FaceSet fs;
+    for (int i = 0; i < 6; ++i) { fs.f[i].mode = 0; fs.f[i].value = 0; fs.f[i].s1 = 0; }
+    for (int d = 0; d < dim; ++d)
+        for (int side = 0; side < 2; ++side) {
+            rnmf_bc_face r;
+            r.kind = kind[d * 2 + side]; r._pad = 0; r.value = value[d * 2 + side]; r.prescribed = nullptr; r.n_prescribed = 0;
+            fs.f[d * 2 + side] = make_face(r, side, dx[d]);
+        }
+    return fs;
+}
+
+}  // namespace
+
+namespace {
+// the checker must be able to fail: a CTA whose second warp waits for a phase nobody completes
+void selftest_deadlock_kernel(int dummy)
+{
+    (void)dummy;
+    RNMF_DYNAMIC_SMEM(smem);
+    const uint32_t bar = tmau::smem_u32(smem);
+    if (threadIdx.x == 0) tmau::mbar_init(bar, 2);
+    __syncthreads();
+    if (threadIdx.x == 32) tmau::mbar_arrive(bar);             // one of the two arrivals is missing
+    if (threadIdx.x >= 32) tmau::mbar_wait(bar, 0);
+}
+// ... and to pass: both arrivals present, a transaction count completed by an emulated TMA load
+void selftest_ok_kernel(CUtensorMap tm)
+{
+    RNMF_DYNAMIC_SMEM(smem);
+    const uint32_t bar = tmau::smem_u32(smem), dst = bar + 128;
+    if (threadIdx.x == 0) tmau::mbar_init(bar, 2);
+    __syncthreads();
+    if (threadIdx.x == 0) { tmau::mbar_arrive_expect_tx(bar, 4 * 8); tmau::tma_load_2d(dst, &tm, -1, 0, bar); }
+    if (threadIdx.x == 32) tmau::mbar_arrive(bar);
+    tmau::mbar_wait(bar, 0);
+    // box (-1..2, row 0) of a 3-wide row {5,6,7}: out-of-bounds column -1 reads as zero
+    if (tmau::lds1(dst) != 0.0 || tmau::lds1(dst + 8) != 5.0 || tmau::lds1(dst + 24) != 7.0) g_deadlocks += 100;
+}
+}  // namespace
+
+extern "C" {
+
+void emu_set_timeout(int seconds) { emu::g_wait_timeout_s = seconds; }
+
+// returns (deadlock detected ? 1 : 0) + 2 * (well-formed CTA completed and read the right TMA data ? 1 : 0): 3 = both as expected
+int emu_selftest()
+{
+    g_deadlocks = 0;
+    const int saved = emu::g_wait_timeout_s.load();
+    emu::g_wait_timeout_s = 1;
+    emu_launch_checked(selftest_deadlock_kernel, dim3(1, 1, 1), 64, 256, 0);
+    emu::g_wait_timeout_s = saved;
+    const int dead = g_deadlocks.load() == 1;
+    g_deadlocks = 0;
+    static const double row[3] = { 5.0, 6.0, 7.0 };
+    emu::Map m;
+    m.base = row; m.rank = 2; m.dims[0] = 3; m.dims[1] = 1; m.dims[2] = 1; m.stride[0] = 1; m.stride[1] = 3; m.stride[2] = 0;
+    m.box[0] = 4; m.box[1] = 1; m.box[2] = 1;
+    CUtensorMap tm;
+    emu::encode(&tm, m);
+    emu_launch_checked(selftest_ok_kernel, dim3(2, 1, 1), 64, 512, tm);
+    return dead + 2 * (g_deadlocks.load() == 0);
+}
+
+// n_pairs double sweeps of one frame on one "device".  face kinds: RNMF_BC_*; coef4 from the oracle.
+// Returns 0, or the number of launches that hit a barrier timeout (deadlock).
+int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
+                      const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_pairs)
+{
+    g_deadlocks = 0;
+    Frame f;
+    init_frame(f, dim, n, dx, psi_dense, rhs_dense);
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = f.g;
+    a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+    a.faces = make_faces(dim, face_kind, face_value, dx);
+    a.fuse_fill = 1;
+    a.variant = variant;
+    a.chunk_override = chunk;
+    a.rhs = f.rhs.data();
+    a.k_begin = 0;
+    a.k_end = f.g.n[dim - 1];
+    for (int it = 0; it < n_pairs; ++it) {
+        a.in = f.buf[f.cur].data();
+        a.out = f.buf[f.cur ^ 1].data();
+        if (dim == 3) {
+            Tb2Args t;
+            memset(&t, 0, sizeof(t));
+            t.a = a;
+            if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
+        } else {
+            if (launch_jacobi_double_sweep_2d(a, nullptr) < 0) return -1;
+        }
+        f.cur ^= 1;
+    }
+    pack(f.g, f.buf[f.cur].data(), out_dense);
+    return g_deadlocks.load();
+}
+
+// The same over z-slabs: `nranks` host threads, each launching its slab's double sweeps; u1 boundary planes and
+// u2 boundary planes travel through the neighbours' buffers, ordered by the half / full step flags -- the
+// argument wiring mirrors rnmf_jacobi_sweeps (capi.cu).  Global dense frames in / out (3D, ng = 1).
+int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
+                            const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_pairs, int nranks)
+{
+    g_deadlocks = 0;
+    const long long G0 = n[0] + 2, G1 = n[1] + 2, plane_dense = G0 * G1;
+    std::vector<Frame> fr(nranks);
+    std::vector<long long> start(nranks), count(nranks);
+    struct Flags { unsigned long long w[16]; };
+    std::vector<Flags> flags(nranks);
+    for (auto& fl : flags) memset(&fl, 0, sizeof(fl));
+    for (int r = 0; r < nranks; ++r) {
+        const long long base = n[2] / nranks;                     // Domain::new_rectangular: remainder to the last block
+        start[r] = base * r;
+        count[r] = r == nranks - 1 ? n[2] - start[r] : base;
+        const long long nl[3] = { n[0], n[1], count[r] };
+        // the slab's dense frame = global planes start-1 .. start+count (ghost planes hold the neighbours' planes:
+        // what the entry halo exchange of rnmf_jacobi_sweeps delivers)
+        init_frame(fr[r], 3, nl, dx, psi_dense + plane_dense * start[r], rhs_dense + plane_dense * start[r]);
+    }
+    std::vector<std::thread> ranks;
+    for (int r = 0; r < nranks; ++r)
+        ranks.emplace_back([&, r] {
+            Frame& f = fr[r];
+            const bool has_lo = r > 0, has_hi = r < nranks - 1;
+            const long long m = count[r];
+            int kind[6];
+            for (int i = 0; i < 6; ++i) kind[i] = face_kind[i];
+            if (has_lo) kind[4] = RNMF_BC_HALO;
+            if (has_hi) kind[5] = RNMF_BC_HALO;
+            unsigned long long epoch = 0, done_a[2] = { 0, 0 }, done_b[2] = { 0, 0 };
+            for (int it = 0; it < n_pairs; ++it) {
+                Tb2Args t;
+                memset(&t, 0, sizeof(t));
+                SweepArgs& a = t.a;
+                a.g = f.g;
+                a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+                a.faces = make_faces(3, kind, face_value, dx);
+                a.fuse_fill = 1;
+                a.variant = variant;
+                a.chunk_override = chunk;
+                a.rhs = f.rhs.data();
+                a.in = f.buf[f.cur].data();
+                a.out = f.buf[f.cur ^ 1].data();
+                a.k_begin = has_lo ? 1 : 0;
+                a.k_end = has_hi ? m - 1 : m;
+                t.b_lo = has_lo; t.b_hi = has_hi;
+                const int out_phys = f.cur ^ 1;
+                if (has_lo) {
+                    Frame& lo = fr[r - 1];
+                    a.peer_lo_plane = lo.buf[out_phys].data() + lo.g.plane * (count[r - 1] + 1);      // its hi ghost plane
+                    t.peer_u1_lo = lo.buf[0].data() + lo.scratch_off() + lo.g.plane;                   // its "from hi" scratch plane
+                    t.u1_in_lo = f.buf[0].data() + f.scratch_off();
+                    t.half_wait_lo = &flags[r].w[8];
+                    t.half_sig_lo = &flags[r - 1].w[9];
+                    a.ps.wait_lo = &flags[r].w[0];
+                    a.ps.sig_lo = &flags[r - 1].w[1];
+                }
+                if (has_hi) {
+                    Frame& hi = fr[r + 1];
+                    a.peer_hi_plane = hi.buf[out_phys].data();                                         // its lo ghost plane
+                    t.peer_u1_hi = hi.buf[0].data() + hi.scratch_off();                                // its "from lo" scratch plane
+                    t.u1_in_hi = f.buf[0].data() + f.scratch_off() + f.g.plane;
+                    t.half_wait_hi = &flags[r].w[9];
+                    t.half_sig_hi = &flags[r + 1].w[8];
+                    a.ps.wait_hi = &flags[r].w[1];
+                    a.ps.sig_hi = &flags[r + 1].w[0];
+                }
+                const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(t);
+                a.ps.enabled = 1;
+                a.ps.done = &flags[r].w[3];
+                if (has_lo) { done_a[0] += tiles; done_b[0] += tiles; }
+                if (has_hi) { done_a[1] += tiles; done_b[1] += tiles; }
+                a.ps.target_lo = done_a[0]; a.ps.target_hi = done_a[1];
+                a.ps.epoch = epoch;
+                a.ps.status = &flags[r].w[2];
+                t.done_b = &flags[r].w[10];
+                t.target_b_lo = done_b[0]; t.target_b_hi = done_b[1];
+                epoch += 2;
+                launch_jacobi_double_sweep(t, nullptr);
+                f.cur ^= 1;
+            }
+            // the closing wait of rnmf_jacobi_sweeps: the neighbours' last stores into my ghost planes have landed
+            if (has_lo) peer_spin_wait(&flags[r].w[0], epoch, &flags[r].w[2]);
+            if (has_hi) peer_spin_wait(&flags[r].w[1], epoch, &flags[r].w[2]);
+        });
+    for (auto& th : ranks) th.join();
+    int bad = g_deadlocks.load();
+    for (int r = 0; r < nranks; ++r) {
+        if (flags[r].w[2]) ++bad;                                   // a handshake wait timed out
+        // valid planes of the slab -> the global dense frame; ghost planes of the outer ranks too
+        std::vector<double> dense((size_t)(plane_dense * (count[r] + 2)));
+        pack(fr[r].g, fr[r].buf[fr[r].cur].data(), dense.data());
+        const long long p0 = r == 0 ? 0 : 1, p1 = r == nranks - 1 ? count[r] + 2 : count[r] + 1;
+        memcpy(out_dense + plane_dense * (start[r] + p0), dense.data() + plane_dense * p0, (size_t)(plane_dense * (p1 - p0)) * sizeof(double));
+    }
+    return bad;
+}
+
+}  // extern "C"

@@ -82,3 +82,18 @@ def test_product_code_never_touches_the_oracle():
                     if re.search(r"\boracle\b|liboracle|ora_[a-z]", txt):
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
+
+
+def test_the_kernel_emulator_is_never_part_of_the_product(capi):
+    # tests/emu/ (a thread-per-lane SIMT emulator for the kernel sources) is test infrastructure: the product build never
+    # defines RNMF_EMULATE, the emulator header lives outside the package, and the library exports / contains none of it
+    import subprocess
+    mk = open(os.path.join(ROOT, "rnmf_b200", "csrc", "Makefile")).read() + open(os.path.join(ROOT, "host", "Makefile")).read()
+    assert "RNMF_EMULATE" not in mk and "tests/emu" not in mk
+    assert not os.path.exists(os.path.join(ROOT, "rnmf_b200", "csrc", "emu"))
+    so = os.path.join(ROOT, "rnmf_b200", "librnmf_b200.so")
+    syms = subprocess.run(["nm", "-C", so], capture_output=True, text=True).stdout
+    assert "emu::" not in syms and "emu_launch" not in syms
+    for fn in os.listdir(os.path.join(ROOT, "rnmf_b200")):
+        if fn.endswith(".py"):
+            assert "emu_driver" not in open(os.path.join(ROOT, "rnmf_b200", fn)).read()

@@ -1,0 +1,111 @@
+"""The double-sweep kernel SOURCES (rnmf_b200/csrc/kernels_sweep_tb2.cu, kernels_sweep2d_tb2.cu) run on the CPU box:
+compiled with g++ -DRNMF_EMULATE against a thread-per-lane SIMT emulator (tests/emu/emu_cuda.hpp: barriers,
+mbarrier phases, TMA box copies with zero fill, shared memory by byte offset, the slab handshake as atomics) and
+driven through the library's own launchers (planner, tensor maps, A/B chunk roles).  Checks, bit for bit against
+the oracle, what a GPU box is too expensive to iterate on: tile / halo / ghost indexing, the ring and barrier
+protocols (a wrong parity or a missing arrival deadlocks and is reported), the half-step / full-step exchange
+between slabs with every "rank" a host thread.  Test infrastructure: nothing here is part of librnmf_b200.so, and
+the GPU tests remain the parity tests proper."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as ora
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "emu_driver.cpp")
+OUT = os.path.join(ROOT, "tests", "emu", "_build", "libemu_driver.so")
+KIND = {"dirichlet": 0, "neumann": 1}
+
+MIXED_3D = ([("dirichlet", 0.0), ("neumann", 0.0), ("dirichlet", 0.25)], [("dirichlet", 1.0), ("neumann", -0.5), ("neumann", 0.5)])
+NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
+MIXED_2D = ([("neumann", 0.3), ("dirichlet", -1.0)], [("dirichlet", 2.0), ("neumann", -0.7)])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(ROOT, "rnmf_b200", "csrc", f) for f in
+                    ("kernels_sweep_tb2.cu", "kernels_sweep2d_tb2.cu", "tma_util.cuh", "common.cuh")] + [os.path.join(ROOT, "tests", "emu", "emu_cuda.hpp")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
+                        "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "emu"), "-Wno-psabi",
+                        "-Wl,-Bsymbolic",          # the driver defines the library's own launcher names: bind them inside the driver
+                        "-o", OUT, SRC], check=True)
+    lib = C.CDLL(OUT)
+    lib.emu_set_timeout(20)
+    return lib
+
+
+def test_the_emulator_reports_deadlocks_and_models_tma_zero_fill(emu):
+    assert emu.emu_selftest() == 3
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _setup(n, hi, spec, sweeps, seed):
+    dim = len(n)
+    g = ora.geom(n, hi=hi)
+    obc = ora.bcs(dim, [spec])
+    rng = np.random.default_rng(seed)
+    psi, rhs = rng.standard_normal(g.n_nodes), rng.standard_normal(g.n_nodes)
+    ora.fill_bc(g, psi, obc)
+    want = psi.copy()
+    ora.jacobi(g, want, rhs, obc, sweeps)
+    kinds, vals = (C.c_int * 6)(*([0] * 6)), (C.c_double * 6)(*([0.0] * 6))
+    for d in range(dim):
+        for side in range(2):
+            kinds[d * 2 + side], vals[d * 2 + side] = KIND[spec[side][d][0]], spec[side][d][1]
+    dx = (C.c_double * 3)(*[hi[d] / n[d] for d in range(dim)], *([1.0] * (3 - dim)))
+    nn = (C.c_longlong * 3)(*n, *([1] * (3 - dim)))
+    return g, psi, rhs, want, kinds, vals, dx, nn, ora.coefs(g)
+
+
+@pytest.mark.parametrize("n,hi,spec,pairs,variant,chunk", [
+    ([20, 9, 5], [1.0, 2.0, 3.0], MIXED_3D, 1, 20, 0),
+    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 20, 0),        # one cell / one row past a tile edge; two launches (ping-pong)
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 20, 2),       # odd n0 (x-hi ghost in a register), 3 y tiles, 4 z chunks
+    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 20, 0),          # a single plane: both z ghosts of u1 formed in registers
+    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 20, 0),
+    ([40, 10, 6], [1.0, 2.0, 3.0], MIXED_3D, 1, 21, 3),          # 128x8 tile variant
+])
+def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, variant, chunk):
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, pairs)
+    assert rc == 0, "a barrier wait timed out (deadlock) or the launch failed"
+    np.testing.assert_array_equal(out, want)      # valid cells, face ghosts, and the untouched edges / corners
+
+
+@pytest.mark.parametrize("n,hi,spec,pairs,chunk", [
+    ([33, 7], [1.0, 2.0], MIXED_2D, 1, 0),
+    ([513, 5], [513.0, 5.0], MIXED_2D, 2, 2),                    # one cell past a 512-column strip; 3 row chunks
+    ([40, 1], [1.0, 1.0], MIXED_2D, 1, 0),                       # a single row
+    ([2, 3], [2.0, 3.0], MIXED_2D, 3, 1),
+])
+def test_2d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=42)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 30, chunk, pairs)
+    assert rc == 0
+    np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("n,hi,spec,pairs,nranks,chunk", [
+    ([20, 9, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0),           # two slabs: each rank has one neighbour
+    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0),         # uneven split (5, 5, 7); the middle rank has both
+    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1),        # 4-plane slabs (the minimum), one-plane A chunks
+])
+def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk):
+    """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial
+    schedule); u1 / u2 boundary planes go through the neighbours' buffers under the half / full step flags."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=43)
+    out = psi.copy()
+    rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 20, chunk, pairs, nranks)
+    assert rc == 0, "deadlock / handshake timeout"
+    np.testing.assert_array_equal(out, want)
