@@ -34,7 +34,7 @@ extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
            "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "jacobi3d_tb2{128x12,128x8},jacobi2d_tb2{512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi3d_tb2{128x12,128x8},jacobi3d_tb2x{128x12m,128x16},jacobi2d_tb2{512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -916,7 +916,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     bool all_faces = true;
     for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
     // default (variant 0 = auto) for 3D; variant 6 = the single-sweep TMA kernel only
-    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21);
+    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21 || c->sweep_variant == 24 || c->sweep_variant == 25);
     const bool tb2_single = tb2_variant && !dist && fused && all_faces;
     // slabs: the fused peer path with the in-kernel handshake; z faces are physical or a neighbour
     const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;

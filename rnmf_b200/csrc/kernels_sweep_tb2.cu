@@ -459,6 +459,425 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
     }
 }
 
+// ===============================================================================================
+// Two rows per row warp (variants 24 / 25; not the default).  The shared-memory pipe bounds the kernel above
+// (88 wavefronts per row warp and plane: DESIGN.md section 9); when one warp owns two ADJACENT rows the
+// N/S neighbour of one row is the other row's register, so N/S costs 8 instead of 16 wavefronts per row and
+// level, and half as many warps wait on the barriers.  Same ring protocol, same arithmetic (bit-identical).
+//   MERGE = true : TY/2 two-row warps + ONE helper warp (both halo rows, then the two halo columns) + producer
+//                  (128x12 tile: 8 warps, up to 255 registers per thread)
+//   MERGE = false: TY/2 two-row warps + halo-row warp + halo-column warp + producer (128x16 tile: 11 warps)
+// ===============================================================================================
+struct C4 { double2 a, b; };                  // the four cells of a lane in one row
+struct EW4 { double w_a0, e_a1, w_b0, e_b1; };
+
+__device__ __forceinline__ C4 ld4(uint32_t a) { C4 v; v.a = lds2(a); v.b = lds2(a + 512); return v; }
+__device__ __forceinline__ EW4 ldew(uint32_t pc)
+{
+    EW4 e;
+    e.w_a0 = lds1(pc - 8); e.e_a1 = lds1(pc + 16);
+    e.w_b0 = lds1(pc + 512 - 8); e.e_b1 = lds1(pc + 512 + 16);
+    return e;
+}
+__device__ __forceinline__ C4 upd3_4(const SweepCoef& c, const C4& r, const C4& cur, const EW4& e, const C4& n, const C4& s, const C4& u, const C4& d)
+{
+    C4 o;
+    o.a.x = upd3(c.c0, c.c1, c.c2, c.c3, r.a.x, cur.a.y, e.w_a0, n.a.x, s.a.x, u.a.x, d.a.x);
+    o.a.y = upd3(c.c0, c.c1, c.c2, c.c3, r.a.y, e.e_a1, cur.a.x, n.a.y, s.a.y, u.a.y, d.a.y);
+    o.b.x = upd3(c.c0, c.c1, c.c2, c.c3, r.b.x, cur.b.y, e.w_b0, n.b.x, s.b.x, u.b.x, d.b.x);
+    o.b.y = upd3(c.c0, c.c1, c.c2, c.c3, r.b.y, e.e_b1, cur.b.x, n.b.y, s.b.y, u.b.y, d.b.y);
+    return o;
+}
+__device__ __forceinline__ C4 part2_4(const SweepCoef& c, const C4& r, const C4& cur, const EW4& e, const C4& n, const C4& s)
+{
+    C4 o;
+    o.a.x = part2(c.c0, c.c1, c.c2, r.a.x, cur.a.y, e.w_a0, n.a.x, s.a.x);
+    o.a.y = part2(c.c0, c.c1, c.c2, r.a.y, e.e_a1, cur.a.x, n.a.y, s.a.y);
+    o.b.x = part2(c.c0, c.c1, c.c2, r.b.x, cur.b.y, e.w_b0, n.b.x, s.b.x);
+    o.b.y = part2(c.c0, c.c1, c.c2, r.b.y, e.e_b1, cur.b.x, n.b.y, s.b.y);
+    return o;
+}
+__device__ __forceinline__ C4 fin2_4(const C4& part, double c3, const C4& u, const C4& d)
+{
+    C4 o;
+    o.a.x = fin2(part.a.x, c3, u.a.x, d.a.x); o.a.y = fin2(part.a.y, c3, u.a.y, d.a.y);
+    o.b.x = fin2(part.b.x, c3, u.b.x, d.b.x); o.b.y = fin2(part.b.y, c3, u.b.y, d.b.y);
+    return o;
+}
+__device__ __forceinline__ C4 ghost4(const Face1& f, const C4& m) { C4 o; o.a = ghost1(f, m.a); o.b = ghost1(f, m.b); return o; }
+
+template <int TY, int NS, bool MERGE>
+struct Tb2xCfg : Tb2Cfg<TY, NS> {
+    static_assert(TY % 2 == 0, "two rows per warp");
+    static constexpr int NFULL = TY / 2;
+    static constexpr int NCONS = NFULL + (MERGE ? 1 : 2);
+    static constexpr int THREADS = 32 * (NCONS + 1);
+};
+
+struct RowK2 {
+    uint32_t pa, ra, ua;                 // the lane's first cell of the warp's FIRST row (second row: + BX*8)
+    uint32_t full0, empty0, u1full0;
+    SweepCoef c;
+    bool xv0, xv1, xv2, xv3;             // x validity of the lane's four cells
+    bool ok[2];                          // the warp's rows are rows of the frame
+    bool do_xlo, any_x, do_ylo;
+    int xhi_sel;
+    uint32_t xhi_off;
+    int yhi_row;                         // which of the two rows is the frame's last row (-1: none)
+    Face1 fx0, fx1, fy0, fy1, fz0, fz1;
+    long long pitch, plane_sz, xy_off;
+    int lane;
+    int it_zlo, it_u1lo, it_u1hi;
+};
+struct RowSt2 {
+    C4 below[2], cur[2];                 // u0 planes a+it-1, a+it
+    C4 u1lo[2], u1c[2];                  // u1 planes q-1, q
+    C4 rp[2];                            // rhs plane q
+    double* oa;
+    uint32_t sc, sn, phn;
+};
+
+__device__ __forceinline__ void st4g(double* a, const C4& v, const RowK2& k, int r)
+{
+    store4(a, v.a, v.b, k.ok[r] && k.xv3, k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
+}
+__device__ __forceinline__ void st4s(uint32_t a, const C4& v, const RowK2& k, int r)
+{
+    sstore4(a, v.a, v.b, k.ok[r] && k.xv3, k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
+}
+__device__ __forceinline__ double xhi_pick(const C4& v, int sel) { return sel == 0 ? v.a.x : sel == 1 ? v.a.y : sel == 2 ? v.b.x : v.b.y; }
+__device__ __forceinline__ void ld4g(const double* q, C4& v, const RowK2& k, int r)
+{
+    if (k.ok[r] && k.xv3) { v.a = *reinterpret_cast<const double2*>(q); v.b = *reinterpret_cast<const double2*>(q + 64); }
+    else if (k.ok[r]) {
+        if (k.xv0) v.a.x = q[0];
+        if (k.xv1) v.a.y = q[1];
+        if (k.xv2) v.b.x = q[64];
+        if (k.xv3) v.b.y = q[65];
+    }
+}
+
+// One plane iteration of a two-row warp (rows r0 = 2w and r0+1 of the tile): see row_iter for the protocol.
+template <int TY, int NS, bool DO_L1, bool DO_L2>
+__device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, RowSt2& st, const int it)
+{
+    using Cfg = Tb2Cfg<TY, NS>;
+    constexpr uint32_t RB = Cfg::BX * 8;                                  // bytes per staged row
+    const double2 zero2 = make_double2(0.0, 0.0);
+    const C4 zero4 = { zero2, zero2 };
+    C4 above[2] = { zero4, zero4 }, u1n[2] = { zero4, zero4 }, rc[2] = { zero4, zero4 }, P[2] = { zero4, zero4 };
+
+    if (DO_L1) mbar_wait(k.full0 + 8 * st.sn, st.phn);
+    if (DO_L2 || it >= 2) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+
+    if (DO_L2) {
+        const uint32_t up = k.ua + (uint32_t)((it - 1) & 1) * Cfg::U1_SLOT;
+        // row 0: S from the ring (row below), N = the warp's second row; row 1: N from the ring, S = the first row
+        const C4 s0 = ld4(up - RB), n1 = ld4(up + 2 * RB);
+        const EW4 e0 = ldew(up), e1 = ldew(up + RB);
+        P[0] = part2_4(k.c, st.rp[0], st.u1c[0], e0, st.u1c[1], s0);
+        P[1] = part2_4(k.c, st.rp[1], st.u1c[1], e1, n1, st.u1c[0]);
+    }
+    if (DO_L1) {
+        const uint32_t pn = k.pa + st.sn * Cfg::U0_STAGE, pc = k.pa + st.sc * Cfg::U0_STAGE, pr = k.ra + st.sc * Cfg::RHS_STAGE;
+        above[0] = ld4(pn); above[1] = ld4(pn + RB);
+        rc[0] = ld4(pr); rc[1] = ld4(pr + RB);
+        const C4 s0 = ld4(pc - RB), n1 = ld4(pc + 2 * RB);
+        const EW4 e0 = ldew(pc), e1 = ldew(pc + RB);
+        // ---------------- level 1: u1 of plane a+it, both rows ----------------
+        u1n[0] = upd3_4(k.c, rc[0], st.cur[0], e0, st.cur[1], s0, above[0], st.below[0]);
+        u1n[1] = upd3_4(k.c, rc[1], st.cur[1], e1, n1, st.cur[0], above[1], st.below[1]);
+        // ghosts of u1 that level 2 takes from REGISTERS: odd n0 (E neighbour of the last valid cell is the pair's
+        // second register) and the y-hi ghost row when the frame's last row is the warp's first row
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (k.xhi_sel == 0) u1n[r].a.y = ghost1(k.fx1, u1n[r].a.x);
+            if (k.xhi_sel == 2) u1n[r].b.y = ghost1(k.fx1, u1n[r].b.x);
+        }
+        if (k.yhi_row == 0) u1n[1] = ghost4(k.fy1, u1n[0]);
+
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
+        const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
+        st4s(us, u1n[0], k, 0);
+        st4s(us + RB, u1n[1], k, 1);
+        if (k.any_x) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (k.ok[r]) {
+                    if (k.do_xlo) sts1(us + r * RB - 8, ghost1(k.fx0, u1n[r].a.x));
+                    if (k.xhi_sel >= 0) sts1(us + r * RB + k.xhi_off, ghost1(k.fx1, xhi_pick(u1n[r], k.xhi_sel)));
+                }
+        }
+        if (k.do_ylo) st4s(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
+        if (k.yhi_row == 1) st4s(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+        if (it == k.it_u1lo) { st4g(p.peer_u1_lo + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_lo + k.xy_off + k.pitch, u1n[1], k, 1); }
+        if (it == k.it_u1hi) { st4g(p.peer_u1_hi + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_hi + k.xy_off + k.pitch, u1n[1], k, 1); }
+    }
+    if (DO_L2) {
+        // ---------------- level 2: u2 of plane q = a+it-1, both rows ----------------
+        C4 dn[2] = { st.u1lo[0], st.u1lo[1] }, upv[2] = { u1n[0], u1n[1] };
+        const bool zlo = it == k.it_zlo;
+        if (zlo) {
+            if (k.fz0.on) { dn[0] = ghost4(k.fz0, st.u1c[0]); dn[1] = ghost4(k.fz0, st.u1c[1]); }
+            else if (p.u1_in_lo) { ld4g(p.u1_in_lo + k.xy_off, dn[0], k, 0); ld4g(p.u1_in_lo + k.xy_off + k.pitch, dn[1], k, 1); }
+        }
+        if (!DO_L1) {
+            if (k.fz1.on) { upv[0] = ghost4(k.fz1, st.u1c[0]); upv[1] = ghost4(k.fz1, st.u1c[1]); }
+            else if (p.u1_in_hi) { ld4g(p.u1_in_hi + k.xy_off, upv[0], k, 0); ld4g(p.u1_in_hi + k.xy_off + k.pitch, upv[1], k, 1); }
+        }
+        double* oa = st.oa;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const C4 u2 = fin2_4(P[r], k.c.c3, upv[r], dn[r]);
+            double* o = oa + r * k.pitch;
+            st4g(o, u2, k, r);
+            if (k.any_x && k.ok[r]) {
+                if (k.do_xlo) o[-1] = ghost1(k.fx0, u2.a.x);
+                if (k.xhi_sel >= 0) o[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, xhi_pick(u2, k.xhi_sel));
+            }
+            if (r == 0 && k.do_ylo) st4g(o - k.pitch, ghost4(k.fy0, u2), k, 0);
+            if (k.yhi_row == r) st4g(o + k.pitch, ghost4(k.fy1, u2), k, r);
+            if (zlo) {
+                if (k.fz0.on) st4g(o - k.plane_sz, ghost4(k.fz0, u2), k, r);
+                if (p.peer_lo_plane) st4g(p.peer_lo_plane + k.xy_off + r * k.pitch, u2, k, r);
+            }
+            if (!DO_L1) {
+                if (k.fz1.on) st4g(o + k.plane_sz, ghost4(k.fz1, u2), k, r);
+                if (p.peer_hi_plane) st4g(p.peer_hi_plane + k.xy_off + r * k.pitch, u2, k, r);
+            }
+        }
+        st.oa = oa + k.plane_sz;
+    }
+    if (DO_L1) {
+        st.below[0] = st.cur[0]; st.below[1] = st.cur[1];
+        st.cur[0] = above[0]; st.cur[1] = above[1];
+        st.sc = st.sn;
+        if (++st.sn == NS) { st.sn = 0; st.phn ^= 1u; }
+    }
+    st.u1lo[0] = st.u1c[0]; st.u1lo[1] = st.u1c[1];
+    st.u1c[0] = u1n[0]; st.u1c[1] = u1n[1];
+    st.rp[0] = rc[0]; st.rp[1] = rc[1];
+}
+
+template <int TY, int NS, bool MERGE>
+__global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_tb2x_kernel(const __grid_constant__ CUtensorMap tm_u0,
+                                                                                           const __grid_constant__ CUtensorMap tm_rhs,
+                                                                                           const __grid_constant__ Tb2Params p)
+{
+    using Cfg = Tb2xCfg<TY, NS, MERGE>;
+    constexpr int TX = Cfg::TX, BX = Cfg::BX, NFULL = Cfg::NFULL;
+    constexpr uint32_t RB = BX * 8;
+    static_assert(TY <= 16, "the halo-column lanes map 16 rows per side");
+    RNMF_DYNAMIC_SMEM(smem_raw);
+    const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, u1_0 = sb + Cfg::U1_OFF;
+    const uint32_t full0 = sb + Cfg::BAR_OFF, empty0 = full0 + NS * 8, u1full0 = empty0 + NS * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n0 = p.g.n[0], n1 = p.g.n[1], n2 = p.g.n[2];
+    const long long i0 = (long long)blockIdx.x * TX;
+    const long long j0 = (long long)blockIdx.y * TY;
+
+    // chunk roles exactly as in jacobi3d_tb2_kernel
+    const int bz = (int)blockIdx.z;
+    const bool is_b = bz >= p.n_a;
+    long long k0, k1;
+    if (!is_b) {
+        const unsigned zc = p.ps.enabled ? peer_chunk_order((unsigned)bz, (unsigned)p.n_a) : (unsigned)bz;
+        k0 = p.m_begin + (long long)zc * p.chunk;
+        k1 = k0 + p.chunk < p.m_end ? k0 + p.chunk : p.m_end;
+    } else {
+        k0 = (p.b_lo && bz == p.n_a) ? 0 : n2 - 1;
+        k1 = k0 + 1;
+    }
+    const long long a = k0 > 0 ? k0 - 1 : 0;
+    const long long b = k1 < n2 ? k1 : n2 - 1;
+    const int nL1 = (int)(b - a) + 1;
+    const int n_planes = nL1 + 2;
+    const bool top = b < k1;
+    const int it_l2_first = (int)(k0 - a) + 1;
+    const bool a_sync_lo = !is_b && p.peer_u1_lo && k0 == p.m_begin;
+    const bool a_sync_hi = !is_b && p.peer_u1_hi && k1 == p.m_end;
+    const bool b_is_lo = is_b && k0 == 0 && p.b_lo;
+    const bool b_is_hi = is_b && !b_is_lo;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, Cfg::NCONS);
+        }
+        mbar_init(u1full0, Cfg::NCONS);
+        mbar_init(u1full0 + 8, Cfg::NCONS);
+        mbar_fence_init();
+        if (a_sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
+        if (a_sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
+        if (b_is_lo) peer_spin_wait(p.half_wait_lo, p.ps.epoch + 1, p.ps.status);
+        if (b_is_hi) peer_spin_wait(p.half_wait_hi, p.ps.epoch + 1, p.ps.status);
+    }
+    __syncthreads();
+
+    const int w_rows = NFULL, w_cols = MERGE ? NFULL : NFULL + 1, w_prod = Cfg::NCONS;
+    const bool do_rows = warp == w_rows, do_cols = warp == w_cols;
+
+    if (warp == w_prod) {
+        // ------------------------------ producer warp ------------------------------
+        if (lane == 0) {
+            const int cx = (int)(p.g.xoff + p.g.ng + i0 - 2);
+            const int cy_u0 = (int)(p.g.ng + j0 - 2);
+            const int cy_rhs = cy_u0 + 1;
+            int cz = (int)(p.g.kg + a - 1);
+            uint32_t s = 0, wrap = 0;
+            for (int idx = 0; idx < n_planes; ++idx) {
+                if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
+                const bool with_rhs = idx >= 1 && idx <= nL1;
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::U0_BYTES + (with_rhs ? Cfg::RHS_BYTES : 0)));
+                tma_load_3d(u0_0 + s * Cfg::U0_STAGE, &tm_u0, cx, cy_u0, cz, full0 + 8 * s);
+                if (with_rhs) tma_load_3d(rhs_0 + s * Cfg::RHS_STAGE, &tm_rhs, cx, cy_rhs, cz, full0 + 8 * s);
+                ++cz;
+                if (++s == NS) { s = 0; ++wrap; }
+            }
+        }
+    } else if (do_rows || do_cols) {
+        // ------------------------------ helper warp(s): halo rows j0-1 and j0+TY, halo columns i0-1 and i0+128 (level 1 only) ---
+        const SweepCoef c = p.c;
+        // rows: h = 0 -> tile row -1, h = 1 -> tile row TY; same lane <-> cell mapping as the row warps
+        const long long ia = i0 + 2 * lane, ib = ia + 64;
+        const bool xv0 = ia < n0, xv1 = ia + 1 < n0, xv2 = ib < n0, xv3 = ib + 1 < n0;
+        const bool rok[2] = { do_rows && j0 - 1 >= 0, do_rows && j0 + TY < n1 };
+        const int rrow[2] = { -1, TY };
+        uint32_t hpa[2], hra[2], hua[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            hpa[h] = u0_0 + (uint32_t)(((rrow[h] + 2) * BX + 2 + 2 * lane) * 8);
+            hra[h] = rhs_0 + (uint32_t)(((rrow[h] + 1) * BX + 2 + 2 * lane) * 8);
+            hua[h] = u1_0 + (uint32_t)(((rrow[h] + 1) * BX + 2 + 2 * lane) * 8);
+        }
+        // columns: lanes 0..15: column i0-1, rows j0+lane; lanes 16..31: column i0+128, rows j0+lane-16
+        const int side = lane >> 4, rcl = (lane & 15) < TY ? (lane & 15) : 0;
+        const int col = side ? TX : -1;
+        const bool cok = do_cols && (lane & 15) < TY && i0 + col >= 0 && i0 + col < n0 && j0 + rcl < n1;
+        const uint32_t cp = u0_0 + (uint32_t)(((rcl + 2) * BX + col + 2) * 8);
+        const uint32_t cr = rhs_0 + (uint32_t)(((rcl + 1) * BX + col + 2) * 8);
+        const uint32_t cu = u1_0 + (uint32_t)(((rcl + 1) * BX + col + 2) * 8);
+
+        mbar_wait(full0, 0);
+        C4 below[2] = { ld4(hpa[0]), ld4(hpa[1]) };
+        double cbelow = lds1(cp);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        C4 cur[2] = { ld4(hpa[0] + Cfg::U0_STAGE), ld4(hpa[1] + Cfg::U0_STAGE) };
+        double ccur = lds1(cp + Cfg::U0_STAGE);
+        uint32_t sc = 1, sn = 2, phn = 0;
+        for (int it = 0; it < nL1; ++it) {
+            mbar_wait(full0 + 8 * sn, phn);
+            if (it >= 2) mbar_wait(u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+            C4 above[2], v[2];
+            double cabove = 0.0, cv = 0.0;
+            if (do_rows) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t pc = hpa[h] + sc * Cfg::U0_STAGE;
+                    above[h] = ld4(hpa[h] + sn * Cfg::U0_STAGE);
+                    const C4 nn = ld4(pc + RB), ss = ld4(pc - RB), rr = ld4(hra[h] + sc * Cfg::RHS_STAGE);
+                    const EW4 e = ldew(pc);
+                    v[h] = upd3_4(c, rr, cur[h], e, nn, ss, above[h], below[h]);
+                }
+            }
+            if (do_cols) {
+                const uint32_t pc = cp + sc * Cfg::U0_STAGE;
+                cabove = lds1(cp + sn * Cfg::U0_STAGE);
+                const double nn = lds1(pc + RB), ss = lds1(pc - RB), ee = lds1(pc + 8), ww = lds1(pc - 8);
+                const double rr = lds1(cr + sc * Cfg::RHS_STAGE);
+                cv = upd3(c.c0, c.c1, c.c2, c.c3, rr, ee, ww, nn, ss, cabove, cbelow);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * sc);
+            const uint32_t slot = (uint32_t)(it & 1) * Cfg::U1_SLOT;
+            if (do_rows) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    sstore4(hua[h] + slot, v[h].a, v[h].b, rok[h] && xv3, rok[h] && xv0, rok[h] && xv1, rok[h] && xv2, rok[h] && xv3);
+            }
+            if (cok) sts1(cu + slot, cv);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(u1full0 + 8 * (it & 1));
+            if (do_rows) { below[0] = cur[0]; below[1] = cur[1]; cur[0] = above[0]; cur[1] = above[1]; }
+            cbelow = ccur; ccur = cabove;
+            sc = sn;
+            if (++sn == NS) { sn = 0; phn ^= 1u; }
+        }
+    } else {
+        // ------------------------------ two-row warps ------------------------------
+        const int r0 = 2 * warp;
+        const long long jr = j0 + r0;
+        const long long ia = i0 + 2 * lane, ib = ia + 64;
+        RowK2 k;
+        k.ok[0] = jr < n1; k.ok[1] = jr + 1 < n1;
+        k.xv0 = ia < n0; k.xv1 = ia + 1 < n0; k.xv2 = ib < n0; k.xv3 = ib + 1 < n0;
+        k.pa = u0_0 + (uint32_t)(((r0 + 2) * BX + 2 + 2 * lane) * 8);
+        k.ra = rhs_0 + (uint32_t)(((r0 + 1) * BX + 2 + 2 * lane) * 8);
+        k.ua = u1_0 + (uint32_t)(((r0 + 1) * BX + 2 + 2 * lane) * 8);
+        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0;
+        k.c = p.c;
+        k.pitch = p.g.pitch; k.plane_sz = p.g.plane;
+        k.xy_off = p.g.xoff + (ia + p.g.ng) + k.pitch * (jr + p.g.ng);
+        k.lane = lane;
+        k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
+        k.fy0 = make_face1(p.faces.f[2], true); k.fy1 = make_face1(p.faces.f[3], true);
+        k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
+        k.do_xlo = k.fx0.on && k.xv0 && ia == 0;
+        const long long last = n0 - 1;
+        k.xhi_sel = !k.fx1.on ? -1 : (k.xv0 && ia == last) ? 0 : (k.xv1 && ia + 1 == last) ? 1 : (k.xv2 && ib == last) ? 2 : (k.xv3 && ib + 1 == last) ? 3 : -1;
+        k.xhi_off = (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        k.any_x = k.do_xlo || k.xhi_sel >= 0;
+        k.do_ylo = k.fy0.on && jr == 0;
+        k.yhi_row = !k.fy1.on ? -1 : (jr == n1 - 1 ? 0 : (jr + 1 == n1 - 1 ? 1 : -1));
+        k.it_zlo = k0 == 0 ? 1 : -1;
+        k.it_u1lo = a_sync_lo ? 0 : -1;
+        k.it_u1hi = a_sync_hi ? nL1 - 1 : -1;
+
+        RowSt2 st;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        const C4 zero4 = { zero2, zero2 };
+        mbar_wait(full0, 0);
+        st.below[0] = ld4(k.pa); st.below[1] = ld4(k.pa + RB);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        st.cur[0] = ld4(k.pa + Cfg::U0_STAGE); st.cur[1] = ld4(k.pa + Cfg::U0_STAGE + RB);
+        st.u1lo[0] = zero4; st.u1lo[1] = zero4; st.u1c[0] = zero4; st.u1c[1] = zero4; st.rp[0] = zero4; st.rp[1] = zero4;
+        st.oa = p.out + p.g.at(ia, jr, k0, 0);
+        st.sc = 1; st.sn = 2; st.phn = 0;
+
+        int it = 0;
+        for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false>(p, k, st, it);
+        for (; it < nL1; it += 3) {
+            row2_iter<TY, NS, true, true>(p, k, st, it);
+            if (it + 1 >= nL1) break;
+            row2_iter<TY, NS, true, true>(p, k, st, it + 1);
+            if (it + 2 >= nL1) break;
+            row2_iter<TY, NS, true, true>(p, k, st, it + 2);
+        }
+        if (top) row2_iter<TY, NS, false, true>(p, k, st, nL1);
+    }
+    if (a_sync_lo || a_sync_hi || is_b) {
+        if (p.ps.enabled) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (a_sync_lo) peer_publish(p.ps.done + 0, p.ps.target_lo, p.half_sig_lo, p.ps.epoch + 1);
+                if (a_sync_hi) peer_publish(p.ps.done + 1, p.ps.target_hi, p.half_sig_hi, p.ps.epoch + 1);
+                if (b_is_lo) peer_publish(p.done_b + 0, p.target_b_lo, p.ps.sig_lo, p.ps.epoch + 2);
+                if (b_is_hi) peer_publish(p.done_b + 1, p.target_b_hi, p.ps.sig_hi, p.ps.epoch + 2);
+            }
+        }
+    }
+}
+
 template <int TY, int NS>
 struct Tb2Launcher {
     using Cfg = Tb2Cfg<TY, NS>;
@@ -519,15 +938,54 @@ struct Tb2Launcher {
     }
 };
 
+// two rows per row warp: same tiling / planner as Tb2Launcher<TY, NS>, its own kernel and thread count
+template <int TY, int NS, bool MERGE>
+struct Tb2xLauncher {
+    using Cfg = Tb2xCfg<TY, NS, MERGE>;
+    static int launch(const Tb2Args& t, cudaStream_t s)
+    {
+        const SweepArgs& a = t.a;
+        dim3 grid;
+        int chunk, n_a;
+        Tb2Launcher<TY, NS>::plan(t, grid, chunk, n_a);
+        CUtensorMap tm_u0, tm_rhs;
+        if (tma3d_encode_map(&tm_u0, a.g, a.in, Cfg::BX, Cfg::U0_ROWS)) return -1;
+        if (tma3d_encode_map(&tm_rhs, a.g, a.rhs, Cfg::BX, Cfg::R_ROWS)) return -1;
+        Tb2Params p;
+        p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
+        p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk; p.n_a = n_a;
+        p.b_lo = t.b_lo; p.b_hi = t.b_hi;
+        p.peer_u1_lo = t.peer_u1_lo; p.peer_u1_hi = t.peer_u1_hi;
+        p.u1_in_lo = t.u1_in_lo; p.u1_in_hi = t.u1_in_hi;
+        p.peer_lo_plane = a.peer_lo_plane; p.peer_hi_plane = a.peer_hi_plane;
+        p.ps = a.ps;
+        p.half_wait_lo = t.half_wait_lo; p.half_wait_hi = t.half_wait_hi;
+        p.half_sig_lo = t.half_sig_lo; p.half_sig_hi = t.half_sig_hi;
+        p.done_b = t.done_b; p.target_b_lo = t.target_b_lo; p.target_b_hi = t.target_b_hi;
+#ifndef RNMF_EMULATE
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(jacobi3d_tb2x_kernel<TY, NS, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            attr_set = true;
+        }
+#endif
+        RNMF_KERNEL_LAUNCH((jacobi3d_tb2x_kernel<TY, NS, MERGE>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
+        return 1;
+    }
+};
+
 }  // namespace
 
-// variants: 20 = 128x12 tile; 21 = 128x8  (16 / 12 warps: registers are allocated per 4 warps, so
-// 128x14 or 128x16 tiles would leave only 96 registers per thread and spill)
+// variants: 20 (and auto) = 128x12 tile, one row per row warp; 21 = 128x8  (16 / 12 warps: registers are allocated per
+// 4 warps, so 128x14 or 128x16 tiles would leave only 96 registers per thread and spill);
+// 24 = 128x12 tile, two rows per row warp, one helper warp (8 warps); 25 = 128x16 tile, two rows per row warp (11 warps)
 int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
 {
     if (t.a.k_end <= t.a.k_begin && !t.b_lo && !t.b_hi) return 0;
     switch (t.a.variant) {
     case 21: return Tb2Launcher<8, 6>::launch(t, s);
+    case 24: return Tb2xLauncher<12, 6, true>::launch(t, s);
+    case 25: return Tb2xLauncher<16, 4, false>::launch(t, s);
     default: return Tb2Launcher<12, 6>::launch(t, s);
     }
 }
@@ -538,6 +996,7 @@ int double_sweep_boundary_ctas(const Tb2Args& t)
     int chunk, n_a;
     switch (t.a.variant) {
     case 21: Tb2Launcher<8, 6>::plan(t, grid, chunk, n_a); break;
+    case 25: Tb2Launcher<16, 4>::plan(t, grid, chunk, n_a); break;
     default: Tb2Launcher<12, 6>::plan(t, grid, chunk, n_a); break;
     }
     return (int)(grid.x * grid.y);

@@ -66,3 +66,13 @@ def test_roofline_accounting_single_and_double_sweep():
     assert abs(r1["frac"] - 0.9455) < 1e-3
     # both describe the same GLUP/s <-> GB/s relation: achieved / 24 B = updates per second
     assert abs(r["achieved"] / 24 - cells * 550 / (663.694677734375e-3) / 1e9) < 1e-6 * r["achieved"]
+
+
+def test_gpu_suite_collects_on_the_cpu_box():
+    """The GPU tests cannot run here, but a syntax or import error in them would only show at round end."""
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "--collect-only", "-q", "-m", "gpu"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "error" not in r.stdout.lower().splitlines()[-1]
+    n = int(r.stdout.strip().splitlines()[-1].split("/")[0].split()[0])
+    assert n >= 200

@@ -73,6 +73,15 @@ def _setup(n, hi, spec, sweeps, seed):
     ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 20, 0),          # a single plane: both z ghosts of u1 formed in registers
     ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 20, 0),
     ([40, 10, 6], [1.0, 2.0, 3.0], MIXED_3D, 1, 21, 3),          # 128x8 tile variant
+    # two rows per row warp (variants 24: 128x12 tile + one helper warp, 25: 128x16 tile): N/S of one row from the other's registers
+    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 24, 0),
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 24, 2),
+    ([30, 11, 3], [1.0, 1.0, 1.0], MIXED_3D, 1, 24, 0),          # the frame's last row is a warp's FIRST row: y-hi ghost of u1 in registers
+    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 24, 0),
+    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 24, 0),
+    ([129, 17, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 25, 0),
+    ([65, 33, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 25, 2),
+    ([30, 15, 2], [1.0, 1.0, 1.0], MIXED_3D, 1, 25, 0),
 ])
 def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, variant, chunk):
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
@@ -96,16 +105,18 @@ def test_2d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     np.testing.assert_array_equal(out, want)
 
 
-@pytest.mark.parametrize("n,hi,spec,pairs,nranks,chunk", [
-    ([20, 9, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0),           # two slabs: each rank has one neighbour
-    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0),         # uneven split (5, 5, 7); the middle rank has both
-    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1),        # 4-plane slabs (the minimum), one-plane A chunks
+@pytest.mark.parametrize("n,hi,spec,pairs,nranks,chunk,variant", [
+    ([20, 9, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 20),           # two slabs: each rank has one neighbour
+    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 20),         # uneven split (5, 5, 7); the middle rank has both
+    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1, 20),        # 4-plane slabs (the minimum), one-plane A chunks
+    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 24),         # two rows per row warp
+    ([20, 17, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 25),
 ])
-def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk):
+def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk, variant):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial
     schedule); u1 / u2 boundary planes go through the neighbours' buffers under the half / full step flags."""
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=43)
     out = psi.copy()
-    rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 20, chunk, pairs, nranks)
+    rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, pairs, nranks)
     assert rc == 0, "deadlock / handshake timeout"
     np.testing.assert_array_equal(out, want)

@@ -4,6 +4,7 @@ Bar: bit-exact for fill_bc / operators / Jacobi sweeps / variable-mu operator / 
 norms within 1e-12 relative of a long-double oracle sum (tree order differs from the serial sum).
 All tests call through librnmf_b200.so via ctypes."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -226,6 +227,9 @@ def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
 
 
 ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
+# variants 24 / 25 (two rows per row warp) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
+# on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 adds them here
+_DOUBLE_SWEEP_VARIANTS = [20, 21] + ([24, 25] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
@@ -239,7 +243,7 @@ ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("ne
     ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 6, False),
     ([260, 30, 2], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 9, True),
 ])
-@pytest.mark.parametrize("variant", [20, 21])
+@pytest.mark.parametrize("variant", _DOUBLE_SWEEP_VARIANTS)
 def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, variant):
     """kernels_sweep_tb2.cu: two sweeps (+ the ghost fill after each) per pass over HBM must equal two
     single sweeps bit for bit, for every tiling edge case and both parities of the sweep count."""
