@@ -34,7 +34,7 @@ extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
            "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "jacobi3d_tb2{128x12,128x8},jacobi3d_tb2x{128x12m,128x16},jacobi2d_tb2{512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi3d_tb2{128x12,128x8},jacobi3d_tb2x{128x12m,128x16},jacobi2d_tb2{512},jacobi2d_tbk{3x512,4x512,4x768,2x512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -128,6 +128,7 @@ struct rnmf_ctx {
     long long partial_cap = 0;
     int sweep_variant = 0;
     long long double_sweeps = 0;                  // launches of the two-sweeps-per-pass kernel (rnmf_double_sweep_launches)
+    long long multi_sweeps = 0;                   // launches of the K-sweeps-per-pass 2D kernel (opt-in variants 32..35)
     int sweep_chunk = 0;
     int overlap_halo = 1;
     ncclComm_t comm = nullptr;
@@ -930,9 +931,23 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
 
     // 2D analogue (kernels_sweep2d_tb2.cu): single GPU; variant 0 = auto, 30 = explicit, 20 = single-sweep TMA kernel only
-    const bool tb2_2d = g.dim == 2 && (c->sweep_variant == 0 || c->sweep_variant == 30) && !dist && fused && xy_faces;
+    // K = 2..4 sweeps per pass (kernels_sweep2d_tbk.cu; opt-in variants 32..35): groups of K sweeps, the rest as pairs / singles
+    const int tbk_depth = g.dim == 2 ? multi_sweep_2d_depth(c->sweep_variant) : 0;
+    const bool tb2_2d = g.dim == 2 && (c->sweep_variant == 0 || c->sweep_variant == 30 || tbk_depth > 0) && !dist && fused && xy_faces;
+    const bool tbk_2d = tb2_2d && tbk_depth > 0;
 
     for (int64_t it = it0; it < n_sweeps; ++it) {
+        if (tbk_2d && it + tbk_depth <= n_pairable) {
+            SweepArgs t = a;
+            t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
+            t.k_begin = 0; t.k_end = m;
+            RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, s));
+            c->multi_sweeps += 1;
+            double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
+            psi->parity ^= 1;
+            it += tbk_depth - 1;
+            continue;
+        }
         if (tb2_2d && it + 2 <= n_pairable) {
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;

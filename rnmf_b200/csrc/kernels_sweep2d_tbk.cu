@@ -1,0 +1,519 @@
+// kernels_sweep2d_tbk.cu -- K1 for 2D frames, temporally blocked over K = 2, 3 or 4 sweeps: K 5-point
+// Jacobi sweeps (each followed by the ng=1 ghost fill, poisson.rs:80-89 + dataframe.rs:289-355) per
+// pass over HBM, i.e. 24/K algorithmic bytes per update.  Generalises kernels_sweep2d_tb2.cu (K = 2);
+// OPT-IN (sweep variants 32..35) until it has been measured on the device.
+//   * a CTA owns a strip of 128*NW columns and marches a chunk of rows in y; the producer warp streams
+//     one row of psi (u0) and one of rhs per stage, the strip plus PAD >= K halo columns either side;
+//   * NW consumer warps own 128 cells each (lane l: pairs 2l,2l+1 and 64+2l,65+2l).  Level l = 1..K
+//     (u_l = sweep(u_{l-1}) + its ghost fill) runs one row behind level l-1: in iteration `it` level l
+//     forms row a+it-(l-1), its N neighbour being the value level l-1 formed in the same iteration and
+//     its centre / S neighbour the two before it -- a two-row register window per level, so N/S never
+//     touch shared memory.  Shared memory serves the next u0 row, rhs, and the E/W neighbours: rows of
+//     u_1..u_{K-1} live in two-slot rings (with the x-face ghosts fill_bc would give them); the y-face
+//     ghosts of u_1..u_{K-1} are formed in registers; rhs of the last K-1 rows is a register queue;
+//   * one more consumer warp computes the halo columns: level l on the K-l columns either side of the
+//     strip, one lane per (level, column), levels chained through the rings with __syncwarp
+//     (redundant work K(K-1)/(128*NW) per row; a chunk re-reads 2K rows);
+//   * one barrier per ring slot: every consumer warp arrives once per iteration after its stores, and
+//     waits for the previous iteration's arrivals before it loads (that wait is also the
+//     write-after-read guard of the slot it overwrites).
+// Every operation is explicitly rounded in the reference's association (poisson.rs:83-85):
+// u_K is bit-identical to K single sweeps.  Single GPU only.
+#include <stdlib.h>
+
+#include "tma_util.cuh"
+
+namespace {
+using namespace tmau;
+
+struct TbkParams {
+    FrameGeom g;
+    double* out;
+    SweepCoef c;
+    FaceSet faces;
+    long long m_begin, m_end;   // output rows
+    int chunk;
+};
+
+template <int K, int NW, int NS>
+struct CfgK {
+    static constexpr int PAD = (K + 1) & ~1;               // even (pairs stay 16-byte aligned in a staged row), >= K
+    static constexpr int TXC = 128 * NW;
+    static constexpr int ROW = TXC + 2 * PAD;              // a staged row: columns i0-PAD .. i0+TXC+PAD-1
+    static constexpr int ROW_BYTES = ROW * 8;
+    static constexpr int STAGE = (ROW_BYTES + 127) / 128 * 128;
+    static constexpr int RHS_OFF = NS * STAGE;
+    static constexpr int RING_OFF = 2 * NS * STAGE;        // ring of level s (1..K-1), slot t: RING_OFF + (2(s-1)+t)*STAGE
+    static constexpr int BAR_OFF = RING_OFF + 2 * (K - 1) * STAGE;
+    static constexpr int SMEM = BAR_OFF + (2 * NS + 2) * 8 + 128;
+    static constexpr int NCONS = NW + 1;                   // + the halo-column warp
+    static constexpr int THREADS = 32 * (NW + 2);
+};
+
+// iterations in which level l+1 is active in this chunk, and the ones in which it meets a y face
+template <int K>
+struct LevelPlan {
+    int first[K], last[K], it_ylo[K], it_yhi[K];
+    int n_it;           // iterations of the chunk
+    int s0, s1;         // steady iterations [s0, s1]: every level active, no y face
+    long long a;        // first level-1 row
+    int nL1;            // level-1 rows
+};
+template <int K>
+__device__ __forceinline__ LevelPlan<K> make_plan(long long j0, long long j1, long long n1)
+{
+    LevelPlan<K> p;
+    long long lo[K], hi[K];
+#pragma unroll
+    for (int l = 1; l <= K; ++l) {
+        lo[l - 1] = j0 - (K - l) > 0 ? j0 - (K - l) : 0;
+        hi[l - 1] = j1 - 1 + (K - l) < n1 - 1 ? j1 - 1 + (K - l) : n1 - 1;
+    }
+    p.a = lo[0];
+    p.nL1 = (int)(hi[0] - lo[0]) + 1;
+#pragma unroll
+    for (int l = 1; l <= K; ++l) {
+        p.first[l - 1] = (int)(lo[l - 1] - p.a) + (l - 1);
+        p.last[l - 1] = (int)(hi[l - 1] - p.a) + (l - 1);
+        p.it_ylo[l - 1] = lo[l - 1] == 0 ? p.first[l - 1] : -1;
+        p.it_yhi[l - 1] = hi[l - 1] == n1 - 1 ? p.last[l - 1] : -1;
+    }
+    p.n_it = p.last[K - 1] + 1;
+    p.s0 = p.first[K - 1] + (lo[K - 1] == 0 ? 1 : 0);
+    p.s1 = p.last[0];
+    return p;
+}
+
+template <int K>
+struct LaneK {
+    uint32_t pa, ra, ua;            // the lane's first pair in stage 0 of u0 / rhs, in slot 0 of the level-1 ring
+    uint32_t full0, empty0, ufull0;
+    double c0, c1, c2;
+    bool full, va0, va1, vb0, vb1;
+    bool do_xlo, any_x;
+    int xhi_sel;
+    uint32_t xhi_off;
+    Face1 fx0, fx1, fy0, fy1;
+    long long pitch;
+    int lane;
+    LevelPlan<K> lp;
+};
+template <int K>
+struct StateK {
+    double2 below_a, below_b, cur_a, cur_b;              // u0 rows a+it-1, a+it
+    double2 lo_a[K - 1], lo_b[K - 1], c_a[K - 1], c_b[K - 1];   // [s-1]: the last two rows level s formed
+    double2 rq_a[K - 1], rq_b[K - 1];                    // [d]: c0 * rhs of row a+it-1-d
+    double* oa;
+    uint32_t sc, sn, phn;
+};
+
+// poisson.rs:83-85: (c0*r + c1*(e+w)) + c2*(n+s); p0 = c0*r is rounded once per cell and row and reused by every
+// level (the same IEEE operation on the same operands, so the result is the reference's)
+__device__ __forceinline__ double updk(double c1, double c2, double p0, double e, double w, double n, double s)
+{
+    return __dadd_rn(__dadd_rn(p0, __dmul_rn(c1, __dadd_rn(e, w))), __dmul_rn(c2, __dadd_rn(n, s)));
+}
+__device__ __forceinline__ double2 mul2(double c, const double2& v) { return make_double2(__dmul_rn(c, v.x), __dmul_rn(c, v.y)); }
+
+// x-face ghosts of a row of u_1..u_{K-1} just stored at `us` (lanes next to a face only: any_x): the ghost
+// fill_bc would give the level goes into the ring beside the row; with odd n0 the E neighbour of the last valid
+// cell at the next level is the pair's second register, which takes the ghost too
+template <int K>
+__device__ __forceinline__ void xface_ring(const LaneK<K>& k, uint32_t us, double2& v_a, double2& v_b)
+{
+    if (k.do_xlo) sts1(us - 8, ghost1(k.fx0, v_a.x));
+    if (k.xhi_sel >= 0) {
+        const double m = k.xhi_sel == 0 ? v_a.x : k.xhi_sel == 1 ? v_a.y : k.xhi_sel == 2 ? v_b.x : v_b.y;
+        const double gv = ghost1(k.fx1, m);
+        sts1(us + k.xhi_off, gv);
+        if (k.xhi_sel == 0) v_a.y = gv;
+        if (k.xhi_sel == 2) v_b.y = gv;
+    }
+}
+
+// XF: an edge warp -- it owns a cell next to an x face, or columns past the frame (masked stores).  Warp-uniform, so
+// the ghost code and the store masks are compiled out of the other warps' loop.
+template <int K, int NW, int NS, bool STEADY, bool XF>
+__device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, const int it)
+{
+    using Cfg = CfgK<K, NW, NS>;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    const bool act1 = STEADY || it <= k.lp.last[0];
+
+    if (act1) mbar_wait(k.full0 + 8 * st.sn, st.phn);
+    if (it >= 1) mbar_wait(k.ufull0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+
+    // ---- every shared-memory load of the iteration, issued together ----
+    const uint32_t pslot = (uint32_t)((it - 1) & 1) * Cfg::STAGE, slot = (uint32_t)(it & 1) * Cfg::STAGE;
+    double uw_a[K - 1], ue_a[K - 1], uw_b[K - 1], ue_b[K - 1];      // [s-1]: E/W of the row level s formed in the previous iteration
+#pragma unroll
+    for (int s = 1; s < K; ++s) {
+        const bool act = STEADY || (it >= k.lp.first[s] && it <= k.lp.last[s]);       // level s+1
+        uw_a[s - 1] = ue_a[s - 1] = uw_b[s - 1] = ue_b[s - 1] = 0.0;
+        if (act) {
+            const uint32_t up = k.ua + (uint32_t)(2 * (s - 1)) * Cfg::STAGE + pslot;
+            uw_a[s - 1] = lds1(up - 8); ue_a[s - 1] = lds1(up + 16);
+            uw_b[s - 1] = lds1(up + 512 - 8); ue_b[s - 1] = lds1(up + 512 + 16);
+        }
+    }
+    double2 above_a = zero2, above_b = zero2, rc_a = zero2, rc_b = zero2, f_a = zero2, f_b = zero2;
+
+    // ---------------- level 1: u1 of row a+it ----------------
+    if (act1) {
+        const uint32_t pn = k.pa + st.sn * Cfg::STAGE, pc = k.pa + st.sc * Cfg::STAGE, pr = k.ra + st.sc * Cfg::STAGE;
+        above_a = lds2(pn); above_b = lds2(pn + 512);
+        rc_a = mul2(k.c0, lds2(pr)); rc_b = mul2(k.c0, lds2(pr + 512));
+        const double w_a0 = lds1(pc - 8), e_a1 = lds1(pc + 16);
+        const double w_b0 = lds1(pc + 512 - 8), e_b1 = lds1(pc + 512 + 16);
+        f_a.x = updk(k.c1, k.c2, rc_a.x, st.cur_a.y, w_a0, above_a.x, st.below_a.x);
+        f_a.y = updk(k.c1, k.c2, rc_a.y, e_a1, st.cur_a.x, above_a.y, st.below_a.y);
+        f_b.x = updk(k.c1, k.c2, rc_b.x, st.cur_b.y, w_b0, above_b.x, st.below_b.x);
+        f_b.y = updk(k.c1, k.c2, rc_b.y, e_b1, st.cur_b.x, above_b.y, st.below_b.y);
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
+        const uint32_t us = k.ua + slot;
+        sstore4(us, f_a, f_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (XF && k.any_x) xface_ring(k, us, f_a, f_b);
+    }
+
+    // ---------------- levels 2..K: u_l of row a+it-(l-1) ----------------
+    bool prev_act = act1;
+#pragma unroll
+    for (int l = 2; l <= K; ++l) {
+        const int s = l - 1;                                   // the source level
+        const bool act = STEADY || (it >= k.lp.first[l - 1] && it <= k.lp.last[l - 1]);
+        double2 o_a = zero2, o_b = zero2;
+        if (act) {
+            const double2 ce_a = st.c_a[s - 1], ce_b = st.c_b[s - 1];
+            double2 dn_a = st.lo_a[s - 1], dn_b = st.lo_b[s - 1], up_a = f_a, up_b = f_b;
+            if (!STEADY) {
+                if (it == k.lp.it_ylo[l - 1]) { dn_a = ghost1(k.fy0, ce_a); dn_b = ghost1(k.fy0, ce_b); }
+                if (it == k.lp.it_yhi[l - 1]) { up_a = ghost1(k.fy1, ce_a); up_b = ghost1(k.fy1, ce_b); }
+            }
+            const double2 r_a = st.rq_a[l - 2], r_b = st.rq_b[l - 2];
+            o_a.x = updk(k.c1, k.c2, r_a.x, ce_a.y, uw_a[s - 1], up_a.x, dn_a.x);
+            o_a.y = updk(k.c1, k.c2, r_a.y, ue_a[s - 1], ce_a.x, up_a.y, dn_a.y);
+            o_b.x = updk(k.c1, k.c2, r_b.x, ce_b.y, uw_b[s - 1], up_b.x, dn_b.x);
+            o_b.y = updk(k.c1, k.c2, r_b.y, ue_b[s - 1], ce_b.x, up_b.y, dn_b.y);
+            if (l < K) {
+                const uint32_t us = k.ua + (uint32_t)(2 * (l - 1)) * Cfg::STAGE + slot;
+                sstore4(us, o_a, o_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+                if (XF && k.any_x) xface_ring(k, us, o_a, o_b);
+            } else {
+                double* oa = st.oa;
+                store4(oa, o_a, o_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+                if (XF && k.any_x) {
+                    if (k.do_xlo) oa[-1] = ghost1(k.fx0, o_a.x);
+                    if (k.xhi_sel >= 0) {
+                        const double m = k.xhi_sel == 0 ? o_a.x : k.xhi_sel == 1 ? o_a.y : k.xhi_sel == 2 ? o_b.x : o_b.y;
+                        oa[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, m);
+                    }
+                }
+                if (!STEADY) {
+                    if (it == k.lp.it_ylo[K - 1]) store4(oa - k.pitch, ghost1(k.fy0, o_a), ghost1(k.fy0, o_b), !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+                    if (it == k.lp.it_yhi[K - 1]) store4(oa + k.pitch, ghost1(k.fy1, o_a), ghost1(k.fy1, o_b), !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+                }
+                st.oa = oa + k.pitch;
+            }
+        }
+        if (prev_act) {                                        // level s formed a row: its window moves up
+            st.lo_a[s - 1] = st.c_a[s - 1]; st.lo_b[s - 1] = st.c_b[s - 1];
+            st.c_a[s - 1] = f_a; st.c_b[s - 1] = f_b;
+        }
+        f_a = o_a; f_b = o_b;
+        prev_act = act;
+    }
+    __syncwarp();
+    if (k.lane == 0) mbar_arrive(k.ufull0 + 8 * (it & 1));
+
+    if (act1) {
+        st.below_a = st.cur_a; st.below_b = st.cur_b;
+        st.cur_a = above_a; st.cur_b = above_b;
+        st.sc = st.sn;
+        if (++st.sn == NS) { st.sn = 0; st.phn ^= 1u; }
+    }
+#pragma unroll
+    for (int d = K - 2; d >= 1; --d) { st.rq_a[d] = st.rq_a[d - 1]; st.rq_b[d] = st.rq_b[d - 1]; }
+    st.rq_a[0] = rc_a; st.rq_b[0] = rc_b;
+}
+
+// the iterations of a chunk: ramp-up (levels start one after the other, y-lo faces), the steady part unrolled by
+// three (the three-row windows rotate by renaming), drain (y-hi faces)
+template <int K, int NW, int NS, bool XF>
+__device__ __forceinline__ void rowk_chunk(const LaneK<K>& k, StateK<K>& st)
+{
+    int it = 0;
+    for (; it < k.lp.s0 && it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, false, XF>(k, st, it);
+    for (; it + 2 <= k.lp.s1; it += 3) {
+        rowk_iter<K, NW, NS, true, XF>(k, st, it);
+        rowk_iter<K, NW, NS, true, XF>(k, st, it + 1);
+        rowk_iter<K, NW, NS, true, XF>(k, st, it + 2);
+    }
+    for (; it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, false, XF>(k, st, it);
+}
+
+template <int K, int NW, int NS, int MINB>
+__global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const __grid_constant__ CUtensorMap tm_u256,
+                                                                             const __grid_constant__ CUtensorMap tm_upad,
+                                                                             const __grid_constant__ CUtensorMap tm_r256,
+                                                                             const __grid_constant__ CUtensorMap tm_rpad,
+                                                                             const __grid_constant__ TbkParams p)
+{
+    using Cfg = CfgK<K, NW, NS>;
+    constexpr int PAD = Cfg::PAD, TXC = Cfg::TXC, STAGE = Cfg::STAGE;
+    RNMF_DYNAMIC_SMEM(smem_raw);
+    const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, ring_0 = sb + Cfg::RING_OFF;
+    const uint32_t full0 = sb + Cfg::BAR_OFF, empty0 = full0 + NS * 8, ufull0 = empty0 + NS * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n0 = p.g.n[0], n1 = p.g.n[1];
+    const long long i0 = (long long)blockIdx.x * TXC;
+    const long long j0 = p.m_begin + (long long)blockIdx.y * p.chunk;
+    const long long j1 = j0 + p.chunk < p.m_end ? j0 + p.chunk : p.m_end;
+    const LevelPlan<K> lp = make_plan<K>(j0, j1, n1);
+    const int n_rows = lp.nL1 + 2;                          // u0 rows a-1..b+1 (row a-1+idx <-> stage idx % NS)
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, Cfg::NCONS);
+        }
+        mbar_init(ufull0, Cfg::NCONS);
+        mbar_init(ufull0 + 8, Cfg::NCONS);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NW + 1) {
+        // ------------------------------ producer warp ------------------------------
+        if (lane == 0) {
+            const int cx = (int)(p.g.xoff + p.g.ng + i0 - PAD);
+            int cy = (int)(p.g.ng + lp.a - 1);
+            uint32_t s = 0, wrap = 0;
+            for (int idx = 0; idx < n_rows; ++idx) {
+                if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
+                const bool with_rhs = idx >= 1 && idx <= lp.nL1;
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(Cfg::ROW_BYTES * (with_rhs ? 2 : 1)));
+                const uint32_t d = u0_0 + s * STAGE;
+#pragma unroll
+                for (int b = 0; b < TXC / 256; ++b) tma_load_2d(d + 2048 * b, &tm_u256, cx + 256 * b, cy, full0 + 8 * s);
+                tma_load_2d(d + 8 * TXC, &tm_upad, cx + TXC, cy, full0 + 8 * s);
+                if (with_rhs) {
+                    const uint32_t r = rhs_0 + s * STAGE;
+#pragma unroll
+                    for (int b = 0; b < TXC / 256; ++b) tma_load_2d(r + 2048 * b, &tm_r256, cx + 256 * b, cy, full0 + 8 * s);
+                    tma_load_2d(r + 8 * TXC, &tm_rpad, cx + TXC, cy, full0 + 8 * s);
+                }
+                ++cy;
+                if (++s == NS) { s = 0; ++wrap; }
+            }
+        }
+    } else if (warp == NW) {
+        // ------------------------------ halo-column warp ------------------------------
+        // one lane per (level L = 1..K-1, column): level L on the K-L columns either side of the strip
+        const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2;
+        int L = 0, col = 0;
+        {
+            int base = 0;
+#pragma unroll
+            for (int l = 1; l < K; ++l) {
+                const int w = K - l;
+                if (L == 0 && lane < base + 2 * w) {
+                    const int j = lane - base;
+                    L = l;
+                    col = j < w ? j - w : TXC + (j - w);
+                }
+                base += 2 * w;
+            }
+        }
+        const long long i = i0 + col;
+        const bool ok = L > 0 && i >= 0 && i < n0;
+        const Face1 fx1 = make_face1(p.faces.f[1], true), fy0 = make_face1(p.faces.f[2], true), fy1 = make_face1(p.faces.f[3], true);
+        const bool xhi = ok && fx1.on && i == n0 - 1;         // the x-hi ghost of my level sits right of my column
+        const uint32_t off = (uint32_t)((col + PAD) * 8);
+        const uint32_t hp = u0_0 + off, hr = rhs_0 + off, hu = ring_0 + off;
+        double below = 0.0, cur = 0.0, wlo = 0.0, wc = 0.0;
+        double q[K - 1];
+#pragma unroll
+        for (int d = 0; d < K - 1; ++d) q[d] = 0.0;
+        mbar_wait(full0, 0);
+        below = lds1(hp);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        cur = lds1(hp + STAGE);
+        uint32_t sc = 1, sn = 2, phn = 0;
+        for (int it = 0; it < lp.n_it; ++it) {
+            const bool act1 = it <= lp.last[0];
+            if (act1) mbar_wait(full0 + 8 * sn, phn);
+            if (it >= 1) mbar_wait(ufull0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+            const uint32_t pslot = (uint32_t)((it - 1) & 1) * STAGE, slot = (uint32_t)(it & 1) * STAGE;
+            double rr = 0.0, above = 0.0;
+            if (act1) {
+                rr = __dmul_rn(c0, lds1(hr + sc * STAGE));
+                above = lds1(hp + sn * STAGE);
+                if (L == 1) {
+                    const uint32_t pc = hp + sc * STAGE;
+                    const double ee = lds1(pc + 8), ww = lds1(pc - 8);
+                    const double v = updk(c1, c2, rr, ee, ww, above, below);
+                    if (ok) {
+                        sts1(hu + slot, v);
+                        if (xhi) sts1(hu + slot + 8, ghost1(fx1, v));
+                    }
+                }
+            }
+            __syncwarp();
+            if (act1 && lane == 0) mbar_arrive(empty0 + 8 * sc);
+#pragma unroll
+            for (int l = 2; l < K; ++l) {
+                const bool actl = it >= lp.first[l - 1] && it <= lp.last[l - 1];
+                const bool actp = it >= lp.first[l - 2] && it <= lp.last[l - 2];   // level l-1 stored a row in this iteration
+                if (L == l) {
+                    const uint32_t src = hu + (uint32_t)(2 * (l - 2)) * STAGE;
+                    double fresh = 0.0;
+                    if (actp && ok) fresh = lds1(src + slot);
+                    if (actl) {
+                        double dn = wlo, up = fresh;
+                        if (it == lp.it_ylo[l - 1]) dn = ghost1(fy0, wc);
+                        if (it == lp.it_yhi[l - 1]) up = ghost1(fy1, wc);
+                        const double ee = lds1(src + pslot + 8), ww = lds1(src + pslot - 8);
+                        const double v = updk(c1, c2, q[l - 2], ee, ww, up, dn);
+                        if (ok) {
+                            const uint32_t dst = hu + (uint32_t)(2 * (l - 1)) * STAGE + slot;
+                            sts1(dst, v);
+                            if (xhi) sts1(dst + 8, ghost1(fx1, v));
+                        }
+                    }
+                    if (actp) { wlo = wc; wc = fresh; }
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ufull0 + 8 * (it & 1));
+            if (act1) {
+                below = cur;
+                cur = above;
+                sc = sn;
+                if (++sn == NS) { sn = 0; phn ^= 1u; }
+            }
+#pragma unroll
+            for (int d = K - 2; d >= 1; --d) q[d] = q[d - 1];
+            q[0] = rr;
+        }
+    } else {
+        // ------------------------------ consumer warps ------------------------------
+        const long long ia = i0 + 128 * warp + 2 * lane, ib = ia + 64;
+        LaneK<K> k;
+        k.va0 = ia < n0; k.va1 = ia + 1 < n0; k.vb0 = ib < n0; k.vb1 = ib + 1 < n0;
+        k.full = k.vb1;
+        // column c of the strip sits at (c+PAD)*8 in a staged u0 / rhs row and in a ring slot
+        const uint32_t off = (uint32_t)((128 * warp + PAD + 2 * lane) * 8);
+        k.pa = u0_0 + off; k.ra = rhs_0 + off; k.ua = ring_0 + off;
+        k.full0 = full0; k.empty0 = empty0; k.ufull0 = ufull0;
+        k.c0 = p.c.c0; k.c1 = p.c.c1; k.c2 = p.c.c2;
+        k.pitch = p.g.pitch;
+        k.lane = lane;
+        k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
+        k.fy0 = make_face1(p.faces.f[2], true); k.fy1 = make_face1(p.faces.f[3], true);
+        k.do_xlo = k.fx0.on && k.va0 && ia == 0;
+        const long long last = n0 - 1;
+        k.xhi_sel = !k.fx1.on ? -1 : (k.va0 && ia == last) ? 0 : (k.va1 && ia + 1 == last) ? 1 : (k.vb0 && ib == last) ? 2 : (k.vb1 && ib + 1 == last) ? 3 : -1;
+        k.xhi_off = (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        k.any_x = k.do_xlo || k.xhi_sel >= 0;
+        k.lp = lp;
+
+        StateK<K> st;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        mbar_wait(full0, 0);
+        st.below_a = lds2(k.pa); st.below_b = lds2(k.pa + 512);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        st.cur_a = lds2(k.pa + STAGE); st.cur_b = lds2(k.pa + STAGE + 512);
+#pragma unroll
+        for (int s = 0; s < K - 1; ++s) {
+            st.lo_a[s] = zero2; st.lo_b[s] = zero2; st.c_a[s] = zero2; st.c_b[s] = zero2;
+            st.rq_a[s] = zero2; st.rq_b[s] = zero2;
+        }
+        st.oa = p.out + p.g.at(ia, j0, 0, 0);
+        st.sc = 1; st.sn = 2; st.phn = 0;
+
+        // warp-uniform: does this warp's 128-column span touch an x face or reach past the frame?
+        const long long w0 = i0 + 128 * warp;
+        const bool warp_x = (k.fx0.on && w0 == 0) || (k.fx1.on && last >= w0 && last < w0 + 128) || w0 + 128 > n0;
+        if (warp_x) rowk_chunk<K, NW, NS, true>(k, st);
+        else rowk_chunk<K, NW, NS, false>(k, st);
+    }
+}
+
+template <int K, int NW, int NS, int MINB>
+int launch_tbk(const SweepArgs& a, cudaStream_t s)
+{
+    using Cfg = CfgK<K, NW, NS>;
+    const FrameGeom& g = a.g;
+    const long long span = a.k_end - a.k_begin;
+    const long long bx = (g.n[0] + Cfg::TXC - 1) / Cfg::TXC;
+    // chunk length: whole waves of MINB CTAs per SM, each CTA paying chunk + 2(K-1) + 1 row iterations
+    long long best_c = 1, best_cost = -1;
+    static const int cand[] = { 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512 };
+    for (int c : cand) {
+        const long long cc = c > span ? span : c;
+        if (cc < 1) break;
+        const long long chunks = (span + cc - 1) / cc;
+        if (chunks <= 60000) {
+            const long long per_wave = 148LL * MINB;
+            const long long waves = (bx * chunks + per_wave - 1) / per_wave;
+            const long long cost = waves * (cc + 2 * (K - 1) + 1);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_c = cc; }
+        }
+        if (c >= span) break;
+    }
+    if (a.chunk_override > 0) best_c = a.chunk_override > span ? span : a.chunk_override;
+    if (best_c < 1) best_c = 1;
+    const dim3 grid((unsigned)bx, (unsigned)((span + best_c - 1) / best_c), 1);
+    CUtensorMap tm_u256, tm_upad, tm_r256, tm_rpad;
+    if (tma2d_encode_map(&tm_u256, g, a.in, 256)) return -1;
+    if (tma2d_encode_map(&tm_upad, g, a.in, 2 * Cfg::PAD)) return -1;
+    if (tma2d_encode_map(&tm_r256, g, a.rhs, 256)) return -1;
+    if (tma2d_encode_map(&tm_rpad, g, a.rhs, 2 * Cfg::PAD)) return -1;
+    TbkParams p;
+    p.g = g; p.out = a.out; p.c = a.c; p.faces = a.faces;
+    p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = (int)best_c;
+    auto kern = jacobi2d_tbk_kernel<K, NW, NS, MINB>;
+#ifndef RNMF_EMULATE
+    static bool attr_set = false;                      // one per instantiation
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
+    }
+#endif
+    RNMF_KERNEL_LAUNCH(kern, grid, Cfg::THREADS, Cfg::SMEM, s, tm_u256, tm_upad, tm_r256, tm_rpad, p);
+    return 1;
+}
+
+}  // namespace
+
+// sweeps per launch of a 2D sweep variant (0: the variant is not a K-sweep variant)
+int multi_sweep_2d_depth(int variant)
+{
+    return variant == 32 ? 3 : variant == 33 || variant == 34 ? 4 : variant == 35 ? 2 : 0;
+}
+
+// K sweeps (+ ghost fills) per launch, a.k_begin..a.k_end = output rows; every x / y face must carry a
+// Dirichlet or Neumann rule (the caller checks).  Variants: 32 = three sweeps, 512-column strips, two CTAs per SM;
+// 33 = four sweeps, same shape; 34 = four sweeps, 768-column strips (8 warps), one CTA per SM (255 registers);
+// 35 = two sweeps through this kernel (cross-check against kernels_sweep2d_tb2.cu).
+int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
+{
+    if (a.k_end <= a.k_begin) return 0;
+    switch (a.variant) {
+    case 32: return launch_tbk<3, 4, 8, 2>(a, s);
+    case 33: return launch_tbk<4, 4, 8, 2>(a, s);
+    case 34: return launch_tbk<4, 6, 8, 1>(a, s);
+    case 35: return launch_tbk<2, 4, 10, 2>(a, s);
+    default: return -1;
+    }
+}

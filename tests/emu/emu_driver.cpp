@@ -1,5 +1,5 @@
 // emu_driver.cpp -- TEST INFRASTRUCTURE: the double-sweep kernel SOURCES (kernels_sweep_tb2.cu,
-// kernels_sweep2d_tb2.cu) compiled with g++ -DRNMF_EMULATE and run on host threads by the SIMT emulator
+// kernels_sweep2d_tb2.cu, and the K-sweep kernels_sweep2d_tbk.cu) compiled with g++ -DRNMF_EMULATE and run on host threads by the SIMT emulator
 // (tests/emu/emu_cuda.hpp).  Exposes a small C interface for tests/test_emulated_kernels.py:
 // dense reference-layout frames in, dense frames out, through the very launchers (planner, tensor maps,
 // A/B chunk roles, handshake flags) the library uses.  Slabs: every "rank" is a host thread with its own
@@ -56,6 +56,7 @@ int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, in
 
 #include "../../rnmf_b200/csrc/kernels_sweep_tb2.cu"
 #include "../../rnmf_b200/csrc/kernels_sweep2d_tb2.cu"
+#include "../../rnmf_b200/csrc/kernels_sweep2d_tbk.cu"
 
 namespace {
 
@@ -188,6 +189,8 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
             memset(&t, 0, sizeof(t));
             t.a = a;
             if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
+        } else if (multi_sweep_2d_depth(variant) > 0) {
+            if (launch_jacobi_multi_sweep_2d(a, nullptr) < 0) return -1;        // n_pairs launches of K sweeps each
         } else {
             if (launch_jacobi_double_sweep_2d(a, nullptr) < 0) return -1;
         }

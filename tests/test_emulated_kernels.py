@@ -23,12 +23,13 @@ KIND = {"dirichlet": 0, "neumann": 1}
 MIXED_3D = ([("dirichlet", 0.0), ("neumann", 0.0), ("dirichlet", 0.25)], [("dirichlet", 1.0), ("neumann", -0.5), ("neumann", 0.5)])
 NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
 MIXED_2D = ([("neumann", 0.3), ("dirichlet", -1.0)], [("dirichlet", 2.0), ("neumann", -0.7)])
+NEUMANN_2D = ([("neumann", 0.3), ("neumann", -0.2)], [("neumann", 0.4), ("neumann", 0.6)])
 
 
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC] + [os.path.join(ROOT, "rnmf_b200", "csrc", f) for f in
-                    ("kernels_sweep_tb2.cu", "kernels_sweep2d_tb2.cu", "tma_util.cuh", "common.cuh")] + [os.path.join(ROOT, "tests", "emu", "emu_cuda.hpp")]
+                    ("kernels_sweep_tb2.cu", "kernels_sweep2d_tb2.cu", "kernels_sweep2d_tbk.cu", "tma_util.cuh", "common.cuh")] + [os.path.join(ROOT, "tests", "emu", "emu_cuda.hpp")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
@@ -102,6 +103,31 @@ def test_2d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     out = np.zeros_like(psi)
     rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 30, chunk, pairs)
     assert rc == 0
+    np.testing.assert_array_equal(out, want)
+
+
+DEPTH = {32: 3, 33: 4, 34: 4, 35: 2}      # sweeps per launch of the K-sweep 2D variants (kernels_sweep2d_tbk.cu)
+
+
+@pytest.mark.parametrize("variant", [35, 32, 33, 34])
+@pytest.mark.parametrize("n,hi,spec,launches,chunk", [
+    ([33, 7], [1.0, 2.0], MIXED_2D, 1, 0),
+    ([513, 5], [513.0, 5.0], MIXED_2D, 2, 2),                    # one cell past a 512-column strip; 3 row chunks; ping-pong
+    ([515, 9], [1.0, 1.0], MIXED_2D, 1, 4),                      # the second strip is 3 columns wide: x-hi ghosts formed by halo lanes
+    ([769, 6], [1.0, 3.0], NEUMANN_2D, 1, 3),                    # one cell past a 768-column strip
+    ([40, 1], [1.0, 1.0], MIXED_2D, 1, 0),                       # a single row: every level meets both y faces
+    ([40, 2], [1.0, 1.0], MIXED_2D, 2, 0),
+    ([2, 3], [2.0, 3.0], MIXED_2D, 3, 1),                        # one-row chunks
+    ([1, 1], [1.0, 1.0], MIXED_2D, 2, 0),
+    ([130, 23], [13.0, 2.3], NEUMANN_2D, 1, 5),                  # chunks whose lower levels are clipped at either face
+    ([64, 40], [1.0, 1.0], MIXED_2D, 1, 0),                      # planner-chosen chunks, steady (unrolled) iterations
+])
+def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk, variant):
+    """K = 2, 3, 4 sweeps per pass (opt-in variants): u_K after `launches` launches == K*launches oracle sweeps, bit for bit."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, DEPTH[variant] * launches, seed=44)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, launches)
+    assert rc == 0, "a barrier wait timed out (deadlock) or the launch failed"
     np.testing.assert_array_equal(out, want)
 
 

@@ -226,6 +226,51 @@ def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
         ctx.set_option("resident", 1)
 
 
+# K = 3 / 4 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..35): validated on the CPU box by the kernel emulator
+# (test_emulated_kernels); on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 runs them here
+_MULTI_SWEEP_2D = {32: 3, 33: 4, 34: 4, 35: 2}
+
+
+@pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in kernels: set RNMF_EXPERIMENTAL=1")
+@pytest.mark.parametrize("variant", sorted(_MULTI_SWEEP_2D))
+@pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
+    ([301, 301], [301.0, 301.0], MIXED_2D, 12, False),
+    ([1500, 300], [15.0, 3.0], MIXED_2D, 13, False),         # several strips and row chunks; leftover sweeps as pairs / singles
+    ([1031, 67], [1.0, 1.0], DIRICHLET_2D, 9, True),         # last valid cell is the first of a pair; the last sweep carries the norm
+    ([515, 40], [515.0, 40.0], MIXED_2D, 8, False),          # a 3-column second strip: x-hi ghosts formed by the halo lanes
+    ([255, 1], [3.0, 5.0], MIXED_2D, 8, False),              # a single row: every level meets both y faces
+    ([2, 3], [2.0, 3.0], MIXED_2D, 9, True),
+    ([2048, 700], [1.0, 1.0], DIRICHLET_2D, 12, False),
+])
+def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, variant):
+    """kernels_sweep2d_tbk.cu: K 2D sweeps (+ ghost fills) per pass over HBM == K single sweeps, bit for bit."""
+    from rnmf_b200 import poisson
+    K = _MULTI_SWEEP_2D[variant]
+    ctx.set_option("sweep_variant", variant)
+    ctx.set_option("resident", 0)
+    try:
+        g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=33)
+        ora.fill_bc(g, psi0, obc)
+        psi.fill_bc()
+        k0, d0 = ctx.kernel_launches, ctx.double_sweep_launches
+        l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=norm)
+        ctx.sync()
+        pairable = sweeps - (1 if norm else 0)
+        groups, rest = divmod(pairable, K)
+        assert ctx.double_sweep_launches - d0 == rest // 2             # leftovers run as pairs, then singles
+        # ghost-shell copy + K-sweep launches + pairs + singles (+ the norm's reduction): the K-sweep kernel really ran
+        assert ctx.kernel_launches - k0 == 1 + groups + rest // 2 + rest % 2 + (2 if norm else 0)
+        want = psi0.copy()
+        l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
+        np.testing.assert_array_equal(psi.data, want)
+        if norm:
+            assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+        assert psi.guards_intact() and rhs.guards_intact()
+    finally:
+        ctx.set_option("sweep_variant", "auto")
+        ctx.set_option("resident", 1)
+
+
 ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
 # variants 24 / 25 (two rows per row warp) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
 # on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 adds them here
