@@ -149,6 +149,10 @@ struct rnmf_ctx {
     long long resident_max_bytes = 48LL << 20;    // psi + psi' + rhs must fit comfortably in the 126 MB L2
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
     rnmf_frame* hp_rhs = nullptr;
+    int e2e_skew = 0;                     // option "e2e_skew" (opt-in): time-skewed start of rnmf_solve_poisson_host
+    int e2e_skew_chunks = 8, e2e_skew_pairs = 56;
+    std::vector<cudaEvent_t> ev_chunks;   // one per upload chunk
+    long long skew_launches = 0;          // double-sweep launches issued by the skewed start (a test reads it back)
 };
 
 struct rnmf_frame {
@@ -257,6 +261,8 @@ static int ctx_common_init(rnmf_ctx* c)
     if (v) c->sweep_variant = atoi(v);
     const char* o = getenv("RNMF_HALO_OVERLAP");
     if (o) c->overlap_halo = atoi(o);
+    const char* k = getenv("RNMF_E2E_SKEW");
+    if (k) c->e2e_skew = atoi(k);
     return RNMF_OK;
 }
 
@@ -324,6 +330,7 @@ extern "C" int32_t rnmf_ctx_destroy(rnmf_ctx* c)
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    for (cudaEvent_t e : c->ev_chunks) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_halo) cudaStreamDestroy(c->stream_halo);
     delete c;
@@ -386,6 +393,9 @@ extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* val
     if (!strcmp(key, "peer_inkernel")) { c->peer_inkernel = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "resident")) { c->resident = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "halo_overlap")) { c->overlap_halo = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "e2e_skew")) { c->e2e_skew = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "e2e_skew_chunks")) { c->e2e_skew_chunks = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "e2e_skew_pairs")) { c->e2e_skew_pairs = atoi(value); return RNMF_OK; }
     rnmf_set_error("unknown option '%s'", key);
     return RNMF_ERR_INVALID;
 }
@@ -1329,6 +1339,88 @@ extern "C" int32_t rnmf_gradient_h_2d(const rnmf_frame* psi, rnmf_frame* h)
 // ------------------------------------------------------------------------------------------
 // host-buffer entry point (the reference-facing call: solve_poisson with host frames)
 // ------------------------------------------------------------------------------------------
+// Time-skewed start of rnmf_solve_poisson_host (opt-in, option "e2e_skew"): psi and rhs go up in chunks of z-planes on
+// the halo stream (1-D PCIe copy into the staging buffer + device repack, which also seeds the ghost shell of the
+// ping-pong buffer), and after every chunk the compute stream runs the first `pairs` double sweeps on the bands that
+// chunk makes computable (skew_region, common.cuh), so the sweeps overlap most of the upload.  Afterwards every plane
+// holds u_{2*pairs} and the frame continues with ordinary whole-frame launches.  Same kernels, same operations: the
+// result is bit-identical to the plain path.  Returns the number of sweeps done (0: not applicable, nothing touched).
+static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,
+                                              const double* coef, int64_t pairable, int* rc_out)
+{
+    *rc_out = RNMF_OK;
+    const FrameGeom& g = psi->g;
+    const int C = c->e2e_skew_chunks;
+    const long long n2 = g.n[2];
+    const long long dense = g.G[0] * g.G[1] * g.G[2];
+    int64_t pairs = c->e2e_skew_pairs < pairable / 2 ? c->e2e_skew_pairs : pairable / 2;
+    bool all_faces = psi->bc_set && !psi->has_reflect;
+    for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
+    const int v = c->sweep_variant;
+    if (!c->e2e_skew || g.dim != 3 || g.ng != 1 || g.ncomp != 1 || c->nranks != 1 || !all_faces || C < 2 || n2 / C < 16 || pairs < 4 ||
+        dense * 8 < (64LL << 20) || !(v == 0 || v == 20 || v == 21 || v == 24 || v == 25))
+        return 0;
+    cudaStream_t s = c->stream, cs = c->stream_halo;
+#define SKEW_TRY(expr) do { int _rc = (expr); if (_rc) { *rc_out = _rc; return 0; } } while (0)
+#define SKEW_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rnmf_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); *rc_out = RNMF_ERR_CUDA; return 0; } } while (0)
+    if (!psi->d2) SKEW_TRY(alloc_buffer(g, &psi->d2, s));
+    if (c->staging_cap < dense) {
+        SKEW_CUDA(cudaStreamSynchronize(s));
+        if (c->d_staging) { SKEW_CUDA(cudaFree(c->d_staging)); c->d_staging = nullptr; c->staging_cap = 0; }
+        SKEW_CUDA(cudaMalloc(&c->d_staging, (size_t)dense * 8));
+        c->staging_cap = dense;
+    }
+    while ((int)c->ev_chunks.size() < C) {
+        cudaEvent_t e;
+        SKEW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_chunks.push_back(e);
+    }
+    // the copy stream starts after everything queued on the compute stream (earlier readers of the staging buffer / frames)
+    SKEW_CUDA(cudaEventRecord(c->ev_boundary, s));
+    SKEW_CUDA(cudaStreamWaitEvent(cs, c->ev_boundary, 0));
+    const long long plane_dense = g.G[0] * g.G[1];
+    for (int ch = 0; ch < C; ++ch) {
+        // grown planes of chunk ch: valid planes [Z(ch), Z(ch+1)) plus the bottom / top ghost plane in the first / last chunk
+        const long long p0 = ch == 0 ? 0 : n2 * ch / C + 1, p1 = ch == C - 1 ? g.G[2] : n2 * (ch + 1) / C + 1;
+        const long long off = plane_dense * p0, cnt = plane_dense * (p1 - p0);
+        SKEW_CUDA(cudaMemcpyAsync(c->d_staging + off, psi_in + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, cs));
+        { int k = launch_unpack_dense_rows(g, c->d_staging, psi->d, psi->d2, g.G[1] * p0, g.G[1] * p1, cs); if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; } c->launches += k; }
+        SKEW_CUDA(cudaMemcpyAsync(c->d_staging + off, rhs_in + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, cs));
+        { int k = launch_unpack_dense_rows(g, c->d_staging, rhs->d, nullptr, g.G[1] * p0, g.G[1] * p1, cs); if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; } c->launches += k; }
+        SKEW_CUDA(cudaEventRecord(c->ev_chunks[ch], cs));
+    }
+    Tb2Args t;
+    memset(&t, 0, sizeof(t));
+    t.a.g = g;
+    t.a.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
+    t.a.faces = psi->faces[0];
+    t.a.fuse_fill = 1;
+    t.a.variant = c->sweep_variant;
+    t.a.chunk_override = c->sweep_chunk;
+    t.a.rhs = rhs->d;
+    double* buf[2] = { psi->d, psi->d2 };
+    for (int ch = 0; ch < C; ++ch) {
+        SKEW_CUDA(cudaStreamWaitEvent(s, c->ev_chunks[ch], 0));
+        for (int64_t sp = 1; sp <= pairs; ++sp) {
+            long long lo, hi;
+            skew_region(n2, C, ch, sp, &lo, &hi);
+            if (hi <= lo) continue;
+            t.a.in = buf[(sp - 1) & 1];
+            t.a.out = buf[sp & 1];
+            t.a.k_begin = lo; t.a.k_end = hi;
+            int k = launch_jacobi_double_sweep(t, s);
+            if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; }
+            c->launches += k;
+            c->skew_launches += k;
+        }
+    }
+    SKEW_CUDA(cudaGetLastError());
+#undef SKEW_TRY
+#undef SKEW_CUDA
+    if (pairs & 1) { double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp; psi->parity ^= 1; }
+    return 2 * pairs;
+}
+
 extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64_t* n, const double* lo, const double* dx,
                                            int32_t ng, const rnmf_bc_face* faces, const double* psi_in, const double* rhs_in,
                                            int64_t n_sub_iter, int32_t mode, double* psi_out, double* l1_update)
@@ -1352,13 +1444,21 @@ extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64
     for (int d = 0; d < dim; ++d) { c->hp_psi->g.dx[d] = dx[d]; c->hp_psi->g.lo[d] = lo[d]; c->hp_rhs->g.dx[d] = dx[d]; c->hp_rhs->g.lo[d] = lo[d]; }
     rc = rnmf_frame_set_bc(c->hp_psi, faces, dim * 2);
     if (rc) return rc;
-    rc = rnmf_frame_upload(c->hp_psi, psi_in);
-    if (rc) return rc;
-    rc = rnmf_frame_upload(c->hp_rhs, rhs_in);
-    if (rc) return rc;
     double coef[4];
     rnmf_poisson_coefs(dim, dx, coef);
-    if (mode == 0) rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter, l1_update);
+    int64_t done = 0;
+    if (mode == 0 && c->e2e_skew) {
+        if (bind(c)) return RNMF_ERR_CUDA;
+        done = skewed_upload_and_first_sweeps(c, c->hp_psi, c->hp_rhs, psi_in, rhs_in, coef, n_sub_iter - (l1_update ? 1 : 0), &rc);
+        if (rc) return rc;
+    }
+    if (done == 0) {
+        rc = rnmf_frame_upload(c->hp_psi, psi_in);
+        if (rc) return rc;
+        rc = rnmf_frame_upload(c->hp_rhs, rhs_in);
+        if (rc) return rc;
+    }
+    if (mode == 0) rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter - done, l1_update);
     else { rc = rnmf_gs_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter); if (l1_update) *l1_update = 0.0; }
     if (rc) return rc;
     return rnmf_frame_download(c->hp_psi, psi_out);

@@ -208,6 +208,19 @@ inline unsigned peer_chunk_order(unsigned b, unsigned n)
 }
 #endif
 
+// Time-skewed start of rnmf_solve_poisson_host (capi.cu): the host frames arrive in C chunks of z-planes, chunk c
+// making valid planes < Z(c+1) = n2*(c+1)/C available (the last one also the top ghost plane).  Double sweep number
+// s = 1, 2, .. (u_{2s} from u_{2s-2}) needs its input two planes beyond its output, so what chunk c makes computable
+// is the band [max(0, Z(c)-2s), max(0, Z(c+1)-2s)) (the last chunk: up to n2): bands of equal s tile [0, n2), and
+// band (c, s) reads exactly what bands (<= c, s-1) wrote.  Ping-pong is safe: band (c, s+1) writes the buffer that
+// band (c+1, s) still reads, but only below plane Z(c+1)-2s-2, the lowest plane that read touches.
+inline void skew_region(long long n2, int n_chunks, int c, long long s, long long* lo, long long* hi)
+{
+    const long long zc = n2 * c / n_chunks - 2 * s, zn = n2 * (c + 1) / n_chunks - 2 * s;
+    *lo = c == 0 ? 0 : (zc > 0 ? zc : 0);
+    *hi = c == n_chunks - 1 ? n2 : (zn > 0 ? zn : 0);
+}
+
 struct SweepArgs {
     FrameGeom g;
     const double* in;
@@ -272,6 +285,7 @@ int launch_mul(long long n, const double* x, const double* y, double* out, cudaS
 int launch_axpby(long long n, double a, const double* x, double b, const double* y, double* out, cudaStream_t s);
 int launch_fill_synthetic(const FrameGeom& g, double* d, unsigned long long seed, cudaStream_t s);
 int launch_unpack_dense(const FrameGeom& g, const double* dense, double* frame, cudaStream_t s);
+int launch_unpack_dense_rows(const FrameGeom& g, const double* dense, double* frame, double* shell_dst, long long r0, long long r1, cudaStream_t s);
 int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s);
 int launch_unpack_valid(const FrameGeom& g, const double* packed, double* d, cudaStream_t s);
 

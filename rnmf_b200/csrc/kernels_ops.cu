@@ -92,6 +92,34 @@ __global__ void __launch_bounds__(256) unpack_dense_kernel(FrameGeom g, const do
     }
 }
 
+// ---- the same for grown rows [r0, r1) only (chunked upload, rnmf_solve_poisson_host); when `shell_dst` is given the
+// ghost shell of those rows (copy_ghost_shell_kernel's cells: face, edge and corner ghosts) also goes to the frame's
+// ping-pong partner, so no whole-frame shell copy is needed before the first sweeps
+__global__ void __launch_bounds__(256) unpack_dense_rows_kernel(FrameGeom g, const double* __restrict__ dense, double* __restrict__ frame,
+                                                                 double* __restrict__ shell_dst, long long r0, long long r1)
+{
+    const long long ng = g.ng;
+    for (long long r = r0 + blockIdx.x; r < r1; r += gridDim.x) {
+        const double* src = dense + r * g.G[0];
+        const long long base = g.xoff + g.pitch * r;
+        for (long long i = threadIdx.x; i < g.G[0]; i += blockDim.x) frame[base + i] = src[i];
+        if (shell_dst) {
+            const long long jj = r % g.G[1];
+            const long long kk = (r / g.G[1]) % g.G[2];
+            const bool j_out = jj < ng || jj >= g.n[1] + ng;
+            const bool k_out = g.dim == 3 && (kk < g.kg || kk >= g.n[2] + g.kg);
+            if (j_out || k_out) {
+                for (long long i = threadIdx.x; i < g.G[0]; i += blockDim.x) shell_dst[base + i] = src[i];
+            } else {
+                for (long long t = threadIdx.x; t < 2 * ng; t += blockDim.x) {
+                    const long long ii = t < ng ? t : g.n[0] + t;
+                    shell_dst[base + ii] = src[ii];
+                }
+            }
+        }
+    }
+}
+
 // ---- K5: sum |v| over valid cells (poisson.rs:94-100), deterministic two-stage tree ---------
 constexpr int kSumThreads = 256;
 __global__ void __launch_bounds__(kSumThreads) abs_sum_valid_kernel(FrameGeom g, const double* __restrict__ d,
@@ -240,6 +268,12 @@ int launch_fill_synthetic(const FrameGeom& g, double* d, unsigned long long seed
 int launch_unpack_dense(const FrameGeom& g, const double* dense, double* frame, cudaStream_t s)
 {
     unpack_dense_kernel<<<row_blocks(g.G[1] * g.G[2] * g.ncomp), 256, 0, s>>>(g, dense, frame);
+    return 1;
+}
+int launch_unpack_dense_rows(const FrameGeom& g, const double* dense, double* frame, double* shell_dst, long long r0, long long r1, cudaStream_t s)
+{
+    if (r1 <= r0) return 0;
+    unpack_dense_rows_kernel<<<row_blocks(r1 - r0), 256, 0, s>>>(g, dense, frame, shell_dst, r0, r1);
     return 1;
 }
 int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s)

@@ -1,10 +1,10 @@
 #!/bin/bash
 # First GPU call of the next round: the opt-in kernels that were written and emulator-checked without a GPU
-# (2D K-sweep kernel, variants 32..35; 3D two-rows-per-warp double sweep, variants 24/25): parity first, then
+# (2D K-sweep kernel, variants 32..35; 3D two-rows-per-warp double sweep, variants 24/25; time-skewed e2e start): parity first, then
 # short sustained benches per variant.  One GPU, about 8 minutes.  Results: gpurun_out/r2exp_*.json|log
 mkdir -p gpurun_out
 export RNMF_EXPERIMENTAL=1
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "multi_sweep or double_sweep" > gpurun_out/r2exp_pytest.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "multi_sweep or double_sweep or time_skewed" > gpurun_out/r2exp_pytest.log 2>&1
 echo "pytest rc=$?"; grep -v "^E  \|^$" gpurun_out/r2exp_pytest.log | tail -15
 unset RNMF_EXPERIMENTAL
 run() { name=$1; shift; timeout 200 "$@" > gpurun_out/r2exp_$name.json 2> gpurun_out/r2exp_$name.err; python -c "
@@ -25,3 +25,15 @@ S3="--workload 3d7_768 --steps 3 --warmup 3 --sub-iters 200 --no-e2e --no-cpu-ba
 run 3d_v0 python bench.py $S3
 run 3d_v24 python bench.py $S3 --variant 24
 run 3d_v25 python bench.py $S3 --variant 25
+# end to end with the time-skewed start (chunked upload overlapped with the first double sweeps): compare `e2e` of the two lines
+SE="--workload 3d7_768 --steps 2 --warmup 3 --sub-iters 550 --no-cpu-baseline --no-others"
+run 3d_e2e_plain python bench.py $SE
+RNMF_E2E_SKEW=1 run 3d_e2e_skew python bench.py $SE
+python - <<'PY'
+import json
+for n in ("3d_e2e_plain", "3d_e2e_skew"):
+    try:
+        d = json.load(open(f"gpurun_out/r2exp_{n}.json")); print(n, "value", round(d["value"], 1), "e2e", d["e2e"])
+    except Exception as e:
+        print(n, "failed", e)
+PY

@@ -8,6 +8,7 @@
 #include "emu_cuda.hpp"
 #include "../../rnmf_b200/csrc/tma_util.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 
@@ -197,6 +198,59 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
         f.cur ^= 1;
     }
     pack(f.g, f.buf[f.cur].data(), out_dense);
+    return g_deadlocks.load();
+}
+
+// The time-skewed start of rnmf_solve_poisson_host (capi.cu: skewed_upload_and_first_sweeps): the frame "arrives" in
+// n_chunks chunks of z-planes (planes that have not arrived yet hold poison); after every chunk the first `pairs` double
+// sweeps run on the bands skew_region() declares computable, ping-ponging between the two buffers.  At the end every
+// plane must hold u_{2*pairs}.  Returns deadlocks, or -1 on a launch failure.
+int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
+                             const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_chunks, int pairs)
+{
+    g_deadlocks = 0;
+    Frame f;
+    init_frame(f, 3, n, dx, psi_dense, rhs_dense);
+    const FrameGeom& g = f.g;
+    // nothing has arrived: poison all three buffers (init_frame filled them from the dense frames)
+    const std::vector<double> full_psi = f.buf[0], full_rhs = f.rhs;
+    std::fill(f.buf[0].begin(), f.buf[0].end(), -3.0e300);
+    std::fill(f.buf[1].begin(), f.buf[1].end(), 4.0e300);
+    std::fill(f.rhs.begin(), f.rhs.end(), 6.0e300);
+    Tb2Args t;
+    memset(&t, 0, sizeof(t));
+    t.a.g = g;
+    t.a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+    t.a.faces = make_faces(3, face_kind, face_value, dx);
+    t.a.fuse_fill = 1;
+    t.a.variant = variant;
+    t.a.chunk_override = chunk;
+    t.a.rhs = f.rhs.data();
+    const long long n2 = g.n[2];
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        // "upload" of chunk ch: grown planes [p0, p1) of psi (+ its ghost shell into the partner buffer) and of rhs
+        const long long p0 = ch == 0 ? 0 : n2 * ch / n_chunks + 1, p1 = ch == n_chunks - 1 ? g.G[2] : n2 * (ch + 1) / n_chunks + 1;
+        for (long long r = g.G[1] * p0; r < g.G[1] * p1; ++r) {
+            const long long jj = r % g.G[1], kk = r / g.G[1];
+            const bool shell_row = jj < 1 || jj >= g.n[1] + 1 || kk < 1 || kk >= n2 + 1;
+            for (long long i = 0; i < g.G[0]; ++i) {
+                const long long q = g.xoff + i + g.pitch * r;
+                f.buf[0][q] = full_psi[q];
+                f.rhs[q] = full_rhs[q];
+                if (shell_row || i < 1 || i >= g.n[0] + 1) f.buf[1][q] = full_psi[q];
+            }
+        }
+        for (long long sp = 1; sp <= pairs; ++sp) {
+            long long lo, hi;
+            skew_region(n2, n_chunks, ch, sp, &lo, &hi);
+            if (hi <= lo) continue;
+            t.a.in = f.buf[(sp - 1) & 1].data();
+            t.a.out = f.buf[sp & 1].data();
+            t.a.k_begin = lo; t.a.k_end = hi;
+            if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
+        }
+    }
+    pack(g, f.buf[pairs & 1].data(), out_dense);
     return g_deadlocks.load();
 }
 

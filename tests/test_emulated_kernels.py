@@ -146,3 +146,21 @@ def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pa
     rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, pairs, nranks)
     assert rc == 0, "deadlock / handshake timeout"
     np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("n,spec,n_chunks,pairs,chunk,variant", [
+    ([20, 9, 32], MIXED_3D, 2, 5, 0, 20),           # 16-plane chunks, bands shrink to nothing at the bottom (2*5 < 16)
+    ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 20),         # 8-plane chunks, more pairs than half a chunk: bands of chunk 0 vanish
+    ([130, 13, 20], MIXED_3D, 4, 3, 2, 20),         # two x tiles, two y tiles, several CTAs per band
+    ([20, 9, 24], MIXED_3D, 3, 4, 0, 24),           # two rows per row warp
+])
+def test_time_skewed_start_schedule_on_the_emulator(emu, n, spec, n_chunks, pairs, chunk, variant):
+    """The band schedule of the opt-in time-skewed start of rnmf_solve_poisson_host (skew_region, common.cuh): planes that have
+    not "arrived" hold poison, yet after the last chunk every plane equals 2*pairs oracle sweeps bit for bit -- no band reads
+    a plane before it exists or after the ping-pong partner overwrote it."""
+    hi = [1.0, 2.0, 3.0]
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=45)
+    out = np.zeros_like(psi)
+    rc = emu.emu_skewed_double_sweeps(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, n_chunks, pairs)
+    assert rc == 0, "deadlock or launch failure"
+    np.testing.assert_array_equal(out, want)

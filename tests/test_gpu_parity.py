@@ -545,6 +545,44 @@ def test_solve_poisson_host_entry_point(R, ctx):
     assert abs(l1.value - l1_ref) <= NORM_RTOL * l1_ref
 
 
+@pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in path: set RNMF_EXPERIMENTAL=1")
+@pytest.mark.parametrize("sweeps,chunks,pairs", [(41, 4, 10), (24, 8, 56), (9, 2, 4)])
+def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
+    """Option e2e_skew: chunked upload overlapped with the first double sweeps on the bands each chunk makes computable
+    (capi.cu: skewed_upload_and_first_sweeps).  Same kernels, same operations: bit-identical to the plain call; the launch
+    counter shows the skewed path really ran.  The frame is just over the 64 MB threshold of the path."""
+    from rnmf_b200 import _capi
+    from rnmf_b200.dataframe import _faces_array
+    n, hi = [254, 126, 260], [254.0, 126.0, 260.0]
+    _, bc = _bc_pair(R, 3, MIXED_3D)
+    faces = _faces_array(bc, 3, 1)
+    rng = np.random.default_rng(83)
+    G = (n[0] + 2) * (n[1] + 2) * (n[2] + 2)
+    psi0, rhs0 = rng.standard_normal(G), rng.standard_normal(G)
+    nn = (C.c_int64 * 3)(*n)
+    lo = (C.c_double * 3)(0.0, 0.0, 0.0)
+    dx = (C.c_double * 3)(1.0, 1.0, 1.0)
+    outs, norms, launches = [], [], []
+    try:
+        for skew in (0, 1):
+            ctx.set_option("e2e_skew", skew)
+            ctx.set_option("e2e_skew_chunks", chunks)
+            ctx.set_option("e2e_skew_pairs", pairs)
+            out = np.empty_like(psi0)
+            l1 = C.c_double()
+            k0 = ctx.kernel_launches
+            _capi.check(_capi.lib().rnmf_solve_poisson_host(ctx._h, 3, nn, lo, dx, 1, faces, psi0.ctypes.data, rhs0.ctypes.data,
+                                                            sweeps, 0, out.ctypes.data, C.byref(l1)))
+            launches.append(ctx.kernel_launches - k0)
+            outs.append(out)
+            norms.append(l1.value)
+    finally:
+        ctx.set_option("e2e_skew", 0)
+    np.testing.assert_array_equal(outs[1], outs[0])
+    assert norms[1] == norms[0]
+    assert launches[1] > launches[0] + chunks          # one band launch per (chunk, pair) instead of one launch per pair
+
+
 def test_kernel_launch_counter_moves(R, ctx):
     from rnmf_b200 import poisson
     g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, [32, 32, 32], [32.0] * 3, MIXED_3D, seed=91)
