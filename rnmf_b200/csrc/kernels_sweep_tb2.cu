@@ -140,7 +140,9 @@ __device__ __forceinline__ void load4(const double* q, double2& a, double2& b, c
 // One plane iteration of a row warp: level 1 of plane a+it (DO_L1) and level 2 of plane q = a+it-1 (DO_L2).
 // All shared-memory loads of both levels are issued behind ONE wait phase; level 2's x/y part is formed
 // before level 1's result exists (part2), its z term is added once u1 of plane a+it is known (fin2).
-template <int TY, int NS, bool DO_L1, bool DO_L2>
+// EDGE = false (interior-specialised kernels only): the warp owns no cell next to an x / y face, no cell past the frame, and the
+// iteration meets neither the z-lo face nor a slab neighbour -- the ghost code and the store masks are compiled out.
+template <int TY, int NS, bool DO_L1, bool DO_L2, bool EDGE = true>
 __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowSt& st, const int it)
 {
     using Cfg = Tb2Cfg<TY, NS>;
@@ -184,36 +186,36 @@ __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowS
         u1n_b.y = upd3(k.c0, k.c1, k.c2, k.c3, rc_b.y, e_b1, st.cur_b.x, n_b.y, s_b.y, above_b.y, st.below_b.y);
         // odd n0: the last valid cell is the first of a pair, whose E neighbour at level 2 is the pair's
         // second register: it must hold the x-hi ghost of u1, not a stencil value
-        if (k.xhi_sel == 0) u1n_a.y = ghost1(k.fx1, u1n_a.x);
-        if (k.xhi_sel == 2) u1n_b.y = ghost1(k.fx1, u1n_b.x);
+        if (EDGE && k.xhi_sel == 0) u1n_a.y = ghost1(k.fx1, u1n_a.x);
+        if (EDGE && k.xhi_sel == 2) u1n_b.y = ghost1(k.fx1, u1n_b.x);
 
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);              // this warp is done with the stage of plane a+it
         const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
-        sstore4(us, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        sstore4(us, u1n_a, u1n_b, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
         // what fill_bc gives u1 on the physical x / y faces (read by level 2 of the edge cells)
-        if (k.any_x) {
+        if (EDGE && k.any_x) {
             if (k.do_xlo) sts1(us - 8, ghost1(k.fx0, u1n_a.x));
             if (k.xhi_sel >= 0) {
                 const double m = k.xhi_sel == 0 ? u1n_a.x : k.xhi_sel == 1 ? u1n_a.y : k.xhi_sel == 2 ? u1n_b.x : u1n_b.y;
                 sts1(us + k.xhi_off, ghost1(k.fx1, m));
             }
         }
-        if (k.any_y) {
-            if (k.do_ylo) sstore4(us - BX * 8, ghost1(k.fy0, u1n_a), ghost1(k.fy0, u1n_b), k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (k.do_yhi) sstore4(us + BX * 8, ghost1(k.fy1, u1n_a), ghost1(k.fy1, u1n_b), k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE && k.any_y) {
+            if (k.do_ylo) sstore4(us - BX * 8, ghost1(k.fy0, u1n_a), ghost1(k.fy0, u1n_b), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.do_yhi) sstore4(us + BX * 8, ghost1(k.fy1, u1n_a), ghost1(k.fy1, u1n_b), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
         // slab neighbours get u1 of my boundary plane (half step) over NVLink
-        if (it == k.it_u1lo) store4(p.peer_u1_lo + k.xy_off, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
-        if (it == k.it_u1hi) store4(p.peer_u1_hi + k.xy_off, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE && it == k.it_u1lo) store4(p.peer_u1_lo + k.xy_off, u1n_a, u1n_b, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE && it == k.it_u1hi) store4(p.peer_u1_hi + k.xy_off, u1n_a, u1n_b, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
     }
     if (DO_L2) {
         // ---------------- level 2: u2 of plane q = a+it-1 ----------------
         // z neighbours of u1: registers, the face's ghost rule, or the neighbour slab's plane
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
-        const bool zlo = it == k.it_zlo;
+        const bool zlo = EDGE && it == k.it_zlo;
         if (zlo) {
             if (k.fz0.on) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
             else if (p.u1_in_lo) load4(p.u1_in_lo + k.xy_off, dn_a, dn_b, k);
@@ -229,25 +231,25 @@ __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowS
         nb.y = fin2(P_b.y, k.c3, up_b.y, dn_b.y);
 
         double* oa = st.oa;
-        store4(oa, na, nb, k.full, k.va0, k.va1, k.vb0, k.vb1);
-        if (k.any_x) {
+        store4(oa, na, nb, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE && k.any_x) {
             if (k.do_xlo) oa[-1] = ghost1(k.fx0, na.x);
             if (k.xhi_sel >= 0) {
                 const double m = k.xhi_sel == 0 ? na.x : k.xhi_sel == 1 ? na.y : k.xhi_sel == 2 ? nb.x : nb.y;
                 oa[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, m);
             }
         }
-        if (k.any_y) {
-            if (k.do_ylo) store4(oa - k.pitch, ghost1(k.fy0, na), ghost1(k.fy0, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (k.do_yhi) store4(oa + k.pitch, ghost1(k.fy1, na), ghost1(k.fy1, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE && k.any_y) {
+            if (k.do_ylo) store4(oa - k.pitch, ghost1(k.fy0, na), ghost1(k.fy0, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.do_yhi) store4(oa + k.pitch, ghost1(k.fy1, na), ghost1(k.fy1, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         if (zlo) {
-            if (k.fz0.on) store4(oa - k.plane_sz, ghost1(k.fz0, na), ghost1(k.fz0, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (p.peer_lo_plane) store4(p.peer_lo_plane + k.xy_off, na, nb, k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.fz0.on) store4(oa - k.plane_sz, ghost1(k.fz0, na), ghost1(k.fz0, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_lo_plane) store4(p.peer_lo_plane + k.xy_off, na, nb, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         if (!DO_L1) {
-            if (k.fz1.on) store4(oa + k.plane_sz, ghost1(k.fz1, na), ghost1(k.fz1, nb), k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (p.peer_hi_plane) store4(p.peer_hi_plane + k.xy_off, na, nb, k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.fz1.on) store4(oa + k.plane_sz, ghost1(k.fz1, na), ghost1(k.fz1, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_hi_plane) store4(p.peer_hi_plane + k.xy_off, na, nb, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         st.oa = oa + k.plane_sz;
     }
@@ -263,7 +265,8 @@ __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowS
     st.rp_a = rc_a; st.rp_b = rc_b;
 }
 
-template <int TY, int NS>
+// SPEC (variant 26, opt-in): row warps that own no face / ragged cell run an interior-only copy of the plane loop
+template <int TY, int NS, bool SPEC = false>
 __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __grid_constant__ CUtensorMap tm_u0,
                                                                          const __grid_constant__ CUtensorMap tm_rhs,
                                                                          const __grid_constant__ Tb2Params p)
@@ -433,6 +436,24 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
         // level 1 only: the planes before the chunk's first output plane; every plane for the halo rows
         const int n_l1_only = do_l2 ? it_l2_first : nL1;
         int it = 0;
+        // warp-uniform: the whole 128-cell row is valid and away from the x / y faces, and the chunk has no slab role
+        const bool interior = SPEC && row_ok && i0 + TX <= n0 && !(k.fx0.on && i0 == 0) && !(k.fx1.on && i0 + TX == n0) &&
+                              !k.any_y && !a_sync_lo && !a_sync_hi && !is_b;
+        if (SPEC && interior) {
+            for (; it < n_l1_only; ++it) row_iter<TY, NS, true, false, false>(p, k, st, it);
+            if (do_l2) {
+                // the first two-level iteration may meet the z-lo face: general code, once
+                if (it < nL1) { row_iter<TY, NS, true, true, true>(p, k, st, it); ++it; }
+                for (; it < nL1; it += 3) {
+                    row_iter<TY, NS, true, true, false>(p, k, st, it);
+                    if (it + 1 >= nL1) { ++it; break; }
+                    row_iter<TY, NS, true, true, false>(p, k, st, it + 1);
+                    if (it + 2 >= nL1) { it += 2; break; }
+                    row_iter<TY, NS, true, true, false>(p, k, st, it + 2);
+                }
+                if (top) row_iter<TY, NS, false, true>(p, k, st, nL1);
+            }
+        } else {
         for (; it < n_l1_only; ++it) row_iter<TY, NS, true, false>(p, k, st, it);
         if (do_l2) {
             // both levels; three plane iterations per trip so that the three-plane register windows rotate by renaming
@@ -444,6 +465,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
                 row_iter<TY, NS, true, true>(p, k, st, it + 2);
             }
             if (top) row_iter<TY, NS, false, true>(p, k, st, nL1);
+        }
         }
     }
     if (a_sync_lo || a_sync_hi || is_b) {
@@ -878,7 +900,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
     }
 }
 
-template <int TY, int NS>
+template <int TY, int NS, bool SPEC = false>
 struct Tb2Launcher {
     using Cfg = Tb2Cfg<TY, NS>;
     // chunk length: whole waves of one CTA per SM, each CTA paying chunk+3 plane iterations
@@ -929,11 +951,11 @@ struct Tb2Launcher {
 #ifndef RNMF_EMULATE
         static bool attr_set = false;
         if (!attr_set) {
-            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             attr_set = true;
         }
 #endif
-        RNMF_KERNEL_LAUNCH((jacobi3d_tb2_kernel<TY, NS>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
+        RNMF_KERNEL_LAUNCH((jacobi3d_tb2_kernel<TY, NS, SPEC>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
         return 1;
     }
 };
@@ -986,6 +1008,7 @@ int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
     case 21: return Tb2Launcher<8, 6>::launch(t, s);
     case 24: return Tb2xLauncher<12, 6, true>::launch(t, s);
     case 25: return Tb2xLauncher<16, 4, false>::launch(t, s);
+    case 26: return Tb2Launcher<12, 6, true>::launch(t, s);          // interior-specialised plane loop (opt-in)
     default: return Tb2Launcher<12, 6>::launch(t, s);
     }
 }

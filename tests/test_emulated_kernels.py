@@ -83,6 +83,11 @@ def _setup(n, hi, spec, sweeps, seed):
     ([129, 17, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 25, 0),
     ([65, 33, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 25, 2),
     ([30, 15, 2], [1.0, 1.0, 1.0], MIXED_3D, 1, 25, 0),
+    # variant 26: interior-specialised plane loop for the row warps of x-interior tiles (needs >= 3 tiles in x to have one)
+    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 26, 0),
+    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 26, 2),        # the last tile holds one column; two launches; 2-plane chunks
+    ([384, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 26, 3),          # x-hi face exactly at a tile edge
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 26, 2),        # no interior tile at all: the general loop only
 ])
 def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, variant, chunk):
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
@@ -137,6 +142,7 @@ def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk
     ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1, 20),        # 4-plane slabs (the minimum), one-plane A chunks
     ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 24),         # two rows per row warp
     ([20, 17, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 25),
+    ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 26),         # interior-specialised loop in the A chunks away from the neighbours
 ])
 def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk, variant):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial

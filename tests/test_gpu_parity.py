@@ -272,9 +272,9 @@ def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, vari
 
 
 ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
-# variants 24 / 25 (two rows per row warp) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
+# variants 24 / 25 (two rows per row warp) and 26 (interior-specialised plane loop) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
 # on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 adds them here
-_DOUBLE_SWEEP_VARIANTS = [20, 21] + ([24, 25] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
+_DOUBLE_SWEEP_VARIANTS = [20, 21] + ([24, 25, 26] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
@@ -287,6 +287,7 @@ _DOUBLE_SWEEP_VARIANTS = [20, 21] + ([24, 25] if os.environ.get("RNMF_EXPERIMENT
     ([127, 25, 1], [1.0, 2.0, 3.0], MIXED_3D, 4, False),          # a single plane: both z ghosts in registers
     ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 6, False),
     ([260, 30, 2], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 9, True),
+    ([520, 40, 70], [5.0, 2.0, 1.0], MIXED_3D, 6, False),         # five x tiles: three with no x face (variant 26's interior loop)
 ])
 @pytest.mark.parametrize("variant", _DOUBLE_SWEEP_VARIANTS)
 def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, variant):
