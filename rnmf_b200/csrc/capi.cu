@@ -34,7 +34,7 @@ extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
            "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "jacobi3d_tb2{128x12,128x8},jacobi3d_tb2x{128x12m,128x16},jacobi2d_tb2{512},jacobi2d_tbk{3x512,4x512,4x768,2x512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi3d_tb2{128x12,128x8},jacobi3d_tb2x{128x12m,128x16},jacobi3d_tb2s{128x12,128x12m},jacobi2d_tb2{512},jacobi2d_tbk{3x512,4x512,4x768,2x512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -927,7 +927,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     bool all_faces = true;
     for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
     // default (variant 0 = auto) for 3D; variant 6 = the single-sweep TMA kernel only
-    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21 || c->sweep_variant == 24 || c->sweep_variant == 25 || c->sweep_variant == 26);
+    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21 || c->sweep_variant == 24 || c->sweep_variant == 25 || c->sweep_variant == 26 || c->sweep_variant == 27);
     const bool tb2_single = tb2_variant && !dist && fused && all_faces;
     // slabs: the fused peer path with the in-kernel handshake; z faces are physical or a neighbour
     const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
@@ -1358,7 +1358,7 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
     for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
     const int v = c->sweep_variant;
     if (!c->e2e_skew || g.dim != 3 || g.ng != 1 || g.ncomp != 1 || c->nranks != 1 || !all_faces || C < 2 || n2 / C < 16 || pairs < 4 ||
-        dense * 8 < (64LL << 20) || !(v == 0 || v == 20 || v == 21 || v == 24 || v == 25 || v == 26))
+        dense * 8 < (64LL << 20) || !(v == 0 || v == 20 || v == 21 || v == 24 || v == 25 || v == 26 || v == 27))
         return 0;
     cudaStream_t s = c->stream, cs = c->stream_halo;
 #define SKEW_TRY(expr) do { int _rc = (expr); if (_rc) { *rc_out = _rc; return 0; } } while (0)

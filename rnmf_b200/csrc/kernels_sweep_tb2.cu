@@ -559,13 +559,15 @@ struct RowSt2 {
     uint32_t sc, sn, phn;
 };
 
+template <bool MASKED = true>
 __device__ __forceinline__ void st4g(double* a, const C4& v, const RowK2& k, int r)
 {
-    store4(a, v.a, v.b, k.ok[r] && k.xv3, k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
+    store4(a, v.a, v.b, !MASKED || (k.ok[r] && k.xv3), k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
 }
+template <bool MASKED = true>
 __device__ __forceinline__ void st4s(uint32_t a, const C4& v, const RowK2& k, int r)
 {
-    sstore4(a, v.a, v.b, k.ok[r] && k.xv3, k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
+    sstore4(a, v.a, v.b, !MASKED || (k.ok[r] && k.xv3), k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
 }
 __device__ __forceinline__ double xhi_pick(const C4& v, int sel) { return sel == 0 ? v.a.x : sel == 1 ? v.a.y : sel == 2 ? v.b.x : v.b.y; }
 __device__ __forceinline__ void ld4g(const double* q, C4& v, const RowK2& k, int r)
@@ -580,7 +582,8 @@ __device__ __forceinline__ void ld4g(const double* q, C4& v, const RowK2& k, int
 }
 
 // One plane iteration of a two-row warp (rows r0 = 2w and r0+1 of the tile): see row_iter for the protocol.
-template <int TY, int NS, bool DO_L1, bool DO_L2>
+// EDGE = false: interior-specialised copy (see row_iter)
+template <int TY, int NS, bool DO_L1, bool DO_L2, bool EDGE = true>
 __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, RowSt2& st, const int it)
 {
     using Cfg = Tb2Cfg<TY, NS>;
@@ -611,19 +614,21 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
         u1n[1] = upd3_4(k.c, rc[1], st.cur[1], e1, n1, st.cur[0], above[1], st.below[1]);
         // ghosts of u1 that level 2 takes from REGISTERS: odd n0 (E neighbour of the last valid cell is the pair's
         // second register) and the y-hi ghost row when the frame's last row is the warp's first row
+        if (EDGE) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (k.xhi_sel == 0) u1n[r].a.y = ghost1(k.fx1, u1n[r].a.x);
-            if (k.xhi_sel == 2) u1n[r].b.y = ghost1(k.fx1, u1n[r].b.x);
+            for (int r = 0; r < 2; ++r) {
+                if (k.xhi_sel == 0) u1n[r].a.y = ghost1(k.fx1, u1n[r].a.x);
+                if (k.xhi_sel == 2) u1n[r].b.y = ghost1(k.fx1, u1n[r].b.x);
+            }
+            if (k.yhi_row == 0) u1n[1] = ghost4(k.fy1, u1n[0]);
         }
-        if (k.yhi_row == 0) u1n[1] = ghost4(k.fy1, u1n[0]);
 
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
         const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
-        st4s(us, u1n[0], k, 0);
-        st4s(us + RB, u1n[1], k, 1);
-        if (k.any_x) {
+        st4s<EDGE>(us, u1n[0], k, 0);
+        st4s<EDGE>(us + RB, u1n[1], k, 1);
+        if (EDGE && k.any_x) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
                 if (k.ok[r]) {
@@ -631,17 +636,17 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
                     if (k.xhi_sel >= 0) sts1(us + r * RB + k.xhi_off, ghost1(k.fx1, xhi_pick(u1n[r], k.xhi_sel)));
                 }
         }
-        if (k.do_ylo) st4s(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
-        if (k.yhi_row == 1) st4s(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
+        if (EDGE && k.do_ylo) st4s(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
+        if (EDGE && k.yhi_row == 1) st4s(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
-        if (it == k.it_u1lo) { st4g(p.peer_u1_lo + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_lo + k.xy_off + k.pitch, u1n[1], k, 1); }
-        if (it == k.it_u1hi) { st4g(p.peer_u1_hi + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_hi + k.xy_off + k.pitch, u1n[1], k, 1); }
+        if (EDGE && it == k.it_u1lo) { st4g(p.peer_u1_lo + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_lo + k.xy_off + k.pitch, u1n[1], k, 1); }
+        if (EDGE && it == k.it_u1hi) { st4g(p.peer_u1_hi + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_hi + k.xy_off + k.pitch, u1n[1], k, 1); }
     }
     if (DO_L2) {
         // ---------------- level 2: u2 of plane q = a+it-1, both rows ----------------
         C4 dn[2] = { st.u1lo[0], st.u1lo[1] }, upv[2] = { u1n[0], u1n[1] };
-        const bool zlo = it == k.it_zlo;
+        const bool zlo = EDGE && it == k.it_zlo;
         if (zlo) {
             if (k.fz0.on) { dn[0] = ghost4(k.fz0, st.u1c[0]); dn[1] = ghost4(k.fz0, st.u1c[1]); }
             else if (p.u1_in_lo) { ld4g(p.u1_in_lo + k.xy_off, dn[0], k, 0); ld4g(p.u1_in_lo + k.xy_off + k.pitch, dn[1], k, 1); }
@@ -655,13 +660,13 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
         for (int r = 0; r < 2; ++r) {
             const C4 u2 = fin2_4(P[r], k.c.c3, upv[r], dn[r]);
             double* o = oa + r * k.pitch;
-            st4g(o, u2, k, r);
-            if (k.any_x && k.ok[r]) {
+            st4g<EDGE>(o, u2, k, r);
+            if (EDGE && k.any_x && k.ok[r]) {
                 if (k.do_xlo) o[-1] = ghost1(k.fx0, u2.a.x);
                 if (k.xhi_sel >= 0) o[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, xhi_pick(u2, k.xhi_sel));
             }
-            if (r == 0 && k.do_ylo) st4g(o - k.pitch, ghost4(k.fy0, u2), k, 0);
-            if (k.yhi_row == r) st4g(o + k.pitch, ghost4(k.fy1, u2), k, r);
+            if (EDGE && r == 0 && k.do_ylo) st4g(o - k.pitch, ghost4(k.fy0, u2), k, 0);
+            if (EDGE && k.yhi_row == r) st4g(o + k.pitch, ghost4(k.fy1, u2), k, r);
             if (zlo) {
                 if (k.fz0.on) st4g(o - k.plane_sz, ghost4(k.fz0, u2), k, r);
                 if (p.peer_lo_plane) st4g(p.peer_lo_plane + k.xy_off + r * k.pitch, u2, k, r);
@@ -684,7 +689,7 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
     st.rp[0] = rc[0]; st.rp[1] = rc[1];
 }
 
-template <int TY, int NS, bool MERGE>
+template <int TY, int NS, bool MERGE, bool SPEC = false>
 __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_tb2x_kernel(const __grid_constant__ CUtensorMap tm_u0,
                                                                                            const __grid_constant__ CUtensorMap tm_rhs,
                                                                                            const __grid_constant__ Tb2Params p)
@@ -877,6 +882,21 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         st.sc = 1; st.sn = 2; st.phn = 0;
 
         int it = 0;
+        // warp-uniform: both rows are whole rows of the frame away from the x / y faces, and the chunk has no slab role
+        const bool interior = SPEC && k.ok[1] && i0 + TX <= n0 && !(k.fx0.on && i0 == 0) && !(k.fx1.on && i0 + TX == n0) &&
+                              !k.do_ylo && k.yhi_row < 0 && !a_sync_lo && !a_sync_hi && !is_b;
+        if (SPEC && interior) {
+            for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, false>(p, k, st, it);
+            // the first two-level iteration may meet the z-lo face: general code, once
+            if (it < nL1) { row2_iter<TY, NS, true, true, true>(p, k, st, it); ++it; }
+            for (; it < nL1; it += 3) {
+                row2_iter<TY, NS, true, true, false>(p, k, st, it);
+                if (it + 1 >= nL1) break;
+                row2_iter<TY, NS, true, true, false>(p, k, st, it + 1);
+                if (it + 2 >= nL1) break;
+                row2_iter<TY, NS, true, true, false>(p, k, st, it + 2);
+            }
+        } else {
         for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false>(p, k, st, it);
         for (; it < nL1; it += 3) {
             row2_iter<TY, NS, true, true>(p, k, st, it);
@@ -884,6 +904,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
             row2_iter<TY, NS, true, true>(p, k, st, it + 1);
             if (it + 2 >= nL1) break;
             row2_iter<TY, NS, true, true>(p, k, st, it + 2);
+        }
         }
         if (top) row2_iter<TY, NS, false, true>(p, k, st, nL1);
     }
@@ -961,7 +982,7 @@ struct Tb2Launcher {
 };
 
 // two rows per row warp: same tiling / planner as Tb2Launcher<TY, NS>, its own kernel and thread count
-template <int TY, int NS, bool MERGE>
+template <int TY, int NS, bool MERGE, bool SPEC = false>
 struct Tb2xLauncher {
     using Cfg = Tb2xCfg<TY, NS, MERGE>;
     static int launch(const Tb2Args& t, cudaStream_t s)
@@ -987,11 +1008,11 @@ struct Tb2xLauncher {
 #ifndef RNMF_EMULATE
         static bool attr_set = false;
         if (!attr_set) {
-            if (cudaFuncSetAttribute(jacobi3d_tb2x_kernel<TY, NS, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             attr_set = true;
         }
 #endif
-        RNMF_KERNEL_LAUNCH((jacobi3d_tb2x_kernel<TY, NS, MERGE>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
+        RNMF_KERNEL_LAUNCH((jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
         return 1;
     }
 };
@@ -1009,6 +1030,7 @@ int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
     case 24: return Tb2xLauncher<12, 6, true>::launch(t, s);
     case 25: return Tb2xLauncher<16, 4, false>::launch(t, s);
     case 26: return Tb2Launcher<12, 6, true>::launch(t, s);          // interior-specialised plane loop (opt-in)
+    case 27: return Tb2xLauncher<12, 6, true, true>::launch(t, s);   // two rows per warp + interior-specialised loop (opt-in)
     default: return Tb2Launcher<12, 6>::launch(t, s);
     }
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: the opt-in kernels that were written and emulator-checked without a GPU
-# (2D K-sweep kernel, variants 32..35; 3D two-rows-per-warp double sweep, variants 24/25; time-skewed e2e start): parity first, then
+# (2D K-sweep kernel, variants 32..35; 3D two-rows-per-warp double sweep, variants 24/25, interior-specialised loops, variants 26/27; time-skewed e2e start): parity first, then
 # short sustained benches per variant.  One GPU, about 8 minutes.  Results: gpurun_out/r2exp_*.json|log
 mkdir -p gpurun_out
 export RNMF_EXPERIMENTAL=1
@@ -26,6 +26,7 @@ run 3d_v0 python bench.py $S3
 run 3d_v24 python bench.py $S3 --variant 24
 run 3d_v25 python bench.py $S3 --variant 25
 run 3d_v26 python bench.py $S3 --variant 26
+run 3d_v27 python bench.py $S3 --variant 27
 # end to end with the time-skewed start (chunked upload overlapped with the first double sweeps): compare `e2e` of the two lines
 SE="--workload 3d7_768 --steps 2 --warmup 3 --sub-iters 550 --no-cpu-baseline --no-others"
 run 3d_e2e_plain python bench.py $SE

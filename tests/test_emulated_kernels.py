@@ -88,6 +88,10 @@ def _setup(n, hi, spec, sweeps, seed):
     ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 26, 2),        # the last tile holds one column; two launches; 2-plane chunks
     ([384, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 26, 3),          # x-hi face exactly at a tile edge
     ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 26, 2),        # no interior tile at all: the general loop only
+    # variant 27: two rows per row warp + the interior-specialised loop
+    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 27, 0),
+    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 27, 2),
+    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 27, 3),          # odd n1: the frame's last row is a warp's first row (not interior)
 ])
 def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, variant, chunk):
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
@@ -143,6 +147,7 @@ def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk
     ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 24),         # two rows per row warp
     ([20, 17, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 25),
     ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 26),         # interior-specialised loop in the A chunks away from the neighbours
+    ([390, 14, 13], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 2, 27),
 ])
 def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk, variant):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial
