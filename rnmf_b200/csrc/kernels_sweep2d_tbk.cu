@@ -35,7 +35,11 @@ struct TbkParams {
     int chunk;
 };
 
-template <int K, int NW, int NS>
+// DI: ring rows are stored de-interleaved -- even positions first, odd positions from ODD_OFF -- so that the E/W loads
+// (the pair's left neighbour is an odd position, its right neighbour an even one) are dense 8-byte accesses, two
+// shared-memory wavefronts per warp instead of the four that 8-byte accesses 16 bytes apart cost; the pair stores
+// become two dense 8-byte stores each (the same four wavefronts as one 16-byte store)
+template <int K, int NW, int NS, bool DI = false>
 struct CfgK {
     static constexpr int PAD = (K + 1) & ~1;               // even (pairs stay 16-byte aligned in a staged row), >= K
     static constexpr int TXC = 128 * NW;
@@ -43,8 +47,10 @@ struct CfgK {
     static constexpr int ROW_BYTES = ROW * 8;
     static constexpr int STAGE = (ROW_BYTES + 127) / 128 * 128;
     static constexpr int RHS_OFF = NS * STAGE;
-    static constexpr int RING_OFF = 2 * NS * STAGE;        // ring of level s (1..K-1), slot t: RING_OFF + (2(s-1)+t)*STAGE
-    static constexpr int BAR_OFF = RING_OFF + 2 * (K - 1) * STAGE;
+    static constexpr int ODD_OFF = (ROW / 2 * 8 + 127) / 128 * 128;     // DI: byte offset of the odd positions in a ring row
+    static constexpr int RSLOT = DI ? 2 * ODD_OFF : STAGE;              // bytes per ring slot
+    static constexpr int RING_OFF = 2 * NS * STAGE;        // ring of level s (1..K-1), slot t: RING_OFF + (2(s-1)+t)*RSLOT
+    static constexpr int BAR_OFF = RING_OFF + 2 * (K - 1) * RSLOT;
     static constexpr int SMEM = BAR_OFF + (2 * NS + 2) * 8 + 128;
     static constexpr int NCONS = NW + 1;                   // + the halo-column warp
     static constexpr int THREADS = 32 * (NW + 2);
@@ -92,7 +98,7 @@ struct LaneK {
     bool full, va0, va1, vb0, vb1;
     bool do_xlo, any_x;
     int xhi_sel;
-    uint32_t xhi_off;
+    uint32_t xhi_off, xlo_off;      // ring-row offsets of the x-hi / x-lo ghost from the lane's first cell
     Face1 fx0, fx1, fy0, fy1;
     long long pitch;
     int lane;
@@ -106,6 +112,30 @@ struct StateK {
     double* oa;
     uint32_t sc, sn, phn;
 };
+
+// ---- ring rows: position q = column - i0 + PAD ----
+template <class Cfg, bool DI>
+__device__ __forceinline__ uint32_t ring_pos(int q) { return DI ? (uint32_t)((q & 1) * Cfg::ODD_OFF + (q >> 1) * 8) : (uint32_t)(q * 8); }
+// E/W neighbours of the lane's two pairs in the ring row where the lane's first cell sits at `u`
+template <class Cfg, bool DI>
+__device__ __forceinline__ void ring_ld_ew(uint32_t u, double& w_a, double& e_a, double& w_b, double& e_b)
+{
+    if (DI) { w_a = lds1(u + Cfg::ODD_OFF - 8); e_a = lds1(u + 8); w_b = lds1(u + Cfg::ODD_OFF + 256 - 8); e_b = lds1(u + 256 + 8); }
+    else { w_a = lds1(u - 8); e_a = lds1(u + 16); w_b = lds1(u + 512 - 8); e_b = lds1(u + 512 + 16); }
+}
+template <class Cfg, bool DI>
+__device__ __forceinline__ void ring_st4(uint32_t u, const double2& va, const double2& vb, bool full, bool a0, bool a1, bool b0, bool b1)
+{
+    if (!DI) { sstore4(u, va, vb, full, a0, a1, b0, b1); return; }
+    if (full) {
+        sts1(u, va.x); sts1(u + Cfg::ODD_OFF, va.y); sts1(u + 256, vb.x); sts1(u + Cfg::ODD_OFF + 256, vb.y);
+    } else {
+        if (a0) sts1(u, va.x);
+        if (a1) sts1(u + Cfg::ODD_OFF, va.y);
+        if (b0) sts1(u + 256, vb.x);
+        if (b1) sts1(u + Cfg::ODD_OFF + 256, vb.y);
+    }
+}
 
 // poisson.rs:83-85: (c0*r + c1*(e+w)) + c2*(n+s); p0 = c0*r is rounded once per cell and row and reused by every
 // level (the same IEEE operation on the same operands, so the result is the reference's)
@@ -121,7 +151,7 @@ __device__ __forceinline__ double2 mul2(double c, const double2& v) { return mak
 template <int K>
 __device__ __forceinline__ void xface_ring(const LaneK<K>& k, uint32_t us, double2& v_a, double2& v_b)
 {
-    if (k.do_xlo) sts1(us - 8, ghost1(k.fx0, v_a.x));
+    if (k.do_xlo) sts1(us + k.xlo_off, ghost1(k.fx0, v_a.x));
     if (k.xhi_sel >= 0) {
         const double m = k.xhi_sel == 0 ? v_a.x : k.xhi_sel == 1 ? v_a.y : k.xhi_sel == 2 ? v_b.x : v_b.y;
         const double gv = ghost1(k.fx1, m);
@@ -133,10 +163,10 @@ __device__ __forceinline__ void xface_ring(const LaneK<K>& k, uint32_t us, doubl
 
 // XF: an edge warp -- it owns a cell next to an x face, or columns past the frame (masked stores).  Warp-uniform, so
 // the ghost code and the store masks are compiled out of the other warps' loop.
-template <int K, int NW, int NS, bool STEADY, bool XF>
+template <int K, int NW, int NS, bool DI, bool STEADY, bool XF>
 __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, const int it)
 {
-    using Cfg = CfgK<K, NW, NS>;
+    using Cfg = CfgK<K, NW, NS, DI>;
     const double2 zero2 = make_double2(0.0, 0.0);
     const bool act1 = STEADY || it <= k.lp.last[0];
 
@@ -144,16 +174,15 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
     if (it >= 1) mbar_wait(k.ufull0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
 
     // ---- every shared-memory load of the iteration, issued together ----
-    const uint32_t pslot = (uint32_t)((it - 1) & 1) * Cfg::STAGE, slot = (uint32_t)(it & 1) * Cfg::STAGE;
+    const uint32_t pslot = (uint32_t)((it - 1) & 1) * Cfg::RSLOT, slot = (uint32_t)(it & 1) * Cfg::RSLOT;
     double uw_a[K - 1], ue_a[K - 1], uw_b[K - 1], ue_b[K - 1];      // [s-1]: E/W of the row level s formed in the previous iteration
 #pragma unroll
     for (int s = 1; s < K; ++s) {
         const bool act = STEADY || (it >= k.lp.first[s] && it <= k.lp.last[s]);       // level s+1
         uw_a[s - 1] = ue_a[s - 1] = uw_b[s - 1] = ue_b[s - 1] = 0.0;
         if (act) {
-            const uint32_t up = k.ua + (uint32_t)(2 * (s - 1)) * Cfg::STAGE + pslot;
-            uw_a[s - 1] = lds1(up - 8); ue_a[s - 1] = lds1(up + 16);
-            uw_b[s - 1] = lds1(up + 512 - 8); ue_b[s - 1] = lds1(up + 512 + 16);
+            const uint32_t up = k.ua + (uint32_t)(2 * (s - 1)) * Cfg::RSLOT + pslot;
+            ring_ld_ew<Cfg, DI>(up, uw_a[s - 1], ue_a[s - 1], uw_b[s - 1], ue_b[s - 1]);
         }
     }
     double2 above_a = zero2, above_b = zero2, rc_a = zero2, rc_b = zero2, f_a = zero2, f_b = zero2;
@@ -172,7 +201,7 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
         const uint32_t us = k.ua + slot;
-        sstore4(us, f_a, f_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        ring_st4<Cfg, DI>(us, f_a, f_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
         if (XF && k.any_x) xface_ring(k, us, f_a, f_b);
     }
 
@@ -196,8 +225,8 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
             o_b.x = updk(k.c1, k.c2, r_b.x, ce_b.y, uw_b[s - 1], up_b.x, dn_b.x);
             o_b.y = updk(k.c1, k.c2, r_b.y, ue_b[s - 1], ce_b.x, up_b.y, dn_b.y);
             if (l < K) {
-                const uint32_t us = k.ua + (uint32_t)(2 * (l - 1)) * Cfg::STAGE + slot;
-                sstore4(us, o_a, o_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+                const uint32_t us = k.ua + (uint32_t)(2 * (l - 1)) * Cfg::RSLOT + slot;
+                ring_st4<Cfg, DI>(us, o_a, o_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
                 if (XF && k.any_x) xface_ring(k, us, o_a, o_b);
             } else {
                 double* oa = st.oa;
@@ -239,28 +268,28 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
 
 // the iterations of a chunk: ramp-up (levels start one after the other, y-lo faces), the steady part unrolled by
 // three (the three-row windows rotate by renaming), drain (y-hi faces)
-template <int K, int NW, int NS, bool XF>
+template <int K, int NW, int NS, bool DI, bool XF>
 __device__ __forceinline__ void rowk_chunk(const LaneK<K>& k, StateK<K>& st)
 {
     int it = 0;
-    for (; it < k.lp.s0 && it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, false, XF>(k, st, it);
+    for (; it < k.lp.s0 && it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, DI, false, XF>(k, st, it);
     for (; it + 2 <= k.lp.s1; it += 3) {
-        rowk_iter<K, NW, NS, true, XF>(k, st, it);
-        rowk_iter<K, NW, NS, true, XF>(k, st, it + 1);
-        rowk_iter<K, NW, NS, true, XF>(k, st, it + 2);
+        rowk_iter<K, NW, NS, DI, true, XF>(k, st, it);
+        rowk_iter<K, NW, NS, DI, true, XF>(k, st, it + 1);
+        rowk_iter<K, NW, NS, DI, true, XF>(k, st, it + 2);
     }
-    for (; it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, false, XF>(k, st, it);
+    for (; it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, DI, false, XF>(k, st, it);
 }
 
-template <int K, int NW, int NS, int MINB>
+template <int K, int NW, int NS, int MINB, bool DI>
 __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const __grid_constant__ CUtensorMap tm_u256,
                                                                              const __grid_constant__ CUtensorMap tm_upad,
                                                                              const __grid_constant__ CUtensorMap tm_r256,
                                                                              const __grid_constant__ CUtensorMap tm_rpad,
                                                                              const __grid_constant__ TbkParams p)
 {
-    using Cfg = CfgK<K, NW, NS>;
-    constexpr int PAD = Cfg::PAD, TXC = Cfg::TXC, STAGE = Cfg::STAGE;
+    using Cfg = CfgK<K, NW, NS, DI>;
+    constexpr int PAD = Cfg::PAD, TXC = Cfg::TXC, STAGE = Cfg::STAGE, RSLOT = Cfg::RSLOT;
     RNMF_DYNAMIC_SMEM(smem_raw);
     const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, ring_0 = sb + Cfg::RING_OFF;
@@ -333,7 +362,9 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         const Face1 fx1 = make_face1(p.faces.f[1], true), fy0 = make_face1(p.faces.f[2], true), fy1 = make_face1(p.faces.f[3], true);
         const bool xhi = ok && fx1.on && i == n0 - 1;         // the x-hi ghost of my level sits right of my column
         const uint32_t off = (uint32_t)((col + PAD) * 8);
-        const uint32_t hp = u0_0 + off, hr = rhs_0 + off, hu = ring_0 + off;
+        const uint32_t hp = u0_0 + off, hr = rhs_0 + off;
+        // my column and its two neighbours in a ring row
+        const uint32_t hu = ring_0 + ring_pos<Cfg, DI>(col + PAD), hue = ring_0 + ring_pos<Cfg, DI>(col + PAD + 1), huw = ring_0 + ring_pos<Cfg, DI>(col + PAD - 1);
         double below = 0.0, cur = 0.0, wlo = 0.0, wc = 0.0;
         double q[K - 1];
 #pragma unroll
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
             const bool act1 = it <= lp.last[0];
             if (act1) mbar_wait(full0 + 8 * sn, phn);
             if (it >= 1) mbar_wait(ufull0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
-            const uint32_t pslot = (uint32_t)((it - 1) & 1) * STAGE, slot = (uint32_t)(it & 1) * STAGE;
+            const uint32_t pslot = (uint32_t)((it - 1) & 1) * RSLOT, slot = (uint32_t)(it & 1) * RSLOT;
             double rr = 0.0, above = 0.0;
             if (act1) {
                 rr = __dmul_rn(c0, lds1(hr + sc * STAGE));
@@ -360,7 +391,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
                     const double v = updk(c1, c2, rr, ee, ww, above, below);
                     if (ok) {
                         sts1(hu + slot, v);
-                        if (xhi) sts1(hu + slot + 8, ghost1(fx1, v));
+                        if (xhi) sts1(hue + slot, ghost1(fx1, v));
                     }
                 }
             }
@@ -371,19 +402,19 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
                 const bool actl = it >= lp.first[l - 1] && it <= lp.last[l - 1];
                 const bool actp = it >= lp.first[l - 2] && it <= lp.last[l - 2];   // level l-1 stored a row in this iteration
                 if (L == l) {
-                    const uint32_t src = hu + (uint32_t)(2 * (l - 2)) * STAGE;
+                    const uint32_t lsrc = (uint32_t)(2 * (l - 2)) * RSLOT;
                     double fresh = 0.0;
-                    if (actp && ok) fresh = lds1(src + slot);
+                    if (actp && ok) fresh = lds1(hu + lsrc + slot);
                     if (actl) {
                         double dn = wlo, up = fresh;
                         if (it == lp.it_ylo[l - 1]) dn = ghost1(fy0, wc);
                         if (it == lp.it_yhi[l - 1]) up = ghost1(fy1, wc);
-                        const double ee = lds1(src + pslot + 8), ww = lds1(src + pslot - 8);
+                        const double ee = lds1(hue + lsrc + pslot), ww = lds1(huw + lsrc + pslot);
                         const double v = updk(c1, c2, q[l - 2], ee, ww, up, dn);
                         if (ok) {
-                            const uint32_t dst = hu + (uint32_t)(2 * (l - 1)) * STAGE + slot;
-                            sts1(dst, v);
-                            if (xhi) sts1(dst + 8, ghost1(fx1, v));
+                            const uint32_t ldst = (uint32_t)(2 * (l - 1)) * RSLOT + slot;
+                            sts1(hu + ldst, v);
+                            if (xhi) sts1(hue + ldst, ghost1(fx1, v));
                         }
                     }
                     if (actp) { wlo = wc; wc = fresh; }
@@ -410,7 +441,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         k.full = k.vb1;
         // column c of the strip sits at (c+PAD)*8 in a staged u0 / rhs row and in a ring slot
         const uint32_t off = (uint32_t)((128 * warp + PAD + 2 * lane) * 8);
-        k.pa = u0_0 + off; k.ra = rhs_0 + off; k.ua = ring_0 + off;
+        k.pa = u0_0 + off; k.ra = rhs_0 + off; k.ua = ring_0 + ring_pos<Cfg, DI>(128 * warp + PAD + 2 * lane);
         k.full0 = full0; k.empty0 = empty0; k.ufull0 = ufull0;
         k.c0 = p.c.c0; k.c1 = p.c.c1; k.c2 = p.c.c2;
         k.pitch = p.g.pitch;
@@ -420,7 +451,10 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         k.do_xlo = k.fx0.on && k.va0 && ia == 0;
         const long long last = n0 - 1;
         k.xhi_sel = !k.fx1.on ? -1 : (k.va0 && ia == last) ? 0 : (k.va1 && ia + 1 == last) ? 1 : (k.vb0 && ib == last) ? 2 : (k.vb1 && ib + 1 == last) ? 3 : -1;
-        k.xhi_off = (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        // the x-hi ghost sits one position right of the last valid cell, the x-lo ghost one left of the lane's first cell
+        k.xhi_off = DI ? (uint32_t)((k.xhi_sel >= 2 ? 256 : 0) + ((k.xhi_sel & 1) ? 8 : Cfg::ODD_OFF))
+                       : (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        k.xlo_off = DI ? (uint32_t)(Cfg::ODD_OFF - 8) : (uint32_t)-8;
         k.any_x = k.do_xlo || k.xhi_sel >= 0;
         k.lp = lp;
 
@@ -443,15 +477,15 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         // warp-uniform: does this warp's 128-column span touch an x face or reach past the frame?
         const long long w0 = i0 + 128 * warp;
         const bool warp_x = (k.fx0.on && w0 == 0) || (k.fx1.on && last >= w0 && last < w0 + 128) || w0 + 128 > n0;
-        if (warp_x) rowk_chunk<K, NW, NS, true>(k, st);
-        else rowk_chunk<K, NW, NS, false>(k, st);
+        if (warp_x) rowk_chunk<K, NW, NS, DI, true>(k, st);
+        else rowk_chunk<K, NW, NS, DI, false>(k, st);
     }
 }
 
-template <int K, int NW, int NS, int MINB>
+template <int K, int NW, int NS, int MINB, bool DI = false>
 int launch_tbk(const SweepArgs& a, cudaStream_t s)
 {
-    using Cfg = CfgK<K, NW, NS>;
+    using Cfg = CfgK<K, NW, NS, DI>;
     const FrameGeom& g = a.g;
     const long long span = a.k_end - a.k_begin;
     const long long bx = (g.n[0] + Cfg::TXC - 1) / Cfg::TXC;
@@ -481,7 +515,7 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
     TbkParams p;
     p.g = g; p.out = a.out; p.c = a.c; p.faces = a.faces;
     p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = (int)best_c;
-    auto kern = jacobi2d_tbk_kernel<K, NW, NS, MINB>;
+    auto kern = jacobi2d_tbk_kernel<K, NW, NS, MINB, DI>;
 #ifndef RNMF_EMULATE
     static bool attr_set = false;                      // one per instantiation
     if (!attr_set) {
@@ -499,13 +533,14 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
 // sweeps per launch of a 2D sweep variant (0: the variant is not a K-sweep variant)
 int multi_sweep_2d_depth(int variant)
 {
-    return variant == 32 ? 3 : variant == 33 || variant == 34 ? 4 : variant == 35 ? 2 : 0;
+    return variant == 32 || variant == 36 ? 3 : variant == 33 || variant == 34 || variant == 37 ? 4 : variant == 35 ? 2 : 0;
 }
 
 // K sweeps (+ ghost fills) per launch, a.k_begin..a.k_end = output rows; every x / y face must carry a
 // Dirichlet or Neumann rule (the caller checks).  Variants: 32 = three sweeps, 512-column strips, two CTAs per SM;
 // 33 = four sweeps, same shape; 34 = four sweeps, 768-column strips (8 warps), one CTA per SM (255 registers);
-// 35 = two sweeps through this kernel (cross-check against kernels_sweep2d_tb2.cu).
+// 35 = two sweeps through this kernel (cross-check against kernels_sweep2d_tb2.cu); 36 / 37 = 32 / 34 with de-interleaved
+// ring rows (dense E/W loads).
 int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
@@ -514,6 +549,8 @@ int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
     case 33: return launch_tbk<4, 4, 8, 2>(a, s);
     case 34: return launch_tbk<4, 6, 8, 1>(a, s);
     case 35: return launch_tbk<2, 4, 10, 2>(a, s);
+    case 36: return launch_tbk<3, 4, 8, 2, true>(a, s);      // 32 with de-interleaved ring rows
+    case 37: return launch_tbk<4, 6, 8, 1, true>(a, s);      // 34 with de-interleaved ring rows
     default: return -1;
     }
 }

@@ -20,6 +20,8 @@ run 2d_v34_k4w python bench.py $S2 --variant 34
 run 2d_v34_k4w_c128 python bench.py $S2 --variant 34 --chunk 128
 run 2d_v34_k4w_c512 python bench.py $S2 --variant 34 --chunk 512
 run 2d_v32_k3_c128 python bench.py $S2 --variant 32 --chunk 128
+run 2d_v36_k3_di python bench.py $S2 --variant 36
+run 2d_v37_k4w_di python bench.py $S2 --variant 37
 # 3D 768^3
 S3="--workload 3d7_768 --steps 3 --warmup 3 --sub-iters 200 --no-e2e --no-cpu-baseline --no-others"
 run 3d_v0 python bench.py $S3

@@ -77,6 +77,60 @@ struct Cta {
 
 inline thread_local Cta* g_cta = nullptr;
 inline thread_local int g_warp = 0;
+inline thread_local int g_lane = 0;
+inline thread_local unsigned g_seq = 0;           // shared-memory accesses this thread has made in its CTA (trace key)
+
+// ---- optional shared-memory wavefront accounting (a STATIC bank model, not a timing model) ---------------
+// With tracing on, every ld/st.shared of a warp is keyed by the issuing lane's access count; lanes of a converged
+// warp agree on it, so one key = one warp instruction.  Its cost is the classic bank model: 32 banks of 4 bytes, a
+// warp instruction is served in passes of 32 / 16 / 8 lanes for 4- / 8- / 16-byte accesses, and a pass needs as many
+// wavefronts as the largest number of distinct 128-byte rows any bank is asked for.  (Divergent lanes -- the few
+// face / ragged lanes -- shift their keys and are mis-grouped; use frames where interior warps dominate.)
+struct Access { uint32_t addr; unsigned char lane, bytes, store; };
+inline std::atomic<bool> g_trace{false};
+inline std::mutex g_trace_mu;
+inline std::map<std::pair<int, unsigned>, std::vector<Access>> g_trace_cta;      // (warp, key) -> accesses, current CTA of this launch thread
+inline std::atomic<long long> g_wf_load{0}, g_wf_store{0}, g_instr_load{0}, g_instr_store{0};
+inline void smem_access(uint32_t addr, int bytes, bool store)
+{
+    if (!g_trace.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_trace_cta[{ g_warp, g_seq++ }].push_back(Access{ addr, (unsigned char)g_lane, (unsigned char)bytes, (unsigned char)store });
+}
+inline int wavefronts_of(const std::vector<Access>& v)
+{
+    const int bytes = v[0].bytes, lpp = bytes == 16 ? 8 : bytes == 8 ? 16 : 32;
+    int total = 0;
+    for (int pass = 0; pass < 32 / lpp; ++pass) {
+        std::map<int, std::vector<uint32_t>> rows;     // bank -> distinct rows
+        bool any = false;
+        for (const Access& a : v) {
+            if (a.lane / lpp != pass) continue;
+            any = true;
+            for (int w = 0; w < bytes / 4; ++w) {
+                const uint32_t word = a.addr / 4 + w;
+                auto& r = rows[(int)(word % 32)];
+                bool seen = false;
+                for (uint32_t x : r) seen = seen || x == word / 32;
+                if (!seen) r.push_back(word / 32);
+            }
+        }
+        if (!any) continue;
+        size_t worst = 1;
+        for (auto& kv : rows) worst = kv.second.size() > worst ? kv.second.size() : worst;
+        total += (int)worst;
+    }
+    return total;
+}
+inline void trace_flush_cta()
+{
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    for (auto& kv : g_trace_cta) {
+        const int wf = wavefronts_of(kv.second);
+        if (kv.second[0].store) { g_wf_store += wf; ++g_instr_store; } else { g_wf_load += wf; ++g_instr_load; }
+    }
+    g_trace_cta.clear();
+}
 inline std::atomic<int> g_wait_timeout_s{20};     // a barrier wait longer than this = deadlock
 
 inline void mbar_check(MBar& b, Cta& c)
@@ -196,6 +250,8 @@ bool launch(Kernel kernel, dim3 grid, int threads, unsigned char* smem, size_t s
                     pool.emplace_back([&, t] {
                         g_cta = &cta;
                         g_warp = t / 32;
+                        g_lane = t % 32;
+                        g_seq = 0;
                         threadIdx = uint3{ (unsigned)t, 0, 0 };
                         blockIdx = uint3{ bx, by, bz };
                         gridDim = grid;
@@ -203,6 +259,7 @@ bool launch(Kernel kernel, dim3 grid, int threads, unsigned char* smem, size_t s
                         kernel(args...);
                     });
                 for (auto& th : pool) th.join();
+                if (g_trace.load()) trace_flush_cta();
                 if (cta.timed_out) ok = false;
             }
     return ok;

@@ -143,6 +143,18 @@ extern "C" {
 
 void emu_set_timeout(int seconds) { emu::g_wait_timeout_s = seconds; }
 
+// shared-memory wavefront accounting (emu_cuda.hpp): switch it on, run launches on ONE host thread, read the totals
+void emu_trace(int on)
+{
+    emu::g_trace = on != 0;
+    if (on) { emu::g_wf_load = 0; emu::g_wf_store = 0; emu::g_instr_load = 0; emu::g_instr_store = 0; }
+}
+// out[0..3] = load wavefronts, store wavefronts, load instructions, store instructions (warp level) since emu_trace(1)
+void emu_trace_read(long long* out)
+{
+    out[0] = emu::g_wf_load; out[1] = emu::g_wf_store; out[2] = emu::g_instr_load; out[3] = emu::g_instr_store;
+}
+
 // returns (deadlock detected ? 1 : 0) + 2 * (well-formed CTA completed and read the right TMA data ? 1 : 0): 3 = both as expected
 int emu_selftest()
 {

@@ -115,10 +115,10 @@ def test_2d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     np.testing.assert_array_equal(out, want)
 
 
-DEPTH = {32: 3, 33: 4, 34: 4, 35: 2}      # sweeps per launch of the K-sweep 2D variants (kernels_sweep2d_tbk.cu)
+DEPTH = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4}      # 36 / 37: de-interleaved ring rows      # sweeps per launch of the K-sweep 2D variants (kernels_sweep2d_tbk.cu)
 
 
-@pytest.mark.parametrize("variant", [35, 32, 33, 34])
+@pytest.mark.parametrize("variant", [35, 32, 33, 34, 36, 37])
 @pytest.mark.parametrize("n,hi,spec,launches,chunk", [
     ([33, 7], [1.0, 2.0], MIXED_2D, 1, 0),
     ([513, 5], [513.0, 5.0], MIXED_2D, 2, 2),                    # one cell past a 512-column strip; 3 row chunks; ping-pong
@@ -130,6 +130,7 @@ DEPTH = {32: 3, 33: 4, 34: 4, 35: 2}      # sweeps per launch of the K-sweep 2D 
     ([1, 1], [1.0, 1.0], MIXED_2D, 2, 0),
     ([130, 23], [13.0, 2.3], NEUMANN_2D, 1, 5),                  # chunks whose lower levels are clipped at either face
     ([64, 40], [1.0, 1.0], MIXED_2D, 1, 0),                      # planner-chosen chunks, steady (unrolled) iterations
+    ([131, 50], [1.0, 1.0], MIXED_2D, 1, 25),                    # odd n0 in the second warp; long chunks: several unrolled trips
 ])
 def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk, variant):
     """K = 2, 3, 4 sweeps per pass (opt-in variants): u_K after `launches` launches == K*launches oracle sweeps, bit for bit."""
