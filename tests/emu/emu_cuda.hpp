@@ -11,8 +11,8 @@
 // It checks what the GPU box is too expensive to iterate on: tile / halo / ghost index logic, ring and
 // barrier protocols (a wrong parity or a missing arrival deadlocks here as it would on the device: the
 // launcher gives up after a timeout), and -- with several launches running concurrently on "devices"
-// that share the process's memory -- the slab handshake.  It does not model timing, bank conflicts,
-// memory-model reordering or register limits.  tests/test_emulated_kernels.py drives it on the CPU box.
+// that share the process's memory -- the slab handshake.  It does not model timing, memory-model
+// reordering or register limits; an optional static bank model counts shared-memory wavefronts (below).  tests/test_emulated_kernels.py drives it on the CPU box.
 #pragma once
 #ifndef RNMF_EMULATE
 #error "emu_cuda.hpp is for -DRNMF_EMULATE builds (tests) only"
