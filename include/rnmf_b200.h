@@ -115,7 +115,16 @@ int64_t rnmf_double_sweep_launches(rnmf_ctx* ctx);
 /* CUDA-event timer on the context's stream: begin records, end records+synchronises. */
 int32_t rnmf_timer_begin(rnmf_ctx* ctx);
 int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);
-/* tuning knob for measurements: selects a sweep-kernel variant by name ("auto" = default). */
+/* tuning knobs for measurements (results never change, only which kernel / schedule produces them):
+ *   "sweep_variant"  "auto" (default) or a number: 3D 1-4,10,11 = non-TMA kernels, 6 = single-sweep TMA kernel only,
+ *                    20/21 = double sweep 128x12 / 128x8, 24/25 = two rows per warp, 26/27 = interior-specialised loops
+ *                    (24-27 opt-in); 2D 1,2 = non-TMA, 20 = single-sweep TMA only, 30 = double sweep, 32-37 = three /
+ *                    four sweeps per pass (opt-in)
+ *   "sweep_chunk"    planes / rows marched per CTA (0 = planner)
+ *   "resident"       1/0: one cooperative launch for all sweeps of an L2-resident frame
+ *   "peer_halo", "peer_inkernel", "halo_overlap"   slab halo exchange: fused peer-memory path / in-kernel handshake / NCCL overlap
+ *   "e2e_skew" (+ "e2e_skew_chunks", "e2e_skew_pairs")  opt-in: rnmf_solve_poisson_host uploads in chunks of z-planes and
+ *                    overlaps the upload with the first double sweeps */
 int32_t rnmf_set_option(rnmf_ctx* ctx, const char* key, const char* value);
 
 /* Domain::new_rectangular split rule (cartesian2d/mod.rs:64-73,109-116), 1-D along one axis.
