@@ -123,8 +123,9 @@ int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);
  *   "sweep_chunk"    planes / rows marched per CTA (0 = planner)
  *   "resident"       1/0: one cooperative launch for all sweeps of an L2-resident frame
  *   "peer_halo", "peer_inkernel", "halo_overlap"   slab halo exchange: fused peer-memory path / in-kernel handshake / NCCL overlap
- *   "e2e_skew" (+ "e2e_skew_chunks", "e2e_skew_pairs")  opt-in: rnmf_solve_poisson_host uploads in chunks of z-planes and
- *                    overlaps the upload with the first double sweeps */
+ *   "e2e_skew" (+ "e2e_skew_chunks", "e2e_skew_pairs", "e2e_skew_tail")  opt-in: 1 = rnmf_solve_poisson_host uploads in
+ *                    chunks of z-planes and overlaps the upload with the first double sweeps; 2 = also runs the last
+ *                    launches band-wise so that the download overlaps them */
 int32_t rnmf_set_option(rnmf_ctx* ctx, const char* key, const char* value);
 
 /* Domain::new_rectangular split rule (cartesian2d/mod.rs:64-73,109-116), 1-D along one axis.

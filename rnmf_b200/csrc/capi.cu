@@ -150,7 +150,9 @@ struct rnmf_ctx {
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
     rnmf_frame* hp_rhs = nullptr;
     int e2e_skew = 0;                     // option "e2e_skew" (opt-in): time-skewed start of rnmf_solve_poisson_host
-    int e2e_skew_chunks = 8, e2e_skew_pairs = 56;
+    int e2e_skew_chunks = 8, e2e_skew_pairs = 56; // upload chunks, double sweeps run band-wise during the upload
+    int e2e_skew_tail = 32;                       // e2e_skew >= 2: last launches run band-wise so the download overlaps them
+    cudaEvent_t ev_tail = nullptr;
     std::vector<cudaEvent_t> ev_chunks;   // one per upload chunk
     long long skew_launches = 0;          // double-sweep launches issued by the skewed start (a test reads it back)
 };
@@ -331,6 +333,7 @@ extern "C" int32_t rnmf_ctx_destroy(rnmf_ctx* c)
     if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     for (cudaEvent_t e : c->ev_chunks) cudaEventDestroy(e);
+    if (c->ev_tail) cudaEventDestroy(c->ev_tail);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_halo) cudaStreamDestroy(c->stream_halo);
     delete c;
@@ -396,6 +399,7 @@ extern "C" int32_t rnmf_set_option(rnmf_ctx* c, const char* key, const char* val
     if (!strcmp(key, "e2e_skew")) { c->e2e_skew = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "e2e_skew_chunks")) { c->e2e_skew_chunks = atoi(value); return RNMF_OK; }
     if (!strcmp(key, "e2e_skew_pairs")) { c->e2e_skew_pairs = atoi(value); return RNMF_OK; }
+    if (!strcmp(key, "e2e_skew_tail")) { c->e2e_skew_tail = atoi(value); return RNMF_OK; }
     rnmf_set_error("unknown option '%s'", key);
     return RNMF_ERR_INVALID;
 }
@@ -1345,6 +1349,16 @@ extern "C" int32_t rnmf_gradient_h_2d(const rnmf_frame* psi, rnmf_frame* h)
 // chunk makes computable (skew_region, common.cuh), so the sweeps overlap most of the upload.  Afterwards every plane
 // holds u_{2*pairs} and the frame continues with ordinary whole-frame launches.  Same kernels, same operations: the
 // result is bit-identical to the plain path.  Returns the number of sweeps done (0: not applicable, nothing touched).
+static bool skew_applicable(const rnmf_ctx* c, const rnmf_frame* psi)
+{
+    const FrameGeom& g = psi->g;
+    bool all_faces = psi->bc_set && !psi->has_reflect;
+    for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
+    const int v = c->sweep_variant, C = c->e2e_skew_chunks;
+    return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && c->nranks == 1 && all_faces && C >= 2 && g.n[2] / C >= 16 &&
+           g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && (v == 0 || v == 20 || v == 21 || v == 24 || v == 25 || v == 26 || v == 27);
+}
+
 static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,
                                               const double* coef, int64_t pairable, int* rc_out)
 {
@@ -1354,12 +1368,7 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
     const long long n2 = g.n[2];
     const long long dense = g.G[0] * g.G[1] * g.G[2];
     int64_t pairs = c->e2e_skew_pairs < pairable / 2 ? c->e2e_skew_pairs : pairable / 2;
-    bool all_faces = psi->bc_set && !psi->has_reflect;
-    for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
-    const int v = c->sweep_variant;
-    if (!c->e2e_skew || g.dim != 3 || g.ng != 1 || g.ncomp != 1 || c->nranks != 1 || !all_faces || C < 2 || n2 / C < 16 || pairs < 4 ||
-        dense * 8 < (64LL << 20) || !(v == 0 || v == 20 || v == 21 || v == 24 || v == 25 || v == 26 || v == 27))
-        return 0;
+    if (!skew_applicable(c, psi) || pairs < 4) return 0;
     cudaStream_t s = c->stream, cs = c->stream_halo;
 #define SKEW_TRY(expr) do { int _rc = (expr); if (_rc) { *rc_out = _rc; return 0; } } while (0)
 #define SKEW_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { rnmf_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); *rc_out = RNMF_ERR_CUDA; return 0; } } while (0)
@@ -1421,6 +1430,97 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
     return 2 * pairs;
 }
 
+// The end of the same call (option e2e_skew >= 2): the last `levels` launches -- double sweeps, the very last one the single
+// norm-carrying sweep when the norm is wanted -- run band-wise from the bottom of the frame (skew_tail_region, common.cuh),
+// and every chunk of z-planes goes back to the host (device pack + 1-D PCIe copy on the halo stream) as soon as its last
+// band is done, while the bands of the chunks above are still being computed.  Bit-identical field; the norm is the same
+// deterministic two-stage tree over per-CTA partials, only grouped by band (so it agrees to rounding, not to the bit).
+static int skewed_last_sweeps_and_download(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* coef, int64_t levels,
+                                           bool last_is_single, double* psi_out, double* l1_update)
+{
+    const FrameGeom& g = psi->g;
+    const int C = c->e2e_skew_chunks;
+    const long long n2 = g.n[2];
+    const long long dense = g.G[0] * g.G[1] * g.G[2], plane_dense = g.G[0] * g.G[1];
+    cudaStream_t s = c->stream, cs = c->stream_halo;
+    if (!psi->d2) { int rc = alloc_buffer(g, &psi->d2, s); if (rc) return rc; }
+    if (c->staging_cap < dense) {
+        RNMF_CUDA_TRY(cudaStreamSynchronize(s));
+        if (c->d_staging) { RNMF_CUDA_TRY(cudaFree(c->d_staging)); c->d_staging = nullptr; c->staging_cap = 0; }
+        RNMF_CUDA_TRY(cudaMalloc(&c->d_staging, (size_t)dense * 8));
+        c->staging_cap = dense;
+    }
+    while ((int)c->ev_chunks.size() < C) {
+        cudaEvent_t e;
+        RNMF_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_chunks.push_back(e);
+    }
+    RNMF_LAUNCH(c, launch_copy_ghost_shell(g, psi->d, psi->d2, s));      // edges / corners agree in both buffers (as rnmf_jacobi_sweeps does)
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g;
+    a.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
+    a.faces = psi->faces[0];
+    a.fuse_fill = 1;
+    a.variant = c->sweep_variant;
+    a.chunk_override = c->sweep_chunk;
+    a.rhs = rhs->d;
+    // partial sums of the norm-carrying level, one segment per band
+    std::vector<long long> part_off(C + 1, 0);
+    if (last_is_single && l1_update) {
+        for (int ch = 0; ch < C; ++ch) {
+            long long lo, hi;
+            skew_tail_region(n2, C, ch, levels, levels, &lo, &hi);
+            SweepArgs q = a;
+            q.k_begin = lo; q.k_end = hi;
+            part_off[ch + 1] = part_off[ch] + (hi > lo ? sweep_num_partials(q) : 0);
+        }
+        int rc = ensure_partials(c, part_off[C]);
+        if (rc) return rc;
+    }
+    double* buf[2] = { psi->d, psi->d2 };
+    double* fin = buf[levels & 1];
+    for (int ch = 0; ch < C; ++ch) {
+        for (int64_t lv = 1; lv <= levels; ++lv) {
+            long long lo, hi;
+            skew_tail_region(n2, C, ch, lv, levels, &lo, &hi);
+            if (hi <= lo) continue;
+            if (lv == levels && last_is_single) {
+                SweepArgs q = a;
+                q.in = buf[(lv - 1) & 1]; q.out = buf[lv & 1];
+                q.k_begin = lo; q.k_end = hi;
+                q.partials = l1_update ? c->d_partials + part_off[ch] : nullptr;
+                RNMF_LAUNCH(c, launch_jacobi_sweep(q, s));
+            } else {
+                Tb2Args t;
+                memset(&t, 0, sizeof(t));
+                t.a = a;
+                t.a.in = buf[(lv - 1) & 1]; t.a.out = buf[lv & 1];
+                t.a.k_begin = lo; t.a.k_end = hi;
+                RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
+                c->skew_launches += 1;
+            }
+        }
+        // planes below Z(ch+1) are final: pack them and send them home while the next chunk's bands run
+        RNMF_CUDA_TRY(cudaEventRecord(c->ev_chunks[ch], s));
+        RNMF_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_chunks[ch], 0));
+        const long long p0 = ch == 0 ? 0 : n2 * ch / C + 1, p1 = ch == C - 1 ? g.G[2] : n2 * (ch + 1) / C + 1;
+        const long long off = plane_dense * p0, cnt = plane_dense * (p1 - p0);
+        RNMF_LAUNCH(c, launch_pack_dense_rows(g, fin, c->d_staging, g.G[1] * p0, g.G[1] * p1, cs));
+        RNMF_CUDA_TRY(cudaMemcpyAsync(psi_out + off, c->d_staging + off, (size_t)cnt * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    if (last_is_single && l1_update) {
+        RNMF_LAUNCH(c, launch_reduce_partials(c->d_partials, (int)part_off[C], c->d_scalar, s));
+        RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, s));
+    }
+    RNMF_CUDA_TRY(cudaGetLastError());
+    if (levels & 1) { double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp; psi->parity ^= 1; }
+    RNMF_CUDA_TRY(cudaStreamSynchronize(s));
+    RNMF_CUDA_TRY(cudaStreamSynchronize(cs));
+    if (l1_update) *l1_update = last_is_single ? c->h_scalar[0] : 0.0;
+    return RNMF_OK;
+}
+
 extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64_t* n, const double* lo, const double* dx,
                                            int32_t ng, const rnmf_bc_face* faces, const double* psi_in, const double* rhs_in,
                                            int64_t n_sub_iter, int32_t mode, double* psi_out, double* l1_update)
@@ -1458,8 +1558,21 @@ extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64
         rc = rnmf_frame_upload(c->hp_rhs, rhs_in);
         if (rc) return rc;
     }
-    if (mode == 0) rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter - done, l1_update);
-    else { rc = rnmf_gs_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter); if (l1_update) *l1_update = 0.0; }
+    if (mode == 0) {
+        // band-wise end of the call: `levels` launches = 2*levels sweeps, one fewer when the last launch is the single
+        // norm-carrying sweep
+        const int64_t rest = n_sub_iter - done;
+        int64_t levels = c->e2e_skew_tail;
+        const bool last_single = l1_update != nullptr;
+        while (levels >= 4 && 2 * levels - (last_single ? 1 : 0) > rest) --levels;
+        if (c->e2e_skew >= 2 && levels >= 4 && skew_applicable(c, c->hp_psi)) {
+            if (bind(c)) return RNMF_ERR_CUDA;
+            rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, rest - (2 * levels - (last_single ? 1 : 0)), nullptr);
+            if (rc) return rc;
+            return skewed_last_sweeps_and_download(c, c->hp_psi, c->hp_rhs, coef, levels, last_single, psi_out, l1_update);
+        }
+        rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, rest, l1_update);
+    } else { rc = rnmf_gs_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter); if (l1_update) *l1_update = 0.0; }
     if (rc) return rc;
     return rnmf_frame_download(c->hp_psi, psi_out);
 }

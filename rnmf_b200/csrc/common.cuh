@@ -221,6 +221,20 @@ inline void skew_region(long long n2, int n_chunks, int c, long long s, long lon
     *hi = c == n_chunks - 1 ? n2 : (zn > 0 ? zn : 0);
 }
 
+// The mirror image at the end of the call: the last `levels` launches (double sweeps; the last one may be the single
+// norm-carrying sweep, for which the two-plane margin is conservative) finish the frame chunk by chunk from the bottom,
+// so that chunk c can go back to the host while chunk c+1 is still being swept.  Level s = 1..levels of chunk c covers
+// [G_s(c-1), G_s(c)), G_s(c) = min(n2, Z(c+1) + 2*(levels - s)) (the last chunk: n2): after level `levels` exactly the
+// planes below Z(c+1) are final.  Band (c, s) reads what bands (<= c, s-1) wrote, and the ping-pong partner is only
+// overwritten below the lowest plane a later band still reads (the same argument as for skew_region, mirrored).
+inline void skew_tail_region(long long n2, int n_chunks, int c, long long s, long long levels, long long* lo, long long* hi)
+{
+    const long long m = 2 * (levels - s);
+    const long long gp = n2 * c / n_chunks + m, gc = n2 * (c + 1) / n_chunks + m;
+    *lo = c == 0 ? 0 : (gp < n2 ? gp : n2);
+    *hi = c == n_chunks - 1 ? n2 : (gc < n2 ? gc : n2);
+}
+
 struct SweepArgs {
     FrameGeom g;
     const double* in;
@@ -286,6 +300,7 @@ int launch_axpby(long long n, double a, const double* x, double b, const double*
 int launch_fill_synthetic(const FrameGeom& g, double* d, unsigned long long seed, cudaStream_t s);
 int launch_unpack_dense(const FrameGeom& g, const double* dense, double* frame, cudaStream_t s);
 int launch_unpack_dense_rows(const FrameGeom& g, const double* dense, double* frame, double* shell_dst, long long r0, long long r1, cudaStream_t s);
+int launch_pack_dense_rows(const FrameGeom& g, const double* frame, double* dense, long long r0, long long r1, cudaStream_t s);
 int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s);
 int launch_unpack_valid(const FrameGeom& g, const double* packed, double* d, cudaStream_t s);
 

@@ -120,6 +120,17 @@ __global__ void __launch_bounds__(256) unpack_dense_rows_kernel(FrameGeom g, con
     }
 }
 
+// ---- pitched frame -> dense, grown rows [r0, r1) (chunked download, rnmf_solve_poisson_host) ----
+__global__ void __launch_bounds__(256) pack_dense_rows_kernel(FrameGeom g, const double* __restrict__ frame, double* __restrict__ dense,
+                                                               long long r0, long long r1)
+{
+    for (long long r = r0 + blockIdx.x; r < r1; r += gridDim.x) {
+        const double* src = frame + g.xoff + g.pitch * r;
+        double* dst = dense + r * g.G[0];
+        for (long long i = threadIdx.x; i < g.G[0]; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
 // ---- K5: sum |v| over valid cells (poisson.rs:94-100), deterministic two-stage tree ---------
 constexpr int kSumThreads = 256;
 __global__ void __launch_bounds__(kSumThreads) abs_sum_valid_kernel(FrameGeom g, const double* __restrict__ d,
@@ -274,6 +285,12 @@ int launch_unpack_dense_rows(const FrameGeom& g, const double* dense, double* fr
 {
     if (r1 <= r0) return 0;
     unpack_dense_rows_kernel<<<row_blocks(r1 - r0), 256, 0, s>>>(g, dense, frame, shell_dst, r0, r1);
+    return 1;
+}
+int launch_pack_dense_rows(const FrameGeom& g, const double* frame, double* dense, long long r0, long long r1, cudaStream_t s)
+{
+    if (r1 <= r0) return 0;
+    pack_dense_rows_kernel<<<row_blocks(r1 - r0), 256, 0, s>>>(g, frame, dense, r0, r1);
     return 1;
 }
 int launch_pack_valid(const FrameGeom& g, const double* d, double* packed, cudaStream_t s)

@@ -33,9 +33,10 @@ run 3d_v27 python bench.py $S3 --variant 27
 SE="--workload 3d7_768 --steps 2 --warmup 3 --sub-iters 550 --no-cpu-baseline --no-others"
 run 3d_e2e_plain python bench.py $SE
 RNMF_E2E_SKEW=1 run 3d_e2e_skew python bench.py $SE
+RNMF_E2E_SKEW=2 run 3d_e2e_skew2 python bench.py $SE
 python - <<'PY'
 import json
-for n in ("3d_e2e_plain", "3d_e2e_skew"):
+for n in ("3d_e2e_plain", "3d_e2e_skew", "3d_e2e_skew2"):
     try:
         d = json.load(open(f"gpurun_out/r2exp_{n}.json")); print(n, "value", round(d["value"], 1), "e2e", d["e2e"])
     except Exception as e:

@@ -266,6 +266,50 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
     return g_deadlocks.load();
 }
 
+// The band-wise END of rnmf_solve_poisson_host (capi.cu: skewed_last_sweeps_and_download): the last `levels` double sweeps run
+// chunk by chunk from the bottom (skew_tail_region); after chunk c's last band the planes below Z(c+1) are "downloaded" into
+// out_dense and everything no later band may read (both buffers below plane Z(c+1)-2) is poisoned.
+int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
+                                  const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_chunks, int levels)
+{
+    g_deadlocks = 0;
+    Frame f;
+    init_frame(f, 3, n, dx, psi_dense, rhs_dense);
+    const FrameGeom& g = f.g;
+    Tb2Args t;
+    memset(&t, 0, sizeof(t));
+    t.a.g = g;
+    t.a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+    t.a.faces = make_faces(3, face_kind, face_value, dx);
+    t.a.fuse_fill = 1;
+    t.a.variant = variant;
+    t.a.chunk_override = chunk;
+    t.a.rhs = f.rhs.data();
+    const long long n2 = g.n[2], G0 = g.G[0], G1 = g.G[1];
+    std::vector<double> dense((size_t)(G0 * G1 * g.G[2]));
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        for (long long lv = 1; lv <= levels; ++lv) {
+            long long lo, hi;
+            skew_tail_region(n2, n_chunks, ch, lv, levels, &lo, &hi);
+            if (hi <= lo) continue;
+            t.a.in = f.buf[(lv - 1) & 1].data();
+            t.a.out = f.buf[lv & 1].data();
+            t.a.k_begin = lo; t.a.k_end = hi;
+            if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
+        }
+        // "download" of chunk ch from the final buffer
+        const long long p0 = ch == 0 ? 0 : n2 * ch / n_chunks + 1, p1 = ch == n_chunks - 1 ? g.G[2] : n2 * (ch + 1) / n_chunks + 1;
+        pack(g, f.buf[levels & 1].data(), dense.data());
+        memcpy(out_dense + G0 * G1 * p0, dense.data() + G0 * G1 * p0, (size_t)(G0 * G1 * (p1 - p0)) * sizeof(double));
+        // nothing below valid plane Z(ch+1)-2 may be read again
+        const long long dead = n2 * (ch + 1) / n_chunks - 2;           // valid planes < dead, i.e. grown planes <= dead
+        if (ch < n_chunks - 1)
+            for (long long kk = 0; kk <= dead && kk < g.G[2]; ++kk)
+                for (long long q = g.plane * kk; q < g.plane * (kk + 1); ++q) { f.buf[0][q] = -8.0e300; f.buf[1][q] = 8.5e300; }
+    }
+    return g_deadlocks.load();
+}
+
 // The same over z-slabs: `nranks` host threads, each launching its slab's double sweeps; u1 boundary planes and
 // u2 boundary planes travel through the neighbours' buffers, ordered by the half / full step flags -- the
 // argument wiring mirrors rnmf_jacobi_sweeps (capi.cu).  Global dense frames in / out (3D, ng = 1).

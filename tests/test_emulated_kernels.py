@@ -176,3 +176,20 @@ def test_time_skewed_start_schedule_on_the_emulator(emu, n, spec, n_chunks, pair
     rc = emu.emu_skewed_double_sweeps(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, n_chunks, pairs)
     assert rc == 0, "deadlock or launch failure"
     np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("n,spec,n_chunks,levels,chunk,variant", [
+    ([20, 9, 32], MIXED_3D, 2, 5, 0, 20),
+    ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 20),         # 8-plane chunks, 2*levels > chunk: the upper bands are clipped at the top
+    ([130, 13, 20], MIXED_3D, 4, 3, 2, 20),
+    ([20, 9, 24], MIXED_3D, 3, 4, 0, 24),
+])
+def test_time_skewed_end_schedule_on_the_emulator(emu, n, spec, n_chunks, levels, chunk, variant):
+    """The band schedule of the END of the opt-in time-skewed host call (skew_tail_region): every chunk is "downloaded" right after
+    its last band and all planes no later band may read are poisoned at once, yet the assembled frame equals 2*levels oracle sweeps."""
+    hi = [1.0, 2.0, 3.0]
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * levels, seed=46)
+    out = np.zeros_like(psi)
+    rc = emu.emu_skewed_tail_double_sweeps(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, n_chunks, levels)
+    assert rc == 0, "deadlock or launch failure"
+    np.testing.assert_array_equal(out, want)

@@ -547,7 +547,7 @@ def test_solve_poisson_host_entry_point(R, ctx):
 
 
 @pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in path: set RNMF_EXPERIMENTAL=1")
-@pytest.mark.parametrize("sweeps,chunks,pairs", [(41, 4, 10), (24, 8, 56), (9, 2, 4)])
+@pytest.mark.parametrize("sweeps,chunks,pairs", [(41, 4, 10), (24, 8, 56), (19, 2, 4)])
 def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
     """Option e2e_skew: chunked upload overlapped with the first double sweeps on the bands each chunk makes computable
     (capi.cu: skewed_upload_and_first_sweeps).  Same kernels, same operations: bit-identical to the plain call; the launch
@@ -565,10 +565,11 @@ def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
     dx = (C.c_double * 3)(1.0, 1.0, 1.0)
     outs, norms, launches = [], [], []
     try:
-        for skew in (0, 1):
+        for skew in (0, 1, 2):                          # 2: the band-wise end with the overlapped download as well
             ctx.set_option("e2e_skew", skew)
             ctx.set_option("e2e_skew_chunks", chunks)
             ctx.set_option("e2e_skew_pairs", pairs)
+            ctx.set_option("e2e_skew_tail", 5)
             out = np.empty_like(psi0)
             l1 = C.c_double()
             k0 = ctx.kernel_launches
@@ -580,8 +581,11 @@ def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
     finally:
         ctx.set_option("e2e_skew", 0)
     np.testing.assert_array_equal(outs[1], outs[0])
+    np.testing.assert_array_equal(outs[2], outs[0])
     assert norms[1] == norms[0]
+    assert abs(norms[2] - norms[0]) <= NORM_RTOL * abs(norms[0])      # same partial sums, grouped by band
     assert launches[1] > launches[0] + chunks          # one band launch per (chunk, pair) instead of one launch per pair
+    assert launches[2] > launches[1]
 
 
 def test_kernel_launch_counter_moves(R, ctx):
