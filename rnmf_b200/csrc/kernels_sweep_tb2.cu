@@ -528,6 +528,43 @@ __device__ __forceinline__ C4 fin2_4(const C4& part, double c3, const C4& u, con
 }
 __device__ __forceinline__ C4 ghost4(const Face1& f, const C4& m) { C4 o; o.a = ghost1(f, m.a); o.b = ghost1(f, m.b); return o; }
 
+// ---- rows of the u1 ring.  DI (variant 28): a row of BX = 132 positions is stored de-interleaved, the 66 even positions first
+// and the 66 odd ones behind (U1_ODD bytes on): a pair's left neighbour is an odd position and its right neighbour an even one,
+// so the E/W loads become dense 8-byte accesses (2 shared-memory wavefronts per warp instead of 4); pair loads / stores become two
+// dense 8-byte accesses each (the same 4 wavefronts as one 16-byte access).  `a` = where the lane's first cell sits in the row.
+constexpr uint32_t U1_ODD = (128 + 4) / 2 * 8;
+template <bool DI>
+__device__ __forceinline__ uint32_t u1_pos(int q) { return DI ? (uint32_t)((q & 1) * U1_ODD + (q >> 1) * 8) : (uint32_t)(q * 8); }
+template <bool DI>
+__device__ __forceinline__ C4 ldu4(uint32_t a)
+{
+    if (!DI) return ld4(a);
+    C4 v;
+    v.a.x = lds1(a); v.a.y = lds1(a + U1_ODD); v.b.x = lds1(a + 256); v.b.y = lds1(a + U1_ODD + 256);
+    return v;
+}
+template <bool DI>
+__device__ __forceinline__ EW4 lduew(uint32_t a)
+{
+    if (!DI) return ldew(a);
+    EW4 e;
+    e.w_a0 = lds1(a + U1_ODD - 8); e.e_a1 = lds1(a + 8);
+    e.w_b0 = lds1(a + U1_ODD + 256 - 8); e.e_b1 = lds1(a + 256 + 8);
+    return e;
+}
+template <bool DI>
+__device__ __forceinline__ void stu4(uint32_t a, const double2& va, const double2& vb, bool full, bool a0, bool a1, bool b0, bool b1)
+{
+    if (!DI) { sstore4(a, va, vb, full, a0, a1, b0, b1); return; }
+    if (full) { sts1(a, va.x); sts1(a + U1_ODD, va.y); sts1(a + 256, vb.x); sts1(a + U1_ODD + 256, vb.y); }
+    else {
+        if (a0) sts1(a, va.x);
+        if (a1) sts1(a + U1_ODD, va.y);
+        if (b0) sts1(a + 256, vb.x);
+        if (b1) sts1(a + U1_ODD + 256, vb.y);
+    }
+}
+
 template <int TY, int NS, bool MERGE>
 struct Tb2xCfg : Tb2Cfg<TY, NS> {
     static_assert(TY % 2 == 0, "two rows per warp");
@@ -544,7 +581,7 @@ struct RowK2 {
     bool ok[2];                          // the warp's rows are rows of the frame
     bool do_xlo, any_x, do_ylo;
     int xhi_sel;
-    uint32_t xhi_off;
+    uint32_t xhi_off, xlo_off;           // u1-ring offsets of the x-hi / x-lo ghost from the lane's first cell
     int yhi_row;                         // which of the two rows is the frame's last row (-1: none)
     Face1 fx0, fx1, fy0, fy1, fz0, fz1;
     long long pitch, plane_sz, xy_off;
@@ -564,10 +601,10 @@ __device__ __forceinline__ void st4g(double* a, const C4& v, const RowK2& k, int
 {
     store4(a, v.a, v.b, !MASKED || (k.ok[r] && k.xv3), k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
 }
-template <bool MASKED = true>
+template <bool MASKED = true, bool DI = false>
 __device__ __forceinline__ void st4s(uint32_t a, const C4& v, const RowK2& k, int r)
 {
-    sstore4(a, v.a, v.b, !MASKED || (k.ok[r] && k.xv3), k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
+    stu4<DI>(a, v.a, v.b, !MASKED || (k.ok[r] && k.xv3), k.ok[r] && k.xv0, k.ok[r] && k.xv1, k.ok[r] && k.xv2, k.ok[r] && k.xv3);
 }
 __device__ __forceinline__ double xhi_pick(const C4& v, int sel) { return sel == 0 ? v.a.x : sel == 1 ? v.a.y : sel == 2 ? v.b.x : v.b.y; }
 __device__ __forceinline__ void ld4g(const double* q, C4& v, const RowK2& k, int r)
@@ -583,7 +620,7 @@ __device__ __forceinline__ void ld4g(const double* q, C4& v, const RowK2& k, int
 
 // One plane iteration of a two-row warp (rows r0 = 2w and r0+1 of the tile): see row_iter for the protocol.
 // EDGE = false: interior-specialised copy (see row_iter)
-template <int TY, int NS, bool DO_L1, bool DO_L2, bool EDGE = true>
+template <int TY, int NS, bool DO_L1, bool DO_L2, bool EDGE = true, bool DI = false>
 __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, RowSt2& st, const int it)
 {
     using Cfg = Tb2Cfg<TY, NS>;
@@ -598,8 +635,8 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
     if (DO_L2) {
         const uint32_t up = k.ua + (uint32_t)((it - 1) & 1) * Cfg::U1_SLOT;
         // row 0: S from the ring (row below), N = the warp's second row; row 1: N from the ring, S = the first row
-        const C4 s0 = ld4(up - RB), n1 = ld4(up + 2 * RB);
-        const EW4 e0 = ldew(up), e1 = ldew(up + RB);
+        const C4 s0 = ldu4<DI>(up - RB), n1 = ldu4<DI>(up + 2 * RB);
+        const EW4 e0 = lduew<DI>(up), e1 = lduew<DI>(up + RB);
         P[0] = part2_4(k.c, st.rp[0], st.u1c[0], e0, st.u1c[1], s0);
         P[1] = part2_4(k.c, st.rp[1], st.u1c[1], e1, n1, st.u1c[0]);
     }
@@ -626,18 +663,18 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
         const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
-        st4s<EDGE>(us, u1n[0], k, 0);
-        st4s<EDGE>(us + RB, u1n[1], k, 1);
+        st4s<EDGE, DI>(us, u1n[0], k, 0);
+        st4s<EDGE, DI>(us + RB, u1n[1], k, 1);
         if (EDGE && k.any_x) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
                 if (k.ok[r]) {
-                    if (k.do_xlo) sts1(us + r * RB - 8, ghost1(k.fx0, u1n[r].a.x));
+                    if (k.do_xlo) sts1(us + r * RB + k.xlo_off, ghost1(k.fx0, u1n[r].a.x));
                     if (k.xhi_sel >= 0) sts1(us + r * RB + k.xhi_off, ghost1(k.fx1, xhi_pick(u1n[r], k.xhi_sel)));
                 }
         }
-        if (EDGE && k.do_ylo) st4s(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
-        if (EDGE && k.yhi_row == 1) st4s(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
+        if (EDGE && k.do_ylo) st4s<true, DI>(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
+        if (EDGE && k.yhi_row == 1) st4s<true, DI>(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
         if (EDGE && it == k.it_u1lo) { st4g(p.peer_u1_lo + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_lo + k.xy_off + k.pitch, u1n[1], k, 1); }
@@ -689,7 +726,7 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
     st.rp[0] = rc[0]; st.rp[1] = rc[1];
 }
 
-template <int TY, int NS, bool MERGE, bool SPEC = false>
+template <int TY, int NS, bool MERGE, bool SPEC = false, bool DI = false>
 __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_tb2x_kernel(const __grid_constant__ CUtensorMap tm_u0,
                                                                                            const __grid_constant__ CUtensorMap tm_rhs,
                                                                                            const __grid_constant__ Tb2Params p)
@@ -781,7 +818,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         for (int h = 0; h < 2; ++h) {
             hpa[h] = u0_0 + (uint32_t)(((rrow[h] + 2) * BX + 2 + 2 * lane) * 8);
             hra[h] = rhs_0 + (uint32_t)(((rrow[h] + 1) * BX + 2 + 2 * lane) * 8);
-            hua[h] = u1_0 + (uint32_t)(((rrow[h] + 1) * BX + 2 + 2 * lane) * 8);
+            hua[h] = u1_0 + (uint32_t)((rrow[h] + 1) * BX * 8) + u1_pos<DI>(2 + 2 * lane);
         }
         // columns: lanes 0..15: column i0-1, rows j0+lane; lanes 16..31: column i0+128, rows j0+lane-16
         const int side = lane >> 4, rcl = (lane & 15) < TY ? (lane & 15) : 0;
@@ -789,7 +826,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         const bool cok = do_cols && (lane & 15) < TY && i0 + col >= 0 && i0 + col < n0 && j0 + rcl < n1;
         const uint32_t cp = u0_0 + (uint32_t)(((rcl + 2) * BX + col + 2) * 8);
         const uint32_t cr = rhs_0 + (uint32_t)(((rcl + 1) * BX + col + 2) * 8);
-        const uint32_t cu = u1_0 + (uint32_t)(((rcl + 1) * BX + col + 2) * 8);
+        const uint32_t cu = u1_0 + (uint32_t)((rcl + 1) * BX * 8) + u1_pos<DI>(col + 2);
 
         mbar_wait(full0, 0);
         C4 below[2] = { ld4(hpa[0]), ld4(hpa[1]) };
@@ -828,7 +865,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
             if (do_rows) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
-                    sstore4(hua[h] + slot, v[h].a, v[h].b, rok[h] && xv3, rok[h] && xv0, rok[h] && xv1, rok[h] && xv2, rok[h] && xv3);
+                    stu4<DI>(hua[h] + slot, v[h].a, v[h].b, rok[h] && xv3, rok[h] && xv0, rok[h] && xv1, rok[h] && xv2, rok[h] && xv3);
             }
             if (cok) sts1(cu + slot, cv);
             __syncwarp();
@@ -848,7 +885,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         k.xv0 = ia < n0; k.xv1 = ia + 1 < n0; k.xv2 = ib < n0; k.xv3 = ib + 1 < n0;
         k.pa = u0_0 + (uint32_t)(((r0 + 2) * BX + 2 + 2 * lane) * 8);
         k.ra = rhs_0 + (uint32_t)(((r0 + 1) * BX + 2 + 2 * lane) * 8);
-        k.ua = u1_0 + (uint32_t)(((r0 + 1) * BX + 2 + 2 * lane) * 8);
+        k.ua = u1_0 + (uint32_t)((r0 + 1) * BX * 8) + u1_pos<DI>(2 + 2 * lane);
         k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0;
         k.c = p.c;
         k.pitch = p.g.pitch; k.plane_sz = p.g.plane;
@@ -860,7 +897,9 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         k.do_xlo = k.fx0.on && k.xv0 && ia == 0;
         const long long last = n0 - 1;
         k.xhi_sel = !k.fx1.on ? -1 : (k.xv0 && ia == last) ? 0 : (k.xv1 && ia + 1 == last) ? 1 : (k.xv2 && ib == last) ? 2 : (k.xv3 && ib + 1 == last) ? 3 : -1;
-        k.xhi_off = (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        k.xhi_off = DI ? (uint32_t)((k.xhi_sel >= 2 ? 256 : 0) + ((k.xhi_sel & 1) ? 8 : U1_ODD))
+                       : (uint32_t)((k.xhi_sel >= 2 ? 512 : 0) + ((k.xhi_sel & 1) + 1) * 8);
+        k.xlo_off = DI ? U1_ODD - 8 : (uint32_t)-8;
         k.any_x = k.do_xlo || k.xhi_sel >= 0;
         k.do_ylo = k.fy0.on && jr == 0;
         k.yhi_row = !k.fy1.on ? -1 : (jr == n1 - 1 ? 0 : (jr + 1 == n1 - 1 ? 1 : -1));
@@ -886,27 +925,27 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         const bool interior = SPEC && k.ok[1] && i0 + TX <= n0 && !(k.fx0.on && i0 == 0) && !(k.fx1.on && i0 + TX == n0) &&
                               !k.do_ylo && k.yhi_row < 0 && !a_sync_lo && !a_sync_hi && !is_b;
         if (SPEC && interior) {
-            for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, false>(p, k, st, it);
+            for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, false, DI>(p, k, st, it);
             // the first two-level iteration may meet the z-lo face: general code, once
-            if (it < nL1) { row2_iter<TY, NS, true, true, true>(p, k, st, it); ++it; }
+            if (it < nL1) { row2_iter<TY, NS, true, true, true, DI>(p, k, st, it); ++it; }
             for (; it < nL1; it += 3) {
-                row2_iter<TY, NS, true, true, false>(p, k, st, it);
+                row2_iter<TY, NS, true, true, false, DI>(p, k, st, it);
                 if (it + 1 >= nL1) break;
-                row2_iter<TY, NS, true, true, false>(p, k, st, it + 1);
+                row2_iter<TY, NS, true, true, false, DI>(p, k, st, it + 1);
                 if (it + 2 >= nL1) break;
-                row2_iter<TY, NS, true, true, false>(p, k, st, it + 2);
+                row2_iter<TY, NS, true, true, false, DI>(p, k, st, it + 2);
             }
         } else {
-        for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false>(p, k, st, it);
+        for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, true, DI>(p, k, st, it);
         for (; it < nL1; it += 3) {
-            row2_iter<TY, NS, true, true>(p, k, st, it);
+            row2_iter<TY, NS, true, true, true, DI>(p, k, st, it);
             if (it + 1 >= nL1) break;
-            row2_iter<TY, NS, true, true>(p, k, st, it + 1);
+            row2_iter<TY, NS, true, true, true, DI>(p, k, st, it + 1);
             if (it + 2 >= nL1) break;
-            row2_iter<TY, NS, true, true>(p, k, st, it + 2);
+            row2_iter<TY, NS, true, true, true, DI>(p, k, st, it + 2);
         }
         }
-        if (top) row2_iter<TY, NS, false, true>(p, k, st, nL1);
+        if (top) row2_iter<TY, NS, false, true, true, DI>(p, k, st, nL1);
     }
     if (a_sync_lo || a_sync_hi || is_b) {
         if (p.ps.enabled) {
@@ -982,7 +1021,7 @@ struct Tb2Launcher {
 };
 
 // two rows per row warp: same tiling / planner as Tb2Launcher<TY, NS>, its own kernel and thread count
-template <int TY, int NS, bool MERGE, bool SPEC = false>
+template <int TY, int NS, bool MERGE, bool SPEC = false, bool DI = false>
 struct Tb2xLauncher {
     using Cfg = Tb2xCfg<TY, NS, MERGE>;
     static int launch(const Tb2Args& t, cudaStream_t s)
@@ -1008,11 +1047,11 @@ struct Tb2xLauncher {
 #ifndef RNMF_EMULATE
         static bool attr_set = false;
         if (!attr_set) {
-            if (cudaFuncSetAttribute(jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC, DI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             attr_set = true;
         }
 #endif
-        RNMF_KERNEL_LAUNCH((jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
+        RNMF_KERNEL_LAUNCH((jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC, DI>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
         return 1;
     }
 };
@@ -1031,6 +1070,7 @@ int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
     case 25: return Tb2xLauncher<16, 4, false>::launch(t, s);
     case 26: return Tb2Launcher<12, 6, true>::launch(t, s);          // interior-specialised plane loop (opt-in)
     case 27: return Tb2xLauncher<12, 6, true, true>::launch(t, s);   // two rows per warp + interior-specialised loop (opt-in)
+    case 28: return Tb2xLauncher<12, 6, true, true, true>::launch(t, s);   // 27 + de-interleaved u1 ring rows (opt-in)
     default: return Tb2Launcher<12, 6>::launch(t, s);
     }
 }

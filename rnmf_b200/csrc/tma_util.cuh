@@ -24,10 +24,10 @@ inline void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uin
 inline uint64_t policy_evict_first() { return 0; }
 inline void tma_load_3d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar, uint64_t) { emu::tma_load(dst, tm, c0, c1, c2, bar); }
 inline void st2_hint(double* p, const double2& v, uint64_t) { p[0] = v.x; p[1] = v.y; }
-inline double2 lds2(uint32_t a) { emu::smem_access(a, 16, false); double2 v; std::memcpy(&v, emu::g_cta->smem + a, 16); return v; }
-inline double lds1(uint32_t a) { emu::smem_access(a, 8, false); double v; std::memcpy(&v, emu::g_cta->smem + a, 8); return v; }
-inline void sts2(uint32_t a, const double2& v) { emu::smem_access(a, 16, true); std::memcpy(emu::g_cta->smem + a, &v, 16); }
-inline void sts1(uint32_t a, double v) { emu::smem_access(a, 8, true); std::memcpy(emu::g_cta->smem + a, &v, 8); }
+__attribute__((always_inline)) inline double2 lds2(uint32_t a) { emu::smem_access(a, 16, false); double2 v; std::memcpy(&v, emu::g_cta->smem + a, 16); return v; }
+__attribute__((always_inline)) inline double lds1(uint32_t a) { emu::smem_access(a, 8, false); double v; std::memcpy(&v, emu::g_cta->smem + a, 8); return v; }
+__attribute__((always_inline)) inline void sts2(uint32_t a, const double2& v) { emu::smem_access(a, 16, true); std::memcpy(emu::g_cta->smem + a, &v, 16); }
+__attribute__((always_inline)) inline void sts1(uint32_t a, double v) { emu::smem_access(a, 8, true); std::memcpy(emu::g_cta->smem + a, &v, 8); }
 #else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -29,6 +29,7 @@ run 3d_v24 python bench.py $S3 --variant 24
 run 3d_v25 python bench.py $S3 --variant 25
 run 3d_v26 python bench.py $S3 --variant 26
 run 3d_v27 python bench.py $S3 --variant 27
+run 3d_v28 python bench.py $S3 --variant 28
 # end to end with the time-skewed start (chunked upload overlapped with the first double sweeps): compare `e2e` of the two lines
 SE="--workload 3d7_768 --steps 2 --warmup 3 --sub-iters 550 --no-cpu-baseline --no-others"
 run 3d_e2e_plain python bench.py $SE

@@ -46,11 +46,11 @@ def main():
         rows.append((name, run(lib, n, [1.0, 1.0], T.MIXED_2D, variant, 96, depth)))
     # 3D: 3 x 2 tiles of 128 x 12 (x 16 for variant 25), one 24-plane chunk
     for name, variant, n in (("3D tb2 128x12 (0/20, default)", 20, [384, 24, 24]), ("3D tb2x two rows per warp (24)", 24, [384, 24, 24]),
-                             ("3D tb2x 128x16 (25)", 25, [384, 32, 24]), ("3D tb2 + interior loop (26)", 26, [384, 24, 24]), ("3D tb2x + interior loop (27)", 27, [384, 24, 24])):
+                             ("3D tb2x 128x16 (25)", 25, [384, 32, 24]), ("3D tb2 + interior loop (26)", 26, [384, 24, 24]), ("3D tb2x + interior loop (27)", 27, [384, 24, 24]), ("3D tb2x + interior loop + de-interleaved u1 (28)", 28, [384, 24, 24])):
         rows.append((name, run(lib, n, [1.0, 2.0, 3.0], T.MIXED_3D, variant, 24, 2)))
-    print(f"{'kernel':44s} {'ld wf/upd':>10s} {'st wf/upd':>10s} {'total':>8s} {'ld instr/upd':>13s} {'st instr/upd':>13s}")
+    print(f"{'kernel':50s} {'ld wf/upd':>10s} {'st wf/upd':>10s} {'total':>8s} {'ld instr/upd':>13s} {'st instr/upd':>13s}")
     for name, (lw, sw, li, si) in rows:
-        print(f"{name:44s} {lw:10.4f} {sw:10.4f} {lw + sw:8.4f} {li:13.4f} {si:13.4f}")
+        print(f"{name:50s} {lw:10.4f} {sw:10.4f} {lw + sw:8.4f} {li:13.4f} {si:13.4f}")
     print("(warp-level; per cell update; multiply by 128 cells x levels for the per-row / per-plane figures of DESIGN.md)")
 
 

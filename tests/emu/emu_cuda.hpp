@@ -81,21 +81,29 @@ inline thread_local int g_lane = 0;
 inline thread_local unsigned g_seq = 0;           // shared-memory accesses this thread has made in its CTA (trace key)
 
 // ---- optional shared-memory wavefront accounting (a STATIC bank model, not a timing model) ---------------
-// With tracing on, every ld/st.shared of a warp is keyed by the issuing lane's access count; lanes of a converged
-// warp agree on it, so one key = one warp instruction.  Its cost is the classic bank model: 32 banks of 4 bytes, a
+// With tracing on, every ld/st.shared of a warp is keyed by its call site and how often the lane has executed it, so
+// one key = one warp instruction (of the lanes that take part in it).  Its cost is the classic bank model: 32 banks of 4 bytes, a
 // warp instruction is served in passes of 32 / 16 / 8 lanes for 4- / 8- / 16-byte accesses, and a pass needs as many
-// wavefronts as the largest number of distinct 128-byte rows any bank is asked for.  (Divergent lanes -- the few
-// face / ragged lanes -- shift their keys and are mis-grouped; use frames where interior warps dominate.)
+// wavefronts as the largest number of distinct 128-byte rows any bank is asked for.
 struct Access { uint32_t addr; unsigned char lane, bytes, store; };
 inline std::atomic<bool> g_trace{false};
 inline std::mutex g_trace_mu;
-inline std::map<std::pair<int, unsigned>, std::vector<Access>> g_trace_cta;      // (warp, key) -> accesses, current CTA of this launch thread
+struct TraceKey {
+    int warp; const void* site; unsigned nth;
+    bool operator<(const TraceKey& o) const { return warp != o.warp ? warp < o.warp : site != o.site ? site < o.site : nth < o.nth; }
+};
+inline std::map<TraceKey, std::vector<Access>> g_trace_cta;      // (warp, call site, n-th execution by the lane) -> accesses, current CTA
+inline thread_local std::map<const void*, unsigned> g_site_count;
 inline std::atomic<long long> g_wf_load{0}, g_wf_store{0}, g_instr_load{0}, g_instr_store{0};
-inline void smem_access(uint32_t addr, int bytes, bool store)
+// one warp instruction = the same call site (the ld/st wrappers are always_inline, so the return address identifies the
+// source-level access) executed for the n-th time by each lane: robust against lanes that make extra accesses elsewhere
+__attribute__((noinline)) inline void smem_access(uint32_t addr, int bytes, bool store)
 {
     if (!g_trace.load(std::memory_order_relaxed)) return;
+    const void* site = __builtin_return_address(0);
+    const unsigned nth = g_site_count[site]++;
     std::lock_guard<std::mutex> lk(g_trace_mu);
-    g_trace_cta[{ g_warp, g_seq++ }].push_back(Access{ addr, (unsigned char)g_lane, (unsigned char)bytes, (unsigned char)store });
+    g_trace_cta[TraceKey{ g_warp, site, nth }].push_back(Access{ addr, (unsigned char)g_lane, (unsigned char)bytes, (unsigned char)store });
 }
 inline int wavefronts_of(const std::vector<Access>& v)
 {
@@ -252,6 +260,7 @@ bool launch(Kernel kernel, dim3 grid, int threads, unsigned char* smem, size_t s
                         g_warp = t / 32;
                         g_lane = t % 32;
                         g_seq = 0;
+                        g_site_count.clear();
                         threadIdx = uint3{ (unsigned)t, 0, 0 };
                         blockIdx = uint3{ bx, by, bz };
                         gridDim = grid;

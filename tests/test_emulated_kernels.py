@@ -92,6 +92,13 @@ def _setup(n, hi, spec, sweeps, seed):
     ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 27, 0),
     ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 27, 2),
     ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 27, 3),          # odd n1: the frame's last row is a warp's first row (not interior)
+    # variant 28: 27 with de-interleaved u1 ring rows
+    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 28, 0),
+    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 28, 2),
+    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 28, 3),
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 28, 2),        # odd n0: x-hi ghost in a register and in the odd half of the row
+    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 28, 0),
+    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 28, 0),
 ])
 def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, variant, chunk):
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
@@ -149,6 +156,7 @@ def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk
     ([20, 17, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 25),
     ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 26),         # interior-specialised loop in the A chunks away from the neighbours
     ([390, 14, 13], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 2, 27),
+    ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 28),
 ])
 def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk, variant):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial
