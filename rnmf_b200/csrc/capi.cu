@@ -274,7 +274,7 @@ extern "C" int32_t rnmf_ctx_create(int32_t device, rnmf_ctx** out)
     rnmf_ctx* c = new rnmf_ctx();
     c->device = device;
     int rc = ctx_common_init(c);
-    if (rc) { delete c; return rc; }
+    if (rc) { rnmf_ctx_destroy(c); return rc; }      // releases whatever the partial initialisation created
     *out = c;
     return RNMF_OK;
 }
@@ -296,16 +296,17 @@ extern "C" int32_t rnmf_ctx_create_dist(int32_t device, int32_t rank, int32_t nr
     rnmf_ctx* c = new rnmf_ctx();
     c->device = device; c->rank = rank; c->nranks = nranks;
     int rc = ctx_common_init(c);
-    if (rc) { delete c; return rc; }
+    if (rc) { rnmf_ctx_destroy(c); return rc; }
     if (nranks > 1) {
         rc = nccl_load();
-        if (rc) { delete c; return rc; }
+        if (rc) { rnmf_ctx_destroy(c); return rc; }
         ncclUniqueId id;
         memcpy(&id, nccl_id, sizeof(id));
         ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
         if (r != ncclSuccess) {
             rnmf_set_error("ncclCommInitRank: %s", g_nccl.GetErrorString(r));
-            delete c;
+            c->comm = nullptr;
+            rnmf_ctx_destroy(c);
             return RNMF_ERR_NCCL;
         }
     }
