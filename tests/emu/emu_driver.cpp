@@ -213,6 +213,13 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
     return g_deadlocks.load();
 }
 
+// the band schedules themselves (common.cuh), for the abstract dependency check in tests/test_skew_schedule.py
+void emu_skew_region(long long n2, int n_chunks, int c, long long s, long long* lo, long long* hi) { skew_region(n2, n_chunks, c, s, lo, hi); }
+void emu_skew_tail_region(long long n2, int n_chunks, int c, long long s, long long levels, long long* lo, long long* hi)
+{
+    skew_tail_region(n2, n_chunks, c, s, levels, lo, hi);
+}
+
 // The time-skewed start of rnmf_solve_poisson_host (capi.cu: skewed_upload_and_first_sweeps): the frame "arrives" in
 // n_chunks chunks of z-planes (planes that have not arrived yet hold poison); after every chunk the first `pairs` double
 // sweeps run on the bands skew_region() declares computable, ping-ponging between the two buffers.  At the end every
