@@ -1,7 +1,7 @@
 // kernels_sweep2d_tbk.cu -- K1 for 2D frames, temporally blocked over K = 2, 3 or 4 sweeps: K 5-point
 // Jacobi sweeps (each followed by the ng=1 ghost fill, poisson.rs:80-89 + dataframe.rs:289-355) per
 // pass over HBM, i.e. 24/K algorithmic bytes per update.  Generalises kernels_sweep2d_tb2.cu (K = 2);
-// OPT-IN (sweep variants 32..35) until it has been measured on the device.
+// OPT-IN (sweep variants 32..37) until it has been measured on the device.
 //   * a CTA owns a strip of 128*NW columns and marches a chunk of rows in y; the producer warp streams
 //     one row of psi (u0) and one of rhs per stage, the strip plus PAD >= K halo columns either side;
 //   * NW consumer warps own 128 cells each (lane l: pairs 2l,2l+1 and 64+2l,65+2l).  Level l = 1..K

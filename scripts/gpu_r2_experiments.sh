@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: the opt-in kernels that were written and emulator-checked without a GPU
-# (2D K-sweep kernel, variants 32..35; 3D two-rows-per-warp double sweep, variants 24/25, interior-specialised loops, variants 26/27; time-skewed e2e start): parity first, then
+# (2D K-sweep kernel, variants 32..37; 3D two-rows-per-warp double sweep, variants 24/25, interior-specialised loops, variants 26/27; time-skewed e2e start): parity first, then
 # short sustained benches per variant.  One GPU, about 8 minutes.  Results: gpurun_out/r2exp_*.json|log
 mkdir -p gpurun_out
 export RNMF_EXPERIMENTAL=1
