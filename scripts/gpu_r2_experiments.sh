@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: the opt-in kernels that were written and emulator-checked without a GPU
 # (2D K-sweep kernel, variants 32..37; 3D two-rows-per-warp double sweep, variants 24/25, interior-specialised loops, variants 26/27; time-skewed e2e start): parity first, then
-# short sustained benches per variant.  One GPU, about 8 minutes.  Results: gpurun_out/r2exp_*.json|log
+# short sustained benches per variant.  One GPU, about 10 minutes.  Results: gpurun_out/r2exp_*.json|log
 mkdir -p gpurun_out
 export RNMF_EXPERIMENTAL=1
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "multi_sweep or double_sweep or time_skewed" > gpurun_out/r2exp_pytest.log 2>&1
@@ -10,7 +10,7 @@ unset RNMF_EXPERIMENTAL
 run() { name=$1; shift; timeout 200 "$@" > gpurun_out/r2exp_$name.json 2> gpurun_out/r2exp_$name.err; python -c "
 import json; d=json.load(open('gpurun_out/r2exp_$name.json')); print('$name', round(d['value'],1), 'GLUP/s', round(d['ms_per_step'],2), 'ms/step', d['clocks']['sm_mhz'], d['clocks']['reasons'], d['clocks']['power_w_max'], d['gpu_launches'])" || tail -3 gpurun_out/r2exp_$name.err; }
 # 2D 8192^2: 480 sweeps per step divide by 2, 3 and 4 (the roofline object of these lines assumes <= 2 sweeps per launch: read `value`)
-S2="--workload 2d5_8192 --steps 3 --warmup 3 --sub-iters 480 --no-e2e --no-cpu-baseline --no-others"
+S2="--workload 2d5_8192 --steps 10 --warmup 3 --sub-iters 480 --no-e2e --no-cpu-baseline --no-others"
 run 2d_v20_single python bench.py $S2 --variant 20
 run 2d_v30_tb2 python bench.py $S2 --variant 30
 run 2d_v35_k2 python bench.py $S2 --variant 35
@@ -23,7 +23,7 @@ run 2d_v32_k3_c128 python bench.py $S2 --variant 32 --chunk 128
 run 2d_v36_k3_di python bench.py $S2 --variant 36
 run 2d_v37_k4w_di python bench.py $S2 --variant 37
 # 3D 768^3
-S3="--workload 3d7_768 --steps 3 --warmup 3 --sub-iters 200 --no-e2e --no-cpu-baseline --no-others"
+S3="--workload 3d7_768 --steps 3 --warmup 3 --sub-iters 550 --no-e2e --no-cpu-baseline --no-others"
 run 3d_v0 python bench.py $S3
 run 3d_v24 python bench.py $S3 --variant 24
 run 3d_v25 python bench.py $S3 --variant 25
