@@ -148,6 +148,37 @@ def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk
     np.testing.assert_array_equal(out, want)
 
 
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.sampled_from([32, 33, 34, 35, 36, 37]), st.integers(1, 1100), st.integers(1, 14), st.integers(0, 14), st.integers(0, 3),
+       st.integers(1, 2))
+def test_2d_multi_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, chunk, bc, launches):
+    """Random frame shapes / chunk lengths / face rules for the K-sweep kernel: strips that end anywhere, chunks shorter than the
+    ramp-up, levels clipped at both y faces at once."""
+    spec = [MIXED_2D, NEUMANN_2D, ([("dirichlet", 0.5), ("neumann", 0.1)], [("neumann", -0.3), ("dirichlet", 1.5)]),
+            ([("dirichlet", 0.0), ("dirichlet", 1.0)], [("dirichlet", 2.0), ("dirichlet", -1.0)])][bc]
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup([n0, n1], [1.0 + n0 / 7.0, 2.0], spec, DEPTH[variant] * launches, seed=n0 * 31 + n1)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, min(chunk, n1), launches)
+    assert rc == 0
+    np.testing.assert_array_equal(out, want)
+
+
+@settings(max_examples=12, deadline=None)
+@given(st.sampled_from([20, 24, 25, 26, 27, 28]), st.integers(1, 400), st.integers(1, 30), st.integers(1, 8), st.integers(0, 8), st.booleans())
+def test_3d_double_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, n2, chunk, neumann):
+    """Random frame shapes / chunk lengths for the 3D double-sweep variants (default, two rows per warp, interior-specialised,
+    de-interleaved u1 ring)."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup([n0, n1, n2], [1.0, 2.0, 3.0], NEUMANN_3D if neumann else MIXED_3D, 2,
+                                                          seed=n0 * 131 + n1 * 17 + n2)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, min(chunk, n2), 1)
+    assert rc == 0
+    np.testing.assert_array_equal(out, want)
+
+
 @pytest.mark.parametrize("n,hi,spec,pairs,nranks,chunk,variant", [
     ([20, 9, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 20),           # two slabs: each rank has one neighbour
     ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 20),         # uneven split (5, 5, 7); the middle rank has both
