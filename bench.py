@@ -386,11 +386,15 @@ def run_e2e(R, ctx, workload, sub_iters, steps):
         for v in n:
             cells *= v
         secs = max(wall, ms_dev * 1e-3)
+        skew = int(os.environ.get("RNMF_E2E_SKEW", "0") or 0)          # opt-in time-skewed upload / download (capi.cu); same bits
         return {"value": cells * sub_iters * steps / secs / 1e9, "unit": "GLUP/s",
                 "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes + 8,
                 "ms_per_step": 1e3 * secs / steps, "steps": steps,
                 "call": "rnmf_solve_poisson_host: pinned host psi+rhs (dense reference layout) -> H2D -> "
-                        f"{sub_iters} sweeps(+fill_bc) + L1 norm -> D2H psi"}
+                        f"{sub_iters} sweeps(+fill_bc) + L1 norm -> D2H psi" + (f" (e2e_skew={skew})" if skew else ""),
+                # of the last call's output frame: equal across e2e_skew settings (the field bit for bit, the norm to rounding)
+                "checks": {"abs_sum_out": float(sum(float(np.abs(out_h[i:i + (1 << 24)]).sum()) for i in range(0, count, 1 << 24))),
+                           "l1_update": l1.value}}
     finally:
         for p in bufs:
             L.rnmf_host_free(p)

@@ -39,7 +39,7 @@ python - <<'PY'
 import json
 for n in ("3d_e2e_plain", "3d_e2e_skew", "3d_e2e_skew2"):
     try:
-        d = json.load(open(f"gpurun_out/r2exp_{n}.json")); print(n, "value", round(d["value"], 1), "e2e", d["e2e"])
+        d = json.load(open(f"gpurun_out/r2exp_{n}.json")); print(n, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "GLUP/s", round(d["e2e"]["ms_per_step"], 1), "ms", d["e2e"]["checks"])
     except Exception as e:
         print(n, "failed", e)
 PY
