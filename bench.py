@@ -173,18 +173,24 @@ def build_roofline(main_res: dict, steps: int, sub_iters: int, workload: str, pe
     # the norm-carrying single sweep, the shell copy and the reduction)
     double = main_res["doubles"] * 2 > steps * sub_iters // 2
     sweeps_per_launch = 2 if double else 1
+    # K sweeps per launch (the opt-in K-sweep 2D kernel): average depth of the temporally blocked launches of the region
+    if main_res.get("multi_launches") and main_res.get("multi_sweeps", 0) * 2 > steps * sub_iters:
+        depth = main_res["multi_sweeps"] / main_res["multi_launches"]
+        double = True
+        sweeps_per_launch = int(round(depth)) if abs(depth - round(depth)) < 1e-9 else depth
     launch_ms = sweep_ms * sweeps_per_launch
     alg_bytes = BYTES_PER_LUP * main_res["local_cells"] * sweeps_per_launch   # 24 B per update x updates per launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9                           # GB/s per GPU (the slowest rank's clock)
-    traffic = ncu_traffic(workload + ("_tb2" if double else ""))
+    traffic = ncu_traffic(workload + ("_tb2" if sweeps_per_launch == 2 else f"_tb{sweeps_per_launch}" if double else ""))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
-                "kernel": "double sweep (2 sweeps + fused ghost fills per launch)" if double else "jacobi sweep (fused ghost fill)",
+                "kernel": (f"{'double' if sweeps_per_launch == 2 else 'multi'} sweep ({sweeps_per_launch} sweeps + fused ghost fills per launch)"
+                           if double else "jacobi sweep (fused ghost fill)"),
                 "sweeps_per_launch": sweeps_per_launch, "double_sweep_launches": main_res["doubles"],
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "avg_launch_ms": launch_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
     if double:
-        roofline["note"] = ("achieved counts the ALGORITHMIC 24 B per update; the kernel performs two updates per byte pass "
+        roofline["note"] = ("achieved counts the ALGORITHMIC 24 B per update; the kernel performs several updates per byte pass "
                             "(temporal blocking), so frac can exceed 1. dram_frac = measured DRAM traffic per launch / launch time / peak.")
         if traffic:
             roofline["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
@@ -318,17 +324,19 @@ def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, redu
     coef = poisson.poisson_coefs(dim, mesh.dx)
     for _ in range(warmup):
         poisson.jacobi_sweeps(psi, rhs, sub_iters, want_norm=True, coef=coef)
-    launches0, doubles0 = ctx.kernel_launches, ctx.double_sweep_launches
+    launches0, doubles0, multi0 = ctx.kernel_launches, ctx.double_sweep_launches, ctx.multi_sweep_stats
     ms, l1 = timed_steps(ctx, psi, rhs, coef, sub_iters, steps, barrier)
     launches = ctx.kernel_launches - launches0
     doubles = ctx.double_sweep_launches - doubles0
+    multi1 = ctx.multi_sweep_stats
+    multi = (multi1[0] - multi0[0], multi1[1] - multi0[1])      # temporally blocked launches, sweeps they covered
     ms = reduce_max(ms)
     cells = 1
     for v in n:
         cells *= v
     lups = cells * sub_iters * steps
     checksum = psi.ctx.allreduce_sum(psi.abs_sum())
-    res = dict(n_global=n, ms=ms, ms_per_step=ms / steps, glups=lups / (ms * 1e-3) / 1e9, launches=launches, doubles=doubles,
+    res = dict(n_global=n, ms=ms, ms_per_step=ms / steps, glups=lups / (ms * 1e-3) / 1e9, launches=launches, doubles=doubles, multi_launches=multi[0], multi_sweeps=multi[1],
                l1_last=l1, abs_sum=checksum, local_cells=int(psi.n_local[0] * psi.n_local[1] * (psi.n_local[2] if dim == 3 else 1)))
     psi.close()
     rhs.close()

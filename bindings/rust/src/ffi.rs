@@ -75,6 +75,7 @@ extern "C" {
     pub fn rnmf_ctx_rank(ctx: *mut rnmf_ctx, rank: *mut i32, nranks: *mut i32) -> i32;
     pub fn rnmf_kernel_launches(ctx: *mut rnmf_ctx) -> i64;
     pub fn rnmf_double_sweep_launches(ctx: *mut rnmf_ctx) -> i64;
+    pub fn rnmf_multi_sweep_stats(ctx: *mut rnmf_ctx, launches: *mut i64, sweeps: *mut i64) -> i32;
     pub fn rnmf_timer_begin(ctx: *mut rnmf_ctx) -> i32;
     pub fn rnmf_timer_end(ctx: *mut rnmf_ctx, elapsed_ms: *mut f64) -> i32;
     pub fn rnmf_set_option(ctx: *mut rnmf_ctx, key: *const c_char, value: *const c_char) -> i32;

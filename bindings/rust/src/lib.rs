@@ -104,6 +104,12 @@ impl Context {
     pub fn double_sweep_launches(&self) -> i64 {
         unsafe { ffi::rnmf_double_sweep_launches(self.raw) }
     }
+    /// (launches, sweeps covered) of all temporally blocked launches
+    pub fn multi_sweep_stats(&self) -> (i64, i64) {
+        let (mut l, mut s) = (0i64, 0i64);
+        ffi::check(unsafe { ffi::rnmf_multi_sweep_stats(self.raw, &mut l, &mut s) }, "rnmf_multi_sweep_stats");
+        (l, s)
+    }
     /// sum of a host scalar over all ranks (identity on a single-GPU context)
     pub fn allreduce_sum(&self, v: Real) -> Real {
         let mut x = v;

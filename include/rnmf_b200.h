@@ -112,6 +112,9 @@ int64_t rnmf_kernel_launches(rnmf_ctx* ctx);
 /* how many of those were double-sweep kernels (two Jacobi sweeps + ghost fills per pass over HBM, 2D and 3D;
  * rnmf_jacobi_sweeps pairs up every two sweeps that do not carry the norm) -- bench.py's roofline accounting */
 int64_t rnmf_double_sweep_launches(rnmf_ctx* ctx);
+/* all temporally blocked launches (two or more sweeps per pass over HBM: the double-sweep kernels and the opt-in K-sweep 2D
+ * kernel) and the number of sweeps they covered, since the context was created; either pointer may be null */
+int32_t rnmf_multi_sweep_stats(rnmf_ctx* ctx, int64_t* launches, int64_t* sweeps);
 /* CUDA-event timer on the context's stream: begin records, end records+synchronises. */
 int32_t rnmf_timer_begin(rnmf_ctx* ctx);
 int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rnmf_ctx_rank": (C.c_int32, [_vp, _P(C.c_int32), _P(C.c_int32)]),
     "rnmf_kernel_launches": (C.c_int64, [_vp]),
     "rnmf_double_sweep_launches": (C.c_int64, [_vp]),
+    "rnmf_multi_sweep_stats": (C.c_int32, [_vp, _i64p, _i64p]),
     "rnmf_timer_begin": (C.c_int32, [_vp]),
     "rnmf_timer_end": (C.c_int32, [_vp, _dp]),
     "rnmf_set_option": (C.c_int32, [_vp, C.c_char_p, C.c_char_p]),

@@ -129,6 +129,7 @@ struct rnmf_ctx {
     int sweep_variant = 0;
     long long double_sweeps = 0;                  // launches of the two-sweeps-per-pass kernel (rnmf_double_sweep_launches)
     long long multi_sweeps = 0;                   // launches of the K-sweeps-per-pass 2D kernel (opt-in variants 32..37)
+    long long multi_sweep_sweeps = 0;             // sweeps those launches covered
     int sweep_chunk = 0;
     int overlap_halo = 1;
     ncclComm_t comm = nullptr;
@@ -367,6 +368,13 @@ extern "C" int32_t rnmf_ctx_rank(rnmf_ctx* c, int32_t* rank, int32_t* nranks)
 
 extern "C" int64_t rnmf_kernel_launches(rnmf_ctx* c) { return c ? c->launches : 0; }
 extern "C" int64_t rnmf_double_sweep_launches(rnmf_ctx* c) { return c ? c->double_sweeps : 0; }
+extern "C" int32_t rnmf_multi_sweep_stats(rnmf_ctx* c, int64_t* launches, int64_t* sweeps)
+{
+    RNMF_REQUIRE(c, "ctx is null");
+    if (launches) *launches = c->double_sweeps + c->multi_sweeps;
+    if (sweeps) *sweeps = 2 * c->double_sweeps + c->multi_sweep_sweeps;
+    return RNMF_OK;
+}
 
 extern "C" int32_t rnmf_timer_begin(rnmf_ctx* c)
 {
@@ -958,6 +966,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             t.k_begin = 0; t.k_end = m;
             RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, s));
             c->multi_sweeps += 1;
+            c->multi_sweep_sweeps += tbk_depth;
             double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
             psi->parity ^= 1;
             it += tbk_depth - 1;

@@ -59,6 +59,13 @@ class Context:
         return int(_capi.lib().rnmf_double_sweep_launches(self._h))
 
     @property
+    def multi_sweep_stats(self):
+        """(launches, sweeps covered) of all temporally blocked launches: double-sweep kernels and the K-sweep 2D kernel"""
+        a, b = C.c_int64(), C.c_int64()
+        _capi.check(_capi.lib().rnmf_multi_sweep_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    @property
     def stream(self) -> int:
         s = C.c_void_p()
         _capi.check(_capi.lib().rnmf_ctx_stream(self._h, C.byref(s)))

@@ -252,12 +252,14 @@ def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, vari
         g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=33)
         ora.fill_bc(g, psi0, obc)
         psi.fill_bc()
-        k0, d0 = ctx.kernel_launches, ctx.double_sweep_launches
+        k0, d0, m0 = ctx.kernel_launches, ctx.double_sweep_launches, ctx.multi_sweep_stats
         l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=norm)
         ctx.sync()
         pairable = sweeps - (1 if norm else 0)
         groups, rest = divmod(pairable, K)
         assert ctx.double_sweep_launches - d0 == rest // 2             # leftovers run as pairs, then singles
+        m1 = ctx.multi_sweep_stats
+        assert (m1[0] - m0[0], m1[1] - m0[1]) == (groups + rest // 2, groups * K + 2 * (rest // 2))
         # ghost-shell copy + K-sweep launches + pairs + singles (+ the norm's reduction): the K-sweep kernel really ran
         assert ctx.kernel_launches - k0 == 1 + groups + rest // 2 + rest % 2 + (2 if norm else 0)
         want = psi0.copy()
