@@ -489,20 +489,22 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
     const FrameGeom& g = a.g;
     const long long span = a.k_end - a.k_begin;
     const long long bx = (g.n[0] + Cfg::TXC - 1) / Cfg::TXC;
-    // chunk length: whole waves of MINB CTAs per SM, each CTA paying chunk + 2(K-1) + 1 row iterations
-    long long best_c = 1, best_cost = -1;
-    static const int cand[] = { 4, 8, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512 };
-    for (int c : cand) {
-        const long long cc = c > span ? span : c;
-        if (cc < 1) break;
-        const long long chunks = (span + cc - 1) / cc;
-        if (chunks <= 60000) {
-            const long long per_wave = 148LL * MINB;
-            const long long waves = (bx * chunks + per_wave - 1) / per_wave;
-            const long long cost = waves * (cc + 2 * (K - 1) + 1);
-            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_c = cc; }
-        }
-        if (c >= span) break;
+    // chunk length: W whole waves of 148*MINB CTAs, each CTA paying chunk + 2(K-1) + 1 row iterations.  For every W the
+    // largest number of chunks that still fits W waves gives the shortest chunk; take the cheapest W (8192^2, 768-column strips:
+    // 40 chunks of 205 rows = 440 CTAs = 2.97 waves, 4 % above the wave-free ideal; the fixed candidate list gave 10 %).
+    long long best_c = span, best_cost = -1;
+    const long long per_wave = 148LL * MINB, ramp = 2 * (K - 1) + 1;
+    for (long long W = 1; W <= 64; ++W) {
+        long long chunks = W * per_wave / bx;
+        if (chunks < 1) continue;
+        if (chunks > span) chunks = span;
+        if (chunks > 60000) chunks = 60000;
+        long long cc = (span + chunks - 1) / chunks;
+        if (cc < 16 * K) cc = 16 * K < span ? 16 * K : span;        // a chunk re-reads 2K rows: keep that below ~12 % of its traffic
+        const long long ctas = bx * ((span + cc - 1) / cc);
+        const long long cost = ((ctas + per_wave - 1) / per_wave) * (cc + ramp);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = cc; }
+        if (chunks == span) break;
     }
     if (a.chunk_override > 0) best_c = a.chunk_override > span ? span : a.chunk_override;
     if (best_c < 1) best_c = 1;
