@@ -10,7 +10,9 @@
 //     its centre / S neighbour the two before it -- a two-row register window per level, so N/S never
 //     touch shared memory.  Shared memory serves the next u0 row, rhs, and the E/W neighbours: rows of
 //     u_1..u_{K-1} live in two-slot rings (with the x-face ghosts fill_bc would give them); the y-face
-//     ghosts of u_1..u_{K-1} are formed in registers; rhs of the last K-1 rows is a register queue;
+//     ghosts of u_1..u_{K-1} are formed in registers; c0*rhs of the last K-1 rows is a register queue
+//     (the product is rounded once and reused by every level); warps that own no face / ragged cell run
+//     a copy of the loop without ghost code and store masks; with DI the ring rows are de-interleaved;
 //   * one more consumer warp computes the halo columns: level l on the K-l columns either side of the
 //     strip, one lane per (level, column), levels chained through the rings with __syncwarp
 //     (redundant work K(K-1)/(128*NW) per row; a chunk re-reads 2K rows);
