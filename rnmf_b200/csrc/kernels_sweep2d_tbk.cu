@@ -178,11 +178,13 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
     // ---- every shared-memory load of the iteration, issued together ----
     const uint32_t pslot = (uint32_t)((it - 1) & 1) * Cfg::RSLOT, slot = (uint32_t)(it & 1) * Cfg::RSLOT;
     double uw_a[K - 1], ue_a[K - 1], uw_b[K - 1], ue_b[K - 1];      // [s-1]: E/W of the row level s formed in the previous iteration
+    // (the 512-column K = 4 form has 170 registers per thread: there the ring loads are issued level by level instead)
+    constexpr bool LAZY = K >= 4 && NW <= 4;
 #pragma unroll
     for (int s = 1; s < K; ++s) {
         const bool act = STEADY || (it >= k.lp.first[s] && it <= k.lp.last[s]);       // level s+1
         uw_a[s - 1] = ue_a[s - 1] = uw_b[s - 1] = ue_b[s - 1] = 0.0;
-        if (act) {
+        if (act && !LAZY) {
             const uint32_t up = k.ua + (uint32_t)(2 * (s - 1)) * Cfg::RSLOT + pslot;
             ring_ld_ew<Cfg, DI>(up, uw_a[s - 1], ue_a[s - 1], uw_b[s - 1], ue_b[s - 1]);
         }
@@ -220,6 +222,10 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
             if (!STEADY) {
                 if (it == k.lp.it_ylo[l - 1]) { dn_a = ghost1(k.fy0, ce_a); dn_b = ghost1(k.fy0, ce_b); }
                 if (it == k.lp.it_yhi[l - 1]) { up_a = ghost1(k.fy1, ce_a); up_b = ghost1(k.fy1, ce_b); }
+            }
+            if (LAZY) {
+                const uint32_t up = k.ua + (uint32_t)(2 * (s - 1)) * Cfg::RSLOT + pslot;
+                ring_ld_ew<Cfg, DI>(up, uw_a[s - 1], ue_a[s - 1], uw_b[s - 1], ue_b[s - 1]);
             }
             const double2 r_a = st.rq_a[l - 2], r_b = st.rq_b[l - 2];
             o_a.x = updk(k.c1, k.c2, r_a.x, ce_a.y, uw_a[s - 1], up_a.x, dn_a.x);
