@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next round: the opt-in kernels that were written and emulator-checked without a GPU
-# (2D K-sweep kernel, variants 32..37; 3D two-rows-per-warp double sweep, variants 24/25, interior-specialised loops, variants 26/27; time-skewed e2e start): parity first, then
+# (2D K-sweep kernel, variants 32..38; 3D two-rows-per-warp double sweep, variants 24/25, interior-specialised loops, variants 26/27; time-skewed e2e start): parity first, then
 # short sustained benches per variant.  One GPU, about 10 minutes.  Results: gpurun_out/r2exp_*.json|log
 mkdir -p gpurun_out
 export RNMF_EXPERIMENTAL=1
@@ -22,6 +22,7 @@ run 2d_v34_k4w_c512 python bench.py $S2 --variant 34 --chunk 512
 run 2d_v32_k3_c128 python bench.py $S2 --variant 32 --chunk 128
 run 2d_v36_k3_di python bench.py $S2 --variant 36
 run 2d_v37_k4w_di python bench.py $S2 --variant 37
+run 2d_v38_k4_di python bench.py $S2 --variant 38
 # 3D 768^3
 S3="--workload 3d7_768 --steps 3 --warmup 3 --sub-iters 550 --no-e2e --no-cpu-baseline --no-others"
 run 3d_v0 python bench.py $S3

@@ -226,9 +226,9 @@ def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
         ctx.set_option("resident", 1)
 
 
-# K = 3 / 4 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..37): validated on the CPU box by the kernel emulator
+# K = 3 / 4 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..38): validated on the CPU box by the kernel emulator
 # (test_emulated_kernels); on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 runs them here
-_MULTI_SWEEP_2D = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4}
+_MULTI_SWEEP_2D = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4}
 
 
 @pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in kernels: set RNMF_EXPERIMENTAL=1")
