@@ -153,7 +153,6 @@ struct rnmf_ctx {
     int e2e_skew = 0;                     // option "e2e_skew" (opt-in): time-skewed start of rnmf_solve_poisson_host
     int e2e_skew_chunks = 8, e2e_skew_pairs = 56; // upload chunks, double sweeps run band-wise during the upload
     int e2e_skew_tail = 32;                       // e2e_skew >= 2: last launches run band-wise so the download overlaps them
-    cudaEvent_t ev_tail = nullptr;
     std::vector<cudaEvent_t> ev_chunks;   // one per upload chunk
     long long skew_launches = 0;          // double-sweep launches issued by the skewed start (a test reads it back)
 };
@@ -335,7 +334,6 @@ extern "C" int32_t rnmf_ctx_destroy(rnmf_ctx* c)
     if (c->ev_boundary) cudaEventDestroy(c->ev_boundary);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     for (cudaEvent_t e : c->ev_chunks) cudaEventDestroy(e);
-    if (c->ev_tail) cudaEventDestroy(c->ev_tail);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream_halo) cudaStreamDestroy(c->stream_halo);
     delete c;
