@@ -140,9 +140,10 @@ __device__ __forceinline__ void load4(const double* q, double2& a, double2& b, c
 // One plane iteration of a row warp: level 1 of plane a+it (DO_L1) and level 2 of plane q = a+it-1 (DO_L2).
 // All shared-memory loads of both levels are issued behind ONE wait phase; level 2's x/y part is formed
 // before level 1's result exists (part2), its z term is added once u1 of plane a+it is known (fin2).
-// EDGE = false (interior-specialised kernels only): the warp owns no cell next to an x / y face, no cell past the frame, and the
-// iteration meets neither the z-lo face nor a slab neighbour -- the ghost code and the store masks are compiled out.
-template <int TY, int NS, bool DO_L1, bool DO_L2, bool EDGE = true>
+// EDGE (specialised kernels only): 2 = general; 0 = the warp owns no cell next to an x / y face, no cell past the frame, and the
+// iteration meets neither the z-lo face nor a slab neighbour -- the ghost code and the store masks are compiled out;
+// 1 = as 0, but some lane sits next to an x face of a whole (even-width) tile: only the x-ghost code stays.
+template <int TY, int NS, bool DO_L1, bool DO_L2, int EDGE = 2>
 __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowSt& st, const int it)
 {
     using Cfg = Tb2Cfg<TY, NS>;
@@ -186,36 +187,36 @@ __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowS
         u1n_b.y = upd3(k.c0, k.c1, k.c2, k.c3, rc_b.y, e_b1, st.cur_b.x, n_b.y, s_b.y, above_b.y, st.below_b.y);
         // odd n0: the last valid cell is the first of a pair, whose E neighbour at level 2 is the pair's
         // second register: it must hold the x-hi ghost of u1, not a stencil value
-        if (EDGE && k.xhi_sel == 0) u1n_a.y = ghost1(k.fx1, u1n_a.x);
-        if (EDGE && k.xhi_sel == 2) u1n_b.y = ghost1(k.fx1, u1n_b.x);
+        if (EDGE == 2 && k.xhi_sel == 0) u1n_a.y = ghost1(k.fx1, u1n_a.x);
+        if (EDGE == 2 && k.xhi_sel == 2) u1n_b.y = ghost1(k.fx1, u1n_b.x);
 
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);              // this warp is done with the stage of plane a+it
         const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
-        sstore4(us, u1n_a, u1n_b, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        sstore4(us, u1n_a, u1n_b, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
         // what fill_bc gives u1 on the physical x / y faces (read by level 2 of the edge cells)
-        if (EDGE && k.any_x) {
+        if (EDGE != 0 && k.any_x) {
             if (k.do_xlo) sts1(us - 8, ghost1(k.fx0, u1n_a.x));
             if (k.xhi_sel >= 0) {
                 const double m = k.xhi_sel == 0 ? u1n_a.x : k.xhi_sel == 1 ? u1n_a.y : k.xhi_sel == 2 ? u1n_b.x : u1n_b.y;
                 sts1(us + k.xhi_off, ghost1(k.fx1, m));
             }
         }
-        if (EDGE && k.any_y) {
-            if (k.do_ylo) sstore4(us - BX * 8, ghost1(k.fy0, u1n_a), ghost1(k.fy0, u1n_b), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (k.do_yhi) sstore4(us + BX * 8, ghost1(k.fy1, u1n_a), ghost1(k.fy1, u1n_b), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE == 2 && k.any_y) {
+            if (k.do_ylo) sstore4(us - BX * 8, ghost1(k.fy0, u1n_a), ghost1(k.fy0, u1n_b), EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.do_yhi) sstore4(us + BX * 8, ghost1(k.fy1, u1n_a), ghost1(k.fy1, u1n_b), EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
         // slab neighbours get u1 of my boundary plane (half step) over NVLink
-        if (EDGE && it == k.it_u1lo) store4(p.peer_u1_lo + k.xy_off, u1n_a, u1n_b, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
-        if (EDGE && it == k.it_u1hi) store4(p.peer_u1_hi + k.xy_off, u1n_a, u1n_b, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE == 2 && it == k.it_u1lo) store4(p.peer_u1_lo + k.xy_off, u1n_a, u1n_b, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE == 2 && it == k.it_u1hi) store4(p.peer_u1_hi + k.xy_off, u1n_a, u1n_b, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
     }
     if (DO_L2) {
         // ---------------- level 2: u2 of plane q = a+it-1 ----------------
         // z neighbours of u1: registers, the face's ghost rule, or the neighbour slab's plane
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
-        const bool zlo = EDGE && it == k.it_zlo;
+        const bool zlo = EDGE == 2 && it == k.it_zlo;
         if (zlo) {
             if (k.fz0.on) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
             else if (p.u1_in_lo) load4(p.u1_in_lo + k.xy_off, dn_a, dn_b, k);
@@ -231,25 +232,25 @@ __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowS
         nb.y = fin2(P_b.y, k.c3, up_b.y, dn_b.y);
 
         double* oa = st.oa;
-        store4(oa, na, nb, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
-        if (EDGE && k.any_x) {
+        store4(oa, na, nb, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE != 0 && k.any_x) {
             if (k.do_xlo) oa[-1] = ghost1(k.fx0, na.x);
             if (k.xhi_sel >= 0) {
                 const double m = k.xhi_sel == 0 ? na.x : k.xhi_sel == 1 ? na.y : k.xhi_sel == 2 ? nb.x : nb.y;
                 oa[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, m);
             }
         }
-        if (EDGE && k.any_y) {
-            if (k.do_ylo) store4(oa - k.pitch, ghost1(k.fy0, na), ghost1(k.fy0, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (k.do_yhi) store4(oa + k.pitch, ghost1(k.fy1, na), ghost1(k.fy1, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE == 2 && k.any_y) {
+            if (k.do_ylo) store4(oa - k.pitch, ghost1(k.fy0, na), ghost1(k.fy0, nb), EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.do_yhi) store4(oa + k.pitch, ghost1(k.fy1, na), ghost1(k.fy1, nb), EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         if (zlo) {
-            if (k.fz0.on) store4(oa - k.plane_sz, ghost1(k.fz0, na), ghost1(k.fz0, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (p.peer_lo_plane) store4(p.peer_lo_plane + k.xy_off, na, nb, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.fz0.on) store4(oa - k.plane_sz, ghost1(k.fz0, na), ghost1(k.fz0, nb), EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_lo_plane) store4(p.peer_lo_plane + k.xy_off, na, nb, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         if (!DO_L1) {
-            if (k.fz1.on) store4(oa + k.plane_sz, ghost1(k.fz1, na), ghost1(k.fz1, nb), !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
-            if (p.peer_hi_plane) store4(p.peer_hi_plane + k.xy_off, na, nb, !EDGE || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (k.fz1.on) store4(oa + k.plane_sz, ghost1(k.fz1, na), ghost1(k.fz1, nb), EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_hi_plane) store4(p.peer_hi_plane + k.xy_off, na, nb, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
         }
         st.oa = oa + k.plane_sz;
     }
@@ -439,17 +440,32 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
         // warp-uniform: the whole 128-cell row is valid and away from the x / y faces, and the chunk has no slab role
         const bool interior = SPEC && row_ok && i0 + TX <= n0 && !(k.fx0.on && i0 == 0) && !(k.fx1.on && i0 + TX == n0) &&
                               !k.any_y && !a_sync_lo && !a_sync_hi && !is_b;
+        // the same tile shape with an x face on one side (n0 a multiple of the tile width): only the x-ghost code is kept
+        const bool xface_only = SPEC && !interior && row_ok && i0 + TX <= n0 && !k.any_y && !a_sync_lo && !a_sync_hi && !is_b;
         if (SPEC && interior) {
-            for (; it < n_l1_only; ++it) row_iter<TY, NS, true, false, false>(p, k, st, it);
+            for (; it < n_l1_only; ++it) row_iter<TY, NS, true, false, 0>(p, k, st, it);
             if (do_l2) {
                 // the first two-level iteration may meet the z-lo face: general code, once
-                if (it < nL1) { row_iter<TY, NS, true, true, true>(p, k, st, it); ++it; }
+                if (it < nL1) { row_iter<TY, NS, true, true, 2>(p, k, st, it); ++it; }
                 for (; it < nL1; it += 3) {
-                    row_iter<TY, NS, true, true, false>(p, k, st, it);
+                    row_iter<TY, NS, true, true, 0>(p, k, st, it);
                     if (it + 1 >= nL1) { ++it; break; }
-                    row_iter<TY, NS, true, true, false>(p, k, st, it + 1);
+                    row_iter<TY, NS, true, true, 0>(p, k, st, it + 1);
                     if (it + 2 >= nL1) { it += 2; break; }
-                    row_iter<TY, NS, true, true, false>(p, k, st, it + 2);
+                    row_iter<TY, NS, true, true, 0>(p, k, st, it + 2);
+                }
+                if (top) row_iter<TY, NS, false, true>(p, k, st, nL1);
+            }
+        } else if (SPEC && xface_only) {
+            for (; it < n_l1_only; ++it) row_iter<TY, NS, true, false, 1>(p, k, st, it);
+            if (do_l2) {
+                if (it < nL1) { row_iter<TY, NS, true, true, 2>(p, k, st, it); ++it; }
+                for (; it < nL1; it += 3) {
+                    row_iter<TY, NS, true, true, 1>(p, k, st, it);
+                    if (it + 1 >= nL1) { ++it; break; }
+                    row_iter<TY, NS, true, true, 1>(p, k, st, it + 1);
+                    if (it + 2 >= nL1) { it += 2; break; }
+                    row_iter<TY, NS, true, true, 1>(p, k, st, it + 2);
                 }
                 if (top) row_iter<TY, NS, false, true>(p, k, st, nL1);
             }
@@ -619,8 +635,8 @@ __device__ __forceinline__ void ld4g(const double* q, C4& v, const RowK2& k, int
 }
 
 // One plane iteration of a two-row warp (rows r0 = 2w and r0+1 of the tile): see row_iter for the protocol.
-// EDGE = false: interior-specialised copy (see row_iter)
-template <int TY, int NS, bool DO_L1, bool DO_L2, bool EDGE = true, bool DI = false>
+// EDGE: 2 = general, 0 = interior-specialised copy, 1 = x-ghost code only (see row_iter)
+template <int TY, int NS, bool DO_L1, bool DO_L2, int EDGE = 2, bool DI = false>
 __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, RowSt2& st, const int it)
 {
     using Cfg = Tb2Cfg<TY, NS>;
@@ -651,7 +667,7 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
         u1n[1] = upd3_4(k.c, rc[1], st.cur[1], e1, n1, st.cur[0], above[1], st.below[1]);
         // ghosts of u1 that level 2 takes from REGISTERS: odd n0 (E neighbour of the last valid cell is the pair's
         // second register) and the y-hi ghost row when the frame's last row is the warp's first row
-        if (EDGE) {
+        if (EDGE == 2) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 if (k.xhi_sel == 0) u1n[r].a.y = ghost1(k.fx1, u1n[r].a.x);
@@ -663,9 +679,9 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
         const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
-        st4s<EDGE, DI>(us, u1n[0], k, 0);
-        st4s<EDGE, DI>(us + RB, u1n[1], k, 1);
-        if (EDGE && k.any_x) {
+        st4s<EDGE == 2, DI>(us, u1n[0], k, 0);
+        st4s<EDGE == 2, DI>(us + RB, u1n[1], k, 1);
+        if (EDGE != 0 && k.any_x) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
                 if (k.ok[r]) {
@@ -673,17 +689,17 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
                     if (k.xhi_sel >= 0) sts1(us + r * RB + k.xhi_off, ghost1(k.fx1, xhi_pick(u1n[r], k.xhi_sel)));
                 }
         }
-        if (EDGE && k.do_ylo) st4s<true, DI>(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
-        if (EDGE && k.yhi_row == 1) st4s<true, DI>(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
+        if (EDGE == 2 && k.do_ylo) st4s<true, DI>(us - RB, ghost4(k.fy0, u1n[0]), k, 0);
+        if (EDGE == 2 && k.yhi_row == 1) st4s<true, DI>(us + 2 * RB, ghost4(k.fy1, u1n[1]), k, 1);
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
-        if (EDGE && it == k.it_u1lo) { st4g(p.peer_u1_lo + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_lo + k.xy_off + k.pitch, u1n[1], k, 1); }
-        if (EDGE && it == k.it_u1hi) { st4g(p.peer_u1_hi + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_hi + k.xy_off + k.pitch, u1n[1], k, 1); }
+        if (EDGE == 2 && it == k.it_u1lo) { st4g(p.peer_u1_lo + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_lo + k.xy_off + k.pitch, u1n[1], k, 1); }
+        if (EDGE == 2 && it == k.it_u1hi) { st4g(p.peer_u1_hi + k.xy_off, u1n[0], k, 0); st4g(p.peer_u1_hi + k.xy_off + k.pitch, u1n[1], k, 1); }
     }
     if (DO_L2) {
         // ---------------- level 2: u2 of plane q = a+it-1, both rows ----------------
         C4 dn[2] = { st.u1lo[0], st.u1lo[1] }, upv[2] = { u1n[0], u1n[1] };
-        const bool zlo = EDGE && it == k.it_zlo;
+        const bool zlo = EDGE == 2 && it == k.it_zlo;
         if (zlo) {
             if (k.fz0.on) { dn[0] = ghost4(k.fz0, st.u1c[0]); dn[1] = ghost4(k.fz0, st.u1c[1]); }
             else if (p.u1_in_lo) { ld4g(p.u1_in_lo + k.xy_off, dn[0], k, 0); ld4g(p.u1_in_lo + k.xy_off + k.pitch, dn[1], k, 1); }
@@ -697,13 +713,13 @@ __device__ __forceinline__ void row2_iter(const Tb2Params& p, const RowK2& k, Ro
         for (int r = 0; r < 2; ++r) {
             const C4 u2 = fin2_4(P[r], k.c.c3, upv[r], dn[r]);
             double* o = oa + r * k.pitch;
-            st4g<EDGE>(o, u2, k, r);
-            if (EDGE && k.any_x && k.ok[r]) {
+            st4g<EDGE == 2>(o, u2, k, r);
+            if (EDGE != 0 && k.any_x && k.ok[r]) {
                 if (k.do_xlo) o[-1] = ghost1(k.fx0, u2.a.x);
                 if (k.xhi_sel >= 0) o[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, xhi_pick(u2, k.xhi_sel));
             }
-            if (EDGE && r == 0 && k.do_ylo) st4g(o - k.pitch, ghost4(k.fy0, u2), k, 0);
-            if (EDGE && k.yhi_row == r) st4g(o + k.pitch, ghost4(k.fy1, u2), k, r);
+            if (EDGE == 2 && r == 0 && k.do_ylo) st4g(o - k.pitch, ghost4(k.fy0, u2), k, 0);
+            if (EDGE == 2 && k.yhi_row == r) st4g(o + k.pitch, ghost4(k.fy1, u2), k, r);
             if (zlo) {
                 if (k.fz0.on) st4g(o - k.plane_sz, ghost4(k.fz0, u2), k, r);
                 if (p.peer_lo_plane) st4g(p.peer_lo_plane + k.xy_off + r * k.pitch, u2, k, r);
@@ -924,28 +940,39 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
         // warp-uniform: both rows are whole rows of the frame away from the x / y faces, and the chunk has no slab role
         const bool interior = SPEC && k.ok[1] && i0 + TX <= n0 && !(k.fx0.on && i0 == 0) && !(k.fx1.on && i0 + TX == n0) &&
                               !k.do_ylo && k.yhi_row < 0 && !a_sync_lo && !a_sync_hi && !is_b;
+        const bool xface_only = SPEC && !interior && k.ok[1] && i0 + TX <= n0 && !k.do_ylo && k.yhi_row < 0 && !a_sync_lo && !a_sync_hi && !is_b;
         if (SPEC && interior) {
-            for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, false, DI>(p, k, st, it);
+            for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, 0, DI>(p, k, st, it);
             // the first two-level iteration may meet the z-lo face: general code, once
-            if (it < nL1) { row2_iter<TY, NS, true, true, true, DI>(p, k, st, it); ++it; }
+            if (it < nL1) { row2_iter<TY, NS, true, true, 2, DI>(p, k, st, it); ++it; }
             for (; it < nL1; it += 3) {
-                row2_iter<TY, NS, true, true, false, DI>(p, k, st, it);
+                row2_iter<TY, NS, true, true, 0, DI>(p, k, st, it);
                 if (it + 1 >= nL1) break;
-                row2_iter<TY, NS, true, true, false, DI>(p, k, st, it + 1);
+                row2_iter<TY, NS, true, true, 0, DI>(p, k, st, it + 1);
                 if (it + 2 >= nL1) break;
-                row2_iter<TY, NS, true, true, false, DI>(p, k, st, it + 2);
+                row2_iter<TY, NS, true, true, 0, DI>(p, k, st, it + 2);
+            }
+        } else if (SPEC && xface_only) {
+            for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, 1, DI>(p, k, st, it);
+            if (it < nL1) { row2_iter<TY, NS, true, true, 2, DI>(p, k, st, it); ++it; }
+            for (; it < nL1; it += 3) {
+                row2_iter<TY, NS, true, true, 1, DI>(p, k, st, it);
+                if (it + 1 >= nL1) break;
+                row2_iter<TY, NS, true, true, 1, DI>(p, k, st, it + 1);
+                if (it + 2 >= nL1) break;
+                row2_iter<TY, NS, true, true, 1, DI>(p, k, st, it + 2);
             }
         } else {
-        for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, true, DI>(p, k, st, it);
+        for (; it < it_l2_first; ++it) row2_iter<TY, NS, true, false, 2, DI>(p, k, st, it);
         for (; it < nL1; it += 3) {
-            row2_iter<TY, NS, true, true, true, DI>(p, k, st, it);
+            row2_iter<TY, NS, true, true, 2, DI>(p, k, st, it);
             if (it + 1 >= nL1) break;
-            row2_iter<TY, NS, true, true, true, DI>(p, k, st, it + 1);
+            row2_iter<TY, NS, true, true, 2, DI>(p, k, st, it + 1);
             if (it + 2 >= nL1) break;
-            row2_iter<TY, NS, true, true, true, DI>(p, k, st, it + 2);
+            row2_iter<TY, NS, true, true, 2, DI>(p, k, st, it + 2);
         }
         }
-        if (top) row2_iter<TY, NS, false, true, true, DI>(p, k, st, nL1);
+        if (top) row2_iter<TY, NS, false, true, 2, DI>(p, k, st, nL1);
     }
     if (a_sync_lo || a_sync_hi || is_b) {
         if (p.ps.enabled) {
