@@ -9,8 +9,8 @@ echo "pytest rc=$?"; grep -v "^E  \|^$" gpurun_out/r2exp_pytest.log | tail -15
 unset RNMF_EXPERIMENTAL
 run() { name=$1; shift; timeout 200 "$@" > gpurun_out/r2exp_$name.json 2> gpurun_out/r2exp_$name.err; python -c "
 import json; d=json.load(open('gpurun_out/r2exp_$name.json')); print('$name', round(d['value'],1), 'GLUP/s', round(d['ms_per_step'],2), 'ms/step', d['clocks']['sm_mhz'], d['clocks']['reasons'], d['clocks']['power_w_max'], d['gpu_launches'])" || tail -3 gpurun_out/r2exp_$name.err; }
-# 2D 8192^2: 480 sweeps per step divide by 2, 3 and 4 (the roofline object of these lines assumes <= 2 sweeps per launch: read `value`)
-S2="--workload 2d5_8192 --steps 10 --warmup 3 --sub-iters 480 --no-e2e --no-cpu-baseline --no-others"
+# 2D 8192^2: 480 sweeps per step divide by 2, 3 and 4; 40 steps = 2-5 s per run, long enough for the power cap to settle
+S2="--workload 2d5_8192 --steps 40 --warmup 3 --sub-iters 480 --no-e2e --no-cpu-baseline --no-others"
 run 2d_v20_single python bench.py $S2 --variant 20
 run 2d_v30_tb2 python bench.py $S2 --variant 30
 run 2d_v35_k2 python bench.py $S2 --variant 35
