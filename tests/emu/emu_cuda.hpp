@@ -12,7 +12,8 @@
 // barrier protocols (a wrong parity or a missing arrival deadlocks here as it would on the device: the
 // launcher gives up after a timeout), and -- with several launches running concurrently on "devices"
 // that share the process's memory -- the slab handshake.  It does not model timing, memory-model
-// reordering or register limits; an optional static bank model counts shared-memory wavefronts (below).  tests/test_emulated_kernels.py drives it on the CPU box.
+// reordering or register limits.  It does check alignment and bounds of shared-memory accesses, TMA destinations and
+// boxes (device faults), and an optional static bank model counts shared-memory wavefronts (below).  tests/test_emulated_kernels.py drives it on the CPU box.
 #pragma once
 #ifndef RNMF_EMULATE
 #error "emu_cuda.hpp is for -DRNMF_EMULATE builds (tests) only"
@@ -72,8 +73,18 @@ struct Cta {
     std::unique_ptr<Barrier> cta_bar;
     std::vector<std::unique_ptr<Barrier>> warp_bars;
     unsigned char* smem = nullptr;
+    size_t smem_bytes = 0;
     std::atomic<bool> timed_out{false};
 };
+
+// ---- access checks the device would turn into "misaligned address" / "illegal address" faults ----
+// every ld/st.shared must be naturally aligned and inside the CTA's dynamic shared memory; a TMA destination must be
+// 128-byte aligned (no swizzle), an mbarrier 8-byte aligned.  Violations are counted (the launch then reports failure).
+inline std::atomic<int> g_faults{0};
+inline void fault(const char* what, unsigned long long a, unsigned long long n)
+{
+    if (g_faults.fetch_add(1) < 5) std::fprintf(stderr, "emu: %s (address %llu, %llu bytes)\n", what, a, n);
+}
 
 inline thread_local Cta* g_cta = nullptr;
 inline thread_local int g_warp = 0;
@@ -99,6 +110,8 @@ inline std::atomic<long long> g_wf_load{0}, g_wf_store{0}, g_instr_load{0}, g_in
 // source-level access) executed for the n-th time by each lane: robust against lanes that make extra accesses elsewhere
 __attribute__((noinline)) inline void smem_access(uint32_t addr, int bytes, bool store)
 {
+    if (addr % (uint32_t)bytes != 0) fault("misaligned ld/st.shared", addr, (unsigned long long)bytes);
+    if ((size_t)addr + (size_t)bytes > g_cta->smem_bytes) fault("ld/st.shared outside the CTA's shared memory", addr, (unsigned long long)bytes);
     if (!g_trace.load(std::memory_order_relaxed)) return;
     const void* site = __builtin_return_address(0);
     const unsigned nth = g_site_count[site]++;
@@ -151,6 +164,7 @@ inline void mbar_check(MBar& b, Cta& c)
 }
 inline void mbar_init(uint32_t bar, uint32_t count)
 {
+    if (bar % 8 != 0 || (size_t)bar + 8 > g_cta->smem_bytes) fault("mbarrier misaligned / outside shared memory", bar, 8);
     Cta& c = *g_cta;
     std::lock_guard<std::mutex> lk(c.mu);
     MBar b;
@@ -206,6 +220,11 @@ inline void tma_load(uint32_t dst, const CUtensorMap* tm, long long c0, long lon
     std::memcpy(&m, tm, sizeof(m));
     double* out = reinterpret_cast<double*>(g_cta->smem + dst);
     const unsigned bz = m.rank == 3 ? m.box[2] : 1;
+    const size_t box_bytes = (size_t)m.box[0] * m.box[1] * bz * 8;
+    if (dst % 128 != 0) fault("TMA destination not 128-byte aligned", dst, box_bytes);
+    if ((size_t)dst + box_bytes > g_cta->smem_bytes) fault("TMA box outside the CTA's shared memory", dst, box_bytes);
+    if ((m.box[0] * 8) % 16 != 0 || m.box[0] > 256 || m.box[1] > 256) fault("TMA box shape not encodable", m.box[0], m.box[1]);
+    if ((reinterpret_cast<uintptr_t>(m.base) % 16) != 0 || (m.stride[1] * 8) % 16 != 0) fault("TMA global base / stride not 16-byte aligned", 0, 0);
     long long bytes = 0;
     for (unsigned z = 0; z < bz; ++z)
         for (unsigned y = 0; y < m.box[1]; ++y)
@@ -241,11 +260,13 @@ template <class Kernel, class... Args>
 bool launch(Kernel kernel, dim3 grid, int threads, unsigned char* smem, size_t smem_bytes, Args... args)
 {
     bool ok = true;
+    const int faults_before = g_faults.load();
     for (unsigned bz = 0; bz < grid.z; ++bz)
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 Cta cta;
                 cta.smem = smem;
+                cta.smem_bytes = smem_bytes;
                 std::memset(smem, 0xA5, smem_bytes);                 // uninitialised shared memory is garbage, not zero
                 cta.cta_bar.reset(new Barrier(threads));
                 for (int w = 0; w < (threads + 31) / 32; ++w) {
@@ -270,6 +291,7 @@ bool launch(Kernel kernel, dim3 grid, int threads, unsigned char* smem, size_t s
                 for (auto& th : pool) th.join();
                 if (g_trace.load()) trace_flush_cta();
                 if (cta.timed_out) ok = false;
+                if (g_faults.load() > faults_before) ok = false;
             }
     return ok;
 }

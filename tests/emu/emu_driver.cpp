@@ -97,6 +97,26 @@ void init_frame(Frame& f, int dim, const long long* n, const double* dx, const d
     unpack(f.g, rhs_dense, f.rhs.data());
 }
 
+// cells that are not data (padding columns of every pitched row, the tail pad / guard band, the scratch planes) must still hold
+// the poison init_frame put there: a kernel that stores outside the grown rows of its frame is caught here (on the device the
+// canary band of rnmf_frame_check_guards only sees the end of the buffer)
+long long clobbered_padding(const Frame& f)
+{
+    long long bad = 0;
+    const double poison[3] = { -7.0e300, 9.0e300, 5.0e300 };
+    const std::vector<double>* bufs[3] = { &f.buf[0], &f.buf[1], &f.rhs };
+    const long long rows = f.g.G[1] * f.g.G[2];
+    for (int b = 0; b < 3; ++b) {
+        const std::vector<double>& v = *bufs[b];
+        for (long long r = 0; r < rows; ++r)
+            for (long long i = 0; i < f.g.pitch; ++i)
+                if ((i < f.g.xoff || i >= f.g.xoff + f.g.G[0]) && v[(size_t)(f.g.pitch * r + i)] != poison[b]) ++bad;
+        for (size_t q = (size_t)f.g.total; q < v.size(); ++q)
+            if (v[q] != poison[b]) ++bad;
+    }
+    return bad;
+}
+
 FaceSet make_faces(int dim, const int* kind, const double* value, const double* dx)
 {
     FaceSet fs;
@@ -137,11 +157,18 @@ void selftest_ok_kernel(CUtensorMap tm)
     // box (-1..2, row 0) of a 3-wide row {5,6,7}: out-of-bounds column -1 reads as zero
     if (tmau::lds1(dst) != 0.0 || tmau::lds1(dst + 8) != 5.0 || tmau::lds1(dst + 24) != 7.0) g_deadlocks += 100;
 }
+void selftest_misaligned_kernel(int dummy)
+{
+    (void)dummy;
+    if (threadIdx.x == 0) (void)tmau::lds2(8);             // 16-byte load from an 8-byte aligned address
+    if (threadIdx.x == 1) (void)tmau::lds1(256);           // one past the 256 bytes of the CTA
+}
 }  // namespace
 
 extern "C" {
 
 void emu_set_timeout(int seconds) { emu::g_wait_timeout_s = seconds; }
+int emu_faults() { return emu::g_faults.load(); }          // access faults (misaligned / out-of-bounds shared memory, bad TMA boxes) so far
 
 // shared-memory wavefront accounting (emu_cuda.hpp): switch it on, run launches on ONE host thread, read the totals
 void emu_trace(int on)
@@ -155,7 +182,8 @@ void emu_trace_read(long long* out)
     out[0] = emu::g_wf_load; out[1] = emu::g_wf_store; out[2] = emu::g_instr_load; out[3] = emu::g_instr_store;
 }
 
-// returns (deadlock detected ? 1 : 0) + 2 * (well-formed CTA completed and read the right TMA data ? 1 : 0): 3 = both as expected
+// returns (deadlock detected ? 1 : 0) + 2 * (well-formed CTA completed and read the right TMA data ? 1 : 0)
+// + 4 * (misaligned / out-of-bounds shared-memory accesses reported ? 1 : 0): 7 = all as expected
 int emu_selftest()
 {
     g_deadlocks = 0;
@@ -165,14 +193,20 @@ int emu_selftest()
     emu::g_wait_timeout_s = saved;
     const int dead = g_deadlocks.load() == 1;
     g_deadlocks = 0;
-    static const double row[3] = { 5.0, 6.0, 7.0 };
+    alignas(16) static const double row[4] = { 5.0, 6.0, 7.0, -1.0 };       // a 3-wide row with a 16-byte aligned pitch, as TMA demands
     emu::Map m;
-    m.base = row; m.rank = 2; m.dims[0] = 3; m.dims[1] = 1; m.dims[2] = 1; m.stride[0] = 1; m.stride[1] = 3; m.stride[2] = 0;
+    m.base = row; m.rank = 2; m.dims[0] = 3; m.dims[1] = 1; m.dims[2] = 1; m.stride[0] = 1; m.stride[1] = 4; m.stride[2] = 0;
     m.box[0] = 4; m.box[1] = 1; m.box[2] = 1;
     CUtensorMap tm;
     emu::encode(&tm, m);
     emu_launch_checked(selftest_ok_kernel, dim3(2, 1, 1), 64, 512, tm);
-    return dead + 2 * (g_deadlocks.load() == 0);
+    const int ok = g_deadlocks.load() == 0;
+    // ... and a misaligned 16-byte shared-memory load / an access past the CTA's shared memory must be reported as a failed launch
+    g_deadlocks = 0;
+    emu_launch_checked(selftest_misaligned_kernel, dim3(1, 1, 1), 32, 256, 0);
+    const int caught = g_deadlocks.load() == 1;
+    g_deadlocks = 0;
+    return dead + 2 * ok + 4 * caught;
 }
 
 // n_pairs double sweeps of one frame on one "device".  face kinds: RNMF_BC_*; coef4 from the oracle.
@@ -210,7 +244,9 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
         f.cur ^= 1;
     }
     pack(f.g, f.buf[f.cur].data(), out_dense);
-    return g_deadlocks.load();
+    const long long bad = clobbered_padding(f);
+    if (bad) fprintf(stderr, "emu: %lld padding / tail cells were overwritten\n", bad);
+    return g_deadlocks.load() + (bad ? 1000 : 0);
 }
 
 // the band schedules themselves (common.cuh), for the abstract dependency check in tests/test_skew_schedule.py

@@ -41,8 +41,8 @@ def emu():
     return lib
 
 
-def test_the_emulator_reports_deadlocks_and_models_tma_zero_fill(emu):
-    assert emu.emu_selftest() == 3
+def test_the_emulator_reports_deadlocks_access_faults_and_models_tma_zero_fill(emu):
+    assert emu.emu_selftest() == 7
 
 
 def _p(a):
