@@ -148,6 +148,9 @@ __device__ __forceinline__ double2 ghost1(const Face1& f, const double2& m) { re
 // store the four cells of a lane (two pairs, 64 cells apart) with the tile-edge validity masks
 __device__ __forceinline__ void store4(double* a, const double2& va, const double2& vb, bool full, bool a0, bool a1, bool b0, bool b1)
 {
+#ifdef RNMF_EMULATE
+    if ((full || a1 || b1) && reinterpret_cast<uintptr_t>(a) % 16 != 0) emu::fault("misaligned 16-byte global store", reinterpret_cast<uintptr_t>(a), 16);
+#endif
     if (full) {
         *reinterpret_cast<double2*>(a) = va;
         *reinterpret_cast<double2*>(a + 64) = vb;
