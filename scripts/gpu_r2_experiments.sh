@@ -4,8 +4,18 @@
 # short sustained benches per variant.  One GPU, about 10 minutes.  Results: gpurun_out/r2exp_*.json|log
 mkdir -p gpurun_out
 export RNMF_EXPERIMENTAL=1
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "multi_sweep or double_sweep or time_skewed" > gpurun_out/r2exp_pytest.log 2>&1
-echo "pytest rc=$?"; grep -v "^E  \|^$" gpurun_out/r2exp_pytest.log | tail -15
+: > gpurun_out/r2exp_pytest.log
+# one pytest process per opt-in variant: a kernel that hangs costs one 150 s timeout, not the whole call
+for v in 35 32 33 34 36 37 38; do
+  RNMF_EXPERIMENTAL_VARIANTS=$v timeout 150 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "2d_multi_sweep" > gpurun_out/r2exp_pytest_v$v.log 2>&1
+  echo "parity 2D variant $v rc=$? $(tail -1 gpurun_out/r2exp_pytest_v$v.log)" | tee -a gpurun_out/r2exp_pytest.log
+done
+for v in 24 25 26 27 28; do
+  RNMF_EXPERIMENTAL_VARIANTS=$v timeout 150 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "3d_double_sweep" > gpurun_out/r2exp_pytest_v$v.log 2>&1
+  echo "parity 3D variant $v rc=$? $(tail -1 gpurun_out/r2exp_pytest_v$v.log)" | tee -a gpurun_out/r2exp_pytest.log
+done
+timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "time_skewed" > gpurun_out/r2exp_pytest_skew.log 2>&1
+echo "parity time-skewed host call rc=$? $(tail -1 gpurun_out/r2exp_pytest_skew.log)" | tee -a gpurun_out/r2exp_pytest.log
 unset RNMF_EXPERIMENTAL
 run() { name=$1; shift; timeout 200 "$@" > gpurun_out/r2exp_$name.json 2> gpurun_out/r2exp_$name.err; python -c "
 import json; d=json.load(open('gpurun_out/r2exp_$name.json')); print('$name', round(d['value'],1), 'GLUP/s', round(d['ms_per_step'],2), 'ms/step', d['clocks']['sm_mhz'], d['clocks']['reasons'], d['clocks']['power_w_max'], d['gpu_launches'])" || tail -3 gpurun_out/r2exp_$name.err; }

@@ -30,4 +30,5 @@ for wl, lst in rows.items():
         print(line)
 log = os.path.join(ROOT, "gpurun_out", "r2exp_pytest.log")
 if os.path.exists(log):
-    print("== parity (RNMF_EXPERIMENTAL=1):", open(log).read().strip().splitlines()[-1])
+    print("== parity (RNMF_EXPERIMENTAL=1)")
+    print(open(log).read().rstrip())

@@ -228,7 +228,10 @@ def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
 
 # K = 3 / 4 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..38): validated on the CPU box by the kernel emulator
 # (test_emulated_kernels); on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 runs them here
-_MULTI_SWEEP_2D = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4}
+# RNMF_EXPERIMENTAL_VARIANTS=32,36 restricts the opt-in variants under test (one pytest process per variant on the GPU box, so
+# that a hanging kernel costs one short timeout instead of the whole run)
+_ONLY = {int(v) for v in os.environ.get("RNMF_EXPERIMENTAL_VARIANTS", "").split(",") if v.strip()}
+_MULTI_SWEEP_2D = {k: v for k, v in {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4}.items() if not _ONLY or k in _ONLY}
 
 
 @pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in kernels: set RNMF_EXPERIMENTAL=1")
@@ -276,7 +279,7 @@ def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, vari
 ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
 # variants 24 / 25 (two rows per row warp) and 26 / 27 (interior-specialised plane loop) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
 # on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 adds them here
-_DOUBLE_SWEEP_VARIANTS = [20, 21] + ([24, 25, 26, 27, 28] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
+_DOUBLE_SWEEP_VARIANTS = [20, 21] + ([v for v in (24, 25, 26, 27, 28) if not _ONLY or v in _ONLY] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
