@@ -121,8 +121,8 @@ int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);
 /* tuning knobs for measurements (results never change, only which kernel / schedule produces them):
  *   "sweep_variant"  "auto" (default) or a number: 3D 1-4,10,11 = non-TMA kernels, 6 = single-sweep TMA kernel only,
  *                    20/21 = double sweep 128x12 / 128x8, 24/25 = two rows per warp, 26/27 = interior-specialised loops
- *                    (24-27 opt-in); 2D 1,2 = non-TMA, 20 = single-sweep TMA only, 30 = double sweep, 32-38 = three /
- *                    four sweeps per pass (opt-in)
+ *                    (24-28 opt-in); 2D 1,2 = non-TMA, 20 = single-sweep TMA only, 30 = double sweep, 32-40 = three ..
+ *                    six sweeps per pass (opt-in)
  *   "sweep_chunk"    planes / rows marched per CTA (0 = planner)
  *   "resident"       1/0: one cooperative launch for all sweeps of an L2-resident frame
  *   "peer_halo", "peer_inkernel", "halo_overlap"   slab halo exchange: fused peer-memory path / in-kernel handshake / NCCL overlap

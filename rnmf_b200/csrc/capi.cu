@@ -128,7 +128,7 @@ struct rnmf_ctx {
     long long partial_cap = 0;
     int sweep_variant = 0;
     long long double_sweeps = 0;                  // launches of the two-sweeps-per-pass kernel (rnmf_double_sweep_launches)
-    long long multi_sweeps = 0;                   // launches of the K-sweeps-per-pass 2D kernel (opt-in variants 32..38)
+    long long multi_sweeps = 0;                   // launches of the K-sweeps-per-pass 2D kernel (opt-in variants 32..40)
     long long multi_sweep_sweeps = 0;             // sweeps those launches covered
     int sweep_chunk = 0;
     int overlap_halo = 1;
@@ -952,7 +952,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
 
     // 2D analogue (kernels_sweep2d_tb2.cu): single GPU; variant 0 = auto, 30 = explicit, 20 = single-sweep TMA kernel only
-    // K = 2..4 sweeps per pass (kernels_sweep2d_tbk.cu; opt-in variants 32..38): groups of K sweeps, the rest as pairs / singles
+    // K = 2..6 sweeps per pass (kernels_sweep2d_tbk.cu; opt-in variants 32..40): groups of K sweeps, the rest as pairs / singles
     const int tbk_depth = g.dim == 2 ? multi_sweep_2d_depth(c->sweep_variant) : 0;
     const bool tb2_2d = g.dim == 2 && (c->sweep_variant == 0 || c->sweep_variant == 30 || tbk_depth > 0) && !dist && fused && xy_faces;
     const bool tbk_2d = tb2_2d && tbk_depth > 0;

@@ -275,7 +275,7 @@ int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s);
 int double_sweep_boundary_ctas(const Tb2Args& t);
 // 2D analogue (kernels_sweep2d_tb2.cu), single GPU: a.k_begin..a.k_end = output rows
 int launch_jacobi_double_sweep_2d(const SweepArgs& a, cudaStream_t s);
-// K = 2..4 sweeps per launch (kernels_sweep2d_tbk.cu; opt-in variants 32..38), single GPU
+// K = 2..6 sweeps per launch (kernels_sweep2d_tbk.cu; opt-in variants 32..40), single GPU
 int multi_sweep_2d_depth(int variant);              // sweeps per launch of the variant, 0 if it is not a K-sweep variant
 int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s);
 int sweep_boundary_ctas(const SweepArgs& a);     // CTAs per boundary side (tiles across the slice) of the kernel that will run

@@ -302,8 +302,8 @@ int tma2d_sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s);
 // 2D default (variant 0 = auto, or 20): the TMA row-streaming kernel; variants 1/2 = jacobi2d_ymarch
 // (variant 30 selects the 2D double-sweep kernel for pairs of sweeps; its single sweeps are this kernel)
-// (variants 32..38 select the K-sweep kernel for groups of K sweeps, kernels_sweep2d_tbk.cu; same single sweeps)
-static inline bool use_tma2d(const SweepArgs& a) { return a.g.dim == 2 && (a.variant == 0 || a.variant == 20 || a.variant == 30 || (a.variant >= 32 && a.variant <= 38)); }
+// (variants 32..40 select the K-sweep kernel for groups of K sweeps, kernels_sweep2d_tbk.cu; same single sweeps)
+static inline bool use_tma2d(const SweepArgs& a) { return a.g.dim == 2 && (a.variant == 0 || a.variant == 20 || a.variant == 30 || (a.variant >= 32 && a.variant <= 40)); }
 
 bool sweep_supports_peer_halo(const SweepArgs& a) { return use_tma(a) || use_tma2d(a); }
 int tma_sweep_boundary_ctas(const SweepArgs& a);

@@ -1,7 +1,7 @@
-// kernels_sweep2d_tbk.cu -- K1 for 2D frames, temporally blocked over K = 2, 3 or 4 sweeps: K 5-point
+// kernels_sweep2d_tbk.cu -- K1 for 2D frames, temporally blocked over K = 2 .. 6 sweeps: K 5-point
 // Jacobi sweeps (each followed by the ng=1 ghost fill, poisson.rs:80-89 + dataframe.rs:289-355) per
 // pass over HBM, i.e. 24/K algorithmic bytes per update.  Generalises kernels_sweep2d_tb2.cu (K = 2);
-// OPT-IN (sweep variants 32..38) until it has been measured on the device.
+// OPT-IN (sweep variants 32..40) until it has been measured on the device.
 //   * a CTA owns a strip of 128*NW columns and marches a chunk of rows in y; the producer warp streams
 //     one row of psi (u0) and one of rhs per stage, the strip plus PAD >= K halo columns either side;
 //   * NW consumer warps own 128 cells each (lane l: pairs 2l,2l+1 and 64+2l,65+2l).  Level l = 1..K
@@ -543,14 +543,14 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
 // sweeps per launch of a 2D sweep variant (0: the variant is not a K-sweep variant)
 int multi_sweep_2d_depth(int variant)
 {
-    return variant == 32 || variant == 36 ? 3 : variant == 33 || variant == 34 || variant == 37 || variant == 38 ? 4 : variant == 35 ? 2 : 0;
+    return variant == 32 || variant == 36 ? 3 : variant == 33 || variant == 34 || variant == 37 || variant == 38 ? 4 : variant == 35 ? 2 : variant == 39 ? 5 : variant == 40 ? 6 : 0;
 }
 
 // K sweeps (+ ghost fills) per launch, a.k_begin..a.k_end = output rows; every x / y face must carry a
 // Dirichlet or Neumann rule (the caller checks).  Variants: 32 = three sweeps, 512-column strips, two CTAs per SM;
 // 33 = four sweeps, same shape; 34 = four sweeps, 768-column strips (8 warps), one CTA per SM (255 registers);
 // 35 = two sweeps through this kernel (cross-check against kernels_sweep2d_tb2.cu); 36 / 37 / 38 = 32 / 34 / 33 with de-interleaved
-// ring rows (dense E/W loads).
+// ring rows (dense E/W loads); 39 / 40 = five / six sweeps per pass (768-column strips, de-interleaved).
 int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
@@ -562,6 +562,8 @@ int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
     case 36: return launch_tbk<3, 4, 8, 2, true>(a, s);      // 32 with de-interleaved ring rows
     case 37: return launch_tbk<4, 6, 8, 1, true>(a, s);      // 34 with de-interleaved ring rows
     case 38: return launch_tbk<4, 4, 8, 2, true>(a, s);      // 33 with de-interleaved ring rows
+    case 39: return launch_tbk<5, 6, 8, 1, true>(a, s);      // five sweeps per pass, 768-column strips, de-interleaved (238 registers)
+    case 40: return launch_tbk<6, 6, 8, 1, true>(a, s);      // six sweeps per pass (253 registers, no spills)
     default: return -1;
     }
 }

@@ -42,7 +42,7 @@ def main():
     # 2D: 3 strips of 512 (2 of 768 for the 768-column variants), one 96-row chunk
     for name, variant, depth, n in (("2D tb2 (30, default)", 30, 2, [1536, 96]), ("2D tbk K=2 (35)", 35, 2, [1536, 96]),
                                     ("2D tbk K=3 (32)", 32, 3, [1536, 96]), ("2D tbk K=3 de-interleaved (36)", 36, 3, [1536, 96]),
-                                    ("2D tbk K=4 768 cols (34)", 34, 4, [1536, 96]), ("2D tbk K=4 768 cols de-interleaved (37)", 37, 4, [1536, 96]), ("2D tbk K=4 512 cols de-interleaved (38)", 38, 4, [1536, 96])):
+                                    ("2D tbk K=4 768 cols (34)", 34, 4, [1536, 96]), ("2D tbk K=4 768 cols de-interleaved (37)", 37, 4, [1536, 96]), ("2D tbk K=4 512 cols de-interleaved (38)", 38, 4, [1536, 96]), ("2D tbk K=5 768 cols de-interleaved (39)", 39, 5, [1536, 96]), ("2D tbk K=6 768 cols de-interleaved (40)", 40, 6, [1536, 96])):
         rows.append((name, run(lib, n, [1.0, 1.0], T.MIXED_2D, variant, 96, depth)))
     # 3D: 3 x 2 tiles of 128 x 12 (x 16 for variant 25), one 24-plane chunk
     for name, variant, n in (("3D tb2 128x12 (0/20, default)", 20, [384, 24, 24]), ("3D tb2x two rows per warp (24)", 24, [384, 24, 24]),

@@ -122,10 +122,10 @@ def test_2d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     np.testing.assert_array_equal(out, want)
 
 
-DEPTH = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4}      # 36 / 37: de-interleaved ring rows      # sweeps per launch of the K-sweep 2D variants (kernels_sweep2d_tbk.cu)
+DEPTH = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4, 39: 5, 40: 6}      # 36 / 37: de-interleaved ring rows      # sweeps per launch of the K-sweep 2D variants (kernels_sweep2d_tbk.cu)
 
 
-@pytest.mark.parametrize("variant", [35, 32, 33, 34, 36, 37, 38])
+@pytest.mark.parametrize("variant", [35, 32, 33, 34, 36, 37, 38, 39, 40])
 @pytest.mark.parametrize("n,hi,spec,launches,chunk", [
     ([33, 7], [1.0, 2.0], MIXED_2D, 1, 0),
     ([513, 5], [513.0, 5.0], MIXED_2D, 2, 2),                    # one cell past a 512-column strip; 3 row chunks; ping-pong
@@ -152,7 +152,7 @@ from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
 @settings(max_examples=30, deadline=None, derandomize=True)
-@given(st.sampled_from([32, 33, 34, 35, 36, 37, 38]), st.integers(1, 1100), st.integers(1, 14), st.integers(0, 14), st.integers(0, 3),
+@given(st.sampled_from([32, 33, 34, 35, 36, 37, 38, 39, 40]), st.integers(1, 1100), st.integers(1, 14), st.integers(0, 14), st.integers(0, 3),
        st.integers(1, 2))
 def test_2d_multi_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, chunk, bc, launches):
     """Random frame shapes / chunk lengths / face rules for the K-sweep kernel: strips that end anywhere, chunks shorter than the

@@ -226,12 +226,12 @@ def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
         ctx.set_option("resident", 1)
 
 
-# K = 3 / 4 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..38): validated on the CPU box by the kernel emulator
+# K = 3 .. 6 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..40): validated on the CPU box by the kernel emulator
 # (test_emulated_kernels); on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 runs them here
 # RNMF_EXPERIMENTAL_VARIANTS=32,36 restricts the opt-in variants under test (one pytest process per variant on the GPU box, so
 # that a hanging kernel costs one short timeout instead of the whole run)
 _ONLY = {int(v) for v in os.environ.get("RNMF_EXPERIMENTAL_VARIANTS", "").split(",") if v.strip()}
-_MULTI_SWEEP_2D = {k: v for k, v in {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4}.items() if not _ONLY or k in _ONLY}
+_MULTI_SWEEP_2D = {k: v for k, v in {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4, 39: 5, 40: 6}.items() if not _ONLY or k in _ONLY}
 
 
 @pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in kernels: set RNMF_EXPERIMENTAL=1")
