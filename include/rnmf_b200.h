@@ -151,7 +151,11 @@ int32_t rnmf_frame_info_get(const rnmf_frame* f, rnmf_frame_info* out);
 int32_t rnmf_frame_check_guards(rnmf_frame* f, int32_t* ok);
 /* the `bc: BCs<S>` field (dataframe.rs:59): n_faces must be n_comp*dim*2 */
 int32_t rnmf_frame_set_bc(rnmf_frame* f, const rnmf_bc_face* faces, int32_t n_faces);
-/* host mirror <-> device (replaces direct access to `data: Vec<S>`, dataframe.rs:37) */
+/* host mirror <-> device (replaces direct access to `data: Vec<S>`, dataframe.rs:37).
+ * The two uploads are ASYNCHRONOUS: they return once the copy is queued on the context's stream.  With pageable host
+ * memory the runtime has staged the source by then; with pinned memory (rnmf_host_alloc) the caller must not modify or
+ * free the buffer before rnmf_sync(ctx) (or any synchronising call: a download, a norm) has returned.  The downloads
+ * synchronise.  The safe wrappers of the bindings (C++ frame.hpp, Rust DeviceFrame::upload, Python `data =`) sync. */
 int32_t rnmf_frame_upload(rnmf_frame* f, const double* host_dense);
 int32_t rnmf_frame_download(rnmf_frame* f, double* host_dense);
 /* get_valid_cells (dataframe.rs:181-189): valid cells, flat order, all components */

@@ -144,6 +144,7 @@ struct rnmf_ctx {
     unsigned long long done_target_b[2] = { 0, 0 }; // same for the B chunks of the double-sweep kernel
     int peer_inkernel = 1;                        // option "peer_inkernel": handshake inside the sweep kernel
     int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
+    int peer_used = 0;                            // a fused-halo sweep has been launched (check_peer_status has something to check)
     double* d_staging = nullptr;                  // dense staging for large uploads (1-D PCIe copy + device repack)
     long long staging_cap = 0;                    // doubles
     int resident = 1;                             // option "resident": multi-sweep cooperative kernel for L2-resident frames
@@ -206,6 +207,21 @@ int bind(rnmf_ctx* c)
 {
     RNMF_CUDA_TRY(cudaSetDevice(c->device));
     return RNMF_OK;
+}
+
+// Fused peer-memory halo: a handshake wait that ran out of patience leaves the awaited epoch in d_flags[2] and lets the
+// kernel go on (never a hang), which means stale halo slices.  Every synchronising entry point (rnmf_sync, the downloads,
+// norm-carrying sweep calls) ends with this check, so that no result computed after a time-out is handed to the caller as
+// good.  The word is cleared once reported.  The stream must be idle.
+int check_peer_status(rnmf_ctx* c)
+{
+    if (c->nranks == 1 || !c->d_flags || !c->peer_used) return RNMF_OK;
+    unsigned long long st = 0;
+    RNMF_CUDA_TRY(cudaMemcpy(&st, c->d_flags + 2, 8, cudaMemcpyDeviceToHost));
+    if (!st) return RNMF_OK;
+    RNMF_CUDA_TRY(cudaMemset(c->d_flags + 2, 0, 8));
+    rnmf_set_error("peer halo handshake timed out waiting for epoch %llu: halo slices are stale, results since then are invalid", st);
+    return RNMF_ERR_NCCL;
 }
 
 // 3D one-component ng=1 frames carry two scratch planes behind the guard band: the u1 boundary planes
@@ -346,7 +362,7 @@ extern "C" int32_t rnmf_sync(rnmf_ctx* c)
     if (bind(c)) return RNMF_ERR_CUDA;
     RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream_halo));
     RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return RNMF_OK;
+    return check_peer_status(c);
 }
 
 extern "C" int32_t rnmf_ctx_stream(rnmf_ctx* c, void** s)
@@ -605,7 +621,7 @@ extern "C" int32_t rnmf_frame_download(rnmf_frame* f, double* host)
     RNMF_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)g.G[0] * 8, f->d + g.xoff, (size_t)g.pitch * 8, (size_t)g.G[0] * 8, rows,
                                     cudaMemcpyDeviceToHost, f->ctx->stream));
     RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
-    return RNMF_OK;
+    return check_peer_status(f->ctx);
 }
 
 static int copy_valid(rnmf_frame* f, double* host, bool to_host)
@@ -634,7 +650,7 @@ extern "C" int32_t rnmf_frame_download_valid(rnmf_frame* f, double* host)
     int rc = copy_valid(f, host, true);
     if (rc) return rc;
     RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
-    return RNMF_OK;
+    return check_peer_status(f->ctx);
 }
 
 extern "C" int32_t rnmf_frame_upload_valid(rnmf_frame* f, const double* host)
@@ -1113,17 +1129,15 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     }
     // neighbours' last sweep must have landed in this frame's ghost planes before anything else
     // in this stream touches the frame
-    if (peer) RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
+    if (peer) { RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s)); c->peer_used = 1; }
     RNMF_CUDA_TRY(cudaGetLastError());
     if (l1_update) {
         RNMF_CUDA_TRY(cudaStreamSynchronize(s));
         *l1_update = c->h_scalar[0];
-        if (peer) {
-            unsigned long long st = 0;
-            RNMF_CUDA_TRY(cudaMemcpy(&st, c->d_flags + 2, 8, cudaMemcpyDeviceToHost));
-            if (st) { rnmf_set_error("peer halo handshake timed out waiting for epoch %llu", st); return RNMF_ERR_NCCL; }
-        }
+        return check_peer_status(c);
     }
+    // no norm wanted: the call stays asynchronous; a handshake time-out surfaces at the next synchronising entry point
+    // (rnmf_sync, rnmf_frame_download*, rnmf_abs_sum_valid, a norm-carrying sweep call)
     return RNMF_OK;
 }
 
@@ -1310,7 +1324,7 @@ extern "C" int32_t rnmf_abs_sum_valid(rnmf_frame* f, double* out)
     RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar + 1, c->d_scalar + 1, 8, cudaMemcpyDeviceToHost, c->stream));
     RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c->h_scalar[1];
-    return RNMF_OK;
+    return check_peer_status(c);
 }
 
 static int varcoef_impl(const rnmf_frame* phi, const rnmf_mu_params* mu, int with_source, double relax, rnmf_frame* out)
@@ -1320,6 +1334,11 @@ static int varcoef_impl(const rnmf_frame* phi, const rnmf_mu_params* mu, int wit
     RNMF_REQUIRE(mu, "mu params null");
     RNMF_REQUIRE(phi->g.dim == 2 && phi->g.ncomp == 1, "variable-mu operator: 2D, n_comp=1 (poisson.rs:13-44)");
     RNMF_REQUIRE(out != phi, "out must not alias phi");
+    // mu(i, j) is evaluated from the LOCAL index and the Dirichlet(0) mirror is written on all four sides: a slab frame
+    // on rank > 0 would get a misplaced droplet and mirrored values in its halo rows.  The outer loop of the example is
+    // "replicas only" (reference-order GS does not decompose), so slabs are refused rather than silently wrong.
+    RNMF_REQUIRE(!(phi->distributed && phi->ctx->nranks > 1) && !(out->distributed && out->ctx->nranks > 1),
+                 "variable-mu operator: slab (distributed) frames are not supported; use replicated frames");
     if (bind(out->ctx)) return RNMF_ERR_CUDA;
     RNMF_LAUNCH(out->ctx, launch_varcoef_2d(phi->g, phi->d, *mu, with_source, relax, out->d, out->ctx->stream));
     RNMF_CUDA_TRY(cudaGetLastError());

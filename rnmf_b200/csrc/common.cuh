@@ -11,6 +11,19 @@
 
 #define RNMF_ROW_ALIGN 16  // doubles (128 bytes)
 
+#ifndef RNMF_EMULATE
+#include <atomic>
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE opt-in and rnmf_ctx_create(device) allows several
+// devices (and host threads) in one process: remember the opt-in per device, atomically (one flag per kernel instantiation).
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> bits[2];
+    PerDeviceOnce() { bits[0] = 0; bits[1] = 0; }
+    static int dev() { int d = 0; cudaGetDevice(&d); return d; }
+    bool done() const { const int d = dev(); return d < 128 && ((bits[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1ULL); }
+    void mark() { const int d = dev(); if (d < 128) bits[d >> 6].fetch_or(1ULL << (d & 63), std::memory_order_release); }
+};
+#endif
+
 struct FrameGeom {
     int dim, ng, ncomp;
     long long n[3];      // valid cells

@@ -18,10 +18,12 @@ inline unsigned ew_blocks(long long n_vec)
 // total is a multiple of 16 doubles, so 128-bit accesses need no tail.
 enum { OP_SCALE = 0, OP_ADD = 1, OP_MUL = 2, OP_AXPBY = 3 };
 
+// No __restrict__: the API is used in place (psi = psi + relax*diff passes out == x); each element is read and
+// written once by the same thread, so aliasing is well defined as long as the compiler is not told otherwise.
 template <int OP>
-__global__ void __launch_bounds__(kEwThreads) ew_kernel(long long n2, double a, const double2* __restrict__ x,
-                                                        double b, const double2* __restrict__ y,
-                                                        double2* __restrict__ out)
+__global__ void __launch_bounds__(kEwThreads) ew_kernel(long long n2, double a, const double2* x,
+                                                        double b, const double2* y,
+                                                        double2* out)
 {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2;
          i += (long long)gridDim.x * blockDim.x) {

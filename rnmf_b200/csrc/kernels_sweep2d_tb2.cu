@@ -348,11 +348,11 @@ int launch_jacobi_double_sweep_2d(const SweepArgs& a, cudaStream_t s)
     p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
     p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
 #ifndef RNMF_EMULATE
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done()) {
         if (cudaFuncSetAttribute(jacobi2d_tb2_kernel<kNS2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
         cudaFuncSetAttribute(jacobi2d_tb2_kernel<kNS2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
+        attr_set.mark();
     }
 #endif
     RNMF_KERNEL_LAUNCH(jacobi2d_tb2_kernel<kNS2>, grid, Cfg::THREADS, Cfg::SMEM, s, tm_u256, tm_u4, tm_r256, tm_r4, p);

@@ -527,11 +527,11 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
     p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = (int)best_c;
     auto kern = jacobi2d_tbk_kernel<K, NW, NS, MINB, DI>;
 #ifndef RNMF_EMULATE
-    static bool attr_set = false;                      // one per instantiation
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;                      // one per instantiation
+    if (!attr_set.done()) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
+        attr_set.mark();
     }
 #endif
     RNMF_KERNEL_LAUNCH(kern, grid, Cfg::THREADS, Cfg::SMEM, s, tm_u256, tm_upad, tm_r256, tm_rpad, p);

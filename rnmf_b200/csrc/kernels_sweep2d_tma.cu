@@ -376,11 +376,11 @@ template <bool NORM>
 int launch2d_one(const dim3& grid, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const Tma2dParams& p, cudaStream_t s)
 {
     using Cfg = Cfg2d<kNS2d>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done()) {
         if (cudaFuncSetAttribute(jacobi2d_tma_kernel<kNS2d, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
         cudaFuncSetAttribute(jacobi2d_tma_kernel<kNS2d, NORM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_set = true;
+        attr_set.mark();
     }
     jacobi2d_tma_kernel<kNS2d, NORM><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a, b, c, p);
     return 1;

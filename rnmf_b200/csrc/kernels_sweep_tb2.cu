@@ -1036,10 +1036,10 @@ struct Tb2Launcher {
         p.half_sig_lo = t.half_sig_lo; p.half_sig_hi = t.half_sig_hi;
         p.done_b = t.done_b; p.target_b_lo = t.target_b_lo; p.target_b_hi = t.target_b_hi;
 #ifndef RNMF_EMULATE
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (!attr_set.done()) {
             if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
-            attr_set = true;
+            attr_set.mark();
         }
 #endif
         RNMF_KERNEL_LAUNCH((jacobi3d_tb2_kernel<TY, NS, SPEC>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
@@ -1072,10 +1072,10 @@ struct Tb2xLauncher {
         p.half_sig_lo = t.half_sig_lo; p.half_sig_hi = t.half_sig_hi;
         p.done_b = t.done_b; p.target_b_lo = t.target_b_lo; p.target_b_hi = t.target_b_hi;
 #ifndef RNMF_EMULATE
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (!attr_set.done()) {
             if (cudaFuncSetAttribute(jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC, DI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
-            attr_set = true;
+            attr_set.mark();
         }
 #endif
         RNMF_KERNEL_LAUNCH((jacobi3d_tb2x_kernel<TY, NS, MERGE, SPEC, DI>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);

@@ -348,11 +348,11 @@ struct Launcher {
     template <bool NORM>
     static int launch_one(const dim3& grid, const CUtensorMap& tm_psi, const CUtensorMap& tm_rhs, const TmaSweepParams& p, cudaStream_t s)
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (!attr_set.done()) {
             if (cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, NORM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             cudaFuncSetAttribute(jacobi3d_tma_kernel<TY, NS, NORM, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            attr_set = true;
+            attr_set.mark();
         }
         jacobi3d_tma_kernel<TY, NS, NORM, MINB><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tm_psi, tm_rhs, p);
         return 1;

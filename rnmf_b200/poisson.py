@@ -108,8 +108,11 @@ def jacobi_sweeps(psi: CartesianDataFrame, rhs: CartesianDataFrame, n_sweeps: in
 
 
 def sum(psi: CartesianDataFrame) -> float:  # noqa: A001 - the reference's name (poisson.rs:94)
-    """poisson.rs:94-100, summed over all ranks on a distributed context."""
-    return psi.ctx.allreduce_sum(psi.abs_sum())
+    """poisson.rs:94-100.  A slab (distributed) frame is summed over all ranks; a replicated frame on a multi-rank
+    context (the reference-order GS path is "replicas only") holds the whole domain on every rank, so its sum is local:
+    all-reducing it would multiply sum_diff by the number of ranks and change the `sum_diff > tol` test of main.rs:65."""
+    local = psi.abs_sum()
+    return psi.ctx.allreduce_sum(local) if psi.info.distributed else local
 
 
 def magnetostatics(config: Config, order: str = "reference", ctx: Optional[Context] = None):

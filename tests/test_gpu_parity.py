@@ -590,7 +590,7 @@ def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
     assert norms[1] == norms[0]
     assert abs(norms[2] - norms[0]) <= NORM_RTOL * abs(norms[0])      # same partial sums, grouped by band
     assert launches[1] > launches[0] + chunks          # one band launch per (chunk, pair) instead of one launch per pair
-    assert launches[2] > launches[1]
+    assert launches[2] >= launches[1]                  # equal when too few sweeps remain for a band-wise end (levels < 4)
 
 
 def test_kernel_launch_counter_moves(R, ctx):
@@ -614,10 +614,70 @@ FULL_SIZES = [
 ]
 
 
+def _synthetic_grown(g, n, seed):
+    """the bench's synthetic field in the reference's dense grown layout, generated on the host by numpy
+    in bounded chunks of rows: valid cell q (flat valid index) = splitmix64(seed ^ q) -> (-1, 1); ghosts 0."""
+    out = ora.zeros(g)
+    v = ora.valid_view(g, out)[0]                    # [nz,] ny, nx view into `out`
+    planes = v if len(n) == 3 else v[None]
+    rows_per = max(1, (1 << 23) // n[0])
+    for k in range(planes.shape[0]):
+        for j0 in range(0, n[1], rows_per):
+            j1 = min(n[1], j0 + rows_per)
+            q0 = (k * n[1] + j0) * n[0]
+            planes[k, j0:j1] = ora.splitmix_field((j1 - j0) * n[0], seed, offset=q0).reshape(j1 - j0, n[0])
+    return out
+
+
+@pytest.mark.parametrize("n,spec", FULL_SIZES)
+def test_full_size_oracle_parity(R, ctx, n, spec):
+    """BASELINE.json's own sizes against the oracle, bit for bit (VERDICT r1 "next" #1): the default path runs
+    5 sweeps (two double-sweep launches + the norm-carrying single sweep) of the update expression of
+    examples/magnetostatics/poisson.rs:80-89 (3D: SURVEY 8a's extrapolation) with the fused ghost fill
+    (dataframe.rs:289-433) on the bench's synthetic fields; the oracle does the same with its OpenMP Jacobi loop
+    (out of place => independent of the thread schedule, bit-identical to the serial loop, which
+    tests/test_oracle_known_answers.py checks).  The host-side synthetic field is generated by numpy, so the
+    device generator is checked at full size as well.  Norm: 1e-12 relative against the long-double serial sum."""
+    from rnmf_b200 import poisson
+    dim = len(n)
+    hi = [float(v) for v in n]
+    g = ora.geom(n, hi=hi)
+    obc, bc = _bc_pair(R, dim, spec)
+    mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
+    sweeps = 5
+    psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx)
+    rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx)
+    psi.fill_synthetic(0x5EED0001)
+    rhs.fill_synthetic(0x5EED0002)
+    psi.fill_bc()
+    want = _synthetic_grown(g, n, 0x5EED0001)
+    rhs0 = _synthetic_grown(g, n, 0x5EED0002)
+    assert ora.fill_bc(g, want, obc) == 0
+    got = psi.data
+    assert np.array_equal(got, want), "synthetic field + fill_bc differ from the oracle at full size"
+    assert np.array_equal(rhs.data, rhs0)
+    d0 = ctx.double_sweep_launches
+    l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
+    if dim == 3:
+        assert ctx.double_sweep_launches - d0 == 2, "the default 3D path did not take the double-sweep kernel"
+    l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps, omp=True)
+    del rhs0
+    del got
+    got = psi.data
+    same = np.array_equal(got, want)
+    if not same:
+        bad = np.flatnonzero(got != want)
+        pytest.fail(f"{bad.size} of {got.size} grown cells differ from the oracle; first at flat index {bad[0]}: "
+                    f"{got[bad[0]]!r} vs {want[bad[0]]!r}")
+    assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref), (l1, l1_ref)
+    assert psi.guards_intact()
+    psi.close(); rhs.close()
+
+
 @pytest.mark.parametrize("n,spec", FULL_SIZES)
 def test_full_size_properties(R, ctx, n, spec):
-    """At the benchmark sizes the oracle is too slow, so the CUDA path is checked through properties
-    evaluated entirely on the device:
+    """Extra, size-independent properties at the benchmark sizes (test_full_size_oracle_parity above is the
+    parity test), evaluated entirely on the device:
       (1) determinism: the same call twice gives bit-identical norm and checksum;
       (2) fill_bc is idempotent (second fill changes nothing: |diff| sums to exactly 0);
       (3) linearity: sweeps(a+b; ra+rb) == sweeps(a; ra) + sweeps(b; rb) with homogeneous
