@@ -155,46 +155,57 @@ def measured_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
 
 
-def ncu_traffic(workload: str):
-    """dram bytes per sweep launch from the committed ncu capture, if any (profiles/traffic.json)."""
+def ncu_traffic(key: str):
+    """(dram bytes per launch of the dominant kernel, which capture they come from) from the committed ncu captures
+    (profiles/traffic.json: `ncu --set full`, dram__bytes_read.sum + dram__bytes_write.sum of ONE launch); (None, None) if
+    no capture exists for this workload / kernel.  A property of the kernel at this shape, not of the timed run."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload)
+            t = json.load(f)
+        return t.get(key), (t.get("_sources") or {}).get(key)
     except Exception:
-        return None
+        return None, None
 
 
 def build_roofline(main_res: dict, steps: int, sub_iters: int, workload: str, peak: float, peak_src: str) -> dict:
     """The `roofline` object of the JSON line from one timed region (pure; tested on the CPU).
-    main_res: ms (timed region, max over ranks), doubles (double-sweep launches in it), local_cells."""
+    main_res: ms (timed region, max over ranks), doubles (double-sweep launches in it), multi_launches / multi_sweeps
+    (temporally blocked launches and the sweeps they covered), local_cells, and -- when measured -- kernel_ms: the
+    dominant kernel's average launch duration from CUDA events around `kernel_launches_timed` back-to-back launches."""
     sweep_ms = main_res["ms"] / (steps * sub_iters)                       # average time per sweep over the timed region
-    # dominant kernel: by default the double-sweep kernel (two sweeps + ghost fills per launch, one pass over HBM);
-    # its launch duration is taken as two sweeps' share of the timed region (an upper bound: the region also holds
-    # the norm-carrying single sweep, the shell copy and the reduction)
     double = main_res["doubles"] * 2 > steps * sub_iters // 2
     sweeps_per_launch = 2 if double else 1
-    # K sweeps per launch (the opt-in K-sweep 2D kernel): average depth of the temporally blocked launches of the region
+    # K sweeps per launch: average depth of the temporally blocked launches of the region
     if main_res.get("multi_launches") and main_res.get("multi_sweeps", 0) * 2 > steps * sub_iters:
         depth = main_res["multi_sweeps"] / main_res["multi_launches"]
         double = True
         sweeps_per_launch = int(round(depth)) if abs(depth - round(depth)) < 1e-9 else depth
-    launch_ms = sweep_ms * sweeps_per_launch
+    step_share_ms = sweep_ms * sweeps_per_launch          # the launch's share of the step (an upper bound: the step also holds the
+    #                                                       norm-carrying single sweep, the shell copy and the reduction)
+    launch_ms = main_res.get("kernel_ms") or step_share_ms
     alg_bytes = BYTES_PER_LUP * main_res["local_cells"] * sweeps_per_launch   # SURVEY 8d: 24 B per update x updates per launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9                           # GB/s per GPU (the slowest rank's clock)
-    traffic = ncu_traffic(workload + ("_tb2" if sweeps_per_launch == 2 else f"_tb{sweeps_per_launch}" if double else ""))
+    traffic, traffic_src = ncu_traffic(workload + ("_tb2" if sweeps_per_launch == 2 else f"_tb{sweeps_per_launch}" if double else ""))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": (f"{'double' if sweeps_per_launch == 2 else 'multi'} sweep ({sweeps_per_launch} sweeps + fused ghost fills per launch)"
                            if double else "jacobi sweep (fused ghost fill)"),
                 "sweeps_per_launch": sweeps_per_launch, "double_sweep_launches": main_res["doubles"],
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_ms": launch_ms, "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
+                # the one-pass-per-sweep roofline allows sweeps_per_launch x 24 B-updates per byte pass: frac / K is the
+                # fraction of the ceiling a K-sweeps-per-pass kernel could reach if DRAM were its only limit
+                "frac_of_k_pass_ceiling": achieved / peak / sweeps_per_launch,
+                "avg_launch_ms": launch_ms, "avg_launch_ms_from_step": step_share_ms,
+                "launch_timing": (f"CUDA events around {main_res.get('kernel_launches_timed')} back-to-back launches on the library's stream, "
+                                  "right after the timed steps (same clocks / power state)" if main_res.get("kernel_ms")
+                                  else "the launch's share of the timed region"),
+                "peak_source": peak_src + " -- of measured" if "MEASURED" in peak_src else peak_src}
     if double:
         roofline["note"] = ("achieved counts the ALGORITHMIC 24 B per update; the kernel performs several updates per byte pass "
                             "(temporal blocking), so frac can exceed 1. dram_frac = measured DRAM traffic per launch / launch time / peak.")
-        if traffic:
-            roofline["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
-            roofline["dram_frac"] = roofline["dram_gbs"] / peak
+    if traffic:
+        roofline["dram_gbs"] = traffic / (launch_ms * 1e-3) / 1e9
+        roofline["dram_frac"] = roofline["dram_gbs"] / peak
     return roofline
 
 
@@ -258,7 +269,9 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (splitmix64 field, same seeds as the GPU arm)",
         "config": {"workload": args.workload, "desc": w["desc"], "update_order": "lexicographic Gauss-Seidel (reference)",
                    "sub_iters": sweeps},
-        "cpu_baseline": {"value": value, "unit": "GLUP/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GLUP/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "an UPPER bound for the reference: the thin slab shortens its stride-G0*G1 walk over the slowest index, "
+                                 "and the C port has none of Rust's bounds checks / iterator overhead (SURVEY 8d)"},
         "e2e": {"value": value, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "host": {"nproc": os.cpu_count(), "cpu": _cpu_model()},
@@ -307,7 +320,9 @@ def timed_steps(ctx, psi, rhs, coef, sub_iters, steps, barrier):
     return ms, l1
 
 
-def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, reduce_max):
+def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, reduce_max, kernel_launches_timed=0):
+    """One workload on the context's device(s): warm-up, K device-timed steps, and -- kernel_launches_timed > 0 -- a direct
+    timing of the dominant kernel right afterwards (that many back-to-back launches, no norm, CUDA events on the library's stream)."""
     from rnmf_b200 import poisson
     w = WORKLOADS[workload]
     n = global_shape(workload, nranks)
@@ -335,12 +350,67 @@ def run_config(R, ctx, workload, nranks, sub_iters, steps, warmup, barrier, redu
     for v in n:
         cells *= v
     lups = cells * sub_iters * steps
-    checksum = psi.ctx.allreduce_sum(psi.abs_sum())
+    checksum = psi.ctx.allreduce_sum(psi.abs_sum())             # of the field after (warmup + steps) x sub_iters sweeps
     res = dict(n_global=n, ms=ms, ms_per_step=ms / steps, glups=lups / (ms * 1e-3) / 1e9, launches=launches, doubles=doubles, multi_launches=multi[0], multi_sweeps=multi[1],
                l1_last=l1, abs_sum=checksum, local_cells=int(psi.n_local[0] * psi.n_local[1] * (psi.n_local[2] if dim == 3 else 1)))
+    if kernel_launches_timed > 0:
+        # the dominant kernel alone: a call of depth x L sweeps without the norm is L launches of the temporally blocked
+        # kernel (depth sweeps each) behind one O(surface) shell copy -- timed with CUDA events on the library's stream
+        depth = int(round(multi[1] / multi[0])) if multi[0] and multi[1] * 2 > sub_iters * steps else 1
+        m0 = ctx.multi_sweep_stats
+        barrier()
+        ctx.timer_begin()
+        poisson.jacobi_sweeps(psi, rhs, depth * kernel_launches_timed, want_norm=False, coef=coef)
+        kms = reduce_max(ctx.timer_end())
+        ctx.sync()
+        barrier()
+        m1 = ctx.multi_sweep_stats
+        if depth == 1 or m1[0] - m0[0] == kernel_launches_timed:
+            res["kernel_ms"] = kms / kernel_launches_timed
+            res["kernel_launches_timed"] = kernel_launches_timed
     psi.close()
     rhs.close()
     return res
+
+
+def run_c1_magnetostatics(R, ctx):
+    """BASELINE config 1: examples/magnetostatics/magnetostatics.lua run whole (301^2, 10 outer iterations x 550 sweeps,
+    main.rs:63-74) on the device, in the reference's update order (K6, bit-identical to the reference's lexicographic
+    Gauss-Seidel) and in Jacobi order, next to the oracle's CPU time for the same case (1 thread)."""
+    from rnmf_b200 import config as rconfig, poisson
+    out = {}
+    path = os.path.join(ROOT, "cases", "ferro_droplet.lua")   # same keys and values as examples/magnetostatics/magnetostatics.lua
+    cfg = rconfig.read_lua(path)
+    out["case"] = os.path.relpath(path, ROOT)
+    out["n_cells"] = list(cfg.geom.n_cells)
+    out["n_iter"], out["n_sub_iter"] = int(cfg.model.n_iter), int(cfg.model.n_sub_iter)
+    for order, key in (("reference", "gpu_reference_order_s"), ("jacobi", "gpu_jacobi_order_s")):
+        poisson.magnetostatics(cfg, order=order, ctx=ctx)[0].close()          # warm-up (module load, allocations)
+        ctx.sync()
+        t0 = time.perf_counter()
+        psi, trace, it = poisson.magnetostatics(cfg, order=order, ctx=ctx)
+        ctx.sync()
+        out[key] = time.perf_counter() - t0
+        out[key.replace("_s", "_sum_diff_last")] = trace[-1]
+        out["outer_iterations"] = it
+        psi.close()
+    try:
+        import ctypes as C
+        import numpy as np
+        from oracle import oracle as ora                     # cpu_baseline leg: the oracle as the timed CPU port
+        m = cfg.model
+        g = ora.geom(list(cfg.geom.n_cells), hi=list(cfg.geom.length))
+        om = ora.model(h_far=tuple(m.h_far), relax=m.relax, n_iter=int(m.n_iter), n_sub_iter=int(m.n_sub_iter),
+                       bubble_centre=tuple(m.bubble_centre), bubble_radius=m.bubble_radius, mu=tuple(m.mu), tol=m.tol)
+        ref, tr, it = ora.zeros(g), np.zeros(int(m.n_iter)), C.c_int64()
+        t0 = time.perf_counter()
+        ora.lib().ora_magnetostatics_run(C.byref(g), ref, C.byref(om), 0, tr, C.byref(it))
+        out["cpu_oracle_reference_order_s"] = time.perf_counter() - t0
+        out["cpu_sum_diff_last"] = float(tr[it.value - 1])
+        out["cpu_cores"] = 1
+    except Exception as e:                                   # reported, never hidden
+        out["cpu_error"] = str(e)
+    return out
 
 
 def run_e2e(R, ctx, workload, sub_iters, steps):
@@ -526,7 +596,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    main_res = run_config(R, ctx, args.workload, world, args.sub_iters, args.steps, args.warmup, barrier, reduce_max)
+    main_res = run_config(R, ctx, args.workload, world, args.sub_iters, args.steps, args.warmup, barrier, reduce_max,
+                          kernel_launches_timed=60)
     if rank == 0:
         sampler.stop()
     launches_total = int(reduce_sum(float(main_res["launches"])))
@@ -545,17 +616,29 @@ def main():
             roofline["copy_gbs_this_box"] = None
             roofline["copy_error"] = str(e)
 
+    # The other BASELINE configs, short: C3 (512^3, single GPU only), C2 (8192^2 per GPU, y-slabs at N > 1) and C4 (1024^3
+    # GLOBAL, z-slabs: strong scaling).  Every line carries the checksums of its final field; C4's domain, seeds and sweep
+    # count are the same at every N, so its checksums must agree across N = 1, 2, 4, 8 (to the rounding of the all-reduce).
     others = {}
-    if rank == 0 and world == 1 and not args.no_others:
-        for name, sub, st in (("3d7_512", 100, 3), ("2d5_8192", 100, 3)):
-            if name == args.workload:
+    if not args.no_others:
+        for name, sub, st in (("3d7_512", 100, 3), ("2d5_8192", 100, 3), ("3d7_1024", 60, 2)):
+            if name == args.workload or (name == "3d7_512" and world > 1):
                 continue
             try:
-                r = run_config(R, ctx, name, 1, sub, st, 1, barrier, reduce_max)
-                others[name] = {"glups": r["glups"], "ms_per_sweep": r["ms"] / (sub * st),
-                                "hbm_frac": BYTES_PER_LUP * r["local_cells"] / (r["ms"] / (sub * st) * 1e-3) / 1e9 / peak}
+                r = run_config(R, ctx, name, world, sub, st, 1, barrier, reduce_max)
+                ms_sweep = r["ms"] / (sub * st)
+                others[name] = {"glups": r["glups"], "ms_per_sweep": ms_sweep, "scaling": WORKLOADS[name]["scaling"],
+                                "n_global": r["n_global"], "sweeps": sub * (st + 1),
+                                "hbm_frac_per_gpu": BYTES_PER_LUP * r["local_cells"] / (ms_sweep * 1e-3) / 1e9 / peak,
+                                "abs_sum_psi": r["abs_sum"], "l1_update_last": r["l1_last"],
+                                "temporally_blocked_launches": r["multi_launches"], "sweeps_in_them": r["multi_sweeps"]}
             except Exception as e:       # reported, never hidden
                 others[name] = {"error": str(e)}
+        if rank == 0 and world == 1:
+            try:
+                others["c1_magnetostatics_lua"] = run_c1_magnetostatics(R, ctx)
+            except Exception as e:
+                others["c1_magnetostatics_lua"] = {"error": str(e)}
 
     e2e = None
     if rank == 0 and not args.no_e2e:
@@ -575,6 +658,8 @@ def main():
         cpu_baseline = {"value": best, "unit": "GLUP/s", "cores": 1, "kind": "port",
                         "sample": f"10 timed (2 warm-up) reference-order Gauss-Seidel sweeps (poisson.rs:80-89 loop order, oracle port) "
                                   f"over a {'x'.join(map(str, n))} slab of the workload, 1 thread; the Rust reference is single-threaded",
+                        "note": "an UPPER bound for the reference: the thin slab shortens its stride-G0*G1 walk over the slowest index, and "
+                                "the C port has none of Rust's bounds checks / iterator overhead (SURVEY 8d)",
                         "host": {"nproc": os.cpu_count(), "cpu": _cpu_model()}}
         try:
             t1, l1c = cpu_reference_run(args.workload, 4, 3, jacobi_1core=True)

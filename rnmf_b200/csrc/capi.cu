@@ -954,7 +954,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     bool all_faces = true;
     for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
     // default (variant 0 = auto) for 3D; variant 6 = the single-sweep TMA kernel only
-    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21 || c->sweep_variant == 24 || c->sweep_variant == 25 || c->sweep_variant == 26 || c->sweep_variant == 27 || c->sweep_variant == 28);
+    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21 || c->sweep_variant == 22 || c->sweep_variant == 23 || c->sweep_variant == 24 || c->sweep_variant == 25 || c->sweep_variant == 26 || c->sweep_variant == 27 || c->sweep_variant == 28);
     const bool tb2_single = tb2_variant && !dist && fused && all_faces;
     // slabs: the fused peer path with the in-kernel handshake; z faces are physical or a neighbour
     const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
@@ -1383,7 +1383,7 @@ static bool skew_applicable(const rnmf_ctx* c, const rnmf_frame* psi)
     for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
     const int v = c->sweep_variant, C = c->e2e_skew_chunks;
     return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && c->nranks == 1 && all_faces && C >= 2 && g.n[2] / C >= 16 &&
-           g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && (v == 0 || v == 20 || v == 21 || v == 24 || v == 25 || v == 26 || v == 27 || v == 28);
+           g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && (v == 0 || v == 20 || v == 21 || v == 22 || v == 23 || v == 24 || v == 25 || v == 26 || v == 27 || v == 28);
 }
 
 static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,

@@ -296,7 +296,7 @@ int tma_sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s);
 // default (variant 0 = auto): the TMA kernel for 3D frames (measured 259 vs 195-231 GLUP/s at 768^3, sustained)
 // (variants 20/21 select the double-sweep kernel for pairs of sweeps; their single sweeps are the default TMA kernel)
-static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9) || a.variant == 13 || a.variant == 20 || a.variant == 21 || a.variant == 24 || a.variant == 25 || a.variant == 26 || a.variant == 27 || a.variant == 28); }
+static inline bool use_tma(const SweepArgs& a) { return a.g.dim == 3 && (a.variant == 0 || (a.variant >= 5 && a.variant <= 9) || a.variant == 13 || a.variant == 20 || a.variant == 21 || a.variant == 22 || a.variant == 23 || a.variant == 24 || a.variant == 25 || a.variant == 26 || a.variant == 27 || a.variant == 28); }
 
 int tma2d_sweep_num_partials(const SweepArgs& a);
 int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s);

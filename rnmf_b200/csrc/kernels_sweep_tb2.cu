@@ -266,8 +266,200 @@ __device__ __forceinline__ void row_iter(const Tb2Params& p, const RowK& k, RowS
     st.rp_a = rc_a; st.rp_b = rc_b;
 }
 
+// ===============================================================================================
+// QUAD mapping of the row warps (template flag QUAD of the kernel below): a warp owns TWO adjacent tile rows x 64 columns
+// instead of one row x 128 columns; lane l holds the 2 x 2 patch {rows jA, jA+1} x {columns ia, ia+1}, ia = i0 + 64*xh + 2l.
+// Still four cells per lane and level (the same register budget, the same 16 warps), but the N neighbour of row jA is the
+// lane's own row jA+1 and vice versa, at both levels: per warp and plane the N/S loads cost 8 + 8 instead of 16 + 16
+// shared-memory wavefronts, 72 instead of 88 in total (the shared-memory pipe bounds this kernel: DESIGN.md section 4).
+// Ring protocol, arithmetic and association are those of row_iter: the result is bit-identical.
+// ===============================================================================================
+struct QuadK {
+    uint32_t pa, ra, ua;                 // byte address of the lane's first cell (row A) in u0 stage 0 / rhs stage 0 / u1 slot 0
+    uint32_t full0, empty0, u1full0;
+    double c0, c1, c2, c3;
+    bool full, va0, va1, vb0, vb1;       // validity: row A cells ia, ia+1; row B cells ia, ia+1
+    bool do_xlo, any_x, any_y, do_ylo;
+    int xhi_sel;                         // 0 / 1: cell ia / ia+1 is i == n0-1 (-1: neither)
+    int yhi_row;                         // 1: row B is j == n1-1; 0: row A is (row B lies outside the frame); -1: neither
+    uint32_t xhi_off;                    // byte offset of the x-hi ghost from the lane's first cell
+    Face1 fx0, fx1, fy0, fy1, fz0, fz1;
+    long long pitch, plane_sz, xy_off;
+    int lane;
+    int it_zlo, it_u1lo, it_u1hi;
+};
+
+// the lane's 2 x 2 patch: pair `a` at q, pair `b` one row (rs elements) further
+__device__ __forceinline__ void qstore(double* q, long long rs, const double2& va, const double2& vb, bool full, bool a0, bool a1, bool b0, bool b1)
+{
+#ifdef RNMF_EMULATE
+    if ((full || a1 || b1) && (reinterpret_cast<uintptr_t>(q) % 16 != 0 || (rs & 1))) emu::fault("misaligned 16-byte global store", reinterpret_cast<uintptr_t>(q), 16);
+#endif
+    if (full) {
+        *reinterpret_cast<double2*>(q) = va;
+        *reinterpret_cast<double2*>(q + rs) = vb;
+    } else {
+        if (a1) *reinterpret_cast<double2*>(q) = va; else if (a0) q[0] = va.x;
+        if (b1) *reinterpret_cast<double2*>(q + rs) = vb; else if (b0) q[rs] = vb.x;
+    }
+}
+__device__ __forceinline__ void pstore(double* q, const double2& v, bool full, bool c0, bool c1)
+{
+    if (full || c1) *reinterpret_cast<double2*>(q) = v; else if (c0) q[0] = v.x;
+}
+__device__ __forceinline__ void qsstore(uint32_t a, uint32_t rb, const double2& va, const double2& vb, bool full, bool a0, bool a1, bool b0, bool b1)
+{
+    if (full) {
+        sts2(a, va);
+        sts2(a + rb, vb);
+    } else {
+        if (a1) sts2(a, va); else if (a0) sts1(a, va.x);
+        if (b1) sts2(a + rb, vb); else if (b0) sts1(a + rb, vb.x);
+    }
+}
+__device__ __forceinline__ void psstore(uint32_t a, const double2& v, bool full, bool c0, bool c1)
+{
+    if (full || c1) sts2(a, v); else if (c0) sts1(a, v.x);
+}
+__device__ __forceinline__ void qload(const double* q, long long rs, double2& a, double2& b, const QuadK& k)
+{
+    if (k.full) { a = *reinterpret_cast<const double2*>(q); b = *reinterpret_cast<const double2*>(q + rs); }
+    else {
+        if (k.va0) a.x = q[0];
+        if (k.va1) a.y = q[1];
+        if (k.vb0) b.x = q[rs];
+        if (k.vb1) b.y = q[rs + 1];
+    }
+}
+
+// One plane iteration of a quad warp; same structure, template flags and EDGE levels as row_iter.
+template <int TY, int NS, bool DO_L1, bool DO_L2, int EDGE = 2>
+__device__ __forceinline__ void quad_iter(const Tb2Params& p, const QuadK& k, RowSt& st, const int it)
+{
+    using Cfg = Tb2Cfg<TY, NS>;
+    constexpr uint32_t RB = Cfg::BX * 8;                                  // one tile row in shared memory
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 above_a = zero2, above_b = zero2, u1n_a = zero2, u1n_b = zero2, rc_a = zero2, rc_b = zero2, P_a = zero2, P_b = zero2;
+
+    // ---- wait phase (as row_iter) ----------------------------------------------------------------
+    if (DO_L1) mbar_wait(k.full0 + 8 * st.sn, st.phn);
+    if (DO_L2 || it >= 2) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+
+    // ---- loads -----------------------------------------------------------------------------------
+    if (DO_L2) {
+        const uint32_t up = k.ua + (uint32_t)((it - 1) & 1) * Cfg::U1_SLOT;
+        const double2 un_b = lds2(up + 2 * RB);                           // N of row B; N of row A is row B (registers)
+        const double2 us_a = lds2(up - RB);                               // S of row A; S of row B is row A
+        const double uw_a0 = lds1(up - 8), ue_a1 = lds1(up + 16);
+        const double uw_b0 = lds1(up + RB - 8), ue_b1 = lds1(up + RB + 16);
+        P_a.x = part2(k.c0, k.c1, k.c2, st.rp_a.x, st.u1c_a.y, uw_a0, st.u1c_b.x, us_a.x);
+        P_a.y = part2(k.c0, k.c1, k.c2, st.rp_a.y, ue_a1, st.u1c_a.x, st.u1c_b.y, us_a.y);
+        P_b.x = part2(k.c0, k.c1, k.c2, st.rp_b.x, st.u1c_b.y, uw_b0, un_b.x, st.u1c_a.x);
+        P_b.y = part2(k.c0, k.c1, k.c2, st.rp_b.y, ue_b1, st.u1c_b.x, un_b.y, st.u1c_a.y);
+    }
+    if (DO_L1) {
+        const uint32_t pn = k.pa + st.sn * Cfg::U0_STAGE, pc = k.pa + st.sc * Cfg::U0_STAGE, pr = k.ra + st.sc * Cfg::RHS_STAGE;
+        above_a = lds2(pn); above_b = lds2(pn + RB);
+        const double2 n_b = lds2(pc + 2 * RB);
+        const double2 s_a = lds2(pc - RB);
+        rc_a = lds2(pr); rc_b = lds2(pr + RB);
+        const double w_a0 = lds1(pc - 8), e_a1 = lds1(pc + 16);
+        const double w_b0 = lds1(pc + RB - 8), e_b1 = lds1(pc + RB + 16);
+
+        // ---------------- level 1: u1 of plane a+it ----------------
+        u1n_a.x = upd3(k.c0, k.c1, k.c2, k.c3, rc_a.x, st.cur_a.y, w_a0, st.cur_b.x, s_a.x, above_a.x, st.below_a.x);
+        u1n_a.y = upd3(k.c0, k.c1, k.c2, k.c3, rc_a.y, e_a1, st.cur_a.x, st.cur_b.y, s_a.y, above_a.y, st.below_a.y);
+        u1n_b.x = upd3(k.c0, k.c1, k.c2, k.c3, rc_b.x, st.cur_b.y, w_b0, n_b.x, st.cur_a.x, above_b.x, st.below_b.x);
+        u1n_b.y = upd3(k.c0, k.c1, k.c2, k.c3, rc_b.y, e_b1, st.cur_b.x, n_b.y, st.cur_a.y, above_b.y, st.below_b.y);
+        // registers that level 2 reads as a neighbour but that are not stencil values of the frame:
+        // odd n0: the pair's second register must hold the x-hi ghost of u1; odd row count: row B must hold the y-hi ghost row
+        if (EDGE == 2 && k.xhi_sel == 0) { u1n_a.y = ghost1(k.fx1, u1n_a.x); u1n_b.y = ghost1(k.fx1, u1n_b.x); }
+        if (EDGE == 2 && k.yhi_row == 0) u1n_b = ghost1(k.fy1, u1n_a);
+
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.sc);
+        const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
+        qsstore(us, RB, u1n_a, u1n_b, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE != 0 && k.any_x) {
+            if (k.do_xlo) {
+                sts1(us - 8, ghost1(k.fx0, u1n_a.x));
+                if (EDGE != 2 || k.vb0) sts1(us + RB - 8, ghost1(k.fx0, u1n_b.x));
+            }
+            if (k.xhi_sel >= 0) {
+                sts1(us + k.xhi_off, ghost1(k.fx1, k.xhi_sel == 0 ? u1n_a.x : u1n_a.y));
+                if (EDGE != 2 || k.vb0) sts1(us + RB + k.xhi_off, ghost1(k.fx1, k.xhi_sel == 0 ? u1n_b.x : u1n_b.y));
+            }
+        }
+        if (EDGE == 2 && k.any_y) {
+            if (k.do_ylo) psstore(us - RB, ghost1(k.fy0, u1n_a), k.full, k.va0, k.va1);
+            if (k.yhi_row == 1) psstore(us + 2 * RB, ghost1(k.fy1, u1n_b), k.full, k.vb0, k.vb1);
+        }
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+        if (EDGE == 2 && it == k.it_u1lo) qstore(p.peer_u1_lo + k.xy_off, k.pitch, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE == 2 && it == k.it_u1hi) qstore(p.peer_u1_hi + k.xy_off, k.pitch, u1n_a, u1n_b, k.full, k.va0, k.va1, k.vb0, k.vb1);
+    }
+    if (DO_L2) {
+        // ---------------- level 2: u2 of plane q = a+it-1 ----------------
+        double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
+        const bool zlo = EDGE == 2 && it == k.it_zlo;
+        if (zlo) {
+            if (k.fz0.on) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
+            else if (p.u1_in_lo) qload(p.u1_in_lo + k.xy_off, k.pitch, dn_a, dn_b, k);
+        }
+        if (!DO_L1) {
+            if (k.fz1.on) { up_a = ghost1(k.fz1, st.u1c_a); up_b = ghost1(k.fz1, st.u1c_b); }
+            else if (p.u1_in_hi) qload(p.u1_in_hi + k.xy_off, k.pitch, up_a, up_b, k);
+        }
+        double2 na, nb;
+        na.x = fin2(P_a.x, k.c3, up_a.x, dn_a.x);
+        na.y = fin2(P_a.y, k.c3, up_a.y, dn_a.y);
+        nb.x = fin2(P_b.x, k.c3, up_b.x, dn_b.x);
+        nb.y = fin2(P_b.y, k.c3, up_b.y, dn_b.y);
+
+        double* oa = st.oa;
+        const bool full = EDGE != 2 || k.full;
+        qstore(oa, k.pitch, na, nb, full, k.va0, k.va1, k.vb0, k.vb1);
+        if (EDGE != 0 && k.any_x) {
+            if (k.do_xlo) {
+                oa[-1] = ghost1(k.fx0, na.x);
+                if (EDGE != 2 || k.vb0) oa[k.pitch - 1] = ghost1(k.fx0, nb.x);
+            }
+            if (k.xhi_sel >= 0) {
+                oa[k.xhi_sel + 1] = ghost1(k.fx1, k.xhi_sel == 0 ? na.x : na.y);
+                if (EDGE != 2 || k.vb0) oa[k.pitch + k.xhi_sel + 1] = ghost1(k.fx1, k.xhi_sel == 0 ? nb.x : nb.y);
+            }
+        }
+        if (EDGE == 2 && k.any_y) {
+            if (k.do_ylo) pstore(oa - k.pitch, ghost1(k.fy0, na), k.full, k.va0, k.va1);
+            if (k.yhi_row == 1) pstore(oa + 2 * k.pitch, ghost1(k.fy1, nb), k.full, k.vb0, k.vb1);
+            if (k.yhi_row == 0) pstore(oa + k.pitch, ghost1(k.fy1, na), false, k.va0, k.va1);
+        }
+        if (zlo) {
+            if (k.fz0.on) qstore(oa - k.plane_sz, k.pitch, ghost1(k.fz0, na), ghost1(k.fz0, nb), full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_lo_plane) qstore(p.peer_lo_plane + k.xy_off, k.pitch, na, nb, full, k.va0, k.va1, k.vb0, k.vb1);
+        }
+        if (!DO_L1) {
+            if (k.fz1.on) qstore(oa + k.plane_sz, k.pitch, ghost1(k.fz1, na), ghost1(k.fz1, nb), full, k.va0, k.va1, k.vb0, k.vb1);
+            if (p.peer_hi_plane) qstore(p.peer_hi_plane + k.xy_off, k.pitch, na, nb, full, k.va0, k.va1, k.vb0, k.vb1);
+        }
+        st.oa = oa + k.plane_sz;
+    }
+    // ---- rotate ----------------------------------------------------------------------------------
+    if (DO_L1) {
+        st.below_a = st.cur_a; st.below_b = st.cur_b;
+        st.cur_a = above_a; st.cur_b = above_b;
+        st.sc = st.sn;
+        if (++st.sn == NS) { st.sn = 0; st.phn ^= 1u; }
+    }
+    st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
+    st.u1c_a = u1n_a; st.u1c_b = u1n_b;
+    st.rp_a = rc_a; st.rp_b = rc_b;
+}
+
 // SPEC (variant 26, opt-in): row warps that own no face / ragged cell run an interior-only copy of the plane loop
-template <int TY, int NS, bool SPEC = false>
+// QUAD: the TY tile-row warps use the 2-rows x 64-columns mapping (quad_iter above); the halo warps are unchanged
+template <int TY, int NS, bool SPEC = false, bool QUAD = false>
 __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __grid_constant__ CUtensorMap tm_u0,
                                                                          const __grid_constant__ CUtensorMap tm_rhs,
                                                                          const __grid_constant__ Tb2Params p)
@@ -275,6 +467,7 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
     using Cfg = Tb2Cfg<TY, NS>;
     constexpr int TX = Cfg::TX, BX = Cfg::BX;
     static_assert(TY <= 16, "the halo-column warp maps 16 rows per side");
+    static_assert(!QUAD || TY % 2 == 0, "QUAD: row pairs");
     RNMF_DYNAMIC_SMEM(smem_raw);
     const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t u0_0 = sb, rhs_0 = sb + Cfg::RHS_OFF, u1_0 = sb + Cfg::U1_OFF;
@@ -384,9 +577,95 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
             sc = sn;
             if (++sn == NS) { sn = 0; phn ^= 1u; }
         }
+    } else if (QUAD && warp < TY) {
+        // ------------------------------ quad warps: rows j0+2*rp, j0+2*rp+1 x columns i0+64*xh .. +63 ------------------------------
+        const int xh = warp & 1, rp = warp >> 1;
+        const int ra = 2 * rp;                                  // tile row of row A
+        const long long jA = j0 + ra, jB = jA + 1;
+        const bool okA = jA < n1, okB = jB < n1;
+        const long long ia = i0 + 64 * xh + 2 * lane;
+        QuadK k;
+        k.va0 = okA && ia < n0; k.va1 = okA && ia + 1 < n0;
+        k.vb0 = okB && ia < n0; k.vb1 = okB && ia + 1 < n0;
+        k.full = k.vb1;
+        const int col = 2 + 64 * xh + 2 * lane;                 // position of cell ia in a tile row (two-cell x halo)
+        k.pa = u0_0 + (uint32_t)(((ra + 2) * BX + col) * 8);
+        k.ra = rhs_0 + (uint32_t)(((ra + 1) * BX + col) * 8);
+        k.ua = u1_0 + (uint32_t)(((ra + 1) * BX + col) * 8);
+        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0;
+        k.c0 = p.c.c0; k.c1 = p.c.c1; k.c2 = p.c.c2; k.c3 = p.c.c3;
+        k.pitch = p.g.pitch; k.plane_sz = p.g.plane;
+        k.xy_off = p.g.xoff + (ia + p.g.ng) + k.pitch * (jA + p.g.ng);
+        k.lane = lane;
+        k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
+        k.fy0 = make_face1(p.faces.f[2], true); k.fy1 = make_face1(p.faces.f[3], true);
+        k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
+        k.do_xlo = k.fx0.on && k.va0 && ia == 0;
+        const long long last = n0 - 1;
+        k.xhi_sel = !k.fx1.on ? -1 : (k.va0 && ia == last) ? 0 : (k.va1 && ia + 1 == last) ? 1 : -1;
+        k.xhi_off = (uint32_t)((k.xhi_sel + 1) * 8);
+        k.do_ylo = k.fy0.on && jA == 0;
+        k.yhi_row = !k.fy1.on ? -1 : (jB == n1 - 1) ? 1 : (jA == n1 - 1) ? 0 : -1;
+        k.any_x = k.do_xlo || k.xhi_sel >= 0;
+        k.any_y = k.do_ylo || k.yhi_row >= 0;
+        k.it_zlo = k0 == 0 ? 1 : -1;
+        k.it_u1lo = a_sync_lo ? 0 : -1;
+        k.it_u1hi = a_sync_hi ? nL1 - 1 : -1;
+
+        RowSt st;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        constexpr uint32_t RB = BX * 8;
+        mbar_wait(full0, 0);
+        st.below_a = lds2(k.pa); st.below_b = lds2(k.pa + RB);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        st.cur_a = lds2(k.pa + Cfg::U0_STAGE); st.cur_b = lds2(k.pa + Cfg::U0_STAGE + RB);
+        st.u1lo_a = zero2; st.u1lo_b = zero2; st.u1c_a = zero2; st.u1c_b = zero2; st.rp_a = zero2; st.rp_b = zero2;
+        st.oa = p.out + p.g.at(ia, jA, k0, 0);
+        st.sc = 1; st.sn = 2; st.phn = 0;
+
+        int it = 0;
+        // warp-uniform: both rows and all 64 columns are valid cells, no face of the frame touches the warp's patch, no slab role
+        const long long iw = i0 + 64 * xh;
+        const bool whole = okB && iw + 64 <= n0 && !k.do_ylo && k.yhi_row < 0 && !a_sync_lo && !a_sync_hi && !is_b;
+        const bool interior = SPEC && whole && !(k.fx0.on && iw == 0) && !(k.fx1.on && iw + 64 == n0);
+        const bool xface_only = SPEC && whole && !interior;
+        if (interior) {
+            for (; it < it_l2_first; ++it) quad_iter<TY, NS, true, false, 0>(p, k, st, it);
+            if (it < nL1) { quad_iter<TY, NS, true, true, 2>(p, k, st, it); ++it; }      // may meet the z-lo face: general code, once
+            for (; it < nL1; it += 3) {
+                quad_iter<TY, NS, true, true, 0>(p, k, st, it);
+                if (it + 1 >= nL1) break;
+                quad_iter<TY, NS, true, true, 0>(p, k, st, it + 1);
+                if (it + 2 >= nL1) break;
+                quad_iter<TY, NS, true, true, 0>(p, k, st, it + 2);
+            }
+        } else if (xface_only) {
+            for (; it < it_l2_first; ++it) quad_iter<TY, NS, true, false, 1>(p, k, st, it);
+            if (it < nL1) { quad_iter<TY, NS, true, true, 2>(p, k, st, it); ++it; }
+            for (; it < nL1; it += 3) {
+                quad_iter<TY, NS, true, true, 1>(p, k, st, it);
+                if (it + 1 >= nL1) break;
+                quad_iter<TY, NS, true, true, 1>(p, k, st, it + 1);
+                if (it + 2 >= nL1) break;
+                quad_iter<TY, NS, true, true, 1>(p, k, st, it + 2);
+            }
+        } else {
+            for (; it < it_l2_first; ++it) quad_iter<TY, NS, true, false, 2>(p, k, st, it);
+            for (; it < nL1; it += 3) {
+                quad_iter<TY, NS, true, true, 2>(p, k, st, it);
+                if (it + 1 >= nL1) break;
+                quad_iter<TY, NS, true, true, 2>(p, k, st, it + 1);
+                if (it + 2 >= nL1) break;
+                quad_iter<TY, NS, true, true, 2>(p, k, st, it + 2);
+            }
+        }
+        if (top) quad_iter<TY, NS, false, true, 2>(p, k, st, nL1);
     } else {
         // ------------------------------ row warps ------------------------------
         // warps 0..TY-1: tile rows (levels 1 and 2); warp TY: halo row j0-1; warp TY+1: halo row j0+TY (level 1 only)
+        // (QUAD: only the two halo-row warps come here)
         const bool do_l2 = warp < TY;
         const int rr = do_l2 ? warp : (warp == TY ? -1 : TY);
         const long long j = j0 + rr;
@@ -987,7 +1266,7 @@ __global__ void __launch_bounds__(32 * (TY / 2 + (MERGE ? 2 : 3)), 1) jacobi3d_t
     }
 }
 
-template <int TY, int NS, bool SPEC = false>
+template <int TY, int NS, bool SPEC = false, bool QUAD = false>
 struct Tb2Launcher {
     using Cfg = Tb2Cfg<TY, NS>;
     // chunk length: whole waves of one CTA per SM, each CTA paying chunk+3 plane iterations
@@ -1038,11 +1317,11 @@ struct Tb2Launcher {
 #ifndef RNMF_EMULATE
         static PerDeviceOnce attr_set;
         if (!attr_set.done()) {
-            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(jacobi3d_tb2_kernel<TY, NS, SPEC, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess) return -1;
             attr_set.mark();
         }
 #endif
-        RNMF_KERNEL_LAUNCH((jacobi3d_tb2_kernel<TY, NS, SPEC>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
+        RNMF_KERNEL_LAUNCH((jacobi3d_tb2_kernel<TY, NS, SPEC, QUAD>), grid, Cfg::THREADS, Cfg::SMEM, s, tm_u0, tm_rhs, p);
         return 1;
     }
 };
@@ -1093,6 +1372,8 @@ int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
     if (t.a.k_end <= t.a.k_begin && !t.b_lo && !t.b_hi) return 0;
     switch (t.a.variant) {
     case 21: return Tb2Launcher<8, 6>::launch(t, s);
+    case 22: return Tb2Launcher<12, 6, true, true>::launch(t, s);    // quad mapping (2 rows x 64 columns per warp) + interior-specialised loop
+    case 23: return Tb2Launcher<12, 6, false, true>::launch(t, s);   // quad mapping, general loop only
     case 24: return Tb2xLauncher<12, 6, true>::launch(t, s);
     case 25: return Tb2xLauncher<16, 4, false>::launch(t, s);
     case 26: return Tb2Launcher<12, 6, true>::launch(t, s);          // interior-specialised plane loop (opt-in)

@@ -60,6 +60,12 @@ def test_roofline_accounting_single_and_double_sweep():
     assert abs(r["frac"] - 1.3755) < 1e-3 and r["frac"] == r["achieved"] / r["peak"]
     assert r["traffic"] and abs(r["dram_frac"] - r["traffic"] / (r["avg_launch_ms"] * 1e-3) / 1e9 / 6549.8) < 1e-12
     assert r["dram_frac"] < 1.0 < r["frac"]
+    assert abs(r["frac_of_k_pass_ceiling"] - r["frac"] / 2) < 1e-12 and r["traffic_source"]
+    # with the dominant kernel timed directly (CUDA events around back-to-back launches) that duration replaces the step share
+    rk = b.build_roofline({"ms": 663.694677734375 * 5, "doubles": 1370, "local_cells": cells, "kernel_ms": 2.30, "kernel_launches_timed": 60},
+                          5, 550, "3d7_768", 6549.8, "MEASURED_PEAKS.json hbm_gbs")
+    assert rk["avg_launch_ms"] == 2.30 and abs(rk["avg_launch_ms_from_step"] - r["avg_launch_ms"]) < 1e-12 and "60 back-to-back" in rk["launch_timing"]
+    assert abs(rk["achieved"] - 2 * 24 * cells / 2.30e-3 / 1e9) < 1e-6
     # single-sweep kernel only (variant 6): one sweep per launch, no note
     r1 = b.build_roofline({"ms": 965.5 * 5, "doubles": 0, "local_cells": cells}, 5, 550, "3d7_768", 6549.8, "MEASURED_PEAKS.json hbm_gbs")
     assert r1["sweeps_per_launch"] == 1 and r1["algorithmic_bytes_per_launch"] == 24 * cells and "note" not in r1

@@ -83,6 +83,20 @@ def _setup(n, hi, spec, sweeps, seed):
     ([129, 17, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 25, 0),
     ([65, 33, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 25, 2),
     ([30, 15, 2], [1.0, 1.0, 1.0], MIXED_3D, 1, 25, 0),
+    # variants 22 / 23: quad mapping (a warp owns 2 rows x 64 columns; N/S between the two rows from registers), with / without the
+    # interior-specialised loop
+    ([20, 9, 5], [1.0, 2.0, 3.0], MIXED_3D, 1, 23, 0),           # odd n1: the last row is a warp's row A (y-hi ghost of u1 in row B's registers)
+    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 23, 0),
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 23, 2),       # odd n0: x-hi ghost in the pair's second register, in the x-half 1 warp
+    ([63, 24, 3], [1.0, 2.0, 3.0], MIXED_3D, 1, 23, 0),          # x-hi face in the x-half 0 warp; n1 = two full tiles
+    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 23, 0),
+    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 23, 0),
+    ([2, 2, 2], [1.0, 1.0, 1.0], NEUMANN_3D, 2, 23, 0),
+    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 22, 0),
+    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 22, 2),
+    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 22, 3),          # x-hi face exactly at a tile edge; odd n1
+    ([192, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 22, 3),          # x-hi face at the edge of an x-half 0 warp
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 22, 2),
     # variant 26: interior-specialised plane loop for the row warps of x-interior tiles (needs >= 3 tiles in x to have one)
     ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 26, 0),
     ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 26, 2),        # the last tile holds one column; two launches; 2-plane chunks
@@ -166,8 +180,8 @@ def test_2d_multi_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, chun
     np.testing.assert_array_equal(out, want)
 
 
-@settings(max_examples=12, deadline=None, derandomize=True)
-@given(st.sampled_from([20, 24, 25, 26, 27, 28]), st.integers(1, 400), st.integers(1, 30), st.integers(1, 8), st.integers(0, 8), st.booleans())
+@settings(max_examples=24, deadline=None, derandomize=True)
+@given(st.sampled_from([20, 22, 22, 23, 24, 25, 26, 27, 28]), st.integers(1, 400), st.integers(1, 30), st.integers(1, 8), st.integers(0, 8), st.booleans())
 def test_3d_double_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, n2, chunk, neumann):
     """Random frame shapes / chunk lengths for the 3D double-sweep variants (default, two rows per warp, interior-specialised,
     de-interleaved u1 ring)."""
@@ -188,6 +202,9 @@ def test_3d_double_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, n2,
     ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 26),         # interior-specialised loop in the A chunks away from the neighbours
     ([390, 14, 13], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 2, 27),
     ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 28),
+    ([390, 15, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 22),         # quad mapping: u1 / u2 boundary planes of 2 x 2 patches; odd n1
+    ([130, 13, 17], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 0, 22),
+    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1, 23),        # 4-plane slabs, one-plane A chunks
 ])
 def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk, variant):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial

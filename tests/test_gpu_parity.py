@@ -279,7 +279,7 @@ def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, vari
 ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
 # variants 24 / 25 (two rows per row warp) and 26 / 27 (interior-specialised plane loop) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
 # on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 adds them here
-_DOUBLE_SWEEP_VARIANTS = [20, 21] + ([v for v in (24, 25, 26, 27, 28) if not _ONLY or v in _ONLY] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
+_DOUBLE_SWEEP_VARIANTS = [20, 21, 22, 23, 26] + ([v for v in (24, 25, 27, 28) if not _ONLY or v in _ONLY] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
