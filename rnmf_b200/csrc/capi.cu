@@ -33,8 +33,8 @@ extern "C" int32_t rnmf_abi_version(void) { return RNMF_ABI_VERSION; }
 extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
-           "jacobi3d_zmarch{32x8,32x4,64x4,16x16},jacobi3d_tma{128x8x5,128x8x4,128x16x4,128x4x6},jacobi2d_tma{512x8},jacobi2d_ymarch{128,256},"
-           "jacobi3d_tb2{128x12,128x8},jacobi3d_tb2x{128x12m,128x16},jacobi3d_tb2s{128x12,128x12m},jacobi2d_tb2{512},jacobi2d_tbk{3x512,4x512,4x768,2x512},jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
+           "jacobi3d_tma{128x8x4},jacobi3d_tb2{128x12 quad},jacobi2d_tma{512x8},jacobi2d_tb2{512},jacobi2d_tbk{4x512 di},"
+           "jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
 // ------------------------------------------------------------------------------------------
@@ -141,7 +141,6 @@ struct rnmf_ctx {
     void* peer_flag_base_hi = nullptr;
     unsigned long long epoch = 0;                 // sweeps completed in peer mode (same on all ranks)
     unsigned long long done_target[2] = { 0, 0 }; // cumulative boundary-CTA counts (in-kernel handshake), lo / hi
-    unsigned long long done_target_b[2] = { 0, 0 }; // same for the B chunks of the double-sweep kernel
     int peer_inkernel = 1;                        // option "peer_inkernel": handshake inside the sweep kernel
     int peer_halo = 1;                            // option "peer_halo": use the fused path when attached
     int peer_used = 0;                            // a fused-halo sweep has been launched (check_peer_status has something to check)
@@ -151,7 +150,7 @@ struct rnmf_ctx {
     long long resident_max_bytes = 48LL << 20;    // psi + psi' + rhs must fit comfortably in the 126 MB L2
     rnmf_frame* hp_psi = nullptr;         // cached frames of rnmf_solve_poisson_host
     rnmf_frame* hp_rhs = nullptr;
-    int e2e_skew = 0;                     // option "e2e_skew" (opt-in): time-skewed start of rnmf_solve_poisson_host
+    int e2e_skew = 2;                     // option "e2e_skew": 1 = time-skewed start of rnmf_solve_poisson_host, 2 = and end (default; measured 294 -> 347 GLUP/s end to end at 768^3), 0 = plain
     int e2e_skew_chunks = 8, e2e_skew_pairs = 56; // upload chunks, double sweeps run band-wise during the upload
     int e2e_skew_tail = 32;                       // e2e_skew >= 2: last launches run band-wise so the download overlaps them
     std::vector<cudaEvent_t> ev_chunks;   // one per upload chunk
@@ -181,15 +180,6 @@ namespace {
 constexpr long long kTailPad = 64;   // doubles; lets edge threads read a little past the last row
 constexpr long long kGuard = 256;    // doubles after the tail pad holding a canary pattern (rnmf_frame_check_guards)
 constexpr unsigned long long kCanary = 0x7FF8C0DEC0DE0000ULL;   // a quiet-NaN payload
-
-int write_guard(double* buf, const FrameGeom& g, cudaStream_t s)
-{
-    static unsigned long long pattern[kGuard];
-    static bool init = false;
-    if (!init) { for (long long i = 0; i < kGuard; ++i) pattern[i] = kCanary + (unsigned long long)i; init = true; }
-    RNMF_CUDA_TRY(cudaMemcpyAsync(buf + g.total + kTailPad, pattern, sizeof(pattern), cudaMemcpyHostToDevice, s));
-    return RNMF_OK;
-}
 
 int ensure_partials(rnmf_ctx* c, long long n)
 {
@@ -224,18 +214,34 @@ int check_peer_status(rnmf_ctx* c)
     return RNMF_ERR_NCCL;
 }
 
-// 3D one-component ng=1 frames carry two scratch planes behind the guard band: the u1 boundary planes
-// the slab neighbours store during a double sweep (kernels_sweep_tb2.cu); [0] from lo, [1] from hi
-long long scratch_planes(const FrameGeom& g) { return g.dim == 3 && g.ng == 1 && g.ncomp == 1 ? 2 : 0; }
-long long scratch_off(long long total) { return total + kTailPad + kGuard; }
+// DEEP HALO: 3D one-component ng=1 frame buffers carry one extra z-plane in front of the z-lo ghost plane and one behind
+// the z-hi ghost plane (kernels_sweep_tb2.cu): with the neighbour slab's two boundary planes in ghost + deep plane, two sweeps
+// per launch need no data that arrives during the launch.  A frame pointer (`d`, `d2`) addresses the z-lo ghost plane as
+// before; the allocation starts deep_elems() doubles earlier and the tail pad / canary band follow the rear deep plane.
+long long deep_elems(const FrameGeom& g) { return g.dim == 3 && g.ng == 1 && g.ncomp == 1 ? g.plane : 0; }
+long long tail_off(const FrameGeom& g) { return g.total + deep_elems(g); }       // first double behind the (rear deep plane of the) frame
+
+int write_guard(double* buf, const FrameGeom& g, cudaStream_t s)
+{
+    static unsigned long long pattern[kGuard];
+    static bool init = false;
+    if (!init) { for (long long i = 0; i < kGuard; ++i) pattern[i] = kCanary + (unsigned long long)i; init = true; }
+    RNMF_CUDA_TRY(cudaMemcpyAsync(buf + tail_off(g) + kTailPad, pattern, sizeof(pattern), cudaMemcpyHostToDevice, s));
+    return RNMF_OK;
+}
 
 int alloc_buffer(const FrameGeom& g, double** out, cudaStream_t s)
 {
-    const size_t bytes = (size_t)(g.total + kTailPad + kGuard + scratch_planes(g) * g.plane) * sizeof(double);
-    RNMF_CUDA_TRY(cudaMalloc(out, bytes));
-    RNMF_CUDA_TRY(cudaMemsetAsync(*out, 0, bytes, s));   // new_from zero-initialises (dataframe.rs:155)
+    const long long deep = deep_elems(g);
+    const size_t bytes = (size_t)(deep + g.total + deep + kTailPad + kGuard) * sizeof(double);
+    double* raw = nullptr;
+    RNMF_CUDA_TRY(cudaMalloc(&raw, bytes));
+    RNMF_CUDA_TRY(cudaMemsetAsync(raw, 0, bytes, s));   // new_from zero-initialises (dataframe.rs:155)
+    *out = raw + deep;
     return write_guard(*out, g, s);
 }
+
+void free_buffer(const FrameGeom& g, double* buf) { if (buf) cudaFree(buf - deep_elems(g)); }
 
 bool same_shape(const FrameGeom& a, const FrameGeom& b)
 {
@@ -503,11 +509,11 @@ extern "C" int32_t rnmf_frame_destroy(rnmf_frame* f)
     cudaStreamSynchronize(f->ctx->stream);
     cudaStreamSynchronize(f->ctx->stream_halo);
     for (int i = 0; i < 2; ++i) {
-        if (f->peer_lo[i]) cudaIpcCloseMemHandle(f->peer_lo[i]);
-        if (f->peer_hi[i]) cudaIpcCloseMemHandle(f->peer_hi[i]);
+        if (f->peer_lo[i]) cudaIpcCloseMemHandle(f->peer_lo[i] - deep_elems(f->g));     // the mapped allocation bases
+        if (f->peer_hi[i]) cudaIpcCloseMemHandle(f->peer_hi[i] - deep_elems(f->g));
     }
-    if (f->d) cudaFree(f->d);
-    if (f->d2) cudaFree(f->d2);
+    free_buffer(f->g, f->d);
+    free_buffer(f->g, f->d2);
     for (double* p : f->prescribed_dev) if (p) cudaFree(p);
     delete f;
     return RNMF_OK;
@@ -524,7 +530,7 @@ extern "C" int32_t rnmf_frame_check_guards(rnmf_frame* f, int32_t* ok)
     unsigned long long host[kGuard];
     for (double* buf : { f->d, f->d2 }) {
         if (!buf) continue;
-        RNMF_CUDA_TRY(cudaMemcpy(host, buf + f->g.total + kTailPad, sizeof(host), cudaMemcpyDeviceToHost));
+        RNMF_CUDA_TRY(cudaMemcpy(host, buf + tail_off(f->g) + kTailPad, sizeof(host), cudaMemcpyDeviceToHost));
         for (long long i = 0; i < kGuard; ++i)
             if (host[i] != kCanary + (unsigned long long)i) { *ok = 0; break; }
     }
@@ -809,7 +815,9 @@ extern "C" int32_t rnmf_poisson_coefs(int32_t dim, const double* dx, double* coe
 // pitch doubles per y-row in 2D), so no pack kernel is needed: pack order == collect_typed_cells
 // order (dataframe.rs:273-278, pinned by :1148-1201), unpack == fill_prescribed_bc (:280-284).
 // ------------------------------------------------------------------------------------------
-static int halo_exchange_on(rnmf_frame* f, double* buf, cudaStream_t s)
+// depth = ng: the ghost slices (the reference's halo).  depth = ng + 1 (deep halo, 3D one-component ng=1 frames only): the
+// slab's TWO slices next to the face go into the neighbour's ghost + deep plane, which are adjacent in memory on both sides.
+static int halo_exchange_on(rnmf_frame* f, double* buf, cudaStream_t s, int extra_depth = 0)
 {
     rnmf_ctx* c = f->ctx;
     if (!f->distributed || c->nranks == 1) return RNMF_OK;
@@ -817,13 +825,15 @@ static int halo_exchange_on(rnmf_frame* f, double* buf, cudaStream_t s)
     const int D = slow_dim(g);
     const long long slice = D == 2 ? g.plane : g.pitch;          // doubles per slowest-direction slice
     const long long ng = g.ng;
-    const long long cnt = slice * ng;
+    const long long depth = ng + extra_depth;
+    RNMF_REQUIRE(extra_depth == 0 || (deep_elems(g) >= slice * extra_depth && g.n[D] >= depth), "deep halo exchange needs deep planes and a slab of >= %lld slices", depth);
+    const long long cnt = slice * depth;
     for (int comp = 0; comp < g.ncomp; ++comp) {
         double* base = buf + g.comp * comp;                       // grown slice 0 of this component
-        double* lo_ghost = base;                                  // slices [0, ng)
-        double* lo_valid = base + slice * ng;                     // slices [ng, 2ng)
-        double* hi_valid = base + slice * g.n[D];                 // slices [n, n+ng)   (grown index)
-        double* hi_ghost = base + slice * (g.n[D] + ng);          // slices [n+ng, n+2ng)
+        double* lo_ghost = base + slice * (ng - depth);           // slices [ng-depth, ng)  (deep slices sit in front of the buffer)
+        double* lo_valid = base + slice * ng;                     // slices [ng, ng+depth)
+        double* hi_valid = base + slice * (g.n[D] + ng - depth);  // slices [n+ng-depth, n+ng)   (grown index)
+        double* hi_ghost = base + slice * (g.n[D] + ng);          // slices [n+ng, n+ng+depth)
         RNMF_NCCL_TRY(g_nccl.GroupStart());
         if (c->rank > 0) {
             RNMF_NCCL_TRY(g_nccl.Send(lo_valid, (size_t)cnt, ncclDouble, c->rank - 1, c->comm, s));
@@ -904,14 +914,6 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     RNMF_LAUNCH(c, launch_copy_ghost_shell(g, psi->d, psi->d2, s));
 
     const bool dist = psi->distributed && c->nranks > 1;
-    if (dist) {
-        // Entry exchange of the current buffer's halos.  It is also what orders the shell copy
-        // above (which rewrites d2's ghost slices) before the neighbours' first peer stores into
-        // d2 of this call: a neighbour cannot leave its own entry exchange before this rank's
-        // send/recv, which is stream-ordered after the copy.
-        rc = halo_exchange_on(psi, psi->d, s);
-        if (rc) return rc;
-    }
     const int D = slow_dim(g);
     const long long m = g.n[D];
     const bool fused = g.ng == 1 && !has_prescribed(psi);
@@ -928,13 +930,42 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     a.peer_lo_plane = nullptr;
     a.peer_hi_plane = nullptr;
     memset(&a.ps, 0, sizeof(a.ps));
-    // fused compute + halo exchange over NVLink peer memory (3D TMA kernel): one launch per sweep,
-    // the boundary planes are stored into the neighbours' ghost planes by the sweep kernel itself
+    // fused compute + halo exchange over NVLink peer memory: one launch per sweep (or per group of sweeps), the boundary
+    // slices are stored into the neighbours' ghost slices by the sweep kernel itself
     const bool peer = dist && psi->peer_attached && c->peer_halo && fused && sweep_supports_peer_halo(a);
     unsigned long long* my_flag_lo = c->rank > 0 ? c->d_flags + 0 : nullptr;
     unsigned long long* my_flag_hi = c->rank < c->nranks - 1 ? c->d_flags + 1 : nullptr;
     int64_t n_lo_slab = 0;
     if (peer && c->rank > 0) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank - 1, nullptr, &n_lo_slab);
+
+    // Temporal blocking (several sweeps per pass over HBM) for every group of sweeps that does not carry the norm.
+    // A face without a Dirichlet/Neumann rule must be a slab neighbour.
+    const SweepVariantInfo* vi = sweep_variant_info(g.dim, c->sweep_variant);
+    RNMF_REQUIRE(vi, "unknown sweep_variant %d for %dD frames", c->sweep_variant, g.dim);
+    bool all_faces = true;
+    for (int fi = 0; fi < 2 * g.dim; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
+    bool side_faces = true;                                                         // the faces across the marching direction
+    for (int fi = 0; fi < 2 * (g.dim - 1); ++fi) side_faces = side_faces && a.faces.f[fi].mode != 0;
+    const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
+    const bool slab_faces = side_faces && (has_lo || a.faces.f[2 * D].mode != 0) && (has_hi || a.faces.f[2 * D + 1].mode != 0);
+    const int depth = vi->depth;                                                    // sweeps per temporally blocked launch (1: none)
+    // slabs: the fused peer path with the in-kernel handshake and the deep halo; every rank must take the same decision:
+    // the thinnest slab (floor(n/P), cartesian2d/mod.rs:64-73) has to hold the 2*depth slices that travel
+    const bool tb_single = depth > 1 && !dist && fused && all_faces;
+    const bool tb_peer = depth > 1 && peer && c->peer_inkernel && slab_faces && deep_elems(g) > 0 && g.nglob[D] / c->nranks >= 2 * depth;
+    const bool tb3d = g.dim == 3 && (tb_single || tb_peer);
+    const bool tb2d = g.dim == 2 && tb_single;
+    const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
+
+    if (dist) {
+        // Entry exchange of the current buffer's halos (deep halo: the two slices next to each face; rhs: its ghost
+        // slices, level 1 on the ghost-plane position reads them).  It is also what orders the shell copy above (which
+        // rewrites d2's ghost slices) before the neighbours' first peer stores into d2 of this call: a neighbour cannot
+        // leave its own entry exchange before this rank's send/recv, which is stream-ordered after the copy.
+        rc = halo_exchange_on(psi, psi->d, s, tb_peer ? depth - 1 : 0);
+        if (rc) return rc;
+        if (tb_peer) { rc = halo_exchange_on(const_cast<rnmf_frame*>(rhs), rhs->d, s, depth - 2); if (rc) return rc; }
+    }
 
     // small (L2-resident) frames: all sweeps but a norm-carrying last one in ONE cooperative launch
     int64_t it0 = 0;
@@ -949,44 +980,22 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
         }
     }
 
-    // two sweeps per pass over HBM (kernels_sweep_tb2.cu): every pair of sweeps that does not carry
-    // the norm; a face without a Dirichlet/Neumann rule must be a slab neighbour
-    bool all_faces = true;
-    for (int fi = 0; fi < 6; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
-    // default (variant 0 = auto) for 3D; variant 6 = the single-sweep TMA kernel only
-    const bool tb2_variant = g.dim == 3 && (c->sweep_variant == 0 || c->sweep_variant == 20 || c->sweep_variant == 21 || c->sweep_variant == 22 || c->sweep_variant == 23 || c->sweep_variant == 24 || c->sweep_variant == 25 || c->sweep_variant == 26 || c->sweep_variant == 27 || c->sweep_variant == 28);
-    const bool tb2_single = tb2_variant && !dist && fused && all_faces;
-    // slabs: the fused peer path with the in-kernel handshake; z faces are physical or a neighbour
-    const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
-    bool xy_faces = true;
-    for (int fi = 0; fi < 4; ++fi) xy_faces = xy_faces && a.faces.f[fi].mode != 0;
-    // every rank must take the same decision: the thinnest slab (floor(n/P), cartesian2d/mod.rs:64-73) needs 4 planes
-    const bool tb2_peer = tb2_variant && peer && c->peer_inkernel && D == 2 && g.nglob[D] / c->nranks >= 4 && xy_faces && scratch_planes(g) == 2 &&
-                          (has_lo || a.faces.f[4].mode != 0) && (has_hi || a.faces.f[5].mode != 0);
-    int64_t n_hi_slab = 0;
-    if (tb2_peer && has_hi) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank + 1, nullptr, &n_hi_slab);
-    const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
-
-    // 2D analogue (kernels_sweep2d_tb2.cu): single GPU; variant 0 = auto, 30 = explicit, 20 = single-sweep TMA kernel only
-    // K = 2..6 sweeps per pass (kernels_sweep2d_tbk.cu; opt-in variants 32..40): groups of K sweeps, the rest as pairs / singles
-    const int tbk_depth = g.dim == 2 ? multi_sweep_2d_depth(c->sweep_variant) : 0;
-    const bool tb2_2d = g.dim == 2 && (c->sweep_variant == 0 || c->sweep_variant == 30 || tbk_depth > 0) && !dist && fused && xy_faces;
-    const bool tbk_2d = tb2_2d && tbk_depth > 0;
-
     for (int64_t it = it0; it < n_sweeps; ++it) {
-        if (tbk_2d && it + tbk_depth <= n_pairable) {
+        if (tb2d && depth > 2 && it + depth <= n_pairable) {
+            // K = depth sweeps per pass (kernels_sweep2d_tbk.cu)
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
             t.k_begin = 0; t.k_end = m;
             RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, s));
             c->multi_sweeps += 1;
-            c->multi_sweep_sweeps += tbk_depth;
+            c->multi_sweep_sweeps += depth;
             double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
             psi->parity ^= 1;
-            it += tbk_depth - 1;
+            it += depth - 1;
             continue;
         }
-        if (tb2_2d && it + 2 <= n_pairable) {
+        if (tb2d && (depth == 2 || vi->pairs) && it + 2 <= n_pairable) {
+            // two sweeps per pass (kernels_sweep2d_tb2.cu): the default's remainder, or variant 30
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
             t.k_begin = 0; t.k_end = m;
@@ -997,44 +1006,34 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             ++it;
             continue;
         }
-        if ((tb2_single || tb2_peer) && it + 2 <= n_pairable) {
+        if (tb3d && it + 2 <= n_pairable) {
+            // two sweeps per pass (kernels_sweep_tb2.cu)
             Tb2Args t;
             memset(&t, 0, sizeof(t));
             t.a = a;
             t.a.in = psi->d; t.a.out = psi->d2; t.a.partials = nullptr;
             t.a.k_begin = 0; t.a.k_end = m;
-            if (tb2_peer) {
+            t.deep = deep_elems(g) > 0;
+            if (tb_peer) {
+                // u2 of my two planes next to each neighbour goes into the ghost + deep plane of ITS `out` buffer
                 const int out_phys = psi->parity ^ 1;
-                double* my_phys0 = psi->parity == 0 ? psi->d : psi->d2;
-                t.a.k_begin = has_lo ? 1 : 0;
-                t.a.k_end = has_hi ? m - 1 : m;
-                t.b_lo = has_lo; t.b_hi = has_hi;
-                // u2 boundary planes go to the neighbours' ghost planes of their `out` buffer (as in the single sweep)
-                t.a.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + g.plane * (n_lo_slab + g.ng) : nullptr;
-                t.a.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + g.plane * (g.ng - 1) : nullptr;
-                // u1 boundary planes go to the scratch planes behind the neighbours' physical buffer 0
-                t.peer_u1_lo = has_lo ? psi->peer_lo[0] + scratch_off(g.plane * (n_lo_slab + 2)) + g.plane : nullptr;
-                t.peer_u1_hi = has_hi ? psi->peer_hi[0] + scratch_off(g.plane * (n_hi_slab + 2)) : nullptr;
-                t.u1_in_lo = has_lo ? my_phys0 + scratch_off(g.total) : nullptr;
-                t.u1_in_hi = has_hi ? my_phys0 + scratch_off(g.total) + g.plane : nullptr;
+                t.nb_lo = has_lo; t.nb_hi = has_hi;
+                t.a.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + g.plane * (n_lo_slab + g.ng) : nullptr;    // its z-hi ghost plane
+                t.peer_lo_deep = has_lo ? t.a.peer_lo_plane + g.plane : nullptr;                                  // and the deep plane behind it
+                t.a.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + g.plane * (g.ng - 1) : nullptr;             // its z-lo ghost plane
+                t.peer_hi_deep = has_hi ? t.a.peer_hi_plane - g.plane : nullptr;                                  // and the deep plane in front
                 const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(t);
                 t.a.ps.enabled = 1;
                 t.a.ps.wait_lo = my_flag_lo; t.a.ps.wait_hi = my_flag_hi;
                 t.a.ps.sig_lo = has_lo ? c->peer_flag_lo : nullptr;
                 t.a.ps.sig_hi = has_hi ? c->peer_flag_hi : nullptr;
                 t.a.ps.done = c->d_flags + 3;
-                if (has_lo) { c->done_target[0] += tiles; c->done_target_b[0] += tiles; }
-                if (has_hi) { c->done_target[1] += tiles; c->done_target_b[1] += tiles; }
+                if (has_lo) c->done_target[0] += tiles;
+                if (has_hi) c->done_target[1] += tiles;
                 t.a.ps.target_lo = c->done_target[0]; t.a.ps.target_hi = c->done_target[1];
                 t.a.ps.epoch = c->epoch;
                 t.a.ps.status = c->d_flags + 2;
-                t.half_wait_lo = has_lo ? c->d_flags + 8 : nullptr;
-                t.half_wait_hi = has_hi ? c->d_flags + 9 : nullptr;
-                t.half_sig_lo = has_lo ? (unsigned long long*)c->peer_flag_base_lo + 9 : nullptr;   // its hi-side half flag
-                t.half_sig_hi = has_hi ? (unsigned long long*)c->peer_flag_base_hi + 8 : nullptr;   // its lo-side half flag
-                t.done_b = c->d_flags + 10;
-                t.target_b_lo = c->done_target_b[0]; t.target_b_hi = c->done_target_b[1];
-                c->epoch += 2;
+                c->epoch += 1;                      // one handshake per launch, as for a single sweep
             }
             RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
             c->double_sweeps += 1;
@@ -1174,14 +1173,14 @@ extern "C" int32_t rnmf_frame_peer_export(rnmf_frame* f, void* handles192)
     cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles192;
     double* phys0 = f->parity == 0 ? f->d : f->d2;
     double* phys1 = f->parity == 0 ? f->d2 : f->d;
-    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[0], phys0));
-    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[1], phys1));
+    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[0], phys0 - deep_elems(f->g)));     // handles name the allocation bases
+    RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[1], phys1 - deep_elems(f->g)));
     RNMF_CUDA_TRY(cudaIpcGetMemHandle(&h[2], c->d_flags));
     // tags in the tail padding / spare flag word: attach verifies that the pointer it maps really
     // is the base of the neighbour's buffer (guards against allocator sub-allocation offsets)
     const unsigned long long t0 = peer_tag(c->rank, 0), t1 = peer_tag(c->rank, 1), t2 = peer_tag(c->rank, 2);
-    RNMF_CUDA_TRY(cudaMemcpy(phys0 + f->g.total + 8, &t0, 8, cudaMemcpyHostToDevice));
-    RNMF_CUDA_TRY(cudaMemcpy(phys1 + f->g.total + 8, &t1, 8, cudaMemcpyHostToDevice));
+    RNMF_CUDA_TRY(cudaMemcpy(phys0 + tail_off(f->g) + 8, &t0, 8, cudaMemcpyHostToDevice));
+    RNMF_CUDA_TRY(cudaMemcpy(phys1 + tail_off(f->g) + 8, &t1, 8, cudaMemcpyHostToDevice));
     RNMF_CUDA_TRY(cudaMemcpy(c->d_flags + 7, &t2, 8, cudaMemcpyHostToDevice));
     return RNMF_OK;
 }
@@ -1204,11 +1203,23 @@ extern "C" int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo192, cons
         RNMF_CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
         return RNMF_OK;
     };
+    // a neighbour's buffer: the handle maps its allocation base; the frame pointer (its z-lo ghost plane) sits deep_elems()
+    // further (same x / y extents, hence the same plane size as mine), the tag in its tail pad
+    const long long deep = deep_elems(f->g);
+    auto open_buffer = [&](const cudaIpcMemHandle_t& h, double** out, int64_t n_peer, int peer_rank, int which) -> int {
+        void* mapped = nullptr;
+        int rc = open(h, &mapped);
+        if (rc) return rc;
+        double* frame = (double*)mapped + deep;
+        rc = verify_peer_tag(frame + peer_total(n_peer) + deep + 8, peer_rank, which);
+        if (rc) { cudaIpcCloseMemHandle(mapped); return rc; }
+        *out = frame;
+        return RNMF_OK;
+    };
     if (lo192) {
         const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)lo192;
         for (int i = 0; i < 2; ++i) {
-            int rc = open(h[i], (void**)&f->peer_lo[i]);
-            if (!rc) rc = verify_peer_tag(f->peer_lo[i] + peer_total(f->g.nglob[f->g.dim - 1] / c->nranks) + 8, c->rank - 1, i);
+            int rc = open_buffer(h[i], &f->peer_lo[i], f->g.nglob[f->g.dim - 1] / c->nranks, c->rank - 1, i);
             if (rc) return rc;
         }
         if (!c->peer_flag_base_lo) {
@@ -1223,8 +1234,7 @@ extern "C" int32_t rnmf_frame_peer_attach(rnmf_frame* f, const void* lo192, cons
         int64_t n_hi = 0;
         rnmf_slab_partition(f->g.nglob[f->g.dim - 1], c->nranks, c->rank + 1, nullptr, &n_hi);
         for (int i = 0; i < 2; ++i) {
-            int rc = open(h[i], (void**)&f->peer_hi[i]);
-            if (!rc) rc = verify_peer_tag(f->peer_hi[i] + peer_total(n_hi) + 8, c->rank + 1, i);
+            int rc = open_buffer(h[i], &f->peer_hi[i], n_hi, c->rank + 1, i);
             if (rc) return rc;
         }
         if (!c->peer_flag_base_hi) {
@@ -1381,9 +1391,10 @@ static bool skew_applicable(const rnmf_ctx* c, const rnmf_frame* psi)
     const FrameGeom& g = psi->g;
     bool all_faces = psi->bc_set && !psi->has_reflect;
     for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
-    const int v = c->sweep_variant, C = c->e2e_skew_chunks;
+    const int C = c->e2e_skew_chunks;
+    const SweepVariantInfo* vi = sweep_variant_info(3, c->sweep_variant);
     return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && c->nranks == 1 && all_faces && C >= 2 && g.n[2] / C >= 16 &&
-           g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && (v == 0 || v == 20 || v == 21 || v == 22 || v == 23 || v == 24 || v == 25 || v == 26 || v == 27 || v == 28);
+           g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && vi && vi->depth == 2;
 }
 
 static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,
@@ -1434,6 +1445,7 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
     t.a.variant = c->sweep_variant;
     t.a.chunk_override = c->sweep_chunk;
     t.a.rhs = rhs->d;
+    t.deep = deep_elems(g) > 0;
     double* buf[2] = { psi->d, psi->d2 };
     for (int ch = 0; ch < C; ++ch) {
         SKEW_CUDA(cudaStreamWaitEvent(s, c->ev_chunks[ch], 0));
@@ -1522,6 +1534,7 @@ static int skewed_last_sweeps_and_download(rnmf_ctx* c, rnmf_frame* psi, rnmf_fr
                 Tb2Args t;
                 memset(&t, 0, sizeof(t));
                 t.a = a;
+                t.deep = deep_elems(g) > 0;
                 t.a.in = buf[(lv - 1) & 1]; t.a.out = buf[lv & 1];
                 t.a.k_begin = lo; t.a.k_end = hi;
                 RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));

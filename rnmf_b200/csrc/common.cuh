@@ -151,13 +151,8 @@ int launch_copy_ghost_shell(const FrameGeom& g, const double* src, double* dst, 
 // ghost slice I am about to overwrite), and the last of them to finish publishes epoch+1 to the
 // neighbour.  Dependency chain: my sweep e+1 <- neighbour's sweep e <- my sweep e-1 (complete):
 // no cycle, and the waiter only depends on another GPU's progress.
-// The double-sweep kernel (kernels_sweep_tb2.cu) advances the epoch by two per launch and adds a second
-// flag word per side for the half step: its A chunks next to a neighbour wait flag >= epoch (the neighbour's
-// previous launch has delivered my input ghosts and no longer reads my scratch plane), store u1 of their
-// boundary plane into the neighbour's scratch plane and publish half = epoch+1; its one-plane B chunks wait
-// half >= epoch+1, store u2 of the boundary plane into the neighbour's ghost plane and publish
-// flag = epoch+2.  Each word is written by one kind of chunk per launch, so both stay monotonic, and the
-// single-sweep kernels' "wait flag >= epoch, publish epoch+1" interleaves with it unchanged.
+// The double-sweep kernel (kernels_sweep_tb2.cu) uses the very same protocol, one epoch per launch: with deep halo
+// planes a launch needs nothing from the neighbour that is produced during the launch.
 struct PeerSync {
     const unsigned long long* wait_lo;   // my flag written by the lo neighbour (null: no lo neighbour / not used)
     const unsigned long long* wait_hi;
@@ -267,29 +262,32 @@ struct SweepArgs {
 };
 bool sweep_supports_peer_halo(const SweepArgs& a);
 
-// Two sweeps per pass over HBM (kernels_sweep_tb2.cu).  `a` carries the frame, the range of output
-// planes of the "A" chunks and, for slabs, the full-step handshake and the neighbours' ghost planes
-// of the `out` buffer; the rest is the half-step exchange of u1 boundary planes between slabs.
+// ONE table of sweep-kernel variants (kernels_sweep.cu; option "sweep_variant", 0 = auto = the defaults)
+struct SweepVariantInfo {
+    int id, dim;
+    int depth;          // sweeps per launch of the temporally blocked kernel used for groups of sweeps (1: single sweeps only)
+    bool pairs;         // depth > 2: sweeps left over by the groups are paired up by the two-sweep kernel
+    const char* what;
+};
+const SweepVariantInfo* sweep_variant_info(int dim, int id);    // nullptr: no such variant
+
+// Two sweeps per pass over HBM (kernels_sweep_tb2.cu).  `a` carries the frame, the range of output planes and, for
+// slabs, the handshake and the neighbours' GHOST planes of their `out` buffer (a.peer_lo_plane / a.peer_hi_plane, as for
+// the single-sweep kernel); the deep halo adds the planes behind those ghost planes.
 struct Tb2Args {
     SweepArgs a;
-    int b_lo, b_hi;                            // one-plane "B" chunk for the slab's first / last plane
-    double* peer_u1_lo;                        // neighbours' scratch planes receiving my u1(0) / u1(m-1)
-    double* peer_u1_hi;
-    const double* u1_in_lo;                    // my scratch planes (written by the neighbours)
-    const double* u1_in_hi;
-    const unsigned long long* half_wait_lo;    // my half-step flags / the neighbours' (peer-mapped)
-    const unsigned long long* half_wait_hi;
-    unsigned long long* half_sig_lo;
-    unsigned long long* half_sig_hi;
-    unsigned long long* done_b;                // [2] completion counters of the B chunks
-    unsigned long long target_b_lo, target_b_hi;
+    int deep;                                  // the in / out / rhs buffers carry one extra plane before the z-lo ghost plane and
+                                               // one behind the z-hi ghost plane (capi.cu: deep_elems)
+    int nb_lo, nb_hi;                          // a slab neighbour sits behind the z-lo / z-hi face; its two boundary planes are in
+                                               // my ghost + deep plane when the launch starts
+    double* peer_lo_deep;                      // neighbours' deep planes of their `out` buffer: receive my u2 plane 1 / n2-2
+    double* peer_hi_deep;
 };
 int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s);
 int double_sweep_boundary_ctas(const Tb2Args& t);
 // 2D analogue (kernels_sweep2d_tb2.cu), single GPU: a.k_begin..a.k_end = output rows
 int launch_jacobi_double_sweep_2d(const SweepArgs& a, cudaStream_t s);
-// K = 2..6 sweeps per launch (kernels_sweep2d_tbk.cu; opt-in variants 32..40), single GPU
-int multi_sweep_2d_depth(int variant);              // sweeps per launch of the variant, 0 if it is not a K-sweep variant
+// four sweeps per launch (kernels_sweep2d_tbk.cu), single GPU
 int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s);
 int sweep_boundary_ctas(const SweepArgs& a);     // CTAs per boundary side (tiles across the slice) of the kernel that will run
 

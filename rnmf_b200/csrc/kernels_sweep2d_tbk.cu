@@ -541,29 +541,12 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
 }  // namespace
 
 // sweeps per launch of a 2D sweep variant (0: the variant is not a K-sweep variant)
-int multi_sweep_2d_depth(int variant)
-{
-    return variant == 32 || variant == 36 ? 3 : variant == 33 || variant == 34 || variant == 37 || variant == 38 ? 4 : variant == 35 ? 2 : variant == 39 ? 5 : variant == 40 ? 6 : 0;
-}
-
-// K sweeps (+ ghost fills) per launch, a.k_begin..a.k_end = output rows; every x / y face must carry a
-// Dirichlet or Neumann rule (the caller checks).  Variants: 32 = three sweeps, 512-column strips, two CTAs per SM;
-// 33 = four sweeps, same shape; 34 = four sweeps, 768-column strips (8 warps), one CTA per SM (255 registers);
-// 35 = two sweeps through this kernel (cross-check against kernels_sweep2d_tb2.cu); 36 / 37 / 38 = 32 / 34 / 33 with de-interleaved
-// ring rows (dense E/W loads); 39 / 40 = five / six sweeps per pass (768-column strips, de-interleaved).
+// Four sweeps (+ ghost fills) per launch, a.k_begin..a.k_end = output rows; every x / y face must carry a Dirichlet or Neumann
+// rule (the caller checks).  512-column strips, 4 consumer warps, 8 stages, two CTAs per SM, de-interleaved ring rows (dense
+// E/W loads).  Measured at 8192^2 (sustained, round 2): 636 GLUP/s; the other shapes of the template that were tried --
+// K = 2 / 3 / 5 / 6, 768-column strips, interleaved rings -- gave 443 .. 614 and are no longer instantiated.
 int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
-    switch (a.variant) {
-    case 32: return launch_tbk<3, 4, 8, 2>(a, s);
-    case 33: return launch_tbk<4, 4, 8, 2>(a, s);
-    case 34: return launch_tbk<4, 6, 8, 1>(a, s);
-    case 35: return launch_tbk<2, 4, 10, 2>(a, s);
-    case 36: return launch_tbk<3, 4, 8, 2, true>(a, s);      // 32 with de-interleaved ring rows
-    case 37: return launch_tbk<4, 6, 8, 1, true>(a, s);      // 34 with de-interleaved ring rows
-    case 38: return launch_tbk<4, 4, 8, 2, true>(a, s);      // 33 with de-interleaved ring rows
-    case 39: return launch_tbk<5, 6, 8, 1, true>(a, s);      // five sweeps per pass, 768-column strips, de-interleaved (238 registers)
-    case 40: return launch_tbk<6, 6, 8, 1, true>(a, s);      // six sweeps per pass (253 registers, no spills)
-    default: return -1;
-    }
+    return launch_tbk<4, 4, 8, 2, true>(a, s);
 }

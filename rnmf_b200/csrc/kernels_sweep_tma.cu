@@ -22,6 +22,8 @@
 // Arithmetic: same explicitly rounded sequence as kernels_sweep.cu => bit-identical results.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "tma_util.cuh"
 
 namespace {
@@ -280,30 +282,35 @@ struct MapKey { const double* base; long long pitch, g1, g2n; int bx, by; };
 struct MapSlot { MapKey k; CUtensorMap tm; bool used; };
 static MapSlot g_map_cache[32];
 static int g_map_next = 0;
+static std::mutex g_map_mutex;      // contexts on different host threads share the cache
 
-int encode_map_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by);
+int encode_map_uncached(CUtensorMap* tm, const double* base, long long pitch, long long g1, long long planes, long long plane_stride, int bx, int by);
 
-int encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by)
+// deep = 1: the buffer has one extra plane in front of the z-lo ghost plane and one behind the z-hi ghost plane (capi.cu)
+int encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep)
 {
-    const MapKey k = { base, g.pitch, g.G[1], g.G[2] * g.ncomp, bx, by };
+    const double* b0 = deep ? base - g.plane : base;
+    const long long planes = g.G[2] * g.ncomp + (deep ? 2 : 0);
+    const MapKey k = { b0, g.pitch, g.G[1], planes, bx, by };
+    std::lock_guard<std::mutex> lock(g_map_mutex);
     for (auto& sl : g_map_cache)
         if (sl.used && sl.k.base == k.base && sl.k.pitch == k.pitch && sl.k.g1 == k.g1 && sl.k.g2n == k.g2n && sl.k.bx == k.bx && sl.k.by == k.by) {
             *tm = sl.tm;
             return 0;
         }
-    if (encode_map_uncached(tm, g, base, bx, by)) return -1;
+    if (encode_map_uncached(tm, b0, g.pitch, g.G[1], planes, g.plane, bx, by)) return -1;
     MapSlot& sl = g_map_cache[g_map_next];
     g_map_next = (g_map_next + 1) % 32;
     sl.k = k; sl.tm = *tm; sl.used = true;
     return 0;
 }
 
-int encode_map_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by)
+int encode_map_uncached(CUtensorMap* tm, const double* base, long long pitch, long long g1, long long planes, long long plane_stride, int bx, int by)
 {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return -1;
-    cuuint64_t dims[3] = { (cuuint64_t)g.pitch, (cuuint64_t)g.G[1], (cuuint64_t)(g.G[2] * g.ncomp) };
-    cuuint64_t strides[2] = { (cuuint64_t)g.pitch * 8, (cuuint64_t)g.plane * 8 };
+    cuuint64_t dims[3] = { (cuuint64_t)pitch, (cuuint64_t)g1, (cuuint64_t)planes };
+    cuuint64_t strides[2] = { (cuuint64_t)pitch * 8, (cuuint64_t)plane_stride * 8 };
     cuuint32_t box[3] = { (cuuint32_t)bx, (cuuint32_t)by, 1 };
     cuuint32_t estr[3] = { 1, 1, 1 };
     static int promo = -1;
@@ -315,7 +322,7 @@ int encode_map_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        rnmf_set_error("cuTensorMapEncodeTiled failed (%d): pitch=%lld G1=%lld G2=%lld box=%dx%d", (int)r, g.pitch, g.G[1], g.G[2], bx, by);
+        rnmf_set_error("cuTensorMapEncodeTiled failed (%d): pitch=%lld G1=%lld planes=%lld box=%dx%d", (int)r, pitch, g1, planes, bx, by);
         return -1;
     }
     return 0;
@@ -363,8 +370,8 @@ struct Launcher {
         int chunk;
         plan(a, grid, chunk);
         CUtensorMap tm_psi, tm_rhs;
-        if (encode_map(&tm_psi, a.g, a.in, Cfg::BX, Cfg::BY)) return -1;
-        if (encode_map(&tm_rhs, a.g, a.rhs, 128, TY)) return -1;
+        if (encode_map(&tm_psi, a.g, a.in, Cfg::BX, Cfg::BY, 0)) return -1;
+        if (encode_map(&tm_rhs, a.g, a.rhs, 128, TY, 0)) return -1;
         TmaSweepParams p;
         p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
         p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;
@@ -379,48 +386,30 @@ struct Launcher {
 
 }  // namespace
 
-int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by) { return encode_map(tm, g, base, bx, by); }
+int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by) { return encode_map(tm, g, base, bx, by, 0); }
+int tma3d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep) { return encode_map(tm, g, base, bx, by, deep); }
 
-// variants: 0/6 = 128x8 tile, 4 stages (default); 5 = 128x8, 5 stages; 7 = 128x16, 4 stages;
-//           8 = 128x4, 6 stages; 9 = 128x8, 3 stages; 13 = 128x16, 3 stages
+// 128x8 tile, 4 stages, 2 CTAs per SM (the other tile shapes tried in round 1 -- 128x8x5, 128x16x4, 128x4x6, 128x8x3,
+// 128x16x3 -- were within 2 % or slower and are gone)
+using DefaultLauncher = Launcher<8, 4, 2>;
+
 int tma_sweep_num_partials(const SweepArgs& a)
 {
     dim3 grid;
     int chunk;
-    switch (a.variant) {
-    case 5: return Launcher<8, 5, 2>::plan(a, grid, chunk);
-    case 7: return Launcher<16, 4>::plan(a, grid, chunk);
-    case 8: return Launcher<4, 6, 3>::plan(a, grid, chunk);
-    case 9: return Launcher<8, 3, 2>::plan(a, grid, chunk);
-    case 13: return Launcher<16, 3, 1>::plan(a, grid, chunk);
-    default: return Launcher<8, 4, 2>::plan(a, grid, chunk);
-    }
+    return DefaultLauncher::plan(a, grid, chunk);
 }
 
 int tma_sweep_boundary_ctas(const SweepArgs& a)
 {
     dim3 grid;
     int chunk;
-    switch (a.variant) {
-    case 5: Launcher<8, 5, 2>::plan(a, grid, chunk); break;
-    case 7: Launcher<16, 4>::plan(a, grid, chunk); break;
-    case 8: Launcher<4, 6, 3>::plan(a, grid, chunk); break;
-    case 9: Launcher<8, 3, 2>::plan(a, grid, chunk); break;
-    case 13: Launcher<16, 3, 1>::plan(a, grid, chunk); break;
-    default: Launcher<8, 4, 2>::plan(a, grid, chunk); break;
-    }
+    DefaultLauncher::plan(a, grid, chunk);
     return (int)(grid.x * grid.y);
 }
 
 int launch_jacobi_sweep_tma(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
-    switch (a.variant) {
-    case 5: return Launcher<8, 5, 2>::launch(a, s);
-    case 7: return Launcher<16, 4>::launch(a, s);
-    case 8: return Launcher<4, 6, 3>::launch(a, s);
-    case 9: return Launcher<8, 3, 2>::launch(a, s);
-    case 13: return Launcher<16, 3, 1>::launch(a, s);
-    default: return Launcher<8, 4, 2>::launch(a, s);
-    }
+    return DefaultLauncher::launch(a, s);
 }

@@ -47,16 +47,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// The suspend-time hint lets a waiting warp sleep in the barrier unit instead of spinning through try_wait / branch / yield:
+// the consumers of a DRAM-bound pipeline wait most of the time, and under the 1 kW cap every issued instruction costs clock.
+#ifndef RNMF_MBAR_HINT_NS
+#define RNMF_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
+#if RNMF_MBAR_HINT_NS > 0
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}"
-        ::"r"(bar), "r"(parity)
+        ::"r"(bar), "r"(parity), "r"(RNMF_MBAR_HINT_NS)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar)
@@ -189,5 +198,8 @@ __device__ __forceinline__ void sstore4(uint32_t a, const double2& va, const dou
 
 // tensor map of a frame buffer with a (bx, by, 1) box (kernels_sweep_tma.cu; cached per buffer/geometry/box)
 int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by);
+// same; deep = 1: the tensor starts one plane BEFORE `base` and has G2 + 2 planes (the deep halo planes of the buffer), so a
+// box at z coordinate c covers grown plane c - 1
+int tma3d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep);
 // tensor map of a 2D frame buffer with a (bx, 1) box (kernels_sweep2d_tma.cu)
 int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);

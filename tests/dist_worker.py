@@ -31,11 +31,13 @@ CASES = [
     ([20, 18, 29], [2.0, 2.0, 3.0], MIXED_3D, 3, 2),       # two ghost layers: stand-alone fill + 2-slice halos
     ([33, 41], [1.0, 2.0], MIXED_2D, 4, 2),
 ]
-# extra cases for the double-sweep kernel across slabs (two sweeps per launch, half-step exchange of u1 planes)
+# extra cases for the double-sweep kernel across slabs (two sweeps per launch, deep halo: ghost + deep plane per neighbour)
 TB2_CASES = [
     ([40, 36, 50], [40.0, 72.0, 150.0], MIXED_3D, 9, 1),   # 1 double | 3 doubles + the norm-carrying single
-    ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 8, 1),      # uneven split; 1 double | 2 doubles + 2 singles
+    ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 8, 1),      # uneven split; 1 double | 2 doubles + 2 singles (world 8: slabs too thin, single sweeps)
     ([257, 30, 16], [3.0, 2.0, 1.0], MIXED_3D, 6, 1),      # 4-plane slabs at world 4 (the minimum), ragged x tiles
+    ([65, 27, 43], [1.0, 2.0, 3.0], MIXED_3D, 7, 1),       # odd n0 / n1: x-hi / y-hi ghosts of the travelling planes; 5-plane slabs at world 8
+    ([200, 40, 300], [2.0, 1.0, 3.0], MIXED_3D, 6, 1),     # slabs of several chunks (world 2: 150 planes = 96 + 54)
 ]
 
 
@@ -72,8 +74,8 @@ def run_nccl():
         overlap = mode
         for n, hi, spec, sweeps, ng in CASES + (TB2_CASES if mode == "peer_tb2" else []):
             dim = len(n)
-            # 3D default = the double-sweep kernel ("peer_tb2"); variant 6 = single-sweep TMA kernel only
-            ctx.set_option("sweep_variant", "auto" if (mode == "peer_tb2" or dim == 2) else 6)
+            # "peer_tb2" = the defaults (3D: two sweeps per launch across slabs); the other modes: one sweep per launch only
+            ctx.set_option("sweep_variant", "auto" if mode == "peer_tb2" else (6 if dim == 3 else 20))
             want, l1_ref = reference(n, hi, spec, sweeps, ng)
             bc = R.BCs([R.ComponentBCs([mk[k](v) for k, v in spec[0]], [mk[k](v) for k, v in spec[1]])])
             mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
@@ -88,7 +90,7 @@ def run_nccl():
                 # two calls: the epoch handshake and buffer parity must carry over between calls
                 before = ctx.kernel_launches
                 poisson.jacobi_sweeps(psi, rhs, 2)
-                if mode == "peer_tb2" and dim == 3 and count >= 4:
+                if mode == "peer_tb2" and dim == 3 and n[-1] // world >= 4:
                     # shell copy + ONE double-sweep launch + the closing wait kernel
                     if ctx.kernel_launches - before != 3:
                         ok = False

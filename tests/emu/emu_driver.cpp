@@ -44,6 +44,16 @@ int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, in
     emu::encode(tm, m);
     return 0;
 }
+int tma3d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep)
+{
+    emu::Map m;
+    m.base = deep ? base - g.plane : base; m.rank = 3;
+    m.dims[0] = (unsigned long long)g.pitch; m.dims[1] = (unsigned long long)g.G[1]; m.dims[2] = (unsigned long long)(g.G[2] * g.ncomp + (deep ? 2 : 0));
+    m.stride[0] = 1; m.stride[1] = (unsigned long long)g.pitch; m.stride[2] = (unsigned long long)g.plane;
+    m.box[0] = (unsigned)bx; m.box[1] = (unsigned)by; m.box[2] = 1;
+    emu::encode(tm, m);
+    return 0;
+}
 int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx)
 {
     emu::Map m;
@@ -63,12 +73,16 @@ namespace {
 
 constexpr long long kTail = 64 + 256;       // tail pad + guard band of the library's buffers (capi.cu)
 
+// a frame as the library allocates it (capi.cu: alloc_buffer): [deep plane][grown frame][deep plane][tail pad + guard band];
+// deep planes only for 3D frames.  d(b) = the frame pointer (z-lo ghost plane) of ping-pong buffer b.
 struct Frame {
     FrameGeom g;
-    std::vector<double> buf[2];              // ping-pong; each: total + tail + 2 scratch planes
-    std::vector<double> rhs;
+    long long deep = 0;
+    std::vector<double> buf[2];
+    std::vector<double> rhs_buf;
     int cur = 0;
-    long long scratch_off() const { return g.total + kTail; }
+    double* d(int b) { return buf[b].data() + deep; }
+    double* rhs() { return rhs_buf.data() + deep; }
 };
 
 void unpack(const FrameGeom& g, const double* dense, double* pitched)
@@ -83,36 +97,52 @@ void pack(const FrameGeom& g, const double* pitched, double* dense)
     for (long long r = 0; r < rows; ++r)
         for (long long i = 0; i < g.G[0]; ++i) dense[i + g.G[0] * r] = pitched[g.xoff + i + g.pitch * r];
 }
+// one dense grown plane -> a pitched plane
+void unpack_plane(const FrameGeom& g, const double* dense_plane, double* pitched_plane)
+{
+    for (long long r = 0; r < g.G[1]; ++r)
+        for (long long i = 0; i < g.G[0]; ++i) pitched_plane[g.xoff + i + g.pitch * r] = dense_plane[i + g.G[0] * r];
+}
+
+const double kPoison[3] = { -7.0e300, 9.0e300, 5.0e300 };
 
 void init_frame(Frame& f, int dim, const long long* n, const double* dx, const double* psi_dense, const double* rhs_dense)
 {
     const int64_t n64[3] = { n[0], n[1], dim == 3 ? n[2] : 1 };
     const double lo[3] = { 0, 0, 0 };
     make_geom(f.g, dim, n64, lo, dx, 1, 1);
-    const size_t len = (size_t)(f.g.total + kTail + 2 * f.g.plane);
-    // poison what is not data: padding columns, the tail, the scratch planes
-    f.buf[0].assign(len, -7.0e300); f.buf[1].assign(len, 9.0e300); f.rhs.assign(len, 5.0e300);
-    unpack(f.g, psi_dense, f.buf[0].data());
-    unpack(f.g, psi_dense, f.buf[1].data());       // the library copies the ghost shell into the second buffer
-    unpack(f.g, rhs_dense, f.rhs.data());
+    f.deep = dim == 3 ? f.g.plane : 0;
+    const size_t len = (size_t)(f.deep + f.g.total + f.deep + kTail);
+    // poison what is not data: padding columns, the deep planes, the tail
+    f.buf[0].assign(len, kPoison[0]); f.buf[1].assign(len, kPoison[1]); f.rhs_buf.assign(len, kPoison[2]);
+    unpack(f.g, psi_dense, f.d(0));
+    unpack(f.g, psi_dense, f.d(1));       // the library copies the ghost shell into the second buffer
+    unpack(f.g, rhs_dense, f.rhs());
 }
 
-// cells that are not data (padding columns of every pitched row, the tail pad / guard band, the scratch planes) must still hold
-// the poison init_frame put there: a kernel that stores outside the grown rows of its frame is caught here (on the device the
-// canary band of rnmf_frame_check_guards only sees the end of the buffer)
-long long clobbered_padding(const Frame& f)
+// cells that are not data (padding columns of every pitched row, the tail pad / guard band, and -- unless a slab neighbour owns
+// them -- the deep planes) must still hold the poison init_frame put there: a kernel that stores outside the grown rows of its
+// frame is caught here (on the device the canary band of rnmf_frame_check_guards only sees the end of the buffer)
+long long clobbered_padding(Frame& f, bool deep_lo_written = false, bool deep_hi_written = false)
 {
     long long bad = 0;
-    const double poison[3] = { -7.0e300, 9.0e300, 5.0e300 };
-    const std::vector<double>* bufs[3] = { &f.buf[0], &f.buf[1], &f.rhs };
+    std::vector<double>* bufs[3] = { &f.buf[0], &f.buf[1], &f.rhs_buf };
     const long long rows = f.g.G[1] * f.g.G[2];
     for (int b = 0; b < 3; ++b) {
         const std::vector<double>& v = *bufs[b];
+        const double* d = v.data() + f.deep;
         for (long long r = 0; r < rows; ++r)
             for (long long i = 0; i < f.g.pitch; ++i)
-                if ((i < f.g.xoff || i >= f.g.xoff + f.g.G[0]) && v[(size_t)(f.g.pitch * r + i)] != poison[b]) ++bad;
-        for (size_t q = (size_t)f.g.total; q < v.size(); ++q)
-            if (v[q] != poison[b]) ++bad;
+                if ((i < f.g.xoff || i >= f.g.xoff + f.g.G[0]) && d[f.g.pitch * r + i] != kPoison[b]) ++bad;
+        const bool lo_w = deep_lo_written && b < 2, hi_w = deep_hi_written && b < 2;     // neighbours write psi buffers only
+        for (long long q = 0; q < f.deep; ++q) {
+            const long long col = q % f.g.pitch;
+            const bool pad = col < f.g.xoff || col >= f.g.xoff + f.g.G[0];
+            if (v[(size_t)q] != kPoison[b] && (pad || !lo_w)) ++bad;
+            if (d[f.g.total + q] != kPoison[b] && (pad || !hi_w)) ++bad;
+        }
+        for (size_t q = (size_t)(f.deep + f.g.total + f.deep); q < v.size(); ++q)
+            if (v[q] != kPoison[b]) ++bad;
     }
     return bad;
 }
@@ -225,25 +255,26 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
     a.fuse_fill = 1;
     a.variant = variant;
     a.chunk_override = chunk;
-    a.rhs = f.rhs.data();
+    a.rhs = f.rhs();
     a.k_begin = 0;
     a.k_end = f.g.n[dim - 1];
     for (int it = 0; it < n_pairs; ++it) {
-        a.in = f.buf[f.cur].data();
-        a.out = f.buf[f.cur ^ 1].data();
+        a.in = f.d(f.cur);
+        a.out = f.d(f.cur ^ 1);
         if (dim == 3) {
             Tb2Args t;
             memset(&t, 0, sizeof(t));
             t.a = a;
+            t.deep = 1;
             if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
-        } else if (multi_sweep_2d_depth(variant) > 0) {
-            if (launch_jacobi_multi_sweep_2d(a, nullptr) < 0) return -1;        // n_pairs launches of K sweeps each
-        } else {
+        } else if (variant == 30) {
             if (launch_jacobi_double_sweep_2d(a, nullptr) < 0) return -1;
+        } else {
+            if (launch_jacobi_multi_sweep_2d(a, nullptr) < 0) return -1;        // n_pairs launches of four sweeps each
         }
         f.cur ^= 1;
     }
-    pack(f.g, f.buf[f.cur].data(), out_dense);
+    pack(f.g, f.d(f.cur), out_dense);
     const long long bad = clobbered_padding(f);
     if (bad) fprintf(stderr, "emu: %lld padding / tail cells were overwritten\n", bad);
     return g_deadlocks.load() + (bad ? 1000 : 0);
@@ -268,10 +299,10 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
     init_frame(f, 3, n, dx, psi_dense, rhs_dense);
     const FrameGeom& g = f.g;
     // nothing has arrived: poison all three buffers (init_frame filled them from the dense frames)
-    const std::vector<double> full_psi = f.buf[0], full_rhs = f.rhs;
+    const std::vector<double> full_psi(f.d(0), f.d(0) + g.total), full_rhs(f.rhs(), f.rhs() + g.total);
     std::fill(f.buf[0].begin(), f.buf[0].end(), -3.0e300);
     std::fill(f.buf[1].begin(), f.buf[1].end(), 4.0e300);
-    std::fill(f.rhs.begin(), f.rhs.end(), 6.0e300);
+    std::fill(f.rhs_buf.begin(), f.rhs_buf.end(), 6.0e300);
     Tb2Args t;
     memset(&t, 0, sizeof(t));
     t.a.g = g;
@@ -280,7 +311,8 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
     t.a.fuse_fill = 1;
     t.a.variant = variant;
     t.a.chunk_override = chunk;
-    t.a.rhs = f.rhs.data();
+    t.a.rhs = f.rhs();
+    t.deep = 1;
     const long long n2 = g.n[2];
     for (int ch = 0; ch < n_chunks; ++ch) {
         // "upload" of chunk ch: grown planes [p0, p1) of psi (+ its ghost shell into the partner buffer) and of rhs
@@ -290,22 +322,22 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
             const bool shell_row = jj < 1 || jj >= g.n[1] + 1 || kk < 1 || kk >= n2 + 1;
             for (long long i = 0; i < g.G[0]; ++i) {
                 const long long q = g.xoff + i + g.pitch * r;
-                f.buf[0][q] = full_psi[q];
-                f.rhs[q] = full_rhs[q];
-                if (shell_row || i < 1 || i >= g.n[0] + 1) f.buf[1][q] = full_psi[q];
+                f.d(0)[q] = full_psi[q];
+                f.rhs()[q] = full_rhs[q];
+                if (shell_row || i < 1 || i >= g.n[0] + 1) f.d(1)[q] = full_psi[q];
             }
         }
         for (long long sp = 1; sp <= pairs; ++sp) {
             long long lo, hi;
             skew_region(n2, n_chunks, ch, sp, &lo, &hi);
             if (hi <= lo) continue;
-            t.a.in = f.buf[(sp - 1) & 1].data();
-            t.a.out = f.buf[sp & 1].data();
+            t.a.in = f.d((sp - 1) & 1);
+            t.a.out = f.d(sp & 1);
             t.a.k_begin = lo; t.a.k_end = hi;
             if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
         }
     }
-    pack(g, f.buf[pairs & 1].data(), out_dense);
+    pack(g, f.d(pairs & 1), out_dense);
     return g_deadlocks.load();
 }
 
@@ -327,7 +359,8 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
     t.a.fuse_fill = 1;
     t.a.variant = variant;
     t.a.chunk_override = chunk;
-    t.a.rhs = f.rhs.data();
+    t.a.rhs = f.rhs();
+    t.deep = 1;
     const long long n2 = g.n[2], G0 = g.G[0], G1 = g.G[1];
     std::vector<double> dense((size_t)(G0 * G1 * g.G[2]));
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -335,27 +368,28 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
             long long lo, hi;
             skew_tail_region(n2, n_chunks, ch, lv, levels, &lo, &hi);
             if (hi <= lo) continue;
-            t.a.in = f.buf[(lv - 1) & 1].data();
-            t.a.out = f.buf[lv & 1].data();
+            t.a.in = f.d((lv - 1) & 1);
+            t.a.out = f.d(lv & 1);
             t.a.k_begin = lo; t.a.k_end = hi;
             if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
         }
         // "download" of chunk ch from the final buffer
         const long long p0 = ch == 0 ? 0 : n2 * ch / n_chunks + 1, p1 = ch == n_chunks - 1 ? g.G[2] : n2 * (ch + 1) / n_chunks + 1;
-        pack(g, f.buf[levels & 1].data(), dense.data());
+        pack(g, f.d(levels & 1), dense.data());
         memcpy(out_dense + G0 * G1 * p0, dense.data() + G0 * G1 * p0, (size_t)(G0 * G1 * (p1 - p0)) * sizeof(double));
         // nothing below valid plane Z(ch+1)-2 may be read again
         const long long dead = n2 * (ch + 1) / n_chunks - 2;           // valid planes < dead, i.e. grown planes <= dead
         if (ch < n_chunks - 1)
             for (long long kk = 0; kk <= dead && kk < g.G[2]; ++kk)
-                for (long long q = g.plane * kk; q < g.plane * (kk + 1); ++q) { f.buf[0][q] = -8.0e300; f.buf[1][q] = 8.5e300; }
+                for (long long q = g.plane * kk; q < g.plane * (kk + 1); ++q) { f.d(0)[q] = -8.0e300; f.d(1)[q] = 8.5e300; }
     }
     return g_deadlocks.load();
 }
 
-// The same over z-slabs: `nranks` host threads, each launching its slab's double sweeps; u1 boundary planes and
-// u2 boundary planes travel through the neighbours' buffers, ordered by the half / full step flags -- the
-// argument wiring mirrors rnmf_jacobi_sweeps (capi.cu).  Global dense frames in / out (3D, ng = 1).
+// The same over z-slabs: `nranks` host threads, each launching its slab's double sweeps.  Deep halo: a rank starts with its
+// neighbours' two boundary planes in its ghost + deep plane (what the entry exchange of rnmf_jacobi_sweeps delivers; rhs: the
+// ghost plane) and stores u2 of its own two boundary planes into the neighbours' ghost + deep planes, ordered by the full-step
+// flags -- the argument wiring mirrors rnmf_jacobi_sweeps (capi.cu).  Global dense frames in / out (3D, ng = 1).
 int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
                             const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_pairs, int nranks)
 {
@@ -371,9 +405,13 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
         start[r] = base * r;
         count[r] = r == nranks - 1 ? n[2] - start[r] : base;
         const long long nl[3] = { n[0], n[1], count[r] };
-        // the slab's dense frame = global planes start-1 .. start+count (ghost planes hold the neighbours' planes:
-        // what the entry halo exchange of rnmf_jacobi_sweeps delivers)
+        // the slab's dense frame = global grown planes start .. start+count+1 (its ghost planes hold the neighbours' planes)
         init_frame(fr[r], 3, nl, dx, psi_dense + plane_dense * start[r], rhs_dense + plane_dense * start[r]);
+        // deep planes: the neighbours' second plane from the face
+        if (r > 0)
+            for (int b = 0; b < 2; ++b) unpack_plane(fr[r].g, psi_dense + plane_dense * (start[r] - 1), fr[r].d(b) - fr[r].g.plane);
+        if (r < nranks - 1)
+            for (int b = 0; b < 2; ++b) unpack_plane(fr[r].g, psi_dense + plane_dense * (start[r] + count[r] + 2), fr[r].d(b) + fr[r].g.total);
     }
     std::vector<std::thread> ranks;
     for (int r = 0; r < nranks; ++r)
@@ -385,7 +423,7 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
             for (int i = 0; i < 6; ++i) kind[i] = face_kind[i];
             if (has_lo) kind[4] = RNMF_BC_HALO;
             if (has_hi) kind[5] = RNMF_BC_HALO;
-            unsigned long long epoch = 0, done_a[2] = { 0, 0 }, done_b[2] = { 0, 0 };
+            unsigned long long epoch = 0, done[2] = { 0, 0 };
             for (int it = 0; it < n_pairs; ++it) {
                 Tb2Args t;
                 memset(&t, 0, sizeof(t));
@@ -396,44 +434,37 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
                 a.fuse_fill = 1;
                 a.variant = variant;
                 a.chunk_override = chunk;
-                a.rhs = f.rhs.data();
-                a.in = f.buf[f.cur].data();
-                a.out = f.buf[f.cur ^ 1].data();
-                a.k_begin = has_lo ? 1 : 0;
-                a.k_end = has_hi ? m - 1 : m;
-                t.b_lo = has_lo; t.b_hi = has_hi;
+                a.rhs = f.rhs();
+                a.in = f.d(f.cur);
+                a.out = f.d(f.cur ^ 1);
+                a.k_begin = 0;
+                a.k_end = m;
+                t.deep = 1;
+                t.nb_lo = has_lo; t.nb_hi = has_hi;
                 const int out_phys = f.cur ^ 1;
                 if (has_lo) {
                     Frame& lo = fr[r - 1];
-                    a.peer_lo_plane = lo.buf[out_phys].data() + lo.g.plane * (count[r - 1] + 1);      // its hi ghost plane
-                    t.peer_u1_lo = lo.buf[0].data() + lo.scratch_off() + lo.g.plane;                   // its "from hi" scratch plane
-                    t.u1_in_lo = f.buf[0].data() + f.scratch_off();
-                    t.half_wait_lo = &flags[r].w[8];
-                    t.half_sig_lo = &flags[r - 1].w[9];
+                    a.peer_lo_plane = lo.d(out_phys) + lo.g.plane * (count[r - 1] + 1);               // its z-hi ghost plane
+                    t.peer_lo_deep = a.peer_lo_plane + lo.g.plane;                                     // and the deep plane behind it
                     a.ps.wait_lo = &flags[r].w[0];
                     a.ps.sig_lo = &flags[r - 1].w[1];
                 }
                 if (has_hi) {
                     Frame& hi = fr[r + 1];
-                    a.peer_hi_plane = hi.buf[out_phys].data();                                         // its lo ghost plane
-                    t.peer_u1_hi = hi.buf[0].data() + hi.scratch_off();                                // its "from lo" scratch plane
-                    t.u1_in_hi = f.buf[0].data() + f.scratch_off() + f.g.plane;
-                    t.half_wait_hi = &flags[r].w[9];
-                    t.half_sig_hi = &flags[r + 1].w[8];
+                    a.peer_hi_plane = hi.d(out_phys);                                                  // its z-lo ghost plane
+                    t.peer_hi_deep = a.peer_hi_plane - hi.g.plane;                                     // and the deep plane in front
                     a.ps.wait_hi = &flags[r].w[1];
                     a.ps.sig_hi = &flags[r + 1].w[0];
                 }
                 const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(t);
                 a.ps.enabled = 1;
                 a.ps.done = &flags[r].w[3];
-                if (has_lo) { done_a[0] += tiles; done_b[0] += tiles; }
-                if (has_hi) { done_a[1] += tiles; done_b[1] += tiles; }
-                a.ps.target_lo = done_a[0]; a.ps.target_hi = done_a[1];
+                if (has_lo) done[0] += tiles;
+                if (has_hi) done[1] += tiles;
+                a.ps.target_lo = done[0]; a.ps.target_hi = done[1];
                 a.ps.epoch = epoch;
                 a.ps.status = &flags[r].w[2];
-                t.done_b = &flags[r].w[10];
-                t.target_b_lo = done_b[0]; t.target_b_hi = done_b[1];
-                epoch += 2;
+                epoch += 1;
                 launch_jacobi_double_sweep(t, nullptr);
                 f.cur ^= 1;
             }
@@ -445,9 +476,11 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
     int bad = g_deadlocks.load();
     for (int r = 0; r < nranks; ++r) {
         if (flags[r].w[2]) ++bad;                                   // a handshake wait timed out
+        const long long clob = clobbered_padding(fr[r], r > 0, r < nranks - 1);
+        if (clob) { fprintf(stderr, "emu: rank %d: %lld padding / tail / deep cells were overwritten\n", r, clob); bad += 1000; }
         // valid planes of the slab -> the global dense frame; ghost planes of the outer ranks too
         std::vector<double> dense((size_t)(plane_dense * (count[r] + 2)));
-        pack(fr[r].g, fr[r].buf[fr[r].cur].data(), dense.data());
+        pack(fr[r].g, fr[r].d(fr[r].cur), dense.data());
         const long long p0 = r == 0 ? 0 : 1, p1 = r == nranks - 1 ? count[r] + 2 : count[r] + 1;
         memcpy(out_dense + plane_dense * (start[r] + p0), dense.data() + plane_dense * p0, (size_t)(plane_dense * (p1 - p0)) * sizeof(double));
     }

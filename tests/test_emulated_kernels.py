@@ -67,57 +67,26 @@ def _setup(n, hi, spec, sweeps, seed):
     return g, psi, rhs, want, kinds, vals, dx, nn, ora.coefs(g)
 
 
-@pytest.mark.parametrize("n,hi,spec,pairs,variant,chunk", [
-    ([20, 9, 5], [1.0, 2.0, 3.0], MIXED_3D, 1, 20, 0),
-    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 20, 0),        # one cell / one row past a tile edge; two launches (ping-pong)
-    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 20, 2),       # odd n0 (x-hi ghost in a register), 3 y tiles, 4 z chunks
-    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 20, 0),          # a single plane: both z ghosts of u1 formed in registers
-    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 20, 0),
-    ([40, 10, 6], [1.0, 2.0, 3.0], MIXED_3D, 1, 21, 3),          # 128x8 tile variant
-    # two rows per row warp (variants 24: 128x12 tile + one helper warp, 25: 128x16 tile): N/S of one row from the other's registers
-    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 24, 0),
-    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 24, 2),
-    ([30, 11, 3], [1.0, 1.0, 1.0], MIXED_3D, 1, 24, 0),          # the frame's last row is a warp's FIRST row: y-hi ghost of u1 in registers
-    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 24, 0),
-    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 24, 0),
-    ([129, 17, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 25, 0),
-    ([65, 33, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 25, 2),
-    ([30, 15, 2], [1.0, 1.0, 1.0], MIXED_3D, 1, 25, 0),
-    # variants 22 / 23: quad mapping (a warp owns 2 rows x 64 columns; N/S between the two rows from registers), with / without the
-    # interior-specialised loop
-    ([20, 9, 5], [1.0, 2.0, 3.0], MIXED_3D, 1, 23, 0),           # odd n1: the last row is a warp's row A (y-hi ghost of u1 in row B's registers)
-    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 23, 0),
-    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 23, 2),       # odd n0: x-hi ghost in the pair's second register, in the x-half 1 warp
-    ([63, 24, 3], [1.0, 2.0, 3.0], MIXED_3D, 1, 23, 0),          # x-hi face in the x-half 0 warp; n1 = two full tiles
-    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 23, 0),
-    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 23, 0),
-    ([2, 2, 2], [1.0, 1.0, 1.0], NEUMANN_3D, 2, 23, 0),
-    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 22, 0),
-    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 22, 2),
-    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 22, 3),          # x-hi face exactly at a tile edge; odd n1
-    ([192, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 22, 3),          # x-hi face at the edge of an x-half 0 warp
-    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 22, 2),
-    # variant 26: interior-specialised plane loop for the row warps of x-interior tiles (needs >= 3 tiles in x to have one)
-    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 26, 0),
-    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 26, 2),        # the last tile holds one column; two launches; 2-plane chunks
-    ([384, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 26, 3),          # x-hi face exactly at a tile edge
-    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 26, 2),        # no interior tile at all: the general loop only
-    # variant 27: two rows per row warp + the interior-specialised loop
-    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 27, 0),
-    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 27, 2),
-    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 27, 3),          # odd n1: the frame's last row is a warp's first row (not interior)
-    # variant 28: 27 with de-interleaved u1 ring rows
-    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 28, 0),
-    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 28, 2),
-    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 28, 3),
-    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 28, 2),        # odd n0: x-hi ghost in a register and in the odd half of the row
-    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 28, 0),
-    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 28, 0),
+@pytest.mark.parametrize("n,hi,spec,pairs,chunk", [
+    ([20, 9, 5], [1.0, 2.0, 3.0], MIXED_3D, 1, 0),               # odd n1: the last row is a warp's row A (y-hi ghost of u1 in row B's registers)
+    ([129, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 0),           # one cell / one row past a tile edge; two launches (ping-pong)
+    ([65, 25, 7], [65.0, 50.0, 21.0], MIXED_3D, 1, 2),           # odd n0: x-hi ghost in the pair's second register (x-half 1 warp); 3 y tiles, 4 z chunks
+    ([63, 24, 3], [1.0, 2.0, 3.0], MIXED_3D, 1, 0),              # x-hi face in the x-half 0 warp; n1 = two full tiles
+    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 0),              # a single plane: both z ghosts of u1 formed in registers
+    ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 2, 0),
+    ([2, 2, 2], [1.0, 1.0, 1.0], NEUMANN_3D, 2, 0),
+    ([40, 10, 6], [1.0, 2.0, 3.0], MIXED_3D, 1, 3),
+    # interior-specialised plane loop: warps whose 2 x 64 patch touches no x / y face
+    ([400, 30, 7], [4.0, 2.0, 3.0], MIXED_3D, 1, 0),
+    ([385, 13, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 2),           # the last tile holds one column; two launches; 2-plane chunks
+    ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 3),             # x-hi face exactly at a tile edge; odd n1
+    ([192, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 3),             # x-hi face at the edge of an x-half 0 warp
+    ([200, 30, 20], [1.0, 2.0, 3.0], MIXED_3D, 1, 7),            # several unrolled trips of the fast loop per chunk
 ])
-def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, variant, chunk):
+def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
     out = np.zeros_like(psi)
-    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, pairs)
+    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, pairs)
     assert rc == 0, "a barrier wait timed out (deadlock) or the launch failed"
     np.testing.assert_array_equal(out, want)      # valid cells, face ghosts, and the untouched edges / corners
 
@@ -136,10 +105,9 @@ def test_2d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     np.testing.assert_array_equal(out, want)
 
 
-DEPTH = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4, 39: 5, 40: 6}      # 36 / 37: de-interleaved ring rows      # sweeps per launch of the K-sweep 2D variants (kernels_sweep2d_tbk.cu)
+DEPTH = 4      # sweeps per launch of the K-sweep 2D kernel (kernels_sweep2d_tbk.cu: the one shape that ships)
 
 
-@pytest.mark.parametrize("variant", [35, 32, 33, 34, 36, 37, 38, 39, 40])
 @pytest.mark.parametrize("n,hi,spec,launches,chunk", [
     ([33, 7], [1.0, 2.0], MIXED_2D, 1, 0),
     ([513, 5], [513.0, 5.0], MIXED_2D, 2, 2),                    # one cell past a 512-column strip; 3 row chunks; ping-pong
@@ -153,11 +121,11 @@ DEPTH = {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4, 39: 5, 40: 6}      # 3
     ([64, 40], [1.0, 1.0], MIXED_2D, 1, 0),                      # planner-chosen chunks, steady (unrolled) iterations
     ([131, 50], [1.0, 1.0], MIXED_2D, 1, 25),                    # odd n0 in the second warp; long chunks: several unrolled trips
 ])
-def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk, variant):
-    """K = 2, 3, 4 sweeps per pass (opt-in variants): u_K after `launches` launches == K*launches oracle sweeps, bit for bit."""
-    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, DEPTH[variant] * launches, seed=44)
+def test_2d_multi_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk):
+    """Four sweeps per pass: u_4 after `launches` launches == 4*launches oracle sweeps, bit for bit."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, DEPTH * launches, seed=44)
     out = np.zeros_like(psi)
-    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, launches)
+    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, launches)
     assert rc == 0, "a barrier wait timed out (deadlock) or the launch failed"
     np.testing.assert_array_equal(out, want)
 
@@ -166,61 +134,55 @@ from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
 @settings(max_examples=30, deadline=None, derandomize=True)
-@given(st.sampled_from([32, 33, 34, 35, 36, 37, 38, 39, 40]), st.integers(1, 1100), st.integers(1, 14), st.integers(0, 14), st.integers(0, 3),
-       st.integers(1, 2))
-def test_2d_multi_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, chunk, bc, launches):
+@given(st.integers(1, 1100), st.integers(1, 14), st.integers(0, 14), st.integers(0, 3), st.integers(1, 2))
+def test_2d_multi_sweep_random_shapes_on_the_emulator(emu, n0, n1, chunk, bc, launches):
     """Random frame shapes / chunk lengths / face rules for the K-sweep kernel: strips that end anywhere, chunks shorter than the
     ramp-up, levels clipped at both y faces at once."""
     spec = [MIXED_2D, NEUMANN_2D, ([("dirichlet", 0.5), ("neumann", 0.1)], [("neumann", -0.3), ("dirichlet", 1.5)]),
             ([("dirichlet", 0.0), ("dirichlet", 1.0)], [("dirichlet", 2.0), ("dirichlet", -1.0)])][bc]
-    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup([n0, n1], [1.0 + n0 / 7.0, 2.0], spec, DEPTH[variant] * launches, seed=n0 * 31 + n1)
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup([n0, n1], [1.0 + n0 / 7.0, 2.0], spec, DEPTH * launches, seed=n0 * 31 + n1)
     out = np.zeros_like(psi)
-    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, min(chunk, n1), launches)
+    rc = emu.emu_double_sweeps(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, min(chunk, n1), launches)
     assert rc == 0
     np.testing.assert_array_equal(out, want)
 
 
-@settings(max_examples=24, deadline=None, derandomize=True)
-@given(st.sampled_from([20, 22, 22, 23, 24, 25, 26, 27, 28]), st.integers(1, 400), st.integers(1, 30), st.integers(1, 8), st.integers(0, 8), st.booleans())
-def test_3d_double_sweep_random_shapes_on_the_emulator(emu, variant, n0, n1, n2, chunk, neumann):
-    """Random frame shapes / chunk lengths for the 3D double-sweep variants (default, two rows per warp, interior-specialised,
-    de-interleaved u1 ring)."""
+@settings(max_examples=16, deadline=None, derandomize=True)
+@given(st.integers(1, 400), st.integers(1, 30), st.integers(1, 8), st.integers(0, 8), st.booleans())
+def test_3d_double_sweep_random_shapes_on_the_emulator(emu, n0, n1, n2, chunk, neumann):
+    """Random frame shapes / chunk lengths for the 3D double-sweep kernel."""
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup([n0, n1, n2], [1.0, 2.0, 3.0], NEUMANN_3D if neumann else MIXED_3D, 2,
                                                           seed=n0 * 131 + n1 * 17 + n2)
     out = np.zeros_like(psi)
-    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, min(chunk, n2), 1)
+    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, min(chunk, n2), 1)
     assert rc == 0
     np.testing.assert_array_equal(out, want)
 
 
-@pytest.mark.parametrize("n,hi,spec,pairs,nranks,chunk,variant", [
-    ([20, 9, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 20),           # two slabs: each rank has one neighbour
-    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 20),         # uneven split (5, 5, 7); the middle rank has both
-    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1, 20),        # 4-plane slabs (the minimum), one-plane A chunks
-    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0, 24),         # two rows per row warp
-    ([20, 17, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0, 25),
-    ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 26),         # interior-specialised loop in the A chunks away from the neighbours
-    ([390, 14, 13], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 2, 27),
-    ([390, 14, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 28),
-    ([390, 15, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2, 22),         # quad mapping: u1 / u2 boundary planes of 2 x 2 patches; odd n1
-    ([130, 13, 17], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 0, 22),
-    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 1, 23),        # 4-plane slabs, one-plane A chunks
+@pytest.mark.parametrize("n,hi,spec,pairs,nranks,chunk", [
+    ([20, 9, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0),           # two slabs: each rank has one neighbour
+    ([130, 13, 17], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0),         # uneven split (5, 5, 7); the middle rank has both
+    ([20, 14, 16], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 2),        # 4-plane slabs (the minimum), two-plane chunks: first and last chunk differ
+    ([20, 14, 16], [1.0, 2.0, 3.0], MIXED_3D, 3, 4, 4),          # 4-plane slabs, one chunk: the same CTA serves both neighbours
+    ([390, 15, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2),         # interior-specialised loop between the planes that travel; odd n1
+    ([130, 13, 17], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 3),       # a chunk length that leaves a one-plane last chunk (the planner lengthens it)
+    ([65, 11, 24], [1.0, 2.0, 3.0], MIXED_3D, 3, 2, 5),          # odd n0: the x-hi ghosts of the travelling planes
 ])
-def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk, variant):
+def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial
-    schedule); u1 / u2 boundary planes go through the neighbours' buffers under the half / full step flags."""
+    schedule).  Deep halo: each rank starts with its neighbours' two boundary planes in its ghost + deep plane and stores u2 of its
+    own two boundary planes (whole grown rows, x / y face ghosts included) into the neighbours' planes under the full-step flags."""
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=43)
     out = psi.copy()
-    rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, pairs, nranks)
+    rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, pairs, nranks)
     assert rc == 0, "deadlock / handshake timeout"
     np.testing.assert_array_equal(out, want)
 
 
 @pytest.mark.parametrize("n,spec,n_chunks,pairs,chunk,variant", [
-    ([20, 9, 32], MIXED_3D, 2, 5, 0, 20),           # 16-plane chunks, bands shrink to nothing at the bottom (2*5 < 16)
-    ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 20),         # 8-plane chunks, more pairs than half a chunk: bands of chunk 0 vanish
-    ([130, 13, 20], MIXED_3D, 4, 3, 2, 20),         # two x tiles, two y tiles, several CTAs per band
-    ([20, 9, 24], MIXED_3D, 3, 4, 0, 24),           # two rows per row warp
+    ([20, 9, 32], MIXED_3D, 2, 5, 0, 0),           # 16-plane chunks, bands shrink to nothing at the bottom (2*5 < 16)
+    ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 0),         # 8-plane chunks, more pairs than half a chunk: bands of chunk 0 vanish
+    ([130, 13, 20], MIXED_3D, 4, 3, 2, 0),         # two x tiles, two y tiles, several CTAs per band
 ])
 def test_time_skewed_start_schedule_on_the_emulator(emu, n, spec, n_chunks, pairs, chunk, variant):
     """The band schedule of the opt-in time-skewed start of rnmf_solve_poisson_host (skew_region, common.cuh): planes that have
@@ -235,10 +197,9 @@ def test_time_skewed_start_schedule_on_the_emulator(emu, n, spec, n_chunks, pair
 
 
 @pytest.mark.parametrize("n,spec,n_chunks,levels,chunk,variant", [
-    ([20, 9, 32], MIXED_3D, 2, 5, 0, 20),
-    ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 20),         # 8-plane chunks, 2*levels > chunk: the upper bands are clipped at the top
-    ([130, 13, 20], MIXED_3D, 4, 3, 2, 20),
-    ([20, 9, 24], MIXED_3D, 3, 4, 0, 24),
+    ([20, 9, 32], MIXED_3D, 2, 5, 0, 0),
+    ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 0),         # 8-plane chunks, 2*levels > chunk: the upper bands are clipped at the top
+    ([130, 13, 20], MIXED_3D, 4, 3, 2, 0),
 ])
 def test_time_skewed_end_schedule_on_the_emulator(emu, n, spec, n_chunks, levels, chunk, variant):
     """The band schedule of the END of the opt-in time-skewed host call (skew_tail_region): every chunk is "downloaded" right after

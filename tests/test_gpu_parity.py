@@ -139,7 +139,7 @@ SWEEP_CASES_2D = [
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_2D)
-@pytest.mark.parametrize("variant", [0, 1, 2, 20, 30])
+@pytest.mark.parametrize("variant", [0, 20, 30])      # kernels_sweep.cu: the table of sweep variants
 def test_jacobi_2d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
@@ -171,7 +171,7 @@ SWEEP_CASES_3D = [
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_3D)
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 20, 21])
+@pytest.mark.parametrize("variant", [0, 6])
 def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
@@ -226,16 +226,7 @@ def test_jacobi_2d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
         ctx.set_option("resident", 1)
 
 
-# K = 3 .. 6 sweeps per pass (kernels_sweep2d_tbk.cu, variants 32..40): validated on the CPU box by the kernel emulator
-# (test_emulated_kernels); on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 runs them here
-# RNMF_EXPERIMENTAL_VARIANTS=32,36 restricts the opt-in variants under test (one pytest process per variant on the GPU box, so
-# that a hanging kernel costs one short timeout instead of the whole run)
-_ONLY = {int(v) for v in os.environ.get("RNMF_EXPERIMENTAL_VARIANTS", "").split(",") if v.strip()}
-_MULTI_SWEEP_2D = {k: v for k, v in {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 38: 4, 39: 5, 40: 6}.items() if not _ONLY or k in _ONLY}
-
-
-@pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in kernels: set RNMF_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", sorted(_MULTI_SWEEP_2D))
+# four sweeps per pass (kernels_sweep2d_tbk.cu): the 2D default for groups of four sweeps; the rest runs as pairs / singles
 @pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
     ([301, 301], [301.0, 301.0], MIXED_2D, 12, False),
     ([1500, 300], [15.0, 3.0], MIXED_2D, 13, False),         # several strips and row chunks; leftover sweeps as pairs / singles
@@ -245,11 +236,11 @@ _MULTI_SWEEP_2D = {k: v for k, v in {32: 3, 33: 4, 34: 4, 35: 2, 36: 3, 37: 4, 3
     ([2, 3], [2.0, 3.0], MIXED_2D, 9, True),
     ([2048, 700], [1.0, 1.0], DIRICHLET_2D, 12, False),
 ])
-def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, variant):
-    """kernels_sweep2d_tbk.cu: K 2D sweeps (+ ghost fills) per pass over HBM == K single sweeps, bit for bit."""
+def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
+    """kernels_sweep2d_tbk.cu: four 2D sweeps (+ ghost fills) per pass over HBM == four single sweeps, bit for bit."""
     from rnmf_b200 import poisson
-    K = _MULTI_SWEEP_2D[variant]
-    ctx.set_option("sweep_variant", variant)
+    K = 4
+    ctx.set_option("sweep_variant", "auto")
     ctx.set_option("resident", 0)
     try:
         g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=33)
@@ -277,11 +268,6 @@ def test_jacobi_2d_multi_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, vari
 
 
 ALL_NEUMANN_3D = ([("neumann", 0.3), ("neumann", -0.2), ("neumann", 0.1)], [("neumann", 0.4), ("neumann", 0.6), ("neumann", -0.9)])
-# variants 24 / 25 (two rows per row warp) and 26 / 27 (interior-specialised plane loop) are validated on the CPU box by the kernel emulator (test_emulated_kernels);
-# on hardware they are opt-in until they have been measured: RNMF_EXPERIMENTAL=1 adds them here
-_DOUBLE_SWEEP_VARIANTS = [20, 21, 22, 23, 26] + ([v for v in (24, 25, 27, 28) if not _ONLY or v in _ONLY] if os.environ.get("RNMF_EXPERIMENTAL") == "1" else [])
-
-
 @pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
     ([64, 64, 64], [64.0, 128.0, 192.0], MIXED_3D, 6, False),     # three double sweeps
     ([65, 33, 17], [1.0, 1.0, 1.0], MIXED_3D, 7, False),          # three double sweeps + one single
@@ -292,14 +278,14 @@ _DOUBLE_SWEEP_VARIANTS = [20, 21, 22, 23, 26] + ([v for v in (24, 25, 27, 28) if
     ([127, 25, 1], [1.0, 2.0, 3.0], MIXED_3D, 4, False),          # a single plane: both z ghosts in registers
     ([1, 1, 1], [1.0, 1.0, 1.0], MIXED_3D, 6, False),
     ([260, 30, 2], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 9, True),
-    ([520, 40, 70], [5.0, 2.0, 1.0], MIXED_3D, 6, False),         # five x tiles: three with no x face (variant 26's interior loop)
+    ([520, 40, 70], [5.0, 2.0, 1.0], MIXED_3D, 6, False),         # five x tiles: warps with no x / y face run the interior-specialised loop
+    ([200, 37, 150], [2.0, 1.0, 3.0], MIXED_3D, 4, False),        # two 96-plane chunks; odd n1
 ])
-@pytest.mark.parametrize("variant", _DOUBLE_SWEEP_VARIANTS)
-def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm, variant):
+def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
     """kernels_sweep_tb2.cu: two sweeps (+ the ghost fill after each) per pass over HBM must equal two
     single sweeps bit for bit, for every tiling edge case and both parities of the sweep count."""
     from rnmf_b200 import poisson
-    ctx.set_option("sweep_variant", variant)
+    ctx.set_option("sweep_variant", "auto")
     ctx.set_option("resident", 0)
     try:
         g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=29)
@@ -551,10 +537,9 @@ def test_solve_poisson_host_entry_point(R, ctx):
     assert abs(l1.value - l1_ref) <= NORM_RTOL * l1_ref
 
 
-@pytest.mark.skipif(os.environ.get("RNMF_EXPERIMENTAL") != "1", reason="opt-in path: set RNMF_EXPERIMENTAL=1")
 @pytest.mark.parametrize("sweeps,chunks,pairs", [(41, 4, 10), (24, 8, 56), (19, 2, 4)])
 def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
-    """Option e2e_skew: chunked upload overlapped with the first double sweeps on the bands each chunk makes computable
+    """Option e2e_skew (default 2; 0 = plain): chunked upload overlapped with the first double sweeps on the bands each chunk makes computable
     (capi.cu: skewed_upload_and_first_sweeps).  Same kernels, same operations: bit-identical to the plain call; the launch
     counter shows the skewed path really ran.  The frame is just over the 64 MB threshold of the path."""
     from rnmf_b200 import _capi
@@ -584,7 +569,10 @@ def test_solve_poisson_host_time_skewed_start(R, ctx, sweeps, chunks, pairs):
             outs.append(out)
             norms.append(l1.value)
     finally:
-        ctx.set_option("e2e_skew", 0)
+        ctx.set_option("e2e_skew", 2)
+        ctx.set_option("e2e_skew_chunks", 8)
+        ctx.set_option("e2e_skew_pairs", 56)
+        ctx.set_option("e2e_skew_tail", 32)
     np.testing.assert_array_equal(outs[1], outs[0])
     np.testing.assert_array_equal(outs[2], outs[0])
     assert norms[1] == norms[0]
@@ -682,9 +670,8 @@ def test_full_size_properties(R, ctx, n, spec):
       (2) fill_bc is idempotent (second fill changes nothing: |diff| sums to exactly 0);
       (3) linearity: sweeps(a+b; ra+rb) == sweeps(a; ra) + sweeps(b; rb) with homogeneous
           Dirichlet faces, to rounding (relative 1e-13 of the field's L1 norm);
-      (4) the default path (3D: the double-sweep kernel, two sweeps per pass over HBM) agrees bit for
-          bit with the non-TMA comparison kernel (an independently written kernel: one sweep per
-          launch, different tiling, loads through L1 instead of TMA)."""
+      (4) the default path (3D: two sweeps per pass over HBM, 2D: four) agrees bit for bit with the
+          single-sweep kernel (one sweep per launch, different tiling)."""
     from rnmf_b200 import poisson
     dim = len(n)
     hi = [float(v) for v in n]
@@ -713,7 +700,7 @@ def test_full_size_properties(R, ctx, n, spec):
         diff.axpby_(1.0, psi, -1.0, psi2)
         assert diff.abs_sum() == 0.0
         psi2.close(); rhs2.close()
-        psi3, rhs3, l1c, csc = run(1)                                       # (4) non-TMA kernel
+        psi3, rhs3, l1c, csc = run(6 if dim == 3 else 20)                   # (4) one sweep per launch
         diff.axpby_(1.0, psi, -1.0, psi3)
         assert diff.abs_sum() == 0.0 and l1c == pytest.approx(l1, rel=1e-12)
         psi3.close(); rhs3.close(); psi.close(); rhs.close()
