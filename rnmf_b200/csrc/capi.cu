@@ -216,9 +216,11 @@ int check_peer_status(rnmf_ctx* c)
 
 // DEEP HALO: 3D one-component ng=1 frame buffers carry one extra z-plane in front of the z-lo ghost plane and one behind
 // the z-hi ghost plane (kernels_sweep_tb2.cu): with the neighbour slab's two boundary planes in ghost + deep plane, two sweeps
-// per launch need no data that arrives during the launch.  A frame pointer (`d`, `d2`) addresses the z-lo ghost plane as
+// per launch need no data that arrives during the launch (K sweeps per launch: K slices, i.e. K - 1 deep ones).  A frame pointer (`d`, `d2`) addresses the z-lo ghost plane as
 // before; the allocation starts deep_elems() doubles earlier and the tail pad / canary band follow the rear deep plane.
-long long deep_elems(const FrameGeom& g) { return g.dim == 3 && g.ng == 1 && g.ncomp == 1 ? g.plane : 0; }
+// 2D frames: three extra ROWS in front of the y-lo ghost row and behind the y-hi ghost row (four sweeps per launch across y-slabs).
+int deep_slices(const FrameGeom& g) { return g.ng == 1 && g.ncomp == 1 ? (g.dim == 3 ? 1 : 3) : 0; }
+long long deep_elems(const FrameGeom& g) { return deep_slices(g) * (g.dim == 3 ? g.plane : g.pitch); }
 long long tail_off(const FrameGeom& g) { return g.total + deep_elems(g); }       // first double behind the (rear deep plane of the) frame
 
 int write_guard(double* buf, const FrameGeom& g, cudaStream_t s)
@@ -929,6 +931,9 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
 
     a.peer_lo_plane = nullptr;
     a.peer_hi_plane = nullptr;
+    a.partials = nullptr;
+    a.deep = deep_slices(g);
+    a.nb_lo = a.nb_hi = 0;
     memset(&a.ps, 0, sizeof(a.ps));
     // fused compute + halo exchange over NVLink peer memory: one launch per sweep (or per group of sweeps), the boundary
     // slices are stored into the neighbours' ghost slices by the sweep kernel itself
@@ -952,9 +957,29 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     // slabs: the fused peer path with the in-kernel handshake and the deep halo; every rank must take the same decision:
     // the thinnest slab (floor(n/P), cartesian2d/mod.rs:64-73) has to hold the 2*depth slices that travel
     const bool tb_single = depth > 1 && !dist && fused && all_faces;
-    const bool tb_peer = depth > 1 && peer && c->peer_inkernel && slab_faces && deep_elems(g) > 0 && g.nglob[D] / c->nranks >= 2 * depth;
+    const bool tb_peer = depth > 1 && peer && c->peer_inkernel && slab_faces && deep_slices(g) >= depth - 1 && g.nglob[D] / c->nranks >= 2 * depth;
     const bool tb3d = g.dim == 3 && (tb_single || tb_peer);
-    const bool tb2d = g.dim == 2 && tb_single;
+    const bool tb2d = g.dim == 2 && (tb_single || tb_peer);
+    const long long slice_sz = D == 2 ? g.plane : g.pitch;       // one slice of the slowest direction (z-plane / y-row)
+    // a temporally blocked launch across slabs: u_depth of my `depth` slices next to each neighbour goes into the ghost + deep
+    // slices of ITS `out` buffer, under the same one-epoch-per-launch handshake as a single sweep
+    auto slab_launch_args = [&](SweepArgs& t, int boundary_ctas) {
+        const int out_phys = psi->parity ^ 1;
+        t.nb_lo = has_lo; t.nb_hi = has_hi;
+        t.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + slice_sz * (n_lo_slab + g.ng) : nullptr;    // its hi ghost slice
+        t.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + slice_sz * (g.ng - 1) : nullptr;             // its lo ghost slice
+        t.ps.enabled = 1;
+        t.ps.wait_lo = my_flag_lo; t.ps.wait_hi = my_flag_hi;
+        t.ps.sig_lo = has_lo ? c->peer_flag_lo : nullptr;
+        t.ps.sig_hi = has_hi ? c->peer_flag_hi : nullptr;
+        t.ps.done = c->d_flags + 3;
+        if (has_lo) c->done_target[0] += (unsigned long long)boundary_ctas;
+        if (has_hi) c->done_target[1] += (unsigned long long)boundary_ctas;
+        t.ps.target_lo = c->done_target[0]; t.ps.target_hi = c->done_target[1];
+        t.ps.epoch = c->epoch;
+        t.ps.status = c->d_flags + 2;
+        c->epoch += 1;
+    };
     const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
 
     if (dist) {
@@ -986,6 +1011,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
             t.k_begin = 0; t.k_end = m;
+            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; slab_launch_args(t, multi_sweep_2d_boundary_ctas(t)); }
             RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, s));
             c->multi_sweeps += 1;
             c->multi_sweep_sweeps += depth;
@@ -994,8 +1020,8 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             it += depth - 1;
             continue;
         }
-        if (tb2d && (depth == 2 || vi->pairs) && it + 2 <= n_pairable) {
-            // two sweeps per pass (kernels_sweep2d_tb2.cu): the default's remainder, or variant 30
+        if (tb2d && !dist && (depth == 2 || vi->pairs) && it + 2 <= n_pairable) {
+            // two sweeps per pass (kernels_sweep2d_tb2.cu; single GPU): the default's remainder, or variant 30
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
             t.k_begin = 0; t.k_end = m;
@@ -1008,33 +1034,10 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
         }
         if (tb3d && it + 2 <= n_pairable) {
             // two sweeps per pass (kernels_sweep_tb2.cu)
-            Tb2Args t;
-            memset(&t, 0, sizeof(t));
-            t.a = a;
-            t.a.in = psi->d; t.a.out = psi->d2; t.a.partials = nullptr;
-            t.a.k_begin = 0; t.a.k_end = m;
-            t.deep = deep_elems(g) > 0;
-            if (tb_peer) {
-                // u2 of my two planes next to each neighbour goes into the ghost + deep plane of ITS `out` buffer
-                const int out_phys = psi->parity ^ 1;
-                t.nb_lo = has_lo; t.nb_hi = has_hi;
-                t.a.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + g.plane * (n_lo_slab + g.ng) : nullptr;    // its z-hi ghost plane
-                t.peer_lo_deep = has_lo ? t.a.peer_lo_plane + g.plane : nullptr;                                  // and the deep plane behind it
-                t.a.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + g.plane * (g.ng - 1) : nullptr;             // its z-lo ghost plane
-                t.peer_hi_deep = has_hi ? t.a.peer_hi_plane - g.plane : nullptr;                                  // and the deep plane in front
-                const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(t);
-                t.a.ps.enabled = 1;
-                t.a.ps.wait_lo = my_flag_lo; t.a.ps.wait_hi = my_flag_hi;
-                t.a.ps.sig_lo = has_lo ? c->peer_flag_lo : nullptr;
-                t.a.ps.sig_hi = has_hi ? c->peer_flag_hi : nullptr;
-                t.a.ps.done = c->d_flags + 3;
-                if (has_lo) c->done_target[0] += tiles;
-                if (has_hi) c->done_target[1] += tiles;
-                t.a.ps.target_lo = c->done_target[0]; t.a.ps.target_hi = c->done_target[1];
-                t.a.ps.epoch = c->epoch;
-                t.a.ps.status = c->d_flags + 2;
-                c->epoch += 1;                      // one handshake per launch, as for a single sweep
-            }
+            SweepArgs t = a;
+            t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
+            t.k_begin = 0; t.k_end = m;
+            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; slab_launch_args(t, double_sweep_boundary_ctas(t)); }
             RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
             c->double_sweeps += 1;
             double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
@@ -1436,16 +1439,16 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
         { int k = launch_unpack_dense_rows(g, c->d_staging, rhs->d, nullptr, g.G[1] * p0, g.G[1] * p1, cs); if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; } c->launches += k; }
         SKEW_CUDA(cudaEventRecord(c->ev_chunks[ch], cs));
     }
-    Tb2Args t;
+    SweepArgs t;
     memset(&t, 0, sizeof(t));
-    t.a.g = g;
-    t.a.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
-    t.a.faces = psi->faces[0];
-    t.a.fuse_fill = 1;
-    t.a.variant = c->sweep_variant;
-    t.a.chunk_override = c->sweep_chunk;
-    t.a.rhs = rhs->d;
-    t.deep = deep_elems(g) > 0;
+    t.g = g;
+    t.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
+    t.faces = psi->faces[0];
+    t.fuse_fill = 1;
+    t.variant = c->sweep_variant;
+    t.chunk_override = c->sweep_chunk;
+    t.rhs = rhs->d;
+    t.deep = deep_slices(g);
     double* buf[2] = { psi->d, psi->d2 };
     for (int ch = 0; ch < C; ++ch) {
         SKEW_CUDA(cudaStreamWaitEvent(s, c->ev_chunks[ch], 0));
@@ -1453,9 +1456,9 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
             long long lo, hi;
             skew_region(n2, C, ch, sp, &lo, &hi);
             if (hi <= lo) continue;
-            t.a.in = buf[(sp - 1) & 1];
-            t.a.out = buf[sp & 1];
-            t.a.k_begin = lo; t.a.k_end = hi;
+            t.in = buf[(sp - 1) & 1];
+            t.out = buf[sp & 1];
+            t.k_begin = lo; t.k_end = hi;
             int k = launch_jacobi_double_sweep(t, s);
             if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; }
             c->launches += k;
@@ -1504,6 +1507,7 @@ static int skewed_last_sweeps_and_download(rnmf_ctx* c, rnmf_frame* psi, rnmf_fr
     a.variant = c->sweep_variant;
     a.chunk_override = c->sweep_chunk;
     a.rhs = rhs->d;
+    a.deep = deep_slices(g);
     // partial sums of the norm-carrying level, one segment per band
     std::vector<long long> part_off(C + 1, 0);
     if (last_is_single && l1_update) {
@@ -1531,12 +1535,9 @@ static int skewed_last_sweeps_and_download(rnmf_ctx* c, rnmf_frame* psi, rnmf_fr
                 q.partials = l1_update ? c->d_partials + part_off[ch] : nullptr;
                 RNMF_LAUNCH(c, launch_jacobi_sweep(q, s));
             } else {
-                Tb2Args t;
-                memset(&t, 0, sizeof(t));
-                t.a = a;
-                t.deep = deep_elems(g) > 0;
-                t.a.in = buf[(lv - 1) & 1]; t.a.out = buf[lv & 1];
-                t.a.k_begin = lo; t.a.k_end = hi;
+                SweepArgs t = a;
+                t.in = buf[(lv - 1) & 1]; t.out = buf[lv & 1];
+                t.k_begin = lo; t.k_end = hi; t.partials = nullptr;
                 RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
                 c->skew_launches += 1;
             }

@@ -256,9 +256,14 @@ struct SweepArgs {
                              // 2D: range of valid rows
     int variant;
     int chunk_override;      // 0 = planner decides (measurement knob "sweep_chunk")
-    double* peer_lo_plane;   // fused peer-memory halo (3D TMA kernel): neighbour ghost-plane bases
-    double* peer_hi_plane;   //   for this sweep's `out` buffer, or null
+    double* peer_lo_plane;   // fused peer-memory halo: the lo neighbour's hi GHOST slice / the hi neighbour's lo GHOST slice of
+    double* peer_hi_plane;   //   their `out` buffers, or null (deep slices follow behind / in front of them)
     PeerSync ps;             // in-kernel handshake (enabled = 0: none)
+    // temporally blocked kernels across slabs (DEEP HALO, capi.cu: deep_elems): the in / out / rhs buffers carry `deep` extra
+    // slices of the slowest direction in front of the lo ghost slice and behind the hi ghost slice; nb_lo / nb_hi: a slab
+    // neighbour sits behind that face and its depth boundary slices are in my ghost + deep slices when the launch starts
+    int deep;
+    int nb_lo, nb_hi;
 };
 bool sweep_supports_peer_halo(const SweepArgs& a);
 
@@ -271,24 +276,14 @@ struct SweepVariantInfo {
 };
 const SweepVariantInfo* sweep_variant_info(int dim, int id);    // nullptr: no such variant
 
-// Two sweeps per pass over HBM (kernels_sweep_tb2.cu).  `a` carries the frame, the range of output planes and, for
-// slabs, the handshake and the neighbours' GHOST planes of their `out` buffer (a.peer_lo_plane / a.peer_hi_plane, as for
-// the single-sweep kernel); the deep halo adds the planes behind those ghost planes.
-struct Tb2Args {
-    SweepArgs a;
-    int deep;                                  // the in / out / rhs buffers carry one extra plane before the z-lo ghost plane and
-                                               // one behind the z-hi ghost plane (capi.cu: deep_elems)
-    int nb_lo, nb_hi;                          // a slab neighbour sits behind the z-lo / z-hi face; its two boundary planes are in
-                                               // my ghost + deep plane when the launch starts
-    double* peer_lo_deep;                      // neighbours' deep planes of their `out` buffer: receive my u2 plane 1 / n2-2
-    double* peer_hi_deep;
-};
-int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s);
-int double_sweep_boundary_ctas(const Tb2Args& t);
+// Two sweeps per pass over HBM (kernels_sweep_tb2.cu), also across z-slabs (a.deep >= 1, a.nb_lo / a.nb_hi)
+int launch_jacobi_double_sweep(const SweepArgs& a, cudaStream_t s);
+int double_sweep_boundary_ctas(const SweepArgs& a);
 // 2D analogue (kernels_sweep2d_tb2.cu), single GPU: a.k_begin..a.k_end = output rows
 int launch_jacobi_double_sweep_2d(const SweepArgs& a, cudaStream_t s);
-// four sweeps per launch (kernels_sweep2d_tbk.cu), single GPU
+// four sweeps per launch (kernels_sweep2d_tbk.cu), also across y-slabs (a.deep >= 3, a.nb_lo / a.nb_hi)
 int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s);
+int multi_sweep_2d_boundary_ctas(const SweepArgs& a);
 int sweep_boundary_ctas(const SweepArgs& a);     // CTAs per boundary side (tiles across the slice) of the kernel that will run
 
 // peer-memory halo handshake (kernels_peer.cu): epoch flags live in each rank's own memory and

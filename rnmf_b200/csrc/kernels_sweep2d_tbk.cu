@@ -20,7 +20,12 @@
 //     waits for the previous iteration's arrivals before it loads (that wait is also the
 //     write-after-read guard of the slot it overwrites).
 // Every operation is explicitly rounded in the reference's association (poisson.rs:83-85):
-// u_K is bit-identical to K single sweeps.  Single GPU only.
+// u_K is bit-identical to K single sweeps.
+// y-slabs (one GPU per slab), DEEP HALO as in kernels_sweep_tb2.cu: the frame buffers carry K-1 extra rows in front of the y-lo
+// ghost row and behind the y-hi ghost row.  With the neighbour's K boundary rows in ghost + deep rows a slab face towards a
+// neighbour is a chunk boundary (no face rule, no clipping of the lower levels); u_K of my K rows next to the face goes into the
+// neighbour's ghost + deep rows of its `out` buffer (whole grown rows, x-face ghosts included) under the single-sweep kernels'
+// epoch handshake, one epoch per launch.
 #include <stdlib.h>
 
 #include "tma_util.cuh"
@@ -35,6 +40,15 @@ struct TbkParams {
     FaceSet faces;
     long long m_begin, m_end;   // output rows
     int chunk;
+    int n_chunks;
+    int nb_lo, nb_hi;           // a slab neighbour behind the y-lo / y-hi face
+    int yshift;                 // the tensor maps start this many rows before the y-lo ghost row (deep rows present)
+    // slabs: u_K of my rows [0, K) also goes to the lo neighbour's y-hi ghost + deep rows, of my rows [n1-K, n1) to the hi
+    // neighbour's deep + y-lo ghost rows (its `out` buffer).  Both are a CONSTANT element offset from where the row goes in my own
+    // `out` buffer (same pitch, same x offsets): destination = own address + delta
+    int has_peer_lo, has_peer_hi;
+    long long peer_lo_delta, peer_hi_delta;
+    PeerSync ps;
 };
 
 // DI: ring rows are stored de-interleaved -- even positions first, odd positions from ODD_OFF -- so that the E/W loads
@@ -68,14 +82,16 @@ struct LevelPlan {
     int nL1;            // level-1 rows
 };
 template <int K>
-__device__ __forceinline__ LevelPlan<K> make_plan(long long j0, long long j1, long long n1)
+__device__ __forceinline__ LevelPlan<K> make_plan(long long j0, long long j1, long long n1, bool nb_lo, bool nb_hi)
 {
     LevelPlan<K> p;
     long long lo[K], hi[K];
+    // level l covers the output rows grown by K-l rows either side, clipped at a PHYSICAL y face (its ghost rule replaces the
+    // missing neighbour row); towards a slab neighbour the deep rows make the grown range computable
 #pragma unroll
     for (int l = 1; l <= K; ++l) {
-        lo[l - 1] = j0 - (K - l) > 0 ? j0 - (K - l) : 0;
-        hi[l - 1] = j1 - 1 + (K - l) < n1 - 1 ? j1 - 1 + (K - l) : n1 - 1;
+        lo[l - 1] = (j0 - (K - l) > 0 || nb_lo) ? j0 - (K - l) : 0;
+        hi[l - 1] = (j1 - 1 + (K - l) < n1 - 1 || nb_hi) ? j1 - 1 + (K - l) : n1 - 1;
     }
     p.a = lo[0];
     p.nL1 = (int)(hi[0] - lo[0]) + 1;
@@ -83,12 +99,16 @@ __device__ __forceinline__ LevelPlan<K> make_plan(long long j0, long long j1, lo
     for (int l = 1; l <= K; ++l) {
         p.first[l - 1] = (int)(lo[l - 1] - p.a) + (l - 1);
         p.last[l - 1] = (int)(hi[l - 1] - p.a) + (l - 1);
-        p.it_ylo[l - 1] = lo[l - 1] == 0 ? p.first[l - 1] : -1;
-        p.it_yhi[l - 1] = hi[l - 1] == n1 - 1 ? p.last[l - 1] : -1;
+        p.it_ylo[l - 1] = (!nb_lo && lo[l - 1] == 0) ? p.first[l - 1] : -1;
+        p.it_yhi[l - 1] = (!nb_hi && hi[l - 1] == n1 - 1) ? p.last[l - 1] : -1;
     }
     p.n_it = p.last[K - 1] + 1;
-    p.s0 = p.first[K - 1] + (lo[K - 1] == 0 ? 1 : 0);
+    p.s0 = p.first[K - 1] + ((!nb_lo && lo[K - 1] == 0) ? 1 : 0);
     p.s1 = p.last[0];
+    // rows that also go to a slab neighbour (the first / last K rows of the slab) are stored by the general iterations:
+    // level K forms row r in iteration r - a + K - 1
+    if (nb_lo && j0 < K) { const int e = (int)(K - 1 - p.a) + K; if (e > p.s0) p.s0 = e; }
+    if (nb_hi && j1 > n1 - K) { const int b = (int)(n1 - K - p.a) + K - 2; if (b < p.s1) p.s1 = b; }
     return p;
 }
 
@@ -163,10 +183,24 @@ __device__ __forceinline__ void xface_ring(const LaneK<K>& k, uint32_t us, doubl
     }
 }
 
+// u_K of the lane's four cells into one grown row: the valid cells and the x-face ghosts fill_bc gives them
+template <int K, bool XF>
+__device__ __forceinline__ void row_store(const LaneK<K>& k, double* oa, const double2& o_a, const double2& o_b)
+{
+    store4(oa, o_a, o_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+    if (XF && k.any_x) {
+        if (k.do_xlo) oa[-1] = ghost1(k.fx0, o_a.x);
+        if (k.xhi_sel >= 0) {
+            const double m = k.xhi_sel == 0 ? o_a.x : k.xhi_sel == 1 ? o_a.y : k.xhi_sel == 2 ? o_b.x : o_b.y;
+            oa[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, m);
+        }
+    }
+}
+
 // XF: an edge warp -- it owns a cell next to an x face, or columns past the frame (masked stores).  Warp-uniform, so
 // the ghost code and the store masks are compiled out of the other warps' loop.
 template <int K, int NW, int NS, bool DI, bool STEADY, bool XF>
-__device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, const int it)
+__device__ __forceinline__ void rowk_iter(const TbkParams& p, const LaneK<K>& k, StateK<K>& st, const int it)
 {
     using Cfg = CfgK<K, NW, NS, DI>;
     const double2 zero2 = make_double2(0.0, 0.0);
@@ -238,17 +272,14 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
                 if (XF && k.any_x) xface_ring(k, us, o_a, o_b);
             } else {
                 double* oa = st.oa;
-                store4(oa, o_a, o_b, !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
-                if (XF && k.any_x) {
-                    if (k.do_xlo) oa[-1] = ghost1(k.fx0, o_a.x);
-                    if (k.xhi_sel >= 0) {
-                        const double m = k.xhi_sel == 0 ? o_a.x : k.xhi_sel == 1 ? o_a.y : k.xhi_sel == 2 ? o_b.x : o_b.y;
-                        oa[(k.xhi_sel >= 2 ? 64 : 0) + (k.xhi_sel & 1) + 1] = ghost1(k.fx1, m);
-                    }
-                }
+                row_store<K, XF>(k, oa, o_a, o_b);
                 if (!STEADY) {
                     if (it == k.lp.it_ylo[K - 1]) store4(oa - k.pitch, ghost1(k.fy0, o_a), ghost1(k.fy0, o_b), !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
                     if (it == k.lp.it_yhi[K - 1]) store4(oa + k.pitch, ghost1(k.fy1, o_a), ghost1(k.fy1, o_b), !XF || k.full, k.va0, k.va1, k.vb0, k.vb1);
+                    // rows next to a slab neighbour: the same grown row into its ghost / deep rows (NVLink stores)
+                    const long long r = k.lp.a - (K - 1) + it;          // the row level K forms in this iteration
+                    if (p.has_peer_lo && r < K) row_store<K, XF>(k, oa + p.peer_lo_delta, o_a, o_b);
+                    if (p.has_peer_hi && r >= p.g.n[1] - K) row_store<K, XF>(k, oa + p.peer_hi_delta, o_a, o_b);
                 }
                 st.oa = oa + k.pitch;
             }
@@ -277,16 +308,16 @@ __device__ __forceinline__ void rowk_iter(const LaneK<K>& k, StateK<K>& st, cons
 // the iterations of a chunk: ramp-up (levels start one after the other, y-lo faces), the steady part unrolled by
 // three (the three-row windows rotate by renaming), drain (y-hi faces)
 template <int K, int NW, int NS, bool DI, bool XF>
-__device__ __forceinline__ void rowk_chunk(const LaneK<K>& k, StateK<K>& st)
+__device__ __forceinline__ void rowk_chunk(const TbkParams& p, const LaneK<K>& k, StateK<K>& st)
 {
     int it = 0;
-    for (; it < k.lp.s0 && it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, DI, false, XF>(k, st, it);
+    for (; it < k.lp.s0 && it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, DI, false, XF>(p, k, st, it);
     for (; it + 2 <= k.lp.s1; it += 3) {
-        rowk_iter<K, NW, NS, DI, true, XF>(k, st, it);
-        rowk_iter<K, NW, NS, DI, true, XF>(k, st, it + 1);
-        rowk_iter<K, NW, NS, DI, true, XF>(k, st, it + 2);
+        rowk_iter<K, NW, NS, DI, true, XF>(p, k, st, it);
+        rowk_iter<K, NW, NS, DI, true, XF>(p, k, st, it + 1);
+        rowk_iter<K, NW, NS, DI, true, XF>(p, k, st, it + 2);
     }
-    for (; it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, DI, false, XF>(k, st, it);
+    for (; it < k.lp.n_it; ++it) rowk_iter<K, NW, NS, DI, false, XF>(p, k, st, it);
 }
 
 template <int K, int NW, int NS, int MINB, bool DI>
@@ -306,10 +337,14 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n0 = p.g.n[0], n1 = p.g.n[1];
     const long long i0 = (long long)blockIdx.x * TXC;
-    const long long j0 = p.m_begin + (long long)blockIdx.y * p.chunk;
+    const unsigned yc = p.ps.enabled ? peer_chunk_order(blockIdx.y, (unsigned)p.n_chunks) : blockIdx.y;      // boundary chunks last
+    const long long j0 = p.m_begin + (long long)yc * p.chunk;
     const long long j1 = j0 + p.chunk < p.m_end ? j0 + p.chunk : p.m_end;
-    const LevelPlan<K> lp = make_plan<K>(j0, j1, n1);
+    const LevelPlan<K> lp = make_plan<K>(j0, j1, n1, p.nb_lo != 0, p.nb_hi != 0);
     const int n_rows = lp.nL1 + 2;                          // u0 rows a-1..b+1 (row a-1+idx <-> stage idx % NS)
+    // slab handshake roles: the chunk reads the neighbour's rows and stores into the neighbour's buffer
+    const bool sync_lo = p.ps.enabled && p.nb_lo && j0 == 0;
+    const bool sync_hi = p.ps.enabled && p.nb_hi && j1 == n1;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -320,6 +355,8 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         mbar_init(ufull0, Cfg::NCONS);
         mbar_init(ufull0 + 8, Cfg::NCONS);
         mbar_fence_init();
+        if (sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
+        if (sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
     }
     __syncthreads();
 
@@ -327,7 +364,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         // ------------------------------ producer warp ------------------------------
         if (lane == 0) {
             const int cx = (int)(p.g.xoff + p.g.ng + i0 - PAD);
-            int cy = (int)(p.g.ng + lp.a - 1);
+            int cy = (int)(p.g.ng + lp.a - 1) + p.yshift;
             uint32_t s = 0, wrap = 0;
             for (int idx = 0; idx < n_rows; ++idx) {
                 if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
@@ -485,13 +522,20 @@ __global__ void __launch_bounds__(32 * (NW + 2), MINB) jacobi2d_tbk_kernel(const
         // warp-uniform: does this warp's 128-column span touch an x face or reach past the frame?
         const long long w0 = i0 + 128 * warp;
         const bool warp_x = (k.fx0.on && w0 == 0) || (k.fx1.on && last >= w0 && last < w0 + 128) || w0 + 128 > n0;
-        if (warp_x) rowk_chunk<K, NW, NS, DI, true>(k, st);
-        else rowk_chunk<K, NW, NS, DI, false>(k, st);
+        if (warp_x) rowk_chunk<K, NW, NS, DI, true>(p, k, st);
+        else rowk_chunk<K, NW, NS, DI, false>(p, k, st);
+    }
+    if (sync_lo || sync_hi) {
+        __syncthreads();                                       // every peer store of this CTA has been issued
+        if (threadIdx.x == 0) {
+            if (sync_lo) peer_publish(p.ps.done + 0, p.ps.target_lo, p.ps.sig_lo, p.ps.epoch + 1);
+            if (sync_hi) peer_publish(p.ps.done + 1, p.ps.target_hi, p.ps.sig_hi, p.ps.epoch + 1);
+        }
     }
 }
 
 template <int K, int NW, int NS, int MINB, bool DI = false>
-int launch_tbk(const SweepArgs& a, cudaStream_t s)
+void plan_tbk(const SweepArgs& a, dim3& grid, int& chunk)
 {
     using Cfg = CfgK<K, NW, NS, DI>;
     const FrameGeom& g = a.g;
@@ -516,15 +560,40 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
     }
     if (a.chunk_override > 0) best_c = a.chunk_override > span ? span : a.chunk_override;
     if (best_c < 1) best_c = 1;
-    const dim3 grid((unsigned)bx, (unsigned)((span + best_c - 1) / best_c), 1);
+    // slabs: the first / last chunk holds all K rows that go to the neighbour
+    if (a.nb_lo || a.nb_hi) {
+        if (best_c < K) best_c = span < K ? span : K;
+        while ((span + best_c - 1) / best_c > 1 && span - ((span + best_c - 1) / best_c - 1) * best_c < K) ++best_c;
+    }
+    chunk = (int)best_c;
+    grid = dim3((unsigned)bx, (unsigned)((span + best_c - 1) / best_c), 1);
+}
+
+template <int K, int NW, int NS, int MINB, bool DI = false>
+int launch_tbk(const SweepArgs& a, cudaStream_t s)
+{
+    using Cfg = CfgK<K, NW, NS, DI>;
+    const FrameGeom& g = a.g;
+    dim3 grid;
+    int chunk;
+    plan_tbk<K, NW, NS, MINB, DI>(a, grid, chunk);
+    if ((a.nb_lo || a.nb_hi) && a.deep < K - 1) { rnmf_set_error("K-sweep kernel across slabs needs K-1 deep halo rows"); return -1; }
+    const int deep = a.deep >= K - 1 ? K - 1 : 0;           // rows in front of the y-lo ghost row that the tensor maps include
     CUtensorMap tm_u256, tm_upad, tm_r256, tm_rpad;
-    if (tma2d_encode_map(&tm_u256, g, a.in, 256)) return -1;
-    if (tma2d_encode_map(&tm_upad, g, a.in, 2 * Cfg::PAD)) return -1;
-    if (tma2d_encode_map(&tm_r256, g, a.rhs, 256)) return -1;
-    if (tma2d_encode_map(&tm_rpad, g, a.rhs, 2 * Cfg::PAD)) return -1;
+    if (tma2d_encode_map_deep(&tm_u256, g, a.in, 256, deep)) return -1;
+    if (tma2d_encode_map_deep(&tm_upad, g, a.in, 2 * Cfg::PAD, deep)) return -1;
+    if (tma2d_encode_map_deep(&tm_r256, g, a.rhs, 256, deep)) return -1;
+    if (tma2d_encode_map_deep(&tm_rpad, g, a.rhs, 2 * Cfg::PAD, deep)) return -1;
     TbkParams p;
     p.g = g; p.out = a.out; p.c = a.c; p.faces = a.faces;
-    p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = (int)best_c;
+    p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk; p.n_chunks = (int)grid.y;
+    p.nb_lo = a.nb_lo; p.nb_hi = a.nb_hi; p.yshift = deep;
+    // my row r sits at out + pitch*(r + ng) (+ x); the lo neighbour's hi ghost row (a.peer_lo_plane) receives row 0, the hi
+    // neighbour's lo ghost row (a.peer_hi_plane) receives row n1-1: element offsets between the two address spaces
+    p.has_peer_lo = a.peer_lo_plane != nullptr; p.has_peer_hi = a.peer_hi_plane != nullptr;
+    p.peer_lo_delta = p.has_peer_lo ? (long long)(((intptr_t)a.peer_lo_plane - (intptr_t)a.out) / 8) - g.pitch * g.ng : 0;
+    p.peer_hi_delta = p.has_peer_hi ? (long long)(((intptr_t)a.peer_hi_plane - (intptr_t)a.out) / 8) - g.pitch * (g.n[1] - 1 + g.ng) : 0;
+    p.ps = a.ps;
     auto kern = jacobi2d_tbk_kernel<K, NW, NS, MINB, DI>;
 #ifndef RNMF_EMULATE
     static PerDeviceOnce attr_set;                      // one per instantiation
@@ -540,7 +609,6 @@ int launch_tbk(const SweepArgs& a, cudaStream_t s)
 
 }  // namespace
 
-// sweeps per launch of a 2D sweep variant (0: the variant is not a K-sweep variant)
 // Four sweeps (+ ghost fills) per launch, a.k_begin..a.k_end = output rows; every x / y face must carry a Dirichlet or Neumann
 // rule (the caller checks).  512-column strips, 4 consumer warps, 8 stages, two CTAs per SM, de-interleaved ring rows (dense
 // E/W loads).  Measured at 8192^2 (sustained, round 2): 636 GLUP/s; the other shapes of the template that were tried --
@@ -549,4 +617,13 @@ int launch_jacobi_multi_sweep_2d(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
     return launch_tbk<4, 4, 8, 2, true>(a, s);
+}
+
+// CTAs per boundary side (strips across a row): the first / last chunk of the launch takes part in the handshake
+int multi_sweep_2d_boundary_ctas(const SweepArgs& a)
+{
+    dim3 grid;
+    int chunk;
+    plan_tbk<4, 4, 8, 2, true>(a, grid, chunk);
+    return (int)grid.x;
 }

@@ -13,6 +13,8 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -311,30 +313,35 @@ struct MapKey2 { const double* base; long long pitch, g1n; int bx; };
 struct MapSlot2 { MapKey2 k; CUtensorMap tm; bool used; };
 static MapSlot2 g_map_cache2[32];
 static int g_map_next2 = 0;
+static std::mutex g_map_mutex2;     // contexts on different host threads share the cache
 
-int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);
+int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, long long rows, int bx);
 
-// cached: see kernels_sweep_tma.cu
-int encode_map2d(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx)
+// cached: see kernels_sweep_tma.cu.  deep > 0: the buffer has `deep` extra rows in front of the y-lo ghost row and behind the
+// y-hi ghost row (capi.cu), and the tensor covers them
+int encode_map2d(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int deep)
 {
-    const MapKey2 k = { base, g.pitch, g.G[1] * g.ncomp, bx };
+    const double* b0 = base - (long long)deep * g.pitch;
+    const long long rows = g.G[1] * g.ncomp + 2 * deep;
+    const MapKey2 k = { b0, g.pitch, rows, bx };
+    std::lock_guard<std::mutex> lock(g_map_mutex2);
     for (auto& sl : g_map_cache2)
         if (sl.used && sl.k.base == k.base && sl.k.pitch == k.pitch && sl.k.g1n == k.g1n && sl.k.bx == k.bx) {
             *tm = sl.tm;
             return 0;
         }
-    if (encode_map2d_uncached(tm, g, base, bx)) return -1;
+    if (encode_map2d_uncached(tm, g, b0, rows, bx)) return -1;
     MapSlot2& sl = g_map_cache2[g_map_next2];
     g_map_next2 = (g_map_next2 + 1) % 32;
     sl.k = k; sl.tm = *tm; sl.used = true;
     return 0;
 }
 
-int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx)
+int encode_map2d_uncached(CUtensorMap* tm, const FrameGeom& g, const double* base, long long rows, int bx)
 {
     EncodeTiledFn enc = get_encoder2d();
     if (!enc) return -1;
-    cuuint64_t dims[2] = { (cuuint64_t)g.pitch, (cuuint64_t)(g.G[1] * g.ncomp) };
+    cuuint64_t dims[2] = { (cuuint64_t)g.pitch, (cuuint64_t)rows };
     cuuint64_t strides[1] = { (cuuint64_t)g.pitch * 8 };
     cuuint32_t box[2] = { (cuuint32_t)bx, 1 };
     cuuint32_t estr[2] = { 1, 1 };
@@ -388,7 +395,8 @@ int launch2d_one(const dim3& grid, const CUtensorMap& a, const CUtensorMap& b, c
 
 }  // namespace
 
-int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx) { return encode_map2d(tm, g, base, bx); }
+int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx) { return encode_map2d(tm, g, base, bx, 0); }
+int tma2d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int deep) { return encode_map2d(tm, g, base, bx, deep); }
 
 int tma2d_sweep_num_partials(const SweepArgs& a)
 {
@@ -412,9 +420,9 @@ int launch_jacobi_sweep_tma2d(const SweepArgs& a, cudaStream_t s)
     int chunk;
     plan2d(a, grid, chunk);
     CUtensorMap tm_psi256, tm_psi4, tm_rhs256;
-    if (encode_map2d(&tm_psi256, a.g, a.in, 256)) return -1;
-    if (encode_map2d(&tm_psi4, a.g, a.in, 4)) return -1;
-    if (encode_map2d(&tm_rhs256, a.g, a.rhs, 256)) return -1;
+    if (encode_map2d(&tm_psi256, a.g, a.in, 256, 0)) return -1;
+    if (encode_map2d(&tm_psi4, a.g, a.in, 4, 0)) return -1;
+    if (encode_map2d(&tm_rhs256, a.g, a.rhs, 256, 0)) return -1;
     Tma2dParams p;
     p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces; p.fuse_fill = a.fuse_fill;
     p.partials = a.partials; p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk;

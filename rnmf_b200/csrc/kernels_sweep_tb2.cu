@@ -580,10 +580,10 @@ template <int TY, int NS>
 struct Tb2Launcher {
     using Cfg = Tb2Cfg<TY, NS>;
     // chunk length: whole waves of one CTA per SM, each CTA paying chunk+3 plane iterations
-    static void plan(const Tb2Args& t, dim3& grid, int& chunk, int& n_chunks)
+    static void plan(const SweepArgs& a, dim3& grid, int& chunk, int& n_chunks)
     {
-        const FrameGeom& g = t.a.g;
-        const long long span = t.a.k_end - t.a.k_begin;
+        const FrameGeom& g = a.g;
+        const long long span = a.k_end - a.k_begin;
         const long long tiles = ((g.n[0] + 127) / 128) * ((g.n[1] + TY - 1) / TY);
         long long best_c = 1, best_cost = -1;
         // at most 128 planes: CTAs that march longer drift apart, and the halo rows / columns a CTA shares with its neighbours
@@ -601,35 +601,36 @@ struct Tb2Launcher {
             }
             if (c >= span) break;
         }
-        if (t.a.chunk_override > 0) best_c = t.a.chunk_override > span ? span : t.a.chunk_override;
+        if (a.chunk_override > 0) best_c = a.chunk_override > span ? span : a.chunk_override;
         // slabs: the first / last chunk holds both planes that go to the neighbour
-        if ((t.nb_lo || t.nb_hi) && best_c < 2) best_c = span < 2 ? span : 2;
+        if ((a.nb_lo || a.nb_hi) && best_c < 2) best_c = span < 2 ? span : 2;
         if (best_c < 1) best_c = 1;
         chunk = (int)best_c;
         n_chunks = (int)((span + best_c - 1) / best_c);
         // a one-plane last chunk would split the two planes that go to the hi neighbour over two chunks: lengthen the chunks
-        while (t.nb_hi && n_chunks > 1 && span - (long long)(n_chunks - 1) * chunk < 2) {
+        while (a.nb_hi && n_chunks > 1 && span - (long long)(n_chunks - 1) * chunk < 2) {
             chunk += 1;
             n_chunks = (int)((span + chunk - 1) / chunk);
         }
         grid = dim3((unsigned)((g.n[0] + 127) / 128), (unsigned)((g.n[1] + TY - 1) / TY), (unsigned)n_chunks);
     }
-    static int launch(const Tb2Args& t, cudaStream_t s)
+    static int launch(const SweepArgs& a, cudaStream_t s)
     {
-        const SweepArgs& a = t.a;
         dim3 grid;
         int chunk, n_chunks;
-        plan(t, grid, chunk, n_chunks);
+        plan(a, grid, chunk, n_chunks);
         CUtensorMap tm_u0, tm_rhs;
-        const int deep = t.deep ? 1 : 0;
+        const int deep = a.deep ? 1 : 0;
         if (tma3d_encode_map_deep(&tm_u0, a.g, a.in, Cfg::BX, Cfg::U0_ROWS, deep)) return -1;
         if (tma3d_encode_map_deep(&tm_rhs, a.g, a.rhs, Cfg::BX, Cfg::R_ROWS, deep)) return -1;
         Tb2Params p;
         p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
         p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk; p.n_chunks = n_chunks;
-        p.nb_lo = t.nb_lo; p.nb_hi = t.nb_hi; p.zshift = deep;
+        p.nb_lo = a.nb_lo; p.nb_hi = a.nb_hi; p.zshift = deep;
+        // the neighbours' ghost planes and the deep planes behind / in front of them
         p.peer_lo_ghost = a.peer_lo_plane; p.peer_hi_ghost = a.peer_hi_plane;
-        p.peer_lo_deep = t.peer_lo_deep; p.peer_hi_deep = t.peer_hi_deep;
+        p.peer_lo_deep = a.peer_lo_plane ? a.peer_lo_plane + a.g.plane : nullptr;
+        p.peer_hi_deep = a.peer_hi_plane ? a.peer_hi_plane - a.g.plane : nullptr;
         p.ps = a.ps;
 #ifndef RNMF_EMULATE
         static PerDeviceOnce attr_set;
@@ -647,18 +648,18 @@ struct Tb2Launcher {
 
 // 128 x 12 tile, 6 stages: 16 warps, 128 registers (registers are allocated per 4 warps, so 128x14 or 128x16 tiles would
 // leave only 96 registers per thread and spill)
-int launch_jacobi_double_sweep(const Tb2Args& t, cudaStream_t s)
+int launch_jacobi_double_sweep(const SweepArgs& a, cudaStream_t s)
 {
-    if (t.a.k_end <= t.a.k_begin) return 0;
-    if ((t.nb_lo || t.nb_hi) && !t.deep) { rnmf_set_error("double sweep across slabs needs deep halo planes"); return -1; }
-    return Tb2Launcher<12, 6>::launch(t, s);
+    if (a.k_end <= a.k_begin) return 0;
+    if ((a.nb_lo || a.nb_hi) && a.deep < 1) { rnmf_set_error("double sweep across slabs needs deep halo planes"); return -1; }
+    return Tb2Launcher<12, 6>::launch(a, s);
 }
 
 // CTAs per boundary side (tiles across a z-plane): the first / last chunk of the launch takes part in the handshake
-int double_sweep_boundary_ctas(const Tb2Args& t)
+int double_sweep_boundary_ctas(const SweepArgs& a)
 {
     dim3 grid;
     int chunk, n_chunks;
-    Tb2Launcher<12, 6>::plan(t, grid, chunk, n_chunks);
+    Tb2Launcher<12, 6>::plan(a, grid, chunk, n_chunks);
     return (int)(grid.x * grid.y);
 }

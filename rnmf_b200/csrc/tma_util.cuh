@@ -203,3 +203,5 @@ int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, in
 int tma3d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep);
 // tensor map of a 2D frame buffer with a (bx, 1) box (kernels_sweep2d_tma.cu)
 int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);
+// same; deep > 0: the tensor starts `deep` rows BEFORE `base` and has G1 + 2*deep rows, so a box at y coordinate c covers grown row c - deep
+int tma2d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int deep);

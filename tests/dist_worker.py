@@ -38,6 +38,10 @@ TB2_CASES = [
     ([257, 30, 16], [3.0, 2.0, 1.0], MIXED_3D, 6, 1),      # 4-plane slabs at world 4 (the minimum), ragged x tiles
     ([65, 27, 43], [1.0, 2.0, 3.0], MIXED_3D, 7, 1),       # odd n0 / n1: x-hi / y-hi ghosts of the travelling planes; 5-plane slabs at world 8
     ([200, 40, 300], [2.0, 1.0, 3.0], MIXED_3D, 6, 1),     # slabs of several chunks (world 2: 150 planes = 96 + 54)
+    # 2D y-slabs, four sweeps per launch (deep halo: ghost + 3 deep rows per neighbour)
+    ([700, 130], [7.0, 1.3], MIXED_2D, 13, 1),             # two strips; 2 | 2 groups of four + 2 singles + the norm-carrying single
+    ([1031, 67], [1.0, 1.0], MIXED_2D, 10, 1),             # odd n0; 8-row slabs at world 8 (the minimum)
+    ([64, 400], [1.0, 4.0], MIXED_2D, 9, 1),               # several chunks per slab
 ]
 
 

@@ -65,6 +65,17 @@ int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, in
     return 0;
 }
 
+int tma2d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int deep)
+{
+    emu::Map m;
+    m.base = base - (long long)deep * g.pitch; m.rank = 2;
+    m.dims[0] = (unsigned long long)g.pitch; m.dims[1] = (unsigned long long)(g.G[1] * g.ncomp + 2 * deep); m.dims[2] = 1;
+    m.stride[0] = 1; m.stride[1] = (unsigned long long)g.pitch; m.stride[2] = 0;
+    m.box[0] = (unsigned)bx; m.box[1] = 1; m.box[2] = 1;
+    emu::encode(tm, m);
+    return 0;
+}
+
 #include "../../rnmf_b200/csrc/kernels_sweep_tb2.cu"
 #include "../../rnmf_b200/csrc/kernels_sweep2d_tb2.cu"
 #include "../../rnmf_b200/csrc/kernels_sweep2d_tbk.cu"
@@ -74,10 +85,11 @@ namespace {
 constexpr long long kTail = 64 + 256;       // tail pad + guard band of the library's buffers (capi.cu)
 
 // a frame as the library allocates it (capi.cu: alloc_buffer): [deep plane][grown frame][deep plane][tail pad + guard band];
-// deep planes only for 3D frames.  d(b) = the frame pointer (z-lo ghost plane) of ping-pong buffer b.
+// 3D: one deep plane either side, 2D: three deep rows.  d(b) = the frame pointer (lo ghost slice) of ping-pong buffer b.
 struct Frame {
     FrameGeom g;
-    long long deep = 0;
+    long long deep = 0;             // doubles
+    int deep_slices = 0;
     std::vector<double> buf[2];
     std::vector<double> rhs_buf;
     int cur = 0;
@@ -97,11 +109,12 @@ void pack(const FrameGeom& g, const double* pitched, double* dense)
     for (long long r = 0; r < rows; ++r)
         for (long long i = 0; i < g.G[0]; ++i) dense[i + g.G[0] * r] = pitched[g.xoff + i + g.pitch * r];
 }
-// one dense grown plane -> a pitched plane
-void unpack_plane(const FrameGeom& g, const double* dense_plane, double* pitched_plane)
+// one dense grown slice (3D: a plane of G1 rows, 2D: one row) -> a pitched slice
+void unpack_slice(const FrameGeom& g, const double* dense_slice, double* pitched_slice)
 {
-    for (long long r = 0; r < g.G[1]; ++r)
-        for (long long i = 0; i < g.G[0]; ++i) pitched_plane[g.xoff + i + g.pitch * r] = dense_plane[i + g.G[0] * r];
+    const long long rows = g.dim == 3 ? g.G[1] : 1;
+    for (long long r = 0; r < rows; ++r)
+        for (long long i = 0; i < g.G[0]; ++i) pitched_slice[g.xoff + i + g.pitch * r] = dense_slice[i + g.G[0] * r];
 }
 
 const double kPoison[3] = { -7.0e300, 9.0e300, 5.0e300 };
@@ -111,7 +124,8 @@ void init_frame(Frame& f, int dim, const long long* n, const double* dx, const d
     const int64_t n64[3] = { n[0], n[1], dim == 3 ? n[2] : 1 };
     const double lo[3] = { 0, 0, 0 };
     make_geom(f.g, dim, n64, lo, dx, 1, 1);
-    f.deep = dim == 3 ? f.g.plane : 0;
+    f.deep_slices = dim == 3 ? 1 : 3;
+    f.deep = dim == 3 ? f.g.plane : 3 * f.g.pitch;
     const size_t len = (size_t)(f.deep + f.g.total + f.deep + kTail);
     // poison what is not data: padding columns, the deep planes, the tail
     f.buf[0].assign(len, kPoison[0]); f.buf[1].assign(len, kPoison[1]); f.rhs_buf.assign(len, kPoison[2]);
@@ -134,7 +148,7 @@ long long clobbered_padding(Frame& f, bool deep_lo_written = false, bool deep_hi
         for (long long r = 0; r < rows; ++r)
             for (long long i = 0; i < f.g.pitch; ++i)
                 if ((i < f.g.xoff || i >= f.g.xoff + f.g.G[0]) && d[f.g.pitch * r + i] != kPoison[b]) ++bad;
-        const bool lo_w = deep_lo_written && b < 2, hi_w = deep_hi_written && b < 2;     // neighbours write psi buffers only
+        const bool lo_w = deep_lo_written, hi_w = deep_hi_written;     // psi: the neighbours' stores; rhs: the driver's "entry exchange"
         for (long long q = 0; q < f.deep; ++q) {
             const long long col = q % f.g.pitch;
             const bool pad = col < f.g.xoff || col >= f.g.xoff + f.g.G[0];
@@ -258,15 +272,12 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
     a.rhs = f.rhs();
     a.k_begin = 0;
     a.k_end = f.g.n[dim - 1];
+    a.deep = f.deep_slices;
     for (int it = 0; it < n_pairs; ++it) {
         a.in = f.d(f.cur);
         a.out = f.d(f.cur ^ 1);
         if (dim == 3) {
-            Tb2Args t;
-            memset(&t, 0, sizeof(t));
-            t.a = a;
-            t.deep = 1;
-            if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
+            if (launch_jacobi_double_sweep(a, nullptr) < 0) return -1;
         } else if (variant == 30) {
             if (launch_jacobi_double_sweep_2d(a, nullptr) < 0) return -1;
         } else {
@@ -303,15 +314,15 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
     std::fill(f.buf[0].begin(), f.buf[0].end(), -3.0e300);
     std::fill(f.buf[1].begin(), f.buf[1].end(), 4.0e300);
     std::fill(f.rhs_buf.begin(), f.rhs_buf.end(), 6.0e300);
-    Tb2Args t;
+    SweepArgs t;
     memset(&t, 0, sizeof(t));
-    t.a.g = g;
-    t.a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
-    t.a.faces = make_faces(3, face_kind, face_value, dx);
-    t.a.fuse_fill = 1;
-    t.a.variant = variant;
-    t.a.chunk_override = chunk;
-    t.a.rhs = f.rhs();
+    t.g = g;
+    t.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+    t.faces = make_faces(3, face_kind, face_value, dx);
+    t.fuse_fill = 1;
+    t.variant = variant;
+    t.chunk_override = chunk;
+    t.rhs = f.rhs();
     t.deep = 1;
     const long long n2 = g.n[2];
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -331,9 +342,9 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
             long long lo, hi;
             skew_region(n2, n_chunks, ch, sp, &lo, &hi);
             if (hi <= lo) continue;
-            t.a.in = f.d((sp - 1) & 1);
-            t.a.out = f.d(sp & 1);
-            t.a.k_begin = lo; t.a.k_end = hi;
+            t.in = f.d((sp - 1) & 1);
+            t.out = f.d(sp & 1);
+            t.k_begin = lo; t.k_end = hi;
             if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
         }
     }
@@ -351,15 +362,15 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
     Frame f;
     init_frame(f, 3, n, dx, psi_dense, rhs_dense);
     const FrameGeom& g = f.g;
-    Tb2Args t;
+    SweepArgs t;
     memset(&t, 0, sizeof(t));
-    t.a.g = g;
-    t.a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
-    t.a.faces = make_faces(3, face_kind, face_value, dx);
-    t.a.fuse_fill = 1;
-    t.a.variant = variant;
-    t.a.chunk_override = chunk;
-    t.a.rhs = f.rhs();
+    t.g = g;
+    t.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+    t.faces = make_faces(3, face_kind, face_value, dx);
+    t.fuse_fill = 1;
+    t.variant = variant;
+    t.chunk_override = chunk;
+    t.rhs = f.rhs();
     t.deep = 1;
     const long long n2 = g.n[2], G0 = g.G[0], G1 = g.G[1];
     std::vector<double> dense((size_t)(G0 * G1 * g.G[2]));
@@ -368,9 +379,9 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
             long long lo, hi;
             skew_tail_region(n2, n_chunks, ch, lv, levels, &lo, &hi);
             if (hi <= lo) continue;
-            t.a.in = f.d((lv - 1) & 1);
-            t.a.out = f.d(lv & 1);
-            t.a.k_begin = lo; t.a.k_end = hi;
+            t.in = f.d((lv - 1) & 1);
+            t.out = f.d(lv & 1);
+            t.k_begin = lo; t.k_end = hi;
             if (launch_jacobi_double_sweep(t, nullptr) < 0) return -1;
         }
         // "download" of chunk ch from the final buffer
@@ -386,32 +397,45 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
     return g_deadlocks.load();
 }
 
-// The same over z-slabs: `nranks` host threads, each launching its slab's double sweeps.  Deep halo: a rank starts with its
-// neighbours' two boundary planes in its ghost + deep plane (what the entry exchange of rnmf_jacobi_sweeps delivers; rhs: the
-// ghost plane) and stores u2 of its own two boundary planes into the neighbours' ghost + deep planes, ordered by the full-step
-// flags -- the argument wiring mirrors rnmf_jacobi_sweeps (capi.cu).  Global dense frames in / out (3D, ng = 1).
-int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
-                            const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_pairs, int nranks)
+// The same over slabs of the slowest direction (3D: z-slabs, two sweeps per launch; 2D: y-slabs, four sweeps per launch):
+// `nranks` host threads, each launching its slab's kernel.  Deep halo: a rank starts with its neighbours' `depth` boundary slices
+// in its ghost + deep slices (what the entry exchange of rnmf_jacobi_sweeps delivers; rhs: depth-1 slices) and stores u_depth of
+// its own `depth` boundary slices into the neighbours' ghost + deep slices, ordered by the full-step flags -- the argument
+// wiring mirrors rnmf_jacobi_sweeps (capi.cu).  Global dense frames in / out (ng = 1).
+int emu_sweeps_slabs(int dim, const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
+                     const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_launches, int nranks)
 {
+    (void)variant;
     g_deadlocks = 0;
-    const long long G0 = n[0] + 2, G1 = n[1] + 2, plane_dense = G0 * G1;
+    const int D = dim - 1;
+    const int depth = dim == 3 ? 2 : 4;
+    const long long G0 = n[0] + 2, slice_dense = dim == 3 ? G0 * (n[1] + 2) : G0;
     std::vector<Frame> fr(nranks);
     std::vector<long long> start(nranks), count(nranks);
     struct Flags { unsigned long long w[16]; };
     std::vector<Flags> flags(nranks);
     for (auto& fl : flags) memset(&fl, 0, sizeof(fl));
     for (int r = 0; r < nranks; ++r) {
-        const long long base = n[2] / nranks;                     // Domain::new_rectangular: remainder to the last block
+        const long long base = n[D] / nranks;                     // Domain::new_rectangular: remainder to the last block
         start[r] = base * r;
-        count[r] = r == nranks - 1 ? n[2] - start[r] : base;
-        const long long nl[3] = { n[0], n[1], count[r] };
-        // the slab's dense frame = global grown planes start .. start+count+1 (its ghost planes hold the neighbours' planes)
-        init_frame(fr[r], 3, nl, dx, psi_dense + plane_dense * start[r], rhs_dense + plane_dense * start[r]);
-        // deep planes: the neighbours' second plane from the face
-        if (r > 0)
-            for (int b = 0; b < 2; ++b) unpack_plane(fr[r].g, psi_dense + plane_dense * (start[r] - 1), fr[r].d(b) - fr[r].g.plane);
-        if (r < nranks - 1)
-            for (int b = 0; b < 2; ++b) unpack_plane(fr[r].g, psi_dense + plane_dense * (start[r] + count[r] + 2), fr[r].d(b) + fr[r].g.total);
+        count[r] = r == nranks - 1 ? n[D] - start[r] : base;
+        long long nl[3] = { n[0], n[1], dim == 3 ? n[2] : 1 };
+        nl[D] = count[r];
+        // the slab's dense frame = global grown slices start .. start+count+1 (its ghost slices hold the neighbours' slices)
+        Frame& f = fr[r];
+        init_frame(f, dim, nl, dx, psi_dense + slice_dense * start[r], rhs_dense + slice_dense * start[r]);
+        const long long slice = dim == 3 ? f.g.plane : f.g.pitch;
+        // deep slices: the neighbours' slices further from the face (psi: depth-1 of them; rhs: depth-2)
+        for (int e = 1; e < depth; ++e) {
+            if (r > 0) {
+                for (int b = 0; b < 2; ++b) unpack_slice(f.g, psi_dense + slice_dense * (start[r] - e), f.d(b) - slice * e);
+                if (e < depth - 1) unpack_slice(f.g, rhs_dense + slice_dense * (start[r] - e), f.rhs() - slice * e);
+            }
+            if (r < nranks - 1) {
+                for (int b = 0; b < 2; ++b) unpack_slice(f.g, psi_dense + slice_dense * (start[r] + count[r] + 1 + e), f.d(b) + slice * (count[r] + 1 + e));
+                if (e < depth - 1) unpack_slice(f.g, rhs_dense + slice_dense * (start[r] + count[r] + 1 + e), f.rhs() + slice * (count[r] + 1 + e));
+            }
+        }
     }
     std::vector<std::thread> ranks;
     for (int r = 0; r < nranks; ++r)
@@ -419,44 +443,41 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
             Frame& f = fr[r];
             const bool has_lo = r > 0, has_hi = r < nranks - 1;
             const long long m = count[r];
+            const long long slice = dim == 3 ? f.g.plane : f.g.pitch;
             int kind[6];
             for (int i = 0; i < 6; ++i) kind[i] = face_kind[i];
-            if (has_lo) kind[4] = RNMF_BC_HALO;
-            if (has_hi) kind[5] = RNMF_BC_HALO;
+            if (has_lo) kind[2 * D] = RNMF_BC_HALO;
+            if (has_hi) kind[2 * D + 1] = RNMF_BC_HALO;
             unsigned long long epoch = 0, done[2] = { 0, 0 };
-            for (int it = 0; it < n_pairs; ++it) {
-                Tb2Args t;
-                memset(&t, 0, sizeof(t));
-                SweepArgs& a = t.a;
+            for (int it = 0; it < n_launches; ++it) {
+                SweepArgs a;
+                memset(&a, 0, sizeof(a));
                 a.g = f.g;
                 a.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
-                a.faces = make_faces(3, kind, face_value, dx);
+                a.faces = make_faces(dim, kind, face_value, dx);
                 a.fuse_fill = 1;
-                a.variant = variant;
                 a.chunk_override = chunk;
                 a.rhs = f.rhs();
                 a.in = f.d(f.cur);
                 a.out = f.d(f.cur ^ 1);
                 a.k_begin = 0;
                 a.k_end = m;
-                t.deep = 1;
-                t.nb_lo = has_lo; t.nb_hi = has_hi;
+                a.deep = f.deep_slices;
+                a.nb_lo = has_lo; a.nb_hi = has_hi;
                 const int out_phys = f.cur ^ 1;
                 if (has_lo) {
                     Frame& lo = fr[r - 1];
-                    a.peer_lo_plane = lo.d(out_phys) + lo.g.plane * (count[r - 1] + 1);               // its z-hi ghost plane
-                    t.peer_lo_deep = a.peer_lo_plane + lo.g.plane;                                     // and the deep plane behind it
+                    a.peer_lo_plane = lo.d(out_phys) + slice * (count[r - 1] + 1);                    // its hi ghost slice
                     a.ps.wait_lo = &flags[r].w[0];
                     a.ps.sig_lo = &flags[r - 1].w[1];
                 }
                 if (has_hi) {
                     Frame& hi = fr[r + 1];
-                    a.peer_hi_plane = hi.d(out_phys);                                                  // its z-lo ghost plane
-                    t.peer_hi_deep = a.peer_hi_plane - hi.g.plane;                                     // and the deep plane in front
+                    a.peer_hi_plane = hi.d(out_phys);                                                  // its lo ghost slice
                     a.ps.wait_hi = &flags[r].w[1];
                     a.ps.sig_hi = &flags[r + 1].w[0];
                 }
-                const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(t);
+                const unsigned long long tiles = (unsigned long long)(dim == 3 ? double_sweep_boundary_ctas(a) : multi_sweep_2d_boundary_ctas(a));
                 a.ps.enabled = 1;
                 a.ps.done = &flags[r].w[3];
                 if (has_lo) done[0] += tiles;
@@ -465,10 +486,11 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
                 a.ps.epoch = epoch;
                 a.ps.status = &flags[r].w[2];
                 epoch += 1;
-                launch_jacobi_double_sweep(t, nullptr);
+                if (dim == 3) launch_jacobi_double_sweep(a, nullptr);
+                else launch_jacobi_multi_sweep_2d(a, nullptr);
                 f.cur ^= 1;
             }
-            // the closing wait of rnmf_jacobi_sweeps: the neighbours' last stores into my ghost planes have landed
+            // the closing wait of rnmf_jacobi_sweeps: the neighbours' last stores into my ghost slices have landed
             if (has_lo) peer_spin_wait(&flags[r].w[0], epoch, &flags[r].w[2]);
             if (has_hi) peer_spin_wait(&flags[r].w[1], epoch, &flags[r].w[2]);
         });
@@ -478,11 +500,11 @@ int emu_double_sweeps_slabs(const long long* n, const double* dx, const int* fac
         if (flags[r].w[2]) ++bad;                                   // a handshake wait timed out
         const long long clob = clobbered_padding(fr[r], r > 0, r < nranks - 1);
         if (clob) { fprintf(stderr, "emu: rank %d: %lld padding / tail / deep cells were overwritten\n", r, clob); bad += 1000; }
-        // valid planes of the slab -> the global dense frame; ghost planes of the outer ranks too
-        std::vector<double> dense((size_t)(plane_dense * (count[r] + 2)));
+        // valid slices of the slab -> the global dense frame; ghost slices of the outer ranks too
+        std::vector<double> dense((size_t)(slice_dense * (count[r] + 2)));
         pack(fr[r].g, fr[r].d(fr[r].cur), dense.data());
         const long long p0 = r == 0 ? 0 : 1, p1 = r == nranks - 1 ? count[r] + 2 : count[r] + 1;
-        memcpy(out_dense + plane_dense * (start[r] + p0), dense.data() + plane_dense * p0, (size_t)(plane_dense * (p1 - p0)) * sizeof(double));
+        memcpy(out_dense + slice_dense * (start[r] + p0), dense.data() + slice_dense * p0, (size_t)(slice_dense * (p1 - p0)) * sizeof(double));
     }
     return bad;
 }

@@ -174,8 +174,25 @@ def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pa
     own two boundary planes (whole grown rows, x / y face ghosts included) into the neighbours' planes under the full-step flags."""
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=43)
     out = psi.copy()
-    rc = emu.emu_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, pairs, nranks)
+    rc = emu.emu_sweeps_slabs(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, pairs, nranks)
     assert rc == 0, "deadlock / handshake timeout"
+    np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("n,hi,spec,launches,nranks,chunk", [
+    ([33, 16], [1.0, 2.0], MIXED_2D, 2, 2, 0),                  # 8-row slabs (the minimum: 2K rows), one chunk serves both faces
+    ([513, 40], [513.0, 40.0], MIXED_2D, 2, 3, 0),              # two strips; uneven split (13, 13, 14); the middle rank has both neighbours
+    ([130, 64], [13.0, 6.4], NEUMANN_2D, 3, 4, 5),              # 16-row slabs in chunks of 5 (the last chunk is lengthened to hold 4 rows)
+    ([1031, 24], [1.0, 1.0], MIXED_2D, 1, 2, 4),                # odd n0: x-hi ghosts of the travelling rows; chunks of exactly K rows
+    ([64, 90], [1.0, 1.0], MIXED_2D, 2, 2, 16),                 # several chunks per slab: steady iterations between the rows that travel
+])
+def test_slab_handshake_of_the_2d_multi_sweep_on_the_emulator(emu, n, hi, spec, launches, nranks, chunk):
+    """y-slabs, four sweeps per launch: K boundary rows travel per neighbour and launch (ghost + 3 deep rows), lower levels are
+    not clipped at a face that has a neighbour behind it."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, DEPTH * launches, seed=47)
+    out = psi.copy()
+    rc = emu.emu_sweeps_slabs(2, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, launches, nranks)
+    assert rc == 0, "deadlock / handshake timeout / stores outside the frame"
     np.testing.assert_array_equal(out, want)
 
 
