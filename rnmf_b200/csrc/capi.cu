@@ -626,10 +626,24 @@ extern "C" int32_t rnmf_frame_download(rnmf_frame* f, double* host)
     if (bind(f->ctx)) return RNMF_ERR_CUDA;
     const FrameGeom& g = f->g;
     const size_t rows = (size_t)(g.G[1] * g.G[2] * g.ncomp);
-    RNMF_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)g.G[0] * 8, f->d + g.xoff, (size_t)g.pitch * 8, (size_t)g.G[0] * 8, rows,
-                                    cudaMemcpyDeviceToHost, f->ctx->stream));
-    RNMF_CUDA_TRY(cudaStreamSynchronize(f->ctx->stream));
-    return check_peer_status(f->ctx);
+    rnmf_ctx* c = f->ctx;
+    const long long dense = g.G[0] * (long long)rows;
+    if (dense * 8 >= (64LL << 20)) {
+        // Large frames, the mirror image of the upload: pack on the device (HBM speed) and send the dense frame home with ONE
+        // 1-D copy (~55 GB/s here; the pitched 2-D copy reaches ~37: scripts/h2d_probe.py)
+        if (c->staging_cap < dense) {
+            if (c->d_staging) { RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream)); RNMF_CUDA_TRY(cudaFree(c->d_staging)); c->d_staging = nullptr; c->staging_cap = 0; }
+            RNMF_CUDA_TRY(cudaMalloc(&c->d_staging, (size_t)dense * 8));
+            c->staging_cap = dense;
+        }
+        RNMF_LAUNCH(c, launch_pack_dense_rows(g, f->d, c->d_staging, 0, (long long)rows, c->stream));
+        RNMF_CUDA_TRY(cudaMemcpyAsync(host, c->d_staging, (size_t)dense * 8, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        RNMF_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)g.G[0] * 8, f->d + g.xoff, (size_t)g.pitch * 8, (size_t)g.G[0] * 8, rows,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    }
+    RNMF_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_peer_status(c);
 }
 
 static int copy_valid(rnmf_frame* f, double* host, bool to_host)
