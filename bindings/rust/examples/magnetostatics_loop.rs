@@ -6,8 +6,10 @@ use rnmf_b200::{gs_sweeps, poisson_coefs, poisson_source_2d, BCs, BcType, Compon
 fn main() {
     let (n, length) = ([301i64, 301], [301.0f64, 301.0]);
     let dx = [length[0] / n[0] as f64, length[1] / n[1] as f64];
-    let (h_far, relax, n_iter, n_sub_iter, tol) = ([0.0, 1.0], 1.8, 10usize, 550usize, 0.1);
-    let mu = MuParams { bubble_centre: [150.5, 150.5], bubble_radius: 15.0, mu: [2.0, 1.0] };
+    // examples/magnetostatics/magnetostatics.lua:7-16: H_far (0, 1), bubble_centre 301/2, bubble_radius 301/20, mu (3.2, 1.0),
+    // relax 0.2, n_iter 10, n_sub_iter 550, tol 0.1
+    let (h_far, relax, n_iter, n_sub_iter, tol) = ([0.0, 1.0], 0.2, 10usize, 550usize, 0.1);
+    let mu = MuParams { bubble_centre: [301.0 / 2.0, 301.0 / 2.0], bubble_radius: 301.0 / 20.0, mu: [3.2, 1.0] };
     let (gx, gy) = (-h_far[0] / dx[0], -h_far[1] / dx[1]);
     let bc = BCs { bcs: vec![ComponentBCs { lo: vec![BcType::Neumann(gx), BcType::Neumann(gy)], hi: vec![BcType::Neumann(gx), BcType::Neumann(gy)] }] };
 

@@ -225,6 +225,8 @@ impl<'c> DeviceFrame<'c> {
     pub fn upload(&mut self, data: &[Real]) {
         assert_eq!(data.len(), self.n_nodes());
         ffi::check(unsafe { ffi::rnmf_frame_upload(self.raw, data.as_ptr()) }, "rnmf_frame_upload");
+        // rnmf_frame_upload is asynchronous (rnmf_b200.h): the borrow of `data` ends with this call, so wait for the copy
+        self.ctx.sync();
     }
     pub fn download(&self, data: &mut [Real]) {
         assert_eq!(data.len(), self.n_nodes());
@@ -240,6 +242,7 @@ impl<'c> DeviceFrame<'c> {
     pub fn upload_valid(&mut self, valid: &[Real]) {
         assert_eq!(valid.len(), self.n_valid());
         ffi::check(unsafe { ffi::rnmf_frame_upload_valid(self.raw, valid.as_ptr()) }, "rnmf_frame_upload_valid");
+        self.ctx.sync();
     }
     /// Index<(isize, isize, usize)> (dataframe.rs:208-219); k = 0 in 2D
     pub fn get(&self, i: isize, j: isize, k: isize, comp: usize) -> Real {
