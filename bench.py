@@ -507,12 +507,14 @@ def run_e2e_dist(R, ctx, workload, nranks, sub_iters, steps, barrier, reduce_max
         arrs[1].reshape(-1, row)[:] = blk[::-1]
         coef = poisson.poisson_coefs(dim, mesh.dx)
 
+        coef4 = (C.c_double * 4)(*coef)
+        l1c = C.c_double()
+
         def call():
-            _capi.check(L.rnmf_frame_upload(psi._h, bufs[0]))
-            _capi.check(L.rnmf_frame_upload(rhs._h, bufs[1]))
-            l1 = poisson.jacobi_sweeps(psi, rhs, sub_iters, want_norm=True, coef=coef)
-            _capi.check(L.rnmf_frame_download(psi._h, bufs[2]))
-            return l1
+            # the per-rank end-to-end call on slab frames: upload (chunked, overlapped with the first double sweeps; the wedges
+            # next to the neighbours catch up once every rank's frames are up), halo-coupled sweeps, norm, download
+            _capi.check(L.rnmf_jacobi_sweeps_host(psi._h, rhs._h, bufs[0], bufs[1], coef4, sub_iters, bufs[2], C.byref(l1c)))
+            return l1c.value
         call()
         barrier()
         t0 = time.perf_counter()
@@ -527,8 +529,10 @@ def run_e2e_dist(R, ctx, workload, nranks, sub_iters, steps, barrier, reduce_max
         return {"value": cells * sub_iters * steps / secs / 1e9, "unit": "GLUP/s",
                 "h2d_bytes_per_step": int(reduce_sum(2.0 * nbytes)), "d2h_bytes_per_step": int(reduce_sum(nbytes + 8.0)),
                 "ms_per_step": 1e3 * secs / steps, "steps": steps,
-                "call": "per rank: rnmf_frame_upload(psi slab), rnmf_frame_upload(rhs slab) from pinned host frames (dense reference "
-                        f"layout) -> {sub_iters} halo-coupled sweeps(+fill_bc) + all-reduced L1 norm -> rnmf_frame_download(psi slab)"}
+                "h2d_gbs_per_rank": 2.0 * nbytes / 1e9 / (secs / steps), "d2h_gbs_per_rank": nbytes / 1e9 / (secs / steps),
+                "call": "per rank: rnmf_jacobi_sweeps_host(psi slab, rhs slab): pinned host slabs (dense reference layout) -> chunked H2D "
+                        f"overlapped with the first double sweeps -> {sub_iters} halo-coupled sweeps(+fill_bc) + all-reduced L1 norm -> D2H psi slab",
+                "note": "h2d/d2h_gbs_per_rank = bytes / WHOLE call time (a lower bound of the copy rates: the copies overlap the sweeps)"}
     finally:
         for p in bufs:
             L.rnmf_host_free(p)

@@ -115,6 +115,7 @@ extern "C" {
     pub fn rnmf_frame_peer_export(f: *mut rnmf_frame, handles192: *mut c_void) -> i32;
     pub fn rnmf_frame_peer_attach(f: *mut rnmf_frame, lo_handles192: *const c_void, hi_handles192: *const c_void) -> i32;
     pub fn rnmf_gradient_h_2d(psi: *const rnmf_frame, h2: *mut rnmf_frame) -> i32;
+    pub fn rnmf_jacobi_sweeps_host(psi: *mut rnmf_frame, rhs: *mut rnmf_frame, psi_in_dense: *const f64, rhs_in_dense: *const f64, coef: *const f64, n_sweeps: i64, psi_out_dense: *mut f64, l1_update: *mut f64) -> i32;
     pub fn rnmf_solve_poisson_host(ctx: *mut rnmf_ctx, dim: i32, n: *const i64, lo: *const f64, dx: *const f64, n_ghost: i32, faces: *const rnmf_bc_face, psi_init_dense: *const f64, rhs_dense: *const f64, n_sub_iter: i64, mode: i32, psi_out_dense: *mut f64, l1_update: *mut f64) -> i32;
     pub fn rnmf_host_alloc(bytes: i64, out: *mut *mut c_void) -> i32;
     pub fn rnmf_host_free(p: *mut c_void) -> i32;

@@ -112,23 +112,22 @@ int64_t rnmf_kernel_launches(rnmf_ctx* ctx);
 /* how many of those were double-sweep kernels (two Jacobi sweeps + ghost fills per pass over HBM, 2D and 3D;
  * rnmf_jacobi_sweeps pairs up every two sweeps that do not carry the norm) -- bench.py's roofline accounting */
 int64_t rnmf_double_sweep_launches(rnmf_ctx* ctx);
-/* all temporally blocked launches (two or more sweeps per pass over HBM: the double-sweep kernels and the opt-in K-sweep 2D
+/* all temporally blocked launches (two or more sweeps per pass over HBM: the double-sweep kernels and the four-sweep 2D
  * kernel) and the number of sweeps they covered, since the context was created; either pointer may be null */
 int32_t rnmf_multi_sweep_stats(rnmf_ctx* ctx, int64_t* launches, int64_t* sweeps);
 /* CUDA-event timer on the context's stream: begin records, end records+synchronises. */
 int32_t rnmf_timer_begin(rnmf_ctx* ctx);
 int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);
 /* tuning knobs for measurements (results never change, only which kernel / schedule produces them):
- *   "sweep_variant"  "auto" (default) or a number: 3D 1-4,10,11 = non-TMA kernels, 6 = single-sweep TMA kernel only,
- *                    20/21 = double sweep 128x12 / 128x8, 24/25 = two rows per warp, 26/27 = interior-specialised loops
- *                    (24-28 opt-in); 2D 1,2 = non-TMA, 20 = single-sweep TMA only, 30 = double sweep, 32-40 = three ..
- *                    six sweeps per pass (opt-in)
+ *   "sweep_variant"  "auto" (default) or a number from the one table in csrc/kernels_sweep.cu: 3D 6 = one sweep per launch only;
+ *                    2D 30 = two sweeps per launch (+ single sweeps), 20 = one sweep per launch only
  *   "sweep_chunk"    planes / rows marched per CTA (0 = planner)
  *   "resident"       1/0: one cooperative launch for all sweeps of an L2-resident frame
  *   "peer_halo", "peer_inkernel", "halo_overlap"   slab halo exchange: fused peer-memory path / in-kernel handshake / NCCL overlap
- *   "e2e_skew" (+ "e2e_skew_chunks", "e2e_skew_pairs", "e2e_skew_tail")  opt-in: 1 = rnmf_solve_poisson_host uploads in
- *                    chunks of z-planes and overlaps the upload with the first double sweeps; 2 = also runs the last
- *                    launches band-wise so that the download overlaps them */
+ *   "e2e_skew" (+ "e2e_skew_chunks", "e2e_skew_pairs", "e2e_skew_tail")  the host-frame entry points (rnmf_jacobi_sweeps_host,
+ *                    rnmf_solve_poisson_host): 2 (default) = upload in chunks of z-planes overlapped with the first double
+ *                    sweeps (also across slabs) and, on a single GPU, the last launches band-wise so that the download overlaps
+ *                    them; 1 = the overlapped upload only; 0 = plain upload / sweeps / download */
 int32_t rnmf_set_option(rnmf_ctx* ctx, const char* key, const char* value);
 
 /* Domain::new_rectangular split rule (cartesian2d/mod.rs:64-73,109-116), 1-D along one axis.
@@ -250,6 +249,13 @@ int32_t rnmf_solve_poisson_host(rnmf_ctx* ctx, int32_t dim, const int64_t* n, co
                                 const double* psi_init_dense, const double* rhs_dense,
                                 int64_t n_sub_iter, int32_t mode, double* psi_out_dense,
                                 double* l1_update);
+/* The same on EXISTING device frames, single-GPU or slab (solve_poisson with the caller's own frames; the per-rank call of a
+ * slab-decomposed job): psi_in / rhs_in / psi_out are THIS rank's frames in the dense grown layout (n + 2*n_ghost cells per
+ * direction, cartesian2d/mod.rs:31-37); psi and rhs receive the uploads, psi ends as the result.  Equivalent, bit for bit,
+ * to rnmf_frame_upload x 2 + rnmf_jacobi_sweeps + rnmf_frame_download; with option "e2e_skew" the copies overlap the sweeps.
+ * Collective over the ranks of a slab frame.  Synchronises.  l1_update nullable. */
+int32_t rnmf_jacobi_sweeps_host(rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in_dense, const double* rhs_in_dense,
+                                const double* coef, int64_t n_sweeps, double* psi_out_dense, double* l1_update);
 /* pinned host allocation for the host-buffer entry points (optional; pageable works, slower) */
 int32_t rnmf_host_alloc(int64_t bytes, void** out);
 int32_t rnmf_host_free(void* p);

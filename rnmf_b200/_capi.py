@@ -96,6 +96,7 @@ SIGNATURES = {
     "rnmf_gradient_h_2d": (C.c_int32, [_vp, _vp]),
     "rnmf_solve_poisson_host": (C.c_int32, [_vp, C.c_int32, _i64p, _dp, _dp, C.c_int32, _P(BcFace), _vp, _vp,
                                             C.c_int64, C.c_int32, _vp, _dp]),
+    "rnmf_jacobi_sweeps_host": (C.c_int32, [_vp, _vp, _vp, _vp, _dp, C.c_int64, _vp, _dp]),
     "rnmf_host_alloc": (C.c_int32, [C.c_int64, _P(_vp)]),
     "rnmf_host_free": (C.c_int32, [_vp]),
 }

@@ -909,6 +909,36 @@ static bool has_prescribed(const rnmf_frame* f)
     return false;
 }
 
+// A temporally blocked launch across slabs: u_depth of my `depth` slices next to each neighbour goes into the ghost + deep
+// slices of ITS buffer with physical id `out_phys` (0 = the buffer the frame was created with), under the same
+// one-epoch-per-launch handshake as a single sweep.  boundary_ctas = CTAs per side that take part in the handshake.
+static void setup_slab_launch(rnmf_frame* psi, int out_phys, int boundary_ctas, SweepArgs& t)
+{
+    rnmf_ctx* c = psi->ctx;
+    const FrameGeom& g = psi->g;
+    const int D = slow_dim(g);
+    const long long slice_sz = D == 2 ? g.plane : g.pitch;
+    const bool has_lo = c->rank > 0, has_hi = c->rank < c->nranks - 1;
+    int64_t n_lo_slab = 0;
+    if (has_lo) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank - 1, nullptr, &n_lo_slab);
+    t.nb_lo = has_lo; t.nb_hi = has_hi;
+    t.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + slice_sz * (n_lo_slab + g.ng) : nullptr;    // its hi ghost slice
+    t.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + slice_sz * (g.ng - 1) : nullptr;             // its lo ghost slice
+    t.ps.enabled = 1;
+    t.ps.wait_lo = has_lo ? c->d_flags + 0 : nullptr;
+    t.ps.wait_hi = has_hi ? c->d_flags + 1 : nullptr;
+    t.ps.sig_lo = has_lo ? c->peer_flag_lo : nullptr;
+    t.ps.sig_hi = has_hi ? c->peer_flag_hi : nullptr;
+    t.ps.done = c->d_flags + 3;
+    if (has_lo) c->done_target[0] += (unsigned long long)boundary_ctas;
+    if (has_hi) c->done_target[1] += (unsigned long long)boundary_ctas;
+    t.ps.target_lo = c->done_target[0]; t.ps.target_hi = c->done_target[1];
+    t.ps.epoch = c->epoch;
+    t.ps.status = c->d_flags + 2;
+    c->epoch += 1;
+    c->peer_used = 1;
+}
+
 extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, const double* coef, int64_t n_sweeps,
                                       double* l1_update)
 {
@@ -948,6 +978,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     a.partials = nullptr;
     a.deep = deep_slices(g);
     a.nb_lo = a.nb_hi = 0;
+    a.hole_begin = a.hole_end = 0;
     memset(&a.ps, 0, sizeof(a.ps));
     // fused compute + halo exchange over NVLink peer memory: one launch per sweep (or per group of sweeps), the boundary
     // slices are stored into the neighbours' ghost slices by the sweep kernel itself
@@ -974,26 +1005,6 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     const bool tb_peer = depth > 1 && peer && c->peer_inkernel && slab_faces && deep_slices(g) >= depth - 1 && g.nglob[D] / c->nranks >= 2 * depth;
     const bool tb3d = g.dim == 3 && (tb_single || tb_peer);
     const bool tb2d = g.dim == 2 && (tb_single || tb_peer);
-    const long long slice_sz = D == 2 ? g.plane : g.pitch;       // one slice of the slowest direction (z-plane / y-row)
-    // a temporally blocked launch across slabs: u_depth of my `depth` slices next to each neighbour goes into the ghost + deep
-    // slices of ITS `out` buffer, under the same one-epoch-per-launch handshake as a single sweep
-    auto slab_launch_args = [&](SweepArgs& t, int boundary_ctas) {
-        const int out_phys = psi->parity ^ 1;
-        t.nb_lo = has_lo; t.nb_hi = has_hi;
-        t.peer_lo_plane = has_lo ? psi->peer_lo[out_phys] + slice_sz * (n_lo_slab + g.ng) : nullptr;    // its hi ghost slice
-        t.peer_hi_plane = has_hi ? psi->peer_hi[out_phys] + slice_sz * (g.ng - 1) : nullptr;             // its lo ghost slice
-        t.ps.enabled = 1;
-        t.ps.wait_lo = my_flag_lo; t.ps.wait_hi = my_flag_hi;
-        t.ps.sig_lo = has_lo ? c->peer_flag_lo : nullptr;
-        t.ps.sig_hi = has_hi ? c->peer_flag_hi : nullptr;
-        t.ps.done = c->d_flags + 3;
-        if (has_lo) c->done_target[0] += (unsigned long long)boundary_ctas;
-        if (has_hi) c->done_target[1] += (unsigned long long)boundary_ctas;
-        t.ps.target_lo = c->done_target[0]; t.ps.target_hi = c->done_target[1];
-        t.ps.epoch = c->epoch;
-        t.ps.status = c->d_flags + 2;
-        c->epoch += 1;
-    };
     const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
 
     if (dist) {
@@ -1025,7 +1036,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
             t.k_begin = 0; t.k_end = m;
-            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; slab_launch_args(t, multi_sweep_2d_boundary_ctas(t)); }
+            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; setup_slab_launch(psi, psi->parity ^ 1, multi_sweep_2d_boundary_ctas(t), t); }
             RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, s));
             c->multi_sweeps += 1;
             c->multi_sweep_sweeps += depth;
@@ -1051,7 +1062,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             SweepArgs t = a;
             t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
             t.k_begin = 0; t.k_end = m;
-            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; slab_launch_args(t, double_sweep_boundary_ctas(t)); }
+            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; setup_slab_launch(psi, psi->parity ^ 1, double_sweep_boundary_ctas(t), t); }
             RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
             c->double_sweeps += 1;
             double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
@@ -1406,11 +1417,15 @@ extern "C" int32_t rnmf_gradient_h_2d(const rnmf_frame* psi, rnmf_frame* h)
 static bool skew_applicable(const rnmf_ctx* c, const rnmf_frame* psi)
 {
     const FrameGeom& g = psi->g;
-    bool all_faces = psi->bc_set && !psi->has_reflect;
-    for (int fi = 0; fi < 6 && all_faces; ++fi) all_faces = psi->faces[0].f[fi].mode != 0;
+    const bool dist = psi->distributed && c->nranks > 1;
+    const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
+    bool faces = psi->bc_set && !psi->has_reflect;
+    for (int fi = 0; fi < 6 && faces; ++fi) faces = psi->faces[0].f[fi].mode != 0 || (fi == 4 && has_lo) || (fi == 5 && has_hi);
     const int C = c->e2e_skew_chunks;
     const SweepVariantInfo* vi = sweep_variant_info(3, c->sweep_variant);
-    return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && c->nranks == 1 && all_faces && C >= 2 && g.n[2] / C >= 16 &&
+    // slabs: only through the fused deep-halo path (every rank takes the same decision: the options are per job)
+    const bool slab_ok = !dist || (psi->peer_attached && c->peer_halo && c->peer_inkernel);
+    return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && (c->nranks == 1 || dist) && slab_ok && faces && C >= 2 && g.n[2] / C >= 16 &&
            g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && vi && vi->depth == 2;
 }
 
@@ -1423,6 +1438,14 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
     const long long n2 = g.n[2];
     const long long dense = g.G[0] * g.G[1] * g.G[2];
     int64_t pairs = c->e2e_skew_pairs < pairable / 2 ? c->e2e_skew_pairs : pairable / 2;
+    // Slabs: while the frames are still arriving a rank cannot exchange halos (the neighbour's boundary planes come with ITS
+    // last / first chunk), so double sweep s leaves a wedge of 2s planes next to each neighbour untouched (it needs no halo:
+    // level s on planes >= 2s reads level s-1 on planes >= 2s-2).  Once everything is up the wedges catch up, level by level,
+    // each level ONE launch over both wedges with the usual slab handshake (the catch-up costs about S^2/n2 of a sweep per
+    // level, S = pairs).  Wedges of both sides must not meet: 4S <= the thinnest slab (the same on every rank).
+    const bool dist = psi->distributed && c->nranks > 1;
+    const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
+    if (dist && pairs > g.nglob[2] / c->nranks / 4) pairs = g.nglob[2] / c->nranks / 4;
     if (!skew_applicable(c, psi) || pairs < 4) return 0;
     cudaStream_t s = c->stream, cs = c->stream_halo;
 #define SKEW_TRY(expr) do { int _rc = (expr); if (_rc) { *rc_out = _rc; return 0; } } while (0)
@@ -1469,11 +1492,32 @@ static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf
         for (int64_t sp = 1; sp <= pairs; ++sp) {
             long long lo, hi;
             skew_region(n2, C, ch, sp, &lo, &hi);
+            if (has_lo && lo < 2 * sp) lo = 2 * sp;                 // the wedges next to the neighbours wait for the catch-up below
+            if (has_hi && hi > n2 - 2 * sp) hi = n2 - 2 * sp;
             if (hi <= lo) continue;
             t.in = buf[(sp - 1) & 1];
             t.out = buf[sp & 1];
             t.k_begin = lo; t.k_end = hi;
             int k = launch_jacobi_double_sweep(t, s);
+            if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; }
+            c->launches += k;
+            c->skew_launches += k;
+        }
+    }
+    if (dist) {
+        // every plane of every rank has arrived: level-0 halos (ghost + deep plane; rhs: ghost plane), then the wedges
+        SKEW_TRY(halo_exchange_on(psi, buf[0], s, 1));
+        SKEW_TRY(halo_exchange_on(rhs, rhs->d, s, 0));
+        for (int64_t sp = 1; sp <= pairs; ++sp) {
+            SweepArgs w = t;
+            w.in = buf[(sp - 1) & 1];
+            w.out = buf[sp & 1];
+            w.k_begin = 0; w.k_end = n2;
+            w.hole_begin = has_lo ? 2 * sp : 0;
+            w.hole_end = has_hi ? n2 - 2 * sp : n2;
+            w.nb_lo = has_lo; w.nb_hi = has_hi;
+            setup_slab_launch(psi, psi->parity ^ (int)(sp & 1), double_sweep_boundary_ctas(w), w);
+            int k = launch_jacobi_double_sweep(w, s);
             if (k < 0) { *rc_out = RNMF_ERR_CUDA; return 0; }
             c->launches += k;
             c->skew_launches += k;
@@ -1576,6 +1620,46 @@ static int skewed_last_sweeps_and_download(rnmf_ctx* c, rnmf_frame* psi, rnmf_fr
     return RNMF_OK;
 }
 
+// Host frames in, `n_sweeps` Jacobi sweeps (+ fill_bc each), host frame out, on EXISTING device frames (single-GPU or slab):
+// psi_in / rhs_in / psi_out are this rank's frames in the reference's dense grown layout (cartesian2d/mod.rs:31-37).
+// With option e2e_skew (default) the upload is chunked and overlapped with the first double sweeps -- also across slabs --
+// and, on a single GPU, the download with the last ones.  Bit-identical to upload + rnmf_jacobi_sweeps + download.
+extern "C" int32_t rnmf_jacobi_sweeps_host(rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,
+                                           const double* coef, int64_t n_sweeps, double* psi_out, double* l1_update)
+{
+    int rc = check_sweep_args(psi, rhs, coef, n_sweeps);
+    if (rc) return rc;
+    RNMF_REQUIRE(psi_in && rhs_in && psi_out, "null host frame");
+    RNMF_REQUIRE(psi != rhs, "psi and rhs must be different frames");
+    rnmf_ctx* c = psi->ctx;
+    if (bind(c)) return RNMF_ERR_CUDA;
+    int64_t done = 0;
+    if (c->e2e_skew) {
+        done = skewed_upload_and_first_sweeps(c, psi, rhs, psi_in, rhs_in, coef, n_sweeps - (l1_update ? 1 : 0), &rc);
+        if (rc) return rc;
+    }
+    if (done == 0) {
+        rc = rnmf_frame_upload(psi, psi_in);
+        if (rc) return rc;
+        rc = rnmf_frame_upload(rhs, rhs_in);
+        if (rc) return rc;
+    }
+    // band-wise end of the call (single GPU): `levels` launches = 2*levels sweeps, one fewer when the last launch is the single
+    // norm-carrying sweep
+    const int64_t rest = n_sweeps - done;
+    int64_t levels = c->e2e_skew_tail;
+    const bool last_single = l1_update != nullptr;
+    while (levels >= 4 && 2 * levels - (last_single ? 1 : 0) > rest) --levels;
+    if (c->e2e_skew >= 2 && levels >= 4 && c->nranks == 1 && skew_applicable(c, psi)) {
+        rc = rnmf_jacobi_sweeps(psi, rhs, coef, rest - (2 * levels - (last_single ? 1 : 0)), nullptr);
+        if (rc) return rc;
+        return skewed_last_sweeps_and_download(c, psi, rhs, coef, levels, last_single, psi_out, l1_update);
+    }
+    rc = rnmf_jacobi_sweeps(psi, rhs, coef, rest, l1_update);
+    if (rc) return rc;
+    return rnmf_frame_download(psi, psi_out);
+}
+
 extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64_t* n, const double* lo, const double* dx,
                                            int32_t ng, const rnmf_bc_face* faces, const double* psi_in, const double* rhs_in,
                                            int64_t n_sub_iter, int32_t mode, double* psi_out, double* l1_update)
@@ -1601,33 +1685,13 @@ extern "C" int32_t rnmf_solve_poisson_host(rnmf_ctx* c, int32_t dim, const int64
     if (rc) return rc;
     double coef[4];
     rnmf_poisson_coefs(dim, dx, coef);
-    int64_t done = 0;
-    if (mode == 0 && c->e2e_skew) {
-        if (bind(c)) return RNMF_ERR_CUDA;
-        done = skewed_upload_and_first_sweeps(c, c->hp_psi, c->hp_rhs, psi_in, rhs_in, coef, n_sub_iter - (l1_update ? 1 : 0), &rc);
-        if (rc) return rc;
-    }
-    if (done == 0) {
-        rc = rnmf_frame_upload(c->hp_psi, psi_in);
-        if (rc) return rc;
-        rc = rnmf_frame_upload(c->hp_rhs, rhs_in);
-        if (rc) return rc;
-    }
-    if (mode == 0) {
-        // band-wise end of the call: `levels` launches = 2*levels sweeps, one fewer when the last launch is the single
-        // norm-carrying sweep
-        const int64_t rest = n_sub_iter - done;
-        int64_t levels = c->e2e_skew_tail;
-        const bool last_single = l1_update != nullptr;
-        while (levels >= 4 && 2 * levels - (last_single ? 1 : 0) > rest) --levels;
-        if (c->e2e_skew >= 2 && levels >= 4 && skew_applicable(c, c->hp_psi)) {
-            if (bind(c)) return RNMF_ERR_CUDA;
-            rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, rest - (2 * levels - (last_single ? 1 : 0)), nullptr);
-            if (rc) return rc;
-            return skewed_last_sweeps_and_download(c, c->hp_psi, c->hp_rhs, coef, levels, last_single, psi_out, l1_update);
-        }
-        rc = rnmf_jacobi_sweeps(c->hp_psi, c->hp_rhs, coef, rest, l1_update);
-    } else { rc = rnmf_gs_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter); if (l1_update) *l1_update = 0.0; }
+    if (mode == 0) return rnmf_jacobi_sweeps_host(c->hp_psi, c->hp_rhs, psi_in, rhs_in, coef, n_sub_iter, psi_out, l1_update);
+    rc = rnmf_frame_upload(c->hp_psi, psi_in);
+    if (rc) return rc;
+    rc = rnmf_frame_upload(c->hp_rhs, rhs_in);
+    if (rc) return rc;
+    rc = rnmf_gs_sweeps(c->hp_psi, c->hp_rhs, coef, n_sub_iter);
+    if (l1_update) *l1_update = 0.0;
     if (rc) return rc;
     return rnmf_frame_download(c->hp_psi, psi_out);
 }

@@ -264,6 +264,9 @@ struct SweepArgs {
     // neighbour sits behind that face and its depth boundary slices are in my ghost + deep slices when the launch starts
     int deep;
     int nb_lo, nb_hi;
+    // 3D double sweep only: the launch covers [k_begin, hole_begin) and [hole_end, k_end) (hole_end > hole_begin; 0, 0 = no hole):
+    // the two boundary wedges of a slab in ONE launch, so that both neighbours see the usual one-epoch handshake
+    long long hole_begin, hole_end;
 };
 bool sweep_supports_peer_halo(const SweepArgs& a);
 

@@ -64,6 +64,7 @@ struct Tb2Params {
     SweepCoef c;
     FaceSet faces;
     long long m_begin, m_end;    // output planes
+    long long hole_begin, hole_end;   // planes [hole_begin, hole_end) are left out (hole_end == hole_begin: none); no chunk straddles it
     int chunk;
     int n_chunks;
     int nb_lo, nb_hi;            // a slab neighbour behind the z-lo / z-hi face (deep halo planes hold its data)
@@ -379,8 +380,10 @@ __global__ void __launch_bounds__(32 * (TY + 4), 1) jacobi3d_tb2_kernel(const __
 
     // ---- which planes ----------------------------------------------------------------------------------
     const unsigned zc = p.ps.enabled ? peer_chunk_order(blockIdx.z, (unsigned)p.n_chunks) : blockIdx.z;
-    const long long k0 = p.m_begin + (long long)zc * p.chunk;
-    const long long k1 = k0 + p.chunk < p.m_end ? k0 + p.chunk : p.m_end;
+    long long k0 = p.m_begin + (long long)zc * p.chunk;
+    if (k0 >= p.hole_begin) k0 += p.hole_end - p.hole_begin;             // chunks are laid out over the range without the hole
+    const long long part_end = k0 < p.hole_begin ? p.hole_begin : p.m_end;
+    const long long k1 = k0 + p.chunk < part_end ? k0 + p.chunk : part_end;
     // level-1 planes a..b: one beyond the output planes on either side, unless a PHYSICAL z face is there (its ghost rule
     // gives u1 on the ghost-plane position); towards a slab neighbour the deep halo plane makes plane -1 / n2 computable
     const long long a = (k0 > 0 || p.nb_lo) ? k0 - 1 : 0;
@@ -583,8 +586,18 @@ struct Tb2Launcher {
     static void plan(const SweepArgs& a, dim3& grid, int& chunk, int& n_chunks)
     {
         const FrameGeom& g = a.g;
-        const long long span = a.k_end - a.k_begin;
         const long long tiles = ((g.n[0] + 127) / 128) * ((g.n[1] + TY - 1) / TY);
+        if (a.hole_end > a.hole_begin) {
+            // two parts [k_begin, hole_begin) and [hole_end, k_end): one chunk length for both, no chunk across the hole --
+            // the lower part is one chunk (or absent), the upper part is cut into chunks of the same length
+            const long long lower = a.hole_begin - a.k_begin, upper = a.k_end - a.hole_end;
+            const long long c = lower > 0 ? lower : (upper > 0 ? upper : 1);
+            chunk = (int)c;
+            n_chunks = (int)((lower > 0 ? 1 : 0) + (upper + c - 1) / c);
+            grid = dim3((unsigned)((g.n[0] + 127) / 128), (unsigned)((g.n[1] + TY - 1) / TY), (unsigned)n_chunks);
+            return;
+        }
+        const long long span = a.k_end - a.k_begin;
         long long best_c = 1, best_cost = -1;
         // at most 128 planes: CTAs that march longer drift apart, and the halo rows / columns a CTA shares with its neighbours
         // have left the L2 by the time the neighbour asks for them (768^3, ncu: 8.75 GB of DRAM reads per launch with
@@ -626,6 +639,9 @@ struct Tb2Launcher {
         Tb2Params p;
         p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
         p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk; p.n_chunks = n_chunks;
+        // no hole: hole_begin = hole_end = m_end, so that k0 >= hole_begin never holds
+        p.hole_begin = a.hole_end > a.hole_begin ? a.hole_begin : a.k_end;
+        p.hole_end = a.hole_end > a.hole_begin ? a.hole_end : a.k_end;
         p.nb_lo = a.nb_lo; p.nb_hi = a.nb_hi; p.zshift = deep;
         // the neighbours' ghost planes and the deep planes behind / in front of them
         p.peer_lo_ghost = a.peer_lo_plane; p.peer_hi_ghost = a.peer_hi_plane;
@@ -651,6 +667,8 @@ struct Tb2Launcher {
 int launch_jacobi_double_sweep(const SweepArgs& a, cudaStream_t s)
 {
     if (a.k_end <= a.k_begin) return 0;
+    if (a.hole_end > a.hole_begin && (a.hole_begin < a.k_begin || a.hole_end > a.k_end)) { rnmf_set_error("double sweep: hole outside the plane range"); return -1; }
+    if (a.hole_end > a.hole_begin && a.hole_begin == a.k_begin && a.hole_end == a.k_end) return 0;
     if ((a.nb_lo || a.nb_hi) && a.deep < 1) { rnmf_set_error("double sweep across slabs needs deep halo planes"); return -1; }
     return Tb2Launcher<12, 6>::launch(a, s);
 }

@@ -58,6 +58,60 @@ def reference(n, hi, spec, sweeps, ng=1):
     return ora.valid_view(g, psi)[0].copy(), l1
 
 
+def host_call_check(R, ctx, rank, world):
+    """rnmf_jacobi_sweeps_host on slab frames (the per-rank end-to-end call): host slabs in, sweeps, host slab out.  With the
+    default e2e_skew the upload is chunked and overlapped with band-wise double sweeps, the wedges next to the neighbours catch
+    up afterwards (capi.cu: skewed_upload_and_first_sweeps); e2e_skew = 0 is the plain path.  Both must equal the oracle on the
+    GLOBAL frame bit for bit.  The slab is just over the 64 MB threshold of the overlapped path."""
+    import ctypes as C
+    from oracle import oracle as ora
+    from rnmf_b200 import _capi, poisson
+    n, sweeps = [254, 126, 264 * world], 23
+    hi = [float(v) for v in n]
+    g = ora.geom(n, hi=hi)
+    obc = ora.bcs(3, [MIXED_3D])
+    rng = np.random.default_rng(5)
+    psi0, rhs0 = rng.standard_normal(g.n_nodes), rng.standard_normal(g.n_nodes)
+    want = psi0.copy()
+    l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps, omp=True)
+    mk = {"dirichlet": R.BcType.Dirichlet, "neumann": R.BcType.Neumann}
+    bc = R.BCs([R.ComponentBCs([mk[k](v) for k, v in MIXED_3D[0]], [mk[k](v) for k, v in MIXED_3D[1]])])
+    mesh = R.CartesianMesh.new([0.0] * 3, hi, n)
+    start, count = R.slab_partition(n[2], world, rank)
+    plane = (n[0] + 2) * (n[1] + 2)
+    # this rank's host frames: its slab of the global dense frames, ghost planes included (grown planes start .. start+count+1)
+    sl = slice(plane * start, plane * (start + count + 2))
+    psi_h, rhs_h = np.ascontiguousarray(psi0[sl]), np.ascontiguousarray(rhs0[sl])
+    psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+    rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx, slab=True)
+    psi.enable_peer_halo()
+    coef = (C.c_double * 4)(*poisson.poisson_coefs(3, mesh.dx))
+    ok = True
+    for skew in (2, 0):
+        ctx.set_option("e2e_skew", skew)
+        ctx.set_option("e2e_skew_chunks", 4)
+        ctx.set_option("e2e_skew_pairs", 9)
+        out = np.empty_like(psi_h)
+        l1 = C.c_double()
+        k0 = ctx.kernel_launches
+        _capi.check(_capi.lib().rnmf_jacobi_sweeps_host(psi._h, rhs._h, psi_h.ctypes.data, rhs_h.ctypes.data, coef, sweeps,
+                                                        out.ctypes.data, C.byref(l1)))
+        launches = ctx.kernel_launches - k0
+        p0, p1 = (0 if rank == 0 else 1), (count + 2 if rank == world - 1 else count + 1)      # my valid planes + the outer ghost planes
+        same = np.array_equal(out[plane * p0:plane * p1], want[plane * (start + p0):plane * (start + p1)])
+        norm_ok = abs(l1.value - l1_ref) <= 1e-12 * abs(l1_ref)
+        used = launches > 40 if skew else launches < 40          # the overlapped path issues one launch per (chunk, pair) band
+        if not (same and norm_ok and used):
+            ok = False
+            print(f"[rank {rank}] FAIL host call e2e_skew={skew}: field={same} norm={norm_ok} ({l1.value} vs {l1_ref}) launches={launches}", flush=True)
+    ctx.set_option("e2e_skew", 2)
+    ctx.set_option("e2e_skew_chunks", 8)
+    ctx.set_option("e2e_skew_pairs", 56)
+    psi.close()
+    rhs.close()
+    return ok
+
+
 def run_nccl():
     import torch
     import torch.distributed as dist
@@ -114,6 +168,10 @@ def run_nccl():
             psi.close()
             rhs.close()
     ctx.set_option("sweep_variant", "auto")
+    ctx.set_option("peer_halo", 1)
+    ctx.set_option("peer_inkernel", 1)
+    ctx.set_option("halo_overlap", 1)
+    ok = host_call_check(R, ctx, rank, world) and ok
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     ctx.close()

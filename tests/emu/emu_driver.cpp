@@ -509,4 +509,148 @@ int emu_sweeps_slabs(int dim, const long long* n, const double* dx, const int* f
     return bad;
 }
 
+// The time-skewed start ACROSS SLABS (capi.cu: skewed_upload_and_first_sweeps with neighbours): every rank's slab "arrives" in
+// n_chunks chunks; double sweep s runs on the bands skew_region() makes computable, clipped to [2s, m - 2s) next to a
+// neighbour (no halo needed); then all ranks meet ("entry exchange" of the level-0 halos: ghost + deep plane, rhs ghost plane)
+// and the wedges catch up level by level, each level ONE launch over both wedges (a hole in the plane range) with the slab
+// handshake.  Unarrived planes hold poison.  At the end every plane must hold u_{2*pairs}.
+int emu_skewed_double_sweeps_slabs(const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
+                                   const double* psi_dense, const double* rhs_dense, double* out_dense, int chunk, int n_chunks, int pairs, int nranks)
+{
+    g_deadlocks = 0;
+    const long long G0 = n[0] + 2, plane_dense = G0 * (n[1] + 2);
+    std::vector<Frame> fr(nranks);
+    std::vector<std::vector<double>> full_psi(nranks), full_rhs(nranks);
+    std::vector<long long> start(nranks), count(nranks);
+    struct Flags { unsigned long long w[16]; };
+    std::vector<Flags> flags(nranks);
+    for (auto& fl : flags) memset(&fl, 0, sizeof(fl));
+    for (int r = 0; r < nranks; ++r) {
+        const long long base = n[2] / nranks;
+        start[r] = base * r;
+        count[r] = r == nranks - 1 ? n[2] - start[r] : base;
+        const long long nl[3] = { n[0], n[1], count[r] };
+        Frame& f = fr[r];
+        // the host frame of a rank: its slab with whatever ghost planes the caller has (here: the neighbours' planes, which the
+        // schedule must NOT rely on before the exchange -- they are poisoned below together with everything else)
+        init_frame(f, 3, nl, dx, psi_dense + plane_dense * start[r], rhs_dense + plane_dense * start[r]);
+        full_psi[r].assign(f.d(0), f.d(0) + f.g.total);
+        full_rhs[r].assign(f.rhs(), f.rhs() + f.g.total);
+        std::fill(f.buf[0].begin(), f.buf[0].end(), -3.0e300);
+        std::fill(f.buf[1].begin(), f.buf[1].end(), 4.0e300);
+        std::fill(f.rhs_buf.begin(), f.rhs_buf.end(), 6.0e300);
+    }
+    std::atomic<int> arrived{0};
+    std::vector<std::thread> ranks;
+    for (int r = 0; r < nranks; ++r)
+        ranks.emplace_back([&, r] {
+            Frame& f = fr[r];
+            const FrameGeom& g = f.g;
+            const bool has_lo = r > 0, has_hi = r < nranks - 1;
+            const long long n2 = count[r];
+            int kind[6];
+            for (int i = 0; i < 6; ++i) kind[i] = face_kind[i];
+            if (has_lo) kind[4] = RNMF_BC_HALO;
+            if (has_hi) kind[5] = RNMF_BC_HALO;
+            SweepArgs t;
+            memset(&t, 0, sizeof(t));
+            t.g = g;
+            t.c = SweepCoef{ coef4[0], coef4[1], coef4[2], coef4[3] };
+            t.faces = make_faces(3, kind, face_value, dx);
+            t.fuse_fill = 1;
+            t.chunk_override = chunk;
+            t.rhs = f.rhs();
+            t.deep = 1;
+            // ---- phase 1: chunks arrive, bands run (clipped next to the neighbours) ----
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const long long p0 = ch == 0 ? 0 : n2 * ch / n_chunks + 1, p1 = ch == n_chunks - 1 ? g.G[2] : n2 * (ch + 1) / n_chunks + 1;
+                for (long long rr = g.G[1] * p0; rr < g.G[1] * p1; ++rr) {
+                    const long long jj = rr % g.G[1], kk = rr / g.G[1];
+                    const bool shell_row = jj < 1 || jj >= g.n[1] + 1 || kk < 1 || kk >= n2 + 1;
+                    // a ghost plane towards a neighbour is not data the caller can provide: leave it poisoned until the exchange
+                    if ((kk == 0 && has_lo) || (kk == n2 + 1 && has_hi)) continue;
+                    for (long long i = 0; i < g.G[0]; ++i) {
+                        const long long q = g.xoff + i + g.pitch * rr;
+                        f.d(0)[q] = full_psi[r][q];
+                        f.rhs()[q] = full_rhs[r][q];
+                        if (shell_row || i < 1 || i >= g.n[0] + 1) f.d(1)[q] = full_psi[r][q];
+                    }
+                }
+                for (long long sp = 1; sp <= pairs; ++sp) {
+                    long long lo, hi;
+                    skew_region(n2, n_chunks, ch, sp, &lo, &hi);
+                    if (has_lo && lo < 2 * sp) lo = 2 * sp;
+                    if (has_hi && hi > n2 - 2 * sp) hi = n2 - 2 * sp;
+                    if (hi <= lo) continue;
+                    t.in = f.d((sp - 1) & 1);
+                    t.out = f.d(sp & 1);
+                    t.k_begin = lo; t.k_end = hi;
+                    launch_jacobi_double_sweep(t, nullptr);
+                }
+            }
+            // ---- all ranks have everything: the level-0 halo exchange (ghost + deep plane of psi, ghost plane of rhs) ----
+            ++arrived;
+            while (arrived.load() < nranks) std::this_thread::yield();
+            if (has_lo) {
+                Frame& lo = fr[r - 1];
+                const long long m_lo = count[r - 1];
+                memcpy(f.d(0) - g.plane, lo.d(0) + g.plane * (m_lo - 1), (size_t)(2 * g.plane) * sizeof(double));      // its planes m-2, m-1 -> my deep, ghost
+                memcpy(f.rhs(), lo.rhs() + g.plane * m_lo, (size_t)g.plane * sizeof(double));
+            }
+            if (has_hi) {
+                Frame& hi = fr[r + 1];
+                memcpy(f.d(0) + g.plane * (n2 + 1), hi.d(0) + g.plane, (size_t)(2 * g.plane) * sizeof(double));         // its planes 0, 1 -> my ghost, deep
+                memcpy(f.rhs() + g.plane * (n2 + 1), hi.rhs() + g.plane, (size_t)g.plane * sizeof(double));
+            }
+            ++arrived;
+            while (arrived.load() < 2 * nranks) std::this_thread::yield();
+            // ---- phase 2: the wedges catch up ----
+            unsigned long long epoch = 0, done[2] = { 0, 0 };
+            for (long long sp = 1; sp <= pairs; ++sp) {
+                SweepArgs w = t;
+                w.in = f.d((sp - 1) & 1);
+                w.out = f.d(sp & 1);
+                w.k_begin = 0; w.k_end = n2;
+                w.hole_begin = has_lo ? 2 * sp : 0;
+                w.hole_end = has_hi ? n2 - 2 * sp : n2;
+                w.nb_lo = has_lo; w.nb_hi = has_hi;
+                const int out_phys = (int)(sp & 1);
+                if (has_lo) {
+                    Frame& lo = fr[r - 1];
+                    w.peer_lo_plane = lo.d(out_phys) + g.plane * (count[r - 1] + 1);
+                    w.ps.wait_lo = &flags[r].w[0];
+                    w.ps.sig_lo = &flags[r - 1].w[1];
+                }
+                if (has_hi) {
+                    Frame& hi = fr[r + 1];
+                    w.peer_hi_plane = hi.d(out_phys);
+                    w.ps.wait_hi = &flags[r].w[1];
+                    w.ps.sig_hi = &flags[r + 1].w[0];
+                }
+                const unsigned long long tiles = (unsigned long long)double_sweep_boundary_ctas(w);
+                w.ps.enabled = 1;
+                w.ps.done = &flags[r].w[3];
+                if (has_lo) done[0] += tiles;
+                if (has_hi) done[1] += tiles;
+                w.ps.target_lo = done[0]; w.ps.target_hi = done[1];
+                w.ps.epoch = epoch;
+                w.ps.status = &flags[r].w[2];
+                epoch += 1;
+                launch_jacobi_double_sweep(w, nullptr);
+            }
+            if (has_lo) peer_spin_wait(&flags[r].w[0], epoch, &flags[r].w[2]);
+            if (has_hi) peer_spin_wait(&flags[r].w[1], epoch, &flags[r].w[2]);
+        });
+    for (auto& th : ranks) th.join();
+    int bad = g_deadlocks.load();
+    for (int r = 0; r < nranks; ++r) {
+        if (flags[r].w[2]) ++bad;
+        std::vector<double> dense((size_t)(plane_dense * (count[r] + 2)));
+        pack(fr[r].g, fr[r].d(pairs & 1), dense.data());
+        const long long p0 = r == 0 ? 0 : 1, p1 = r == nranks - 1 ? count[r] + 2 : count[r] + 1;
+        memcpy(out_dense + plane_dense * (start[r] + p0), dense.data() + plane_dense * p0, (size_t)(plane_dense * (p1 - p0)) * sizeof(double));
+    }
+    return bad;
+}
+
 }  // extern "C"

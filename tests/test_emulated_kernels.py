@@ -213,6 +213,24 @@ def test_time_skewed_start_schedule_on_the_emulator(emu, n, spec, n_chunks, pair
     np.testing.assert_array_equal(out, want)
 
 
+@pytest.mark.parametrize("n,spec,n_chunks,pairs,chunk,nranks", [
+    ([20, 9, 64], MIXED_3D, 2, 4, 0, 2),            # 32-plane slabs, 16-plane chunks, wedges of up to 8 planes
+    ([20, 9, 96], NEUMANN_3D, 3, 5, 3, 3),          # the middle rank has both neighbours: two wedges per catch-up launch (hole)
+    ([130, 13, 50], MIXED_3D, 2, 6, 0, 2),          # uneven split (25, 25), 4 * pairs = 24 <= 25: the wedges almost meet
+    ([20, 9, 80], MIXED_3D, 4, 3, 2, 4),            # four ranks, four chunks of five planes each
+])
+def test_time_skewed_start_across_slabs_on_the_emulator(emu, n, spec, n_chunks, pairs, chunk, nranks):
+    """The time-skewed start of rnmf_jacobi_sweeps_host on slab frames: bands clipped to [2s, m - 2s) next to a neighbour while the
+    frames arrive (the neighbours' ghost planes are poison until the exchange), then the wedge catch-up, one launch per level over
+    both wedges with the slab handshake.  Every plane ends as 2*pairs oracle sweeps of the GLOBAL frame, bit for bit."""
+    hi = [1.0, 2.0, 3.0]
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=48)
+    out = psi.copy()
+    rc = emu.emu_skewed_double_sweeps_slabs(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), chunk, n_chunks, pairs, nranks)
+    assert rc == 0, "deadlock / handshake timeout"
+    np.testing.assert_array_equal(out, want)
+
+
 @pytest.mark.parametrize("n,spec,n_chunks,levels,chunk,variant", [
     ([20, 9, 32], MIXED_3D, 2, 5, 0, 0),
     ([20, 9, 24], NEUMANN_3D, 3, 6, 3, 0),         # 8-plane chunks, 2*levels > chunk: the upper bands are clipped at the top
