@@ -74,11 +74,11 @@ def test_roofline_accounting_single_and_double_sweep():
     r2 = b.build_roofline({"ms": 663.694677734375 * 5, "doubles": 1370, "multi_launches": 1370, "multi_sweeps": 2740, "local_cells": cells},
                           5, 550, "3d7_768", 6549.8, "MEASURED_PEAKS.json hbm_gbs")
     assert r2["sweeps_per_launch"] == 2 and r2["frac"] == r["frac"] and r2["traffic"] == r["traffic"]
-    # a K-sweep 2D kernel (opt-in): 480 sweeps per step in launches of four
+    # the four-sweep 2D kernel: 480 sweeps per step in launches of four; its DRAM bytes come from the round-2 capture
     c2 = 8192 ** 2
     r4 = b.build_roofline({"ms": 100.0, "doubles": 0, "multi_launches": 360, "multi_sweeps": 1440, "local_cells": c2}, 3, 480, "2d5_8192", 6549.8, "x")
     assert r4["sweeps_per_launch"] == 4 and r4["algorithmic_bytes_per_launch"] == 4 * 24 * c2 and "multi sweep (4 sweeps" in r4["kernel"]
-    assert abs(r4["avg_launch_ms"] - 4 * 100.0 / 1440) < 1e-12 and r4["traffic"] is None
+    assert abs(r4["avg_launch_ms"] - 4 * 100.0 / 1440) < 1e-12 and r4["traffic"] and "r2_ncu_2d5_8192_tbk" in r4["traffic_source"]
     # both describe the same GLUP/s <-> GB/s relation: achieved / 24 B = updates per second
     assert abs(r["achieved"] / 24 - cells * 550 / (663.694677734375e-3) / 1e9) < 1e-6 * r["achieved"]
 
