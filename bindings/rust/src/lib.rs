@@ -349,6 +349,20 @@ pub fn jacobi_sweeps(psi: &mut DeviceFrame, rhs: &DeviceFrame, coef: &[Real; 4],
     }
 }
 
+/// solve_poisson with HOST frames on existing device frames (single-GPU or slab): this rank's dense grown frames in, n_sweeps
+/// Jacobi sweeps (+ fill_bc each), this rank's dense frame out; the copies overlap the sweeps (option "e2e_skew").  Collective
+/// over the ranks of a slab frame.  Returns the L1 norm of the last update.
+pub fn jacobi_sweeps_host(psi: &mut DeviceFrame, rhs: &mut DeviceFrame, psi_in: &[Real], rhs_in: &[Real], coef: &[Real; 4], n_sweeps: usize,
+                          psi_out: &mut [Real]) -> Real {
+    assert!(psi_in.len() == psi.n_nodes() && rhs_in.len() == psi_in.len() && psi_out.len() == psi_in.len());
+    let mut l1 = 0.0;
+    ffi::check(
+        unsafe { ffi::rnmf_jacobi_sweeps_host(psi.raw, rhs.raw, psi_in.as_ptr(), rhs_in.as_ptr(), coef.as_ptr(), n_sweeps as i64, psi_out.as_mut_ptr(), &mut l1) },
+        "rnmf_jacobi_sweeps_host",
+    );
+    l1
+}
+
 /// Same loop in the reference's exact (lexicographic Gauss-Seidel) order: bit-identical to poisson.rs:80-89. 2D.
 pub fn gs_sweeps(psi: &mut DeviceFrame, rhs: &DeviceFrame, coef: &[Real; 4], n_sweeps: usize) {
     ffi::check(unsafe { ffi::rnmf_gs_sweeps(psi.raw, rhs.raw, coef.as_ptr(), n_sweeps as i64) }, "rnmf_gs_sweeps");

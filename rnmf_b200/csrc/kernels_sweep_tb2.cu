@@ -204,23 +204,36 @@ __device__ __forceinline__ void plane_store(const QuadK& k, double* oa, const do
 // EDGE: 2 = general; 0 = the warp's patch is whole, touches no x / y face, and the iteration meets neither a z face nor a
 // plane that goes to a slab neighbour -- the ghost code and the store masks are compiled out; 1 = as 0, but the patch sits
 // next to an x face: only the x-ghost code stays.
-template <int TY, int NS, bool DO_L1, bool DO_L2, int EDGE = 2>
+// R: it % 6 when it is known at compile time (the steady loop is unrolled by 6 = lcm of the NS = 6 stages, the two u1 slots and
+// the three-plane register windows), -1 otherwise.  With R >= 0 every ring index is a constant, so all shared-memory and barrier
+// addresses are immediate offsets and the stage arithmetic (about a sixth of the loop's instructions) disappears; the barrier
+// parities are st.r.phn (= (it / 6) & 1 throughout a trip, toggled by the caller after it) xor a constant.
+template <int TY, int NS, bool DO_L1, bool DO_L2, int EDGE = 2, int R = -1>
 __device__ __forceinline__ void quad_iter(const Tb2Params& p, const QuadK& k, QuadSt& st, const int it)
 {
     using Cfg = Tb2Cfg<TY, NS>;
+    static_assert(R < 0 || NS == 6, "static ring indices assume six stages");
     constexpr uint32_t RB = Cfg::BX * 8;                                  // one tile row in shared memory
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above_a = zero2, above_b = zero2, u1n_a = zero2, u1n_b = zero2, rc_a = zero2, rc_b = zero2, P_a = zero2, P_b = zero2;
+    // ring position: stage of plane a+it (sc), of plane a+it+1 (sn), parity the wait for sn completes with; u1 slots / parities
+    const uint32_t sc = R >= 0 ? (uint32_t)((R + 1) % 6) : st.r.sc;
+    const uint32_t sn = R >= 0 ? (uint32_t)((R + 2) % 6) : st.r.sn;
+    const uint32_t phn = R >= 0 ? st.r.phn ^ (R >= 4 ? 1u : 0u) : st.r.phn;
+    const uint32_t slot = R >= 0 ? (uint32_t)(R & 1) : (uint32_t)(it & 1);                      // u1 slot of plane a+it
+    const uint32_t pslot = slot ^ 1u;                                                           // ... of plane a+it-1
+    // ((it-1) >> 1) & 1 for it = 6t + R:  R = 0: t+1, 1: t, 2: t, 3: t+1, 4: t+1, 5: t   (mod 2)
+    const uint32_t pu = R >= 0 ? st.r.phn ^ ((R == 0 || R == 3 || R == 4) ? 1u : 0u) : (uint32_t)((it - 1) >> 1) & 1u;
 
     // ---- wait phase --------------------------------------------------------------------------------
-    if (DO_L1) mbar_wait(k.full0 + 8 * st.r.sn, st.r.phn);                // u0 plane a+it+1 (plane a+it was waited for one iteration ago)
+    if (DO_L1) mbar_wait(k.full0 + 8 * sn, phn);                          // u0 plane a+it+1 (plane a+it was waited for one iteration ago)
     // u1 plane a+it-1 complete: level 2 reads it; and every warp has finished reading plane a+it-2,
     // whose slot level 1 overwrites below (reads precede the arrival in program order)
-    if (DO_L2 || it >= 2) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+    if (DO_L2 || it >= 2) mbar_wait(k.u1full0 + 8 * pslot, pu);
 
     // ---- loads ---------------------------------------------------------------------------------------
     if (DO_L2) {
-        const uint32_t up = k.ua + (uint32_t)((it - 1) & 1) * Cfg::U1_SLOT;
+        const uint32_t up = k.ua + pslot * Cfg::U1_SLOT;
         const double2 un_b = lds2(up + 2 * RB);                           // N of row B; N of row A is row B (registers)
         const double2 us_a = lds2(up - RB);                               // S of row A; S of row B is row A
         const double uw_a0 = lds1(up - 8), ue_a1 = lds1(up + 16);
@@ -231,7 +244,7 @@ __device__ __forceinline__ void quad_iter(const Tb2Params& p, const QuadK& k, Qu
         P_b.y = part2(k.c0, k.c1, k.c2, st.rp_b.y, ue_b1, st.u1c_b.x, un_b.y, st.u1c_a.y);
     }
     if (DO_L1) {
-        const uint32_t pn = k.pa + st.r.sn * Cfg::U0_STAGE, pc = k.pa + st.r.sc * Cfg::U0_STAGE, pr = k.ra + st.r.sc * Cfg::RHS_STAGE;
+        const uint32_t pn = k.pa + sn * Cfg::U0_STAGE, pc = k.pa + sc * Cfg::U0_STAGE, pr = k.ra + sc * Cfg::RHS_STAGE;
         above_a = lds2(pn); above_b = lds2(pn + RB);
         const double2 n_b = lds2(pc + 2 * RB);
         const double2 s_a = lds2(pc - RB);
@@ -250,8 +263,8 @@ __device__ __forceinline__ void quad_iter(const Tb2Params& p, const QuadK& k, Qu
         if (EDGE == 2 && k.yhi_row == 0) u1n_b = ghost1(k.fy1, u1n_a);
 
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * st.r.sc);            // this warp is done with the stage of plane a+it
-        const uint32_t us = k.ua + (uint32_t)(it & 1) * Cfg::U1_SLOT;
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);                 // this warp is done with the stage of plane a+it
+        const uint32_t us = k.ua + slot * Cfg::U1_SLOT;
         qsstore(us, RB, u1n_a, u1n_b, EDGE != 2 || k.full, k.va0, k.va1, k.vb0, k.vb1);
         // what fill_bc gives u1 on the physical x / y faces (read by level 2 of the edge cells)
         if (EDGE != 0 && k.any_x) {
@@ -269,7 +282,7 @@ __device__ __forceinline__ void quad_iter(const Tb2Params& p, const QuadK& k, Qu
             if (k.yhi_row == 1) psstore(us + 2 * RB, ghost1(k.fy1, u1n_b), k.full, k.vb0, k.vb1);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
     }
     if (DO_L2) {
         // ---------------- level 2: u2 of plane q = a+it-1 ----------------
@@ -302,21 +315,41 @@ __device__ __forceinline__ void quad_iter(const Tb2Params& p, const QuadK& k, Qu
     if (DO_L1) {
         st.below_a = st.cur_a; st.below_b = st.cur_b;
         st.cur_a = above_a; st.cur_b = above_b;
-        st.r.advance(NS);
+        if (R < 0) st.r.advance(NS);          // static trips leave the ring state alone: after six iterations it is the same, parity aside
     }
     st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
     st.u1c_a = u1n_a; st.u1c_b = u1n_b;
     st.rp_a = rc_a; st.rp_b = rc_b;
 }
 
-// plane iterations [it, end) with both levels, three per trip (the register windows rotate by renaming)
+// plane iterations [it, end) with both levels.  The steady part runs in trips of six iterations that start at it % 6 == 0, where
+// the ring is at (sc, sn) = (1, 2) and st.r.phn == (it / 6) & 1: there every ring index is a compile-time constant (quad_iter's
+// R) and the register windows rotate by renaming.  EDGE == 2 (general code, rare) keeps the run-time ring.
 template <int TY, int NS, int EDGE>
 __device__ __forceinline__ void quad_run(const Tb2Params& p, const QuadK& k, QuadSt& st, int& it, const int end)
 {
-    for (; it + 3 <= end; it += 3) {
-        quad_iter<TY, NS, true, true, EDGE>(p, k, st, it);
-        quad_iter<TY, NS, true, true, EDGE>(p, k, st, it + 1);
-        quad_iter<TY, NS, true, true, EDGE>(p, k, st, it + 2);
+#ifdef RNMF_DYNAMIC_RING          // A/B builds only (scripts/build_alt.sh): the run-time ring everywhere
+    constexpr bool kStatic = false;
+#else
+    constexpr bool kStatic = true;
+#endif
+    if (kStatic && EDGE != 2 && NS == 6) {
+        for (; it < end && it % 6 != 0; ++it) quad_iter<TY, NS, true, true, EDGE>(p, k, st, it);
+        for (; it + 6 <= end; it += 6) {
+            quad_iter<TY, NS, true, true, EDGE, 0>(p, k, st, it);
+            quad_iter<TY, NS, true, true, EDGE, 1>(p, k, st, it + 1);
+            quad_iter<TY, NS, true, true, EDGE, 2>(p, k, st, it + 2);
+            quad_iter<TY, NS, true, true, EDGE, 3>(p, k, st, it + 3);
+            quad_iter<TY, NS, true, true, EDGE, 4>(p, k, st, it + 4);
+            quad_iter<TY, NS, true, true, EDGE, 5>(p, k, st, it + 5);
+            st.r.phn ^= 1u;
+        }
+    } else {
+        for (; it + 3 <= end; it += 3) {
+            quad_iter<TY, NS, true, true, EDGE>(p, k, st, it);
+            quad_iter<TY, NS, true, true, EDGE>(p, k, st, it + 1);
+            quad_iter<TY, NS, true, true, EDGE>(p, k, st, it + 2);
+        }
     }
     for (; it < end; ++it) quad_iter<TY, NS, true, true, EDGE>(p, k, st, it);
 }

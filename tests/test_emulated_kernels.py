@@ -82,6 +82,9 @@ def _setup(n, hi, spec, sweeps, seed):
     ([384, 27, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 3),             # x-hi face exactly at a tile edge; odd n1
     ([192, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 3),             # x-hi face at the edge of an x-half 0 warp
     ([200, 30, 20], [1.0, 2.0, 3.0], MIXED_3D, 1, 7),            # several unrolled trips of the fast loop per chunk
+    # chunks long enough for the six-iteration trips with compile-time ring indices (they start at it % 6 == 0), two launches
+    ([200, 26, 27], [1.0, 2.0, 3.0], MIXED_3D, 2, 0),            # one 27-plane chunk: three static trips, then the drain
+    ([260, 14, 40], [1.0, 2.0, 3.0], NEUMANN_3D, 1, 20),         # two 20-plane chunks: the second starts at a chunk boundary (a = k0 - 1)
 ])
 def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=41)
@@ -167,6 +170,7 @@ def test_3d_double_sweep_random_shapes_on_the_emulator(emu, n0, n1, n2, chunk, n
     ([390, 15, 13], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 2),         # interior-specialised loop between the planes that travel; odd n1
     ([130, 13, 17], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 3),       # a chunk length that leaves a one-plane last chunk (the planner lengthens it)
     ([65, 11, 24], [1.0, 2.0, 3.0], MIXED_3D, 3, 2, 5),          # odd n0: the x-hi ghosts of the travelling planes
+    ([200, 26, 60], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0),         # 30-plane slabs in one chunk: static trips between the planes that travel
 ])
 def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pairs, nranks, chunk):
     """Every rank is a host thread launching its slab's kernel (CTAs one at a time, in order: the most adversarial

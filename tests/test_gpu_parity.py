@@ -766,6 +766,12 @@ def test_error_paths(R, ctx):
     _, bcp = _bc_pair(R, 2, ([("prescribed", [1.0, 2.0]), ("dirichlet", 0.0)], [("dirichlet", 0.0)] * 2))
     fp = R.CartesianDataFrame.new_from(mesh2, bcp, 1, 1, ctx)
     assert code(L.rnmf_gs_sweeps, fp._h, a._h, coef, 1) == _capi.ERR_INVALID
+    # a sweep variant that is not in the table (kernels_sweep.cu) is an error, not a silent default
+    ctx.set_option("sweep_variant", 26)
+    try:
+        assert code(L.rnmf_jacobi_sweeps, a._h, a.clone()._h, coef, 1, None) == _capi.ERR_INVALID
+    finally:
+        ctx.set_option("sweep_variant", "auto")
     # after the errors the context still works
     assert poisson.jacobi_sweeps(a, a.clone(), 2, want_norm=True) >= 0.0
 
