@@ -1425,8 +1425,11 @@ static bool skew_applicable(const rnmf_ctx* c, const rnmf_frame* psi)
     const SweepVariantInfo* vi = sweep_variant_info(3, c->sweep_variant);
     // slabs: only through the fused deep-halo path (every rank takes the same decision: the options are per job)
     const bool slab_ok = !dist || (psi->peer_attached && c->peer_halo && c->peer_inkernel);
-    return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && (c->nranks == 1 || dist) && slab_ok && faces && C >= 2 && g.n[2] / C >= 16 &&
-           g.G[0] * g.G[1] * g.G[2] * 8 >= (64LL << 20) && vi && vi->depth == 2;
+    // every rank of a slab job must take the same decision (the wedge catch-up is collective): size the tests by the thinnest slab
+    // (floor(n/P), cartesian2d/mod.rs:64-73), which is the same number on every rank
+    const long long n2_min = dist ? g.nglob[2] / c->nranks : g.n[2];
+    return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && (c->nranks == 1 || dist) && slab_ok && faces && C >= 2 && n2_min / C >= 16 &&
+           g.G[0] * g.G[1] * (n2_min + 2) * 8 >= (64LL << 20) && vi && vi->depth == 2;
 }
 
 static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,
