@@ -249,8 +249,8 @@ int32_t rnmf_solve_poisson_host(rnmf_ctx* ctx, int32_t dim, const int64_t* n, co
                                 const double* psi_init_dense, const double* rhs_dense,
                                 int64_t n_sub_iter, int32_t mode, double* psi_out_dense,
                                 double* l1_update);
-/* The same on EXISTING device frames, single-GPU or slab (solve_poisson with the caller's own frames; the per-rank call of a
- * slab-decomposed job): psi_in / rhs_in / psi_out are THIS rank's frames in the dense grown layout (n + 2*n_ghost cells per
+/* The same on EXISTING device frames, single-GPU or slab (solve_poisson, poisson.rs:67-92, with the caller's own frames; the
+ * per-rank call of a job decomposed as Domain::new_rectangular does, cartesian2d/mod.rs:58-143): psi_in / rhs_in / psi_out are THIS rank's frames in the dense grown layout (n + 2*n_ghost cells per
  * direction, cartesian2d/mod.rs:31-37); psi and rhs receive the uploads, psi ends as the result.  Equivalent, bit for bit,
  * to rnmf_frame_upload x 2 + rnmf_jacobi_sweeps + rnmf_frame_download; with option "e2e_skew" the copies overlap the sweeps.
  * Collective over the ranks of a slab frame.  Synchronises.  l1_update nullable. */

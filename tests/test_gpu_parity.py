@@ -91,6 +91,11 @@ def test_reflect_is_unimplemented_on_gpu(R, ctx):
     assert e.value.code == -4
 
 
+# Quirk Q1 (declared in oracle/rnmf_oracle.c and DESIGN.md section 2): the reference's fillers loop the TANGENTIAL index over
+# 0..n[i_dim] instead of the other dimension's extent (dataframe.rs:290,308,325,341), which is wrong on non-square meshes.  The
+# oracle and the library fill the INTENDED tangential extent.  On the square / cubic meshes of every BASELINE config and of the
+# reference's own golden vectors the two agree; the non-square shapes below ([7,5], [5,4,3], [33,1,2], ...) therefore pin the
+# intended behaviour, not the reference's bug.
 @pytest.mark.parametrize("n,hi,ng,spec", [
     ([7, 5], [7.0, 10.0], 1, MIXED_2D),
     ([16, 16], [4.0, 4.0], 3, MIXED_2D),
@@ -127,6 +132,7 @@ def test_fill_bc_multicomponent_and_prescribed_3d(R, ctx):
 
 
 # ---- Jacobi sweeps (K1) --------------------------------------------------------------------------
+# (non-square cases: quirk Q1 above applies to the fused ghost fill of the sweeps as well)
 SWEEP_CASES_2D = [
     ([301, 301], [301.0, 301.0], MIXED_2D, 4),
     ([256, 256], [256.0, 256.0], DIRICHLET_2D, 3),
