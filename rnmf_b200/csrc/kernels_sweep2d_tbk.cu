@@ -558,6 +558,10 @@ void plan_tbk(const SweepArgs& a, dim3& grid, int& chunk)
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = cc; }
         if (chunks == span) break;
     }
+    // Measured at 8192^2 (profiles/r2_notes.md section 7): the wave model's pick, 37 chunks of 222 rows = exactly two waves of
+    // 296 CTAs, runs 589 GLUP/s; chunks of 96-128 rows run 679 (48-64: 664-668, 160-256: 635-639, 32: 585) although the model
+    // charges them a fourth wave -- the two CTAs of an SM then ramp up / drain at different times.  Cap the chunk at 128 rows.
+    if (best_c > 128) best_c = 128;
     if (a.chunk_override > 0) best_c = a.chunk_override > span ? span : a.chunk_override;
     if (best_c < 1) best_c = 1;
     // slabs: the first / last chunk holds all K rows that go to the neighbour
