@@ -939,6 +939,163 @@ static void setup_slab_launch(rnmf_frame* psi, int out_phys, int boundary_ctas, 
     c->peer_used = 1;
 }
 
+namespace {
+
+// The decisions of one rnmf_jacobi_sweeps call (the same on every rank of a slab job: they depend on the frame's GLOBAL shape,
+// the options and the table of sweep variants only).
+struct SweepCall {
+    bool dist;            // slab frame on a multi-rank context
+    bool fused;           // the kernels write the face ghosts themselves (ng == 1, no Prescribed side)
+    bool peer;            // halo exchange by peer-memory stores from inside the sweep kernels
+    bool has_lo, has_hi;  // slab neighbours
+    bool tb;              // groups of `depth` sweeps run temporally blocked
+    bool tb_peer;         // ... across slabs (deep halo)
+    bool pairs;           // leftovers of the groups run as pairs (2D, single GPU)
+    int depth;            // sweeps per temporally blocked launch
+    int D;                // slowest direction
+    long long m;          // slices of this rank along D
+};
+
+int plan_sweep_call(const rnmf_frame* psi, const SweepArgs& a, SweepCall* out)
+{
+    const rnmf_ctx* c = psi->ctx;
+    const FrameGeom& g = psi->g;
+    SweepCall p;
+    p.dist = psi->distributed && c->nranks > 1;
+    p.D = slow_dim(g);
+    p.m = g.n[p.D];
+    p.fused = a.fuse_fill != 0;
+    // fused compute + halo exchange over NVLink peer memory: one launch per sweep (or per group of sweeps), the boundary
+    // slices are stored into the neighbours' ghost slices by the sweep kernel itself
+    p.peer = p.dist && psi->peer_attached && c->peer_halo && p.fused && sweep_supports_peer_halo(a);
+    p.has_lo = p.dist && c->rank > 0;
+    p.has_hi = p.dist && c->rank < c->nranks - 1;
+    // Temporal blocking (several sweeps per pass over HBM) for every group of sweeps that does not carry the norm.
+    // A face without a Dirichlet/Neumann rule must be a slab neighbour.
+    const SweepVariantInfo* vi = sweep_variant_info(g.dim, c->sweep_variant);
+    RNMF_REQUIRE(vi, "unknown sweep_variant %d for %dD frames", c->sweep_variant, g.dim);
+    bool all_faces = true, side_faces = true;                       // side faces: those across the marching direction
+    for (int fi = 0; fi < 2 * g.dim; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
+    for (int fi = 0; fi < 2 * (g.dim - 1); ++fi) side_faces = side_faces && a.faces.f[fi].mode != 0;
+    const bool slab_faces = side_faces && (p.has_lo || a.faces.f[2 * p.D].mode != 0) && (p.has_hi || a.faces.f[2 * p.D + 1].mode != 0);
+    p.depth = vi->depth;
+    // slabs: the fused peer path with the in-kernel handshake and the deep halo; the thinnest slab (floor(n/P),
+    // cartesian2d/mod.rs:64-73) has to hold the 2*depth slices that travel
+    // (the 2D pair kernel, kernels_sweep2d_tb2.cu, has no slab form: variant 30 runs single sweeps across slabs)
+    const bool slab_kernel = g.dim == 3 || p.depth > 2;
+    p.tb_peer = p.depth > 1 && slab_kernel && p.peer && c->peer_inkernel && slab_faces && deep_slices(g) >= p.depth - 1 && g.nglob[p.D] / c->nranks >= 2 * p.depth;
+    p.tb = p.tb_peer || (p.depth > 1 && !p.dist && p.fused && all_faces);
+    p.pairs = p.tb && !p.dist && g.dim == 2 && (p.depth == 2 || vi->pairs);
+    *out = p;
+    return RNMF_OK;
+}
+
+void swap_buffers(rnmf_frame* psi)
+{
+    double* t = psi->d; psi->d = psi->d2; psi->d2 = t;
+    psi->parity ^= 1;
+}
+
+// ONE temporally blocked launch of `sweeps` sweeps (3D: 2; 2D: 4, or 2 for the pairs).  Returns RNMF_OK / an error code.
+int launch_blocked_sweeps(rnmf_frame* psi, const SweepArgs& a, const SweepCall& p, int sweeps)
+{
+    rnmf_ctx* c = psi->ctx;
+    SweepArgs t = a;
+    t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
+    t.k_begin = 0; t.k_end = p.m;
+    const bool d3 = a.g.dim == 3;
+    if (p.tb_peer) {
+        t.nb_lo = p.has_lo; t.nb_hi = p.has_hi;
+        setup_slab_launch(psi, psi->parity ^ 1, d3 ? double_sweep_boundary_ctas(t) : multi_sweep_2d_boundary_ctas(t), t);
+    }
+    if (d3) RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, c->stream));                  // kernels_sweep_tb2.cu
+    else if (sweeps > 2) RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, c->stream));   // kernels_sweep2d_tbk.cu
+    else RNMF_LAUNCH(c, launch_jacobi_double_sweep_2d(t, c->stream));                  // kernels_sweep2d_tb2.cu
+    if (sweeps == 2) c->double_sweeps += 1;
+    else { c->multi_sweeps += 1; c->multi_sweep_sweeps += sweeps; }
+    swap_buffers(psi);
+    return RNMF_OK;
+}
+
+// ONE sweep (+ fill_bc, + halo exchange on slabs); want_norm: per-CTA partial sums of |new - old| go to c->d_partials, *n_part of them.
+int launch_single_sweep(rnmf_frame* psi, SweepArgs a, const SweepCall& p, bool want_norm, long long* n_part)
+{
+    rnmf_ctx* c = psi->ctx;
+    const FrameGeom& g = psi->g;
+    cudaStream_t s = c->stream;
+    int rc;
+    a.in = psi->d;
+    a.out = psi->d2;
+    a.partials = nullptr;
+    a.k_begin = 0; a.k_end = p.m;
+    *n_part = 0;
+    auto with_partials = [&](SweepArgs& q, long long offset) -> int {
+        const long long n = sweep_num_partials(q);
+        int r = ensure_partials(c, offset + n);
+        if (r) return r;
+        q.partials = c->d_partials + offset;
+        *n_part = offset + n;
+        return RNMF_OK;
+    };
+    if (p.peer) {
+        unsigned long long* my_flag_lo = p.has_lo ? c->d_flags + 0 : nullptr;
+        unsigned long long* my_flag_hi = p.has_hi ? c->d_flags + 1 : nullptr;
+        if (want_norm) { rc = with_partials(a, 0); if (rc) return rc; }
+        if (c->peer_inkernel) {
+            // handshake inside the sweep kernel: boundary CTAs (scheduled last) wait / publish
+            const int tiles = sweep_boundary_ctas(a);           // (peer pointers and flags do not change the plan)
+            setup_slab_launch(psi, psi->parity ^ 1, tiles, a);
+            a.nb_lo = a.nb_hi = 0;                              // single sweeps need no deep halo
+            RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
+        } else {
+            // the same protocol with 1-thread flag kernels around the sweep (option peer_inkernel = 0)
+            RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
+            int64_t n_lo_slab = 0;
+            if (p.has_lo) rnmf_slab_partition(g.nglob[p.D], c->nranks, c->rank - 1, nullptr, &n_lo_slab);
+            const long long slice = p.D == 2 ? g.plane : g.pitch;
+            const int out_phys = psi->parity ^ 1;
+            a.peer_lo_plane = p.has_lo ? psi->peer_lo[out_phys] + slice * (n_lo_slab + g.ng) : nullptr;
+            a.peer_hi_plane = p.has_hi ? psi->peer_hi[out_phys] + slice * (g.ng - 1) : nullptr;
+            RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
+            RNMF_LAUNCH(c, launch_peer_signal(p.has_lo ? c->peer_flag_lo : nullptr, p.has_hi ? c->peer_flag_hi : nullptr, c->epoch + 1, s));
+            c->epoch += 1;
+            c->peer_used = 1;
+        }
+    } else if (!p.dist || p.m < 3 || !c->overlap_halo || !p.fused) {
+        if (want_norm) { rc = with_partials(a, 0); if (rc) return rc; }
+        RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
+        if (!p.fused) { rc = fill_bc_on(psi, psi->d2, s); if (rc) return rc; }
+        if (p.dist) { rc = halo_exchange_on(psi, psi->d2, s); if (rc) return rc; }
+    } else {
+        // NCCL path: boundary slices first, then exchange them on the halo stream while the interior runs
+        SweepArgs lo = a, hi = a, mid = a;
+        lo.k_begin = 0; lo.k_end = 1;
+        hi.k_begin = p.m - 1; hi.k_end = p.m;
+        mid.k_begin = 1; mid.k_end = p.m - 1;
+        if (want_norm) {
+            rc = with_partials(lo, 0); if (rc) return rc;
+            rc = with_partials(hi, *n_part); if (rc) return rc;
+            rc = with_partials(mid, *n_part); if (rc) return rc;
+            // ensure_partials may have moved the buffer: re-base the earlier segments
+            const long long p_lo = sweep_num_partials(lo), p_hi = sweep_num_partials(hi);
+            lo.partials = c->d_partials; hi.partials = c->d_partials + p_lo; mid.partials = c->d_partials + p_lo + p_hi;
+        }
+        RNMF_LAUNCH(c, launch_jacobi_sweep(lo, s));
+        RNMF_LAUNCH(c, launch_jacobi_sweep(hi, s));
+        RNMF_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
+        RNMF_CUDA_TRY(cudaStreamWaitEvent(c->stream_halo, c->ev_boundary, 0));
+        rc = halo_exchange_on(psi, psi->d2, c->stream_halo);
+        if (rc) return rc;
+        RNMF_CUDA_TRY(cudaEventRecord(c->ev_halo, c->stream_halo));
+        RNMF_LAUNCH(c, launch_jacobi_sweep(mid, s));
+        RNMF_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_halo, 0));
+    }
+    swap_buffers(psi);
+    return RNMF_OK;
+}
+
+}  // namespace
+
 extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, const double* coef, int64_t n_sweeps,
                                       double* l1_update)
 {
@@ -951,6 +1108,20 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     if (l1_update) *l1_update = 0.0;
     if (n_sweeps == 0) return RNMF_OK;
 
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g;
+    a.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
+    a.faces = psi->faces[0];
+    a.fuse_fill = g.ng == 1 && !has_prescribed(psi) ? 1 : 0;
+    a.variant = c->sweep_variant;
+    a.chunk_override = c->sweep_chunk;
+    a.rhs = rhs->d;
+    a.deep = deep_slices(g);
+    SweepCall p;
+    rc = plan_sweep_call(psi, a, &p);
+    if (rc) return rc;
+
     if (!psi->d2) {
         rc = alloc_buffer(g, &psi->d2, s);
         if (rc) return rc;
@@ -959,204 +1130,54 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
     // agree in both buffers: the reference's in-place frame keeps them untouched.
     RNMF_LAUNCH(c, launch_copy_ghost_shell(g, psi->d, psi->d2, s));
 
-    const bool dist = psi->distributed && c->nranks > 1;
-    const int D = slow_dim(g);
-    const long long m = g.n[D];
-    const bool fused = g.ng == 1 && !has_prescribed(psi);
-
-    SweepArgs a;
-    a.g = g;
-    a.c = SweepCoef{ coef[0], coef[1], coef[2], coef[3] };
-    a.faces = psi->faces[0];
-    a.fuse_fill = fused ? 1 : 0;
-    a.variant = c->sweep_variant;
-    a.chunk_override = c->sweep_chunk;
-    a.rhs = rhs->d;
-
-    a.peer_lo_plane = nullptr;
-    a.peer_hi_plane = nullptr;
-    a.partials = nullptr;
-    a.deep = deep_slices(g);
-    a.nb_lo = a.nb_hi = 0;
-    a.hole_begin = a.hole_end = 0;
-    memset(&a.ps, 0, sizeof(a.ps));
-    // fused compute + halo exchange over NVLink peer memory: one launch per sweep (or per group of sweeps), the boundary
-    // slices are stored into the neighbours' ghost slices by the sweep kernel itself
-    const bool peer = dist && psi->peer_attached && c->peer_halo && fused && sweep_supports_peer_halo(a);
-    unsigned long long* my_flag_lo = c->rank > 0 ? c->d_flags + 0 : nullptr;
-    unsigned long long* my_flag_hi = c->rank < c->nranks - 1 ? c->d_flags + 1 : nullptr;
-    int64_t n_lo_slab = 0;
-    if (peer && c->rank > 0) rnmf_slab_partition(g.nglob[D], c->nranks, c->rank - 1, nullptr, &n_lo_slab);
-
-    // Temporal blocking (several sweeps per pass over HBM) for every group of sweeps that does not carry the norm.
-    // A face without a Dirichlet/Neumann rule must be a slab neighbour.
-    const SweepVariantInfo* vi = sweep_variant_info(g.dim, c->sweep_variant);
-    RNMF_REQUIRE(vi, "unknown sweep_variant %d for %dD frames", c->sweep_variant, g.dim);
-    bool all_faces = true;
-    for (int fi = 0; fi < 2 * g.dim; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
-    bool side_faces = true;                                                         // the faces across the marching direction
-    for (int fi = 0; fi < 2 * (g.dim - 1); ++fi) side_faces = side_faces && a.faces.f[fi].mode != 0;
-    const bool has_lo = dist && c->rank > 0, has_hi = dist && c->rank < c->nranks - 1;
-    const bool slab_faces = side_faces && (has_lo || a.faces.f[2 * D].mode != 0) && (has_hi || a.faces.f[2 * D + 1].mode != 0);
-    const int depth = vi->depth;                                                    // sweeps per temporally blocked launch (1: none)
-    // slabs: the fused peer path with the in-kernel handshake and the deep halo; every rank must take the same decision:
-    // the thinnest slab (floor(n/P), cartesian2d/mod.rs:64-73) has to hold the 2*depth slices that travel
-    const bool tb_single = depth > 1 && !dist && fused && all_faces;
-    const bool tb_peer = depth > 1 && peer && c->peer_inkernel && slab_faces && deep_slices(g) >= depth - 1 && g.nglob[D] / c->nranks >= 2 * depth;
-    const bool tb3d = g.dim == 3 && (tb_single || tb_peer);
-    const bool tb2d = g.dim == 2 && (tb_single || tb_peer);
-    const int64_t n_pairable = n_sweeps - (l1_update ? 1 : 0);
-
-    if (dist) {
-        // Entry exchange of the current buffer's halos (deep halo: the two slices next to each face; rhs: its ghost
-        // slices, level 1 on the ghost-plane position reads them).  It is also what orders the shell copy above (which
-        // rewrites d2's ghost slices) before the neighbours' first peer stores into d2 of this call: a neighbour cannot
-        // leave its own entry exchange before this rank's send/recv, which is stream-ordered after the copy.
-        rc = halo_exchange_on(psi, psi->d, s, tb_peer ? depth - 1 : 0);
+    if (p.dist) {
+        // Entry exchange of the current buffer's halos (deep halo: the `depth` slices next to each face; rhs: depth-1 of
+        // them, the lower levels on the ghost-slice positions read them).  It is also what orders the shell copy above
+        // (which rewrites d2's ghost slices) before the neighbours' first peer stores into d2 of this call: a neighbour
+        // cannot leave its own entry exchange before this rank's send/recv, which is stream-ordered after the copy.
+        rc = halo_exchange_on(psi, psi->d, s, p.tb_peer ? p.depth - 1 : 0);
         if (rc) return rc;
-        if (tb_peer) { rc = halo_exchange_on(const_cast<rnmf_frame*>(rhs), rhs->d, s, depth - 2); if (rc) return rc; }
+        if (p.tb_peer) { rc = halo_exchange_on(const_cast<rnmf_frame*>(rhs), rhs->d, s, p.depth - 2); if (rc) return rc; }
     }
 
-    // small (L2-resident) frames: all sweeps but a norm-carrying last one in ONE cooperative launch
-    int64_t it0 = 0;
-    if (!dist && fused && c->resident && g.total * 8 * 3 <= c->resident_max_bytes) {
-        const int64_t nres = n_sweeps - (l1_update ? 1 : 0);
-        if (nres >= 4) {
-            int k = launch_jacobi_resident(g, psi->d, psi->d2, rhs->d, a.c, a.faces, nres, s);
-            if (k < 0) return RNMF_ERR_CUDA;
-            c->launches += k;
-            if (nres & 1) { double* t = psi->d; psi->d = psi->d2; psi->d2 = t; psi->parity ^= 1; }
-            it0 = nres;
-        }
+    // every sweep but a norm-carrying last one may be grouped
+    const int64_t n_groupable = n_sweeps - (l1_update ? 1 : 0);
+    int64_t it = 0;
+    // small (L2-resident) frames: all of them in ONE cooperative launch
+    if (!p.dist && p.fused && c->resident && g.total * 8 * 3 <= c->resident_max_bytes && n_groupable >= 4) {
+        int k = launch_jacobi_resident(g, psi->d, psi->d2, rhs->d, a.c, a.faces, n_groupable, s);
+        if (k < 0) return RNMF_ERR_CUDA;
+        c->launches += k;
+        if (n_groupable & 1) swap_buffers(psi);
+        it = n_groupable;
     }
-
-    for (int64_t it = it0; it < n_sweeps; ++it) {
-        if (tb2d && depth > 2 && it + depth <= n_pairable) {
-            // K = depth sweeps per pass (kernels_sweep2d_tbk.cu)
-            SweepArgs t = a;
-            t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
-            t.k_begin = 0; t.k_end = m;
-            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; setup_slab_launch(psi, psi->parity ^ 1, multi_sweep_2d_boundary_ctas(t), t); }
-            RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, s));
-            c->multi_sweeps += 1;
-            c->multi_sweep_sweeps += depth;
-            double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
-            psi->parity ^= 1;
-            it += depth - 1;
-            continue;
-        }
-        if (tb2d && !dist && (depth == 2 || vi->pairs) && it + 2 <= n_pairable) {
-            // two sweeps per pass (kernels_sweep2d_tb2.cu; single GPU): the default's remainder, or variant 30
-            SweepArgs t = a;
-            t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
-            t.k_begin = 0; t.k_end = m;
-            RNMF_LAUNCH(c, launch_jacobi_double_sweep_2d(t, s));
-            c->double_sweeps += 1;
-            double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
-            psi->parity ^= 1;
-            ++it;
-            continue;
-        }
-        if (tb3d && it + 2 <= n_pairable) {
-            // two sweeps per pass (kernels_sweep_tb2.cu)
-            SweepArgs t = a;
-            t.in = psi->d; t.out = psi->d2; t.partials = nullptr;
-            t.k_begin = 0; t.k_end = m;
-            if (tb_peer) { t.nb_lo = has_lo; t.nb_hi = has_hi; setup_slab_launch(psi, psi->parity ^ 1, double_sweep_boundary_ctas(t), t); }
-            RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, s));
-            c->double_sweeps += 1;
-            double* tmp = psi->d; psi->d = psi->d2; psi->d2 = tmp;
-            psi->parity ^= 1;
-            ++it;
-            continue;
-        }
-        const bool want_norm = l1_update && it == n_sweeps - 1;
-        a.in = psi->d;
-        a.out = psi->d2;
-        a.partials = nullptr;
-        long long n_part = 0;
-        if (peer) {
-            const int out_phys = psi->parity ^ 1;
-            const bool inkernel = c->peer_inkernel != 0;
-            if (!inkernel) RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s));
-            a.k_begin = 0; a.k_end = m;
-            const long long slice = D == 2 ? g.plane : g.pitch;       // one slowest-direction slice (z-plane / y-row)
-            a.peer_lo_plane = c->rank > 0 ? psi->peer_lo[out_phys] + slice * (n_lo_slab + g.ng) : nullptr;
-            a.peer_hi_plane = c->rank < c->nranks - 1 ? psi->peer_hi[out_phys] + slice * (g.ng - 1) : nullptr;
-            if (want_norm) {
-                n_part = sweep_num_partials(a);
-                rc = ensure_partials(c, n_part);
-                if (rc) return rc;
-                a.partials = c->d_partials;
-            }
-            if (inkernel) {
-                // handshake inside the sweep kernel: boundary CTAs (scheduled last) wait / publish
-                const unsigned long long tiles = (unsigned long long)sweep_boundary_ctas(a);
-                a.ps.enabled = 1;
-                a.ps.wait_lo = my_flag_lo; a.ps.wait_hi = my_flag_hi;
-                a.ps.sig_lo = c->rank > 0 ? c->peer_flag_lo : nullptr;
-                a.ps.sig_hi = c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr;
-                a.ps.done = c->d_flags + 3;
-                if (a.peer_lo_plane) c->done_target[0] += tiles;
-                if (a.peer_hi_plane) c->done_target[1] += tiles;
-                a.ps.target_lo = c->done_target[0]; a.ps.target_hi = c->done_target[1];
-                a.ps.epoch = c->epoch;
-                a.ps.status = c->d_flags + 2;
-            }
-            RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
-            a.ps.enabled = 0;
-            if (!inkernel)
-                RNMF_LAUNCH(c, launch_peer_signal(c->rank > 0 ? c->peer_flag_lo : nullptr,
-                                                  c->rank < c->nranks - 1 ? c->peer_flag_hi : nullptr, c->epoch + 1, s));
-            c->epoch += 1;
-        } else if (!dist || m < 3 || !c->overlap_halo || !fused) {
-            a.k_begin = 0; a.k_end = m;
-            if (want_norm) {
-                n_part = sweep_num_partials(a);
-                rc = ensure_partials(c, n_part);
-                if (rc) return rc;
-                a.partials = c->d_partials;
-            }
-            RNMF_LAUNCH(c, launch_jacobi_sweep(a, s));
-            if (!fused) { rc = fill_bc_on(psi, psi->d2, s); if (rc) return rc; }
-            if (dist) { rc = halo_exchange_on(psi, psi->d2, s); if (rc) return rc; }
-        } else {
-            // boundary slices first, then exchange them on the halo stream while the interior runs
-            SweepArgs lo = a, hi = a, mid = a;
-            lo.k_begin = 0; lo.k_end = 1;
-            hi.k_begin = m - 1; hi.k_end = m;
-            mid.k_begin = 1; mid.k_end = m - 1;
-            long long p_lo = 0, p_hi = 0, p_mid = 0;
-            if (want_norm) {
-                p_lo = sweep_num_partials(lo); p_hi = sweep_num_partials(hi); p_mid = sweep_num_partials(mid);
-                n_part = p_lo + p_hi + p_mid;
-                rc = ensure_partials(c, n_part);
-                if (rc) return rc;
-                lo.partials = c->d_partials;
-                hi.partials = c->d_partials + p_lo;
-                mid.partials = c->d_partials + p_lo + p_hi;
-            }
-            RNMF_LAUNCH(c, launch_jacobi_sweep(lo, s));
-            RNMF_LAUNCH(c, launch_jacobi_sweep(hi, s));
-            RNMF_CUDA_TRY(cudaEventRecord(c->ev_boundary, s));
-            RNMF_CUDA_TRY(cudaStreamWaitEvent(c->stream_halo, c->ev_boundary, 0));
-            rc = halo_exchange_on(psi, psi->d2, c->stream_halo);
+    long long n_part = 0;
+    while (it < n_sweeps) {
+        if (p.tb && it + p.depth <= n_groupable) {                       // a full group: `depth` sweeps per pass over HBM
+            rc = launch_blocked_sweeps(psi, a, p, p.depth);
             if (rc) return rc;
-            RNMF_CUDA_TRY(cudaEventRecord(c->ev_halo, c->stream_halo));
-            RNMF_LAUNCH(c, launch_jacobi_sweep(mid, s));
-            RNMF_CUDA_TRY(cudaStreamWaitEvent(s, c->ev_halo, 0));
+            it += p.depth;
+        } else if (p.pairs && p.depth > 2 && it + 2 <= n_groupable) {    // 2D leftovers as a pair
+            rc = launch_blocked_sweeps(psi, a, p, 2);
+            if (rc) return rc;
+            it += 2;
+        } else {
+            const bool want_norm = l1_update && it == n_sweeps - 1;
+            rc = launch_single_sweep(psi, a, p, want_norm, &n_part);
+            if (rc) return rc;
+            if (want_norm) {
+                RNMF_LAUNCH(c, launch_reduce_partials(c->d_partials, (int)n_part, c->d_scalar, s));
+                if (p.dist) RNMF_NCCL_TRY(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclSum, c->comm, s));
+                RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, s));
+            }
+            it += 1;
         }
-        if (want_norm) {
-            RNMF_LAUNCH(c, launch_reduce_partials(c->d_partials, (int)n_part, c->d_scalar, s));
-            if (dist) RNMF_NCCL_TRY(g_nccl.AllReduce(c->d_scalar, c->d_scalar, 1, ncclDouble, ncclSum, c->comm, s));
-            RNMF_CUDA_TRY(cudaMemcpyAsync(c->h_scalar, c->d_scalar, 8, cudaMemcpyDeviceToHost, s));
-        }
-        double* t = psi->d; psi->d = psi->d2; psi->d2 = t;
-        psi->parity ^= 1;
     }
-    // neighbours' last sweep must have landed in this frame's ghost planes before anything else
-    // in this stream touches the frame
-    if (peer) { RNMF_LAUNCH(c, launch_peer_wait(my_flag_lo, my_flag_hi, c->epoch, c->d_flags + 2, s)); c->peer_used = 1; }
+    // neighbours' last sweep must have landed in this frame's ghost slices before anything else in this stream touches the frame
+    if (p.peer) {
+        RNMF_LAUNCH(c, launch_peer_wait(p.has_lo ? c->d_flags + 0 : nullptr, p.has_hi ? c->d_flags + 1 : nullptr, c->epoch, c->d_flags + 2, s));
+        c->peer_used = 1;
+    }
     RNMF_CUDA_TRY(cudaGetLastError());
     if (l1_update) {
         RNMF_CUDA_TRY(cudaStreamSynchronize(s));
