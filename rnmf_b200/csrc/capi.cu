@@ -219,7 +219,7 @@ int check_peer_status(rnmf_ctx* c)
 // per launch need no data that arrives during the launch (K sweeps per launch: K slices, i.e. K - 1 deep ones).  A frame pointer (`d`, `d2`) addresses the z-lo ghost plane as
 // before; the allocation starts deep_elems() doubles earlier and the tail pad / canary band follow the rear deep plane.
 // 2D frames: three extra ROWS in front of the y-lo ghost row and behind the y-hi ghost row (four sweeps per launch across y-slabs).
-int deep_slices(const FrameGeom& g) { return g.ng == 1 && g.ncomp == 1 ? (g.dim == 3 ? 1 : 3) : 0; }
+int deep_slices(const FrameGeom& g) { return g.ng == 1 && g.ncomp == 1 ? (g.dim == 3 ? 2 : 3) : 0; }
 long long deep_elems(const FrameGeom& g) { return deep_slices(g) * (g.dim == 3 ? g.plane : g.pitch); }
 long long tail_off(const FrameGeom& g) { return g.total + deep_elems(g); }       // first double behind the (rear deep plane of the) frame
 
@@ -978,14 +978,22 @@ int plan_sweep_call(const rnmf_frame* psi, const SweepArgs& a, SweepCall* out)
     for (int fi = 0; fi < 2 * g.dim; ++fi) all_faces = all_faces && a.faces.f[fi].mode != 0;
     for (int fi = 0; fi < 2 * (g.dim - 1); ++fi) side_faces = side_faces && a.faces.f[fi].mode != 0;
     const bool slab_faces = side_faces && (p.has_lo || a.faces.f[2 * p.D].mode != 0) && (p.has_hi || a.faces.f[2 * p.D + 1].mode != 0);
-    p.depth = vi->depth;
+    // three sweeps per launch (3D) need even n0 / n1 (kernels_sweep_tb3.cu) and, across slabs, six planes per slab: frames that do
+    // not qualify run two sweeps per launch (the same decision on every rank: global shape and options only)
+    int depth = vi->depth;
+    if (g.dim == 3 && depth == 3 && !triple_sweep_applicable(g)) depth = 2;
     // slabs: the fused peer path with the in-kernel handshake and the deep halo; the thinnest slab (floor(n/P),
     // cartesian2d/mod.rs:64-73) has to hold the 2*depth slices that travel
     // (the 2D pair kernel, kernels_sweep2d_tb2.cu, has no slab form: variant 30 runs single sweeps across slabs)
-    const bool slab_kernel = g.dim == 3 || p.depth > 2;
-    p.tb_peer = p.depth > 1 && slab_kernel && p.peer && c->peer_inkernel && slab_faces && deep_slices(g) >= p.depth - 1 && g.nglob[p.D] / c->nranks >= 2 * p.depth;
-    p.tb = p.tb_peer || (p.depth > 1 && !p.dist && p.fused && all_faces);
-    p.pairs = p.tb && !p.dist && g.dim == 2 && (p.depth == 2 || vi->pairs);
+    auto slab_ok = [&](int d) {
+        return d > 1 && (g.dim == 3 || d > 2) && p.peer && c->peer_inkernel && slab_faces && deep_slices(g) >= d - 1 && g.nglob[p.D] / c->nranks >= 2 * d;
+    };
+    if (p.dist && g.dim == 3 && depth == 3 && !slab_ok(3)) depth = 2;
+    p.depth = depth;
+    p.tb_peer = p.dist && slab_ok(depth);
+    p.tb = p.tb_peer || (depth > 1 && !p.dist && p.fused && all_faces);
+    // sweeps left over by the groups run as pairs: 2D on a single GPU, 3D also across slabs (the two-sweep kernel has a slab form)
+    p.pairs = p.tb && depth > 2 && vi->pairs && (g.dim == 3 || !p.dist);
     *out = p;
     return RNMF_OK;
 }
@@ -996,7 +1004,7 @@ void swap_buffers(rnmf_frame* psi)
     psi->parity ^= 1;
 }
 
-// ONE temporally blocked launch of `sweeps` sweeps (3D: 2; 2D: 4, or 2 for the pairs).  Returns RNMF_OK / an error code.
+// ONE temporally blocked launch of `sweeps` sweeps (3D: 3, or 2 for the pairs / frames the three-sweep kernel does not take; 2D: 4, or 2 for the pairs).  Returns RNMF_OK / an error code.
 int launch_blocked_sweeps(rnmf_frame* psi, const SweepArgs& a, const SweepCall& p, int sweeps)
 {
     rnmf_ctx* c = psi->ctx;
@@ -1006,9 +1014,11 @@ int launch_blocked_sweeps(rnmf_frame* psi, const SweepArgs& a, const SweepCall& 
     const bool d3 = a.g.dim == 3;
     if (p.tb_peer) {
         t.nb_lo = p.has_lo; t.nb_hi = p.has_hi;
-        setup_slab_launch(psi, psi->parity ^ 1, d3 ? double_sweep_boundary_ctas(t) : multi_sweep_2d_boundary_ctas(t), t);
+        const int ctas = !d3 ? multi_sweep_2d_boundary_ctas(t) : sweeps == 3 ? triple_sweep_boundary_ctas(t) : double_sweep_boundary_ctas(t);
+        setup_slab_launch(psi, psi->parity ^ 1, ctas, t);
     }
-    if (d3) RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, c->stream));                  // kernels_sweep_tb2.cu
+    if (d3 && sweeps == 3) RNMF_LAUNCH(c, launch_jacobi_triple_sweep(t, c->stream));   // kernels_sweep_tb3.cu
+    else if (d3) RNMF_LAUNCH(c, launch_jacobi_double_sweep(t, c->stream));             // kernels_sweep_tb2.cu
     else if (sweeps > 2) RNMF_LAUNCH(c, launch_jacobi_multi_sweep_2d(t, c->stream));   // kernels_sweep2d_tbk.cu
     else RNMF_LAUNCH(c, launch_jacobi_double_sweep_2d(t, c->stream));                  // kernels_sweep2d_tb2.cu
     if (sweeps == 2) c->double_sweeps += 1;
@@ -1157,7 +1167,7 @@ extern "C" int32_t rnmf_jacobi_sweeps(rnmf_frame* psi, const rnmf_frame* rhs, co
             rc = launch_blocked_sweeps(psi, a, p, p.depth);
             if (rc) return rc;
             it += p.depth;
-        } else if (p.pairs && p.depth > 2 && it + 2 <= n_groupable) {    // 2D leftovers as a pair
+        } else if (p.pairs && p.depth > 2 && it + 2 <= n_groupable) {    // leftovers as a pair
             rc = launch_blocked_sweeps(psi, a, p, 2);
             if (rc) return rc;
             it += 2;
@@ -1450,7 +1460,7 @@ static bool skew_applicable(const rnmf_ctx* c, const rnmf_frame* psi)
     // (floor(n/P), cartesian2d/mod.rs:64-73), which is the same number on every rank
     const long long n2_min = dist ? g.nglob[2] / c->nranks : g.n[2];
     return c->e2e_skew && g.dim == 3 && g.ng == 1 && g.ncomp == 1 && (c->nranks == 1 || dist) && slab_ok && faces && C >= 2 && n2_min / C >= 16 &&
-           g.G[0] * g.G[1] * (n2_min + 2) * 8 >= (64LL << 20) && vi && vi->depth == 2;
+           g.G[0] * g.G[1] * (n2_min + 2) * 8 >= (64LL << 20) && vi && vi->depth >= 2;
 }
 
 static int64_t skewed_upload_and_first_sweeps(rnmf_ctx* c, rnmf_frame* psi, rnmf_frame* rhs, const double* psi_in, const double* rhs_in,

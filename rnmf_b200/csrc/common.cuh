@@ -282,6 +282,10 @@ const SweepVariantInfo* sweep_variant_info(int dim, int id);    // nullptr: no s
 // Two sweeps per pass over HBM (kernels_sweep_tb2.cu), also across z-slabs (a.deep >= 1, a.nb_lo / a.nb_hi)
 int launch_jacobi_double_sweep(const SweepArgs& a, cudaStream_t s);
 int double_sweep_boundary_ctas(const SweepArgs& a);
+// Three sweeps per pass over HBM (kernels_sweep_tb3.cu): frames with even n0 / n1; across z-slabs a.deep >= 2
+bool triple_sweep_applicable(const FrameGeom& g);
+int launch_jacobi_triple_sweep(const SweepArgs& a, cudaStream_t s);
+int triple_sweep_boundary_ctas(const SweepArgs& a);
 // 2D analogue (kernels_sweep2d_tb2.cu), single GPU: a.k_begin..a.k_end = output rows
 int launch_jacobi_double_sweep_2d(const SweepArgs& a, cudaStream_t s);
 // four sweeps per launch (kernels_sweep2d_tbk.cu), also across y-slabs (a.deep >= 3, a.nb_lo / a.nb_hi)

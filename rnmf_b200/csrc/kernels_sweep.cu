@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double* __r
 // launcher; rnmf_jacobi_sweeps (capi.cu) only reads `depth` / `pairs`.
 const SweepVariantInfo kVariants[] = {
     // id dim depth pairs  what
-    { 0, 3, 2, false, "3D default: two sweeps per launch (128x12 tile, quad mapping), single sweeps by the TMA kernel" },
+    { 0, 3, 3, true, "3D default: three sweeps per launch (128x12 tile, quad mapping, kernels_sweep_tb3.cu), then a pair, then single sweeps" },
+    { 31, 3, 2, false, "3D: two sweeps per launch (kernels_sweep_tb2.cu), single sweeps by the TMA kernel" },
     { 6, 3, 1, false, "3D: one sweep per launch only (TMA kernel, 128x8 tile, 4 stages)" },
     { 0, 2, 4, true, "2D default: four sweeps per launch (512-column strips, de-interleaved rings), then pairs, then single sweeps" },
     { 30, 2, 2, false, "2D: two sweeps per launch (kernels_sweep2d_tb2.cu), single sweeps by the TMA kernel" },

@@ -68,7 +68,7 @@ struct Tb2Params {
     int chunk;
     int n_chunks;
     int nb_lo, nb_hi;            // a slab neighbour behind the z-lo / z-hi face (deep halo planes hold its data)
-    int zshift;                  // the tensor maps start one plane before the z-lo ghost plane (deep planes present)
+    int zshift;                  // the tensor maps start this many planes before the z-lo ghost plane (the buffers' deep planes)
     // neighbours' planes of THEIR `out` buffer that receive my u2 planes 0, 1 (lo) and n2-1, n2-2 (hi)
     double* peer_lo_ghost;
     double* peer_lo_deep;
@@ -666,7 +666,7 @@ struct Tb2Launcher {
         int chunk, n_chunks;
         plan(a, grid, chunk, n_chunks);
         CUtensorMap tm_u0, tm_rhs;
-        const int deep = a.deep ? 1 : 0;
+        const int deep = a.deep;
         if (tma3d_encode_map_deep(&tm_u0, a.g, a.in, Cfg::BX, Cfg::U0_ROWS, deep)) return -1;
         if (tma3d_encode_map_deep(&tm_rhs, a.g, a.rhs, Cfg::BX, Cfg::R_ROWS, deep)) return -1;
         Tb2Params p;

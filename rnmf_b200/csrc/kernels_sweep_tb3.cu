@@ -1,0 +1,781 @@
+// kernels_sweep_tb3.cu -- K1 for 3D frames, temporally blocked over THREE Jacobi sweeps (each followed by the
+// ng=1 ghost fill, poisson.rs:80-89 + dataframe.rs:289-355) per pass over HBM: 24 B per three updates.
+//
+// The two-sweep kernel (kernels_sweep_tb2.cu) is DRAM-bound in real bytes; the only way past it is fewer bytes per
+// update.  Same structure, one level more: a CTA streams psi (u0) and rhs once, forms u1 = sweep(u0) and
+// u2 = sweep(u1) in shared memory and writes only u3 = sweep(u2).
+//
+//   * CTA tile: 128 x 12 cells of u3, a chunk of z-planes.  u2 is needed on the tile grown by one cell in x / y (no
+//     corners) and one plane in z, u1 on the tile grown by two (a diamond: Manhattan distance <= 2), u0 by three.
+//   * producer warp: per plane one TMA box of u0 (138 x 18: x from i0-4, y from j0-3) and one of rhs (134 x 16: x from
+//     i0-2, y from j0-2) into a 4-stage ring (full / empty mbarriers).  The row lengths are chosen so that the column
+//     warp's accesses (one row apart) fall into different banks.
+//   * u1 and u2 planes live in two-slot rings with DE-INTERLEAVED rows: even x first, odd x from ODD bytes on.  A lane
+//     owns the pair (x, x+1), x even: its W neighbour is an odd position, its E neighbour an even one, so the E/W loads
+//     of a warp are dense 8-byte accesses (2 shared-memory wavefronts instead of the 4 that 8-byte accesses 16 bytes
+//     apart cost -- the shared-memory pipe is what bounds three levels per plane).
+//   * 12 "quad" warps own two adjacent tile rows x 64 columns each (lane: a 2 x 2 patch, as in the two-sweep kernel)
+//     and run all three levels on their cells, each level register z-marched over the lane's own values of the level
+//     below: in iteration `it` level 1 forms plane a1+it, level 2 plane a1+it-1, level 3 plane a1+it-2.
+//     Two halo-row warps own the row pairs (j0-2, j0-1) and (j0+12, j0+13) x 128 columns: level 1 on both rows,
+//     level 2 on the row next to the tile.  One warp owns the columns i0-2, i0-1, i0+128, i0+129 (level 1; level 2 on
+//     the inner ones) and the four diamond corners (level 1).
+//   * per iteration one wait phase (full[next u0 plane], u1full[slot of plane a1+it-1], u2full[slot of plane a1+it-2]);
+//     every consumer warp arrives on a slot's barrier after its stores, and the wait for the previous plane is also the
+//     write-after-read guard of the slot about to be overwritten (the two-sweep kernel's argument, once per ring).
+//   * level 3's and level 2's x/y parts (c0*rhs + c1*(E+W)) + c2*(N+S) are formed before the level below has produced
+//     the plane above; + c3*(U+D) is added afterwards: the reference's association (poisson.rs:83-88).
+//   * quad warps whose patch is whole and touches no y face run an interior-specialised copy of the steady loop
+//     (EDGE 0; EDGE 1 keeps the x-ghost code); the iterations that meet a z face or a plane that travels to a slab
+//     neighbour run the general code (EDGE 2).
+//
+// Restriction: n0 and n1 even (every 2 x 2 patch is whole or absent; the x-hi ghost is an even position); other frames
+// take the two-sweep kernel (capi.cu: plan_sweep_call).
+//
+// Slabs (one GPU per z-slab), DEEP HALO as in kernels_sweep_tb2.cu with one plane more: the buffers carry TWO extra
+// planes in front of the z-lo ghost plane and behind the z-hi ghost plane; with the neighbour's three boundary planes
+// there (rhs: two) a slab face is a chunk boundary, and u3 of my three planes next to the face goes into the
+// neighbour's ghost + deep planes of its `out` buffer under the same one-epoch-per-launch handshake.
+//
+// Arithmetic: the same explicitly rounded sequence as every other sweep kernel: u3 is bit-identical to three single sweeps.
+#include <stdlib.h>
+
+#include "tma_util.cuh"
+
+namespace {
+using namespace tmau;
+
+struct Tb3Params {
+    FrameGeom g;
+    double* out;
+    SweepCoef c;
+    FaceSet faces;
+    long long m_begin, m_end;    // output planes
+    int chunk;
+    int n_chunks;
+    int nb_lo, nb_hi;            // a slab neighbour behind the z-lo / z-hi face (deep halo planes hold its data)
+    int zshift;                  // the tensor maps start this many planes before the z-lo ghost plane
+    double* peer_lo[3];          // the lo neighbour's planes (of ITS `out`) that receive my u3 planes 0, 1, 2
+    double* peer_hi[3];          // the hi neighbour's planes that receive my u3 planes n2-1, n2-2, n2-3
+    PeerSync ps;
+};
+
+struct Cfg3 {
+    static constexpr int TX = 128, TY = 12, NS = 4;
+    static constexpr int BX0 = 138, U0_ROWS = TY + 6;      // u0 box: column c <-> x = i0-4+c, row r <-> y = j0-3+r
+    static constexpr int BXR = 134, R_ROWS = TY + 4;       // rhs box: column c <-> x = i0-2+c, row r <-> y = j0-2+r
+    static constexpr int HALF = 67;                        // ring row: E[m] <-> x = i0-2+2m, O[m] <-> x = i0-1+2m, m < 67
+    static constexpr uint32_t RB0 = BX0 * 8, RBR = BXR * 8, ODD = HALF * 8, RBU = 2 * HALF * 8;
+    static constexpr int U0_BYTES = BX0 * U0_ROWS * 8;
+    static constexpr int U0_STAGE = (U0_BYTES + 127) / 128 * 128;
+    static constexpr int RHS_BYTES = BXR * R_ROWS * 8;
+    static constexpr int RHS_STAGE = (RHS_BYTES + 127) / 128 * 128;
+    static constexpr int U1_SLOT = ((int)RBU * (TY + 4) + 127) / 128 * 128;     // rows y = j0-2 .. j0+13
+    static constexpr int U2_SLOT = ((int)RBU * (TY + 2) + 127) / 128 * 128;     // rows y = j0-1 .. j0+12
+    static constexpr int RHS_OFF = NS * U0_STAGE;
+    static constexpr int U1_OFF = RHS_OFF + NS * RHS_STAGE;
+    static constexpr int U2_OFF = U1_OFF + 2 * U1_SLOT;
+    static constexpr int BAR_OFF = U2_OFF + 2 * U2_SLOT;
+    static constexpr int SMEM = BAR_OFF + (2 * NS + 4) * 8 + 128;
+    static constexpr int NCONS = TY + 3;                   // 12 quad warps + 2 halo-row warps + 1 column warp
+    static constexpr int THREADS = 32 * (TY + 4);          // + producer warp
+    static_assert(SMEM <= 227 * 1024, "shared-memory budget");
+    static_assert(U0_BYTES % 16 == 0 && RHS_BYTES % 16 == 0 && (BX0 * 8) % 16 == 0 && (BXR * 8) % 16 == 0, "TMA box rows are multiples of 16 bytes");
+};
+
+// first two terms of poisson.rs:83-88 (the z term is added last: same association as upd3)
+__device__ __forceinline__ double part3(double c0, double c1, double c2, double r, double e, double w, double n, double s)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(c0, r), __dmul_rn(c1, __dadd_rn(e, w))), __dmul_rn(c2, __dadd_rn(n, s)));
+}
+__device__ __forceinline__ double fin3(double part, double c3, double u, double d) { return __dadd_rn(part, __dmul_rn(c3, __dadd_rn(u, d))); }
+__device__ __forceinline__ double2 fin3(const double2& part, double c3, const double2& u, const double2& d)
+{
+    return make_double2(fin3(part.x, c3, u.x, d.x), fin3(part.y, c3, u.y, d.y));
+}
+
+// a pair (x, x+1), x even, in a de-interleaved ring row: b = byte address of its even position
+__device__ __forceinline__ double2 ldp(uint32_t b) { return make_double2(lds1(b), lds1(b + Cfg3::ODD)); }
+__device__ __forceinline__ void stp(uint32_t b, const double2& v) { sts1(b, v.x); sts1(b + Cfg3::ODD, v.y); }
+// its W neighbour (x-1, an odd position) and its E neighbour (x+2, an even position); also where the x-lo / x-hi ghost of a
+// pair next to the face lives
+constexpr uint32_t kW = Cfg3::ODD - 8, kE = 8;
+
+// position in the u0 / rhs ring shared by every consumer: stage of plane a1+it, of plane a1+it+1, parity its full barrier completes with
+struct Ring3 {
+    uint32_t sc, sn, phn;
+    __device__ __forceinline__ void advance() { sc = sn; if (++sn == (uint32_t)Cfg3::NS) { sn = 0; phn ^= 1u; } }
+};
+
+// what every consumer warp of the CTA knows about the chunk (CTA-uniform)
+struct ChunkPlan {
+    long long k0, k1, a1;
+    int nL1;                     // level-1 planes a1 .. a1+nL1-1; iteration it: level 1 of plane a1+it, level 2 of a1+it-1, level 3 of a1+it-2
+    int it2_first, it2_last;     // iterations in which level 2 / level 3 is active
+    int it3_first, it3_last;
+    int it_zlo2, it_zlo3;        // iteration whose level 2 / level 3 forms plane 0 next to a PHYSICAL z-lo face (-1: none)
+};
+
+// ---------------------------------------------------------------------------------------------------
+// quad warps
+// ---------------------------------------------------------------------------------------------------
+struct QuadK3 {
+    uint32_t pa, ra, u1a, u2a;           // the lane's first cell (row A): u0 stage 0, rhs stage 0, u1 slot 0, u2 slot 0 (even half)
+    uint32_t full0, empty0, u1full0, u2full0;
+    bool ok;                             // the 2 x 2 patch lies inside the frame
+    bool xlo, xhi, ylo, yhi;             // it touches that physical face (and the face has a Dirichlet / Neumann rule)
+    Face1 fx0, fx1, fy0, fy1, fz0, fz1;
+    long long pitch, plane_sz, xy_off;
+    int lane;
+    int it_send[6];                      // iterations whose u3 plane also goes to a neighbour: lo ghost, lo deep 1, lo deep 2, hi ghost, hi deep 1, hi deep 2
+};
+
+struct QuadSt3 {
+    double2 below_a, below_b, cur_a, cur_b;      // u0 of planes a1+it-1, a1+it
+    double2 u1lo_a, u1lo_b, u1c_a, u1c_b;        // u1 of planes a1+it-2, a1+it-1
+    double2 u2lo_a, u2lo_b, u2c_a, u2c_b;        // u2 of planes a1+it-3, a1+it-2
+    double2 r1_a, r1_b, r2_a, r2_b;              // rhs of planes a1+it-1, a1+it-2
+    double* oa;                                  // where u3 of plane a1+it-2 goes
+    Ring3 r;
+};
+
+// the lane's patch of one level into a ring slot, with the ghost values fill_bc would give that level on the physical x / y faces
+template <int EDGE>
+__device__ __forceinline__ void ring_store(const QuadK3& k, uint32_t b, const double2& va, const double2& vb)
+{
+    constexpr uint32_t RBU = Cfg3::RBU;
+    if (EDGE == 2 && !k.ok) return;
+    stp(b, va);
+    stp(b + RBU, vb);
+    if (EDGE != 0) {
+        if (k.xlo) { sts1(b + kW, ghost1(k.fx0, va.x)); sts1(b + RBU + kW, ghost1(k.fx0, vb.x)); }
+        if (k.xhi) { sts1(b + kE, ghost1(k.fx1, va.y)); sts1(b + RBU + kE, ghost1(k.fx1, vb.y)); }
+    }
+    if (EDGE == 2) {
+        if (k.ylo) stp(b - RBU, ghost1(k.fy0, va));
+        if (k.yhi) stp(b + 2 * RBU, ghost1(k.fy1, vb));
+    }
+}
+
+// u3 of the lane's patch into one grown plane of a frame buffer: the valid cells and the x / y face ghosts
+template <int EDGE>
+__device__ __forceinline__ void plane_store3(const QuadK3& k, double* oa, const double2& na, const double2& nb)
+{
+    if (EDGE == 2 && !k.ok) return;
+#ifdef RNMF_EMULATE
+    if (reinterpret_cast<uintptr_t>(oa) % 16 != 0 || (k.pitch & 1)) emu::fault("misaligned 16-byte global store", reinterpret_cast<uintptr_t>(oa), 16);
+#endif
+    *reinterpret_cast<double2*>(oa) = na;
+    *reinterpret_cast<double2*>(oa + k.pitch) = nb;
+    if (EDGE != 0) {
+        if (k.xlo) { oa[-1] = ghost1(k.fx0, na.x); oa[k.pitch - 1] = ghost1(k.fx0, nb.x); }
+        if (k.xhi) { oa[2] = ghost1(k.fx1, na.y); oa[k.pitch + 2] = ghost1(k.fx1, nb.y); }
+    }
+    if (EDGE == 2) {
+        if (k.ylo) *reinterpret_cast<double2*>(oa - k.pitch) = ghost1(k.fy0, na);
+        if (k.yhi) *reinterpret_cast<double2*>(oa + 2 * k.pitch) = ghost1(k.fy1, nb);
+    }
+}
+
+// One plane iteration of a quad warp.  L1 / L2 / L3: which levels are active.  EDGE: 2 = general; 0 = the warp's patches are
+// whole, touch no x / y face, and the iteration meets neither a z face nor a plane that goes to a slab neighbour; 1 = as 0,
+// but next to an x face.
+template <bool L1, bool L2, bool L3, int EDGE>
+__device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
+{
+    using C = Cfg3;
+    constexpr uint32_t RB0 = C::RB0, RBR = C::RBR, RBU = C::RBU;
+    const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 above_a = zero2, above_b = zero2, rc_a = zero2, rc_b = zero2;
+    double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2, P2_a = zero2, P2_b = zero2, P3_a = zero2, P3_b = zero2;
+    const int j = it - cp.it2_first;                       // level 2 forms its j-th plane now (slot j & 1); level 3 reads plane j-1
+    const uint32_t sc = st.r.sc, sn = st.r.sn;
+
+    // ---- wait phase ----------------------------------------------------------------------------------
+    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);                                            // u0 plane a1+it+1
+    if ((L1 || L2) && it >= 1) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);   // u1 plane a1+it-1 complete, plane a1+it-2 no longer read
+    if (j >= 1) mbar_wait(k.u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);     // u2 plane a1+it-2 complete, the one before no longer read
+
+    // ---- level 3, x/y part: plane a1+it-2 from the u2 ring ---------------------------------------------
+    if (L3) {
+        const uint32_t b = k.u2a + (uint32_t)((j - 1) & 1) * C::U2_SLOT;
+        const double2 n_b = ldp(b + 2 * RBU), s_a = ldp(b - RBU);
+        const double w_a = lds1(b + kW), e_a = lds1(b + kE), w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+        P3_a.x = part3(c0, c1, c2, st.r2_a.x, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
+        P3_a.y = part3(c0, c1, c2, st.r2_a.y, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y);
+        P3_b.x = part3(c0, c1, c2, st.r2_b.x, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x);
+        P3_b.y = part3(c0, c1, c2, st.r2_b.y, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y);
+    }
+    // ---- level 2, x/y part: plane a1+it-1 from the u1 ring ---------------------------------------------
+    if (L2) {
+        const uint32_t b = k.u1a + (uint32_t)((it - 1) & 1) * C::U1_SLOT;
+        const double2 n_b = ldp(b + 2 * RBU), s_a = ldp(b - RBU);
+        const double w_a = lds1(b + kW), e_a = lds1(b + kE), w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+        P2_a.x = part3(c0, c1, c2, st.r1_a.x, st.u1c_a.y, w_a, st.u1c_b.x, s_a.x);
+        P2_a.y = part3(c0, c1, c2, st.r1_a.y, e_a, st.u1c_a.x, st.u1c_b.y, s_a.y);
+        P2_b.x = part3(c0, c1, c2, st.r1_b.x, st.u1c_b.y, w_b, n_b.x, st.u1c_a.x);
+        P2_b.y = part3(c0, c1, c2, st.r1_b.y, e_b, st.u1c_b.x, n_b.y, st.u1c_a.y);
+    }
+    // ---- level 1: u1 of plane a1+it ----------------------------------------------------------------------
+    if (L1) {
+        const uint32_t pn = k.pa + sn * C::U0_STAGE, pc = k.pa + sc * C::U0_STAGE, pr = k.ra + sc * C::RHS_STAGE;
+        above_a = lds2(pn); above_b = lds2(pn + RB0);
+        const double2 n_b = lds2(pc + 2 * RB0), s_a = lds2(pc - RB0);
+        rc_a = lds2(pr); rc_b = lds2(pr + RBR);
+        const double w_a = lds1(pc - 8), e_a = lds1(pc + 16), w_b = lds1(pc + RB0 - 8), e_b = lds1(pc + RB0 + 16);
+        u1n_a.x = upd3(c0, c1, c2, c3, rc_a.x, st.cur_a.y, w_a, st.cur_b.x, s_a.x, above_a.x, st.below_a.x);
+        u1n_a.y = upd3(c0, c1, c2, c3, rc_a.y, e_a, st.cur_a.x, st.cur_b.y, s_a.y, above_a.y, st.below_a.y);
+        u1n_b.x = upd3(c0, c1, c2, c3, rc_b.x, st.cur_b.y, w_b, n_b.x, st.cur_a.x, above_b.x, st.below_b.x);
+        u1n_b.y = upd3(c0, c1, c2, c3, rc_b.y, e_b, st.cur_b.x, n_b.y, st.cur_a.y, above_b.y, st.below_b.y);
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);                  // this warp is done with the stage of plane a1+it
+        ring_store<EDGE>(k, k.u1a + (uint32_t)(it & 1) * C::U1_SLOT, u1n_a, u1n_b);
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+    }
+    // ---- level 2, z part: u2 of plane a1+it-1 ---------------------------------------------------------------
+    if (L2) {
+        double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
+        if (EDGE == 2 && it == cp.it_zlo2) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
+        if (!L1) { up_a = ghost1(k.fz1, st.u1c_a); up_b = ghost1(k.fz1, st.u1c_b); }         // the frame's last plane next to a physical z-hi face
+        u2n_a = fin3(P2_a, c3, up_a, dn_a);
+        u2n_b = fin3(P2_b, c3, up_b, dn_b);
+        ring_store<EDGE>(k, k.u2a + (uint32_t)(j & 1) * C::U2_SLOT, u2n_a, u2n_b);
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * (j & 1));
+    }
+    // ---- level 3, z part: u3 of plane a1+it-2 ---------------------------------------------------------------
+    if (L3) {
+        double2 dn_a = st.u2lo_a, dn_b = st.u2lo_b, up_a = u2n_a, up_b = u2n_b;
+        const bool zlo = EDGE == 2 && it == cp.it_zlo3;
+        if (zlo) { dn_a = ghost1(k.fz0, st.u2c_a); dn_b = ghost1(k.fz0, st.u2c_b); }
+        if (!L2) { up_a = ghost1(k.fz1, st.u2c_a); up_b = ghost1(k.fz1, st.u2c_b); }
+        const double2 na = fin3(P3_a, c3, up_a, dn_a), nb = fin3(P3_b, c3, up_b, dn_b);
+        double* oa = st.oa;
+        plane_store3<EDGE>(k, oa, na, nb);
+        if (EDGE == 2) {
+            if (k.ok) {
+                if (zlo) { *reinterpret_cast<double2*>(oa - k.plane_sz) = ghost1(k.fz0, na); *reinterpret_cast<double2*>(oa - k.plane_sz + k.pitch) = ghost1(k.fz0, nb); }
+                if (!L2) { *reinterpret_cast<double2*>(oa + k.plane_sz) = ghost1(k.fz1, na); *reinterpret_cast<double2*>(oa + k.plane_sz + k.pitch) = ghost1(k.fz1, nb); }
+            }
+            // planes next to a slab neighbour: the same grown rows into its ghost / deep planes (NVLink stores)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                if (it == k.it_send[e]) plane_store3<2>(k, p.peer_lo[e] + k.xy_off, na, nb);
+                if (it == k.it_send[3 + e]) plane_store3<2>(k, p.peer_hi[e] + k.xy_off, na, nb);
+            }
+        }
+        st.oa = oa + k.plane_sz;
+    }
+    // ---- rotate ------------------------------------------------------------------------------------------
+    if (L1) {
+        st.below_a = st.cur_a; st.below_b = st.cur_b;
+        st.cur_a = above_a; st.cur_b = above_b;
+        st.r.advance();
+    }
+    st.u2lo_a = st.u2c_a; st.u2lo_b = st.u2c_b;
+    st.u2c_a = u2n_a; st.u2c_b = u2n_b;
+    st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
+    st.u1c_a = u1n_a; st.u1c_b = u1n_b;
+    st.r2_a = st.r1_a; st.r2_b = st.r1_b;
+    st.r1_a = rc_a; st.r1_b = rc_b;
+}
+
+// an iteration with the general code, whatever levels are active in it
+__device__ __forceinline__ void quad_general3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
+{
+    const bool l1 = it < cp.nL1, l2 = it >= cp.it2_first && it <= cp.it2_last, l3 = it >= cp.it3_first && it <= cp.it3_last;
+    if (l1 && l2 && l3) quad_iter3<true, true, true, 2>(p, cp, k, st, it);
+    else if (l1 && l2) quad_iter3<true, true, false, 2>(p, cp, k, st, it);
+    else if (l1) quad_iter3<true, false, false, 2>(p, cp, k, st, it);
+    else if (l2 && l3) quad_iter3<false, true, true, 2>(p, cp, k, st, it);
+    else if (l2) quad_iter3<false, true, false, 2>(p, cp, k, st, it);
+    else if (l3) quad_iter3<false, false, true, 2>(p, cp, k, st, it);
+}
+
+template <int EDGE>
+__device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, int& it, const int end)
+{
+    for (; it + 3 <= end; it += 3) {
+        quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
+        quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 1);
+        quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 2);
+    }
+    for (; it < end; ++it) quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// halo-row warps: the row pair below (TOP = false: rows j0-2, j0-1) or above (TOP = true: rows j0+12, j0+13) the tile,
+// 128 columns (lane l: pairs at x = i0+2l and i0+64+2l).  Level 1 on both rows, level 2 on the row next to the tile.
+// ---------------------------------------------------------------------------------------------------
+struct HaloK3 {
+    uint32_t pa, ra, u1a, u2a;           // row A, pair a: u0 stage 0, rhs stage 0, u1 slot 0; the INNER row's pair a in u2 slot 0
+    uint32_t full0, empty0, u1full0, u2full0;
+    bool ok_a, ok_b;                     // pair a / pair b lies inside the frame (both rows do, or neither)
+    bool xlo;                            // pair a starts at x = 0 next to a physical face with a rule
+    int xhi;                             // 0 / 1: pair a / b ends at x = n0-1 next to a physical face with a rule; -1: neither
+    Face1 fx0, fx1, fz0, fz1;
+    int lane;
+};
+
+struct HaloSt3 {
+    double2 below[4], cur[4];            // u0: Aa, Ab, Ba, Bb
+    double2 u1c_out[2];                  // u1 of plane a1+it-1, the outer row (pairs a, b)
+    double2 u1lo_in[2], u1c_in[2];       // u1 of planes a1+it-2, a1+it-1, the inner row
+    double2 r1_in[2];                    // rhs of plane a1+it-1, the inner row
+    Ring3 r;
+};
+
+template <bool TOP, bool L1, bool L2>
+__device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& cp, const HaloK3& k, HaloSt3& st, const int it)
+{
+    using C = Cfg3;
+    constexpr uint32_t RB0 = C::RB0, RBR = C::RBR, RBU = C::RBU;
+    constexpr int IN = TOP ? 0 : 1, OUT = TOP ? 1 : 0;      // row index (A = 0, B = 1) of the row next to the tile / the outer row
+    const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, rc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
+    const int j = it - cp.it2_first;
+    const uint32_t sc = st.r.sc, sn = st.r.sn;
+
+    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);
+    if (it >= 1) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+    if (j >= 1) mbar_wait(k.u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+
+    if (L2) {
+        // inner row: the neighbour row towards the tile comes from the ring, the other one is the lane's own outer row
+        const uint32_t b = k.u1a + (uint32_t)((it - 1) & 1) * C::U1_SLOT + IN * RBU;
+        const uint32_t bt = TOP ? b - RBU : b + RBU;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double2 t = ldp(bt + 256 * h);
+            const double w = lds1(b + 256 * h + kW), e = lds1(b + 256 * h + kE);
+            const double2 n = TOP ? st.u1c_out[h] : t, s = TOP ? t : st.u1c_out[h];
+            P2[h].x = part3(c0, c1, c2, st.r1_in[h].x, st.u1c_in[h].y, w, n.x, s.x);
+            P2[h].y = part3(c0, c1, c2, st.r1_in[h].y, e, st.u1c_in[h].x, n.y, s.y);
+        }
+    }
+    if (L1) {
+        const uint32_t pn = k.pa + sn * C::U0_STAGE, pc = k.pa + sc * C::U0_STAGE, pr = k.ra + sc * C::RHS_STAGE;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t o = 512 * h;
+            above[h] = lds2(pn + o); above[2 + h] = lds2(pn + RB0 + o);
+            const double2 s_a = lds2(pc - RB0 + o), n_b = lds2(pc + 2 * RB0 + o);
+            const double2 r_a = lds2(pr + o), r_b = lds2(pr + RBR + o);
+            const double w_a = lds1(pc + o - 8), e_a = lds1(pc + o + 16), w_b = lds1(pc + RB0 + o - 8), e_b = lds1(pc + RB0 + o + 16);
+            const double2 ca = st.cur[h], cb = st.cur[2 + h];
+            u1n[h].x = upd3(c0, c1, c2, c3, r_a.x, ca.y, w_a, cb.x, s_a.x, above[h].x, st.below[h].x);
+            u1n[h].y = upd3(c0, c1, c2, c3, r_a.y, e_a, ca.x, cb.y, s_a.y, above[h].y, st.below[h].y);
+            u1n[2 + h].x = upd3(c0, c1, c2, c3, r_b.x, cb.y, w_b, n_b.x, ca.x, above[2 + h].x, st.below[2 + h].x);
+            u1n[2 + h].y = upd3(c0, c1, c2, c3, r_b.y, e_b, cb.x, n_b.y, ca.y, above[2 + h].y, st.below[2 + h].y);
+            rc_in[h] = IN ? r_b : r_a;
+        }
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);
+        const uint32_t b = k.u1a + (uint32_t)(it & 1) * C::U1_SLOT;
+        if (k.ok_a) { stp(b, u1n[0]); stp(b + RBU, u1n[2]); }
+        if (k.ok_b) { stp(b + 256, u1n[1]); stp(b + RBU + 256, u1n[3]); }
+        // the x-face ghosts of u1 that level 2 of the inner row reads
+        if (k.xlo) sts1(b + IN * RBU + kW, ghost1(k.fx0, u1n[2 * IN].x));
+        if (k.xhi >= 0) sts1(b + IN * RBU + 256 * k.xhi + kE, ghost1(k.fx1, k.xhi ? u1n[2 * IN + 1].y : u1n[2 * IN].y));
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+    }
+    if (L2) {
+        const uint32_t b = k.u2a + (uint32_t)(j & 1) * C::U2_SLOT;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double2 dn = st.u1lo_in[h], up = u1n[2 * IN + h];
+            if (it == cp.it_zlo2) dn = ghost1(k.fz0, st.u1c_in[h]);
+            if (!L1) up = ghost1(k.fz1, st.u1c_in[h]);
+            const double2 v = fin3(P2[h], c3, up, dn);
+            if (h == 0 ? k.ok_a : k.ok_b) stp(b + 256 * h, v);
+        }
+        __syncwarp();
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * (j & 1));
+    }
+    if (L1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { st.below[q] = st.cur[q]; st.cur[q] = above[q]; }
+        st.r.advance();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        st.u1lo_in[h] = st.u1c_in[h];
+        st.u1c_in[h] = u1n[2 * IN + h];
+        st.u1c_out[h] = u1n[2 * OUT + h];
+        st.r1_in[h] = rc_in[h];
+    }
+}
+
+template <bool TOP>
+__device__ __forceinline__ void halo_rows3(const Tb3Params& p, const ChunkPlan& cp, const HaloK3& k, HaloSt3& st)
+{
+    int it = 0;
+    for (; it < cp.it2_first && it < cp.nL1; ++it) halo_iter3<TOP, true, false>(p, cp, k, st, it);
+    for (; it < cp.nL1; ++it) halo_iter3<TOP, true, true>(p, cp, k, st, it);
+    for (; it <= cp.it2_last; ++it) halo_iter3<TOP, false, true>(p, cp, k, st, it);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __grid_constant__ CUtensorMap tm_u0,
+                                                                        const __grid_constant__ CUtensorMap tm_rhs,
+                                                                        const __grid_constant__ Tb3Params p)
+{
+    using C = Cfg3;
+    constexpr int TX = C::TX, TY = C::TY, NS = C::NS;
+    constexpr uint32_t RB0 = C::RB0, RBR = C::RBR, RBU = C::RBU;
+    RNMF_DYNAMIC_SMEM(smem_raw);
+    const uint32_t sb = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t u0_0 = sb, rhs_0 = sb + C::RHS_OFF, u1_0 = sb + C::U1_OFF, u2_0 = sb + C::U2_OFF;
+    const uint32_t full0 = sb + C::BAR_OFF, empty0 = full0 + NS * 8, u1full0 = empty0 + NS * 8, u2full0 = u1full0 + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n0 = p.g.n[0], n1 = p.g.n[1], n2 = p.g.n[2];
+    const long long i0 = (long long)blockIdx.x * TX;
+    const long long j0 = (long long)blockIdx.y * TY;
+
+    // ---- which planes ----------------------------------------------------------------------------------
+    ChunkPlan cp;
+    {
+        const unsigned zc = p.ps.enabled ? peer_chunk_order(blockIdx.z, (unsigned)p.n_chunks) : blockIdx.z;
+        cp.k0 = p.m_begin + (long long)zc * p.chunk;
+        cp.k1 = cp.k0 + p.chunk < p.m_end ? cp.k0 + p.chunk : p.m_end;
+        // level 1 runs two planes, level 2 one plane beyond the output planes, unless a PHYSICAL z face is in the way (its ghost
+        // rule gives that level on the ghost-plane position); towards a slab neighbour the deep halo planes make them computable
+        const long long lo1 = cp.k0 - 2, lo2 = cp.k0 - 1, hi1 = cp.k1 + 1, hi2 = cp.k1;
+        cp.a1 = p.nb_lo || lo1 > 0 ? lo1 : 0;
+        const long long a2 = p.nb_lo || lo2 > 0 ? lo2 : 0;
+        const long long b1 = p.nb_hi || hi1 < n2 - 1 ? hi1 : n2 - 1;
+        const long long b2 = p.nb_hi || hi2 < n2 - 1 ? hi2 : n2 - 1;
+        cp.nL1 = (int)(b1 - cp.a1) + 1;
+        cp.it2_first = (int)(a2 - cp.a1) + 1;
+        cp.it2_last = (int)(b2 - cp.a1) + 1;
+        cp.it3_first = (int)(cp.k0 - cp.a1) + 2;
+        cp.it3_last = (int)(cp.k1 - 1 - cp.a1) + 2;
+        cp.it_zlo2 = (!p.nb_lo && a2 == 0) ? cp.it2_first : -1;
+        cp.it_zlo3 = (!p.nb_lo && cp.k0 == 0) ? cp.it3_first : -1;
+    }
+    const long long k0 = cp.k0, k1 = cp.k1, a1 = cp.a1;
+    const int nL1 = cp.nL1;
+    const int n_planes = nL1 + 2;                         // u0 planes a1-1 .. a1+nL1  (plane a1-1+idx <-> stage idx % NS)
+
+    // slab handshake roles of this CTA: its chunk reads the neighbour's planes and stores into the neighbour's buffer
+    const bool sync_lo = p.ps.enabled && p.nb_lo && k0 == 0;
+    const bool sync_hi = p.ps.enabled && p.nb_hi && k1 == n2;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, C::NCONS);
+        }
+        mbar_init(u1full0, C::NCONS);
+        mbar_init(u1full0 + 8, C::NCONS);
+        mbar_init(u2full0, C::NCONS);
+        mbar_init(u2full0 + 8, C::NCONS);
+        mbar_fence_init();
+        if (sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
+        if (sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
+    }
+    __syncthreads();
+
+    if (warp == TY + 3) {
+        // ------------------------------ producer warp ------------------------------
+        if (lane == 0) {
+            const int cx_u0 = (int)(p.g.xoff + p.g.ng + i0 - 4), cx_rhs = cx_u0 + 2;
+            const int cy_u0 = (int)(p.g.ng + j0 - 3), cy_rhs = cy_u0 + 1;
+            int cz = (int)(p.g.kg + a1 - 1) + p.zshift;
+            uint32_t s = 0, wrap = 0;
+            for (int idx = 0; idx < n_planes; ++idx) {
+                if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
+                const bool with_rhs = idx >= 1 && idx <= nL1;
+                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(C::U0_BYTES + (with_rhs ? C::RHS_BYTES : 0)));
+                tma_load_3d(u0_0 + s * C::U0_STAGE, &tm_u0, cx_u0, cy_u0, cz, full0 + 8 * s);
+                if (with_rhs) tma_load_3d(rhs_0 + s * C::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s);
+                ++cz;
+                if (++s == NS) { s = 0; ++wrap; }
+            }
+        }
+    } else if (warp == TY + 2) {
+        // ------------------------------ column warp ------------------------------
+        // lanes 0..15: left of the tile, lanes 16..31: right of it.  r = lane & 15 < 12: row j0+r, an INNER cell (x = i0-1 / i0+128:
+        // levels 1 and 2) and an OUTER cell (x = i0-2 / i0+129: level 1); r = 12 / 13: the diamond corner (inner x, j0-1) /
+        // (inner x, j0+12), level 1 only; r = 14, 15: idle
+        const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
+        const int side = lane >> 4, r = lane & 15;
+        const bool has_out = r < TY, corner = r == TY || r == TY + 1;
+        const int row = has_out ? r : (r == TY ? -1 : TY);             // tile row of the lane's cells (idle lanes: that of lane 13)
+        const int xin = side ? TX : -1, xout = side ? TX + 1 : -2;     // tile columns
+        const long long y = j0 + row;
+        const bool side_ok = side ? i0 + TX < n0 : i0 > 0;
+        const bool ok = (has_out || corner) && side_ok && y >= 0 && y < n1;
+        const bool ok2 = ok && has_out;                                // level 2 on the inner cell
+        // byte addresses: u0 cell (c, row) at ((row+3)*BX0 + c+4)*8; rhs at ((row+2)*BXR + c+2)*8; ring: row (row+2) of a u1 slot,
+        // row (row+1) of a u2 slot, x = i0+c at the even / odd half by parity, position (c+2)/2
+        const uint32_t hpi = u0_0 + (uint32_t)(((row + 3) * C::BX0 + xin + 4) * 8), hpo = u0_0 + (uint32_t)(((row + 3) * C::BX0 + xout + 4) * 8);
+        const uint32_t hri = rhs_0 + (uint32_t)(((row + 2) * C::BXR + xin + 2) * 8), hro = rhs_0 + (uint32_t)(((row + 2) * C::BXR + xout + 2) * 8);
+        auto ring_pos = [](int c) -> uint32_t { return (uint32_t)(((c + 2) >> 1) * 8 + (((c + 2) & 1) ? Cfg3::ODD : 0)); };
+        const uint32_t u1i = u1_0 + (uint32_t)(row + 2) * RBU + ring_pos(xin), u1o = u1_0 + (uint32_t)(row + 2) * RBU + ring_pos(xout);
+        const uint32_t u1t = u1_0 + (uint32_t)(row + 2) * RBU + ring_pos(side ? TX - 1 : 0);      // the tile cell next to the inner cell
+        const uint32_t u2i = u2_0 + (uint32_t)(row + 1) * RBU + ring_pos(xin);
+        const Face1 fy0 = make_face1(p.faces.f[2], true), fy1 = make_face1(p.faces.f[3], true);
+        const Face1 fz0 = make_face1(p.faces.f[4], true), fz1 = make_face1(p.faces.f[5], true);
+        const bool ylo = ok2 && fy0.on && y == 0, yhi = ok2 && fy1.on && y == n1 - 1;
+
+        mbar_wait(full0, 0);
+        double below_i = lds1(hpi), below_o = lds1(hpo);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        double cur_i = lds1(hpi + C::U0_STAGE), cur_o = lds1(hpo + C::U0_STAGE);
+        double u1lo_i = 0.0, u1c_i = 0.0, r1_i = 0.0;
+        Ring3 rg = { 1, 2, 0 };
+        for (int it = 0; it <= cp.it2_last; ++it) {
+            const bool l1 = it < nL1, l2 = it >= cp.it2_first;
+            const int j = it - cp.it2_first;
+            if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
+            if (it >= 1) mbar_wait(u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
+            if (j >= 1) mbar_wait(u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, rc_i = 0.0;
+            if (l2) {
+                const uint32_t so = (uint32_t)((it - 1) & 1) * C::U1_SLOT;
+                const double nn = lds1(u1i + so + RBU), ss = lds1(u1i + so - RBU);
+                const double tt = lds1(u1t + so), oo = lds1(u1o + so);
+                // E / W: left of the tile the tile cell is the E neighbour, right of it the W neighbour
+                P2 = part3(c0, c1, c2, r1_i, side ? oo : tt, side ? tt : oo, nn, ss);
+            }
+            if (l1) {
+                const uint32_t so = rg.sc * C::U0_STAGE, sn_ = rg.sn * C::U0_STAGE;
+                above_i = lds1(hpi + sn_); above_o = lds1(hpo + sn_);
+                const double n_i = lds1(hpi + so + RB0), s_i = lds1(hpi + so - RB0), e_i = lds1(hpi + so + 8), w_i = lds1(hpi + so - 8);
+                const double n_o = lds1(hpo + so + RB0), s_o = lds1(hpo + so - RB0), e_o = lds1(hpo + so + 8), w_o = lds1(hpo + so - 8);
+                rc_i = lds1(hri + rg.sc * C::RHS_STAGE);
+                const double rc_o = lds1(hro + rg.sc * C::RHS_STAGE);
+                u1n_i = upd3(c0, c1, c2, c3, rc_i, e_i, w_i, n_i, s_i, above_i, below_i);
+                const double u1n_o = upd3(c0, c1, c2, c3, rc_o, e_o, w_o, n_o, s_o, above_o, below_o);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * rg.sc);
+                const uint32_t so1 = (uint32_t)(it & 1) * C::U1_SLOT;
+                if (ok) sts1(u1i + so1, u1n_i);
+                if (ok2) sts1(u1o + so1, u1n_o);
+                // the y-face ghosts of u1 in the inner column (read by level 2 of this warp)
+                if (ylo) sts1(u1i + so1 - RBU, ghost1(fy0, u1n_i));
+                if (yhi) sts1(u1i + so1 + RBU, ghost1(fy1, u1n_i));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(u1full0 + 8 * (it & 1));
+            }
+            if (l2) {
+                double dn = u1lo_i, up = u1n_i;
+                if (it == cp.it_zlo2) dn = ghost1(fz0, u1c_i);
+                if (!l1) up = ghost1(fz1, u1c_i);
+                const double v = fin3(P2, c3, up, dn);
+                if (ok2) sts1(u2i + (uint32_t)(j & 1) * C::U2_SLOT, v);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(u2full0 + 8 * (j & 1));
+            }
+            if (l1) {
+                below_i = cur_i; below_o = cur_o;
+                cur_i = above_i; cur_o = above_o;
+                rg.advance();
+            }
+            u1lo_i = u1c_i; u1c_i = u1n_i; r1_i = rc_i;
+        }
+    } else if (warp >= TY) {
+        // ------------------------------ halo-row warps ------------------------------
+        const bool top = warp == TY + 1;
+        const int rowA = top ? TY : -2;
+        const bool rows_ok = top ? j0 + TY < n1 : j0 > 0;
+        const long long xa = i0 + 2 * lane, xb = xa + 64;
+        HaloK3 k;
+        k.ok_a = rows_ok && xa < n0;
+        k.ok_b = rows_ok && xb < n0;
+        k.pa = u0_0 + (uint32_t)(((rowA + 3) * C::BX0 + 4 + 2 * lane) * 8);
+        k.ra = rhs_0 + (uint32_t)(((rowA + 2) * C::BXR + 2 + 2 * lane) * 8);
+        k.u1a = u1_0 + (uint32_t)(rowA + 2) * RBU + (uint32_t)(8 * (1 + lane));
+        k.u2a = u2_0 + (uint32_t)((top ? TY : -1) + 1) * RBU + (uint32_t)(8 * (1 + lane));
+        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0; k.u2full0 = u2full0;
+        k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
+        k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
+        k.xlo = k.ok_a && k.fx0.on && xa == 0;
+        k.xhi = !k.fx1.on ? -1 : (k.ok_a && xa + 2 == n0) ? 0 : (k.ok_b && xb + 2 == n0) ? 1 : -1;
+        k.lane = lane;
+        HaloSt3 st;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        mbar_wait(full0, 0);
+        st.below[0] = lds2(k.pa); st.below[1] = lds2(k.pa + 512); st.below[2] = lds2(k.pa + RB0); st.below[3] = lds2(k.pa + RB0 + 512);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        st.cur[0] = lds2(k.pa + C::U0_STAGE); st.cur[1] = lds2(k.pa + C::U0_STAGE + 512);
+        st.cur[2] = lds2(k.pa + C::U0_STAGE + RB0); st.cur[3] = lds2(k.pa + C::U0_STAGE + RB0 + 512);
+        for (int h = 0; h < 2; ++h) { st.u1c_out[h] = zero2; st.u1lo_in[h] = zero2; st.u1c_in[h] = zero2; st.r1_in[h] = zero2; }
+        st.r = Ring3{ 1, 2, 0 };
+        if (top) halo_rows3<true>(p, cp, k, st);
+        else halo_rows3<false>(p, cp, k, st);
+    } else {
+        // ------------------------------ quad warps: rows j0+2*rp, j0+2*rp+1 x columns i0+64*xh .. +63 ------------------------------
+        const int xh = warp & 1, rp = warp >> 1;
+        const int ra = 2 * rp;                                  // tile row of row A
+        const long long jA = j0 + ra, jB = jA + 1;
+        const int t = 32 * xh + lane;                           // pair index within the tile row
+        const long long ia = i0 + 2 * t;
+        QuadK3 k;
+        k.ok = jA < n1 && ia < n0;
+        k.pa = u0_0 + (uint32_t)(((ra + 3) * C::BX0 + 4 + 2 * t) * 8);
+        k.ra = rhs_0 + (uint32_t)(((ra + 2) * C::BXR + 2 + 2 * t) * 8);
+        k.u1a = u1_0 + (uint32_t)(ra + 2) * RBU + (uint32_t)(8 * (1 + t));
+        k.u2a = u2_0 + (uint32_t)(ra + 1) * RBU + (uint32_t)(8 * (1 + t));
+        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0; k.u2full0 = u2full0;
+        k.pitch = p.g.pitch; k.plane_sz = p.g.plane;
+        // offset of the lane's first cell inside a grown xy plane (the neighbours' ghost / deep planes)
+        k.xy_off = p.g.xoff + (ia + p.g.ng) + k.pitch * (jA + p.g.ng);
+        k.lane = lane;
+        // ghost rules of the six faces (a z face with mode 0 is a slab neighbour)
+        k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
+        k.fy0 = make_face1(p.faces.f[2], true); k.fy1 = make_face1(p.faces.f[3], true);
+        k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
+        k.xlo = k.ok && k.fx0.on && ia == 0;
+        k.xhi = k.ok && k.fx1.on && ia + 2 == n0;
+        k.ylo = k.ok && k.fy0.on && jA == 0;
+        k.yhi = k.ok && k.fy1.on && jB == n1 - 1;
+        // u3 planes that also go to a neighbour: plane P is formed by iteration P - a1 + 2 of the chunk that holds it
+        auto it_of = [&](long long P, bool on) -> int { return on && P >= k0 && P < k1 ? (int)(P - a1) + 2 : -1; };
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            k.it_send[e] = it_of(e, p.peer_lo[e] != nullptr);
+            k.it_send[3 + e] = it_of(n2 - 1 - e, p.peer_hi[e] != nullptr);
+        }
+
+        QuadSt3 st;
+        const double2 zero2 = make_double2(0.0, 0.0);
+        mbar_wait(full0, 0);
+        st.below_a = lds2(k.pa); st.below_b = lds2(k.pa + RB0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+        st.cur_a = lds2(k.pa + C::U0_STAGE); st.cur_b = lds2(k.pa + C::U0_STAGE + RB0);
+        st.u1lo_a = zero2; st.u1lo_b = zero2; st.u1c_a = zero2; st.u1c_b = zero2;
+        st.u2lo_a = zero2; st.u2lo_b = zero2; st.u2c_a = zero2; st.u2c_b = zero2;
+        st.r1_a = zero2; st.r1_b = zero2; st.r2_a = zero2; st.r2_b = zero2;
+        st.oa = p.out + p.g.at(ia, jA, k0, 0);
+        st.r = Ring3{ 1, 2, 0 };
+
+        // warp-uniform: all 32 patches are whole and no y face touches them -> the steady iterations that meet neither a z face
+        // nor a neighbour's plane run without ghost code / store masks
+        const long long iw = i0 + 64 * xh;
+        const bool whole = jA < n1 && iw + 64 <= n0 && !(k.fy0.on && jA == 0) && !(k.fy1.on && jB == n1 - 1);
+        const int edge = !whole ? 2 : ((k.fx0.on && iw == 0) || (k.fx1.on && iw + 64 == n0)) ? 1 : 0;
+        // general code: the first level-3 iterations of the frame's first chunk (z-lo face: plane 0; neighbour: planes 0, 1, 2) and
+        // the last three of its last chunk when a neighbour sits behind the z-hi face
+        const int head = k0 == 0 ? (p.nb_lo ? (p.peer_lo[0] ? 3 : 0) : 1) : 0;
+        const int tail = (k1 == n2 && p.nb_hi && p.peer_hi[0]) ? 3 : 0;
+        const int it_end = cp.it3_last + 1;
+        int it = 0;
+        const int fast_begin = cp.it3_first + head < nL1 ? cp.it3_first + head : nL1;
+        const int fast_end = nL1 - tail > fast_begin ? nL1 - tail : fast_begin;
+        for (; it < fast_begin; ++it) quad_general3(p, cp, k, st, it);
+        if (edge == 0) quad_run3<0>(p, cp, k, st, it, fast_end);
+        else if (edge == 1) quad_run3<1>(p, cp, k, st, it, fast_end);
+        else quad_run3<2>(p, cp, k, st, it, fast_end);
+        for (; it < it_end; ++it) quad_general3(p, cp, k, st, it);
+    }
+    if (sync_lo || sync_hi) {
+        __syncthreads();                                       // every peer store of this CTA has been issued
+        if (threadIdx.x == 0) {
+            if (sync_lo) peer_publish(p.ps.done + 0, p.ps.target_lo, p.ps.sig_lo, p.ps.epoch + 1);
+            if (sync_hi) peer_publish(p.ps.done + 1, p.ps.target_hi, p.ps.sig_hi, p.ps.epoch + 1);
+        }
+    }
+}
+
+// chunk length: whole waves of one CTA per SM, each CTA paying chunk+5 plane iterations
+void plan_tb3(const SweepArgs& a, dim3& grid, int& chunk, int& n_chunks)
+{
+    const FrameGeom& g = a.g;
+    const long long tiles = ((g.n[0] + 127) / 128) * ((g.n[1] + Cfg3::TY - 1) / Cfg3::TY);
+    const long long span = a.k_end - a.k_begin;
+    long long best_c = 1, best_cost = -1;
+    static const int cand[] = { 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128 };
+    for (int c : cand) {
+        const long long cc = c > span ? span : c;
+        if (cc < 1) break;
+        const long long chunks = (span + cc - 1) / cc;
+        if (chunks <= 60000) {
+            const long long waves = (tiles * chunks + 147) / 148;
+            const long long cost = waves * (cc + 5);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_c = cc; }
+        }
+        if (c >= span) break;
+    }
+    if (a.chunk_override > 0) best_c = a.chunk_override > span ? span : a.chunk_override;
+    // slabs: the first / last chunk holds all three planes that go to the neighbour
+    if ((a.nb_lo || a.nb_hi) && best_c < 3) best_c = span < 3 ? span : 3;
+    if (best_c < 1) best_c = 1;
+    chunk = (int)best_c;
+    n_chunks = (int)((span + best_c - 1) / best_c);
+    // a last chunk of fewer than three planes would split the planes that go to the hi neighbour over two chunks: lengthen the chunks
+    while (a.nb_hi && n_chunks > 1 && span - (long long)(n_chunks - 1) * chunk < 3) {
+        chunk += 1;
+        n_chunks = (int)((span + chunk - 1) / chunk);
+    }
+    grid = dim3((unsigned)((g.n[0] + 127) / 128), (unsigned)((g.n[1] + Cfg3::TY - 1) / Cfg3::TY), (unsigned)n_chunks);
+}
+
+}  // namespace
+
+// frames the three-sweep kernel takes (the others run the two-sweep kernel)
+bool triple_sweep_applicable(const FrameGeom& g)
+{
+    return g.dim == 3 && g.ng == 1 && g.ncomp == 1 && g.n[0] % 2 == 0 && g.n[1] % 2 == 0;
+}
+
+int launch_jacobi_triple_sweep(const SweepArgs& a, cudaStream_t s)
+{
+    using C = Cfg3;
+    if (a.k_end <= a.k_begin) return 0;
+    if (!triple_sweep_applicable(a.g)) { rnmf_set_error("triple sweep: needs a 3D one-component frame with one ghost layer and even n0, n1"); return -1; }
+    if (a.hole_end > a.hole_begin) { rnmf_set_error("triple sweep: plane ranges with a hole are not supported"); return -1; }
+    if ((a.nb_lo || a.nb_hi) && (a.deep < 2 || a.k_begin != 0 || a.k_end != a.g.n[2] || a.g.n[2] < 6)) {
+        rnmf_set_error("triple sweep across slabs needs two deep halo planes, the whole slab and >= 6 planes");
+        return -1;
+    }
+    dim3 grid;
+    int chunk, n_chunks;
+    plan_tb3(a, grid, chunk, n_chunks);
+    CUtensorMap tm_u0, tm_rhs;
+    if (tma3d_encode_map_deep(&tm_u0, a.g, a.in, C::BX0, C::U0_ROWS, a.deep)) return -1;
+    if (tma3d_encode_map_deep(&tm_rhs, a.g, a.rhs, C::BXR, C::R_ROWS, a.deep)) return -1;
+    Tb3Params p;
+    p.g = a.g; p.out = a.out; p.c = a.c; p.faces = a.faces;
+    p.m_begin = a.k_begin; p.m_end = a.k_end; p.chunk = chunk; p.n_chunks = n_chunks;
+    p.nb_lo = a.nb_lo; p.nb_hi = a.nb_hi; p.zshift = a.deep;
+    for (int e = 0; e < 3; ++e) {
+        // the neighbours' ghost planes and the deep planes behind / in front of them
+        p.peer_lo[e] = a.peer_lo_plane ? a.peer_lo_plane + a.g.plane * e : nullptr;
+        p.peer_hi[e] = a.peer_hi_plane ? a.peer_hi_plane - a.g.plane * e : nullptr;
+    }
+    p.ps = a.ps;
+#ifndef RNMF_EMULATE
+    static PerDeviceOnce attr_set;
+    if (!attr_set.done()) {
+        if (cudaFuncSetAttribute(jacobi3d_tb3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) return -1;
+        attr_set.mark();
+    }
+#endif
+    RNMF_KERNEL_LAUNCH(jacobi3d_tb3_kernel, grid, C::THREADS, C::SMEM, s, tm_u0, tm_rhs, p);
+    return 1;
+}
+
+// CTAs per boundary side (tiles across a z-plane): the first / last chunk of the launch takes part in the handshake
+int triple_sweep_boundary_ctas(const SweepArgs& a)
+{
+    dim3 grid;
+    int chunk, n_chunks;
+    plan_tb3(a, grid, chunk, n_chunks);
+    return (int)(grid.x * grid.y);
+}

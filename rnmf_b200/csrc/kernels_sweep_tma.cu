@@ -286,11 +286,11 @@ static std::mutex g_map_mutex;      // contexts on different host threads share 
 
 int encode_map_uncached(CUtensorMap* tm, const double* base, long long pitch, long long g1, long long planes, long long plane_stride, int bx, int by);
 
-// deep = 1: the buffer has one extra plane in front of the z-lo ghost plane and one behind the z-hi ghost plane (capi.cu)
+// deep > 0: the buffer has `deep` extra planes in front of the z-lo ghost plane and behind the z-hi ghost plane (capi.cu)
 int encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep)
 {
-    const double* b0 = deep ? base - g.plane : base;
-    const long long planes = g.G[2] * g.ncomp + (deep ? 2 : 0);
+    const double* b0 = base - (long long)deep * g.plane;
+    const long long planes = g.G[2] * g.ncomp + 2 * deep;
     const MapKey k = { b0, g.pitch, g.G[1], planes, bx, by };
     std::lock_guard<std::mutex> lock(g_map_mutex);
     for (auto& sl : g_map_cache)

@@ -198,8 +198,8 @@ __device__ __forceinline__ void sstore4(uint32_t a, const double2& va, const dou
 
 // tensor map of a frame buffer with a (bx, by, 1) box (kernels_sweep_tma.cu; cached per buffer/geometry/box)
 int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by);
-// same; deep = 1: the tensor starts one plane BEFORE `base` and has G2 + 2 planes (the deep halo planes of the buffer), so a
-// box at z coordinate c covers grown plane c - 1
+// same; deep > 0: the tensor starts `deep` planes BEFORE `base` and has G2 + 2*deep planes (the deep halo planes of the buffer),
+// so a box at z coordinate c covers grown plane c - deep
 int tma3d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep);
 // tensor map of a 2D frame buffer with a (bx, 1) box (kernels_sweep2d_tma.cu)
 int tma2d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx);

@@ -47,8 +47,8 @@ int tma3d_encode_map(CUtensorMap* tm, const FrameGeom& g, const double* base, in
 int tma3d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* base, int bx, int by, int deep)
 {
     emu::Map m;
-    m.base = deep ? base - g.plane : base; m.rank = 3;
-    m.dims[0] = (unsigned long long)g.pitch; m.dims[1] = (unsigned long long)g.G[1]; m.dims[2] = (unsigned long long)(g.G[2] * g.ncomp + (deep ? 2 : 0));
+    m.base = base - (long long)deep * g.plane; m.rank = 3;
+    m.dims[0] = (unsigned long long)g.pitch; m.dims[1] = (unsigned long long)g.G[1]; m.dims[2] = (unsigned long long)(g.G[2] * g.ncomp + 2 * deep);
     m.stride[0] = 1; m.stride[1] = (unsigned long long)g.pitch; m.stride[2] = (unsigned long long)g.plane;
     m.box[0] = (unsigned)bx; m.box[1] = (unsigned)by; m.box[2] = 1;
     emu::encode(tm, m);
@@ -77,6 +77,7 @@ int tma2d_encode_map_deep(CUtensorMap* tm, const FrameGeom& g, const double* bas
 }
 
 #include "../../rnmf_b200/csrc/kernels_sweep_tb2.cu"
+#include "../../rnmf_b200/csrc/kernels_sweep_tb3.cu"
 #include "../../rnmf_b200/csrc/kernels_sweep2d_tb2.cu"
 #include "../../rnmf_b200/csrc/kernels_sweep2d_tbk.cu"
 
@@ -85,7 +86,7 @@ namespace {
 constexpr long long kTail = 64 + 256;       // tail pad + guard band of the library's buffers (capi.cu)
 
 // a frame as the library allocates it (capi.cu: alloc_buffer): [deep plane][grown frame][deep plane][tail pad + guard band];
-// 3D: one deep plane either side, 2D: three deep rows.  d(b) = the frame pointer (lo ghost slice) of ping-pong buffer b.
+// 3D: two deep planes either side, 2D: three deep rows.  d(b) = the frame pointer (lo ghost slice) of ping-pong buffer b.
 struct Frame {
     FrameGeom g;
     long long deep = 0;             // doubles
@@ -124,8 +125,8 @@ void init_frame(Frame& f, int dim, const long long* n, const double* dx, const d
     const int64_t n64[3] = { n[0], n[1], dim == 3 ? n[2] : 1 };
     const double lo[3] = { 0, 0, 0 };
     make_geom(f.g, dim, n64, lo, dx, 1, 1);
-    f.deep_slices = dim == 3 ? 1 : 3;
-    f.deep = dim == 3 ? f.g.plane : 3 * f.g.pitch;
+    f.deep_slices = dim == 3 ? 2 : 3;
+    f.deep = dim == 3 ? 2 * f.g.plane : 3 * f.g.pitch;
     const size_t len = (size_t)(f.deep + f.g.total + f.deep + kTail);
     // poison what is not data: padding columns, the deep planes, the tail
     f.buf[0].assign(len, kPoison[0]); f.buf[1].assign(len, kPoison[1]); f.rhs_buf.assign(len, kPoison[2]);
@@ -276,7 +277,9 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
     for (int it = 0; it < n_pairs; ++it) {
         a.in = f.d(f.cur);
         a.out = f.d(f.cur ^ 1);
-        if (dim == 3) {
+        if (dim == 3 && variant == 3) {
+            if (launch_jacobi_triple_sweep(a, nullptr) < 0) return -1;          // n_pairs launches of three sweeps each
+        } else if (dim == 3) {
             if (launch_jacobi_double_sweep(a, nullptr) < 0) return -1;
         } else if (variant == 30) {
             if (launch_jacobi_double_sweep_2d(a, nullptr) < 0) return -1;
@@ -323,7 +326,7 @@ int emu_skewed_double_sweeps(const long long* n, const double* dx, const int* fa
     t.variant = variant;
     t.chunk_override = chunk;
     t.rhs = f.rhs();
-    t.deep = 1;
+    t.deep = 2;
     const long long n2 = g.n[2];
     for (int ch = 0; ch < n_chunks; ++ch) {
         // "upload" of chunk ch: grown planes [p0, p1) of psi (+ its ghost shell into the partner buffer) and of rhs
@@ -371,7 +374,7 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
     t.variant = variant;
     t.chunk_override = chunk;
     t.rhs = f.rhs();
-    t.deep = 1;
+    t.deep = 2;
     const long long n2 = g.n[2], G0 = g.G[0], G1 = g.G[1];
     std::vector<double> dense((size_t)(G0 * G1 * g.G[2]));
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -405,10 +408,10 @@ int emu_skewed_tail_double_sweeps(const long long* n, const double* dx, const in
 int emu_sweeps_slabs(int dim, const long long* n, const double* dx, const int* face_kind, const double* face_value, const double* coef4,
                      const double* psi_dense, const double* rhs_dense, double* out_dense, int variant, int chunk, int n_launches, int nranks)
 {
-    (void)variant;
     g_deadlocks = 0;
     const int D = dim - 1;
-    const int depth = dim == 3 ? 2 : 4;
+    const bool triple = dim == 3 && variant == 3;
+    const int depth = dim == 3 ? (triple ? 3 : 2) : 4;
     const long long G0 = n[0] + 2, slice_dense = dim == 3 ? G0 * (n[1] + 2) : G0;
     std::vector<Frame> fr(nranks);
     std::vector<long long> start(nranks), count(nranks);
@@ -477,7 +480,7 @@ int emu_sweeps_slabs(int dim, const long long* n, const double* dx, const int* f
                     a.ps.wait_hi = &flags[r].w[1];
                     a.ps.sig_hi = &flags[r + 1].w[0];
                 }
-                const unsigned long long tiles = (unsigned long long)(dim == 3 ? double_sweep_boundary_ctas(a) : multi_sweep_2d_boundary_ctas(a));
+                const unsigned long long tiles = (unsigned long long)(triple ? triple_sweep_boundary_ctas(a) : dim == 3 ? double_sweep_boundary_ctas(a) : multi_sweep_2d_boundary_ctas(a));
                 a.ps.enabled = 1;
                 a.ps.done = &flags[r].w[3];
                 if (has_lo) done[0] += tiles;
@@ -486,7 +489,8 @@ int emu_sweeps_slabs(int dim, const long long* n, const double* dx, const int* f
                 a.ps.epoch = epoch;
                 a.ps.status = &flags[r].w[2];
                 epoch += 1;
-                if (dim == 3) launch_jacobi_double_sweep(a, nullptr);
+                if (triple) launch_jacobi_triple_sweep(a, nullptr);
+                else if (dim == 3) launch_jacobi_double_sweep(a, nullptr);
                 else launch_jacobi_multi_sweep_2d(a, nullptr);
                 f.cur ^= 1;
             }
@@ -560,7 +564,7 @@ int emu_skewed_double_sweeps_slabs(const long long* n, const double* dx, const i
             t.fuse_fill = 1;
             t.chunk_override = chunk;
             t.rhs = f.rhs();
-            t.deep = 1;
+            t.deep = 2;
             // ---- phase 1: chunks arrive, bands run (clipped next to the neighbours) ----
             for (int ch = 0; ch < n_chunks; ++ch) {
                 const long long p0 = ch == 0 ? 0 : n2 * ch / n_chunks + 1, p1 = ch == n_chunks - 1 ? g.G[2] : n2 * (ch + 1) / n_chunks + 1;

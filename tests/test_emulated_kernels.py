@@ -29,7 +29,7 @@ NEUMANN_2D = ([("neumann", 0.3), ("neumann", -0.2)], [("neumann", 0.4), ("neuman
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC] + [os.path.join(ROOT, "rnmf_b200", "csrc", f) for f in
-                    ("kernels_sweep_tb2.cu", "kernels_sweep2d_tb2.cu", "kernels_sweep2d_tbk.cu", "tma_util.cuh", "common.cuh")] + [os.path.join(ROOT, "tests", "emu", "emu_cuda.hpp")]
+                    ("kernels_sweep_tb2.cu", "kernels_sweep_tb3.cu", "kernels_sweep2d_tb2.cu", "kernels_sweep2d_tbk.cu", "tma_util.cuh", "common.cuh")] + [os.path.join(ROOT, "tests", "emu", "emu_cuda.hpp")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-pthread",
@@ -92,6 +92,34 @@ def test_3d_double_sweep_source_on_the_emulator(emu, n, hi, spec, pairs, chunk):
     rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, pairs)
     assert rc == 0, "a barrier wait timed out (deadlock) or the launch failed"
     np.testing.assert_array_equal(out, want)      # valid cells, face ghosts, and the untouched edges / corners
+
+
+@pytest.mark.parametrize("n,hi,spec,launches,chunk", [
+    ([20, 8, 5], [1.0, 2.0, 3.0], MIXED_3D, 1, 0),               # one tile, one chunk: both z faces in the same chunk
+    ([130, 14, 4], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 0),           # one pair / one row pair past a tile edge; two launches (ping-pong)
+    ([66, 26, 7], [66.0, 52.0, 21.0], MIXED_3D, 1, 2),           # x-hi face inside the x-half 1 warp; 3 y tiles, 4 z chunks
+    ([64, 24, 3], [1.0, 2.0, 3.0], MIXED_3D, 1, 0),              # x-hi face at the edge of the x-half 0 warp; n1 = two full tiles
+    ([30, 12, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 0),              # a single plane: every level meets both z faces
+    ([2, 2, 2], [1.0, 1.0, 1.0], NEUMANN_3D, 2, 0),
+    ([2, 2, 1], [1.0, 1.0, 1.0], MIXED_3D, 1, 0),
+    ([40, 10, 6], [1.0, 2.0, 3.0], MIXED_3D, 1, 1),              # one-plane chunks: every chunk clips some level at a face or starts next to one
+    ([40, 10, 7], [1.0, 2.0, 3.0], NEUMANN_3D, 1, 3),
+    # interior-specialised steady loop: warps whose 2 x 64 patch touches no x / y face
+    ([400, 30, 9], [4.0, 2.0, 3.0], MIXED_3D, 1, 0),
+    ([386, 14, 5], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 2),           # the last tile holds one pair; two launches; 2-plane chunks
+    ([384, 28, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 4),             # x-hi face exactly at a tile edge
+    ([192, 26, 9], [1.0, 2.0, 3.0], MIXED_3D, 1, 3),             # x-hi face at the edge of an x-half 0 warp
+    ([200, 30, 20], [1.0, 2.0, 3.0], MIXED_3D, 1, 7),            # several steady iterations per chunk
+    ([260, 14, 40], [1.0, 2.0, 3.0], NEUMANN_3D, 1, 20),         # two 20-plane chunks: the second starts at a chunk boundary (a1 = k0 - 2)
+])
+def test_3d_triple_sweep_source_on_the_emulator(emu, n, hi, spec, launches, chunk):
+    """Three sweeps per pass (kernels_sweep_tb3.cu; frames with even n0, n1): u after `launches` launches == 3*launches oracle sweeps,
+    valid cells, face ghosts and the untouched edges / corners, bit for bit."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 3 * launches, seed=51)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 3, chunk, launches)
+    assert rc == 0, "a barrier wait timed out (deadlock), an access fault, or the launch failed"
+    np.testing.assert_array_equal(out, want)
 
 
 @pytest.mark.parametrize("n,hi,spec,pairs,chunk", [
@@ -179,6 +207,38 @@ def test_slab_handshake_of_the_double_sweep_on_the_emulator(emu, n, hi, spec, pa
     g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 2 * pairs, seed=43)
     out = psi.copy()
     rc = emu.emu_sweeps_slabs(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 0, chunk, pairs, nranks)
+    assert rc == 0, "deadlock / handshake timeout"
+    np.testing.assert_array_equal(out, want)
+
+
+@settings(max_examples=16, deadline=None, derandomize=True)
+@given(st.integers(1, 200), st.integers(1, 15), st.integers(1, 9), st.integers(0, 9), st.booleans())
+def test_3d_triple_sweep_random_shapes_on_the_emulator(emu, h0, h1, n2, chunk, neumann):
+    """Random (even n0, n1) frame shapes / chunk lengths for the three-sweep kernel."""
+    n0, n1 = 2 * h0, 2 * h1
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup([n0, n1, n2], [1.0, 2.0, 3.0], NEUMANN_3D if neumann else MIXED_3D, 3,
+                                                          seed=n0 * 131 + n1 * 17 + n2)
+    out = np.zeros_like(psi)
+    rc = emu.emu_double_sweeps(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 3, min(chunk, n2), 1)
+    assert rc == 0
+    np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("n,hi,spec,launches,nranks,chunk", [
+    ([20, 8, 12], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0),           # two 6-plane slabs (the minimum): one chunk serves the neighbour and the face
+    ([130, 14, 20], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0),         # uneven split (6, 6, 8); the middle rank has both neighbours
+    ([20, 14, 24], [1.0, 2.0, 3.0], NEUMANN_3D, 3, 4, 3),        # 6-plane slabs, three-plane chunks: first and last chunk differ
+    ([20, 14, 24], [1.0, 2.0, 3.0], MIXED_3D, 2, 4, 6),          # 6-plane slabs, one chunk: the same CTA serves both neighbours
+    ([390, 16, 21], [1.0, 2.0, 3.0], MIXED_3D, 2, 3, 0),         # interior-specialised loop between the planes that travel
+    ([130, 14, 22], [1.0, 2.0, 3.0], NEUMANN_3D, 2, 3, 5),       # chunk lengths that leave a short last chunk (the planner lengthens the chunks)
+    ([200, 26, 60], [1.0, 2.0, 3.0], MIXED_3D, 2, 2, 0),         # 30-plane slabs in one chunk
+])
+def test_slab_handshake_of_the_triple_sweep_on_the_emulator(emu, n, hi, spec, launches, nranks, chunk):
+    """z-slabs, three sweeps per launch: each rank starts with its neighbours' three boundary planes in its ghost + two deep planes
+    (rhs: two) and stores u3 of its own three boundary planes into the neighbours' planes under the one-epoch-per-launch handshake."""
+    g, psi, rhs, want, kinds, vals, dx, nn, coef = _setup(n, hi, spec, 3 * launches, seed=53)
+    out = psi.copy()
+    rc = emu.emu_sweeps_slabs(3, nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), 3, chunk, launches, nranks)
     assert rc == 0, "deadlock / handshake timeout"
     np.testing.assert_array_equal(out, want)
 
