@@ -83,11 +83,13 @@ struct Cfg3 {
     static_assert(U0_BYTES % 16 == 0 && RHS_BYTES % 16 == 0 && (BX0 * 8) % 16 == 0 && (BXR * 8) % 16 == 0, "TMA box rows are multiples of 16 bytes");
 };
 
-// first two terms of poisson.rs:83-88 (the z term is added last: same association as upd3)
-__device__ __forceinline__ double part3(double c0, double c1, double c2, double r, double e, double w, double n, double s)
+// first two terms of poisson.rs:83-88 on q = c0*rhs (rounded once per cell and plane and reused by all three levels -- the same
+// product, so nothing changes in the result); the z term is added last (fin3): same association as upd3
+__device__ __forceinline__ double part3(double q, double c1, double c2, double e, double w, double n, double s)
 {
-    return __dadd_rn(__dadd_rn(__dmul_rn(c0, r), __dmul_rn(c1, __dadd_rn(e, w))), __dmul_rn(c2, __dadd_rn(n, s)));
+    return __dadd_rn(__dadd_rn(q, __dmul_rn(c1, __dadd_rn(e, w))), __dmul_rn(c2, __dadd_rn(n, s)));
 }
+__device__ __forceinline__ double2 mulc2(double c, const double2& v) { return make_double2(__dmul_rn(c, v.x), __dmul_rn(c, v.y)); }
 __device__ __forceinline__ double fin3(double part, double c3, double u, double d) { return __dadd_rn(part, __dmul_rn(c3, __dadd_rn(u, d))); }
 __device__ __forceinline__ double2 fin3(const double2& part, double c3, const double2& u, const double2& d)
 {
@@ -134,7 +136,7 @@ struct QuadSt3 {
     double2 below_a, below_b, cur_a, cur_b;      // u0 of planes a1+it-1, a1+it
     double2 u1lo_a, u1lo_b, u1c_a, u1c_b;        // u1 of planes a1+it-2, a1+it-1
     double2 u2lo_a, u2lo_b, u2c_a, u2c_b;        // u2 of planes a1+it-3, a1+it-2
-    double2 r1_a, r1_b, r2_a, r2_b;              // rhs of planes a1+it-1, a1+it-2
+    double2 q1_a, q1_b, q2_a, q2_b;              // c0*rhs of planes a1+it-1, a1+it-2
     double* oa;                                  // where u3 of plane a1+it-2 goes
     Ring3 r;
 };
@@ -187,7 +189,7 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     constexpr uint32_t RB0 = C::RB0, RBR = C::RBR, RBU = C::RBU;
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
-    double2 above_a = zero2, above_b = zero2, rc_a = zero2, rc_b = zero2;
+    double2 above_a = zero2, above_b = zero2, qc_a = zero2, qc_b = zero2;
     double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2, P2_a = zero2, P2_b = zero2, P3_a = zero2, P3_b = zero2;
     const int j = it - cp.it2_first;                       // level 2 forms its j-th plane now (slot j & 1); level 3 reads plane j-1
     const uint32_t sc = st.r.sc, sn = st.r.sn;
@@ -195,47 +197,60 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     // ---- wait phase ----------------------------------------------------------------------------------
     if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);                                            // u0 plane a1+it+1
     if ((L1 || L2) && it >= 1) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);   // u1 plane a1+it-1 complete, plane a1+it-2 no longer read
-    if (j >= 1) mbar_wait(k.u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);     // u2 plane a1+it-2 complete, the one before no longer read
+    // u2 plane a1+it-2 complete and the one before no longer read; it also says that every warp has finished level 2 of the
+    // previous iteration, i.e. its loads from the u1 slot that level 1 overwrites below
+    if (j >= 1) mbar_wait(k.u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
 
     // ---- level 3, x/y part: plane a1+it-2 from the u2 ring ---------------------------------------------
     if (L3) {
         const uint32_t b = k.u2a + (uint32_t)((j - 1) & 1) * C::U2_SLOT;
-        const double2 n_b = ldp(b + 2 * RBU), s_a = ldp(b - RBU);
-        const double w_a = lds1(b + kW), e_a = lds1(b + kE), w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
-        P3_a.x = part3(c0, c1, c2, st.r2_a.x, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
-        P3_a.y = part3(c0, c1, c2, st.r2_a.y, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y);
-        P3_b.x = part3(c0, c1, c2, st.r2_b.x, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x);
-        P3_b.y = part3(c0, c1, c2, st.r2_b.y, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y);
+        const double2 s_a = ldp(b - RBU);
+        const double w_a = lds1(b + kW), e_a = lds1(b + kE);
+        P3_a.x = part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
+        P3_a.y = part3(st.q2_a.y, c1, c2, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y);
+        const double2 n_b = ldp(b + 2 * RBU);
+        const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+        P3_b.x = part3(st.q2_b.x, c1, c2, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x);
+        P3_b.y = part3(st.q2_b.y, c1, c2, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y);
     }
-    // ---- level 2, x/y part: plane a1+it-1 from the u1 ring ---------------------------------------------
-    if (L2) {
-        const uint32_t b = k.u1a + (uint32_t)((it - 1) & 1) * C::U1_SLOT;
-        const double2 n_b = ldp(b + 2 * RBU), s_a = ldp(b - RBU);
-        const double w_a = lds1(b + kW), e_a = lds1(b + kE), w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
-        P2_a.x = part3(c0, c1, c2, st.r1_a.x, st.u1c_a.y, w_a, st.u1c_b.x, s_a.x);
-        P2_a.y = part3(c0, c1, c2, st.r1_a.y, e_a, st.u1c_a.x, st.u1c_b.y, s_a.y);
-        P2_b.x = part3(c0, c1, c2, st.r1_b.x, st.u1c_b.y, w_b, n_b.x, st.u1c_a.x);
-        P2_b.y = part3(c0, c1, c2, st.r1_b.y, e_b, st.u1c_b.x, n_b.y, st.u1c_a.y);
-    }
-    // ---- level 1: u1 of plane a1+it ----------------------------------------------------------------------
+    // ---- level 1: u1 of plane a1+it (row A, then row B: fewer values in flight at a time) --------------------
     if (L1) {
         const uint32_t pn = k.pa + sn * C::U0_STAGE, pc = k.pa + sc * C::U0_STAGE, pr = k.ra + sc * C::RHS_STAGE;
-        above_a = lds2(pn); above_b = lds2(pn + RB0);
-        const double2 n_b = lds2(pc + 2 * RB0), s_a = lds2(pc - RB0);
-        rc_a = lds2(pr); rc_b = lds2(pr + RBR);
-        const double w_a = lds1(pc - 8), e_a = lds1(pc + 16), w_b = lds1(pc + RB0 - 8), e_b = lds1(pc + RB0 + 16);
-        u1n_a.x = upd3(c0, c1, c2, c3, rc_a.x, st.cur_a.y, w_a, st.cur_b.x, s_a.x, above_a.x, st.below_a.x);
-        u1n_a.y = upd3(c0, c1, c2, c3, rc_a.y, e_a, st.cur_a.x, st.cur_b.y, s_a.y, above_a.y, st.below_a.y);
-        u1n_b.x = upd3(c0, c1, c2, c3, rc_b.x, st.cur_b.y, w_b, n_b.x, st.cur_a.x, above_b.x, st.below_b.x);
-        u1n_b.y = upd3(c0, c1, c2, c3, rc_b.y, e_b, st.cur_b.x, n_b.y, st.cur_a.y, above_b.y, st.below_b.y);
+        {
+            qc_a = mulc2(c0, lds2(pr));
+            const double2 s_a = lds2(pc - RB0);
+            const double w_a = lds1(pc - 8), e_a = lds1(pc + 16);
+            above_a = lds2(pn);
+            u1n_a.x = fin3(part3(qc_a.x, c1, c2, st.cur_a.y, w_a, st.cur_b.x, s_a.x), c3, above_a.x, st.below_a.x);
+            u1n_a.y = fin3(part3(qc_a.y, c1, c2, e_a, st.cur_a.x, st.cur_b.y, s_a.y), c3, above_a.y, st.below_a.y);
+        }
+        {
+            qc_b = mulc2(c0, lds2(pr + RBR));
+            const double2 n_b = lds2(pc + 2 * RB0);
+            const double w_b = lds1(pc + RB0 - 8), e_b = lds1(pc + RB0 + 16);
+            above_b = lds2(pn + RB0);
+            u1n_b.x = fin3(part3(qc_b.x, c1, c2, st.cur_b.y, w_b, n_b.x, st.cur_a.x), c3, above_b.x, st.below_b.x);
+            u1n_b.y = fin3(part3(qc_b.y, c1, c2, e_b, st.cur_b.x, n_b.y, st.cur_a.y), c3, above_b.y, st.below_b.y);
+        }
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);                  // this warp is done with the stage of plane a1+it
         ring_store<EDGE>(k, k.u1a + (uint32_t)(it & 1) * C::U1_SLOT, u1n_a, u1n_b);
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
     }
-    // ---- level 2, z part: u2 of plane a1+it-1 ---------------------------------------------------------------
+    // ---- level 2: u2 of plane a1+it-1; x/y part from the u1 ring (AFTER this warp's arrival for u1 plane a1+it: the slot these
+    // loads read is overwritten by level 1 of the next iteration, which every warp starts behind the u2full wait for THIS
+    // iteration's level 2 -- see the wait phase), then the z part from registers --------------------------------------------
     if (L2) {
+        const uint32_t b = k.u1a + (uint32_t)((it - 1) & 1) * C::U1_SLOT;
+        const double2 s_a = ldp(b - RBU);
+        const double w_a = lds1(b + kW), e_a = lds1(b + kE);
+        P2_a.x = part3(st.q1_a.x, c1, c2, st.u1c_a.y, w_a, st.u1c_b.x, s_a.x);
+        P2_a.y = part3(st.q1_a.y, c1, c2, e_a, st.u1c_a.x, st.u1c_b.y, s_a.y);
+        const double2 n_b = ldp(b + 2 * RBU);
+        const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+        P2_b.x = part3(st.q1_b.x, c1, c2, st.u1c_b.y, w_b, n_b.x, st.u1c_a.x);
+        P2_b.y = part3(st.q1_b.y, c1, c2, e_b, st.u1c_b.x, n_b.y, st.u1c_a.y);
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
         if (EDGE == 2 && it == cp.it_zlo2) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
         if (!L1) { up_a = ghost1(k.fz1, st.u1c_a); up_b = ghost1(k.fz1, st.u1c_b); }         // the frame's last plane next to a physical z-hi face
@@ -278,8 +293,8 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     st.u2c_a = u2n_a; st.u2c_b = u2n_b;
     st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
     st.u1c_a = u1n_a; st.u1c_b = u1n_b;
-    st.r2_a = st.r1_a; st.r2_b = st.r1_b;
-    st.r1_a = rc_a; st.r1_b = rc_b;
+    st.q2_a = st.q1_a; st.q2_b = st.q1_b;
+    st.q1_a = qc_a; st.q1_b = qc_b;
 }
 
 // an iteration with the general code, whatever levels are active in it
@@ -323,7 +338,7 @@ struct HaloSt3 {
     double2 below[4], cur[4];            // u0: Aa, Ab, Ba, Bb
     double2 u1c_out[2];                  // u1 of plane a1+it-1, the outer row (pairs a, b)
     double2 u1lo_in[2], u1c_in[2];       // u1 of planes a1+it-2, a1+it-1, the inner row
-    double2 r1_in[2];                    // rhs of plane a1+it-1, the inner row
+    double2 q1_in[2];                    // c0*rhs of plane a1+it-1, the inner row
     Ring3 r;
 };
 
@@ -335,7 +350,7 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
     constexpr int IN = TOP ? 0 : 1, OUT = TOP ? 1 : 0;      // row index (A = 0, B = 1) of the row next to the tile / the outer row
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
-    double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, rc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
+    double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, qc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
     const int j = it - cp.it2_first;
     const uint32_t sc = st.r.sc, sn = st.r.sn;
 
@@ -352,8 +367,8 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
             const double2 t = ldp(bt + 256 * h);
             const double w = lds1(b + 256 * h + kW), e = lds1(b + 256 * h + kE);
             const double2 n = TOP ? st.u1c_out[h] : t, s = TOP ? t : st.u1c_out[h];
-            P2[h].x = part3(c0, c1, c2, st.r1_in[h].x, st.u1c_in[h].y, w, n.x, s.x);
-            P2[h].y = part3(c0, c1, c2, st.r1_in[h].y, e, st.u1c_in[h].x, n.y, s.y);
+            P2[h].x = part3(st.q1_in[h].x, c1, c2, st.u1c_in[h].y, w, n.x, s.x);
+            P2[h].y = part3(st.q1_in[h].y, c1, c2, e, st.u1c_in[h].x, n.y, s.y);
         }
     }
     if (L1) {
@@ -363,14 +378,14 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
             const uint32_t o = 512 * h;
             above[h] = lds2(pn + o); above[2 + h] = lds2(pn + RB0 + o);
             const double2 s_a = lds2(pc - RB0 + o), n_b = lds2(pc + 2 * RB0 + o);
-            const double2 r_a = lds2(pr + o), r_b = lds2(pr + RBR + o);
+            const double2 q_a = mulc2(c0, lds2(pr + o)), q_b = mulc2(c0, lds2(pr + RBR + o));
             const double w_a = lds1(pc + o - 8), e_a = lds1(pc + o + 16), w_b = lds1(pc + RB0 + o - 8), e_b = lds1(pc + RB0 + o + 16);
             const double2 ca = st.cur[h], cb = st.cur[2 + h];
-            u1n[h].x = upd3(c0, c1, c2, c3, r_a.x, ca.y, w_a, cb.x, s_a.x, above[h].x, st.below[h].x);
-            u1n[h].y = upd3(c0, c1, c2, c3, r_a.y, e_a, ca.x, cb.y, s_a.y, above[h].y, st.below[h].y);
-            u1n[2 + h].x = upd3(c0, c1, c2, c3, r_b.x, cb.y, w_b, n_b.x, ca.x, above[2 + h].x, st.below[2 + h].x);
-            u1n[2 + h].y = upd3(c0, c1, c2, c3, r_b.y, e_b, cb.x, n_b.y, ca.y, above[2 + h].y, st.below[2 + h].y);
-            rc_in[h] = IN ? r_b : r_a;
+            u1n[h].x = fin3(part3(q_a.x, c1, c2, ca.y, w_a, cb.x, s_a.x), c3, above[h].x, st.below[h].x);
+            u1n[h].y = fin3(part3(q_a.y, c1, c2, e_a, ca.x, cb.y, s_a.y), c3, above[h].y, st.below[h].y);
+            u1n[2 + h].x = fin3(part3(q_b.x, c1, c2, cb.y, w_b, n_b.x, ca.x), c3, above[2 + h].x, st.below[2 + h].x);
+            u1n[2 + h].y = fin3(part3(q_b.y, c1, c2, e_b, cb.x, n_b.y, ca.y), c3, above[2 + h].y, st.below[2 + h].y);
+            qc_in[h] = IN ? q_b : q_a;
         }
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);
@@ -406,7 +421,7 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
         st.u1lo_in[h] = st.u1c_in[h];
         st.u1c_in[h] = u1n[2 * IN + h];
         st.u1c_out[h] = u1n[2 * OUT + h];
-        st.r1_in[h] = rc_in[h];
+        st.q1_in[h] = qc_in[h];
     }
 }
 
@@ -533,7 +548,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         if (lane == 0) mbar_arrive(empty0);
         mbar_wait(full0 + 8, 0);
         double cur_i = lds1(hpi + C::U0_STAGE), cur_o = lds1(hpo + C::U0_STAGE);
-        double u1lo_i = 0.0, u1c_i = 0.0, r1_i = 0.0;
+        double u1lo_i = 0.0, u1c_i = 0.0, q1_i = 0.0;
         Ring3 rg = { 1, 2, 0 };
         for (int it = 0; it <= cp.it2_last; ++it) {
             const bool l1 = it < nL1, l2 = it >= cp.it2_first;
@@ -541,23 +556,23 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
             if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
             if (it >= 1) mbar_wait(u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
             if (j >= 1) mbar_wait(u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
-            double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, rc_i = 0.0;
+            double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, qc_i = 0.0;
             if (l2) {
                 const uint32_t so = (uint32_t)((it - 1) & 1) * C::U1_SLOT;
                 const double nn = lds1(u1i + so + RBU), ss = lds1(u1i + so - RBU);
                 const double tt = lds1(u1t + so), oo = lds1(u1o + so);
                 // E / W: left of the tile the tile cell is the E neighbour, right of it the W neighbour
-                P2 = part3(c0, c1, c2, r1_i, side ? oo : tt, side ? tt : oo, nn, ss);
+                P2 = part3(q1_i, c1, c2, side ? oo : tt, side ? tt : oo, nn, ss);
             }
             if (l1) {
                 const uint32_t so = rg.sc * C::U0_STAGE, sn_ = rg.sn * C::U0_STAGE;
                 above_i = lds1(hpi + sn_); above_o = lds1(hpo + sn_);
                 const double n_i = lds1(hpi + so + RB0), s_i = lds1(hpi + so - RB0), e_i = lds1(hpi + so + 8), w_i = lds1(hpi + so - 8);
                 const double n_o = lds1(hpo + so + RB0), s_o = lds1(hpo + so - RB0), e_o = lds1(hpo + so + 8), w_o = lds1(hpo + so - 8);
-                rc_i = lds1(hri + rg.sc * C::RHS_STAGE);
-                const double rc_o = lds1(hro + rg.sc * C::RHS_STAGE);
-                u1n_i = upd3(c0, c1, c2, c3, rc_i, e_i, w_i, n_i, s_i, above_i, below_i);
-                const double u1n_o = upd3(c0, c1, c2, c3, rc_o, e_o, w_o, n_o, s_o, above_o, below_o);
+                qc_i = __dmul_rn(c0, lds1(hri + rg.sc * C::RHS_STAGE));
+                const double qc_o = __dmul_rn(c0, lds1(hro + rg.sc * C::RHS_STAGE));
+                u1n_i = fin3(part3(qc_i, c1, c2, e_i, w_i, n_i, s_i), c3, above_i, below_i);
+                const double u1n_o = fin3(part3(qc_o, c1, c2, e_o, w_o, n_o, s_o), c3, above_o, below_o);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8 * rg.sc);
                 const uint32_t so1 = (uint32_t)(it & 1) * C::U1_SLOT;
@@ -583,7 +598,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
                 cur_i = above_i; cur_o = above_o;
                 rg.advance();
             }
-            u1lo_i = u1c_i; u1c_i = u1n_i; r1_i = rc_i;
+            u1lo_i = u1c_i; u1c_i = u1n_i; q1_i = qc_i;
         }
     } else if (warp >= TY) {
         // ------------------------------ halo-row warps ------------------------------
@@ -613,7 +628,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         mbar_wait(full0 + 8, 0);
         st.cur[0] = lds2(k.pa + C::U0_STAGE); st.cur[1] = lds2(k.pa + C::U0_STAGE + 512);
         st.cur[2] = lds2(k.pa + C::U0_STAGE + RB0); st.cur[3] = lds2(k.pa + C::U0_STAGE + RB0 + 512);
-        for (int h = 0; h < 2; ++h) { st.u1c_out[h] = zero2; st.u1lo_in[h] = zero2; st.u1c_in[h] = zero2; st.r1_in[h] = zero2; }
+        for (int h = 0; h < 2; ++h) { st.u1c_out[h] = zero2; st.u1lo_in[h] = zero2; st.u1c_in[h] = zero2; st.q1_in[h] = zero2; }
         st.r = Ring3{ 1, 2, 0 };
         if (top) halo_rows3<true>(p, cp, k, st);
         else halo_rows3<false>(p, cp, k, st);
@@ -661,7 +676,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         st.cur_a = lds2(k.pa + C::U0_STAGE); st.cur_b = lds2(k.pa + C::U0_STAGE + RB0);
         st.u1lo_a = zero2; st.u1lo_b = zero2; st.u1c_a = zero2; st.u1c_b = zero2;
         st.u2lo_a = zero2; st.u2lo_b = zero2; st.u2c_a = zero2; st.u2c_b = zero2;
-        st.r1_a = zero2; st.r1_b = zero2; st.r2_a = zero2; st.r2_b = zero2;
+        st.q1_a = zero2; st.q1_b = zero2; st.q2_a = zero2; st.q2_b = zero2;
         st.oa = p.out + p.g.at(ia, jA, k0, 0);
         st.r = Ring3{ 1, 2, 0 };
 

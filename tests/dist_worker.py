@@ -31,13 +31,16 @@ CASES = [
     ([20, 18, 29], [2.0, 2.0, 3.0], MIXED_3D, 3, 2),       # two ghost layers: stand-alone fill + 2-slice halos
     ([33, 41], [1.0, 2.0], MIXED_2D, 4, 2),
 ]
-# extra cases for the double-sweep kernel across slabs (two sweeps per launch, deep halo: ghost + deep plane per neighbour)
+# extra cases for the temporally blocked kernels across slabs (3D: three sweeps per launch for even n0 / n1, otherwise two; deep halo:
+# ghost + deep planes per neighbour)
 TB2_CASES = [
     ([40, 36, 50], [40.0, 72.0, 150.0], MIXED_3D, 9, 1),   # 1 double | 3 doubles + the norm-carrying single
     ([130, 20, 23], [1.0, 1.0, 1.0], MIXED_3D, 8, 1),      # uneven split; 1 double | 2 doubles + 2 singles (world 8: slabs too thin, single sweeps)
     ([257, 30, 16], [3.0, 2.0, 1.0], MIXED_3D, 6, 1),      # 4-plane slabs at world 4 (the minimum), ragged x tiles
     ([65, 27, 43], [1.0, 2.0, 3.0], MIXED_3D, 7, 1),       # odd n0 / n1: x-hi / y-hi ghosts of the travelling planes; 5-plane slabs at world 8
     ([200, 40, 300], [2.0, 1.0, 3.0], MIXED_3D, 6, 1),     # slabs of several chunks (world 2: 150 planes = 96 + 54)
+    ([260, 38, 96], [2.0, 1.0, 3.0], MIXED_3D, 12, 1),     # even n0 / n1: THREE sweeps per launch across slabs (12-plane slabs at world 8): a pair | 3 triples + the norm-carrying single
+    ([128, 24, 48], [1.0, 1.0, 1.0], MIXED_3D, 7, 1),      # 6-plane slabs at world 8 (the minimum for three sweeps per launch): a pair | a triple, a single, the norm-carrying single
     # 2D y-slabs, four sweeps per launch (deep halo: ghost + 3 deep rows per neighbour)
     ([700, 130], [7.0, 1.3], MIXED_2D, 13, 1),             # two strips; 2 | 2 groups of four + 2 singles + the norm-carrying single
     ([1031, 67], [1.0, 1.0], MIXED_2D, 10, 1),             # odd n0; 8-row slabs at world 8 (the minimum)

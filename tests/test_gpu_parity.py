@@ -177,7 +177,7 @@ SWEEP_CASES_3D = [
 
 
 @pytest.mark.parametrize("n,hi,spec,sweeps", SWEEP_CASES_3D)
-@pytest.mark.parametrize("variant", [0, 6])
+@pytest.mark.parametrize("variant", [0, 31, 6])      # three (even n0, n1; otherwise two) / two / one sweep per launch
 def test_jacobi_3d_bit_exact(R, ctx, n, hi, spec, sweeps, variant):
     from rnmf_b200 import poisson
     ctx.set_option("sweep_variant", variant)
@@ -291,7 +291,7 @@ def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
     """kernels_sweep_tb2.cu: two sweeps (+ the ghost fill after each) per pass over HBM must equal two
     single sweeps bit for bit, for every tiling edge case and both parities of the sweep count."""
     from rnmf_b200 import poisson
-    ctx.set_option("sweep_variant", "auto")
+    ctx.set_option("sweep_variant", 31)
     ctx.set_option("resident", 0)
     try:
         g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=29)
@@ -302,6 +302,48 @@ def test_jacobi_3d_double_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
         ctx.sync()
         pairs = (sweeps - (1 if norm else 0)) // 2
         assert ctx.kernel_launches - before <= 1 + pairs + (sweeps - 2 * pairs) + 1      # shell copy, doubles, singles, reduce
+        want = psi0.copy()
+        l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
+        np.testing.assert_array_equal(psi.data, want)
+        if norm:
+            assert abs(l1 - l1_ref) <= NORM_RTOL * abs(l1_ref)
+        assert psi.guards_intact() and rhs.guards_intact()
+    finally:
+        ctx.set_option("sweep_variant", "auto")
+        ctx.set_option("resident", 1)
+
+
+@pytest.mark.parametrize("n,hi,spec,sweeps,norm", [
+    ([64, 64, 64], [64.0, 128.0, 192.0], MIXED_3D, 6, False),     # two triple sweeps
+    ([66, 34, 17], [1.0, 1.0, 1.0], MIXED_3D, 7, False),          # two triples + one single
+    ([66, 34, 17], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 9, True),     # two triples + a pair + the norm-carrying single
+    ([300, 70, 80], [3.0, 2.0, 1.0], MIXED_3D, 4, True),          # x/y/z tiling with ragged edges
+    ([130, 14, 5], [1.0, 2.0, 3.0], ALL_NEUMANN_3D, 6, False),    # one pair / one row pair past a tile edge
+    ([128, 12, 4], [1.0, 2.0, 3.0], MIXED_3D, 3, False),          # exactly one tile
+    ([126, 26, 1], [1.0, 2.0, 3.0], MIXED_3D, 6, False),          # a single plane: every level meets both z faces
+    ([2, 2, 1], [1.0, 1.0, 1.0], MIXED_3D, 6, False),
+    ([260, 30, 2], [1.0, 1.0, 1.0], ALL_NEUMANN_3D, 10, True),
+    ([520, 40, 70], [5.0, 2.0, 1.0], MIXED_3D, 6, False),         # five x tiles: warps with no x / y face run the interior-specialised loop
+    ([200, 38, 300], [2.0, 1.0, 3.0], MIXED_3D, 3, False),        # several chunks per launch
+    ([768, 24, 40], [7.0, 1.0, 3.0], MIXED_3D, 6, False),         # the benchmark's row length
+])
+def test_jacobi_3d_triple_sweep_bit_exact(R, ctx, n, hi, spec, sweeps, norm):
+    """kernels_sweep_tb3.cu (the 3D default for frames with even n0, n1): three sweeps (+ the ghost fill after each) per pass over
+    HBM must equal three single sweeps bit for bit; leftovers run as a pair (kernels_sweep_tb2.cu), then singles."""
+    from rnmf_b200 import poisson
+    ctx.set_option("sweep_variant", "auto")
+    ctx.set_option("resident", 0)
+    try:
+        g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, n, hi, spec, seed=33)
+        ora.fill_bc(g, psi0, obc)
+        psi.fill_bc()
+        d0, m0 = ctx.double_sweep_launches, ctx.multi_sweep_stats
+        l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=norm)
+        ctx.sync()
+        groupable = sweeps - (1 if norm else 0)
+        m1, pairs = ctx.multi_sweep_stats, ctx.double_sweep_launches - d0        # the stats count all temporally blocked launches
+        assert pairs == (groupable % 3) // 2
+        assert (m1[0] - m0[0] - pairs, m1[1] - m0[1] - 2 * pairs) == (groupable // 3, 3 * (groupable // 3)), "the three-sweep kernel did not run"
         want = psi0.copy()
         l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps)
         np.testing.assert_array_equal(psi.data, want)
@@ -592,12 +634,13 @@ def test_kernel_launch_counter_moves(R, ctx):
     g, obc, psi0, rhs0, psi, rhs = _frames(R, ctx, [32, 32, 32], [32.0] * 3, MIXED_3D, seed=91)
     ctx.set_option("resident", 0)
     before = ctx.kernel_launches
-    d0 = ctx.double_sweep_launches
+    m0 = ctx.multi_sweep_stats
     poisson.jacobi_sweeps(psi, rhs, 10)
     ctx.sync()
     ctx.set_option("resident", 1)
-    assert ctx.double_sweep_launches - d0 == 5                 # 3D default: two sweeps per launch
-    assert ctx.kernel_launches - before >= 5 + 1
+    m1 = ctx.multi_sweep_stats
+    assert (m1[0] - m0[0], m1[1] - m0[1]) == (3, 9)            # 3D default: three sweeps per launch (+ one single sweep)
+    assert ctx.kernel_launches - before >= 4 + 1
 
 
 # ---- size-independent properties at BASELINE.json's full sizes (no host arrays involved) --------
@@ -638,7 +681,7 @@ def test_full_size_oracle_parity(R, ctx, n, spec):
     g = ora.geom(n, hi=hi)
     obc, bc = _bc_pair(R, dim, spec)
     mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
-    sweeps = 5
+    sweeps = 6 if dim == 3 else 5      # 3D: one triple-sweep launch + one double-sweep launch + the norm-carrying single sweep
     psi = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx)
     rhs = R.CartesianDataFrame.new_from(mesh, bc, 1, 1, ctx)
     psi.fill_synthetic(0x5EED0001)
@@ -650,10 +693,12 @@ def test_full_size_oracle_parity(R, ctx, n, spec):
     got = psi.data
     assert np.array_equal(got, want), "synthetic field + fill_bc differ from the oracle at full size"
     assert np.array_equal(rhs.data, rhs0)
-    d0 = ctx.double_sweep_launches
+    d0, m0 = ctx.double_sweep_launches, ctx.multi_sweep_stats
     l1 = poisson.jacobi_sweeps(psi, rhs, sweeps, want_norm=True)
     if dim == 3:
-        assert ctx.double_sweep_launches - d0 == 2, "the default 3D path did not take the double-sweep kernel"
+        m1 = ctx.multi_sweep_stats
+        assert ctx.double_sweep_launches - d0 == 1, "the leftover pair did not take the double-sweep kernel"
+        assert (m1[0] - m0[0], m1[1] - m0[1]) == (2, 5), "the default 3D path did not take the three-sweep kernel"
     l1_ref = ora.jacobi(g, want, rhs0, obc, sweeps, omp=True)
     del rhs0
     del got
@@ -676,7 +721,7 @@ def test_full_size_properties(R, ctx, n, spec):
       (2) fill_bc is idempotent (second fill changes nothing: |diff| sums to exactly 0);
       (3) linearity: sweeps(a+b; ra+rb) == sweeps(a; ra) + sweeps(b; rb) with homogeneous
           Dirichlet faces, to rounding (relative 1e-13 of the field's L1 norm);
-      (4) the default path (3D: two sweeps per pass over HBM, 2D: four) agrees bit for bit with the
+      (4) the default path (3D: three sweeps per pass over HBM, 2D: four) agrees bit for bit with the
           single-sweep kernel (one sweep per launch, different tiling)."""
     from rnmf_b200 import poisson
     dim = len(n)
@@ -684,7 +729,7 @@ def test_full_size_properties(R, ctx, n, spec):
     mesh = R.CartesianMesh.new([0.0] * dim, hi, n)
     _, bc = _bc_pair(R, dim, spec)
     mk = lambda b: R.CartesianDataFrame.new_from(mesh, b, 1, 1, ctx)
-    sweeps = 5          # 3D default: two double-sweep launches + the norm-carrying single sweep
+    sweeps = 6          # 3D default: a triple-sweep launch, a double-sweep launch and the norm-carrying single sweep
 
     def run(variant):
         ctx.set_option("sweep_variant", variant)
