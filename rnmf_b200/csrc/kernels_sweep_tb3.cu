@@ -127,7 +127,7 @@ struct QuadK3 {
     bool ok;                             // the 2 x 2 patch lies inside the frame
     bool xlo, xhi, ylo, yhi;             // it touches that physical face (and the face has a Dirichlet / Neumann rule)
     Face1 fx0, fx1, fy0, fy1, fz0, fz1;
-    long long pitch, plane_sz, xy_off;
+    long long xy_off;
     int lane;
     int it_send[6];                      // iterations whose u3 plane also goes to a neighbour: lo ghost, lo deep 1, lo deep 2, hi ghost, hi deep 1, hi deep 2
 };
@@ -161,28 +161,32 @@ __device__ __forceinline__ void ring_store(const QuadK3& k, uint32_t b, const do
 
 // u3 of the lane's patch into one grown plane of a frame buffer: the valid cells and the x / y face ghosts
 template <int EDGE>
-__device__ __forceinline__ void plane_store3(const QuadK3& k, double* oa, const double2& na, const double2& nb)
+__device__ __forceinline__ void plane_store3(const QuadK3& k, const int pitch, double* oa, const double2& na, const double2& nb)
 {
     if (EDGE == 2 && !k.ok) return;
 #ifdef RNMF_EMULATE
-    if (reinterpret_cast<uintptr_t>(oa) % 16 != 0 || (k.pitch & 1)) emu::fault("misaligned 16-byte global store", reinterpret_cast<uintptr_t>(oa), 16);
+    if (reinterpret_cast<uintptr_t>(oa) % 16 != 0 || (pitch & 1)) emu::fault("misaligned 16-byte global store", reinterpret_cast<uintptr_t>(oa), 16);
 #endif
     *reinterpret_cast<double2*>(oa) = na;
-    *reinterpret_cast<double2*>(oa + k.pitch) = nb;
+    *reinterpret_cast<double2*>(oa + pitch) = nb;
     if (EDGE != 0) {
-        if (k.xlo) { oa[-1] = ghost1(k.fx0, na.x); oa[k.pitch - 1] = ghost1(k.fx0, nb.x); }
-        if (k.xhi) { oa[2] = ghost1(k.fx1, na.y); oa[k.pitch + 2] = ghost1(k.fx1, nb.y); }
+        if (k.xlo) { oa[-1] = ghost1(k.fx0, na.x); oa[pitch - 1] = ghost1(k.fx0, nb.x); }
+        if (k.xhi) { oa[2] = ghost1(k.fx1, na.y); oa[pitch + 2] = ghost1(k.fx1, nb.y); }
     }
     if (EDGE == 2) {
-        if (k.ylo) *reinterpret_cast<double2*>(oa - k.pitch) = ghost1(k.fy0, na);
-        if (k.yhi) *reinterpret_cast<double2*>(oa + 2 * k.pitch) = ghost1(k.fy1, nb);
+        if (k.ylo) *reinterpret_cast<double2*>(oa - pitch) = ghost1(k.fy0, na);
+        if (k.yhi) *reinterpret_cast<double2*>(oa + 2 * pitch) = ghost1(k.fy1, nb);
     }
 }
 
 // One plane iteration of a quad warp.  L1 / L2 / L3: which levels are active.  EDGE: 2 = general; 0 = the warp's patches are
 // whole, touch no x / y face, and the iteration meets neither a z face nor a plane that goes to a slab neighbour; 1 = as 0,
 // but next to an x face.
-template <bool L1, bool L2, bool L3, int EDGE>
+// R: it % 4 when it is known at compile time (the steady loop runs in trips of twelve iterations = lcm of the four stages, the two
+// ring slots and the three-plane register windows), -1 otherwise.  With R >= 0 every ring index is a constant: all shared-memory
+// and barrier addresses are immediate offsets, the barrier parities are st.r.phn (= (it / 4) & 1, toggled by the caller every four
+// iterations) xor a constant, and the windows rotate by renaming.
+template <bool L1, bool L2, bool L3, int EDGE, int R = -1>
 __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
 {
     using C = Cfg3;
@@ -191,19 +195,30 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above_a = zero2, above_b = zero2, qc_a = zero2, qc_b = zero2;
     double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2, P2_a = zero2, P2_b = zero2, P3_a = zero2, P3_b = zero2;
-    const int j = it - cp.it2_first;                       // level 2 forms its j-th plane now (slot j & 1); level 3 reads plane j-1
-    const uint32_t sc = st.r.sc, sn = st.r.sn;
+    // ring position: stage of plane a1+it (sc), of plane a1+it+1 (sn), parity the wait for sn completes with; slot of the u1 plane
+    // level 1 / the u2 plane level 2 writes now (slot), of the planes levels 2 / 3 read (pslot) and the parity their barriers
+    // complete with: ((it-1) >> 1) & 1, which for it = 4t + R, t >= 1, is 1 for R = 0, 3 and 0 for R = 1, 2
+    const uint32_t sc = R >= 0 ? (uint32_t)((R + 1) & 3) : st.r.sc;
+    const uint32_t sn = R >= 0 ? (uint32_t)((R + 2) & 3) : st.r.sn;
+    const uint32_t phn = R >= 0 ? st.r.phn ^ (R >= 2 ? 1u : 0u) : st.r.phn;
+    const uint32_t slot = R >= 0 ? (uint32_t)(R & 1) : (uint32_t)(it & 1);
+    const uint32_t pslot = slot ^ 1u;
+    const uint32_t pu = R >= 0 ? ((R == 0 || R == 3) ? 1u : 0u) : (uint32_t)((it - 1) >> 1) & 1u;
 
     // ---- wait phase ----------------------------------------------------------------------------------
-    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);                                            // u0 plane a1+it+1
-    if ((L1 || L2) && it >= 1) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);   // u1 plane a1+it-1 complete, plane a1+it-2 no longer read
-    // u2 plane a1+it-2 complete and the one before no longer read; it also says that every warp has finished level 2 of the
-    // previous iteration, i.e. its loads from the u1 slot that level 1 overwrites below
-    if (j >= 1) mbar_wait(k.u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+    if (L1) mbar_wait(k.full0 + 8 * sn, phn);                                                 // u0 plane a1+it+1
+    if (it >= 1) {
+        // u1 plane a1+it-1 complete (level 2 reads it) ...
+        if (L1 || L2) mbar_wait(k.u1full0 + 8 * pslot, pu);
+        // ... and every warp is through iteration it-1 up to its u2 arrival (dummy arrivals while level 2 is not active yet): u2
+        // plane a1+it-2 is complete (level 3 reads it), nobody reads the u2 slot level 2 overwrites below any more, and nobody
+        // reads the u1 slot level 1 overwrites below any more (level 2's loads of iteration it-1 precede that arrival)
+        mbar_wait(k.u2full0 + 8 * pslot, pu);
+    }
 
     // ---- level 3, x/y part: plane a1+it-2 from the u2 ring ---------------------------------------------
     if (L3) {
-        const uint32_t b = k.u2a + (uint32_t)((j - 1) & 1) * C::U2_SLOT;
+        const uint32_t b = k.u2a + pslot * C::U2_SLOT;
         const double2 s_a = ldp(b - RBU);
         const double w_a = lds1(b + kW), e_a = lds1(b + kE);
         P3_a.x = part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
@@ -234,15 +249,15 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         }
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);                  // this warp is done with the stage of plane a1+it
-        ring_store<EDGE>(k, k.u1a + (uint32_t)(it & 1) * C::U1_SLOT, u1n_a, u1n_b);
+        ring_store<EDGE>(k, k.u1a + slot * C::U1_SLOT, u1n_a, u1n_b);
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
     }
     // ---- level 2: u2 of plane a1+it-1; x/y part from the u1 ring (AFTER this warp's arrival for u1 plane a1+it: the slot these
     // loads read is overwritten by level 1 of the next iteration, which every warp starts behind the u2full wait for THIS
     // iteration's level 2 -- see the wait phase), then the z part from registers --------------------------------------------
     if (L2) {
-        const uint32_t b = k.u1a + (uint32_t)((it - 1) & 1) * C::U1_SLOT;
+        const uint32_t b = k.u1a + pslot * C::U1_SLOT;
         const double2 s_a = ldp(b - RBU);
         const double w_a = lds1(b + kW), e_a = lds1(b + kE);
         P2_a.x = part3(st.q1_a.x, c1, c2, st.u1c_a.y, w_a, st.u1c_b.x, s_a.x);
@@ -256,9 +271,11 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         if (!L1) { up_a = ghost1(k.fz1, st.u1c_a); up_b = ghost1(k.fz1, st.u1c_b); }         // the frame's last plane next to a physical z-hi face
         u2n_a = fin3(P2_a, c3, up_a, dn_a);
         u2n_b = fin3(P2_b, c3, up_b, dn_b);
-        ring_store<EDGE>(k, k.u2a + (uint32_t)(j & 1) * C::U2_SLOT, u2n_a, u2n_b);
+        ring_store<EDGE>(k, k.u2a + slot * C::U2_SLOT, u2n_a, u2n_b);
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * (j & 1));
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);
+    } else if (L1) {
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);               // level 2 not active yet: keep the barrier's phases in step with `it`
     }
     // ---- level 3, z part: u3 of plane a1+it-2 ---------------------------------------------------------------
     if (L3) {
@@ -268,26 +285,27 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         if (!L2) { up_a = ghost1(k.fz1, st.u2c_a); up_b = ghost1(k.fz1, st.u2c_b); }
         const double2 na = fin3(P3_a, c3, up_a, dn_a), nb = fin3(P3_b, c3, up_b, dn_b);
         double* oa = st.oa;
-        plane_store3<EDGE>(k, oa, na, nb);
+        const int pitch = (int)p.g.pitch, plane_sz = (int)p.g.plane;      // kernel parameters (constant bank), not registers
+        plane_store3<EDGE>(k, pitch, oa, na, nb);
         if (EDGE == 2) {
             if (k.ok) {
-                if (zlo) { *reinterpret_cast<double2*>(oa - k.plane_sz) = ghost1(k.fz0, na); *reinterpret_cast<double2*>(oa - k.plane_sz + k.pitch) = ghost1(k.fz0, nb); }
-                if (!L2) { *reinterpret_cast<double2*>(oa + k.plane_sz) = ghost1(k.fz1, na); *reinterpret_cast<double2*>(oa + k.plane_sz + k.pitch) = ghost1(k.fz1, nb); }
+                if (zlo) { *reinterpret_cast<double2*>(oa - plane_sz) = ghost1(k.fz0, na); *reinterpret_cast<double2*>(oa - plane_sz + pitch) = ghost1(k.fz0, nb); }
+                if (!L2) { *reinterpret_cast<double2*>(oa + plane_sz) = ghost1(k.fz1, na); *reinterpret_cast<double2*>(oa + plane_sz + pitch) = ghost1(k.fz1, nb); }
             }
             // planes next to a slab neighbour: the same grown rows into its ghost / deep planes (NVLink stores)
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
-                if (it == k.it_send[e]) plane_store3<2>(k, p.peer_lo[e] + k.xy_off, na, nb);
-                if (it == k.it_send[3 + e]) plane_store3<2>(k, p.peer_hi[e] + k.xy_off, na, nb);
+                if (it == k.it_send[e]) plane_store3<2>(k, pitch, p.peer_lo[e] + k.xy_off, na, nb);
+                if (it == k.it_send[3 + e]) plane_store3<2>(k, pitch, p.peer_hi[e] + k.xy_off, na, nb);
             }
         }
-        st.oa = oa + k.plane_sz;
+        st.oa = oa + plane_sz;
     }
     // ---- rotate ------------------------------------------------------------------------------------------
     if (L1) {
         st.below_a = st.cur_a; st.below_b = st.cur_b;
         st.cur_a = above_a; st.cur_b = above_b;
-        st.r.advance();
+        if (R < 0) st.r.advance();            // static trips leave the ring state alone: after four iterations it is the same, parity aside
     }
     st.u2lo_a = st.u2c_a; st.u2lo_b = st.u2c_b;
     st.u2c_a = u2n_a; st.u2c_b = u2n_b;
@@ -309,13 +327,33 @@ __device__ __forceinline__ void quad_general3(const Tb3Params& p, const ChunkPla
     else if (l3) quad_iter3<false, false, true, 2>(p, cp, k, st, it);
 }
 
+// four iterations that start at it % 4 == 0 (ring at (sc, sn) = (1, 2), st.r.phn == (it / 4) & 1)
+template <int EDGE>
+__device__ __forceinline__ void quad_four3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
+{
+    quad_iter3<true, true, true, EDGE, 0>(p, cp, k, st, it);
+    quad_iter3<true, true, true, EDGE, 1>(p, cp, k, st, it + 1);
+    quad_iter3<true, true, true, EDGE, 2>(p, cp, k, st, it + 2);
+    quad_iter3<true, true, true, EDGE, 3>(p, cp, k, st, it + 3);
+    st.r.phn ^= 1u;
+}
+
+// plane iterations [it, end) with all three levels; the steady part in trips of twelve with compile-time ring indices
 template <int EDGE>
 __device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, int& it, const int end)
 {
-    for (; it + 3 <= end; it += 3) {
-        quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
-        quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 1);
-        quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 2);
+#ifdef RNMF_DYNAMIC_RING          // A/B builds only (scripts/build_alt.sh): the run-time ring everywhere
+    constexpr bool kStatic = false;
+#else
+    constexpr bool kStatic = EDGE != 2;
+#endif
+    if (kStatic) {
+        for (; it < end && ((it & 3) != 0 || it < 4); ++it) quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
+        for (; it + 12 <= end; it += 12) {
+            quad_four3<EDGE>(p, cp, k, st, it);
+            quad_four3<EDGE>(p, cp, k, st, it + 4);
+            quad_four3<EDGE>(p, cp, k, st, it + 8);
+        }
     }
     for (; it < end; ++it) quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
 }
@@ -342,7 +380,7 @@ struct HaloSt3 {
     Ring3 r;
 };
 
-template <bool TOP, bool L1, bool L2>
+template <bool TOP, bool L1, bool L2, int R = -1>
 __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& cp, const HaloK3& k, HaloSt3& st, const int it)
 {
     using C = Cfg3;
@@ -351,16 +389,20 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, qc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
-    const int j = it - cp.it2_first;
-    const uint32_t sc = st.r.sc, sn = st.r.sn;
+    // ring position, static for R >= 0: as in quad_iter3
+    const uint32_t sc = R >= 0 ? (uint32_t)((R + 1) & 3) : st.r.sc;
+    const uint32_t sn = R >= 0 ? (uint32_t)((R + 2) & 3) : st.r.sn;
+    const uint32_t phn = R >= 0 ? st.r.phn ^ (R >= 2 ? 1u : 0u) : st.r.phn;
+    const uint32_t slot = R >= 0 ? (uint32_t)(R & 1) : (uint32_t)(it & 1);
+    const uint32_t pslot = slot ^ 1u;
+    const uint32_t pu = R >= 0 ? ((R == 0 || R == 3) ? 1u : 0u) : (uint32_t)((it - 1) >> 1) & 1u;
 
-    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);
-    if (it >= 1) mbar_wait(k.u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
-    if (j >= 1) mbar_wait(k.u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+    if (L1) mbar_wait(k.full0 + 8 * sn, phn);
+    if (it >= 1) { mbar_wait(k.u1full0 + 8 * pslot, pu); mbar_wait(k.u2full0 + 8 * pslot, pu); }
 
     if (L2) {
         // inner row: the neighbour row towards the tile comes from the ring, the other one is the lane's own outer row
-        const uint32_t b = k.u1a + (uint32_t)((it - 1) & 1) * C::U1_SLOT + IN * RBU;
+        const uint32_t b = k.u1a + pslot * C::U1_SLOT + IN * RBU;
         const uint32_t bt = TOP ? b - RBU : b + RBU;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -389,17 +431,17 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
         }
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);
-        const uint32_t b = k.u1a + (uint32_t)(it & 1) * C::U1_SLOT;
+        const uint32_t b = k.u1a + slot * C::U1_SLOT;
         if (k.ok_a) { stp(b, u1n[0]); stp(b + RBU, u1n[2]); }
         if (k.ok_b) { stp(b + 256, u1n[1]); stp(b + RBU + 256, u1n[3]); }
         // the x-face ghosts of u1 that level 2 of the inner row reads
         if (k.xlo) sts1(b + IN * RBU + kW, ghost1(k.fx0, u1n[2 * IN].x));
         if (k.xhi >= 0) sts1(b + IN * RBU + 256 * k.xhi + kE, ghost1(k.fx1, k.xhi ? u1n[2 * IN + 1].y : u1n[2 * IN].y));
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * (it & 1));
+        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
     }
     if (L2) {
-        const uint32_t b = k.u2a + (uint32_t)(j & 1) * C::U2_SLOT;
+        const uint32_t b = k.u2a + slot * C::U2_SLOT;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             double2 dn = st.u1lo_in[h], up = u1n[2 * IN + h];
@@ -409,12 +451,14 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
             if (h == 0 ? k.ok_a : k.ok_b) stp(b + 256 * h, v);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * (j & 1));
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);
+    } else {
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);               // keeps the barrier's phases in step with `it`
     }
     if (L1) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { st.below[q] = st.cur[q]; st.cur[q] = above[q]; }
-        st.r.advance();
+        if (R < 0) st.r.advance();
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -430,6 +474,15 @@ __device__ __forceinline__ void halo_rows3(const Tb3Params& p, const ChunkPlan& 
 {
     int it = 0;
     for (; it < cp.it2_first && it < cp.nL1; ++it) halo_iter3<TOP, true, false>(p, cp, k, st, it);
+    // steady part: trips of four iterations from it % 4 == 0 with compile-time ring indices (it >= 4 there)
+    for (; it < cp.nL1 && ((it & 3) != 0 || it < 4); ++it) halo_iter3<TOP, true, true>(p, cp, k, st, it);
+    for (; it + 4 <= cp.nL1; it += 4) {
+        halo_iter3<TOP, true, true, 0>(p, cp, k, st, it);
+        halo_iter3<TOP, true, true, 1>(p, cp, k, st, it + 1);
+        halo_iter3<TOP, true, true, 2>(p, cp, k, st, it + 2);
+        halo_iter3<TOP, true, true, 3>(p, cp, k, st, it + 3);
+        st.r.phn ^= 1u;
+    }
     for (; it < cp.nL1; ++it) halo_iter3<TOP, true, true>(p, cp, k, st, it);
     for (; it <= cp.it2_last; ++it) halo_iter3<TOP, false, true>(p, cp, k, st, it);
 }
@@ -552,13 +605,12 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         Ring3 rg = { 1, 2, 0 };
         for (int it = 0; it <= cp.it2_last; ++it) {
             const bool l1 = it < nL1, l2 = it >= cp.it2_first;
-            const int j = it - cp.it2_first;
+            const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;
             if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
-            if (it >= 1) mbar_wait(u1full0 + 8 * ((it - 1) & 1), (uint32_t)((it - 1) >> 1) & 1u);
-            if (j >= 1) mbar_wait(u2full0 + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+            if (it >= 1) { mbar_wait(u1full0 + 8 * pslot, pu); mbar_wait(u2full0 + 8 * pslot, pu); }      // as in quad_iter3
             double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, qc_i = 0.0;
             if (l2) {
-                const uint32_t so = (uint32_t)((it - 1) & 1) * C::U1_SLOT;
+                const uint32_t so = pslot * C::U1_SLOT;
                 const double nn = lds1(u1i + so + RBU), ss = lds1(u1i + so - RBU);
                 const double tt = lds1(u1t + so), oo = lds1(u1o + so);
                 // E / W: left of the tile the tile cell is the E neighbour, right of it the W neighbour
@@ -575,23 +627,25 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
                 const double u1n_o = fin3(part3(qc_o, c1, c2, e_o, w_o, n_o, s_o), c3, above_o, below_o);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8 * rg.sc);
-                const uint32_t so1 = (uint32_t)(it & 1) * C::U1_SLOT;
+                const uint32_t so1 = slot * C::U1_SLOT;
                 if (ok) sts1(u1i + so1, u1n_i);
                 if (ok2) sts1(u1o + so1, u1n_o);
                 // the y-face ghosts of u1 in the inner column (read by level 2 of this warp)
                 if (ylo) sts1(u1i + so1 - RBU, ghost1(fy0, u1n_i));
                 if (yhi) sts1(u1i + so1 + RBU, ghost1(fy1, u1n_i));
                 __syncwarp();
-                if (lane == 0) mbar_arrive(u1full0 + 8 * (it & 1));
+                if (lane == 0) mbar_arrive(u1full0 + 8 * slot);
             }
             if (l2) {
                 double dn = u1lo_i, up = u1n_i;
                 if (it == cp.it_zlo2) dn = ghost1(fz0, u1c_i);
                 if (!l1) up = ghost1(fz1, u1c_i);
                 const double v = fin3(P2, c3, up, dn);
-                if (ok2) sts1(u2i + (uint32_t)(j & 1) * C::U2_SLOT, v);
+                if (ok2) sts1(u2i + slot * C::U2_SLOT, v);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(u2full0 + 8 * (j & 1));
+                if (lane == 0) mbar_arrive(u2full0 + 8 * slot);
+            } else {
+                if (lane == 0) mbar_arrive(u2full0 + 8 * slot);           // keeps the barrier's phases in step with `it`
             }
             if (l1) {
                 below_i = cur_i; below_o = cur_o;
@@ -646,9 +700,8 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         k.u1a = u1_0 + (uint32_t)(ra + 2) * RBU + (uint32_t)(8 * (1 + t));
         k.u2a = u2_0 + (uint32_t)(ra + 1) * RBU + (uint32_t)(8 * (1 + t));
         k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0; k.u2full0 = u2full0;
-        k.pitch = p.g.pitch; k.plane_sz = p.g.plane;
         // offset of the lane's first cell inside a grown xy plane (the neighbours' ghost / deep planes)
-        k.xy_off = p.g.xoff + (ia + p.g.ng) + k.pitch * (jA + p.g.ng);
+        k.xy_off = p.g.xoff + (ia + p.g.ng) + p.g.pitch * (jA + p.g.ng);
         k.lane = lane;
         // ghost rules of the six faces (a z face with mode 0 is a slab neighbour)
         k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
