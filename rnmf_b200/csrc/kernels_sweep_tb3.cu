@@ -75,8 +75,9 @@ struct Cfg3 {
     static constexpr int RHS_OFF = NS * U0_STAGE;
     static constexpr int U1_OFF = RHS_OFF + NS * RHS_STAGE;
     static constexpr int U2_OFF = U1_OFF + 2 * U1_SLOT;
-    static constexpr int BAR_OFF = U2_OFF + 2 * U2_SLOT;
-    static constexpr int SMEM = BAR_OFF + (2 * NS + 4) * 8 + 128;
+    static constexpr int NU2 = 3;                          // u2 slots (three: level 3 reads a plane AFTER this warp's arrival for the next one)
+    static constexpr int BAR_OFF = U2_OFF + NU2 * U2_SLOT;
+    static constexpr int SMEM = BAR_OFF + (2 * NS + 2 + NU2) * 8 + 128;
     static constexpr int NCONS = TY + 3;                   // 12 quad warps + 2 halo-row warps + 1 column warp
     static constexpr int THREADS = 32 * (TY + 4);          // + producer warp
     static_assert(SMEM <= 227 * 1024, "shared-memory budget");
@@ -103,10 +104,15 @@ __device__ __forceinline__ void stp(uint32_t b, const double2& v) { sts1(b, v.x)
 // pair next to the face lives
 constexpr uint32_t kW = Cfg3::ODD - 8, kE = 8;
 
-// position in the u0 / rhs ring shared by every consumer: stage of plane a1+it, of plane a1+it+1, parity its full barrier completes with
+// ring positions shared by every consumer warp.  u0 / rhs: stage of plane a1+it (sc), of plane a1+it+1 (sn), parity its full barrier
+// completes with (phn).  u2: slot level 2 writes in this iteration (u2w = it % 3) and the parity its barrier completes with
+// (u2p = (it / 3) & 1); level 3 reads the slot written one iteration ago.  (u1: slot it & 1, parity (it >> 1) & 1.)
 struct Ring3 {
-    uint32_t sc, sn, phn;
-    __device__ __forceinline__ void advance() { sc = sn; if (++sn == (uint32_t)Cfg3::NS) { sn = 0; phn ^= 1u; } }
+    uint32_t sc, sn, phn, u2w, u2p;
+    __device__ __forceinline__ void advance_u0() { sc = sn; if (++sn == (uint32_t)Cfg3::NS) { sn = 0; phn ^= 1u; } }
+    __device__ __forceinline__ void advance_u2() { if (++u2w == (uint32_t)Cfg3::NU2) { u2w = 0; u2p ^= 1u; } }
+    __device__ __forceinline__ uint32_t u2r() const { return u2w == 0 ? (uint32_t)Cfg3::NU2 - 1 : u2w - 1; }     // slot written in iteration it-1
+    __device__ __forceinline__ uint32_t u2rp() const { return u2w == 0 ? u2p ^ 1u : u2p; }                       // ... and its parity
 };
 
 // what every consumer warp of the CTA knows about the chunk (CTA-uniform)
@@ -182,11 +188,13 @@ __device__ __forceinline__ void plane_store3(const QuadK3& k, const int pitch, d
 // One plane iteration of a quad warp.  L1 / L2 / L3: which levels are active.  EDGE: 2 = general; 0 = the warp's patches are
 // whole, touch no x / y face, and the iteration meets neither a z face nor a plane that goes to a slab neighbour; 1 = as 0,
 // but next to an x face.
-// R: it % 4 when it is known at compile time (the steady loop runs in trips of twelve iterations = lcm of the four stages, the two
-// ring slots and the three-plane register windows), -1 otherwise.  With R >= 0 every ring index is a constant: all shared-memory
-// and barrier addresses are immediate offsets, the barrier parities are st.r.phn (= (it / 4) & 1, toggled by the caller every four
-// iterations) xor a constant, and the windows rotate by renaming.
-template <bool L1, bool L2, bool L3, int EDGE, int R = -1>
+// Order: level 1 (plane a1+it), level 2 (plane a1+it-1), level 3 (plane a1+it-2): each level loads what it needs right before it
+// uses it (few values in flight: the kernel lives at the 128-register limit), a warp arrives for its u1 / u2 plane as early as
+// possible, and the work behind the arrivals (level 3: loads, 44 operations, the global stores) is slack for the slower warps.
+// Ring hazards: level 2 loads from the u1 slot that level 1 of the NEXT iteration overwrites -- every warp starts that iteration
+// behind the wait for this iteration's u2 arrivals, which follow the loads; level 3 loads from the u2 slot written one iteration
+// ago AFTER this warp's u2 arrival, so that slot must survive the next iteration's level 2: three u2 slots.
+template <bool L1, bool L2, bool L3, int EDGE>
 __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
 {
     using C = Cfg3;
@@ -194,41 +202,23 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above_a = zero2, above_b = zero2, qc_a = zero2, qc_b = zero2;
-    double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2, P2_a = zero2, P2_b = zero2, P3_a = zero2, P3_b = zero2;
-    // ring position: stage of plane a1+it (sc), of plane a1+it+1 (sn), parity the wait for sn completes with; slot of the u1 plane
-    // level 1 / the u2 plane level 2 writes now (slot), of the planes levels 2 / 3 read (pslot) and the parity their barriers
-    // complete with: ((it-1) >> 1) & 1, which for it = 4t + R, t >= 1, is 1 for R = 0, 3 and 0 for R = 1, 2
-    const uint32_t sc = R >= 0 ? (uint32_t)((R + 1) & 3) : st.r.sc;
-    const uint32_t sn = R >= 0 ? (uint32_t)((R + 2) & 3) : st.r.sn;
-    const uint32_t phn = R >= 0 ? st.r.phn ^ (R >= 2 ? 1u : 0u) : st.r.phn;
-    const uint32_t slot = R >= 0 ? (uint32_t)(R & 1) : (uint32_t)(it & 1);
-    const uint32_t pslot = slot ^ 1u;
-    const uint32_t pu = R >= 0 ? ((R == 0 || R == 3) ? 1u : 0u) : (uint32_t)((it - 1) >> 1) & 1u;
+    double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2;
+    const uint32_t sc = st.r.sc, sn = st.r.sn;
+    const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;      // u1 ring
+    const uint32_t w2 = st.r.u2w, r2 = st.r.u2r();                                                        // u2 ring
 
     // ---- wait phase ----------------------------------------------------------------------------------
-    if (L1) mbar_wait(k.full0 + 8 * sn, phn);                                                 // u0 plane a1+it+1
+    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);                                            // u0 plane a1+it+1
     if (it >= 1) {
         // u1 plane a1+it-1 complete (level 2 reads it) ...
         if (L1 || L2) mbar_wait(k.u1full0 + 8 * pslot, pu);
         // ... and every warp is through iteration it-1 up to its u2 arrival (dummy arrivals while level 2 is not active yet): u2
-        // plane a1+it-2 is complete (level 3 reads it), nobody reads the u2 slot level 2 overwrites below any more, and nobody
-        // reads the u1 slot level 1 overwrites below any more (level 2's loads of iteration it-1 precede that arrival)
-        mbar_wait(k.u2full0 + 8 * pslot, pu);
+        // plane a1+it-2 is complete (level 3 reads it), every warp has left iteration it-2 (whose level 3 read the u2 slot level 2
+        // overwrites below), and nobody reads the u1 slot level 1 overwrites below any more
+        mbar_wait(k.u2full0 + 8 * r2, st.r.u2rp());
     }
 
-    // ---- level 3, x/y part: plane a1+it-2 from the u2 ring ---------------------------------------------
-    if (L3) {
-        const uint32_t b = k.u2a + pslot * C::U2_SLOT;
-        const double2 s_a = ldp(b - RBU);
-        const double w_a = lds1(b + kW), e_a = lds1(b + kE);
-        P3_a.x = part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
-        P3_a.y = part3(st.q2_a.y, c1, c2, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y);
-        const double2 n_b = ldp(b + 2 * RBU);
-        const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
-        P3_b.x = part3(st.q2_b.x, c1, c2, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x);
-        P3_b.y = part3(st.q2_b.y, c1, c2, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y);
-    }
-    // ---- level 1: u1 of plane a1+it (row A, then row B: fewer values in flight at a time) --------------------
+    // ---- level 1: u1 of plane a1+it (row A, then row B) --------------------------------------------------
     if (L1) {
         const uint32_t pn = k.pa + sn * C::U0_STAGE, pc = k.pa + sc * C::U0_STAGE, pr = k.ra + sc * C::RHS_STAGE;
         {
@@ -253,37 +243,50 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         __syncwarp();
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
     }
-    // ---- level 2: u2 of plane a1+it-1; x/y part from the u1 ring (AFTER this warp's arrival for u1 plane a1+it: the slot these
-    // loads read is overwritten by level 1 of the next iteration, which every warp starts behind the u2full wait for THIS
-    // iteration's level 2 -- see the wait phase), then the z part from registers --------------------------------------------
+    // ---- level 2: u2 of plane a1+it-1; x/y neighbours from the u1 ring, z neighbours from registers --------------
     if (L2) {
         const uint32_t b = k.u1a + pslot * C::U1_SLOT;
-        const double2 s_a = ldp(b - RBU);
-        const double w_a = lds1(b + kW), e_a = lds1(b + kE);
-        P2_a.x = part3(st.q1_a.x, c1, c2, st.u1c_a.y, w_a, st.u1c_b.x, s_a.x);
-        P2_a.y = part3(st.q1_a.y, c1, c2, e_a, st.u1c_a.x, st.u1c_b.y, s_a.y);
-        const double2 n_b = ldp(b + 2 * RBU);
-        const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
-        P2_b.x = part3(st.q1_b.x, c1, c2, st.u1c_b.y, w_b, n_b.x, st.u1c_a.x);
-        P2_b.y = part3(st.q1_b.y, c1, c2, e_b, st.u1c_b.x, n_b.y, st.u1c_a.y);
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
         if (EDGE == 2 && it == cp.it_zlo2) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
         if (!L1) { up_a = ghost1(k.fz1, st.u1c_a); up_b = ghost1(k.fz1, st.u1c_b); }         // the frame's last plane next to a physical z-hi face
-        u2n_a = fin3(P2_a, c3, up_a, dn_a);
-        u2n_b = fin3(P2_b, c3, up_b, dn_b);
-        ring_store<EDGE>(k, k.u2a + slot * C::U2_SLOT, u2n_a, u2n_b);
+        {
+            const double2 s_a = ldp(b - RBU);
+            const double w_a = lds1(b + kW), e_a = lds1(b + kE);
+            u2n_a.x = fin3(part3(st.q1_a.x, c1, c2, st.u1c_a.y, w_a, st.u1c_b.x, s_a.x), c3, up_a.x, dn_a.x);
+            u2n_a.y = fin3(part3(st.q1_a.y, c1, c2, e_a, st.u1c_a.x, st.u1c_b.y, s_a.y), c3, up_a.y, dn_a.y);
+        }
+        {
+            const double2 n_b = ldp(b + 2 * RBU);
+            const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+            u2n_b.x = fin3(part3(st.q1_b.x, c1, c2, st.u1c_b.y, w_b, n_b.x, st.u1c_a.x), c3, up_b.x, dn_b.x);
+            u2n_b.y = fin3(part3(st.q1_b.y, c1, c2, e_b, st.u1c_b.x, n_b.y, st.u1c_a.y), c3, up_b.y, dn_b.y);
+        }
+        ring_store<EDGE>(k, k.u2a + w2 * C::U2_SLOT, u2n_a, u2n_b);
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);
     } else if (L1) {
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);               // level 2 not active yet: keep the barrier's phases in step with `it`
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);                 // level 2 not active yet: keep the barrier's phases in step with `it`
     }
-    // ---- level 3, z part: u3 of plane a1+it-2 ---------------------------------------------------------------
+    // ---- level 3: u3 of plane a1+it-2; x/y neighbours from the u2 ring, z neighbours from registers --------------
     if (L3) {
+        const uint32_t b = k.u2a + r2 * C::U2_SLOT;
         double2 dn_a = st.u2lo_a, dn_b = st.u2lo_b, up_a = u2n_a, up_b = u2n_b;
         const bool zlo = EDGE == 2 && it == cp.it_zlo3;
         if (zlo) { dn_a = ghost1(k.fz0, st.u2c_a); dn_b = ghost1(k.fz0, st.u2c_b); }
         if (!L2) { up_a = ghost1(k.fz1, st.u2c_a); up_b = ghost1(k.fz1, st.u2c_b); }
-        const double2 na = fin3(P3_a, c3, up_a, dn_a), nb = fin3(P3_b, c3, up_b, dn_b);
+        double2 na, nb;
+        {
+            const double2 s_a = ldp(b - RBU);
+            const double w_a = lds1(b + kW), e_a = lds1(b + kE);
+            na.x = fin3(part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x), c3, up_a.x, dn_a.x);
+            na.y = fin3(part3(st.q2_a.y, c1, c2, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y), c3, up_a.y, dn_a.y);
+        }
+        {
+            const double2 n_b = ldp(b + 2 * RBU);
+            const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+            nb.x = fin3(part3(st.q2_b.x, c1, c2, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x), c3, up_b.x, dn_b.x);
+            nb.y = fin3(part3(st.q2_b.y, c1, c2, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y), c3, up_b.y, dn_b.y);
+        }
         double* oa = st.oa;
         const int pitch = (int)p.g.pitch, plane_sz = (int)p.g.plane;      // kernel parameters (constant bank), not registers
         plane_store3<EDGE>(k, pitch, oa, na, nb);
@@ -305,8 +308,9 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     if (L1) {
         st.below_a = st.cur_a; st.below_b = st.cur_b;
         st.cur_a = above_a; st.cur_b = above_b;
-        if (R < 0) st.r.advance();            // static trips leave the ring state alone: after four iterations it is the same, parity aside
+        st.r.advance_u0();
     }
+    st.r.advance_u2();
     st.u2lo_a = st.u2c_a; st.u2lo_b = st.u2c_b;
     st.u2c_a = u2n_a; st.u2c_b = u2n_b;
     st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
@@ -327,34 +331,22 @@ __device__ __forceinline__ void quad_general3(const Tb3Params& p, const ChunkPla
     else if (l3) quad_iter3<false, false, true, 2>(p, cp, k, st, it);
 }
 
-// four iterations that start at it % 4 == 0 (ring at (sc, sn) = (1, 2), st.r.phn == (it / 4) & 1)
-template <int EDGE>
-__device__ __forceinline__ void quad_four3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
-{
-    quad_iter3<true, true, true, EDGE, 0>(p, cp, k, st, it);
-    quad_iter3<true, true, true, EDGE, 1>(p, cp, k, st, it + 1);
-    quad_iter3<true, true, true, EDGE, 2>(p, cp, k, st, it + 2);
-    quad_iter3<true, true, true, EDGE, 3>(p, cp, k, st, it + 3);
-    st.r.phn ^= 1u;
-}
-
-// plane iterations [it, end) with all three levels; the steady part in trips of twelve with compile-time ring indices
+// plane iterations [it, end) with all three levels.  RNMF_TB3_UNROLL (A/B builds): 3 = the three-plane register windows rotate by
+// renaming, 1 = smallest code (the steady loops of all warps of a CTA should stay inside the 32 KB instruction cache)
+#ifndef RNMF_TB3_UNROLL
+#define RNMF_TB3_UNROLL 3
+#endif
 template <int EDGE>
 __device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, int& it, const int end)
 {
-#ifdef RNMF_DYNAMIC_RING          // A/B builds only (scripts/build_alt.sh): the run-time ring everywhere
-    constexpr bool kStatic = false;
-#else
-    constexpr bool kStatic = EDGE != 2;
-#endif
-    if (kStatic) {
-        for (; it < end && ((it & 3) != 0 || it < 4); ++it) quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
-        for (; it + 12 <= end; it += 12) {
-            quad_four3<EDGE>(p, cp, k, st, it);
-            quad_four3<EDGE>(p, cp, k, st, it + 4);
-            quad_four3<EDGE>(p, cp, k, st, it + 8);
+    if (RNMF_TB3_UNROLL == 3) {
+        for (; it + 3 <= end; it += 3) {
+            quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
+            quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 1);
+            quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 2);
         }
     }
+#pragma unroll 1
     for (; it < end; ++it) quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
 }
 
@@ -380,7 +372,7 @@ struct HaloSt3 {
     Ring3 r;
 };
 
-template <bool TOP, bool L1, bool L2, int R = -1>
+template <bool TOP, bool L1, bool L2>
 __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& cp, const HaloK3& k, HaloSt3& st, const int it)
 {
     using C = Cfg3;
@@ -389,16 +381,12 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, qc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
-    // ring position, static for R >= 0: as in quad_iter3
-    const uint32_t sc = R >= 0 ? (uint32_t)((R + 1) & 3) : st.r.sc;
-    const uint32_t sn = R >= 0 ? (uint32_t)((R + 2) & 3) : st.r.sn;
-    const uint32_t phn = R >= 0 ? st.r.phn ^ (R >= 2 ? 1u : 0u) : st.r.phn;
-    const uint32_t slot = R >= 0 ? (uint32_t)(R & 1) : (uint32_t)(it & 1);
-    const uint32_t pslot = slot ^ 1u;
-    const uint32_t pu = R >= 0 ? ((R == 0 || R == 3) ? 1u : 0u) : (uint32_t)((it - 1) >> 1) & 1u;
+    const uint32_t sc = st.r.sc, sn = st.r.sn;
+    const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;
+    const uint32_t w2 = st.r.u2w;
 
-    if (L1) mbar_wait(k.full0 + 8 * sn, phn);
-    if (it >= 1) { mbar_wait(k.u1full0 + 8 * pslot, pu); mbar_wait(k.u2full0 + 8 * pslot, pu); }
+    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);
+    if (it >= 1) { mbar_wait(k.u1full0 + 8 * pslot, pu); mbar_wait(k.u2full0 + 8 * st.r.u2r(), st.r.u2rp()); }     // as in quad_iter3
 
     if (L2) {
         // inner row: the neighbour row towards the tile comes from the ring, the other one is the lane's own outer row
@@ -441,7 +429,7 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
         if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
     }
     if (L2) {
-        const uint32_t b = k.u2a + slot * C::U2_SLOT;
+        const uint32_t b = k.u2a + w2 * C::U2_SLOT;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             double2 dn = st.u1lo_in[h], up = u1n[2 * IN + h];
@@ -451,15 +439,16 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
             if (h == 0 ? k.ok_a : k.ok_b) stp(b + 256 * h, v);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);
     } else {
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * slot);               // keeps the barrier's phases in step with `it`
+        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);                 // keeps the barrier's phases in step with `it`
     }
     if (L1) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { st.below[q] = st.cur[q]; st.cur[q] = above[q]; }
-        if (R < 0) st.r.advance();
+        st.r.advance_u0();
     }
+    st.r.advance_u2();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         st.u1lo_in[h] = st.u1c_in[h];
@@ -474,15 +463,7 @@ __device__ __forceinline__ void halo_rows3(const Tb3Params& p, const ChunkPlan& 
 {
     int it = 0;
     for (; it < cp.it2_first && it < cp.nL1; ++it) halo_iter3<TOP, true, false>(p, cp, k, st, it);
-    // steady part: trips of four iterations from it % 4 == 0 with compile-time ring indices (it >= 4 there)
-    for (; it < cp.nL1 && ((it & 3) != 0 || it < 4); ++it) halo_iter3<TOP, true, true>(p, cp, k, st, it);
-    for (; it + 4 <= cp.nL1; it += 4) {
-        halo_iter3<TOP, true, true, 0>(p, cp, k, st, it);
-        halo_iter3<TOP, true, true, 1>(p, cp, k, st, it + 1);
-        halo_iter3<TOP, true, true, 2>(p, cp, k, st, it + 2);
-        halo_iter3<TOP, true, true, 3>(p, cp, k, st, it + 3);
-        st.r.phn ^= 1u;
-    }
+#pragma unroll 1
     for (; it < cp.nL1; ++it) halo_iter3<TOP, true, true>(p, cp, k, st, it);
     for (; it <= cp.it2_last; ++it) halo_iter3<TOP, false, true>(p, cp, k, st, it);
 }
@@ -544,8 +525,8 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         }
         mbar_init(u1full0, C::NCONS);
         mbar_init(u1full0 + 8, C::NCONS);
-        mbar_init(u2full0, C::NCONS);
-        mbar_init(u2full0 + 8, C::NCONS);
+#pragma unroll
+        for (int q = 0; q < C::NU2; ++q) mbar_init(u2full0 + 8 * q, C::NCONS);
         mbar_fence_init();
         if (sync_lo) peer_spin_wait(p.ps.wait_lo, p.ps.epoch, p.ps.status);
         if (sync_hi) peer_spin_wait(p.ps.wait_hi, p.ps.epoch, p.ps.status);
@@ -602,12 +583,13 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         mbar_wait(full0 + 8, 0);
         double cur_i = lds1(hpi + C::U0_STAGE), cur_o = lds1(hpo + C::U0_STAGE);
         double u1lo_i = 0.0, u1c_i = 0.0, q1_i = 0.0;
-        Ring3 rg = { 1, 2, 0 };
+        Ring3 rg = { 1, 2, 0, 0, 0 };
         for (int it = 0; it <= cp.it2_last; ++it) {
             const bool l1 = it < nL1, l2 = it >= cp.it2_first;
             const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;
+            const uint32_t w2 = rg.u2w;
             if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
-            if (it >= 1) { mbar_wait(u1full0 + 8 * pslot, pu); mbar_wait(u2full0 + 8 * pslot, pu); }      // as in quad_iter3
+            if (it >= 1) { mbar_wait(u1full0 + 8 * pslot, pu); mbar_wait(u2full0 + 8 * rg.u2r(), rg.u2rp()); }      // as in quad_iter3
             double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, qc_i = 0.0;
             if (l2) {
                 const uint32_t so = pslot * C::U1_SLOT;
@@ -641,17 +623,18 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
                 if (it == cp.it_zlo2) dn = ghost1(fz0, u1c_i);
                 if (!l1) up = ghost1(fz1, u1c_i);
                 const double v = fin3(P2, c3, up, dn);
-                if (ok2) sts1(u2i + slot * C::U2_SLOT, v);
+                if (ok2) sts1(u2i + w2 * C::U2_SLOT, v);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(u2full0 + 8 * slot);
+                if (lane == 0) mbar_arrive(u2full0 + 8 * w2);
             } else {
-                if (lane == 0) mbar_arrive(u2full0 + 8 * slot);           // keeps the barrier's phases in step with `it`
+                if (lane == 0) mbar_arrive(u2full0 + 8 * w2);             // keeps the barrier's phases in step with `it`
             }
             if (l1) {
                 below_i = cur_i; below_o = cur_o;
                 cur_i = above_i; cur_o = above_o;
-                rg.advance();
+                rg.advance_u0();
             }
+            rg.advance_u2();
             u1lo_i = u1c_i; u1c_i = u1n_i; q1_i = qc_i;
         }
     } else if (warp >= TY) {
@@ -683,7 +666,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         st.cur[0] = lds2(k.pa + C::U0_STAGE); st.cur[1] = lds2(k.pa + C::U0_STAGE + 512);
         st.cur[2] = lds2(k.pa + C::U0_STAGE + RB0); st.cur[3] = lds2(k.pa + C::U0_STAGE + RB0 + 512);
         for (int h = 0; h < 2; ++h) { st.u1c_out[h] = zero2; st.u1lo_in[h] = zero2; st.u1c_in[h] = zero2; st.q1_in[h] = zero2; }
-        st.r = Ring3{ 1, 2, 0 };
+        st.r = Ring3{ 1, 2, 0, 0, 0 };
         if (top) halo_rows3<true>(p, cp, k, st);
         else halo_rows3<false>(p, cp, k, st);
     } else {
@@ -731,7 +714,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         st.u2lo_a = zero2; st.u2lo_b = zero2; st.u2c_a = zero2; st.u2c_b = zero2;
         st.q1_a = zero2; st.q1_b = zero2; st.q2_a = zero2; st.q2_b = zero2;
         st.oa = p.out + p.g.at(ia, jA, k0, 0);
-        st.r = Ring3{ 1, 2, 0 };
+        st.r = Ring3{ 1, 2, 0, 0, 0 };
 
         // warp-uniform: all 32 patches are whole and no y face touches them -> the steady iterations that meet neither a z face
         // nor a neighbour's plane run without ghost code / store masks
