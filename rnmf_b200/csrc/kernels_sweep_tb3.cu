@@ -104,16 +104,32 @@ __device__ __forceinline__ void stp(uint32_t b, const double2& v) { sts1(b, v.x)
 // pair next to the face lives
 constexpr uint32_t kW = Cfg3::ODD - 8, kE = 8;
 
-// ring positions shared by every consumer warp.  u0 / rhs: stage of plane a1+it (sc), of plane a1+it+1 (sn), parity its full barrier
-// completes with (phn).  u2: slot level 2 writes in this iteration (u2w = it % 3) and the parity its barrier completes with
-// (u2p = (it / 3) & 1); level 3 reads the slot written one iteration ago.  (u1: slot it & 1, parity (it >> 1) & 1.)
-struct Ring3 {
-    uint32_t sc, sn, phn, u2w, u2p;
-    __device__ __forceinline__ void advance_u0() { sc = sn; if (++sn == (uint32_t)Cfg3::NS) { sn = 0; phn ^= 1u; } }
-    __device__ __forceinline__ void advance_u2() { if (++u2w == (uint32_t)Cfg3::NU2) { u2w = 0; u2p ^= 1u; } }
-    __device__ __forceinline__ uint32_t u2r() const { return u2w == 0 ? (uint32_t)Cfg3::NU2 - 1 : u2w - 1; }     // slot written in iteration it-1
-    __device__ __forceinline__ uint32_t u2rp() const { return u2w == 0 ? u2p ^ 1u : u2p; }                       // ... and its parity
+// Ring positions of iteration `it`, shared by every consumer warp and derived from the iteration number alone (no loop-carried ring
+// state: the kernel lives at the 128-register limit, and what spills goes through an L1 that the 223 KB of shared memory leave
+// almost no room for).  u0 / rhs: stage of plane a1+it (sc), of plane a1+it+1 (sn), parity its full barrier completes with (phn).
+// u1: slot level 1 writes (u1w = it & 1), the slot written one iteration ago and the parity of its barrier (u1r, u1rp).
+// u2: three slots, u2w = it % 3; the slot written one iteration ago and its parity (u2r, u2rp).
+struct RingAt {
+    uint32_t sc, sn, phn, u1w, u1r, u1rp, u2w, u2r, u2rp;
 };
+__device__ __forceinline__ RingAt ring_at(const int it)
+{
+    RingAt r;
+    const uint32_t u = (uint32_t)it;
+    r.sc = (u + 1u) & 3u;
+    r.sn = (u + 2u) & 3u;
+    r.phn = ((u + 2u) >> 2) & 1u;
+    r.u1w = u & 1u;
+    r.u1r = r.u1w ^ 1u;
+    r.u1rp = ((u - 1u) >> 1) & 1u;                        // it >= 1 wherever it is used
+    const uint32_t q = u / 3u;
+    r.u2w = u - 3u * q;
+    r.u2r = r.u2w == 0 ? 2u : r.u2w - 1u;
+    r.u2rp = (r.u2w == 0 ? q + 1u : q) & 1u;              // (it - 1) / 3
+    return r;
+}
+// barriers behind one base address: full[NS], empty[NS], u1full[2], u2full[3]
+constexpr uint32_t kEmpty = 8 * Cfg3::NS, kU1Full = 16 * Cfg3::NS, kU2Full = 16 * Cfg3::NS + 16;
 
 // what every consumer warp of the CTA knows about the chunk (CTA-uniform)
 struct ChunkPlan {
@@ -129,7 +145,7 @@ struct ChunkPlan {
 // ---------------------------------------------------------------------------------------------------
 struct QuadK3 {
     uint32_t pa, ra, u1a, u2a;           // the lane's first cell (row A): u0 stage 0, rhs stage 0, u1 slot 0, u2 slot 0 (even half)
-    uint32_t full0, empty0, u1full0, u2full0;
+    uint32_t bar0;                       // the CTA's barriers (full[0])
     bool ok;                             // the 2 x 2 patch lies inside the frame
     bool xlo, xhi, ylo, yhi;             // it touches that physical face (and the face has a Dirichlet / Neumann rule)
     Face1 fx0, fx1, fy0, fy1, fz0, fz1;
@@ -144,7 +160,6 @@ struct QuadSt3 {
     double2 u2lo_a, u2lo_b, u2c_a, u2c_b;        // u2 of planes a1+it-3, a1+it-2
     double2 q1_a, q1_b, q2_a, q2_b;              // c0*rhs of planes a1+it-1, a1+it-2
     double* oa;                                  // where u3 of plane a1+it-2 goes
-    Ring3 r;
 };
 
 // the lane's patch of one level into a ring slot, with the ghost values fill_bc would give that level on the physical x / y faces
@@ -194,7 +209,24 @@ __device__ __forceinline__ void plane_store3(const QuadK3& k, const int pitch, d
 // Ring hazards: level 2 loads from the u1 slot that level 1 of the NEXT iteration overwrites -- every warp starts that iteration
 // behind the wait for this iteration's u2 arrivals, which follow the loads; level 3 loads from the u2 slot written one iteration
 // ago AFTER this warp's u2 arrival, so that slot must survive the next iteration's level 2: three u2 slots.
-template <bool L1, bool L2, bool L3, int EDGE>
+// A/B knobs (scripts/build_alt.sh): RNMF_TB3_UNROLL = plane iterations per trip of the steady loop (1, 2, 3); RNMF_TB3_ORDER = 0: level 3's
+// x/y part is formed at the top of the iteration (its loads overlap level 1), 1: levels strictly in the order 1, 2, 3;
+// RNMF_TB3_U1LATE = 1: the wait for the u1 plane follows level 1
+#ifndef RNMF_TB3_UNROLL
+#define RNMF_TB3_UNROLL 3
+#endif
+#ifndef RNMF_TB3_ORDER
+#define RNMF_TB3_ORDER 1
+#endif
+#ifndef RNMF_TB3_PREFETCH
+#define RNMF_TB3_PREFETCH 4        // planes ahead of the TMA load that are prefetched into the L2 (0: none)
+#endif
+#ifndef RNMF_TB3_U1LATE
+#define RNMF_TB3_U1LATE 1
+#endif
+// PAR: it & 1 when known at compile time (the steady loop is unrolled by two: the u1 slots become constants and the register windows
+// -- two live planes per level -- rotate by renaming), -1 otherwise.
+template <bool L1, bool L2, bool L3, int EDGE, int PAR = -1>
 __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
 {
     using C = Cfg3;
@@ -203,19 +235,31 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above_a = zero2, above_b = zero2, qc_a = zero2, qc_b = zero2;
     double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2;
-    const uint32_t sc = st.r.sc, sn = st.r.sn;
-    const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;      // u1 ring
-    const uint32_t w2 = st.r.u2w, r2 = st.r.u2r();                                                        // u2 ring
+    const RingAt rg = ring_at(it);
+    const uint32_t sc = rg.sc, sn = rg.sn;
+    const uint32_t slot = PAR >= 0 ? (uint32_t)PAR : rg.u1w, pslot = slot ^ 1u, pu = rg.u1rp;      // u1 ring
+    const uint32_t w2 = rg.u2w, r2 = rg.u2r;                                                       // u2 ring
 
     // ---- wait phase ----------------------------------------------------------------------------------
-    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);                                            // u0 plane a1+it+1
-    if (it >= 1) {
-        // u1 plane a1+it-1 complete (level 2 reads it) ...
-        if (L1 || L2) mbar_wait(k.u1full0 + 8 * pslot, pu);
-        // ... and every warp is through iteration it-1 up to its u2 arrival (dummy arrivals while level 2 is not active yet): u2
-        // plane a1+it-2 is complete (level 3 reads it), every warp has left iteration it-2 (whose level 3 read the u2 slot level 2
-        // overwrites below), and nobody reads the u1 slot level 1 overwrites below any more
-        mbar_wait(k.u2full0 + 8 * r2, st.r.u2rp());
+    if (L1) mbar_wait(k.bar0 + 8 * sn, rg.phn);                                              // u0 plane a1+it+1
+    // every warp is through iteration it-1 up to its u2 arrival (dummy arrivals while level 2 is not active yet): u2 plane a1+it-2 is
+    // complete (level 3 reads it), every warp has left iteration it-2 (whose level 3 read the u2 slot level 2 overwrites below), and
+    // nobody reads the u1 slot level 1 overwrites below any more.  (The wait for the u1 plane follows level 1: the halo-row warps
+    // arrive for it late in their iteration.)
+    if (it >= 1) mbar_wait(k.bar0 + kU2Full + 8 * r2, rg.u2rp);
+    if (!RNMF_TB3_U1LATE && L2) mbar_wait(k.bar0 + kU1Full + 8 * pslot, pu);
+
+    double2 P3_a = zero2, P3_b = zero2;
+    if (RNMF_TB3_ORDER == 0 && L3) {
+        const uint32_t b = k.u2a + r2 * C::U2_SLOT;
+        const double2 s_a = ldp(b - RBU);
+        const double w_a = lds1(b + kW), e_a = lds1(b + kE);
+        P3_a.x = part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
+        P3_a.y = part3(st.q2_a.y, c1, c2, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y);
+        const double2 n_b = ldp(b + 2 * RBU);
+        const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
+        P3_b.x = part3(st.q2_b.x, c1, c2, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x);
+        P3_b.y = part3(st.q2_b.y, c1, c2, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y);
     }
 
     // ---- level 1: u1 of plane a1+it (row A, then row B) --------------------------------------------------
@@ -238,13 +282,14 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
             u1n_b.y = fin3(part3(qc_b.y, c1, c2, e_b, st.cur_b.x, n_b.y, st.cur_a.y), c3, above_b.y, st.below_b.y);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);                  // this warp is done with the stage of plane a1+it
+        if (k.lane == 0) mbar_arrive(k.bar0 + kEmpty + 8 * sc);                  // this warp is done with the stage of plane a1+it
         ring_store<EDGE>(k, k.u1a + slot * C::U1_SLOT, u1n_a, u1n_b);
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU1Full + 8 * slot);
     }
     // ---- level 2: u2 of plane a1+it-1; x/y neighbours from the u1 ring, z neighbours from registers --------------
     if (L2) {
+        if (RNMF_TB3_U1LATE) mbar_wait(k.bar0 + kU1Full + 8 * pslot, pu);        // u1 plane a1+it-1 complete (it >= 1 wherever level 2 is active)
         const uint32_t b = k.u1a + pslot * C::U1_SLOT;
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
         if (EDGE == 2 && it == cp.it_zlo2) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
@@ -263,9 +308,9 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         }
         ring_store<EDGE>(k, k.u2a + w2 * C::U2_SLOT, u2n_a, u2n_b);
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * w2);
     } else if (L1) {
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);                 // level 2 not active yet: keep the barrier's phases in step with `it`
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * w2);                 // level 2 not active yet: keep the barrier's phases in step with `it`
     }
     // ---- level 3: u3 of plane a1+it-2; x/y neighbours from the u2 ring, z neighbours from registers --------------
     if (L3) {
@@ -275,13 +320,14 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         if (zlo) { dn_a = ghost1(k.fz0, st.u2c_a); dn_b = ghost1(k.fz0, st.u2c_b); }
         if (!L2) { up_a = ghost1(k.fz1, st.u2c_a); up_b = ghost1(k.fz1, st.u2c_b); }
         double2 na, nb;
-        {
+        if (RNMF_TB3_ORDER == 0) {
+            na = fin3(P3_a, c3, up_a, dn_a);
+            nb = fin3(P3_b, c3, up_b, dn_b);
+        } else {
             const double2 s_a = ldp(b - RBU);
             const double w_a = lds1(b + kW), e_a = lds1(b + kE);
             na.x = fin3(part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x), c3, up_a.x, dn_a.x);
             na.y = fin3(part3(st.q2_a.y, c1, c2, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y), c3, up_a.y, dn_a.y);
-        }
-        {
             const double2 n_b = ldp(b + 2 * RBU);
             const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
             nb.x = fin3(part3(st.q2_b.x, c1, c2, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x), c3, up_b.x, dn_b.x);
@@ -308,9 +354,7 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     if (L1) {
         st.below_a = st.cur_a; st.below_b = st.cur_b;
         st.cur_a = above_a; st.cur_b = above_b;
-        st.r.advance_u0();
     }
-    st.r.advance_u2();
     st.u2lo_a = st.u2c_a; st.u2lo_b = st.u2c_b;
     st.u2c_a = u2n_a; st.u2c_b = u2n_b;
     st.u1lo_a = st.u1c_a; st.u1lo_b = st.u1c_b;
@@ -331,15 +375,20 @@ __device__ __forceinline__ void quad_general3(const Tb3Params& p, const ChunkPla
     else if (l3) quad_iter3<false, false, true, 2>(p, cp, k, st, it);
 }
 
-// plane iterations [it, end) with all three levels.  RNMF_TB3_UNROLL (A/B builds): 3 = the three-plane register windows rotate by
-// renaming, 1 = smallest code (the steady loops of all warps of a CTA should stay inside the 32 KB instruction cache)
-#ifndef RNMF_TB3_UNROLL
-#define RNMF_TB3_UNROLL 3
-#endif
+// plane iterations [it, end) with all three levels, two per trip from an even `it` (small code: the steady loops of all warps of a
+// CTA have to stay inside the 32 KB instruction cache -- longer trips with compile-time ring indices were measured slower)
 template <int EDGE>
 __device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, int& it, const int end)
 {
-    if (RNMF_TB3_UNROLL == 3) {
+    if (RNMF_TB3_UNROLL == 2) {
+        if (it < end && (it & 1)) { quad_iter3<true, true, true, EDGE>(p, cp, k, st, it); ++it; }
+#pragma unroll 1
+        for (; it + 2 <= end; it += 2) {
+            quad_iter3<true, true, true, EDGE, 0>(p, cp, k, st, it);
+            quad_iter3<true, true, true, EDGE, 1>(p, cp, k, st, it + 1);
+        }
+    } else if (RNMF_TB3_UNROLL == 3) {
+#pragma unroll 1
         for (; it + 3 <= end; it += 3) {
             quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
             quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 1);
@@ -356,7 +405,7 @@ __device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& c
 // ---------------------------------------------------------------------------------------------------
 struct HaloK3 {
     uint32_t pa, ra, u1a, u2a;           // row A, pair a: u0 stage 0, rhs stage 0, u1 slot 0; the INNER row's pair a in u2 slot 0
-    uint32_t full0, empty0, u1full0, u2full0;
+    uint32_t bar0;
     bool ok_a, ok_b;                     // pair a / pair b lies inside the frame (both rows do, or neither)
     bool xlo;                            // pair a starts at x = 0 next to a physical face with a rule
     int xhi;                             // 0 / 1: pair a / b ends at x = n0-1 next to a physical face with a rule; -1: neither
@@ -369,7 +418,6 @@ struct HaloSt3 {
     double2 u1c_out[2];                  // u1 of plane a1+it-1, the outer row (pairs a, b)
     double2 u1lo_in[2], u1c_in[2];       // u1 of planes a1+it-2, a1+it-1, the inner row
     double2 q1_in[2];                    // c0*rhs of plane a1+it-1, the inner row
-    Ring3 r;
 };
 
 template <bool TOP, bool L1, bool L2>
@@ -381,12 +429,11 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, qc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
-    const uint32_t sc = st.r.sc, sn = st.r.sn;
-    const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;
-    const uint32_t w2 = st.r.u2w;
+    const RingAt rg = ring_at(it);
+    const uint32_t sc = rg.sc, sn = rg.sn, slot = rg.u1w, pslot = rg.u1r, w2 = rg.u2w;
 
-    if (L1) mbar_wait(k.full0 + 8 * sn, st.r.phn);
-    if (it >= 1) { mbar_wait(k.u1full0 + 8 * pslot, pu); mbar_wait(k.u2full0 + 8 * st.r.u2r(), st.r.u2rp()); }     // as in quad_iter3
+    if (L1) mbar_wait(k.bar0 + 8 * sn, rg.phn);
+    if (it >= 1) { mbar_wait(k.bar0 + kU1Full + 8 * pslot, rg.u1rp); mbar_wait(k.bar0 + kU2Full + 8 * rg.u2r, rg.u2rp); }     // as in quad_iter3
 
     if (L2) {
         // inner row: the neighbour row towards the tile comes from the ring, the other one is the lane's own outer row
@@ -418,7 +465,7 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
             qc_in[h] = IN ? q_b : q_a;
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.empty0 + 8 * sc);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kEmpty + 8 * sc);
         const uint32_t b = k.u1a + slot * C::U1_SLOT;
         if (k.ok_a) { stp(b, u1n[0]); stp(b + RBU, u1n[2]); }
         if (k.ok_b) { stp(b + 256, u1n[1]); stp(b + RBU + 256, u1n[3]); }
@@ -426,7 +473,7 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
         if (k.xlo) sts1(b + IN * RBU + kW, ghost1(k.fx0, u1n[2 * IN].x));
         if (k.xhi >= 0) sts1(b + IN * RBU + 256 * k.xhi + kE, ghost1(k.fx1, k.xhi ? u1n[2 * IN + 1].y : u1n[2 * IN].y));
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u1full0 + 8 * slot);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU1Full + 8 * slot);
     }
     if (L2) {
         const uint32_t b = k.u2a + w2 * C::U2_SLOT;
@@ -439,16 +486,14 @@ __device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& 
             if (h == 0 ? k.ok_a : k.ok_b) stp(b + 256 * h, v);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * w2);
     } else {
-        if (k.lane == 0) mbar_arrive(k.u2full0 + 8 * w2);                 // keeps the barrier's phases in step with `it`
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * w2);                 // keeps the barrier's phases in step with `it`
     }
     if (L1) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { st.below[q] = st.cur[q]; st.cur[q] = above[q]; }
-        st.r.advance_u0();
     }
-    st.r.advance_u2();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         st.u1lo_in[h] = st.u1c_in[h];
@@ -483,7 +528,8 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
     const uint32_t u0_0 = sb, rhs_0 = sb + C::RHS_OFF, u1_0 = sb + C::U1_OFF, u2_0 = sb + C::U2_OFF;
     const uint32_t full0 = sb + C::BAR_OFF, empty0 = full0 + NS * 8, u1full0 = empty0 + NS * 8, u2full0 = u1full0 + 16;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps what derives from it in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long n0 = p.g.n[0], n1 = p.g.n[1], n2 = p.g.n[2];
     const long long i0 = (long long)blockIdx.x * TX;
     const long long j0 = (long long)blockIdx.y * TY;
@@ -543,6 +589,12 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
             for (int idx = 0; idx < n_planes; ++idx) {
                 if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
                 const bool with_rhs = idx >= 1 && idx <= nL1;
+                // the ring holds only two planes in flight: pull the planes behind them into the L2 so that their TMA loads see L2
+                // latency, not DRAM latency
+                if (RNMF_TB3_PREFETCH > 0 && idx + RNMF_TB3_PREFETCH < n_planes) {
+                    tma_prefetch_3d(&tm_u0, cx_u0, cy_u0, cz + RNMF_TB3_PREFETCH);
+                    if (idx + RNMF_TB3_PREFETCH <= nL1) tma_prefetch_3d(&tm_rhs, cx_rhs, cy_rhs, cz + RNMF_TB3_PREFETCH);
+                }
                 mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(C::U0_BYTES + (with_rhs ? C::RHS_BYTES : 0)));
                 tma_load_3d(u0_0 + s * C::U0_STAGE, &tm_u0, cx_u0, cy_u0, cz, full0 + 8 * s);
                 if (with_rhs) tma_load_3d(rhs_0 + s * C::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s);
@@ -583,13 +635,12 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         mbar_wait(full0 + 8, 0);
         double cur_i = lds1(hpi + C::U0_STAGE), cur_o = lds1(hpo + C::U0_STAGE);
         double u1lo_i = 0.0, u1c_i = 0.0, q1_i = 0.0;
-        Ring3 rg = { 1, 2, 0, 0, 0 };
         for (int it = 0; it <= cp.it2_last; ++it) {
+            const RingAt rg = ring_at(it);
             const bool l1 = it < nL1, l2 = it >= cp.it2_first;
-            const uint32_t slot = (uint32_t)(it & 1), pslot = slot ^ 1u, pu = (uint32_t)((it - 1) >> 1) & 1u;
-            const uint32_t w2 = rg.u2w;
+            const uint32_t slot = rg.u1w, pslot = rg.u1r, w2 = rg.u2w;
             if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
-            if (it >= 1) { mbar_wait(u1full0 + 8 * pslot, pu); mbar_wait(u2full0 + 8 * rg.u2r(), rg.u2rp()); }      // as in quad_iter3
+            if (it >= 1) { mbar_wait(u1full0 + 8 * pslot, rg.u1rp); mbar_wait(u2full0 + 8 * rg.u2r, rg.u2rp); }      // as in quad_iter3
             double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, qc_i = 0.0;
             if (l2) {
                 const uint32_t so = pslot * C::U1_SLOT;
@@ -632,9 +683,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
             if (l1) {
                 below_i = cur_i; below_o = cur_o;
                 cur_i = above_i; cur_o = above_o;
-                rg.advance_u0();
             }
-            rg.advance_u2();
             u1lo_i = u1c_i; u1c_i = u1n_i; q1_i = qc_i;
         }
     } else if (warp >= TY) {
@@ -650,7 +699,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         k.ra = rhs_0 + (uint32_t)(((rowA + 2) * C::BXR + 2 + 2 * lane) * 8);
         k.u1a = u1_0 + (uint32_t)(rowA + 2) * RBU + (uint32_t)(8 * (1 + lane));
         k.u2a = u2_0 + (uint32_t)((top ? TY : -1) + 1) * RBU + (uint32_t)(8 * (1 + lane));
-        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0; k.u2full0 = u2full0;
+        k.bar0 = full0;
         k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
         k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
         k.xlo = k.ok_a && k.fx0.on && xa == 0;
@@ -666,7 +715,6 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         st.cur[0] = lds2(k.pa + C::U0_STAGE); st.cur[1] = lds2(k.pa + C::U0_STAGE + 512);
         st.cur[2] = lds2(k.pa + C::U0_STAGE + RB0); st.cur[3] = lds2(k.pa + C::U0_STAGE + RB0 + 512);
         for (int h = 0; h < 2; ++h) { st.u1c_out[h] = zero2; st.u1lo_in[h] = zero2; st.u1c_in[h] = zero2; st.q1_in[h] = zero2; }
-        st.r = Ring3{ 1, 2, 0, 0, 0 };
         if (top) halo_rows3<true>(p, cp, k, st);
         else halo_rows3<false>(p, cp, k, st);
     } else {
@@ -682,7 +730,7 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         k.ra = rhs_0 + (uint32_t)(((ra + 2) * C::BXR + 2 + 2 * t) * 8);
         k.u1a = u1_0 + (uint32_t)(ra + 2) * RBU + (uint32_t)(8 * (1 + t));
         k.u2a = u2_0 + (uint32_t)(ra + 1) * RBU + (uint32_t)(8 * (1 + t));
-        k.full0 = full0; k.empty0 = empty0; k.u1full0 = u1full0; k.u2full0 = u2full0;
+        k.bar0 = full0;
         // offset of the lane's first cell inside a grown xy plane (the neighbours' ghost / deep planes)
         k.xy_off = p.g.xoff + (ia + p.g.ng) + p.g.pitch * (jA + p.g.ng);
         k.lane = lane;
@@ -714,7 +762,6 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         st.u2lo_a = zero2; st.u2lo_b = zero2; st.u2c_a = zero2; st.u2c_b = zero2;
         st.q1_a = zero2; st.q1_b = zero2; st.q2_a = zero2; st.q2_b = zero2;
         st.oa = p.out + p.g.at(ia, jA, k0, 0);
-        st.r = Ring3{ 1, 2, 0, 0, 0 };
 
         // warp-uniform: all 32 patches are whole and no y face touches them -> the steady iterations that meet neither a z face
         // nor a neighbour's plane run without ghost code / store masks

@@ -251,6 +251,8 @@ inline thread_local uint3 threadIdx, blockIdx;
 inline thread_local dim3 gridDim, blockDim;
 inline void __syncthreads() { emu::g_cta->cta_bar->arrive_and_wait(emu::g_cta->timed_out); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::g_cta->warp_bars[emu::g_warp]->arrive_and_wait(emu::g_cta->timed_out); }
+// broadcast of a value that every lane of the warp holds anyway (the kernels use it to tell the compiler "warp-uniform")
+inline int __shfl_sync(unsigned, int v, int) { return v; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
