@@ -78,8 +78,8 @@ struct Cfg3 {
     static constexpr int NU2 = 3;                          // u2 slots (three: level 3 reads a plane AFTER this warp's arrival for the next one)
     static constexpr int BAR_OFF = U2_OFF + NU2 * U2_SLOT;
     static constexpr int SMEM = BAR_OFF + (2 * NS + 2 + NU2) * 8 + 128;
-    static constexpr int NCONS = TY + 3;                   // 12 quad warps + 2 halo-row warps + 1 column warp
-    static constexpr int THREADS = 32 * (TY + 4);          // + producer warp
+    static constexpr int NCONS = TY + 4;                   // 12 quad warps + 2 inner-row warps + the column warp + the outer-rows warp (which is also the producer)
+    static constexpr int THREADS = 32 * (TY + 4);
     static_assert(SMEM <= 227 * 1024, "shared-memory budget");
     static_assert(U0_BYTES % 16 == 0 && RHS_BYTES % 16 == 0 && (BX0 * 8) % 16 == 0 && (BXR * 8) % 16 == 0, "TMA box rows are multiples of 16 bytes");
 };
@@ -400,117 +400,89 @@ __device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// halo-row warps: the row pair below (TOP = false: rows j0-2, j0-1) or above (TOP = true: rows j0+12, j0+13) the tile,
-// 128 columns (lane l: pairs at x = i0+2l and i0+64+2l).  Level 1 on both rows, level 2 on the row next to the tile.
+// inner-row warps: ONE 128-cell row next to the tile (j0-1 or j0+12; lane l: pairs at x = i0+2l and i0+64+2l), levels 1 and 2.
+// The same 8 cell updates per lane and iteration as the first two levels of a quad warp; both warps run the same code (the row
+// is a run-time offset), every x/y neighbour comes from shared memory.
 // ---------------------------------------------------------------------------------------------------
-struct HaloK3 {
-    uint32_t pa, ra, u1a, u2a;           // row A, pair a: u0 stage 0, rhs stage 0, u1 slot 0; the INNER row's pair a in u2 slot 0
+struct RowK3 {
+    uint32_t pa, ra, u1a, u2a;           // pair a of the row: u0 stage 0, rhs stage 0, u1 slot 0, u2 slot 0 (even half)
     uint32_t bar0;
-    bool ok_a, ok_b;                     // pair a / pair b lies inside the frame (both rows do, or neither)
+    bool ok_a, ok_b;                     // pair a / pair b lies inside the frame
     bool xlo;                            // pair a starts at x = 0 next to a physical face with a rule
     int xhi;                             // 0 / 1: pair a / b ends at x = n0-1 next to a physical face with a rule; -1: neither
     Face1 fx0, fx1, fz0, fz1;
     int lane;
 };
 
-struct HaloSt3 {
-    double2 below[4], cur[4];            // u0: Aa, Ab, Ba, Bb
-    double2 u1c_out[2];                  // u1 of plane a1+it-1, the outer row (pairs a, b)
-    double2 u1lo_in[2], u1c_in[2];       // u1 of planes a1+it-2, a1+it-1, the inner row
-    double2 q1_in[2];                    // c0*rhs of plane a1+it-1, the inner row
+struct RowSt3 {
+    double2 below[2], cur[2];            // u0 of planes a1+it-1, a1+it (pairs a, b)
+    double2 u1lo[2], u1c[2];             // u1 of planes a1+it-2, a1+it-1
+    double2 q1[2];                       // c0*rhs of plane a1+it-1
 };
 
-template <bool TOP, bool L1, bool L2>
-__device__ __forceinline__ void halo_iter3(const Tb3Params& p, const ChunkPlan& cp, const HaloK3& k, HaloSt3& st, const int it)
+template <bool L1, bool L2>
+__device__ __forceinline__ void row_iter3(const Tb3Params& p, const ChunkPlan& cp, const RowK3& k, RowSt3& st, const int it)
 {
     using C = Cfg3;
-    constexpr uint32_t RB0 = C::RB0, RBR = C::RBR, RBU = C::RBU;
-    constexpr int IN = TOP ? 0 : 1, OUT = TOP ? 1 : 0;      // row index (A = 0, B = 1) of the row next to the tile / the outer row
+    constexpr uint32_t RB0 = C::RB0, RBU = C::RBU;
     const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
     const double2 zero2 = make_double2(0.0, 0.0);
-    double2 above[4] = { zero2, zero2, zero2, zero2 }, u1n[4] = { zero2, zero2, zero2, zero2 }, qc_in[2] = { zero2, zero2 }, P2[2] = { zero2, zero2 };
+    double2 above[2] = { zero2, zero2 }, u1n[2] = { zero2, zero2 }, qc[2] = { zero2, zero2 };
     const RingAt rg = ring_at(it);
-    const uint32_t sc = rg.sc, sn = rg.sn, slot = rg.u1w, pslot = rg.u1r, w2 = rg.u2w;
 
-    if (L1) mbar_wait(k.bar0 + 8 * sn, rg.phn);
-    if (it >= 1) { mbar_wait(k.bar0 + kU1Full + 8 * pslot, rg.u1rp); mbar_wait(k.bar0 + kU2Full + 8 * rg.u2r, rg.u2rp); }     // as in quad_iter3
-
-    if (L2) {
-        // inner row: the neighbour row towards the tile comes from the ring, the other one is the lane's own outer row
-        const uint32_t b = k.u1a + pslot * C::U1_SLOT + IN * RBU;
-        const uint32_t bt = TOP ? b - RBU : b + RBU;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const double2 t = ldp(bt + 256 * h);
-            const double w = lds1(b + 256 * h + kW), e = lds1(b + 256 * h + kE);
-            const double2 n = TOP ? st.u1c_out[h] : t, s = TOP ? t : st.u1c_out[h];
-            P2[h].x = part3(st.q1_in[h].x, c1, c2, st.u1c_in[h].y, w, n.x, s.x);
-            P2[h].y = part3(st.q1_in[h].y, c1, c2, e, st.u1c_in[h].x, n.y, s.y);
-        }
-    }
+    if (L1) mbar_wait(k.bar0 + 8 * rg.sn, rg.phn);
+    if (it >= 1) mbar_wait(k.bar0 + kU2Full + 8 * rg.u2r, rg.u2rp);      // as in quad_iter3
     if (L1) {
-        const uint32_t pn = k.pa + sn * C::U0_STAGE, pc = k.pa + sc * C::U0_STAGE, pr = k.ra + sc * C::RHS_STAGE;
+        const uint32_t pn = k.pa + rg.sn * C::U0_STAGE, pc = k.pa + rg.sc * C::U0_STAGE, pr = k.ra + rg.sc * C::RHS_STAGE;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const uint32_t o = 512 * h;
-            above[h] = lds2(pn + o); above[2 + h] = lds2(pn + RB0 + o);
-            const double2 s_a = lds2(pc - RB0 + o), n_b = lds2(pc + 2 * RB0 + o);
-            const double2 q_a = mulc2(c0, lds2(pr + o)), q_b = mulc2(c0, lds2(pr + RBR + o));
-            const double w_a = lds1(pc + o - 8), e_a = lds1(pc + o + 16), w_b = lds1(pc + RB0 + o - 8), e_b = lds1(pc + RB0 + o + 16);
-            const double2 ca = st.cur[h], cb = st.cur[2 + h];
-            u1n[h].x = fin3(part3(q_a.x, c1, c2, ca.y, w_a, cb.x, s_a.x), c3, above[h].x, st.below[h].x);
-            u1n[h].y = fin3(part3(q_a.y, c1, c2, e_a, ca.x, cb.y, s_a.y), c3, above[h].y, st.below[h].y);
-            u1n[2 + h].x = fin3(part3(q_b.x, c1, c2, cb.y, w_b, n_b.x, ca.x), c3, above[2 + h].x, st.below[2 + h].x);
-            u1n[2 + h].y = fin3(part3(q_b.y, c1, c2, e_b, cb.x, n_b.y, ca.y), c3, above[2 + h].y, st.below[2 + h].y);
-            qc_in[h] = IN ? q_b : q_a;
+            qc[h] = mulc2(c0, lds2(pr + o));
+            const double2 n = lds2(pc + RB0 + o), s = lds2(pc - RB0 + o);
+            const double w = lds1(pc + o - 8), e = lds1(pc + o + 16);
+            above[h] = lds2(pn + o);
+            u1n[h].x = fin3(part3(qc[h].x, c1, c2, st.cur[h].y, w, n.x, s.x), c3, above[h].x, st.below[h].x);
+            u1n[h].y = fin3(part3(qc[h].y, c1, c2, e, st.cur[h].x, n.y, s.y), c3, above[h].y, st.below[h].y);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.bar0 + kEmpty + 8 * sc);
-        const uint32_t b = k.u1a + slot * C::U1_SLOT;
-        if (k.ok_a) { stp(b, u1n[0]); stp(b + RBU, u1n[2]); }
-        if (k.ok_b) { stp(b + 256, u1n[1]); stp(b + RBU + 256, u1n[3]); }
-        // the x-face ghosts of u1 that level 2 of the inner row reads
-        if (k.xlo) sts1(b + IN * RBU + kW, ghost1(k.fx0, u1n[2 * IN].x));
-        if (k.xhi >= 0) sts1(b + IN * RBU + 256 * k.xhi + kE, ghost1(k.fx1, k.xhi ? u1n[2 * IN + 1].y : u1n[2 * IN].y));
+        if (k.lane == 0) mbar_arrive(k.bar0 + kEmpty + 8 * rg.sc);
+        const uint32_t b = k.u1a + rg.u1w * C::U1_SLOT;
+        if (k.ok_a) stp(b, u1n[0]);
+        if (k.ok_b) stp(b + 256, u1n[1]);
+        // the x-face ghosts of u1 that level 2 of this row reads
+        if (k.xlo) sts1(b + kW, ghost1(k.fx0, u1n[0].x));
+        if (k.xhi >= 0) sts1(b + 256 * k.xhi + kE, ghost1(k.fx1, k.xhi ? u1n[1].y : u1n[0].y));
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.bar0 + kU1Full + 8 * slot);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU1Full + 8 * rg.u1w);
     }
     if (L2) {
-        const uint32_t b = k.u2a + w2 * C::U2_SLOT;
+        mbar_wait(k.bar0 + kU1Full + 8 * rg.u1r, rg.u1rp);               // u1 plane a1+it-1 complete
+        const uint32_t b = k.u1a + rg.u1r * C::U1_SLOT, b2 = k.u2a + rg.u2w * C::U2_SLOT;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            double2 dn = st.u1lo_in[h], up = u1n[2 * IN + h];
-            if (it == cp.it_zlo2) dn = ghost1(k.fz0, st.u1c_in[h]);
-            if (!L1) up = ghost1(k.fz1, st.u1c_in[h]);
-            const double2 v = fin3(P2[h], c3, up, dn);
-            if (h == 0 ? k.ok_a : k.ok_b) stp(b + 256 * h, v);
+            const uint32_t o = 256 * h;
+            const double2 n = ldp(b + RBU + o), s = ldp(b - RBU + o);
+            const double w = lds1(b + o + kW), e = lds1(b + o + kE);
+            double2 dn = st.u1lo[h], up = u1n[h];
+            if (it == cp.it_zlo2) dn = ghost1(k.fz0, st.u1c[h]);
+            if (!L1) up = ghost1(k.fz1, st.u1c[h]);
+            double2 v;
+            v.x = fin3(part3(st.q1[h].x, c1, c2, st.u1c[h].y, w, n.x, s.x), c3, up.x, dn.x);
+            v.y = fin3(part3(st.q1[h].y, c1, c2, e, st.u1c[h].x, n.y, s.y), c3, up.y, dn.y);
+            if (h == 0 ? k.ok_a : k.ok_b) stp(b2 + o, v);
         }
         __syncwarp();
-        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * w2);
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * rg.u2w);
     } else {
-        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * w2);                 // keeps the barrier's phases in step with `it`
-    }
-    if (L1) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { st.below[q] = st.cur[q]; st.cur[q] = above[q]; }
+        if (k.lane == 0) mbar_arrive(k.bar0 + kU2Full + 8 * rg.u2w);     // keeps the barrier's phases in step with `it`
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        st.u1lo_in[h] = st.u1c_in[h];
-        st.u1c_in[h] = u1n[2 * IN + h];
-        st.u1c_out[h] = u1n[2 * OUT + h];
-        st.q1_in[h] = qc_in[h];
+        if (L1) { st.below[h] = st.cur[h]; st.cur[h] = above[h]; }
+        st.u1lo[h] = st.u1c[h];
+        st.u1c[h] = u1n[h];
+        st.q1[h] = qc[h];
     }
-}
-
-template <bool TOP>
-__device__ __forceinline__ void halo_rows3(const Tb3Params& p, const ChunkPlan& cp, const HaloK3& k, HaloSt3& st)
-{
-    int it = 0;
-    for (; it < cp.it2_first && it < cp.nL1; ++it) halo_iter3<TOP, true, false>(p, cp, k, st, it);
-#pragma unroll 1
-    for (; it < cp.nL1; ++it) halo_iter3<TOP, true, true>(p, cp, k, st, it);
-    for (; it <= cp.it2_last; ++it) halo_iter3<TOP, false, true>(p, cp, k, st, it);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -580,27 +552,78 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
     __syncthreads();
 
     if (warp == TY + 3) {
-        // ------------------------------ producer warp ------------------------------
-        if (lane == 0) {
-            const int cx_u0 = (int)(p.g.xoff + p.g.ng + i0 - 4), cx_rhs = cx_u0 + 2;
-            const int cy_u0 = (int)(p.g.ng + j0 - 3), cy_rhs = cy_u0 + 1;
-            int cz = (int)(p.g.kg + a1 - 1) + p.zshift;
-            uint32_t s = 0, wrap = 0;
-            for (int idx = 0; idx < n_planes; ++idx) {
-                if (wrap > 0) mbar_wait(empty0 + 8 * s, (wrap - 1) & 1u);
-                const bool with_rhs = idx >= 1 && idx <= nL1;
-                // the ring holds only two planes in flight: pull the planes behind them into the L2 so that their TMA loads see L2
-                // latency, not DRAM latency
-                if (RNMF_TB3_PREFETCH > 0 && idx + RNMF_TB3_PREFETCH < n_planes) {
-                    tma_prefetch_3d(&tm_u0, cx_u0, cy_u0, cz + RNMF_TB3_PREFETCH);
-                    if (idx + RNMF_TB3_PREFETCH <= nL1) tma_prefetch_3d(&tm_rhs, cx_rhs, cy_rhs, cz + RNMF_TB3_PREFETCH);
-                }
-                mbar_arrive_expect_tx(full0 + 8 * s, (uint32_t)(C::U0_BYTES + (with_rhs ? C::RHS_BYTES : 0)));
-                tma_load_3d(u0_0 + s * C::U0_STAGE, &tm_u0, cx_u0, cy_u0, cz, full0 + 8 * s);
-                if (with_rhs) tma_load_3d(rhs_0 + s * C::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz, full0 + 8 * s);
-                ++cz;
-                if (++s == NS) { s = 0; ++wrap; }
+        // ------------------------------ outer-rows warp, also the producer ------------------------------
+        // Level 1 on the rows j0-2 and j0+13 (lane l: pairs at x = i0+2l and i0+64+2l of either row; every neighbour from shared
+        // memory).  Lane 0 also feeds the ring: at the top of iteration `it` it waits for the stage that held plane a1+it-1 (every
+        // warp released it during iteration it-1) and loads plane a1+it+3 into it -- two iterations before it is read.
+        const double c0 = p.c.c0, c1 = p.c.c1, c2 = p.c.c2, c3 = p.c.c3;
+        const int cx_u0 = (int)(p.g.xoff + p.g.ng + i0 - 4), cx_rhs = cx_u0 + 2;
+        const int cy_u0 = (int)(p.g.ng + j0 - 3), cy_rhs = cy_u0 + 1;
+        const int cz0 = (int)(p.g.kg + a1 - 1) + p.zshift;                    // z coordinate of plane index 0 (plane a1-1)
+        auto load_plane = [&](int idx) {                                      // lane 0: plane index idx -> stage idx % NS
+            const uint32_t sg = (uint32_t)idx & (NS - 1);
+            const bool with_rhs = idx >= 1 && idx <= nL1;
+            mbar_arrive_expect_tx(full0 + 8 * sg, (uint32_t)(C::U0_BYTES + (with_rhs ? C::RHS_BYTES : 0)));
+            tma_load_3d(u0_0 + sg * C::U0_STAGE, &tm_u0, cx_u0, cy_u0, cz0 + idx, full0 + 8 * sg);
+            if (with_rhs) tma_load_3d(rhs_0 + sg * C::RHS_STAGE, &tm_rhs, cx_rhs, cy_rhs, cz0 + idx, full0 + 8 * sg);
+        };
+        if (lane == 0)
+            for (int idx = 0; idx < NS && idx < n_planes; ++idx) load_plane(idx);
+        const bool ok_bot = j0 > 0, ok_top = j0 + TY + 1 < n1;
+        const long long xa = i0 + 2 * lane, xb = xa + 64;
+        const bool okx[2] = { xa < n0, xb < n0 };
+        // rows: q = 0: j0-2 (tile row -2), q = 1: j0+13 (tile row TY+1); pair h of row q lives in v[2q+h]
+        const int trow[2] = { -2, TY + 1 };
+        uint32_t pa[2], ra[2], ua[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            pa[q] = u0_0 + (uint32_t)(((trow[q] + 3) * C::BX0 + 4 + 2 * lane) * 8);
+            ra[q] = rhs_0 + (uint32_t)(((trow[q] + 2) * C::BXR + 2 + 2 * lane) * 8);
+            ua[q] = u1_0 + (uint32_t)(trow[q] + 2) * RBU + (uint32_t)(8 * (1 + lane));
+        }
+        double2 below[4], cur[4];
+        mbar_wait(full0, 0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) below[v] = lds2(pa[v >> 1] + 512 * (v & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0);
+        mbar_wait(full0 + 8, 0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) cur[v] = lds2(pa[v >> 1] + C::U0_STAGE + 512 * (v & 1));
+#pragma unroll 1
+        for (int it = 0; it <= cp.it2_last; ++it) {
+            const RingAt rg = ring_at(it);
+            const bool l1 = it < nL1;
+            if (lane == 0 && it + NS < n_planes) {
+                mbar_wait(empty0 + 8 * (uint32_t)(it & (NS - 1)), (uint32_t)(it >> 2) & 1u);      // plane index `it` released by every warp
+                load_plane(it + NS);
             }
+            if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
+            if (it >= 1) mbar_wait(u2full0 + 8 * rg.u2r, rg.u2rp);            // as in quad_iter3 (the u1 slot written below is free)
+            if (l1) {
+                double2 above[4], u1n[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const uint32_t o = 512 * (v & 1);
+                    const uint32_t pn = pa[v >> 1] + rg.sn * C::U0_STAGE + o, pc = pa[v >> 1] + rg.sc * C::U0_STAGE + o;
+                    const double2 q = mulc2(c0, lds2(ra[v >> 1] + rg.sc * C::RHS_STAGE + o));
+                    const double2 n = lds2(pc + RB0), s = lds2(pc - RB0);
+                    const double w = lds1(pc - 8), e = lds1(pc + 16);
+                    above[v] = lds2(pn);
+                    u1n[v].x = fin3(part3(q.x, c1, c2, cur[v].y, w, n.x, s.x), c3, above[v].x, below[v].x);
+                    u1n[v].y = fin3(part3(q.y, c1, c2, e, cur[v].x, n.y, s.y), c3, above[v].y, below[v].y);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * rg.sc);
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (((v >> 1) ? ok_top : ok_bot) && okx[v & 1]) stp(ua[v >> 1] + rg.u1w * C::U1_SLOT + 256 * (v & 1), u1n[v]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(u1full0 + 8 * rg.u1w);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { below[v] = cur[v]; cur[v] = above[v]; }
+            }
+            if (lane == 0) mbar_arrive(u2full0 + 8 * rg.u2w);                 // no level 2 here: keeps the barrier's phases in step with `it`
         }
     } else if (warp == TY + 2) {
         // ------------------------------ column warp ------------------------------
@@ -687,36 +710,38 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
             u1lo_i = u1c_i; u1c_i = u1n_i; q1_i = qc_i;
         }
     } else if (warp >= TY) {
-        // ------------------------------ halo-row warps ------------------------------
-        const bool top = warp == TY + 1;
-        const int rowA = top ? TY : -2;
-        const bool rows_ok = top ? j0 + TY < n1 : j0 > 0;
+        // ------------------------------ inner-row warps: row j0-1 (warp TY), row j0+12 (warp TY+1) ------------------------------
+        const int trow = warp == TY ? -1 : TY;
+        const long long y = j0 + trow;
+        const bool row_ok = y >= 0 && y < n1;
         const long long xa = i0 + 2 * lane, xb = xa + 64;
-        HaloK3 k;
-        k.ok_a = rows_ok && xa < n0;
-        k.ok_b = rows_ok && xb < n0;
-        k.pa = u0_0 + (uint32_t)(((rowA + 3) * C::BX0 + 4 + 2 * lane) * 8);
-        k.ra = rhs_0 + (uint32_t)(((rowA + 2) * C::BXR + 2 + 2 * lane) * 8);
-        k.u1a = u1_0 + (uint32_t)(rowA + 2) * RBU + (uint32_t)(8 * (1 + lane));
-        k.u2a = u2_0 + (uint32_t)((top ? TY : -1) + 1) * RBU + (uint32_t)(8 * (1 + lane));
+        RowK3 k;
+        k.ok_a = row_ok && xa < n0;
+        k.ok_b = row_ok && xb < n0;
+        k.pa = u0_0 + (uint32_t)(((trow + 3) * C::BX0 + 4 + 2 * lane) * 8);
+        k.ra = rhs_0 + (uint32_t)(((trow + 2) * C::BXR + 2 + 2 * lane) * 8);
+        k.u1a = u1_0 + (uint32_t)(trow + 2) * RBU + (uint32_t)(8 * (1 + lane));
+        k.u2a = u2_0 + (uint32_t)(trow + 1) * RBU + (uint32_t)(8 * (1 + lane));
         k.bar0 = full0;
         k.fx0 = make_face1(p.faces.f[0], true); k.fx1 = make_face1(p.faces.f[1], true);
         k.fz0 = make_face1(p.faces.f[4], true); k.fz1 = make_face1(p.faces.f[5], true);
         k.xlo = k.ok_a && k.fx0.on && xa == 0;
         k.xhi = !k.fx1.on ? -1 : (k.ok_a && xa + 2 == n0) ? 0 : (k.ok_b && xb + 2 == n0) ? 1 : -1;
         k.lane = lane;
-        HaloSt3 st;
+        RowSt3 st;
         const double2 zero2 = make_double2(0.0, 0.0);
         mbar_wait(full0, 0);
-        st.below[0] = lds2(k.pa); st.below[1] = lds2(k.pa + 512); st.below[2] = lds2(k.pa + RB0); st.below[3] = lds2(k.pa + RB0 + 512);
+        st.below[0] = lds2(k.pa); st.below[1] = lds2(k.pa + 512);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0);
         mbar_wait(full0 + 8, 0);
         st.cur[0] = lds2(k.pa + C::U0_STAGE); st.cur[1] = lds2(k.pa + C::U0_STAGE + 512);
-        st.cur[2] = lds2(k.pa + C::U0_STAGE + RB0); st.cur[3] = lds2(k.pa + C::U0_STAGE + RB0 + 512);
-        for (int h = 0; h < 2; ++h) { st.u1c_out[h] = zero2; st.u1lo_in[h] = zero2; st.u1c_in[h] = zero2; st.q1_in[h] = zero2; }
-        if (top) halo_rows3<true>(p, cp, k, st);
-        else halo_rows3<false>(p, cp, k, st);
+        for (int h = 0; h < 2; ++h) { st.u1lo[h] = zero2; st.u1c[h] = zero2; st.q1[h] = zero2; }
+        int it = 0;
+        for (; it < cp.it2_first && it < nL1; ++it) row_iter3<true, false>(p, cp, k, st, it);
+#pragma unroll 1
+        for (; it < nL1; ++it) row_iter3<true, true>(p, cp, k, st, it);
+        for (; it <= cp.it2_last; ++it) row_iter3<false, true>(p, cp, k, st, it);
     } else {
         // ------------------------------ quad warps: rows j0+2*rp, j0+2*rp+1 x columns i0+64*xh .. +63 ------------------------------
         const int xh = warp & 1, rp = warp >> 1;
