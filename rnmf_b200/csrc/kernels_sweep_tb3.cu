@@ -213,13 +213,13 @@ __device__ __forceinline__ void plane_store3(const QuadK3& k, const int pitch, d
 // x/y part is formed at the top of the iteration (its loads overlap level 1), 1: levels strictly in the order 1, 2, 3;
 // RNMF_TB3_U1LATE = 1: the wait for the u1 plane follows level 1
 #ifndef RNMF_TB3_UNROLL
-#define RNMF_TB3_UNROLL 3
+#define RNMF_TB3_UNROLL 1
 #endif
 #ifndef RNMF_TB3_ORDER
 #define RNMF_TB3_ORDER 1
 #endif
 #ifndef RNMF_TB3_PREFETCH
-#define RNMF_TB3_PREFETCH 4        // planes ahead of the TMA load that are prefetched into the L2 (0: none)
+#define RNMF_TB3_PREFETCH 0        // planes ahead of the TMA load that are prefetched into the L2 (0: none)
 #endif
 #ifndef RNMF_TB3_U1LATE
 #define RNMF_TB3_U1LATE 1
