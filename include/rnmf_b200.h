@@ -109,17 +109,19 @@ int32_t rnmf_ctx_rank(rnmf_ctx* ctx, int32_t* rank, int32_t* nranks);
 /* number of this library's kernels launched on the context since creation (graph replays count
  * their kernel nodes) -- bench.py's gpu_launches */
 int64_t rnmf_kernel_launches(rnmf_ctx* ctx);
-/* how many of those were double-sweep kernels (two Jacobi sweeps + ghost fills per pass over HBM, 2D and 3D;
- * rnmf_jacobi_sweeps pairs up every two sweeps that do not carry the norm) -- bench.py's roofline accounting */
+/* how many of those were double-sweep kernels (two Jacobi sweeps + ghost fills per pass over HBM, 2D and 3D: the pairs
+ * that the groups of three (3D) / four (2D) sweeps leave over, and 3D frames the three-sweep kernel does not take) */
 int64_t rnmf_double_sweep_launches(rnmf_ctx* ctx);
-/* all temporally blocked launches (two or more sweeps per pass over HBM: the double-sweep kernels and the four-sweep 2D
- * kernel) and the number of sweeps they covered, since the context was created; either pointer may be null */
+/* all temporally blocked launches (two or more sweeps per pass over HBM: the three-sweep 3D kernel, the four-sweep 2D
+ * kernel and the double-sweep kernels) and the number of sweeps they covered, since the context was created; either
+ * pointer may be null -- bench.py's roofline accounting */
 int32_t rnmf_multi_sweep_stats(rnmf_ctx* ctx, int64_t* launches, int64_t* sweeps);
 /* CUDA-event timer on the context's stream: begin records, end records+synchronises. */
 int32_t rnmf_timer_begin(rnmf_ctx* ctx);
 int32_t rnmf_timer_end(rnmf_ctx* ctx, double* elapsed_ms);
 /* tuning knobs for measurements (results never change, only which kernel / schedule produces them):
- *   "sweep_variant"  "auto" (default) or a number from the one table in csrc/kernels_sweep.cu: 3D 6 = one sweep per launch only;
+ *   "sweep_variant"  "auto" (default: 3D three, 2D four sweeps per launch) or a number from the one table in csrc/kernels_sweep.cu:
+ *                    3D 31 = two sweeps per launch (+ single sweeps), 6 = one sweep per launch only;
  *                    2D 30 = two sweeps per launch (+ single sweeps), 20 = one sweep per launch only
  *   "sweep_chunk"    planes / rows marched per CTA (0 = planner)
  *   "resident"       1/0: one cooperative launch for all sweeps of an L2-resident frame
@@ -192,8 +194,8 @@ int32_t rnmf_poisson_coefs(int32_t dim, const double* dx, double* coef4);
 /* The sweep of solve_poisson (poisson.rs:80-89) as out-of-place Jacobi:
  *   n_sweeps x { psi' = coef0*rhs + coef1*(E+W) + coef2*(N+S) [+ coef3*(U+D)] on valid cells;
  *                psi'.fill_bc() }        (association exactly as poisson.rs:83-85)
- * psi is updated in place from the caller's view (internally ping-pong; every two sweeps that do not carry
- * the norm run as ONE double-sweep launch with bit-identical results).  On a distributed
+ * psi is updated in place from the caller's view (internally ping-pong; groups of sweeps that do not carry
+ * the norm -- three in 3D, four in 2D -- run as ONE temporally blocked launch with bit-identical results).  On a distributed
  * context the slab halos are exchanged every sweep, overlapped with the interior update.
  * l1_update (nullable): sum |psi'_last - psi_prev| over valid cells (all ranks), i.e. the
  * quantity main.rs:68-69 forms with two frame operators and `sum`; requesting it synchronises. */
