@@ -54,7 +54,10 @@ ctx.set_option("e2e_skew", 0)
 print("plain", round(measure(), 1), flush=True)
 ctx.set_option("e2e_skew", 2)
 ref = None
-for chunks, pairs, tail in itertools.chain([(8, 56, 32)], itertools.product((4, 6, 8, 12, 16), (40, 56, 72, 96), (24, 32, 48))):
+# grid: RNMF_E2E_GRID="chunks;pairs;tail" (comma-separated values each), default = the round-2 grid around the defaults
+grid = os.environ.get("RNMF_E2E_GRID", "4,6,8,12,16;40,56,72,96;24,32,48").split(";")
+axes = [tuple(int(v) for v in a.split(",")) for a in grid]
+for chunks, pairs, tail in itertools.chain([(8, 56, 32)], itertools.product(*axes)):
     ctx.set_option("e2e_skew_chunks", chunks)
     ctx.set_option("e2e_skew_pairs", pairs)
     ctx.set_option("e2e_skew_tail", tail)
