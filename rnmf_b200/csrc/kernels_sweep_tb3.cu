@@ -7,27 +7,34 @@
 //
 //   * CTA tile: 128 x 12 cells of u3, a chunk of z-planes.  u2 is needed on the tile grown by one cell in x / y (no
 //     corners) and one plane in z, u1 on the tile grown by two (a diamond: Manhattan distance <= 2), u0 by three.
-//   * producer warp: per plane one TMA box of u0 (138 x 18: x from i0-4, y from j0-3) and one of rhs (134 x 16: x from
+//   * per plane one TMA box of u0 (138 x 18: x from i0-4, y from j0-3) and one of rhs (134 x 16: x from
 //     i0-2, y from j0-2) into a 4-stage ring (full / empty mbarriers).  The row lengths are chosen so that the column
 //     warp's accesses (one row apart) fall into different banks.
-//   * u1 and u2 planes live in two-slot rings with DE-INTERLEAVED rows: even x first, odd x from ODD bytes on.  A lane
+//   * u1 planes live in a two-slot ring, u2 planes in a three-slot ring, both with DE-INTERLEAVED rows: even x first, odd x from ODD bytes on.  A lane
 //     owns the pair (x, x+1), x even: its W neighbour is an odd position, its E neighbour an even one, so the E/W loads
 //     of a warp are dense 8-byte accesses (2 shared-memory wavefronts instead of the 4 that 8-byte accesses 16 bytes
 //     apart cost -- the shared-memory pipe is what bounds three levels per plane).
 //   * 12 "quad" warps own two adjacent tile rows x 64 columns each (lane: a 2 x 2 patch, as in the two-sweep kernel)
 //     and run all three levels on their cells, each level register z-marched over the lane's own values of the level
-//     below: in iteration `it` level 1 forms plane a1+it, level 2 plane a1+it-1, level 3 plane a1+it-2.
-//     Two halo-row warps own the row pairs (j0-2, j0-1) and (j0+12, j0+13) x 128 columns: level 1 on both rows,
-//     level 2 on the row next to the tile.  One warp owns the columns i0-2, i0-1, i0+128, i0+129 (level 1; level 2 on
-//     the inner ones) and the four diamond corners (level 1).
-//   * per iteration one wait phase (full[next u0 plane], u1full[slot of plane a1+it-1], u2full[slot of plane a1+it-2]);
-//     every consumer warp arrives on a slot's barrier after its stores, and the wait for the previous plane is also the
-//     write-after-read guard of the slot about to be overwritten (the two-sweep kernel's argument, once per ring).
-//   * level 3's and level 2's x/y parts (c0*rhs + c1*(E+W)) + c2*(N+S) are formed before the level below has produced
-//     the plane above; + c3*(U+D) is added afterwards: the reference's association (poisson.rs:83-88).
+//     below: in iteration `it` level 1 forms plane a1+it, level 2 plane a1+it-1, level 3 plane a1+it-2; c0*rhs is rounded
+//     once and queued in registers for the two later levels.
+//     Two inner-row warps own ONE 128-cell row next to the tile each (j0-1, j0+12): levels 1 and 2, the same 8 cell updates
+//     in front of their arrivals as a quad warp (row-PAIR warps with 12 paced every iteration).  One warp owns the columns
+//     i0-2, i0-1, i0+128, i0+129 (level 1; level 2 on the inner ones) and the four diamond corners.  The 16th warp forms
+//     level 1 on the outer rows j0-2, j0+13 and is also the producer: at the top of iteration `it` its lane 0 waits for the
+//     stage that held plane a1+it-1 and loads plane a1+it+3 into it.
+//   * levels run in the order 1, 2, 3, each loading what it needs right before it uses it (the kernel lives at the
+//     128-register limit; spills would go to an L1 that 223 KB of shared memory leave no room for).  A warp arrives on
+//     u1full[it & 1] after its level-1 stores and on u2full[it % 3] after its level-2 stores (dummy arrivals while level 2
+//     is not active yet: the phases stay in step with `it`).  One wait at the top -- u2full of the previous iteration: u2
+//     plane a1+it-2 is complete, every warp has left iteration it-2 (whose level 3 read the slot level 2 overwrites now:
+//     hence THREE u2 slots), and nobody reads the u1 slot level 1 overwrites any more (level 2's loads precede that
+//     arrival).  The wait for the u1 plane follows level 1.  All ring positions are functions of `it` (ring_at).
 //   * quad warps whose patch is whole and touches no y face run an interior-specialised copy of the steady loop
 //     (EDGE 0; EDGE 1 keeps the x-ghost code); the iterations that meet a z face or a plane that travels to a slab
-//     neighbour run the general code (EDGE 2).
+//     neighbour run the general code (EDGE 2).  The steady loop is NOT unrolled: 4.8 KB with 86 register moves per
+//     iteration beat every unrolled form (compile-time ring indices included) -- it has to fit the instruction caches
+//     (profiles/r2_notes.md, section 9).
 //
 // Restriction: n0 and n1 even (every 2 x 2 patch is whole or absent; the x-hi ghost is an even position); other frames
 // take the two-sweep kernel (capi.cu: plan_sweep_call).
