@@ -91,6 +91,41 @@ struct Cfg3 {
     static_assert(U0_BYTES % 16 == 0 && RHS_BYTES % 16 == 0 && (BX0 * 8) % 16 == 0 && (BXR * 8) % 16 == 0, "TMA box rows are multiples of 16 bytes");
 };
 
+// Barrier waits of this kernel.  RNMF_TB3_WAIT (A/B builds): 0 = mbarrier.try_wait with the suspend-time hint of tma_util.cuh (the other
+// kernels' choice: their consumers mostly wait for DRAM), 1 = try_wait without a hint, 2 = test_wait polling, 3 = test_wait with a short
+// nanosleep.  Sixteen warps meet at two barriers per plane here: what a late wake-up costs is paid every iteration.
+#ifndef RNMF_TB3_WAIT
+#define RNMF_TB3_WAIT 1
+#endif
+__device__ __forceinline__ void mbar_wait3(uint32_t bar, uint32_t parity)
+{
+#if defined(RNMF_EMULATE) || RNMF_TB3_WAIT == 0
+    mbar_wait(bar, parity);
+#elif RNMF_TB3_WAIT == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT3_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE3_%=;\n\t"
+        "bra WAIT3_%=;\n\t"
+        "DONE3_%=:\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+#else
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#if RNMF_TB3_WAIT == 3
+        if (!done) __nanosleep(32);
+#endif
+    } while (!done);
+#endif
+}
+
 // first two terms of poisson.rs:83-88 on q = c0*rhs (rounded once per cell and plane and reused by all three levels -- the same
 // product, so nothing changes in the result); the z term is added last (fin3): same association as upd3
 __device__ __forceinline__ double part3(double q, double c1, double c2, double e, double w, double n, double s)
@@ -248,13 +283,13 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     const uint32_t w2 = rg.u2w, r2 = rg.u2r;                                                       // u2 ring
 
     // ---- wait phase ----------------------------------------------------------------------------------
-    if (L1) mbar_wait(k.bar0 + 8 * sn, rg.phn);                                              // u0 plane a1+it+1
+    if (L1) mbar_wait3(k.bar0 + 8 * sn, rg.phn);                                              // u0 plane a1+it+1
     // every warp is through iteration it-1 up to its u2 arrival (dummy arrivals while level 2 is not active yet): u2 plane a1+it-2 is
     // complete (level 3 reads it), every warp has left iteration it-2 (whose level 3 read the u2 slot level 2 overwrites below), and
     // nobody reads the u1 slot level 1 overwrites below any more.  (The wait for the u1 plane follows level 1: the halo-row warps
     // arrive for it late in their iteration.)
-    if (it >= 1) mbar_wait(k.bar0 + kU2Full + 8 * r2, rg.u2rp);
-    if (!RNMF_TB3_U1LATE && L2) mbar_wait(k.bar0 + kU1Full + 8 * pslot, pu);
+    if (it >= 1) mbar_wait3(k.bar0 + kU2Full + 8 * r2, rg.u2rp);
+    if (!RNMF_TB3_U1LATE && L2) mbar_wait3(k.bar0 + kU1Full + 8 * pslot, pu);
 
     double2 P3_a = zero2, P3_b = zero2;
     if (RNMF_TB3_ORDER == 0 && L3) {
@@ -296,7 +331,7 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     }
     // ---- level 2: u2 of plane a1+it-1; x/y neighbours from the u1 ring, z neighbours from registers --------------
     if (L2) {
-        if (RNMF_TB3_U1LATE) mbar_wait(k.bar0 + kU1Full + 8 * pslot, pu);        // u1 plane a1+it-1 complete (it >= 1 wherever level 2 is active)
+        if (RNMF_TB3_U1LATE) mbar_wait3(k.bar0 + kU1Full + 8 * pslot, pu);        // u1 plane a1+it-1 complete (it >= 1 wherever level 2 is active)
         const uint32_t b = k.u1a + pslot * C::U1_SLOT;
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
         if (EDGE == 2 && it == cp.it_zlo2) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
@@ -437,8 +472,8 @@ __device__ __forceinline__ void row_iter3(const Tb3Params& p, const ChunkPlan& c
     double2 above[2] = { zero2, zero2 }, u1n[2] = { zero2, zero2 }, qc[2] = { zero2, zero2 };
     const RingAt rg = ring_at(it);
 
-    if (L1) mbar_wait(k.bar0 + 8 * rg.sn, rg.phn);
-    if (it >= 1) mbar_wait(k.bar0 + kU2Full + 8 * rg.u2r, rg.u2rp);      // as in quad_iter3
+    if (L1) mbar_wait3(k.bar0 + 8 * rg.sn, rg.phn);
+    if (it >= 1) mbar_wait3(k.bar0 + kU2Full + 8 * rg.u2r, rg.u2rp);      // as in quad_iter3
     if (L1) {
         const uint32_t pn = k.pa + rg.sn * C::U0_STAGE, pc = k.pa + rg.sc * C::U0_STAGE, pr = k.ra + rg.sc * C::RHS_STAGE;
 #pragma unroll
@@ -463,7 +498,7 @@ __device__ __forceinline__ void row_iter3(const Tb3Params& p, const ChunkPlan& c
         if (k.lane == 0) mbar_arrive(k.bar0 + kU1Full + 8 * rg.u1w);
     }
     if (L2) {
-        mbar_wait(k.bar0 + kU1Full + 8 * rg.u1r, rg.u1rp);               // u1 plane a1+it-1 complete
+        mbar_wait3(k.bar0 + kU1Full + 8 * rg.u1r, rg.u1rp);               // u1 plane a1+it-1 complete
         const uint32_t b = k.u1a + rg.u1r * C::U1_SLOT, b2 = k.u2a + rg.u2w * C::U2_SLOT;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -592,12 +627,12 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
             ua[q] = u1_0 + (uint32_t)(trow[q] + 2) * RBU + (uint32_t)(8 * (1 + lane));
         }
         double2 below[4], cur[4];
-        mbar_wait(full0, 0);
+        mbar_wait3(full0, 0);
 #pragma unroll
         for (int v = 0; v < 4; ++v) below[v] = lds2(pa[v >> 1] + 512 * (v & 1));
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0);
-        mbar_wait(full0 + 8, 0);
+        mbar_wait3(full0 + 8, 0);
 #pragma unroll
         for (int v = 0; v < 4; ++v) cur[v] = lds2(pa[v >> 1] + C::U0_STAGE + 512 * (v & 1));
 #pragma unroll 1
@@ -605,11 +640,11 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
             const RingAt rg = ring_at(it);
             const bool l1 = it < nL1;
             if (lane == 0 && it + NS < n_planes) {
-                mbar_wait(empty0 + 8 * (uint32_t)(it & (NS - 1)), (uint32_t)(it >> 2) & 1u);      // plane index `it` released by every warp
+                mbar_wait3(empty0 + 8 * (uint32_t)(it & (NS - 1)), (uint32_t)(it >> 2) & 1u);      // plane index `it` released by every warp
                 load_plane(it + NS);
             }
-            if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
-            if (it >= 1) mbar_wait(u2full0 + 8 * rg.u2r, rg.u2rp);            // as in quad_iter3 (the u1 slot written below is free)
+            if (l1) mbar_wait3(full0 + 8 * rg.sn, rg.phn);
+            if (it >= 1) mbar_wait3(u2full0 + 8 * rg.u2r, rg.u2rp);            // as in quad_iter3 (the u1 slot written below is free)
             if (l1) {
                 double2 above[4], u1n[4];
 #pragma unroll
@@ -661,19 +696,19 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         const Face1 fz0 = make_face1(p.faces.f[4], true), fz1 = make_face1(p.faces.f[5], true);
         const bool ylo = ok2 && fy0.on && y == 0, yhi = ok2 && fy1.on && y == n1 - 1;
 
-        mbar_wait(full0, 0);
+        mbar_wait3(full0, 0);
         double below_i = lds1(hpi), below_o = lds1(hpo);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0);
-        mbar_wait(full0 + 8, 0);
+        mbar_wait3(full0 + 8, 0);
         double cur_i = lds1(hpi + C::U0_STAGE), cur_o = lds1(hpo + C::U0_STAGE);
         double u1lo_i = 0.0, u1c_i = 0.0, q1_i = 0.0;
         for (int it = 0; it <= cp.it2_last; ++it) {
             const RingAt rg = ring_at(it);
             const bool l1 = it < nL1, l2 = it >= cp.it2_first;
             const uint32_t slot = rg.u1w, pslot = rg.u1r, w2 = rg.u2w;
-            if (l1) mbar_wait(full0 + 8 * rg.sn, rg.phn);
-            if (it >= 1) { mbar_wait(u1full0 + 8 * pslot, rg.u1rp); mbar_wait(u2full0 + 8 * rg.u2r, rg.u2rp); }      // as in quad_iter3
+            if (l1) mbar_wait3(full0 + 8 * rg.sn, rg.phn);
+            if (it >= 1) { mbar_wait3(u1full0 + 8 * pslot, rg.u1rp); mbar_wait3(u2full0 + 8 * rg.u2r, rg.u2rp); }      // as in quad_iter3
             double P2 = 0.0, u1n_i = 0.0, above_i = 0.0, above_o = 0.0, qc_i = 0.0;
             if (l2) {
                 const uint32_t so = pslot * C::U1_SLOT;
@@ -740,11 +775,11 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
         k.lane = lane;
         RowSt3 st;
         const double2 zero2 = make_double2(0.0, 0.0);
-        mbar_wait(full0, 0);
+        mbar_wait3(full0, 0);
         st.below[0] = lds2(k.pa); st.below[1] = lds2(k.pa + 512);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0);
-        mbar_wait(full0 + 8, 0);
+        mbar_wait3(full0 + 8, 0);
         st.cur[0] = lds2(k.pa + C::U0_STAGE); st.cur[1] = lds2(k.pa + C::U0_STAGE + 512);
         for (int h = 0; h < 2; ++h) { st.u1lo[h] = zero2; st.u1c[h] = zero2; st.q1[h] = zero2; }
         int it = 0;
@@ -787,11 +822,11 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
 
         QuadSt3 st;
         const double2 zero2 = make_double2(0.0, 0.0);
-        mbar_wait(full0, 0);
+        mbar_wait3(full0, 0);
         st.below_a = lds2(k.pa); st.below_b = lds2(k.pa + RB0);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0);
-        mbar_wait(full0 + 8, 0);
+        mbar_wait3(full0 + 8, 0);
         st.cur_a = lds2(k.pa + C::U0_STAGE); st.cur_b = lds2(k.pa + C::U0_STAGE + RB0);
         st.u1lo_a = zero2; st.u1lo_b = zero2; st.u1c_a = zero2; st.u1c_b = zero2;
         st.u2lo_a = zero2; st.u2lo_b = zero2; st.u2c_a = zero2; st.u2c_b = zero2;
