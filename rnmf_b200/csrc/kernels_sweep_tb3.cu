@@ -91,17 +91,14 @@ struct Cfg3 {
     static_assert(U0_BYTES % 16 == 0 && RHS_BYTES % 16 == 0 && (BX0 * 8) % 16 == 0 && (BXR * 8) % 16 == 0, "TMA box rows are multiples of 16 bytes");
 };
 
-// Barrier waits of this kernel.  RNMF_TB3_WAIT (A/B builds): 0 = mbarrier.try_wait with the suspend-time hint of tma_util.cuh (the other
-// kernels' choice: their consumers mostly wait for DRAM), 1 = try_wait without a hint, 2 = test_wait polling, 3 = test_wait with a short
-// nanosleep.  Sixteen warps meet at two barriers per plane here: what a late wake-up costs is paid every iteration.
-#ifndef RNMF_TB3_WAIT
-#define RNMF_TB3_WAIT 1
-#endif
+// Barrier waits of this kernel: mbarrier.try_wait WITHOUT the suspend-time hint of tma_util.cuh's mbar_wait (the other kernels' consumers
+// mostly wait for DRAM; here sixteen warps meet at two barriers per plane and a late wake-up is paid every iteration: 497 against 488
+// GLUP/s with the hint, 477 with test_wait polling, 395 with polling + nanosleep; profiles/r2_notes.md, section 9).
 __device__ __forceinline__ void mbar_wait3(uint32_t bar, uint32_t parity)
 {
-#if defined(RNMF_EMULATE) || RNMF_TB3_WAIT == 0
+#ifdef RNMF_EMULATE
     mbar_wait(bar, parity);
-#elif RNMF_TB3_WAIT == 1
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT3_%=:\n\t"
@@ -111,18 +108,6 @@ __device__ __forceinline__ void mbar_wait3(uint32_t bar, uint32_t parity)
         "DONE3_%=:\n\t}"
         ::"r"(bar), "r"(parity)
         : "memory");
-#else
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-#if RNMF_TB3_WAIT == 3
-        if (!done) __nanosleep(32);
-#endif
-    } while (!done);
 #endif
 }
 
@@ -251,24 +236,7 @@ __device__ __forceinline__ void plane_store3(const QuadK3& k, const int pitch, d
 // Ring hazards: level 2 loads from the u1 slot that level 1 of the NEXT iteration overwrites -- every warp starts that iteration
 // behind the wait for this iteration's u2 arrivals, which follow the loads; level 3 loads from the u2 slot written one iteration
 // ago AFTER this warp's u2 arrival, so that slot must survive the next iteration's level 2: three u2 slots.
-// A/B knobs (scripts/build_alt.sh): RNMF_TB3_UNROLL = plane iterations per trip of the steady loop (1, 2, 3); RNMF_TB3_ORDER = 0: level 3's
-// x/y part is formed at the top of the iteration (its loads overlap level 1), 1: levels strictly in the order 1, 2, 3;
-// RNMF_TB3_U1LATE = 1: the wait for the u1 plane follows level 1
-#ifndef RNMF_TB3_UNROLL
-#define RNMF_TB3_UNROLL 1
-#endif
-#ifndef RNMF_TB3_ORDER
-#define RNMF_TB3_ORDER 1
-#endif
-#ifndef RNMF_TB3_PREFETCH
-#define RNMF_TB3_PREFETCH 0        // planes ahead of the TMA load that are prefetched into the L2 (0: none)
-#endif
-#ifndef RNMF_TB3_U1LATE
-#define RNMF_TB3_U1LATE 1
-#endif
-// PAR: it & 1 when known at compile time (the steady loop is unrolled by two: the u1 slots become constants and the register windows
-// -- two live planes per level -- rotate by renaming), -1 otherwise.
-template <bool L1, bool L2, bool L3, int EDGE, int PAR = -1>
+template <bool L1, bool L2, bool L3, int EDGE>
 __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, const int it)
 {
     using C = Cfg3;
@@ -279,7 +247,7 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     double2 u1n_a = zero2, u1n_b = zero2, u2n_a = zero2, u2n_b = zero2;
     const RingAt rg = ring_at(it);
     const uint32_t sc = rg.sc, sn = rg.sn;
-    const uint32_t slot = PAR >= 0 ? (uint32_t)PAR : rg.u1w, pslot = slot ^ 1u, pu = rg.u1rp;      // u1 ring
+    const uint32_t slot = rg.u1w, pslot = slot ^ 1u, pu = rg.u1rp;      // u1 ring
     const uint32_t w2 = rg.u2w, r2 = rg.u2r;                                                       // u2 ring
 
     // ---- wait phase ----------------------------------------------------------------------------------
@@ -289,20 +257,6 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     // nobody reads the u1 slot level 1 overwrites below any more.  (The wait for the u1 plane follows level 1: the halo-row warps
     // arrive for it late in their iteration.)
     if (it >= 1) mbar_wait3(k.bar0 + kU2Full + 8 * r2, rg.u2rp);
-    if (!RNMF_TB3_U1LATE && L2) mbar_wait3(k.bar0 + kU1Full + 8 * pslot, pu);
-
-    double2 P3_a = zero2, P3_b = zero2;
-    if (RNMF_TB3_ORDER == 0 && L3) {
-        const uint32_t b = k.u2a + r2 * C::U2_SLOT;
-        const double2 s_a = ldp(b - RBU);
-        const double w_a = lds1(b + kW), e_a = lds1(b + kE);
-        P3_a.x = part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x);
-        P3_a.y = part3(st.q2_a.y, c1, c2, e_a, st.u2c_a.x, st.u2c_b.y, s_a.y);
-        const double2 n_b = ldp(b + 2 * RBU);
-        const double w_b = lds1(b + RBU + kW), e_b = lds1(b + RBU + kE);
-        P3_b.x = part3(st.q2_b.x, c1, c2, st.u2c_b.y, w_b, n_b.x, st.u2c_a.x);
-        P3_b.y = part3(st.q2_b.y, c1, c2, e_b, st.u2c_b.x, n_b.y, st.u2c_a.y);
-    }
 
     // ---- level 1: u1 of plane a1+it (row A, then row B) --------------------------------------------------
     if (L1) {
@@ -331,7 +285,7 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
     }
     // ---- level 2: u2 of plane a1+it-1; x/y neighbours from the u1 ring, z neighbours from registers --------------
     if (L2) {
-        if (RNMF_TB3_U1LATE) mbar_wait3(k.bar0 + kU1Full + 8 * pslot, pu);        // u1 plane a1+it-1 complete (it >= 1 wherever level 2 is active)
+        mbar_wait3(k.bar0 + kU1Full + 8 * pslot, pu);                     // u1 plane a1+it-1 complete (it >= 1 wherever level 2 is active)
         const uint32_t b = k.u1a + pslot * C::U1_SLOT;
         double2 dn_a = st.u1lo_a, dn_b = st.u1lo_b, up_a = u1n_a, up_b = u1n_b;
         if (EDGE == 2 && it == cp.it_zlo2) { dn_a = ghost1(k.fz0, st.u1c_a); dn_b = ghost1(k.fz0, st.u1c_b); }
@@ -362,10 +316,7 @@ __device__ __forceinline__ void quad_iter3(const Tb3Params& p, const ChunkPlan& 
         if (zlo) { dn_a = ghost1(k.fz0, st.u2c_a); dn_b = ghost1(k.fz0, st.u2c_b); }
         if (!L2) { up_a = ghost1(k.fz1, st.u2c_a); up_b = ghost1(k.fz1, st.u2c_b); }
         double2 na, nb;
-        if (RNMF_TB3_ORDER == 0) {
-            na = fin3(P3_a, c3, up_a, dn_a);
-            nb = fin3(P3_b, c3, up_b, dn_b);
-        } else {
+        {
             const double2 s_a = ldp(b - RBU);
             const double w_a = lds1(b + kW), e_a = lds1(b + kE);
             na.x = fin3(part3(st.q2_a.x, c1, c2, st.u2c_a.y, w_a, st.u2c_b.x, s_a.x), c3, up_a.x, dn_a.x);
@@ -417,26 +368,11 @@ __device__ __forceinline__ void quad_general3(const Tb3Params& p, const ChunkPla
     else if (l3) quad_iter3<false, false, true, 2>(p, cp, k, st, it);
 }
 
-// plane iterations [it, end) with all three levels, two per trip from an even `it` (small code: the steady loops of all warps of a
-// CTA have to stay inside the 32 KB instruction cache -- longer trips with compile-time ring indices were measured slower)
+// plane iterations [it, end) with all three levels.  NOT unrolled: the 4.8 KB loop with its 86 register moves per iteration beat the
+// forms unrolled by 2 / 3 / 12 (the last with compile-time ring indices, 25 % fewer instructions): profiles/r2_notes.md, section 9
 template <int EDGE>
 __device__ __forceinline__ void quad_run3(const Tb3Params& p, const ChunkPlan& cp, const QuadK3& k, QuadSt3& st, int& it, const int end)
 {
-    if (RNMF_TB3_UNROLL == 2) {
-        if (it < end && (it & 1)) { quad_iter3<true, true, true, EDGE>(p, cp, k, st, it); ++it; }
-#pragma unroll 1
-        for (; it + 2 <= end; it += 2) {
-            quad_iter3<true, true, true, EDGE, 0>(p, cp, k, st, it);
-            quad_iter3<true, true, true, EDGE, 1>(p, cp, k, st, it + 1);
-        }
-    } else if (RNMF_TB3_UNROLL == 3) {
-#pragma unroll 1
-        for (; it + 3 <= end; it += 3) {
-            quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
-            quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 1);
-            quad_iter3<true, true, true, EDGE>(p, cp, k, st, it + 2);
-        }
-    }
 #pragma unroll 1
     for (; it < end; ++it) quad_iter3<true, true, true, EDGE>(p, cp, k, st, it);
 }

@@ -21,7 +21,6 @@ inline void mbar_arrive(uint32_t bar) { emu::mbar_arrive(bar); }
 inline void mbar_wait(uint32_t bar, uint32_t parity) { emu::mbar_wait(bar, parity); }
 inline void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) { emu::tma_load(dst, tm, c0, c1, c2, bar); }
 inline void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) { emu::tma_load(dst, tm, c0, c1, 0, bar); }
-inline void tma_prefetch_3d(const CUtensorMap*, int, int, int) {}
 inline uint64_t policy_evict_first() { return 0; }
 inline void tma_load_3d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar, uint64_t) { emu::tma_load(dst, tm, c0, c1, c2, bar); }
 inline void st2_hint(double* p, const double2& v, uint64_t) { p[0] = v.x; p[1] = v.y; }
@@ -82,11 +81,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
-}
-// the box into the L2 only (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // L2 eviction-priority hints: rhs and psi' are touched once per sweep, psi tiles are re-read by the
 // neighbouring CTAs (xy halo) a few microseconds later; at 6.6 TB/s the 126 MB L2 turns over in
