@@ -797,22 +797,27 @@ __global__ void __launch_bounds__(Cfg3::THREADS, 1) jacobi3d_tb3_kernel(const __
     }
 }
 
-// chunk length: whole waves of one CTA per SM, each CTA paying chunk+5 plane iterations
+// chunk length: a CTA pays (its planes + 5) plane iterations, and a launch of W = CTAs / 148 waves takes about W + 1 CTA times (one
+// CTA per SM; the CTAs of a wave do not finish together, so the last wave costs a whole one however full it is).  Fitted to thin
+// frames, where it matters (1024 x 1024 x 128: 416 GLUP/s with one 128-plane chunk per tile, 455 with 48-plane chunks; the
+// ceil(W) model of the two-sweep kernel chose the former): profiles/r2_notes.md, section 9
 void plan_tb3(const SweepArgs& a, dim3& grid, int& chunk, int& n_chunks)
 {
     const FrameGeom& g = a.g;
     const long long tiles = ((g.n[0] + 127) / 128) * ((g.n[1] + Cfg3::TY - 1) / Cfg3::TY);
     const long long span = a.k_end - a.k_begin;
-    long long best_c = 1, best_cost = -1;
+    long long best_c = 1;
+    double best_cost = -1.0;
     static const int cand[] = { 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 96, 128 };
     for (int c : cand) {
         const long long cc = c > span ? span : c;
         if (cc < 1) break;
         const long long chunks = (span + cc - 1) / cc;
         if (chunks <= 60000) {
-            const long long waves = (tiles * chunks + 147) / 148;
-            const long long cost = waves * (cc + 5);
-            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_c = cc; }
+            const double waves = (double)(tiles * chunks) / 148.0;
+            const double cost = (waves + 1.0) * ((double)span / (double)chunks + 5.0);
+            // that many chunks of (almost) equal length
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = (span + chunks - 1) / chunks; }
         }
         if (c >= span) break;
     }
