@@ -33,7 +33,7 @@ extern "C" int32_t rnmf_abi_version(void) { return RNMF_ABI_VERSION; }
 extern "C" const char* rnmf_build_info(void)
 {
     return "librnmf_b200 abi=1 arch=sm_100a fmad=false kernels="
-           "jacobi3d_tma{128x8x4},jacobi3d_tb2{128x12 quad},jacobi2d_tma{512x8},jacobi2d_tb2{512},jacobi2d_tbk{4x512 di},"
+           "jacobi3d_tma{128x8x4},jacobi3d_tb3{128x12 quad, 3 sweeps},jacobi3d_tb2{128x12 quad},jacobi2d_tma{512x8},jacobi2d_tb2{512},jacobi2d_tbk{4x512 di},"
            "jacobi_resident,fill_bc_faces,fill_prescribed,gs_wavefront_2d,varcoef_2d,abs_sum_valid,ew{scale,add,mul,axpby}";
 }
 
