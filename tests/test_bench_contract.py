@@ -79,6 +79,12 @@ def test_roofline_accounting_single_and_double_sweep():
     r4 = b.build_roofline({"ms": 100.0, "doubles": 0, "multi_launches": 360, "multi_sweeps": 1440, "local_cells": c2}, 3, 480, "2d5_8192", 6549.8, "x")
     assert r4["sweeps_per_launch"] == 4 and r4["algorithmic_bytes_per_launch"] == 4 * 24 * c2 and "multi sweep (4 sweeps" in r4["kernel"]
     assert abs(r4["avg_launch_ms"] - 4 * 100.0 / 1440) < 1e-12 and r4["traffic"] and "r2_ncu_2d5_8192_tbk" in r4["traffic_source"]
+    # the three-sweep 3D kernel (the 3D default): 549 of the 550 sweeps of a step in 183 launches of three; DRAM bytes from its capture
+    r3 = b.build_roofline({"ms": 508.0 * 5, "doubles": 0, "multi_launches": 915, "multi_sweeps": 2745, "local_cells": cells, "kernel_ms": 2.78,
+                           "kernel_launches_timed": 60}, 5, 550, "3d7_768", 6549.8, "MEASURED_PEAKS.json hbm_gbs")
+    assert r3["sweeps_per_launch"] == 3 and r3["algorithmic_bytes_per_launch"] == 3 * 24 * cells and "multi sweep (3 sweeps" in r3["kernel"]
+    assert r3["traffic"] and "r2_ncu_3d7_768_tb3" in r3["traffic_source"] and 0.5 < r3["dram_frac"] < 1.0 < r3["frac"]
+    assert abs(r3["frac_of_k_pass_ceiling"] - r3["frac"] / 3) < 1e-12
     # both describe the same GLUP/s <-> GB/s relation: achieved / 24 B = updates per second
     assert abs(r["achieved"] / 24 - cells * 550 / (663.694677734375e-3) / 1e9) < 1e-6 * r["achieved"]
 
