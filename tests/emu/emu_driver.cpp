@@ -294,6 +294,24 @@ int emu_double_sweeps(int dim, const long long* n, const double* dx, const int* 
     return g_deadlocks.load() + (bad ? 1000 : 0);
 }
 
+// the chunk planner of the three-sweep kernel (kernels_sweep_tb3.cu: plan_tb3) for a frame of n0 x n1 x n2 cells whose launch covers
+// all planes: out[0] = planes per chunk, out[1] = chunks, out[2] = CTAs
+void emu_plan_triple(long long n0, long long n1, long long n2, int nb_lo, int nb_hi, int chunk_override, int* out)
+{
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    const int64_t n64[3] = { n0, n1, n2 };
+    const double lo[3] = { 0, 0, 0 }, dx[3] = { 1, 1, 1 };
+    make_geom(a.g, 3, n64, lo, dx, 1, 1);
+    a.k_begin = 0; a.k_end = n2;
+    a.nb_lo = nb_lo; a.nb_hi = nb_hi;
+    a.chunk_override = chunk_override;
+    dim3 grid;
+    int chunk, n_chunks;
+    plan_tb3(a, grid, chunk, n_chunks);
+    out[0] = chunk; out[1] = n_chunks; out[2] = (int)(grid.x * grid.y * grid.z);
+}
+
 // the band schedules themselves (common.cuh), for the abstract dependency check in tests/test_skew_schedule.py
 void emu_skew_region(long long n2, int n_chunks, int c, long long s, long long* lo, long long* hi) { skew_region(n2, n_chunks, c, s, lo, hi); }
 void emu_skew_tail_region(long long n2, int n_chunks, int c, long long s, long long levels, long long* lo, long long* hi)

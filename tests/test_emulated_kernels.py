@@ -309,3 +309,33 @@ def test_time_skewed_end_schedule_on_the_emulator(emu, n, spec, n_chunks, levels
     rc = emu.emu_skewed_tail_double_sweeps(nn, dx, kinds, vals, _p(coef), _p(psi), _p(rhs), _p(out), variant, chunk, n_chunks, levels)
     assert rc == 0, "deadlock or launch failure"
     np.testing.assert_array_equal(out, want)
+
+
+@settings(max_examples=200, deadline=None, derandomize=True)
+@given(st.integers(1, 1100), st.integers(1, 1100), st.integers(1, 1100), st.booleans(), st.booleans(), st.integers(0, 200))
+def test_triple_sweep_chunk_planner_properties(emu, h0, h1, n2, nb_lo, nb_hi, override):
+    """plan_tb3 (kernels_sweep_tb3.cu): the chunks cover the plane range, hold at most 128 planes unless overridden, and next to a slab
+    neighbour the first and the last chunk hold the three planes that travel (the launcher refuses slabs of fewer than six planes)."""
+    if (nb_lo or nb_hi) and n2 < 6:
+        n2 += 6
+    out = (C.c_int * 3)()
+    emu.emu_plan_triple(C.c_longlong(2 * h0), C.c_longlong(2 * h1), C.c_longlong(n2), int(nb_lo), int(nb_hi), override, out)
+    chunk, n_chunks, ctas = out[0], out[1], out[2]
+    assert chunk >= 1 and n_chunks >= 1 and (n_chunks - 1) * chunk < n2 <= n_chunks * chunk
+    assert ctas == n_chunks * ((2 * h0 + 127) // 128) * ((2 * h1 + 11) // 12)
+    if override == 0:
+        assert chunk <= 128 or (nb_hi and chunk <= 131)
+    last = n2 - (n_chunks - 1) * chunk
+    if nb_lo:
+        assert chunk >= 3
+    if nb_hi:
+        assert last >= 3
+
+
+def test_triple_sweep_chunk_planner_choices(emu):
+    """The shapes the planner was fitted to (profiles/r2_notes.md, section 9): equal chunks, (waves + 1) x (planes per chunk + 5)."""
+    out = (C.c_int * 3)()
+    want = {(768, 768, 768): (96, 8), (512, 512, 512): (47, 11), (1024, 1024, 128): (64, 2), (1024, 1024, 1024): (128, 8)}
+    for (n0, n1, n2), (chunk, n_chunks) in want.items():
+        emu.emu_plan_triple(C.c_longlong(n0), C.c_longlong(n1), C.c_longlong(n2), 0, 0, 0, out)
+        assert (out[0], out[1]) == (chunk, n_chunks), ((n0, n1, n2), out[0], out[1])
